@@ -1,0 +1,7 @@
+"""CPU oracle (TEST INFRASTRUCTURE -- see bevy_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs may import this package.  The product
+(``bevy_b200``) never does.
+"""
+from .oracle import *  # noqa: F401,F403
