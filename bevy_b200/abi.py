@@ -1,0 +1,315 @@
+"""ctypes binding of include/b200vis.h (one Python method per C entry point)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+NO_PARENT = 0xFFFFFFFF
+DETACHED = 0xFFFFFFFE
+F_INHERITED_VISIBLE, F_HAS_AABB, F_HAS_SPHERE, F_NO_FRUSTUM_CULLING = 0x01, 0x02, 0x04, 0x08
+F_HAS_VIS_RANGE, F_NO_CPU_CULLING, F_SPHERE_FROM_GT = 0x10, 0x20, 0x40
+VIEW_ACTIVE, VIEW_NO_CPU_CULLING = 0x01, 0x02
+STAGE_PROPAGATE, STAGE_CULL, STAGE_CLUSTER_ASSIGN, STAGE_CLUSTER_LISTS = 0x1, 0x2, 0x4, 0x8
+STAGE_CLUSTER = STAGE_CLUSTER_ASSIGN | STAGE_CLUSTER_LISTS
+STAGE_ALL = 0xF
+MAX_VIEWS = 8
+MAX_CLUSTERS = 4096
+
+ERR_NAMES = {1: "INVALID_ARG", 2: "CUDA", 3: "OUT_OF_MEMORY", 4: "HIERARCHY_CYCLE", 5: "PARENT_OUT_OF_RANGE",
+             6: "CAPACITY", 7: "NOT_READY", 8: "UNSUPPORTED"}
+
+
+class B200VisError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"b200vis error {code} ({ERR_NAMES.get(code, '?')}): {message}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_entities", C.c_uint32), ("max_lights", C.c_uint32),
+                ("max_views", C.c_uint32), ("max_cluster_indices", C.c_uint32), ("world_size", C.c_uint32),
+                ("rank", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class View(C.Structure):
+    _fields_ = [("half_spaces", (C.c_float * 4) * 6), ("layer_mask", C.c_uint64), ("flags", C.c_uint8),
+                ("range_view_index", C.c_int8), ("pad", C.c_uint8 * 6)]
+
+    @staticmethod
+    def make(half_spaces, layer_mask=1, flags=VIEW_ACTIVE, range_view_index=-1):
+        v = View()
+        hs = np.ascontiguousarray(half_spaces, np.float32).reshape(6, 4)
+        for i in range(6):
+            for j in range(4):
+                v.half_spaces[i][j] = hs[i, j]
+        v.layer_mask = layer_mask; v.flags = flags; v.range_view_index = range_view_index
+        return v
+
+
+class ClusterView(C.Structure):
+    _fields_ = [("enabled", C.c_uint32), ("dims", C.c_uint32 * 3), ("tile_size", C.c_uint32 * 2),
+                ("is_orthographic", C.c_uint32), ("near_z", C.c_float), ("far_z", C.c_float),
+                ("cluster_factors", C.c_float * 2), ("view_from_world", C.c_float * 16),
+                ("clip_from_view", C.c_float * 16), ("view_from_world_scale", C.c_float * 3),
+                ("view_from_world_scale_max", C.c_float), ("frustum", (C.c_float * 4) * 6),
+                ("layer_mask", C.c_uint64), ("x_planes", C.POINTER(C.c_float)), ("y_planes", C.POINTER(C.c_float)),
+                ("z_planes", C.POINTER(C.c_float))]
+
+
+class ClusterConfig(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("dims", C.c_uint32 * 3), ("total", C.c_uint32), ("z_slices", C.c_uint32),
+                ("first_slice_depth", C.c_float), ("far_z_mode", C.c_uint32), ("far_z_constant", C.c_float),
+                ("dynamic_resizing", C.c_uint32), ("screen_w", C.c_uint32), ("screen_h", C.c_uint32),
+                ("view_cluster_bindings_max_indices", C.c_uint32)]
+
+
+class ClusterFeedback(C.Structure):
+    _fields_ = [("has_farthest_z", C.c_uint32), ("farthest_z", C.c_float), ("has_index_count", C.c_uint32),
+                ("index_count", C.c_uint32)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("visible_count", C.c_uint32 * MAX_VIEWS), ("cluster_index_count", C.c_uint32 * MAX_VIEWS),
+                ("cluster_farthest_z", C.c_float * MAX_VIEWS), ("cluster_index_overflow", C.c_uint32 * MAX_VIEWS),
+                ("gt_changed_count", C.c_uint32), ("vv_changed_count", C.c_uint32), ("frame", C.c_uint32),
+                ("pad", C.c_uint32)]
+
+
+_lib = None
+_P = C.POINTER
+_vp = C.c_void_p
+
+_SIGNATURES = {
+    "b200vis_abi_version": (C.c_int32, []),
+    "b200vis_create": (C.c_int32, [_P(Config), _P(_vp)]),
+    "b200vis_destroy": (None, [_vp]),
+    "b200vis_last_error": (C.c_char_p, [_vp]),
+    "b200vis_set_stream": (C.c_int32, [_vp, _vp]),
+    "b200vis_synchronize": (C.c_int32, [_vp]),
+    "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
+    "b200vis_plan_row_order": (C.c_int32, [C.c_uint32, _vp, _vp]),
+    "b200vis_upload_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "b200vis_upload_transforms_scattered": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
+    "b200vis_mark_transforms_changed": (C.c_int32, [_vp, C.c_uint32, C.c_uint32]),
+    "b200vis_upload_global_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "b200vis_upload_bounds": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "b200vis_upload_view_visibility": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "b200vis_set_static_transform_optimizations": (C.c_int32, [_vp, C.c_int32]),
+    "b200vis_set_views": (C.c_int32, [_vp, C.c_uint32, _P(View)]),
+    "b200vis_set_lights": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "b200vis_set_cluster_view": (C.c_int32, [_vp, C.c_uint32, _P(ClusterView)]),
+    "b200vis_run": (C.c_int32, [_vp, C.c_uint32]),
+    "b200vis_download_frame_stats": (C.c_int32, [_vp, _P(FrameStats)]),
+    "b200vis_download_global_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, _vp]),
+    "b200vis_download_view_visibility": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "b200vis_download_visible": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32)]),
+    "b200vis_download_clusters": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _P(C.c_uint32)]),
+    "b200vis_cluster_exchange_bytes": (C.c_int32, [_vp, _P(C.c_size_t)]),
+    "b200vis_set_cluster_exchange_buffers": (C.c_int32, [_vp, _vp, _vp]),
+    "b200vis_host_perspective": (None, [C.c_float, C.c_float, C.c_float, _vp]),
+    "b200vis_host_compute_frustum": (None, [_vp, _vp, C.c_float, _vp]),
+    "b200vis_host_default_cluster_config": (None, [_P(ClusterConfig), C.c_uint32, C.c_uint32]),
+    "b200vis_host_cluster_view_setup": (C.c_int32, [_P(ClusterConfig), _vp, _vp, _vp, C.c_uint64,
+                                                    _P(ClusterFeedback), _vp, _P(ClusterView)]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def library_path():
+    return os.path.join(_HERE, "libb200vis.so")
+
+
+def load_library():
+    """Loads the in-tree libb200vis.so.  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} is missing: run `python -m bevy_b200.build` (there is no CPU fallback)")
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def abi_version():
+    return load_library().b200vis_abi_version()
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _arr(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+def host_perspective(fov_y, aspect, near):
+    out = np.zeros(16, np.float32)
+    load_library().b200vis_host_perspective(fov_y, aspect, near, _ptr(out))
+    return out
+
+
+def host_compute_frustum(clip_from_view, camera_gt12, far):
+    cfv = _arr(clip_from_view, np.float32); g = _arr(camera_gt12, np.float32); out = np.zeros((6, 4), np.float32)
+    load_library().b200vis_host_compute_frustum(_ptr(cfv), _ptr(g), far, _ptr(out))
+    return out
+
+
+def host_default_cluster_config(w=1920, h=1080):
+    cfg = ClusterConfig()
+    load_library().b200vis_host_default_cluster_config(C.byref(cfg), w, h)
+    return cfg
+
+
+def host_cluster_view_setup(cfg, camera_gt12, clip_from_view, frustum, layer_mask=1, feedback=None):
+    """Returns (ClusterView, scratch) -- keep `scratch` alive while the view is in use."""
+    g = _arr(camera_gt12, np.float32); cfv = _arr(clip_from_view, np.float32); fr = _arr(frustum, np.float32)
+    scratch = np.zeros(3 * 4097 * 4, np.float32)
+    out = ClusterView()
+    rc = load_library().b200vis_host_cluster_view_setup(C.byref(cfg), _ptr(g), _ptr(cfv), _ptr(fr), layer_mask,
+                                                        None if feedback is None else C.byref(feedback),
+                                                        _ptr(scratch), C.byref(out))
+    if rc:
+        raise B200VisError(rc, "b200vis_host_cluster_view_setup")
+    return out, scratch
+
+
+def plan_row_order(parent):
+    parent = _arr(parent, np.uint32); out = np.zeros(len(parent), np.uint32)
+    rc = load_library().b200vis_plan_row_order(len(parent), _ptr(parent), _ptr(out))
+    if rc:
+        raise B200VisError(rc, "b200vis_plan_row_order")
+    return out
+
+
+class Context:
+    """One b200vis_ctx.  Method names follow the C ABI one to one."""
+
+    def __init__(self, max_entities, max_lights=0, max_views=1, device=0, max_cluster_indices=0, world_size=1, rank=0):
+        self._lib = load_library()
+        self._h = _vp()
+        cfg = Config(device, max_entities, max_lights, max_views, max_cluster_indices, world_size, rank, 0)
+        rc = self._lib.b200vis_create(C.byref(cfg), C.byref(self._h))
+        if rc:
+            raise B200VisError(rc, self._lib.b200vis_last_error(None).decode())
+        self.max_entities, self.max_lights, self.max_views = max_entities, max_lights, max_views
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self._lib.b200vis_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise B200VisError(rc, self._lib.b200vis_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.b200vis_set_stream(self._h, _vp(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self._lib.b200vis_synchronize(self._h))
+
+    def set_topology(self, parent_row, entity_bits):
+        p = _arr(parent_row, np.uint32); e = _arr(entity_bits, np.uint64)
+        assert len(p) == len(e)
+        self._check(self._lib.b200vis_set_topology(self._h, len(p), _ptr(p), _ptr(e)))
+        self.n = len(p)
+
+    def upload_transforms(self, first_row, trs):
+        t = _arr(trs, np.float32).reshape(-1, 10)
+        self._check(self._lib.b200vis_upload_transforms(self._h, first_row, len(t), _ptr(t)))
+
+    def upload_transforms_raw(self, first_row, count, host_ptr):
+        """trs at a raw host address (e.g. pinned memory): no numpy conversion on the hot path."""
+        self._check(self._lib.b200vis_upload_transforms(self._h, first_row, count, _vp(host_ptr)))
+
+    def upload_transforms_scattered(self, rows, trs):
+        r = _arr(rows, np.uint32); t = _arr(trs, np.float32).reshape(-1, 10)
+        assert len(r) == len(t)
+        self._check(self._lib.b200vis_upload_transforms_scattered(self._h, len(r), _ptr(r), _ptr(t)))
+
+    def upload_transforms_scattered_raw(self, count, rows_ptr, trs_ptr):
+        self._check(self._lib.b200vis_upload_transforms_scattered(self._h, count, _vp(rows_ptr), _vp(trs_ptr)))
+
+    def mark_transforms_changed(self, first_row, count):
+        self._check(self._lib.b200vis_mark_transforms_changed(self._h, first_row, count))
+
+    def upload_global_transforms(self, first_row, gt):
+        g = _arr(gt, np.float32).reshape(-1, 12)
+        self._check(self._lib.b200vis_upload_global_transforms(self._h, first_row, len(g), _ptr(g)))
+
+    def upload_bounds(self, first_row, bounds, flags, class_mask, layer_mask=None, range_mask=None):
+        b = _arr(bounds, np.float32).reshape(-1, 6); f = _arr(flags, np.uint8); c = _arr(class_mask, np.uint8)
+        l = _arr(layer_mask, np.uint64); r = _arr(range_mask, np.uint32)
+        self._check(self._lib.b200vis_upload_bounds(self._h, first_row, len(b), _ptr(b), _ptr(f), _ptr(c), _ptr(l), _ptr(r)))
+
+    def upload_view_visibility(self, first_row, vv):
+        v = _arr(vv, np.uint8)
+        self._check(self._lib.b200vis_upload_view_visibility(self._h, first_row, len(v), _ptr(v)))
+
+    def set_static_transform_optimizations(self, enabled):
+        self._check(self._lib.b200vis_set_static_transform_optimizations(self._h, int(bool(enabled))))
+
+    def set_views(self, views):
+        arr = (View * max(len(views), 1))(*views)
+        self._check(self._lib.b200vis_set_views(self._h, len(views), arr))
+        self.n_views = len(views)
+
+    def set_lights(self, light_row, light_range, layer_mask=None):
+        r = _arr(light_row, np.uint32); g = _arr(light_range, np.float32); l = _arr(layer_mask, np.uint64)
+        self._check(self._lib.b200vis_set_lights(self._h, len(r), _ptr(r), _ptr(g), _ptr(l)))
+
+    def set_cluster_view(self, view, cluster_view):
+        self._check(self._lib.b200vis_set_cluster_view(self._h, view, C.byref(cluster_view)))
+
+    def run(self, stages=STAGE_ALL):
+        self._check(self._lib.b200vis_run(self._h, stages))
+
+    def download_frame_stats(self):
+        s = FrameStats()
+        self._check(self._lib.b200vis_download_frame_stats(self._h, C.byref(s)))
+        return s
+
+    def download_global_transforms(self, first_row, count, stride=12, want_changed=True):
+        gt = np.zeros((count, stride), np.float32)
+        ch = np.zeros(count, np.uint8) if want_changed else None
+        self._check(self._lib.b200vis_download_global_transforms(self._h, first_row, count, _ptr(gt), stride, _ptr(ch)))
+        return gt, ch
+
+    def download_view_visibility(self, first_row, count):
+        vv = np.zeros(count, np.uint8); ch = np.zeros(count, np.uint8)
+        self._check(self._lib.b200vis_download_view_visibility(self._h, first_row, count, _ptr(vv), _ptr(ch)))
+        return vv, ch
+
+    def download_visible(self, view):
+        cnt = C.c_uint32(0)
+        self._check(self._lib.b200vis_download_visible(self._h, view, None, 0, C.byref(cnt)))
+        rows = np.zeros(max(cnt.value, 1), np.uint32)
+        self._check(self._lib.b200vis_download_visible(self._h, view, _ptr(rows), len(rows), C.byref(cnt)))
+        return rows[:cnt.value]
+
+    def download_clusters(self, view, capacity=1 << 20):
+        offsets = np.zeros(MAX_CLUSTERS + 1, np.uint32); idx = np.zeros(capacity, np.uint32); tot = C.c_uint32(0)
+        self._check(self._lib.b200vis_download_clusters(self._h, view, _ptr(offsets), _ptr(idx), capacity, C.byref(tot)))
+        return offsets, idx[:tot.value]
+
+    def cluster_exchange_bytes(self):
+        n = C.c_size_t(0)
+        self._check(self._lib.b200vis_cluster_exchange_bytes(self._h, C.byref(n)))
+        return n.value
+
+    def set_cluster_exchange_buffers(self, send_ptr, recv_ptr):
+        self._check(self._lib.b200vis_set_cluster_exchange_buffers(self._h, _vp(send_ptr), _vp(recv_ptr)))

@@ -1,0 +1,676 @@
+// api.cu -- host runtime + C ABI of libb200vis.so (include/b200vis.h).
+//
+// Owns the SoA device mirror of the ECS columns, the execution plan built from the hierarchy
+// (tiles and passes), the per-frame constants, and the stream every stage is issued on.
+// There is NO CPU fallback: without a CUDA device b200vis_create fails with B200VIS_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b200vis.h"
+#include "device_types.cuh"
+#include "host_view.hpp"
+#include "kernels.cuh"
+
+using namespace b200vis;
+
+static thread_local std::string g_create_error;
+
+struct b200vis_ctx {
+    b200vis_config cfg{};
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    uint32_t n = 0;                 // current row count
+    Rows rows{};                    // device SoA (capacity cfg.max_entities)
+    uint32_t *d_parent = nullptr; uint64_t *d_layers = nullptr; uint32_t *d_range = nullptr;
+    uint32_t *d_rank = nullptr, *d_row_of_rank = nullptr; uint8_t *d_dirty = nullptr;
+    bool have_layers = false, have_range = false, rank_identity = true, topology_set = false;
+    bool bounds_set = false;
+
+    // plan
+    Tile *d_tiles = nullptr; uint32_t tiles_cap = 0;
+    std::vector<uint32_t> pass_begin;   // tile index ranges per pass: [pass_begin[p], pass_begin[p+1])
+    int static_opt = 1;
+
+    // per-frame constants
+    FrameConsts *h_consts = nullptr;    // pinned
+    FrameConsts *d_consts = nullptr;
+    bool consts_dirty = true;
+    float4 *d_xplanes = nullptr, *d_yplanes = nullptr, *d_zplanes = nullptr; float *d_zthr = nullptr;
+    float *h_planes = nullptr;          // pinned staging: [3][4097*4] + thresholds [4096] per upload
+    b200vis_cluster_view cview_host[kMaxViews]{};
+
+    // visible set
+    VisibleBufs vis{};
+    DevStats *d_stats = nullptr; DevStats *h_stats = nullptr;   // h pinned
+    uint32_t frame = 0, parity = 0;
+
+    // lights + clusters
+    Lights lights{}; uint32_t *d_light_row = nullptr; float *d_light_range = nullptr; uint64_t *d_light_layers = nullptr;
+    ClusterBufs cl{}; uint32_t *d_slab = nullptr; void *ext_send = nullptr, *ext_recv = nullptr;
+    size_t slab_bytes = 0;
+
+    // staging for AoS <-> SoA conversion
+    uint8_t *d_stage = nullptr; size_t stage_bytes = 0;
+    uint8_t *h_stage = nullptr;         // pinned, same size (downloads)
+};
+
+static int32_t fail(b200vis_ctx *c, int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? B200VIS_ERR_OUT_OF_MEMORY : B200VIS_ERR_CUDA, \
+                        "%s failed: %s", #call, cudaGetErrorString(e_));                                \
+    } while (0)
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T));
+    return e;
+}
+
+extern "C" int32_t b200vis_abi_version(void) { return B200VIS_ABI_VERSION; }
+
+extern "C" const char *b200vis_last_error(const b200vis_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    Rows &r = ctx->rows;
+    void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
+                   ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
+                   ctx->d_tiles, ctx->d_consts, ctx->d_xplanes, ctx->d_yplanes, ctx->d_zplanes, ctx->d_zthr,
+                   ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->d_stats, ctx->d_light_row,
+                   ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage};
+    for (void *p : dev) if (p) cudaFree(p);
+    if (ctx->h_consts) cudaFreeHost(ctx->h_consts);
+    if (ctx->h_planes) cudaFreeHost(ctx->h_planes);
+    if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) {
+    b200vis_ctx *ctx = nullptr;   // for CU(): errors before allocation go to the thread-local slot
+    if (!cfg || !out) return fail(nullptr, B200VIS_ERR_INVALID_ARG, "b200vis_create: null argument");
+    *out = nullptr;
+    if (cfg->max_views == 0 || cfg->max_views > B200VIS_MAX_VIEWS)
+        return fail(nullptr, B200VIS_ERR_INVALID_ARG, "max_views must be in 1..%u", B200VIS_MAX_VIEWS);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, B200VIS_ERR_CUDA, "no CUDA device (%s): libb200vis has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, B200VIS_ERR_INVALID_ARG, "device %d out of range", cfg->device);
+    CU(cudaSetDevice(cfg->device));
+    ctx = new b200vis_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    if (ctx->cfg.world_size == 0) ctx->cfg.world_size = 1;
+    if (ctx->cfg.max_cluster_indices == 0) ctx->cfg.max_cluster_indices = 1u << 20;
+    const size_t N = cfg->max_entities, V = cfg->max_views;
+    int32_t rc = [&]() -> int32_t {
+        CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        Rows &r = ctx->rows;
+        CU(dalloc(&r.trsA, N)); CU(dalloc(&r.trsB, N)); CU(dalloc(&r.trsC, N));
+        CU(dalloc(&r.gt0, N)); CU(dalloc(&r.gt1, N)); CU(dalloc(&r.gt2, N));
+        CU(dalloc(&r.bndA, N)); CU(dalloc(&r.bndB, N));
+        CU(dalloc(&r.flags, N)); CU(dalloc(&r.state, N)); CU(dalloc(&r.topo, N));
+        CU(dalloc(&ctx->d_parent, N)); CU(dalloc(&ctx->d_layers, N)); CU(dalloc(&ctx->d_range, N));
+        CU(dalloc(&ctx->d_rank, N)); CU(dalloc(&ctx->d_row_of_rank, N)); CU(dalloc(&ctx->d_dirty, N));
+        r.parent = ctx->d_parent;
+        ctx->tiles_cap = (uint32_t)(N / 1 + 1);   // worst case one tile per row is never reached; see planner
+        ctx->tiles_cap = (uint32_t)std::min<size_t>(N + 1, (N / 8) + 1024);
+        CU(dalloc(&ctx->d_tiles, ctx->tiles_cap));
+        CU(cudaMallocHost(&ctx->h_consts, sizeof(FrameConsts)));
+        memset(ctx->h_consts, 0, sizeof(FrameConsts));
+        CU(dalloc(&ctx->d_consts, 1));
+        CU(dalloc(&ctx->d_xplanes, V * (kMaxClusters + 1))); CU(dalloc(&ctx->d_yplanes, V * (kMaxClusters + 1)));
+        CU(dalloc(&ctx->d_zplanes, V * (kMaxClusters + 1))); CU(dalloc(&ctx->d_zthr, V * kMaxClusters));
+        CU(cudaMallocHost(&ctx->h_planes, (3 * (kMaxClusters + 1) * 4 + kMaxClusters) * sizeof(float) * V));
+        // visible set buffers
+        VisibleBufs &vb = ctx->vis;
+        vb.words_stride = (uint32_t)((N + 31) / 32 + 2);
+        vb.chunks_stride = (vb.words_stride + kChunkWords - 1) / kChunkWords + 1;
+        vb.list_stride = (uint32_t)std::max<size_t>(N, 1);
+        CU(dalloc(&vb.mask, (size_t)vb.words_stride * V));
+        CU(dalloc(&vb.chunk_count, (size_t)2 * kMaxViews * vb.chunks_stride));
+        CU(dalloc(&vb.lists, (size_t)vb.list_stride * V));
+        CU(dalloc(&ctx->d_stats, 1));
+        CU(cudaMallocHost(&ctx->h_stats, sizeof(DevStats)));
+        // lights + clusters
+        const size_t Lm = std::max<uint32_t>(cfg->max_lights, 1);
+        CU(dalloc(&ctx->d_light_row, Lm)); CU(dalloc(&ctx->d_light_range, Lm)); CU(dalloc(&ctx->d_light_layers, Lm));
+        ClusterBufs &cl = ctx->cl;
+        cl.words = (uint32_t)((Lm + 31) / 32); cl.max_lights = cl.words * 32; cl.world = ctx->cfg.world_size;
+        cl.rank = cfg->rank; cl.max_views = (uint32_t)V; cl.index_cap = ctx->cfg.max_cluster_indices;
+        ctx->slab_bytes = (size_t)V * cl.words * kMaxClusters * sizeof(uint32_t);
+        CU(dalloc(&ctx->d_slab, ctx->slab_bytes / 4));
+        cl.send = ctx->d_slab; cl.recv = ctx->d_slab;
+        cl.xplanes = ctx->d_xplanes; cl.yplanes = ctx->d_yplanes; cl.zplanes = ctx->d_zplanes; cl.zthr = ctx->d_zthr;
+        CU(dalloc(&cl.offsets, V * (kMaxClusters + 1)));
+        CU(dalloc(&cl.indices, V * (size_t)cl.index_cap));
+        ctx->stage_bytes = std::max<size_t>(N, 1) * 64;
+        CU(cudaMalloc(&ctx->d_stage, ctx->stage_bytes));
+        CU(cudaMallocHost(&ctx->h_stage, ctx->stage_bytes));
+        return B200VIS_OK;
+    }();
+    if (rc != B200VIS_OK) { g_create_error = ctx->err; b200vis_destroy(ctx); return rc; }
+    *out = ctx;
+    return B200VIS_OK;
+}
+
+#define CHECK_CTX()                                                        \
+    if (!ctx) return B200VIS_ERR_INVALID_ARG;                              \
+    CU(cudaSetDevice(ctx->device))
+
+static int32_t check_range(b200vis_ctx *ctx, uint32_t first, uint32_t count, const char *what) {
+    if ((uint64_t)first + count > ctx->cfg.max_entities)
+        return fail(ctx, B200VIS_ERR_CAPACITY, "%s: rows [%u, %u) exceed max_entities %u", what, first, first + count,
+                    ctx->cfg.max_entities);
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_set_stream(b200vis_ctx *ctx, void *cuda_stream) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_synchronize(b200vis_ctx *ctx) {
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_set_static_transform_optimizations(b200vis_ctx *ctx, int32_t enabled) {
+    if (!ctx) return B200VIS_ERR_INVALID_ARG;
+    ctx->static_opt = enabled ? 1 : 0;
+    return B200VIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// execution plan
+// ------------------------------------------------------------------------------------------
+// Validates the hierarchy (range, cycles), cuts the rows into tiles of <= kTileRows rows --
+// preferring cuts at tree boundaries so parents sit in the same tile as their children -- and
+// orders the tiles into passes so that a tile's out-of-tile parents are finished by an earlier
+// launch.  Forests of small trees need one pass; a tree larger than a tile needs a few.
+static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, std::vector<uint32_t> &topo,
+                          std::vector<Tile> &tiles_sorted) {
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint32_t p = parent[r];
+        if (p == kNoParent || p == kDetached) continue;
+        if (p >= n) return fail(ctx, B200VIS_ERR_PARENT_OUT_OF_RANGE, "row %u: parent %u out of range (n=%u)", r, p, n);
+    }
+    {   // cycle check: every chain must end at a root / detached row
+        std::vector<uint8_t> color(n, 0);
+        std::vector<uint32_t> path;
+        for (uint32_t r = 0; r < n; ++r) {
+            if (color[r]) continue;
+            path.clear();
+            uint32_t c = r;
+            while (true) {
+                if (color[c] == 2) break;
+                if (color[c] == 1) return fail(ctx, B200VIS_ERR_HIERARCHY_CYCLE, "hierarchy cycle through row %u", c);
+                color[c] = 1; path.push_back(c);
+                const uint32_t p = parent[c];
+                if (p >= n) break;
+                c = p;
+            }
+            for (uint32_t x : path) color[x] = 2;
+        }
+    }
+    for (uint32_t r = 0; r < n; ++r)
+        if (parent[r] < n && parent[r] >= r)
+            return fail(ctx, B200VIS_ERR_UNSUPPORTED,
+                        "row %u has parent %u >= itself: rows must be in topological order (use b200vis_plan_row_order)", r,
+                        parent[r]);
+    std::vector<uint8_t> has_children(n, 0);
+    for (uint32_t r = 0; r < n; ++r) if (parent[r] < n) has_children[parent[r]] = 1;
+    // greedy tiling, cutting at the latest tree boundary inside a full tile
+    std::vector<Tile> tiles;
+    std::vector<uint32_t> tile_of(n);
+    uint32_t start = 0;
+    while (start < n) {
+        uint32_t end = std::min<uint32_t>(n, start + kTileRows);
+        if (end < n && parent[end] < n) {          // the cut would split a tree: back up to a boundary
+            uint32_t c = end;
+            while (c > start + 1 && parent[c] < n) --c;   // c = latest row in (start, end] that starts a tree
+            if (c > start && !(parent[c] < n)) end = c;
+        }
+        Tile t; t.base = start; t.n_rows = (uint16_t)(end - start); t.n_levels = 1;
+        for (uint32_t r = start; r < end; ++r) tile_of[r] = (uint32_t)tiles.size();
+        tiles.push_back(t);
+        start = end;
+    }
+    // topo words, in-tile depth, tile levels
+    topo.assign(n, 0);
+    std::vector<uint32_t> ldepth(n, 0), tile_level(tiles.size(), 0);
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint32_t p = parent[r], ti = tile_of[r];
+        uint32_t w = 0;
+        if (p == kNoParent) w |= T_ROOT;
+        else if (p == kDetached) w |= T_DETACHED;
+        else if (tile_of[p] == ti) {
+            ldepth[r] = ldepth[p] + 1;
+            w |= (p - tiles[ti].base) | (ldepth[r] << 9);
+            tiles[ti].n_levels = std::max<uint16_t>(tiles[ti].n_levels, (uint16_t)(ldepth[r] + 1));
+        } else {
+            w |= T_EXT_PARENT;
+            tile_level[ti] = std::max(tile_level[ti], tile_level[tile_of[p]] + 1);
+        }
+        if (has_children[r]) w |= T_HAS_CHILDREN;
+        topo[r] = w;
+    }
+    // NOTE: tile_level of tile t only depends on tiles with a smaller index (topological rows), and
+    // those are final by the time a row of t is visited, because rows are visited in ascending order.
+    const uint32_t n_pass = tiles.empty() ? 0 : *std::max_element(tile_level.begin(), tile_level.end()) + 1;
+    ctx->pass_begin.assign(n_pass + 1, 0);
+    for (uint32_t lv : tile_level) ctx->pass_begin[lv + 1]++;
+    for (uint32_t p = 0; p < n_pass; ++p) ctx->pass_begin[p + 1] += ctx->pass_begin[p];
+    tiles_sorted.resize(tiles.size());
+    std::vector<uint32_t> cursor(ctx->pass_begin.begin(), ctx->pass_begin.end() - (n_pass ? 1 : 0));
+    for (size_t i = 0; i < tiles.size(); ++i) tiles_sorted[cursor[tile_level[i]]++] = tiles[i];
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, const uint64_t *entity_bits) {
+    CHECK_CTX();
+    if (n && (!parent || !entity_bits)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_topology: null array");
+    if (n > ctx->cfg.max_entities) return fail(ctx, B200VIS_ERR_CAPACITY, "set_topology: %u rows > max_entities %u", n, ctx->cfg.max_entities);
+    std::vector<uint32_t> topo; std::vector<Tile> tiles;
+    int32_t rc = build_plan(ctx, n, parent, topo, tiles);
+    if (rc != B200VIS_OK) return rc;
+    if (tiles.size() > ctx->tiles_cap) {
+        if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+        ctx->d_tiles = nullptr; ctx->tiles_cap = (uint32_t)tiles.size() + 1024;
+        CU(dalloc(&ctx->d_tiles, ctx->tiles_cap));
+    }
+    // Entity::to_bits() order -> rank
+    bool sorted = true;
+    for (uint32_t r = 1; r < n && sorted; ++r) sorted = entity_bits[r - 1] < entity_bits[r];
+    std::vector<uint32_t> order, rank;
+    if (!sorted) {
+        order.resize(n); std::iota(order.begin(), order.end(), 0u);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return entity_bits[a] < entity_bits[b]; });
+        rank.resize(n);
+        for (uint32_t i = 0; i < n; ++i) rank[order[i]] = i;
+    }
+    cudaStream_t st = ctx->stream;
+    CU(cudaStreamSynchronize(st));   // the vectors below are pageable and short-lived: copy synchronously
+    CU(cudaMemcpy(ctx->rows.topo, topo.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_parent, parent, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+    if (!sorted) {
+        CU(cudaMemcpy(ctx->d_rank, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_row_of_rank, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+    ctx->rank_identity = sorted;
+    ctx->n = n;
+    ctx->rows.n = n;
+    ctx->vis.n_words = (n + 31) / 32;
+    ctx->vis.n_chunks = (ctx->vis.n_words + kChunkWords - 1) / kChunkWords;
+    // fresh accumulation state
+    CU(cudaMemset(ctx->vis.mask, 0, (size_t)ctx->vis.words_stride * ctx->cfg.max_views * 4));
+    CU(cudaMemset(ctx->vis.chunk_count, 0, (size_t)2 * kMaxViews * ctx->vis.chunks_stride * 4));
+    CU(cudaMemset(ctx->d_stats, 0, sizeof(DevStats)));
+    CU(cudaMemset(ctx->d_slab, 0, ctx->slab_bytes));
+    ctx->topology_set = true;
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_plan_row_order(uint32_t n, const uint32_t *parent, uint32_t *new_to_old) {
+    if (n && (!parent || !new_to_old)) return B200VIS_ERR_INVALID_ARG;
+    // children lists (ascending old row), then BFS per root in ascending root order
+    std::vector<uint32_t> first(n + 1, 0), kids(n);
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint32_t p = parent[r];
+        if (p < n) first[p + 1]++;
+        else if (p != kNoParent && p != kDetached) return B200VIS_ERR_PARENT_OUT_OF_RANGE;
+    }
+    for (uint32_t r = 0; r < n; ++r) first[r + 1] += first[r];
+    { std::vector<uint32_t> cur(first.begin(), first.end() - 1);
+      for (uint32_t r = 0; r < n; ++r) if (parent[r] < n) kids[cur[parent[r]]++] = r; }
+    uint32_t out = 0;
+    for (uint32_t r = 0; r < n; ++r) {
+        if (parent[r] < n) continue;               // roots, flat entities and detached subtrees start a block
+        const uint32_t head = out;
+        new_to_old[out++] = r;
+        for (uint32_t i = head; i < out; ++i) {
+            const uint32_t c = new_to_old[i];
+            for (uint32_t k = first[c]; k < first[c + 1]; ++k) new_to_old[out++] = kids[k];
+        }
+    }
+    return out == n ? B200VIS_OK : B200VIS_ERR_HIERARCHY_CYCLE;   // rows on a cycle are never reached
+}
+
+// ------------------------------------------------------------------------------------------
+// uploads
+// ------------------------------------------------------------------------------------------
+static int32_t stage_in(b200vis_ctx *ctx, const void *src, size_t bytes, size_t offset) {
+    if (offset + bytes > ctx->stage_bytes) return fail(ctx, B200VIS_ERR_CAPACITY, "staging buffer too small");
+    CU(cudaMemcpyAsync(ctx->d_stage + offset, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_upload_transforms(b200vis_ctx *ctx, uint32_t first, uint32_t count, const float *trs) {
+    CHECK_CTX();
+    if (count && !trs) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_transforms: null");
+    int32_t rc = check_range(ctx, first, count, "upload_transforms"); if (rc) return rc;
+    rc = stage_in(ctx, trs, (size_t)count * 40, 0); if (rc) return rc;
+    launch_unpack_trs(ctx->stream, ctx->rows, first, count, reinterpret_cast<const float *>(ctx->d_stage), 0);
+    CU(cudaGetLastError());
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_upload_transforms_scattered(b200vis_ctx *ctx, uint32_t count, const uint32_t *rows, const float *trs) {
+    CHECK_CTX();
+    if (count && (!rows || !trs)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_transforms_scattered: null");
+    if (count > ctx->cfg.max_entities) return fail(ctx, B200VIS_ERR_CAPACITY, "upload_transforms_scattered: count > max_entities");
+    const size_t off_rows = ((size_t)count * 40 + 15) & ~(size_t)15;
+    int32_t rc = stage_in(ctx, trs, (size_t)count * 40, 0); if (rc) return rc;
+    rc = stage_in(ctx, rows, (size_t)count * 4, off_rows); if (rc) return rc;
+    launch_scatter_trs(ctx->stream, ctx->rows, count, reinterpret_cast<const uint32_t *>(ctx->d_stage + off_rows),
+                       reinterpret_cast<const float *>(ctx->d_stage));
+    CU(cudaGetLastError());
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_mark_transforms_changed(b200vis_ctx *ctx, uint32_t first, uint32_t count) {
+    CHECK_CTX();
+    int32_t rc = check_range(ctx, first, count, "mark_transforms_changed"); if (rc) return rc;
+    launch_unpack_trs(ctx->stream, ctx->rows, first, count, nullptr, 1);
+    CU(cudaGetLastError());
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_upload_global_transforms(b200vis_ctx *ctx, uint32_t first, uint32_t count, const float *gt) {
+    CHECK_CTX();
+    if (count && !gt) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_global_transforms: null");
+    int32_t rc = check_range(ctx, first, count, "upload_global_transforms"); if (rc) return rc;
+    rc = stage_in(ctx, gt, (size_t)count * 48, 0); if (rc) return rc;
+    launch_unpack_gt(ctx->stream, ctx->rows, first, count, reinterpret_cast<const float *>(ctx->d_stage));
+    CU(cudaGetLastError());
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_upload_bounds(b200vis_ctx *ctx, uint32_t first, uint32_t count, const float *bounds,
+                                         const uint8_t *flags, const uint8_t *class_mask, const uint64_t *layer_mask,
+                                         const uint32_t *range_mask) {
+    CHECK_CTX();
+    if (count && (!bounds || !flags || !class_mask)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_bounds: null");
+    int32_t rc = check_range(ctx, first, count, "upload_bounds"); if (rc) return rc;
+    const size_t ob = 0, of = (size_t)count * 24, oc = of + (((size_t)count + 15) & ~(size_t)15);
+    rc = stage_in(ctx, bounds, (size_t)count * 24, ob); if (rc) return rc;
+    rc = stage_in(ctx, flags, count, of); if (rc) return rc;
+    rc = stage_in(ctx, class_mask, count, oc); if (rc) return rc;
+    launch_unpack_bounds(ctx->stream, ctx->rows, first, count, reinterpret_cast<const float *>(ctx->d_stage + ob),
+                         ctx->d_stage + of, ctx->d_stage + oc);
+    CU(cudaGetLastError());
+    if (layer_mask) {
+        CU(cudaMemcpyAsync(ctx->d_layers + first, layer_mask, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->have_layers) {
+            // rows never uploaded keep the default layer (RenderLayers::default() = layer 0)
+            std::vector<uint64_t> ones(ctx->cfg.max_entities, 1ull);
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (first) CU(cudaMemcpy(ctx->d_layers, ones.data(), (size_t)first * 8, cudaMemcpyHostToDevice));
+            const size_t tail = ctx->cfg.max_entities - (first + count);
+            if (tail) CU(cudaMemcpy(ctx->d_layers + first + count, ones.data(), tail * 8, cudaMemcpyHostToDevice));
+            ctx->have_layers = true;
+        }
+    }
+    if (range_mask) {
+        CU(cudaMemcpyAsync(ctx->d_range + first, range_mask, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->have_range = true;
+    }
+    ctx->bounds_set = true;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_upload_view_visibility(b200vis_ctx *ctx, uint32_t first, uint32_t count, const uint8_t *vv) {
+    CHECK_CTX();
+    if (count && !vv) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_view_visibility: null");
+    int32_t rc = check_range(ctx, first, count, "upload_view_visibility"); if (rc) return rc;
+    rc = stage_in(ctx, vv, count, 0); if (rc) return rc;
+    launch_unpack_vv(ctx->stream, ctx->rows, first, count, ctx->d_stage);
+    CU(cudaGetLastError());
+    return B200VIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-frame constants
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t b200vis_set_views(b200vis_ctx *ctx, uint32_t n_views, const b200vis_view *views) {
+    if (!ctx) return B200VIS_ERR_INVALID_ARG;
+    if (n_views > ctx->cfg.max_views) return fail(ctx, B200VIS_ERR_CAPACITY, "set_views: %u > max_views %u", n_views, ctx->cfg.max_views);
+    if (n_views && !views) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_views: null");
+    FrameConsts &fc = *ctx->h_consts;
+    // h_consts is pinned and read by an async copy: make sure the previous copy has been consumed
+    cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+    fc.n_views = n_views;
+    for (uint32_t v = 0; v < n_views; ++v) {
+        DevView &d = fc.views[v];
+        memcpy(d.hs, views[v].half_spaces, sizeof d.hs);
+        d.layer_mask = views[v].layer_mask; d.flags = views[v].flags; d.range_index = views[v].range_view_index;
+    }
+    ctx->consts_dirty = true;
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, const uint32_t *light_row, const float *range,
+                                      const uint64_t *layer_mask) {
+    CHECK_CTX();
+    if (n_lights > ctx->cfg.max_lights) return fail(ctx, B200VIS_ERR_CAPACITY, "set_lights: %u > max_lights %u", n_lights, ctx->cfg.max_lights);
+    if (n_lights && (!light_row || !range)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_lights: null");
+    for (uint32_t i = 0; i < n_lights; ++i)
+        if (light_row[i] >= ctx->cfg.max_entities) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_lights: light %u row %u out of range", i, light_row[i]);
+    CU(cudaMemcpyAsync(ctx->d_light_row, light_row, (size_t)n_lights * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_light_range, range, (size_t)n_lights * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (layer_mask) CU(cudaMemcpyAsync(ctx->d_light_layers, layer_mask, (size_t)n_lights * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->lights.n = n_lights; ctx->lights.row = ctx->d_light_row; ctx->lights.range = ctx->d_light_range;
+    ctx->lights.layers = layer_mask ? ctx->d_light_layers : nullptr;
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_set_cluster_view(b200vis_ctx *ctx, uint32_t view, const b200vis_cluster_view *p) {
+    CHECK_CTX();
+    if (view >= ctx->cfg.max_views || !p) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_cluster_view: bad view %u", view);
+    CU(cudaStreamSynchronize(ctx->stream));   // pinned staging reuse
+    FrameConsts &fc = *ctx->h_consts;
+    DevClusterView &d = fc.cviews[view];
+    memset(&d, 0, sizeof d);
+    ctx->cview_host[view] = *p;
+    d.enabled = p->enabled;
+    if (p->enabled) {
+        const uint64_t nc = (uint64_t)p->dims[0] * p->dims[1] * p->dims[2];
+        if (nc == 0 || nc > kMaxClusters) return fail(ctx, B200VIS_ERR_CAPACITY, "set_cluster_view: %llu clusters (max %d)", (unsigned long long)nc, kMaxClusters);
+        if (!p->x_planes || !p->y_planes || !p->z_planes) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_cluster_view: null plane table");
+        for (int i = 0; i < 3; ++i) d.dims[i] = p->dims[i];
+        d.is_ortho = p->is_orthographic; d.n_clusters = (uint32_t)nc;
+        memcpy(d.vfw, p->view_from_world, sizeof d.vfw); memcpy(d.cfv, p->clip_from_view, sizeof d.cfv);
+        memcpy(d.scale, p->view_from_world_scale, sizeof d.scale); d.scale_max = p->view_from_world_scale_max;
+        memcpy(d.frustum, p->frustum, sizeof d.frustum); d.layer_mask = p->layer_mask;
+        const size_t per_view = 3 * (kMaxClusters + 1) * 4 + kMaxClusters;
+        float *hp = ctx->h_planes + per_view * view;
+        float *hx = hp, *hy = hp + (kMaxClusters + 1) * 4, *hz = hp + 2 * (kMaxClusters + 1) * 4, *ht = hp + 3 * (kMaxClusters + 1) * 4;
+        memcpy(hx, p->x_planes, (size_t)(p->dims[0] + 1) * 16);
+        memcpy(hy, p->y_planes, (size_t)(p->dims[1] + 1) * 16);
+        memcpy(hz, p->z_planes, (size_t)(p->dims[2] + 1) * 16);
+        host::z_slice_thresholds(p->cluster_factors, p->dims[2], p->is_orthographic != 0, ht);
+        cudaStream_t st = ctx->stream;
+        CU(cudaMemcpyAsync(ctx->d_xplanes + (size_t)view * (kMaxClusters + 1), hx, (size_t)(p->dims[0] + 1) * 16, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_yplanes + (size_t)view * (kMaxClusters + 1), hy, (size_t)(p->dims[1] + 1) * 16, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_zplanes + (size_t)view * (kMaxClusters + 1), hz, (size_t)(p->dims[2] + 1) * 16, cudaMemcpyHostToDevice, st));
+        if (p->dims[2] > 1)
+            CU(cudaMemcpyAsync(ctx->d_zthr + (size_t)view * kMaxClusters, ht, (size_t)(p->dims[2] - 1) * 4, cudaMemcpyHostToDevice, st));
+    }
+    ctx->consts_dirty = true;
+    return B200VIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU exchange buffers
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t b200vis_cluster_exchange_bytes(const b200vis_ctx *ctx, size_t *slab_bytes) {
+    if (!ctx || !slab_bytes) return B200VIS_ERR_INVALID_ARG;
+    *slab_bytes = ctx->slab_bytes;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_set_cluster_exchange_buffers(b200vis_ctx *ctx, void *send, void *recv) {
+    CHECK_CTX();
+    if ((send == nullptr) != (recv == nullptr)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "exchange buffers: both or neither");
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (send) {
+        ctx->cl.send = static_cast<uint32_t *>(send); ctx->cl.recv = static_cast<const uint32_t *>(recv);
+        CU(cudaMemsetAsync(send, 0, ctx->slab_bytes, ctx->stream));
+    } else { ctx->cl.send = ctx->d_slab; ctx->cl.recv = ctx->d_slab; }
+    ctx->ext_send = send; ctx->ext_recv = recv;
+    return B200VIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// run
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
+    CHECK_CTX();
+    if (!ctx->topology_set) return fail(ctx, B200VIS_ERR_NOT_READY, "run: b200vis_set_topology has not been called");
+    if ((stages & B200VIS_STAGE_CULL) && !ctx->bounds_set) return fail(ctx, B200VIS_ERR_NOT_READY, "run: bounds/flags were never uploaded");
+    cudaStream_t st = ctx->stream;
+    if (ctx->consts_dirty) {
+        CU(cudaMemcpyAsync(ctx->d_consts, ctx->h_consts, sizeof(FrameConsts), cudaMemcpyHostToDevice, st));
+        ctx->consts_dirty = false;
+    }
+    Rows R = ctx->rows;
+    R.layers = ctx->have_layers ? ctx->d_layers : nullptr;
+    R.range = ctx->have_range ? ctx->d_range : nullptr;
+    R.rank = ctx->rank_identity ? nullptr : ctx->d_rank;
+    R.row_of_rank = ctx->rank_identity ? nullptr : ctx->d_row_of_rank;
+    const uint32_t n_pass = ctx->pass_begin.empty() ? 0 : (uint32_t)ctx->pass_begin.size() - 1;
+    const bool do_prop = stages & B200VIS_STAGE_PROPAGATE, do_cull = stages & B200VIS_STAGE_CULL;
+    R.dirty = nullptr;
+    if (do_prop && ctx->static_opt && n_pass > 1) {
+        CU(cudaMemsetAsync(ctx->d_dirty, 0, ctx->n, st));
+        R.dirty = ctx->d_dirty;
+        launch_mark_dirty_global(st, R);
+    }
+    const uint32_t parity = ctx->parity;
+    if (do_prop || do_cull) {
+        const uint32_t tile_stages = (do_prop ? 1u : 0u) | (do_cull ? 2u : 0u);
+        if (do_prop) {
+            for (uint32_t p = 0; p < n_pass; ++p)
+                launch_propagate_cull(st, R, ctx->d_tiles + ctx->pass_begin[p], ctx->pass_begin[p + 1] - ctx->pass_begin[p],
+                                      ctx->d_consts, ctx->vis, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, parity);
+        } else if (n_pass) {
+            launch_propagate_cull(st, R, ctx->d_tiles, ctx->pass_begin[n_pass], ctx->d_consts, ctx->vis, ctx->d_stats,
+                                  tile_stages, 0, parity);
+        }
+    }
+    if (do_cull) launch_expand_visible(st, ctx->vis, R.row_of_rank, ctx->d_consts, ctx->d_stats, parity, ctx->n, ctx->cfg.max_views);
+    if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
+        launch_cluster_assign(st, R, ctx->lights, ctx->d_consts, ctx->cl, ctx->d_stats, ctx->cfg.max_views);
+    if (stages & B200VIS_STAGE_CLUSTER_LISTS)
+        launch_cluster_lists(st, ctx->d_consts, ctx->cl, ctx->d_stats, ctx->cfg.max_views);
+    CU(cudaGetLastError());
+    if (do_cull) { ctx->frame++; ctx->parity ^= 1u; }
+    return B200VIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// downloads (synchronous: the host buffers are valid on return)
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t b200vis_download_frame_stats(b200vis_ctx *ctx, b200vis_frame_stats *out) {
+    CHECK_CTX();
+    if (!out) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_frame_stats: null");
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const DevStats &s = *ctx->h_stats;
+    memset(out, 0, sizeof *out);
+    for (int v = 0; v < kMaxViews; ++v) {
+        out->visible_count[v] = s.visible_count[v];
+        out->cluster_index_count[v] = s.cl_index_count[v];
+        memcpy(&out->cluster_farthest_z[v], &s.cl_farthest_bits[v], 4);
+        out->cluster_index_overflow[v] = s.cl_overflow[v];
+    }
+    const uint32_t lp = ctx->parity ^ 1u;   // parity the last CULL frame accumulated into
+    out->gt_changed_count = s.changed[lp][0]; out->vv_changed_count = s.changed[lp][1]; out->frame = ctx->frame;
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_download_global_transforms(b200vis_ctx *ctx, uint32_t first, uint32_t count, float *gt,
+                                                      uint32_t stride, uint8_t *changed) {
+    CHECK_CTX();
+    int32_t rc = check_range(ctx, first, count, "download_global_transforms"); if (rc) return rc;
+    if (gt && stride != 12 && stride != 16) return fail(ctx, B200VIS_ERR_INVALID_ARG, "stride_floats must be 12 or 16");
+    cudaStream_t st = ctx->stream;
+    if (gt) {
+        launch_pack_gt(st, ctx->rows, first, count, reinterpret_cast<float *>(ctx->d_stage), stride);
+        CU(cudaMemcpyAsync(gt, ctx->d_stage, (size_t)count * stride * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (changed) {
+        CU(cudaStreamSynchronize(st));
+        launch_pack_state(st, ctx->rows, first, count, ctx->d_stage, S_GT_CHANGED);
+        CU(cudaMemcpyAsync(changed, ctx->d_stage + count, count, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_download_view_visibility(b200vis_ctx *ctx, uint32_t first, uint32_t count, uint8_t *vv, uint8_t *changed) {
+    CHECK_CTX();
+    int32_t rc = check_range(ctx, first, count, "download_view_visibility"); if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    launch_pack_state(st, ctx->rows, first, count, ctx->d_stage, S_VV_CHANGED);
+    if (vv) CU(cudaMemcpyAsync(vv, ctx->d_stage, count, cudaMemcpyDeviceToHost, st));
+    if (changed) CU(cudaMemcpyAsync(changed, ctx->d_stage + count, count, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_download_visible(b200vis_ctx *ctx, uint32_t view, uint32_t *rows, uint32_t capacity, uint32_t *count) {
+    CHECK_CTX();
+    if (view >= ctx->cfg.max_views || !count) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_visible: bad argument");
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint32_t c = ctx->h_stats->visible_count[view];   // an inactive view keeps its last list (mod.rs:780-782)
+    *count = c;
+    if (rows) {
+        if (c > capacity) return fail(ctx, B200VIS_ERR_CAPACITY, "download_visible: %u rows > capacity %u", c, capacity);
+        CU(cudaMemcpyAsync(rows, ctx->vis.lists + (size_t)view * ctx->vis.list_stride, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, uint32_t *offsets, uint32_t *indices,
+                                             uint32_t indices_capacity, uint32_t *total) {
+    CHECK_CTX();
+    if (view >= ctx->cfg.max_views || !offsets || !total) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_clusters: bad argument");
+    const DevClusterView &cv = ctx->h_consts->cviews[view];
+    const uint32_t nc = cv.enabled ? cv.n_clusters : 0;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(offsets, ctx->cl.offsets + (size_t)view * (kMaxClusters + 1), (size_t)(nc + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *total = offsets[nc];
+    if (*total > ctx->cl.index_cap) return fail(ctx, B200VIS_ERR_CAPACITY, "cluster index list overflow: %u > max_cluster_indices %u", *total, ctx->cl.index_cap);
+    if (indices) {
+        if (*total > indices_capacity) return fail(ctx, B200VIS_ERR_CAPACITY, "download_clusters: %u indices > capacity %u", *total, indices_capacity);
+        CU(cudaMemcpyAsync(indices, ctx->cl.indices + (size_t)view * ctx->cl.index_cap, (size_t)*total * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200VIS_OK;
+}

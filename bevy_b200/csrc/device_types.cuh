@@ -1,0 +1,119 @@
+// device_types.cuh -- structures shared by the kernels and the host runtime of libb200vis.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200vis {
+
+constexpr int kTileRows = 256;          // rows per tile == threads per CTA of the tile kernel
+constexpr int kMaxViews = 8;
+constexpr int kMaxClusters = 4096;
+constexpr int kChunkWords = 1024;       // visible-mask words per compaction chunk (32768 rows)
+constexpr uint32_t kNoParent = 0xFFFFFFFFu;
+constexpr uint32_t kDetached = 0xFFFFFFFEu;
+
+// row flag byte (include/b200vis.h)
+constexpr uint32_t F_INHERITED = 0x01, F_AABB = 0x02, F_SPHERE = 0x04, F_NO_FRUSTUM = 0x08, F_RANGE = 0x10,
+                   F_NO_CPU_CULL = 0x20, F_SPHERE_GT = 0x40, F_TCHANGED = 0x80;
+// per-row device state byte: bits 0-1 ViewVisibility, 4 gt_changed, 5 vv_changed, 6 visited, 7 has_class
+constexpr uint32_t S_VV = 0x03, S_GT_CHANGED = 0x10, S_VV_CHANGED = 0x20, S_VISITED = 0x40, S_HAS_CLASS = 0x80;
+// topo word: parent_local[0:9) local_depth[9:18) | flags
+constexpr uint32_t T_ROOT = 1u << 28, T_HAS_CHILDREN = 1u << 29, T_EXT_PARENT = 1u << 30, T_DETACHED = 1u << 31;
+
+struct Tile {               // one CTA's work: a contiguous, (mostly) hierarchy-closed row range
+    uint32_t base;
+    uint16_t n_rows;
+    uint16_t n_levels;      // in-tile depth levels (1 for flat rows)
+};
+
+// SoA mirror of the ECS columns in HBM.  Every array is indexed by row.
+struct Rows {
+    uint32_t n;
+    // Transform: 40 B/row  (A = t.xyz, s.x | B = q.xyzw | C = s.y, s.z)
+    float4 *trsA; float4 *trsB; float2 *trsC;
+    // GlobalTransform: 48 B/row, the three rows of the 3x4 matrix: gtK = (X[k], Y[k], Z[k], T[k])
+    float4 *gt0; float4 *gt1; float4 *gt2;
+    // Aabb / Sphere: 24 B/row (A = c.xyz, h.x | B = h.y, h.z)
+    float4 *bndA; float2 *bndB;
+    uint8_t *flags;          // B200VIS_F_* | F_TCHANGED
+    uint8_t *state;          // S_*
+    uint32_t *topo;          // T_* | local parent | local depth
+    const uint32_t *parent;  // global parent row (read only for T_EXT_PARENT rows)
+    const uint64_t *layers;  // RenderLayers first block, or nullptr
+    const uint32_t *range;   // VisibleEntityRanges bitmask, or nullptr
+    const uint32_t *rank;    // position in Entity::to_bits() order, or nullptr when rank == row
+    const uint32_t *row_of_rank;
+    uint8_t *dirty;          // global TransformTreeChanged bytes (multi-pass plans only), or nullptr
+};
+
+struct DevView {
+    float4 hs[6];
+    unsigned long long layer_mask;
+    uint32_t flags;
+    int32_t range_index;
+};
+
+struct DevClusterView {
+    uint32_t enabled, dims[3], is_ortho, n_clusters, pad0, pad1;
+    float vfw[16];           // view_from_world, column major
+    float cfv[16];           // clip_from_view
+    float scale[3];          // view_from_world_scale
+    float scale_max;
+    float4 frustum[6];
+    unsigned long long layer_mask;
+    unsigned long long pad2;
+};
+
+struct FrameConsts {
+    uint32_t n_views, pad[3];
+    DevView views[kMaxViews];
+    DevClusterView cviews[kMaxViews];
+};
+
+// counters written by the kernels (one D2H copy per frame)
+struct DevStats {
+    uint32_t visible_count[kMaxViews];     // written by the expand kernel for ACTIVE views only
+    uint32_t cl_index_count[kMaxViews];    // outputs of the last cluster frame (copied from the accumulators
+    uint32_t cl_farthest_bits[kMaxViews];  //   by the lists kernel, which also re-zeroes them)
+    uint32_t cl_overflow[kMaxViews];
+    uint32_t cl_acc_index[kMaxViews];      // accumulators of the assign kernel
+    uint32_t cl_acc_far[kMaxViews];        // float bits; values > 0 only, so integer max == float max
+    uint32_t changed[2][2];                // [frame parity][0 = gt, 1 = vv]; the expand kernel of frame f
+                                           // zeroes the parity frame f+1 accumulates into
+};
+
+struct VisibleBufs {
+    uint32_t n_words;        // ceil(n/32)
+    uint32_t n_chunks;       // ceil(n_words / kChunkWords)
+    uint32_t words_stride;   // words per view
+    uint32_t chunks_stride;  // chunk counters per view
+    uint32_t *mask;          // [V][words_stride], bit = rank
+    uint32_t *chunk_count;   // [2][V][chunks_stride]
+    uint32_t *lists;         // [V][list_stride] rows, ascending Entity::to_bits()
+    uint32_t list_stride;
+};
+
+struct Lights {
+    uint32_t n;
+    const uint32_t *row;
+    const float *range;
+    const uint64_t *layers;  // or nullptr
+};
+
+struct ClusterBufs {
+    uint32_t words;          // mask words per rank = ceil(max_lights/32)
+    uint32_t max_lights;     // per rank
+    uint32_t world, rank;
+    uint32_t max_views;
+    uint32_t index_cap;      // per view
+    uint32_t *send;          // this rank's slab: [V][words][kMaxClusters]
+    const uint32_t *recv;    // gathered: [world][V][words][kMaxClusters]
+    const float4 *xplanes;   // [V][4097]
+    const float4 *yplanes;
+    const float4 *zplanes;
+    const float *zthr;       // [V][4096]: thresholds on u = -view_z
+    uint32_t *offsets;       // [V][kMaxClusters+1]
+    uint32_t *indices;       // [V][index_cap]
+};
+
+}  // namespace b200vis

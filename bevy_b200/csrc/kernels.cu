@@ -1,0 +1,687 @@
+// kernels.cu -- the sm_100a kernels of libb200vis: propagate -> cull -> cluster.
+//
+// Numerics contract: every float operation below is IEEE-754 binary32 in the
+// operation order of glam's x86-64/SSE2 backend, with
+// NO fused multiply-add (this translation unit is compiled with -fmad=false,
+// -prec-div=true, -prec-sqrt=true, -ftz=false), so the float compares that
+// decide ViewVisibility bits and cluster membership are bit-identical to the
+// reference's CPU systems.  These are HBM-bound byte/float streaming kernels:
+// no tensor cores on purpose (~1.3 flop/B).
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "device_types.cuh"
+#include "kernels.cuh"
+
+namespace b200vis {
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+struct Aff { float4 r0, r1, r2; };   // row form of a glam Affine3A: rK = (X[k], Y[k], Z[k], T[k])
+
+// Transform::compute_affine = Affine3A::from_scale_rotation_translation
+// (crates/bevy_transform/src/components/transform.rs:273-275; glam Mat3A::from_quat)
+__device__ __forceinline__ Aff affine_from_trs(float4 A, float4 q, float2 C) {
+    const float sx = A.w, sy = C.x, sz = C.y;
+    const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
+    const float xx = q.x * x2, xy = q.x * y2, xz = q.x * z2;
+    const float yy = q.y * y2, yz = q.y * z2, zz = q.z * z2;
+    const float wx = q.w * x2, wy = q.w * y2, wz = q.w * z2;
+    Aff a;
+    a.r0 = make_float4((1.0f - (yy + zz)) * sx, (xy - wz) * sy, (xz + wy) * sz, A.x);
+    a.r1 = make_float4((xy + wz) * sx, (1.0f - (xx + zz)) * sy, (yz - wx) * sz, A.y);
+    a.r2 = make_float4((xz - wy) * sx, (yz + wx) * sy, (1.0f - (xx + yy)) * sz, A.z);
+    return a;
+}
+
+// one output row of Affine3A * Affine3A (global_transform.rs:315-317):
+//   matrix3 = P.m3 * L.m3 with mul_vec3a = ((X*v.x) + (Y*v.y)) + (Z*v.z); translation = P.m3*L.t + P.t
+__device__ __forceinline__ float4 affine_mul_row(float4 p, const Aff &l) {
+    float4 r;
+    r.x = (p.x * l.r0.x + p.y * l.r1.x) + p.z * l.r2.x;
+    r.y = (p.x * l.r0.y + p.y * l.r1.y) + p.z * l.r2.y;
+    r.z = (p.x * l.r0.z + p.y * l.r1.z) + p.z * l.r2.z;
+    r.w = ((p.x * l.r0.w + p.y * l.r1.w) + p.z * l.r2.w) + p.w;
+    return r;
+}
+__device__ __forceinline__ bool row_neq(float4 a, float4 b) {
+    return (a.x != b.x) | (a.y != b.y) | (a.z != b.z) | (a.w != b.w);
+}
+// glam SSE2 dot4 of a plane with (p, 1): (n.x*p.x + n.z*p.z) + (n.y*p.y + n.w*1)
+__device__ __forceinline__ float plane_dot_point(float4 n, float px, float py, float pz) {
+    return (n.x * px + n.z * pz) + (n.y * py + n.w * 1.0f);
+}
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return (ax * bx + ay * by) + az * bz;
+}
+__device__ __forceinline__ float gl_min(float a, float b) { return a < b ? a : b; }   // glam / SSE min,max
+__device__ __forceinline__ float gl_max(float a, float b) { return a > b ? a : b; }
+
+// The closure of check_visibility_cpu_culling for one entity and one view
+// (crates/bevy_camera/src/visibility/mod.rs:804-844), frustum part.
+//   Aabb:   sphere pre-test (primitives.rs:255-268, planes 0..4) then OBB test (primitives.rs:272-294,
+//           planes 0..4: near included, far skipped); both use the same dot(plane, (center,1)).
+//   Sphere: sphere test only.
+__device__ __forceinline__ bool frustum_visible(const float4 *hs, uint32_t f, const Aff &g, float4 bA, float2 bB) {
+    if (f & F_AABB) {
+        const float cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;   // transform_point3a
+        const float cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
+        const float cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+        const float hx = bA.w, hy = bB.x, hz = bB.y;
+        const float vx = (g.r0.x * hx + g.r0.y * hy) + g.r0.z * hz;                    // radius_vec3a
+        const float vy = (g.r1.x * hx + g.r1.y * hy) + g.r1.z * hz;
+        const float vz = (g.r2.x * hx + g.r2.y * hy) + g.r2.z * hz;
+        const float radius = sqrtf((vx * vx + vy * vy) + vz * vz);
+        float d[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            d[k] = plane_dot_point(hs[k], cx, cy, cz);
+            if (d[k] + radius <= 0.0f) return false;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float4 n = hs[k];
+            // Aabb::relative_radius (primitives.rs:109-119)
+            const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+            const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+            const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+            const float rr = (dx * hx + dy * hy) + dz * hz;
+            if (d[k] + rr <= 0.0f) return false;
+        }
+        return true;
+    }
+    if (f & F_SPHERE) {
+        float cx = bA.x, cy = bA.y, cz = bA.z;
+        if (f & F_SPHERE_GT) { cx = g.r0.w; cy = g.r1.w; cz = g.r2.w; }
+        const float radius = bA.w;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (plane_dot_point(hs[k], cx, cy, cz) + radius <= 0.0f) return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 1: fused propagate -> cull over one tile of rows per CTA.
+//
+// A tile is a contiguous row range whose hierarchy edges stay inside the tile (parents in
+// shared memory) or point at rows finished by an earlier pass (parents read from HBM).
+//   phase 1  all rows: coalesced float4 loads of Transform, old GlobalTransform, bounds, flags
+//            (everything a row needs is requested up front: ~11 independent loads per thread)
+//   phase 2  per in-tile depth level: GT = parentGT * local, parent tiles staged in shared memory
+//   phase 3  all rows: set_if_neq write-back, frustum tests for every view, warp-ballot bits into
+//            the rank-ordered visible mask, ViewVisibility state machine, change flags
+// ------------------------------------------------------------------------------------------
+struct TileSmem {
+    float4 g0[kTileRows], g1[kTileRows], g2[kTileRows];
+    uint16_t parent[kTileRows];
+    uint8_t st[kTileRows];       // bit0 visited, bit1 gt changed
+    uint8_t dirty[kTileRows];    // TransformTreeChanged this frame (mark_dirty_trees)
+    DevView views[kMaxViews];
+    uint32_t n_views;
+};
+
+__global__ void __launch_bounds__(kTileRows)
+k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__restrict__ fc, VisibleBufs vb,
+                 DevStats *__restrict__ stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
+    __shared__ TileSmem s;
+    const Tile tile = tiles[blockIdx.x];
+    const uint32_t lr = threadIdx.x;
+    const bool active = lr < tile.n_rows;
+    const uint32_t row = tile.base + lr;
+    const bool do_prop = stages & 1u, do_cull = stages & 2u;
+
+    if (do_cull) {   // stage the per-view constants once per CTA
+        const uint32_t nv = fc->n_views;
+        if (lr == 0) s.n_views = nv;
+        const uint32_t words = nv * (sizeof(DevView) / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(fc->views);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s.views);
+        for (uint32_t i = lr; i < words; i += kTileRows) dst[i] = src[i];
+    }
+
+    // ---- phase 1: loads -------------------------------------------------------------
+    float4 A = make_float4(0, 0, 0, 0), q = A, bA = A;
+    float2 C = make_float2(0, 0), bB = C;
+    Aff g;            // current GlobalTransform (old value until overwritten)
+    g.r0 = g.r1 = g.r2 = A;
+    uint32_t f = 0, st8 = 0, topo = T_DETACHED;
+    if (active) {
+        f = R.flags[row];
+        st8 = R.state[row];
+        g.r0 = R.gt0[row]; g.r1 = R.gt1[row]; g.r2 = R.gt2[row];
+        if (do_prop) { topo = R.topo[row]; A = R.trsA[row]; q = R.trsB[row]; C = R.trsC[row]; }
+        if (do_cull) { bA = R.bndA[row]; bB = R.bndB[row]; }
+    }
+
+    bool visited = false, changed = false;
+    if (do_prop) {
+        const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
+        const bool tchanged = f & F_TCHANGED;
+        // -- mark_dirty_trees (systems.rs:111-306) inside the tile: climb the staged parent links
+        bool dirty = tchanged;
+        if (static_opt && R.dirty != nullptr) {
+            dirty = active && R.dirty[row];     // multi-pass plan: k_mark_dirty_global ran first
+        } else if (static_opt && tile.n_levels > 1) {
+            s.parent[lr] = (uint16_t)((depth > 0) ? plocal : 0xFFFFu);
+            s.dirty[lr] = 0;
+            __syncthreads();
+            if (active && tchanged) {
+                uint32_t c = lr;
+                while (!s.dirty[c]) {           // benign race: every writer stores 1, every chain finishes
+                    s.dirty[c] = 1;
+                    const uint32_t p = s.parent[c];
+                    if (p == 0xFFFFu) break;
+                    c = p;
+                }
+            }
+            __syncthreads();
+            dirty = s.dirty[lr];
+        }
+        const Aff l = affine_from_trs(A, q, C);
+        for (uint32_t lvl = 0; lvl < tile.n_levels; ++lvl) {
+            if (active && depth == lvl && !(topo & T_DETACHED)) {
+                Aff n = l;
+                if (topo & T_ROOT) {
+                    // flat entity: sync_simple_transforms (systems.rs:42-79); root with children:
+                    // unconditional write (systems.rs:525-530)
+                    visited = (topo & T_HAS_CHILDREN) ? (!static_opt || dirty) : tchanged;
+                    changed = visited;
+                } else {
+                    float4 p0, p1, p2; uint32_t pst;
+                    if (lvl == 0) {   // parent finished by an earlier pass: read it from HBM
+                        const uint32_t pr = R.parent[row];
+                        p0 = R.gt0[pr]; p1 = R.gt1[pr]; p2 = R.gt2[pr];
+                        const uint32_t ps = R.state[pr];
+                        pst = ((ps & S_VISITED) ? 1u : 0u) | ((ps & S_GT_CHANGED) ? 2u : 0u);
+                    } else {
+                        p0 = s.g0[plocal]; p1 = s.g1[plocal]; p2 = s.g2[plocal];
+                        pst = s.st[plocal];
+                    }
+                    // propagate_descendants_unchecked (systems.rs:706-727)
+                    visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                    if (visited) {
+                        n.r0 = affine_mul_row(p0, l); n.r1 = affine_mul_row(p1, l); n.r2 = affine_mul_row(p2, l);
+                        changed = row_neq(n.r0, g.r0) | row_neq(n.r1, g.r1) | row_neq(n.r2, g.r2);   // set_if_neq
+                    }
+                }
+                if (changed) g = n;
+                if (topo & T_HAS_CHILDREN) {
+                    s.g0[lr] = g.r0; s.g1[lr] = g.r1; s.g2[lr] = g.r2;
+                    s.st[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+                }
+            }
+            if (lvl + 1 < tile.n_levels) __syncthreads();
+        }
+        if (active) {
+            if (changed) { R.gt0[row] = g.r0; R.gt1[row] = g.r1; R.gt2[row] = g.r2; }
+            if (tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
+        }
+    }
+    uint32_t out = st8 & (S_VV | S_HAS_CLASS);
+    if (do_prop) out |= (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
+    else out |= st8 & (S_GT_CHANGED | S_VISITED);
+
+    // ---- phase 3: cull ----------------------------------------------------------------
+    bool vv_changed = false;
+    if (do_cull) {
+        __syncthreads();   // s.views
+        const bool in_query = active && !(f & F_NO_CPU_CULL);          // Without<NoCpuCulling>
+        const uint32_t prev = st8 & 1u;                                // reset_view_visibility: v = (v&1)<<1
+        bool any = false;
+        const uint32_t nv = s.n_views;
+        const uint32_t lane = lr & 31u;
+        const uint32_t rnk = (R.rank != nullptr && active) ? R.rank[row] : row;
+        const unsigned long long elayers = (R.layers != nullptr && active) ? R.layers[row] : 1ull;
+        const uint32_t erange = ((f & F_RANGE) && R.range != nullptr) ? R.range[row] : 0xFFFFFFFFu;
+        for (uint32_t v = 0; v < nv; ++v) {
+            const DevView &view = s.views[v];
+            if (!(view.flags & 1u)) continue;                          // !camera.is_active
+            bool vis = in_query && (f & F_INHERITED) && (view.layer_mask & elayers) != 0ull;
+            if (vis && (f & F_RANGE) && R.range != nullptr)
+                vis = view.range_index >= 0 && ((erange >> view.range_index) & 1u);
+            if (vis && !(f & F_NO_FRUSTUM) && !(view.flags & 2u)) vis = frustum_visible(view.hs, f, g, bA, bB);
+            any |= vis;
+            // entities without a VisibilityClass are set_visible() but not listed (mod.rs:846-857)
+            const bool listed = vis && (st8 & S_HAS_CLASS);
+            uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
+            uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
+            if (R.rank == nullptr) {
+                // warp-ballot compaction: 32 consecutive rows -> at most two mask words
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
+                if (lane == 0 && b) {
+                    const uint32_t row0 = row, w0 = row0 >> 5, sh = row0 & 31u;
+                    const uint32_t lo = b << sh, hi = sh ? (b >> (32u - sh)) : 0u;
+                    if (lo) { atomicOr(mask + w0, lo); atomicAdd(cc + (w0 / kChunkWords), __popc(lo)); }
+                    if (hi) { atomicOr(mask + w0 + 1, hi); atomicAdd(cc + ((w0 + 1) / kChunkWords), __popc(hi)); }
+                }
+            } else if (listed) {
+                atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+                atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
+            }
+        }
+        if (in_query) {
+            // set_visible + mark_newly_hidden_entities_invisible (mod.rs:292-306, 908-918):
+            // visible -> 0b01 | prev<<1 ; hidden -> 0 ; Changed fires on 0->1 and 1->0 only
+            out = (out & ~S_VV) | (any ? (1u | (prev << 1)) : 0u);
+            vv_changed = (any ? 1u : 0u) != prev;
+            if (vv_changed) out |= S_VV_CHANGED;
+        }
+    } else {
+        out |= st8 & S_VV_CHANGED;
+    }
+    if (active && out != st8) R.state[row] = (uint8_t)out;
+
+    // per-frame change counters (one atomic per warp)
+    const uint32_t bg = __ballot_sync(0xFFFFFFFFu, do_prop && changed);
+    const uint32_t bv = __ballot_sync(0xFFFFFFFFu, vv_changed);
+    if ((lr & 31u) == 0) {
+        if (bg) atomicAdd(&stats->changed[parity][0], __popc(bg));
+        if (bv) atomicAdd(&stats->changed[parity][1], __popc(bv));
+    }
+}
+
+// mark_dirty_trees for plans whose tiles have parents in other tiles: every Changed row climbs its
+// ancestor chain through HBM, stopping at the first already-dirty ancestor (the reference's
+// fetch_or early exit, systems.rs:208-223).  `dirty` is zeroed by the caller.
+__global__ void k_mark_dirty_global(Rows R) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= R.n || !(R.flags[row] & F_TCHANGED)) return;
+    uint32_t c = row;
+    while (true) {
+        if (R.dirty[c]) break;
+        R.dirty[c] = 1;
+        const uint32_t p = R.parent[c];
+        if (p >= R.n) break;
+        c = p;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 2: visible mask -> sorted row lists (one CTA per 1024-word chunk per view).
+// Output order is ascending rank == ascending Entity::to_bits(): the result of the reference's
+// serial `sort_unstable` (visibility/mod.rs:870-874) without a sort.  Also zeroes the mask it
+// consumed and the counters of the NEXT frame's parity.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kChunkWords)
+k_expand_visible(VisibleBufs vb, const uint32_t *__restrict__ row_of_rank, const FrameConsts *__restrict__ fc,
+                 DevStats *__restrict__ stats, uint32_t parity, uint32_t n_rows) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base, s_total;
+    const uint32_t v = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+    if (v >= fc->n_views) return;
+    uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
+    uint32_t *cc_next = vb.chunk_count + ((size_t)(parity ^ 1u) * kMaxViews + v) * vb.chunks_stride;
+    if (t == 0) cc_next[chunk] = 0;
+    if (chunk == 0 && v == 0 && t < 2) stats->changed[parity ^ 1u][t] = 0;   // next frame's accumulators
+    if (!(fc->views[v].flags & 1u)) return;   // inactive view: VisibleEntities untouched (mod.rs:780-782)
+
+    const uint32_t word = chunk * kChunkWords + t;
+    uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
+    uint32_t w = 0;
+    if (word < vb.n_words) { w = mask[word]; if (w) mask[word] = 0; }
+    const uint32_t c = __popc(w);
+    // block exclusive scan of c
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((t & 31u) >= (uint32_t)o) incl += y; }
+    if ((t & 31u) == 31u) s_warp[t >> 5] = incl;
+    // base = sum of the counts of the preceding chunks (<= a few hundred values)
+    uint32_t part = 0, tot = 0;
+    if (t < 32) {
+        for (uint32_t i = t; i < vb.n_chunks; i += 32) { const uint32_t x = cc[i]; tot += x; if (i < chunk) part += x; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xFFFFFFFFu, part, o); tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o); }
+        if (t == 0) { s_base = part; s_total = tot; }
+    }
+    __syncthreads();
+    if (t < 32) {
+        uint32_t x = s_warp[t];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
+        s_warp[t] = x;   // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t pos = s_base + (incl - c) + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+    uint32_t *out = vb.lists + (size_t)v * vb.list_stride;
+    while (w) {
+        const uint32_t b = __ffs(w) - 1; w &= w - 1;
+        const uint32_t rk = word * 32u + b;
+        out[pos++] = row_of_rank ? row_of_rank[rk] : rk;
+    }
+    if (chunk == 0 && t == 0) stats->visible_count[v] = s_total;
+    (void)n_rows;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 3: assign_objects_to_clusters, point lights: one warp per (light, view)
+// (crates/bevy_light/src/cluster/assign.rs:487-748).  Lanes split the (z, y) rows of the
+// iterative sphere refinement; each row sets its [min_x, max_x] bits in the cluster x light mask.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 mat4_mul_point(const float *m, float x, float y, float z) {   // M * (p, 1)
+    float4 r;   // (((X*x) + (Y*y)) + (Z*z)) + (W*1)
+    r.x = ((m[0] * x + m[4] * y) + m[8] * z) + m[12] * 1.0f;
+    r.y = ((m[1] * x + m[5] * y) + m[9] * z) + m[13] * 1.0f;
+    r.z = ((m[2] * x + m[6] * y) + m[10] * z) + m[14] * 1.0f;
+    r.w = ((m[3] * x + m[7] * y) + m[11] * z) + m[15] * 1.0f;
+    return r;
+}
+// view_z_to_z_slice (assign.rs:1046-1062) through the host-computed thresholds on u = -view_z
+__device__ __forceinline__ uint32_t z_slice_of(const float *thr, uint32_t z_slices, float view_z) {
+    const float u = -view_z;
+    uint32_t lo = 0, hi = z_slices - 1;       // number of k in [1, z_slices) with u >= thr[k-1]
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (u >= thr[mid]) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// ndc_position_to_cluster (assign.rs:922-941)
+__device__ __forceinline__ uint3 ndc_to_cluster(const DevClusterView &cv, const float *thr, float nx, float ny, float view_z) {
+    const float fx = gl_min(gl_max(nx * 0.5f + 0.5f, 0.0f), 1.0f);
+    const float fy = gl_min(gl_max(ny * -0.5f + 0.5f, 0.0f), 1.0f);
+    const uint32_t x = __float2uint_rz(floorf(fx * (float)cv.dims[0]));
+    const uint32_t y = __float2uint_rz(floorf(fy * (float)cv.dims[1]));
+    const uint32_t z = z_slice_of(thr, cv.dims[2], view_z);
+    return make_uint3(min(x, cv.dims[0] - 1), min(y, cv.dims[1] - 1), min(z, cv.dims[2] - 1));
+}
+
+__global__ void __launch_bounds__(256)
+k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__restrict__ stats) {
+    const uint32_t v = blockIdx.y;
+    if (v >= fc->n_views) return;
+    const DevClusterView &cv = fc->cviews[v];
+    if (!cv.enabled) return;
+    const uint32_t li = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (li >= L.n) return;
+    const uint32_t row = L.row[li];
+    if (!(R.state[row] & 1u)) return;                                   // view_visibility.get() (assign.rs:195)
+    const unsigned long long ll = L.layers ? L.layers[li] : 1ull;
+    if (!(cv.layer_mask & ll)) return;                                  // assign.rs:489
+    const float px = R.gt0[row].w, py = R.gt1[row].w, pz = R.gt2[row].w;   // GlobalTransform::translation
+    const float range = L.range[li];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)                                         // frustum.intersects_sphere(.., true)
+        if (plane_dot_point(cv.frustum[k], px, py, pz) + range <= 0.0f) return;
+
+    const float *thr = cb.zthr + (size_t)v * kMaxClusters;
+    const bool ortho = cv.is_ortho;
+    // cluster_space_clusterable_object_aabb (assign.rs:948-1036)
+    const float4 vc = mat4_mul_point(cv.vfw, px, py, pz);
+    const float hx = range * fabsf(cv.scale[0]), hy = range * fabsf(cv.scale[1]), hz = range * fabsf(cv.scale[2]);
+    const float minx = vc.x - hx, miny = vc.y - hy, maxx = vc.x + hx, maxy = vc.y + hy;
+    const float minz = fminf(vc.z - hz, -1.17549435e-38f), maxz = fminf(vc.z + hz, -1.17549435e-38f);
+    float nminx, nminy, nmaxx, nmaxy;
+    {
+        const float4 a = mat4_mul_point(cv.cfv, minx, miny, minz), b = mat4_mul_point(cv.cfv, minx, miny, maxz);
+        const float4 c = mat4_mul_point(cv.cfv, maxx, maxy, minz), d = mat4_mul_point(cv.cfv, maxx, maxy, maxz);
+        const float ax = a.x / a.w, ay = a.y / a.w, bx = b.x / b.w, by = b.y / b.w;
+        const float cx = c.x / c.w, cy = c.y / c.w, dx = d.x / d.w, dy = d.y / d.w;
+        nminx = gl_min(gl_min(gl_min(ax, bx), cx), dx); nminy = gl_min(gl_min(gl_min(ay, by), cy), dy);
+        nmaxx = gl_max(gl_max(gl_max(ax, bx), cx), dx); nmaxy = gl_max(gl_max(gl_max(ay, by), cy), dy);
+        nminx = gl_min(gl_max(nminx, -1.0f), 1.0f); nminy = gl_min(gl_max(nminy, -1.0f), 1.0f);
+        nmaxx = gl_min(gl_max(nmaxx, -1.0f), 1.0f); nmaxy = gl_min(gl_max(nmaxy, -1.0f), 1.0f);
+    }
+    const uint3 c0 = ndc_to_cluster(cv, thr, nminx, nminy, minz), c1 = ndc_to_cluster(cv, thr, nmaxx, nmaxy, maxz);
+    const uint3 lo = make_uint3(min(c0.x, c1.x), min(c0.y, c1.y), min(c0.z, c1.z));
+    const uint3 hi = make_uint3(max(c0.x, c1.x), max(c0.y, c1.y), max(c0.z, c1.z));
+    // view-space sphere (assign.rs:551-556)
+    const float sr = range * cv.scale_max;
+    if (lane == 0) {
+        // farthest_z (assign.rs:558-561): -row2 . (t,1) + range*scale.z ; fmax against 0
+        const float4 r2 = make_float4(cv.vfw[2], cv.vfw[6], cv.vfw[10], cv.vfw[14]);
+        const float this_far = -plane_dot_point(r2, px, py, pz) + range * cv.scale[2];
+        if (this_far > 0.0f) atomicMax(&stats->cl_acc_far[v], __float_as_uint(this_far));
+    }
+    const float4 cc = mat4_mul_point(cv.cfv, vc.x, vc.y, vc.z);
+    const float ndx = cc.x / cc.w, ndy = cc.y / cc.w, ndz = cc.z / cc.w;
+    const uint3 ccl = ndc_to_cluster(cv, thr, ndx, ndy, vc.z);
+    const bool has_zc = ndz <= 1.0f; const uint32_t zc = ccl.z;
+    bool has_yc; uint32_t yc = 0;
+    if (ndy > 1.0f) has_yc = false;
+    else if (ndy < -1.0f) { has_yc = true; yc = cv.dims[1] + 1; }
+    else { has_yc = true; yc = ccl.y; }
+
+    const float4 *xp = cb.xplanes + (size_t)v * (kMaxClusters + 1);
+    const float4 *yp = cb.yplanes + (size_t)v * (kMaxClusters + 1);
+    const float4 *zp = cb.zplanes + (size_t)v * (kMaxClusters + 1);
+    uint32_t *mask = cb.send + ((size_t)v * cb.words + (li >> 5)) * kMaxClusters;
+    const uint32_t bit = 1u << (li & 31u);
+    const uint32_t ny = hi.y - lo.y + 1, npairs = (hi.z - lo.z + 1) * ny;
+    uint32_t count = 0;
+    for (uint32_t p = lane; p < npairs; p += 32) {
+        const uint32_t z = lo.z + p / ny, y = lo.y + p % ny;
+        float ox = vc.x, oy = vc.y, oz = vc.z, orad = sr;
+        if (!has_zc || z != zc) {                                  // project_to_plane_z (assign.rs:1094-1113)
+            const float4 pl = (has_zc && z < zc) ? zp[z + 1] : zp[z];
+            const float zz = pl.w / pl.z;
+            const float dist = zz - oz;
+            if (fabsf(dist) > orad) continue;
+            oz = zz;
+            orad = sqrtf(orad * orad - dist * dist);
+        }
+        if (!has_yc || y != yc) {                                  // project_to_plane_y (assign.rs:1116-1134)
+            const float4 pl = (has_yc && y < yc) ? yp[y + 1] : yp[y];
+            const float dist = ortho ? pl.w - oy : -(oy * pl.y + oz * pl.z);
+            if (fabsf(dist) > orad) continue;
+            ox = ox + dist * pl.x; oy = oy + dist * pl.y; oz = oz + dist * pl.z;
+            orad = sqrtf(orad * orad - dist * dist);
+        }
+        uint32_t min_x = lo.x;                                     // assign.rs:647-675, get_distance_x :1081-1091
+        while (true) {
+            if (min_x >= hi.x) break;
+            const float4 pl = xp[min_x + 1];
+            const float dx = ortho ? ox - pl.w : pl.x * ox + pl.z * oz;
+            if (-dx + orad > 0.0f) break;
+            ++min_x;
+        }
+        uint32_t max_x = hi.x;
+        while (true) {
+            if (max_x <= min_x) break;
+            const float4 pl = xp[max_x];
+            const float dx = ortho ? ox - pl.w : pl.x * ox + pl.z * oz;
+            if (dx + orad > 0.0f) break;
+            --max_x;
+        }
+        uint32_t ci = (y * cv.dims[0] + min_x) * cv.dims[2] + z;   // assign.rs:676-678
+        for (uint32_t x = min_x; x <= max_x; ++x) { atomicOr(mask + ci, bit); ci += cv.dims[2]; }
+        count += max_x - min_x + 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xFFFFFFFFu, count, o);
+    if (lane == 0 && count) atomicAdd(&stats->cl_acc_index[v], count);
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 4: cluster x light bitmask (all ranks' slabs) -> per-cluster ordered index lists.
+// One CTA per view: popcount -> block scan -> ordered emit.  Ascending (rank, light) order is
+// the reference's push order (the outer loop runs over lights, assign.rs:487).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__restrict__ stats) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t v = blockIdx.x, t = threadIdx.x;
+    if (v >= fc->n_views) return;
+    const DevClusterView &cv = fc->cviews[v];
+    uint32_t *offsets = cb.offsets + (size_t)v * (kMaxClusters + 1);
+    if (t == 0) {   // publish this frame's accumulators and re-arm them
+        stats->cl_index_count[v] = stats->cl_acc_index[v]; stats->cl_acc_index[v] = 0;
+        stats->cl_farthest_bits[v] = stats->cl_acc_far[v]; stats->cl_acc_far[v] = 0;
+    }
+    if (!cv.enabled) { if (t == 0) { offsets[0] = 0; stats->cl_overflow[v] = 0; } return; }
+    const uint32_t nc = cv.n_clusters;
+    const size_t rank_stride = (size_t)cb.max_views * cb.words * kMaxClusters;
+    const uint32_t *base = cb.recv + (size_t)v * cb.words * kMaxClusters;
+    uint32_t *indices = cb.indices + (size_t)v * cb.index_cap;
+    if (t == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < nc; c0 += 1024) {
+        const uint32_t c = c0 + t;
+        uint32_t cnt = 0;
+        if (c < nc)
+            for (uint32_t r = 0; r < cb.world; ++r)
+                for (uint32_t w = 0; w < cb.words; ++w) cnt += __popc(base[r * rank_stride + (size_t)w * kMaxClusters + c]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((t & 31u) >= (uint32_t)o) incl += y; }
+        if ((t & 31u) == 31u) s_warp[t >> 5] = incl;
+        __syncthreads();
+        if (t < 32) {
+            uint32_t x = s_warp[t];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
+            s_warp[t] = x;
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        uint32_t pos = carry + (incl - cnt) + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+        if (c < nc) {
+            offsets[c] = pos;
+            for (uint32_t r = 0; r < cb.world; ++r)
+                for (uint32_t w = 0; w < cb.words; ++w) {
+                    uint32_t m = base[r * rank_stride + (size_t)w * kMaxClusters + c];
+                    while (m) {
+                        const uint32_t b = __ffs(m) - 1; m &= m - 1;
+                        if (pos < cb.index_cap) indices[pos] = r * cb.max_lights + w * 32u + b;
+                        ++pos;
+                    }
+                }
+            // leave this rank's slab zeroed for the next frame's assign kernel
+            uint32_t *mine = cb.send + (size_t)v * cb.words * kMaxClusters;
+            for (uint32_t w = 0; w < cb.words; ++w) mine[(size_t)w * kMaxClusters + c] = 0;
+        }
+        __syncthreads();
+        if (t == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (t == 0) {
+        const uint32_t total = s_carry;
+        offsets[nc] = total;
+        stats->cl_overflow[v] = total > cb.index_cap ? 1u : 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pack / unpack kernels for the C ABI's AoS <-> device SoA conversion
+// ------------------------------------------------------------------------------------------
+__global__ void k_unpack_trs(Rows R, uint32_t first, uint32_t count, const float *__restrict__ src, int mark_only) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t row = first + i;
+    if (!mark_only) {
+        const float *t = src + (size_t)i * 10;
+        R.trsA[row] = make_float4(t[0], t[1], t[2], t[7]);
+        R.trsB[row] = make_float4(t[3], t[4], t[5], t[6]);
+        R.trsC[row] = make_float2(t[8], t[9]);
+    }
+    R.flags[row] = (uint8_t)(R.flags[row] | F_TCHANGED);
+}
+__global__ void k_scatter_trs(Rows R, uint32_t count, const uint32_t *__restrict__ rows, const float *__restrict__ src) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t row = rows[i];
+    if (row >= R.n) return;
+    const float *t = src + (size_t)i * 10;
+    R.trsA[row] = make_float4(t[0], t[1], t[2], t[7]);
+    R.trsB[row] = make_float4(t[3], t[4], t[5], t[6]);
+    R.trsC[row] = make_float2(t[8], t[9]);
+    R.flags[row] = (uint8_t)(R.flags[row] | F_TCHANGED);
+}
+__global__ void k_unpack_gt(Rows R, uint32_t first, uint32_t count, const float *__restrict__ src) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float *g = src + (size_t)i * 12;   // X.xyz Y.xyz Z.xyz T.xyz
+    const uint32_t row = first + i;
+    R.gt0[row] = make_float4(g[0], g[3], g[6], g[9]);
+    R.gt1[row] = make_float4(g[1], g[4], g[7], g[10]);
+    R.gt2[row] = make_float4(g[2], g[5], g[8], g[11]);
+}
+__global__ void k_pack_gt(Rows R, uint32_t first, uint32_t count, float *__restrict__ dst, uint32_t stride) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t row = first + i;
+    const float4 a = R.gt0[row], b = R.gt1[row], c = R.gt2[row];
+    float *g = dst + (size_t)i * stride;
+    if (stride == 12) {
+        g[0] = a.x; g[1] = b.x; g[2] = c.x; g[3] = a.y; g[4] = b.y; g[5] = c.y;
+        g[6] = a.z; g[7] = b.z; g[8] = c.z; g[9] = a.w; g[10] = b.w; g[11] = c.w;
+    } else {   // glam Affine3A: four 16-byte Vec3A lanes
+        g[0] = a.x; g[1] = b.x; g[2] = c.x; g[3] = 0.0f; g[4] = a.y; g[5] = b.y; g[6] = c.y; g[7] = 0.0f;
+        g[8] = a.z; g[9] = b.z; g[10] = c.z; g[11] = 0.0f; g[12] = a.w; g[13] = b.w; g[14] = c.w; g[15] = 0.0f;
+    }
+}
+__global__ void k_unpack_bounds(Rows R, uint32_t first, uint32_t count, const float *__restrict__ bounds,
+                                const uint8_t *__restrict__ flags, const uint8_t *__restrict__ cls) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t row = first + i;
+    const float *b = bounds + (size_t)i * 6;
+    R.bndA[row] = make_float4(b[0], b[1], b[2], b[3]);
+    R.bndB[row] = make_float2(b[4], b[5]);
+    R.flags[row] = (uint8_t)((flags[i] & 0x7Fu) | (R.flags[row] & F_TCHANGED));
+    R.state[row] = (uint8_t)((R.state[row] & ~S_HAS_CLASS) | (cls[i] ? S_HAS_CLASS : 0u));
+}
+__global__ void k_unpack_vv(Rows R, uint32_t first, uint32_t count, const uint8_t *__restrict__ vv) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t row = first + i;
+    R.state[row] = (uint8_t)((R.state[row] & ~S_VV) | (vv[i] & S_VV));
+}
+// out[0..count) = vv byte, out[count..2count) = changed byte selected by `changed_bit`
+__global__ void k_pack_state(Rows R, uint32_t first, uint32_t count, uint8_t *__restrict__ out, uint32_t changed_bit) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t s = R.state[first + i];
+    out[i] = (uint8_t)(s & S_VV);
+    out[count + i] = (s & changed_bit) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const FrameConsts *fc,
+                           const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
+    if (n_tiles == 0) return;
+    k_propagate_cull<<<n_tiles, kTileRows, 0, st>>>(R, tiles, fc, vb, stats, stages, static_opt, parity);
+}
+void launch_mark_dirty_global(cudaStream_t st, const Rows &R) {
+    if (R.n) k_mark_dirty_global<<<cdiv(R.n, 256), 256, 0, st>>>(R);
+}
+void launch_expand_visible(cudaStream_t st, const VisibleBufs &vb, const uint32_t *row_of_rank, const FrameConsts *fc,
+                           DevStats *stats, uint32_t parity, uint32_t n_rows, uint32_t max_views) {
+    if (vb.n_chunks == 0) return;
+    k_expand_visible<<<dim3(vb.n_chunks, max_views), kChunkWords, 0, st>>>(vb, row_of_rank, fc, stats, parity, n_rows);
+}
+void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
+                           DevStats *stats, uint32_t max_views) {
+    if (L.n == 0) return;
+    k_cluster_assign<<<dim3(cdiv(L.n, 8), max_views), 256, 0, st>>>(R, L, fc, cb, stats);
+}
+void launch_cluster_lists(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, DevStats *stats, uint32_t max_views) {
+    k_cluster_lists<<<max_views, 1024, 0, st>>>(fc, cb, stats);
+}
+void launch_unpack_trs(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *src, int mark_only) {
+    if (count) k_unpack_trs<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, src, mark_only);
+}
+void launch_scatter_trs(cudaStream_t st, const Rows &R, uint32_t count, const uint32_t *rows, const float *src) {
+    if (count) k_scatter_trs<<<cdiv(count, 256), 256, 0, st>>>(R, count, rows, src);
+}
+void launch_unpack_gt(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *src) {
+    if (count) k_unpack_gt<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, src);
+}
+void launch_pack_gt(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, float *dst, uint32_t stride) {
+    if (count) k_pack_gt<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, dst, stride);
+}
+void launch_unpack_bounds(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *bounds,
+                          const uint8_t *flags, const uint8_t *cls) {
+    if (count) k_unpack_bounds<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, bounds, flags, cls);
+}
+void launch_unpack_vv(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const uint8_t *vv) {
+    if (count) k_unpack_vv<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, vv);
+}
+void launch_pack_state(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, uint8_t *out, uint32_t changed_bit) {
+    if (count) k_pack_state<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, out, changed_bit);
+}
+
+}  // namespace b200vis

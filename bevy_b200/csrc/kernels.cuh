@@ -1,0 +1,23 @@
+// kernels.cuh -- launchers of the sm_100a kernels (kernels.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include "device_types.cuh"
+
+namespace b200vis {
+void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const FrameConsts *fc,
+                           const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity);
+void launch_mark_dirty_global(cudaStream_t st, const Rows &R);
+void launch_expand_visible(cudaStream_t st, const VisibleBufs &vb, const uint32_t *row_of_rank, const FrameConsts *fc,
+                           DevStats *stats, uint32_t parity, uint32_t n_rows, uint32_t max_views);
+void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
+                           DevStats *stats, uint32_t max_views);
+void launch_cluster_lists(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, DevStats *stats, uint32_t max_views);
+void launch_unpack_trs(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *src, int mark_only);
+void launch_scatter_trs(cudaStream_t st, const Rows &R, uint32_t count, const uint32_t *rows, const float *src);
+void launch_unpack_gt(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *src);
+void launch_pack_gt(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, float *dst, uint32_t stride);
+void launch_unpack_bounds(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *bounds,
+                          const uint8_t *flags, const uint8_t *cls);
+void launch_unpack_vv(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const uint8_t *vv);
+void launch_pack_state(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, uint8_t *out, uint32_t changed_bit);
+}

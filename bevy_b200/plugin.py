@@ -1,0 +1,81 @@
+"""Host-side mirror of the reference's three systems on top of the C ABI.
+
+`VisibilityPipeline` plays the role of the `B200VisibilityPlugin` a Bevy app
+would add: it owns one device context, mirrors a scene's
+columns into it, recomputes the per-view constants each frame exactly where
+the reference does (update_frusta, the per-view prologue of
+assign_objects_to_clusters) and exposes the stages under the reference's names.
+"""
+import numpy as np
+
+from . import abi
+
+
+class VisibilityPipeline:
+    def __init__(self, scene, device=0, static_transform_optimizations=True, max_cluster_indices=0,
+                 world_size=1, rank=0, cluster_config=None):
+        self.scene = scene
+        n, L, V = scene.n, len(scene.light_row), max(len(scene.cameras), 1)
+        self.ctx = abi.Context(n, max_lights=max(L, 1), max_views=V, device=device,
+                               max_cluster_indices=max_cluster_indices, world_size=world_size, rank=rank)
+        c = self.ctx
+        c.set_static_transform_optimizations(static_transform_optimizations)
+        c.set_topology(scene.parent, scene.entity_bits)
+        c.upload_transforms(0, scene.trs)
+        identity = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32), (n, 1))
+        c.upload_global_transforms(0, identity)                       # GlobalTransform::IDENTITY at spawn
+        c.upload_bounds(0, scene.bounds, scene.flags, scene.class_mask)
+        c.upload_view_visibility(0, np.zeros(n, np.uint8))             # ViewVisibility::HIDDEN
+        c.set_lights(scene.light_row, scene.light_range)
+        self.cluster_config = cluster_config or abi.host_default_cluster_config(*scene.screen)
+        self.feedback = [abi.ClusterFeedback() for _ in range(V)]
+        self._scratch = [None] * V
+        self.cluster_views = [None] * V
+        self.update_views()
+
+    # -- update_frusta (visibility/mod.rs:627-636) + the per-view prologue of assign_objects_to_clusters
+    def update_views(self, clusters=True):
+        views = []
+        for v, cam in enumerate(self.scene.cameras):
+            cfv = abi.host_perspective(cam.fov, cam.aspect, cam.near)
+            frustum = abi.host_compute_frustum(cfv, cam.gt, cam.far)
+            views.append(abi.View.make(frustum))
+            if clusters and len(self.scene.light_row):
+                cv, scratch = abi.host_cluster_view_setup(self.cluster_config, cam.gt, cfv, frustum, 1, self.feedback[v])
+                self._scratch[v] = scratch
+                self.cluster_views[v] = cv
+                self.ctx.set_cluster_view(v, cv)
+        self.ctx.set_views(views)
+        self.views = views
+
+    # -- the three systems, by the names BASELINE.json / the reference use -----------------------
+    def propagate_transforms(self):
+        """TransformSystems::Propagate: mark_dirty_trees + propagate_parent_transforms + sync_simple_transforms."""
+        self.ctx.run(abi.STAGE_PROPAGATE)
+
+    def check_visibility(self):
+        """reset_view_visibility + check_visibility_cpu_culling + mark_newly_hidden_entities_invisible."""
+        self.ctx.run(abi.STAGE_CULL)
+
+    def assign_lights_to_clusters(self):
+        """assign_objects_to_clusters (point lights)."""
+        self.ctx.run(abi.STAGE_CLUSTER)
+
+    def run_frame(self):
+        """The fused per-frame path: one launch sequence for all three systems."""
+        self.ctx.run(abi.STAGE_ALL if len(self.scene.light_row) else (abi.STAGE_PROPAGATE | abi.STAGE_CULL))
+
+    def read_feedback(self):
+        """Clusters::last_frame_* (assign.rs:810-811): feeds next frame's far_z and dynamic resizing."""
+        s = self.ctx.download_frame_stats()
+        for v in range(len(self.scene.cameras)):
+            cv = self.cluster_views[v]
+            if cv is None or not cv.enabled:
+                continue
+            fb = self.feedback[v]
+            fb.has_farthest_z = 1; fb.farthest_z = s.cluster_farthest_z[v]
+            fb.has_index_count = 1; fb.index_count = s.cluster_index_count[v]
+        return s
+
+    def close(self):
+        self.ctx.close()

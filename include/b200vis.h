@@ -1,0 +1,257 @@
+/*
+ * b200vis.h -- C ABI of libb200vis.so: the B200-native replacement for the
+ * per-frame visibility pipeline of bevyengine/bevy 0.20.0-dev
+ * (propagate -> cull -> cluster).
+ *
+ * The reference has NO FFI seam for these stages: they are plain Rust systems.
+ * Each entry point below therefore cites the reference system / type whose
+ * work it takes over; the Rust-side binding a maintainer adds (a
+ * `B200VisibilityPlugin` calling these through `extern "C"`) is shown in
+ * INTEGRATION.md and rust/b200vis_plugin.rs.
+ *
+ * Conventions: every call returns an int32 status (0 = B200VIS_OK); no
+ * unwinding, no global state; the caller owns all host memory, the library
+ * owns all device memory; a context is thread-compatible (one caller at a
+ * time), like a Bevy system holding `ResMut`.  Plain pointers and sizes only.
+ * Rows are the caller's mirror of ECS archetype rows (one row per entity that
+ * has Transform + GlobalTransform); ranges are [first_row, first_row+count).
+ */
+#ifndef B200VIS_H
+#define B200VIS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VIS_ABI_VERSION 1
+#if defined(__GNUC__)
+#define B200VIS_API __attribute__((visibility("default")))
+#else
+#define B200VIS_API
+#endif
+
+/* ---- status codes -------------------------------------------------------- */
+enum {
+    B200VIS_OK = 0,
+    B200VIS_ERR_INVALID_ARG = 1,
+    B200VIS_ERR_CUDA = 2,            /* CUDA runtime error or no CUDA device: see b200vis_last_error */
+    B200VIS_ERR_OUT_OF_MEMORY = 3,
+    B200VIS_ERR_HIERARCHY_CYCLE = 4, /* the shim must panic!(): crates/bevy_transform/src/systems.rs:715, test :1101 */
+    B200VIS_ERR_PARENT_OUT_OF_RANGE = 5,
+    B200VIS_ERR_CAPACITY = 6,        /* more rows / lights / views / indices than the context was created for */
+    B200VIS_ERR_NOT_READY = 7,       /* a stage was run before its inputs were uploaded */
+    B200VIS_ERR_UNSUPPORTED = 8
+};
+
+/* parent_row sentinels (b200vis_set_topology) */
+#define B200VIS_NO_PARENT 0xFFFFFFFFu /* no ChildOf: a hierarchy root or a flat entity */
+#define B200VIS_DETACHED  0xFFFFFFFEu /* has ChildOf, but the parent lacks Transform/GlobalTransform: never
+                                         reached by propagation (NodeQuery, systems.rs:752-764) */
+
+/* per-row flag byte (b200vis_upload_bounds) */
+#define B200VIS_F_INHERITED_VISIBLE  0x01u /* InheritedVisibility::get() (visibility/mod.rs:164) */
+#define B200VIS_F_HAS_AABB           0x02u /* Option<&Aabb> is Some (primitives.rs:63-68) */
+#define B200VIS_F_HAS_SPHERE         0x04u /* Option<&Sphere> is Some (primitives.rs:197-211) */
+#define B200VIS_F_NO_FRUSTUM_CULLING 0x08u /* Has<NoFrustumCulling> */
+#define B200VIS_F_HAS_VIS_RANGE      0x10u /* Has<VisibilityRange> (visibility/range.rs) */
+#define B200VIS_F_NO_CPU_CULLING     0x20u /* With<NoCpuCulling>: row is outside the visibility queries */
+#define B200VIS_F_SPHERE_FROM_GT     0x40u /* Sphere.center is the row's own GlobalTransform translation, i.e. the
+                                              steady state of update_point_light_bounding_spheres
+                                              (crates/bevy_light/src/point_light.rs:195-209) */
+/* bit 0x80 is owned by the library: "Transform changed since the last propagate" */
+
+/* per-view flag byte */
+#define B200VIS_VIEW_ACTIVE          0x01u /* camera.is_active (visibility/mod.rs:780) */
+#define B200VIS_VIEW_NO_CPU_CULLING  0x02u /* Has<NoCpuCulling> on the camera (visibility/mod.rs:823) */
+
+/* stages for b200vis_run */
+#define B200VIS_STAGE_PROPAGATE      0x1u  /* TransformSystems::Propagate */
+#define B200VIS_STAGE_CULL           0x2u  /* reset_view_visibility + check_visibility_cpu_culling +
+                                              mark_newly_hidden_entities_invisible */
+#define B200VIS_STAGE_CLUSTER_ASSIGN 0x4u  /* assign_objects_to_clusters: lights -> cluster x light bitmask slab */
+#define B200VIS_STAGE_CLUSTER_LISTS  0x8u  /* bitmask (after the optional all-gather) -> ordered index lists */
+#define B200VIS_STAGE_CLUSTER        (B200VIS_STAGE_CLUSTER_ASSIGN | B200VIS_STAGE_CLUSTER_LISTS)
+#define B200VIS_STAGE_ALL            0xFu
+
+#define B200VIS_MAX_VIEWS     8u
+#define B200VIS_MAX_CLUSTERS  4096u  /* assign.rs:410-413 */
+
+typedef struct b200vis_ctx b200vis_ctx;
+
+typedef struct b200vis_config {
+    int32_t  device;              /* CUDA device ordinal */
+    uint32_t max_entities;        /* row capacity */
+    uint32_t max_lights;          /* point lights this context (this rank's shard) may hold */
+    uint32_t max_views;           /* <= B200VIS_MAX_VIEWS */
+    uint32_t max_cluster_indices; /* per-view capacity of the cluster index list (0 => 1<<20) */
+    uint32_t world_size;          /* ranks sharing the cluster exchange (0/1 => single GPU) */
+    uint32_t rank;
+    uint32_t reserved;
+} b200vis_config;
+
+/* One camera: what check_visibility_cpu_culling reads per view
+ * (view_query, crates/bevy_camera/src/visibility/mod.rs:750-757). */
+typedef struct b200vis_view {
+    float    half_spaces[6][4];   /* Frustum: normal.xyz, d; order L,R,T,B,Near,Far (view_frustum.rs:25-34) */
+    uint64_t layer_mask;          /* RenderLayers first block; default layer 0 => 1 */
+    uint8_t  flags;               /* B200VIS_VIEW_* */
+    int8_t   range_view_index;    /* bit index in VisibleEntityRanges, -1 if the view is not in it */
+    uint8_t  pad[6];
+} b200vis_view;
+
+/* Per-view constants of assign_objects_to_clusters, computed on the host exactly
+ * where the reference computes them (assign.rs:324-485); b200vis_host_cluster_view_setup
+ * fills one of these from a camera + ClusterConfig + last frame's feedback. */
+typedef struct b200vis_cluster_view {
+    uint32_t enabled;             /* 0 => clusters.clear() path (ClusterConfig::None / empty viewport) */
+    uint32_t dims[3];             /* Clusters::dimensions */
+    uint32_t tile_size[2];        /* Clusters::tile_size (reported back, unused on the device) */
+    uint32_t is_orthographic;
+    float    near_z, far_z;       /* Clusters::near / far */
+    float    cluster_factors[2];  /* calculate_cluster_factors (assign.rs:817-832) */
+    float    view_from_world[16]; /* Mat4, column major */
+    float    clip_from_view[16];
+    float    view_from_world_scale[3];
+    float    view_from_world_scale_max;
+    float    frustum[6][4];       /* the view's Frustum, all six planes are used (assign.rs:496) */
+    uint64_t layer_mask;
+    const float *x_planes;        /* [(dims.x+1)][4] HalfSpace normal_d, view space (assign.rs:455-475) */
+    const float *y_planes;        /* [(dims.y+1)][4] */
+    const float *z_planes;        /* [(dims.z+1)][4] */
+} b200vis_cluster_view;
+
+/* Small per-frame result block (one D2H copy): what the shim writes back into
+ * VisibleEntities / Clusters bookkeeping. */
+typedef struct b200vis_frame_stats {
+    uint32_t visible_count[B200VIS_MAX_VIEWS];       /* entries in each view's visible list */
+    uint32_t cluster_index_count[B200VIS_MAX_VIEWS]; /* -> Clusters::last_frame_total_cluster_index_count */
+    float    cluster_farthest_z[B200VIS_MAX_VIEWS];  /* -> Clusters::last_frame_farthest_z */
+    uint32_t cluster_index_overflow[B200VIS_MAX_VIEWS]; /* 1 if the list did not fit max_cluster_indices */
+    uint32_t gt_changed_count;                       /* rows whose Changed<GlobalTransform> fired */
+    uint32_t vv_changed_count;                       /* rows whose Changed<ViewVisibility> fired */
+    uint32_t frame;                                  /* frames run so far */
+    uint32_t pad;
+} b200vis_frame_stats;
+
+/* ---- lifetime ------------------------------------------------------------- */
+B200VIS_API int32_t b200vis_abi_version(void);
+B200VIS_API int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out);
+B200VIS_API void b200vis_destroy(b200vis_ctx *ctx);
+B200VIS_API const char *b200vis_last_error(const b200vis_ctx *ctx); /* valid until the next call on ctx; ctx may be NULL */
+/* All uploads, kernels and downloads of this context are issued on `cuda_stream`
+ * (a cudaStream_t; NULL => the context's own stream). */
+B200VIS_API int32_t b200vis_set_stream(b200vis_ctx *ctx, void *cuda_stream);
+B200VIS_API int32_t b200vis_synchronize(b200vis_ctx *ctx);
+
+/* ---- mirroring the ECS columns --------------------------------------------- */
+/* Hierarchy + identity; call on spawn/despawn/Changed<ChildOf> only.
+ * Replaces the Children/ChildOf walks of propagate_descendants_unchecked
+ * (systems.rs:679-748) with a cached execution plan.  entity_bits = Entity::to_bits()
+ * (crates/bevy_ecs/src/entity/mod.rs:468-476), which fixes the order of every
+ * visible list (visibility/mod.rs:870-874).  Rows must be in topological order
+ * (parent_row[r] < r); b200vis_plan_row_order produces such an order. */
+B200VIS_API int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n_rows, const uint32_t *parent_row,
+                             const uint64_t *entity_bits);
+/* Helper for the shim: a permutation (new_row -> old_row) that is topological and
+ * keeps every tree contiguous in BFS order (the layout the tile kernel likes). */
+B200VIS_API int32_t b200vis_plan_row_order(uint32_t n_rows, const uint32_t *parent_row, uint32_t *new_to_old);
+
+/* Transform column, dirty ranges: trs[count][10] = translation.xyz, rotation.xyzw, scale.xyz
+ * (components/transform.rs:86-105).  Marks the rows Changed<Transform>. */
+B200VIS_API int32_t b200vis_upload_transforms(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const float *trs);
+/* Same, for the scattered row set a `Changed<Transform>` query yields: rows[count], trs[count][10]. */
+B200VIS_API int32_t b200vis_upload_transforms_scattered(b200vis_ctx *ctx, uint32_t count, const uint32_t *rows,
+                                                        const float *trs);
+/* Rows that are Changed<ChildOf> | Added<GlobalTransform> | freshly orphaned without new Transform data
+ * (mark_dirty_trees' input set, systems.rs:112-113). */
+B200VIS_API int32_t b200vis_mark_transforms_changed(b200vis_ctx *ctx, uint32_t first_row, uint32_t count);
+/* GlobalTransform column as it stands on the host (initial mirror / external writes):
+ * gt[count][12] = Affine3A x_axis.xyz, y_axis.xyz, z_axis.xyz, translation.xyz */
+B200VIS_API int32_t b200vis_upload_global_transforms(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const float *gt);
+/* Aabb / Sphere / flags / VisibilityClass / RenderLayers / VisibleEntityRanges columns:
+ * bounds[count][6] = center.xyz, half_extents.xyz (Aabb) or center.xyz, radius,0,0 (Sphere);
+ * class_mask: one bit per VisibilityClass the entity is in (0 => set_visible() but no list entry,
+ * visibility/mod.rs:846-857); layer_mask / range_mask may be NULL (=> default layer / no
+ * VisibleEntityRanges resource). */
+B200VIS_API int32_t b200vis_upload_bounds(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const float *bounds,
+                              const uint8_t *flags, const uint8_t *class_mask, const uint64_t *layer_mask,
+                              const uint32_t *range_mask);
+/* ViewVisibility column (bit0 current, bit1 previous; visibility/mod.rs:226-242) */
+B200VIS_API int32_t b200vis_upload_view_visibility(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const uint8_t *vv);
+
+/* StaticTransformOptimizations resource (systems.rs:87-103); default Enabled (1). */
+B200VIS_API int32_t b200vis_set_static_transform_optimizations(b200vis_ctx *ctx, int32_t enabled);
+
+/* ---- per-frame constants ----------------------------------------------------- */
+B200VIS_API int32_t b200vis_set_views(b200vis_ctx *ctx, uint32_t n_views, const b200vis_view *views);
+/* PointLight set (point_lights_query, assign.rs:146-153): light_row = the light entity's row (its
+ * GlobalTransform translation and ViewVisibility are read on the device), in query order. */
+B200VIS_API int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, const uint32_t *light_row, const float *range,
+                           const uint64_t *layer_mask /* nullable */);
+B200VIS_API int32_t b200vis_set_cluster_view(b200vis_ctx *ctx, uint32_t view, const b200vis_cluster_view *params);
+
+/* ---- run ----------------------------------------------------------------------- */
+B200VIS_API int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages);
+
+/* ---- results --------------------------------------------------------------------- */
+B200VIS_API int32_t b200vis_download_frame_stats(b200vis_ctx *ctx, b200vis_frame_stats *out);
+/* gt[count][stride_floats] (stride 12, or 16 for glam's padded Affine3A layout); changed[count]:
+ * 1 where the shim must stamp changed_ticks (set_if_neq semantics, systems.rs:719). Either may be NULL. */
+B200VIS_API int32_t b200vis_download_global_transforms(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, float *gt,
+                                           uint32_t stride_floats, uint8_t *changed);
+B200VIS_API int32_t b200vis_download_view_visibility(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, uint8_t *vv,
+                                         uint8_t *changed);
+/* VisibleEntities of one view: rows of the visible entities that have a VisibilityClass, ascending by
+ * Entity::to_bits() (visibility/mod.rs:861-874).  An inactive view keeps last frame's list (:780-782). */
+B200VIS_API int32_t b200vis_download_visible(b200vis_ctx *ctx, uint32_t view, uint32_t *rows, uint32_t capacity,
+                                 uint32_t *count);
+/* Clusters of one view in CSR form: offsets[n_clusters+1], light ordinals (index into the
+ * b200vis_set_lights arrays; with world_size>1: global ordinal = rank-major) in the reference's
+ * push order, cluster index = (y*dims.x + x)*dims.z + z (assign.rs:676-678). */
+B200VIS_API int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, uint32_t *offsets, uint32_t *indices,
+                                  uint32_t indices_capacity, uint32_t *total);
+
+/* ---- multi-GPU cluster exchange (one all-gather per frame, done by the host's collective) ------- */
+/* Each rank fills `slab_bytes` at `send`; after all-gathering the slabs rank-major into `recv`
+ * (world_size * slab_bytes) the LISTS stage reads `recv`.  Buffers are caller-allocated device memory
+ * (e.g. torch tensors); with world_size <= 1 the library uses its own buffer and no exchange. */
+B200VIS_API int32_t b200vis_cluster_exchange_bytes(const b200vis_ctx *ctx, size_t *slab_bytes);
+B200VIS_API int32_t b200vis_set_cluster_exchange_buffers(b200vis_ctx *ctx, void *send_device, void *recv_device);
+
+/* ---- host-side mirror of the reference's per-view math (no GPU needed) --------------------------- */
+/* PerspectiveProjection::get_clip_from_view (crates/bevy_camera/src/projection.rs:339-343) */
+B200VIS_API void b200vis_host_perspective(float fov_y, float aspect, float near_z, float *clip_from_view16);
+/* CameraProjection::compute_frustum (projection.rs:72-80): camera_gt[12] as in upload_global_transforms */
+B200VIS_API void b200vis_host_compute_frustum(const float *clip_from_view16, const float *camera_gt12, float far_z,
+                                  float half_spaces[6][4]);
+
+typedef struct b200vis_cluster_config {      /* ClusterConfig + GlobalClusterSettings + viewport */
+    uint32_t kind;               /* 0 None, 1 Single, 2 XYZ, 3 FixedZ (cluster/mod.rs:107-139) */
+    uint32_t dims[3];            /* XYZ */
+    uint32_t total, z_slices;    /* FixedZ */
+    float    first_slice_depth;  /* ClusterZConfig */
+    uint32_t far_z_mode;         /* 0 MaxClusterableObjectRange, 1 Constant */
+    float    far_z_constant;
+    uint32_t dynamic_resizing;
+    uint32_t screen_w, screen_h; /* Camera::physical_viewport_size */
+    uint32_t view_cluster_bindings_max_indices;
+} b200vis_cluster_config;
+typedef struct b200vis_cluster_feedback {    /* Clusters::last_frame_* (cluster/mod.rs:155-161) */
+    uint32_t has_farthest_z;     float farthest_z;
+    uint32_t has_index_count;    uint32_t index_count;
+} b200vis_cluster_feedback;
+B200VIS_API void b200vis_host_default_cluster_config(b200vis_cluster_config *cfg, uint32_t screen_w, uint32_t screen_h);
+/* The per-view prologue of assign_objects_to_clusters (assign.rs:324-485).  planes_scratch must hold
+ * 3*4097*4 floats; out->x/y/z_planes point into it. */
+B200VIS_API int32_t b200vis_host_cluster_view_setup(const b200vis_cluster_config *cfg, const float *camera_gt12,
+                                        const float *clip_from_view16, const float frustum[6][4],
+                                        uint64_t layer_mask, const b200vis_cluster_feedback *feedback,
+                                        float *planes_scratch, b200vis_cluster_view *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VIS_H */

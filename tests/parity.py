@@ -1,0 +1,100 @@
+"""Differential harness: the CUDA path (through the C ABI) against the CPU oracle on the same scene,
+frame by frame.  Bit-exact for GlobalTransform bits, change flags, ViewVisibility bytes, visible lists
+and cluster index lists (north_star: bit-exact bits/indices; 1e-5 abs on GlobalTransform floats -- we
+hold the floats to bit equality too and report the max abs difference if that ever fails)."""
+import numpy as np
+
+import bevy_b200 as bb
+from bevy_b200 import scenes
+import oracle as orc
+
+IDENTITY = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32)
+
+
+class OracleWorld:
+    """The reference-side world state for one scene, advanced by the oracle."""
+
+    def __init__(self, scene, static_opt=True):
+        self.scene = scene
+        n = scene.n
+        self.gt = np.tile(IDENTITY, (n, 1))
+        self.vv = np.zeros(n, np.uint8)
+        self.tchanged = np.ones(n, np.uint8)     # Added<GlobalTransform> on the first frame
+        self.static_opt = static_opt
+        self.fb = [dict(far=None, cnt=None) for _ in scene.cameras]
+
+    def frame(self, views_planes, view_flags=None, cluster=True, mt=False):
+        sc = self.scene
+        rc, gt_changed = orc.propagate(sc.parent, sc.trs, self.gt, self.tchanged, self.static_opt, mt=mt)
+        assert rc == 0
+        self.tchanged[:] = 0
+        vv_changed, lists = orc.cull(self.gt, sc.bounds, sc.flags, sc.class_mask, sc.entity_bits, self.vv,
+                                     views_planes, view_flags=view_flags, mt=mt)
+        clusters = []
+        if cluster and len(sc.light_row):
+            vis = np.nonzero(self.vv[sc.light_row] & 1)[0]
+            lights = np.concatenate([self.gt[sc.light_row[vis], 9:12], sc.light_range[vis, None]], 1).astype(np.float32)
+            for v, cam in enumerate(sc.cameras):
+                cfv = orc.perspective(cam.fov, cam.aspect, cam.near)
+                vin = orc.default_cluster_view_in(cam.gt, cfv, views_planes[v], screen=sc.screen,
+                                                  last_farthest_z=self.fb[v]["far"], last_index_count=self.fb[v]["cnt"])
+                out, offsets, idx, _ = orc.assign_lights_to_clusters(vin, lights)
+                self.fb[v]["far"] = out.farthest_z; self.fb[v]["cnt"] = out.total_index_count
+                clusters.append((out, offsets, vis[idx].astype(np.uint32)))
+        return gt_changed, vv_changed, lists, clusters
+
+
+def compare_frame(pipe, world, frame_no, cluster=True, check_gt=True):
+    sc = pipe.scene
+    n = sc.n
+    planes = np.stack([np.ctypeslib.as_array(v.half_spaces).reshape(6, 4).copy() for v in pipe.views])
+    gt_changed, vv_changed, lists, clusters = world.frame(planes, cluster=cluster)
+    pipe.run_frame()
+    tag = f"[{sc.name} frame {frame_no}]"
+    if check_gt:
+        gt, ch = pipe.ctx.download_global_transforms(0, n)
+        same = gt.view(np.uint32) == world.gt.view(np.uint32)
+        if not same.all():
+            bad = np.nonzero(~same.all(1))[0]
+            raise AssertionError(f"{tag} GlobalTransform bits differ on {len(bad)} rows (first {bad[:5]}), "
+                                 f"max abs diff {np.nanmax(np.abs(gt - world.gt))}")
+        assert (ch == gt_changed).all(), f"{tag} Changed<GlobalTransform> differs on {np.nonzero(ch != gt_changed)[0][:8]}"
+    vv, vch = pipe.ctx.download_view_visibility(0, n)
+    assert (vv == world.vv).all(), f"{tag} ViewVisibility differs on rows {np.nonzero(vv != world.vv)[0][:8]}"
+    assert (vch == vv_changed).all(), f"{tag} Changed<ViewVisibility> differs on rows {np.nonzero(vch != vv_changed)[0][:8]}"
+    for v in range(len(sc.cameras)):
+        got = pipe.ctx.download_visible(v)
+        want = lists[v]
+        assert want is not None
+        assert len(got) == len(want) and (got == want).all(), f"{tag} view {v}: visible list differs ({len(got)} vs {len(want)})"
+    stats = pipe.read_feedback()
+    if cluster and len(sc.light_row):
+        for v in range(len(sc.cameras)):
+            out, offsets, idx = clusters[v]
+            cv = pipe.cluster_views[v]
+            assert tuple(cv.dims) == tuple(out.dims), f"{tag} view {v}: cluster dims {tuple(cv.dims)} vs {tuple(out.dims)}"
+            goff, gidx = pipe.ctx.download_clusters(v)
+            nc = out.dims[0] * out.dims[1] * out.dims[2]
+            assert (goff[:nc + 1] == offsets).all(), f"{tag} view {v}: cluster offsets differ"
+            assert len(gidx) == len(idx) and (gidx == idx).all(), f"{tag} view {v}: cluster index lists differ"
+            assert stats.cluster_index_count[v] == out.total_index_count
+            assert np.float32(stats.cluster_farthest_z[v]).view(np.uint32) == np.float32(out.farthest_z).view(np.uint32), \
+                f"{tag} view {v}: farthest_z {stats.cluster_farthest_z[v]} vs {out.farthest_z}"
+    return stats
+
+
+def run_parity(scene, frames=3, static_opt=True, animate=True, cluster=True):
+    pipe = bb.VisibilityPipeline(scene, static_transform_optimizations=static_opt)
+    world = OracleWorld(scene, static_opt)
+    try:
+        for f in range(frames):
+            if f > 0 and animate:
+                scenes.advance_cameras(scene)
+                if scene.roots is not None and len(scene.roots):
+                    rows, trs = scenes.mutate_roots(scene, f)
+                    pipe.ctx.upload_transforms_scattered(rows, trs)
+                    world.tchanged[rows] = 1
+            pipe.update_views(clusters=cluster)
+            compare_frame(pipe, world, f, cluster=cluster)
+    finally:
+        pipe.close()
