@@ -100,6 +100,10 @@ _SIGNATURES = {
     "b200vis_set_views": (C.c_int32, [_vp, C.c_uint32, _P(View)]),
     "b200vis_set_lights": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, _vp]),
     "b200vis_set_cluster_view": (C.c_int32, [_vp, C.c_uint32, _P(ClusterView)]),
+    "b200vis_snapshot_frame_constants": (C.c_int32, [_vp, _vp, C.c_size_t, _P(C.c_size_t)]),
+    "b200vis_use_frame_constants": (C.c_int32, [_vp, _vp]),
+    "b200vis_set_profiling": (C.c_int32, [_vp, C.c_int32]),
+    "b200vis_last_stage_times_ms": (C.c_int32, [_vp, _P(C.c_float), _P(C.c_float), _P(C.c_float)]),
     "b200vis_run": (C.c_int32, [_vp, C.c_uint32]),
     "b200vis_download_frame_stats": (C.c_int32, [_vp, _P(FrameStats)]),
     "b200vis_download_global_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, _vp]),
@@ -274,6 +278,22 @@ class Context:
 
     def set_cluster_view(self, view, cluster_view):
         self._check(self._lib.b200vis_set_cluster_view(self._h, view, C.byref(cluster_view)))
+
+    def snapshot_frame_constants(self, device_ptr, capacity):
+        n = C.c_size_t(0)
+        self._check(self._lib.b200vis_snapshot_frame_constants(self._h, _vp(device_ptr), capacity, C.byref(n)))
+        return n.value
+
+    def use_frame_constants(self, device_ptr):
+        self._check(self._lib.b200vis_use_frame_constants(self._h, _vp(device_ptr) if device_ptr else None))
+
+    def set_profiling(self, enabled):
+        self._check(self._lib.b200vis_set_profiling(self._h, int(bool(enabled))))
+
+    def last_stage_times_ms(self):
+        a, b_, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        self._check(self._lib.b200vis_last_stage_times_ms(self._h, C.byref(a), C.byref(b_), C.byref(c)))
+        return a.value, b_.value, c.value
 
     def run(self, stages=STAGE_ALL):
         self._check(self._lib.b200vis_run(self._h, stages))

@@ -43,12 +43,24 @@ struct b200vis_ctx {
     int static_opt = 1;
 
     // per-frame constants
-    FrameConsts *h_consts = nullptr;    // pinned
-    FrameConsts *d_consts = nullptr;
+    // The "frame blob": FrameConsts followed by the packed per-view plane tables and z thresholds.
+    // Setters edit the host working copy; run() packs it into the next pinned ring slot and issues
+    // ONE async H2D copy, so per-frame constant updates never block on the stream.
+    FrameConsts consts{};               // host working copy
+    std::vector<float> tab_x[kMaxViews], tab_y[kMaxViews], tab_z[kMaxViews], tab_thr[kMaxViews];
+    static constexpr int kRing = 4;
+    uint8_t *h_ring[kRing] = {nullptr, nullptr, nullptr, nullptr};   // pinned
+    cudaEvent_t ring_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    int ring_next = 0;
+    size_t blob_cap = 0;
+    uint8_t *d_blob = nullptr;
+    FrameConsts *d_consts = nullptr;    // == d_blob
     bool consts_dirty = true;
-    float4 *d_xplanes = nullptr, *d_yplanes = nullptr, *d_zplanes = nullptr; float *d_zthr = nullptr;
-    float *h_planes = nullptr;          // pinned staging: [3][4097*4] + thresholds [4096] per upload
-    b200vis_cluster_view cview_host[kMaxViews]{};
+    size_t blob_used = 0;               // bytes of the last packed blob
+    const uint8_t *ext_blob = nullptr;  // caller-owned device blob (b200vis_use_frame_constants)
+    // optional per-stage timing (b200vis_set_profiling)
+    bool profiling = false;
+    cudaEvent_t prof_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // visible set
     VisibleBufs vis{};
@@ -99,12 +111,15 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     Rows &r = ctx->rows;
     void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
-                   ctx->d_tiles, ctx->d_consts, ctx->d_xplanes, ctx->d_yplanes, ctx->d_zplanes, ctx->d_zthr,
+                   ctx->d_tiles, ctx->d_blob,
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage};
     for (void *p : dev) if (p) cudaFree(p);
-    if (ctx->h_consts) cudaFreeHost(ctx->h_consts);
-    if (ctx->h_planes) cudaFreeHost(ctx->h_planes);
+    for (int i = 0; i < b200vis_ctx::kRing; ++i) {
+        if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
+        if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
+    }
+    for (cudaEvent_t e : ctx->prof_ev) if (e) cudaEventDestroy(e);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -144,12 +159,15 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         ctx->tiles_cap = (uint32_t)(N / 1 + 1);   // worst case one tile per row is never reached; see planner
         ctx->tiles_cap = (uint32_t)std::min<size_t>(N + 1, (N / 8) + 1024);
         CU(dalloc(&ctx->d_tiles, ctx->tiles_cap));
-        CU(cudaMallocHost(&ctx->h_consts, sizeof(FrameConsts)));
-        memset(ctx->h_consts, 0, sizeof(FrameConsts));
-        CU(dalloc(&ctx->d_consts, 1));
-        CU(dalloc(&ctx->d_xplanes, V * (kMaxClusters + 1))); CU(dalloc(&ctx->d_yplanes, V * (kMaxClusters + 1)));
-        CU(dalloc(&ctx->d_zplanes, V * (kMaxClusters + 1))); CU(dalloc(&ctx->d_zthr, V * kMaxClusters));
-        CU(cudaMallocHost(&ctx->h_planes, (3 * (kMaxClusters + 1) * 4 + kMaxClusters) * sizeof(float) * V));
+        // worst case tables: every view with three (kMaxClusters+1)-entry plane tables + kMaxClusters thresholds
+        ctx->blob_cap = sizeof(FrameConsts) + V * (3 * (size_t)(kMaxClusters + 1) * 16 + (size_t)kMaxClusters * 4);
+        CU(dalloc(&ctx->d_blob, ctx->blob_cap));
+        ctx->d_consts = reinterpret_cast<FrameConsts *>(ctx->d_blob);
+        for (int i = 0; i < b200vis_ctx::kRing; ++i) {
+            CU(cudaMallocHost(&ctx->h_ring[i], ctx->blob_cap));
+            CU(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+        }
+        for (cudaEvent_t &e : ctx->prof_ev) CU(cudaEventCreate(&e));
         // visible set buffers
         VisibleBufs &vb = ctx->vis;
         vb.words_stride = (uint32_t)((N + 31) / 32 + 2);
@@ -169,7 +187,7 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         ctx->slab_bytes = (size_t)V * cl.words * kMaxClusters * sizeof(uint32_t);
         CU(dalloc(&ctx->d_slab, ctx->slab_bytes / 4));
         cl.send = ctx->d_slab; cl.recv = ctx->d_slab;
-        cl.xplanes = ctx->d_xplanes; cl.yplanes = ctx->d_yplanes; cl.zplanes = ctx->d_zplanes; cl.zthr = ctx->d_zthr;
+        cl.blob = reinterpret_cast<const float *>(ctx->d_blob);
         CU(dalloc(&cl.offsets, V * (kMaxClusters + 1)));
         CU(dalloc(&cl.indices, V * (size_t)cl.index_cap));
         ctx->stage_bytes = std::max<size_t>(N, 1) * 64;
@@ -371,7 +389,7 @@ extern "C" int32_t b200vis_plan_row_order(uint32_t n, const uint32_t *parent, ui
 // ------------------------------------------------------------------------------------------
 static int32_t stage_in(b200vis_ctx *ctx, const void *src, size_t bytes, size_t offset) {
     if (offset + bytes > ctx->stage_bytes) return fail(ctx, B200VIS_ERR_CAPACITY, "staging buffer too small");
-    CU(cudaMemcpyAsync(ctx->d_stage + offset, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_stage + offset, src, bytes, cudaMemcpyDefault, ctx->stream));   // host or device source (UVA)
     return B200VIS_OK;
 }
 
@@ -461,9 +479,7 @@ extern "C" int32_t b200vis_set_views(b200vis_ctx *ctx, uint32_t n_views, const b
     if (!ctx) return B200VIS_ERR_INVALID_ARG;
     if (n_views > ctx->cfg.max_views) return fail(ctx, B200VIS_ERR_CAPACITY, "set_views: %u > max_views %u", n_views, ctx->cfg.max_views);
     if (n_views && !views) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_views: null");
-    FrameConsts &fc = *ctx->h_consts;
-    // h_consts is pinned and read by an async copy: make sure the previous copy has been consumed
-    cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+    FrameConsts &fc = ctx->consts;
     fc.n_views = n_views;
     for (uint32_t v = 0; v < n_views; ++v) {
         DevView &d = fc.views[v];
@@ -490,13 +506,11 @@ extern "C" int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, const
 }
 
 extern "C" int32_t b200vis_set_cluster_view(b200vis_ctx *ctx, uint32_t view, const b200vis_cluster_view *p) {
-    CHECK_CTX();
+    if (!ctx) return B200VIS_ERR_INVALID_ARG;
     if (view >= ctx->cfg.max_views || !p) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_cluster_view: bad view %u", view);
-    CU(cudaStreamSynchronize(ctx->stream));   // pinned staging reuse
-    FrameConsts &fc = *ctx->h_consts;
-    DevClusterView &d = fc.cviews[view];
+    DevClusterView &d = ctx->consts.cviews[view];
     memset(&d, 0, sizeof d);
-    ctx->cview_host[view] = *p;
+    ctx->tab_x[view].clear(); ctx->tab_y[view].clear(); ctx->tab_z[view].clear(); ctx->tab_thr[view].clear();
     d.enabled = p->enabled;
     if (p->enabled) {
         const uint64_t nc = (uint64_t)p->dims[0] * p->dims[1] * p->dims[2];
@@ -507,21 +521,73 @@ extern "C" int32_t b200vis_set_cluster_view(b200vis_ctx *ctx, uint32_t view, con
         memcpy(d.vfw, p->view_from_world, sizeof d.vfw); memcpy(d.cfv, p->clip_from_view, sizeof d.cfv);
         memcpy(d.scale, p->view_from_world_scale, sizeof d.scale); d.scale_max = p->view_from_world_scale_max;
         memcpy(d.frustum, p->frustum, sizeof d.frustum); d.layer_mask = p->layer_mask;
-        const size_t per_view = 3 * (kMaxClusters + 1) * 4 + kMaxClusters;
-        float *hp = ctx->h_planes + per_view * view;
-        float *hx = hp, *hy = hp + (kMaxClusters + 1) * 4, *hz = hp + 2 * (kMaxClusters + 1) * 4, *ht = hp + 3 * (kMaxClusters + 1) * 4;
-        memcpy(hx, p->x_planes, (size_t)(p->dims[0] + 1) * 16);
-        memcpy(hy, p->y_planes, (size_t)(p->dims[1] + 1) * 16);
-        memcpy(hz, p->z_planes, (size_t)(p->dims[2] + 1) * 16);
-        host::z_slice_thresholds(p->cluster_factors, p->dims[2], p->is_orthographic != 0, ht);
-        cudaStream_t st = ctx->stream;
-        CU(cudaMemcpyAsync(ctx->d_xplanes + (size_t)view * (kMaxClusters + 1), hx, (size_t)(p->dims[0] + 1) * 16, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_yplanes + (size_t)view * (kMaxClusters + 1), hy, (size_t)(p->dims[1] + 1) * 16, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_zplanes + (size_t)view * (kMaxClusters + 1), hz, (size_t)(p->dims[2] + 1) * 16, cudaMemcpyHostToDevice, st));
-        if (p->dims[2] > 1)
-            CU(cudaMemcpyAsync(ctx->d_zthr + (size_t)view * kMaxClusters, ht, (size_t)(p->dims[2] - 1) * 4, cudaMemcpyHostToDevice, st));
+        ctx->tab_x[view].assign(p->x_planes, p->x_planes + (size_t)(p->dims[0] + 1) * 4);
+        ctx->tab_y[view].assign(p->y_planes, p->y_planes + (size_t)(p->dims[1] + 1) * 4);
+        ctx->tab_z[view].assign(p->z_planes, p->z_planes + (size_t)(p->dims[2] + 1) * 4);
+        // view_z_to_z_slice through exact thresholds found with the host's libm (host_view.cpp)
+        ctx->tab_thr[view].assign(((size_t)p->dims[2] + 3) & ~(size_t)3, NAN);
+        host::z_slice_thresholds(p->cluster_factors, p->dims[2], p->is_orthographic != 0, ctx->tab_thr[view].data());
     }
     ctx->consts_dirty = true;
+    return B200VIS_OK;
+}
+
+// Packs the working copy into the next pinned ring slot and issues one async copy.
+static int32_t flush_consts(b200vis_ctx *ctx) {
+    if (!ctx->consts_dirty) return B200VIS_OK;
+    const int slot = ctx->ring_next;
+    ctx->ring_next = (slot + 1) % b200vis_ctx::kRing;
+    CU(cudaEventSynchronize(ctx->ring_ev[slot]));   // the copy issued kRing frames ago has long finished
+    uint8_t *h = ctx->h_ring[slot];
+    size_t off = (sizeof(FrameConsts) + 15) & ~(size_t)15;   // bytes; tables are float4 aligned
+    for (uint32_t v = 0; v < ctx->consts.n_views && v < ctx->cfg.max_views; ++v) {
+        DevClusterView &d = ctx->consts.cviews[v];
+        if (!d.enabled) continue;
+        std::vector<float> *tabs[4] = {&ctx->tab_x[v], &ctx->tab_y[v], &ctx->tab_z[v], &ctx->tab_thr[v]};
+        uint32_t *offs[4] = {&d.x_off, &d.y_off, &d.z_off, &d.thr_off};
+        for (int k = 0; k < 4; ++k) {
+            *offs[k] = (uint32_t)(off / 4);
+            memcpy(h + off, tabs[k]->data(), tabs[k]->size() * 4);
+            off += (tabs[k]->size() * 4 + 15) & ~(size_t)15;
+        }
+    }
+    memcpy(h, &ctx->consts, sizeof(FrameConsts));
+    CU(cudaMemcpyAsync(ctx->d_blob, h, off, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+    ctx->blob_used = off;
+    ctx->consts_dirty = false;
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_snapshot_frame_constants(b200vis_ctx *ctx, void *device_dst, size_t capacity, size_t *bytes) {
+    CHECK_CTX();
+    const int32_t rc = flush_consts(ctx); if (rc) return rc;
+    if (bytes) *bytes = ctx->blob_used;
+    if (device_dst) {
+        if (ctx->blob_used > capacity) return fail(ctx, B200VIS_ERR_CAPACITY, "snapshot_frame_constants: %zu > capacity %zu", ctx->blob_used, capacity);
+        CU(cudaMemcpyAsync(device_dst, ctx->d_blob, ctx->blob_used, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_use_frame_constants(b200vis_ctx *ctx, const void *device_blob) {
+    if (!ctx) return B200VIS_ERR_INVALID_ARG;
+    ctx->ext_blob = static_cast<const uint8_t *>(device_blob);
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_set_profiling(b200vis_ctx *ctx, int32_t enabled) {
+    if (!ctx) return B200VIS_ERR_INVALID_ARG;
+    ctx->profiling = enabled != 0;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_last_stage_times_ms(b200vis_ctx *ctx, float *tile_ms, float *expand_ms, float *cluster_ms) {
+    CHECK_CTX();
+    if (!ctx->profiling) return fail(ctx, B200VIS_ERR_NOT_READY, "profiling is off");
+    CU(cudaEventSynchronize(ctx->prof_ev[3]));
+    float t = 0;
+    if (tile_ms) { CU(cudaEventElapsedTime(&t, ctx->prof_ev[0], ctx->prof_ev[1])); *tile_ms = t; }
+    if (expand_ms) { CU(cudaEventElapsedTime(&t, ctx->prof_ev[1], ctx->prof_ev[2])); *expand_ms = t; }
+    if (cluster_ms) { CU(cudaEventElapsedTime(&t, ctx->prof_ev[2], ctx->prof_ev[3])); *cluster_ms = t; }
     return B200VIS_OK;
 }
 
@@ -553,10 +619,12 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     if (!ctx->topology_set) return fail(ctx, B200VIS_ERR_NOT_READY, "run: b200vis_set_topology has not been called");
     if ((stages & B200VIS_STAGE_CULL) && !ctx->bounds_set) return fail(ctx, B200VIS_ERR_NOT_READY, "run: bounds/flags were never uploaded");
     cudaStream_t st = ctx->stream;
-    if (ctx->consts_dirty) {
-        CU(cudaMemcpyAsync(ctx->d_consts, ctx->h_consts, sizeof(FrameConsts), cudaMemcpyHostToDevice, st));
-        ctx->consts_dirty = false;
-    }
+    const FrameConsts *fc = ctx->d_consts;
+    ClusterBufs cl = ctx->cl;
+    if (ctx->ext_blob) {   // constants already resident in HBM (recorded earlier): no host work, no copy
+        fc = reinterpret_cast<const FrameConsts *>(ctx->ext_blob);
+        cl.blob = reinterpret_cast<const float *>(ctx->ext_blob);
+    } else { const int32_t rc = flush_consts(ctx); if (rc) return rc; }
     Rows R = ctx->rows;
     R.layers = ctx->have_layers ? ctx->d_layers : nullptr;
     R.range = ctx->have_range ? ctx->d_range : nullptr;
@@ -571,22 +639,26 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         launch_mark_dirty_global(st, R);
     }
     const uint32_t parity = ctx->parity;
+    if (ctx->profiling) CU(cudaEventRecord(ctx->prof_ev[0], st));
     if (do_prop || do_cull) {
         const uint32_t tile_stages = (do_prop ? 1u : 0u) | (do_cull ? 2u : 0u);
         if (do_prop) {
             for (uint32_t p = 0; p < n_pass; ++p)
                 launch_propagate_cull(st, R, ctx->d_tiles + ctx->pass_begin[p], ctx->pass_begin[p + 1] - ctx->pass_begin[p],
-                                      ctx->d_consts, ctx->vis, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, parity);
+                                      fc, ctx->vis, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, parity);
         } else if (n_pass) {
-            launch_propagate_cull(st, R, ctx->d_tiles, ctx->pass_begin[n_pass], ctx->d_consts, ctx->vis, ctx->d_stats,
+            launch_propagate_cull(st, R, ctx->d_tiles, ctx->pass_begin[n_pass], fc, ctx->vis, ctx->d_stats,
                                   tile_stages, 0, parity);
         }
     }
-    if (do_cull) launch_expand_visible(st, ctx->vis, R.row_of_rank, ctx->d_consts, ctx->d_stats, parity, ctx->n, ctx->cfg.max_views);
+    if (ctx->profiling) CU(cudaEventRecord(ctx->prof_ev[1], st));
+    if (do_cull) launch_expand_visible(st, ctx->vis, R.row_of_rank, fc, ctx->d_stats, parity, ctx->n, ctx->cfg.max_views);
+    if (ctx->profiling) CU(cudaEventRecord(ctx->prof_ev[2], st));
     if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
-        launch_cluster_assign(st, R, ctx->lights, ctx->d_consts, ctx->cl, ctx->d_stats, ctx->cfg.max_views);
+        launch_cluster_assign(st, R, ctx->lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if (stages & B200VIS_STAGE_CLUSTER_LISTS)
-        launch_cluster_lists(st, ctx->d_consts, ctx->cl, ctx->d_stats, ctx->cfg.max_views);
+        launch_cluster_lists(st, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+    if (ctx->profiling) CU(cudaEventRecord(ctx->prof_ev[3], st));
     CU(cudaGetLastError());
     if (do_cull) { ctx->frame++; ctx->parity ^= 1u; }
     return B200VIS_OK;
@@ -660,7 +732,7 @@ extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, ui
                                              uint32_t indices_capacity, uint32_t *total) {
     CHECK_CTX();
     if (view >= ctx->cfg.max_views || !offsets || !total) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_clusters: bad argument");
-    const DevClusterView &cv = ctx->h_consts->cviews[view];
+    const DevClusterView &cv = ctx->consts.cviews[view];
     const uint32_t nc = cv.enabled ? cv.n_clusters : 0;
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(offsets, ctx->cl.offsets + (size_t)view * (kMaxClusters + 1), (size_t)(nc + 1) * 4, cudaMemcpyDeviceToHost, st));

@@ -54,14 +54,15 @@ struct DevView {
 };
 
 struct DevClusterView {
-    uint32_t enabled, dims[3], is_ortho, n_clusters, pad0, pad1;
+    uint32_t enabled, dims[3], is_ortho, n_clusters;
+    uint32_t x_off, y_off;   // offsets (in floats) of the plane tables inside the frame blob
     float vfw[16];           // view_from_world, column major
     float cfv[16];           // clip_from_view
     float scale[3];          // view_from_world_scale
     float scale_max;
     float4 frustum[6];
     unsigned long long layer_mask;
-    unsigned long long pad2;
+    uint32_t z_off, thr_off; // z plane table, z-slice thresholds on u = -view_z
 };
 
 struct FrameConsts {
@@ -108,10 +109,7 @@ struct ClusterBufs {
     uint32_t index_cap;      // per view
     uint32_t *send;          // this rank's slab: [V][words][kMaxClusters]
     const uint32_t *recv;    // gathered: [world][V][words][kMaxClusters]
-    const float4 *xplanes;   // [V][4097]
-    const float4 *yplanes;
-    const float4 *zplanes;
-    const float *zthr;       // [V][4096]: thresholds on u = -view_z
+    const float *blob;       // frame blob base: FrameConsts, then the packed per-view tables
     uint32_t *offsets;       // [V][kMaxClusters+1]
     uint32_t *indices;       // [V][index_cap]
 };

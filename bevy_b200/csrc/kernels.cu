@@ -402,7 +402,7 @@ k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBu
     for (int k = 0; k < 6; ++k)                                         // frustum.intersects_sphere(.., true)
         if (plane_dot_point(cv.frustum[k], px, py, pz) + range <= 0.0f) return;
 
-    const float *thr = cb.zthr + (size_t)v * kMaxClusters;
+    const float *thr = cb.blob + cv.thr_off;
     const bool ortho = cv.is_ortho;
     // cluster_space_clusterable_object_aabb (assign.rs:948-1036)
     const float4 vc = mat4_mul_point(cv.vfw, px, py, pz);
@@ -440,9 +440,9 @@ k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBu
     else if (ndy < -1.0f) { has_yc = true; yc = cv.dims[1] + 1; }
     else { has_yc = true; yc = ccl.y; }
 
-    const float4 *xp = cb.xplanes + (size_t)v * (kMaxClusters + 1);
-    const float4 *yp = cb.yplanes + (size_t)v * (kMaxClusters + 1);
-    const float4 *zp = cb.zplanes + (size_t)v * (kMaxClusters + 1);
+    const float4 *xp = reinterpret_cast<const float4 *>(cb.blob + cv.x_off);
+    const float4 *yp = reinterpret_cast<const float4 *>(cb.blob + cv.y_off);
+    const float4 *zp = reinterpret_cast<const float4 *>(cb.blob + cv.z_off);
     uint32_t *mask = cb.send + ((size_t)v * cb.words + (li >> 5)) * kMaxClusters;
     const uint32_t bit = 1u << (li & 31u);
     const uint32_t ny = hi.y - lo.y + 1, npairs = (hi.z - lo.z + 1) * ny;

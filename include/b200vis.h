@@ -193,6 +193,18 @@ B200VIS_API int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, cons
                            const uint64_t *layer_mask /* nullable */);
 B200VIS_API int32_t b200vis_set_cluster_view(b200vis_ctx *ctx, uint32_t view, const b200vis_cluster_view *params);
 
+/* Frame constants kept in HBM: snapshot packs the current views / cluster views (one blob, `bytes` long) into
+ * caller-owned device memory; use_frame_constants makes b200vis_run read that blob instead of uploading the
+ * host copy (NULL returns to the normal path).  Lets a recorded frame sequence replay with no host work. */
+B200VIS_API int32_t b200vis_snapshot_frame_constants(b200vis_ctx *ctx, void *device_dst, size_t capacity, size_t *bytes);
+B200VIS_API int32_t b200vis_use_frame_constants(b200vis_ctx *ctx, const void *device_blob);
+
+/* Optional per-stage device timing: when on, b200vis_run brackets its stages with CUDA events on the
+ * context's stream; b200vis_last_stage_times_ms waits for the last run and returns the durations of the
+ * tile kernel(s) (propagate+cull), the visible-list expansion and the cluster kernels. */
+B200VIS_API int32_t b200vis_set_profiling(b200vis_ctx *ctx, int32_t enabled);
+B200VIS_API int32_t b200vis_last_stage_times_ms(b200vis_ctx *ctx, float *tile_ms, float *expand_ms, float *cluster_ms);
+
 /* ---- run ----------------------------------------------------------------------- */
 B200VIS_API int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages);
 

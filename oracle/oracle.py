@@ -131,6 +131,16 @@ def _declare(l):
 
 
 FP = C.POINTER(C.c_float)
+_SCRATCH = {}
+
+
+def _scratch(name, shape, dtype):
+    """Reusable output buffers, so timing the oracle does not time numpy allocations."""
+    key = (name, tuple(shape), np.dtype(dtype).str)
+    buf = _SCRATCH.get(key)
+    if buf is None:
+        buf = _SCRATCH[key] = np.zeros(shape, dtype)
+    return buf
 
 
 # ---- small helpers ---------------------------------------------------------
@@ -246,7 +256,7 @@ def cull(gt, bounds, flags, class_mask, entity_bits, vv, view_planes, view_layer
     if view_range_index is not None:
         view_range_index = np.ascontiguousarray(view_range_index, np.int8)
     vv_changed = np.zeros(n, np.uint8)
-    rows = np.zeros((V, max(n, 1)), np.uint32)
+    rows = _scratch("cull_rows", (V, max(n, 1)), np.uint32)      # reused across calls: no per-frame 16 MB allocation
     counts = np.zeros(V, np.uint32)
     l = lib_mt() if mt else lib()
     fn = l.orc_cull_mt if mt else l.orc_cull
@@ -300,8 +310,8 @@ def assign_lights_to_clusters(view_in, lights, light_layers=None, indices_cap=No
     offsets = np.zeros(4097, np.uint32)
     cap = indices_cap if indices_cap is not None else max(4096 * max(L, 1), 1)
     cap = min(cap, 1 << 28)
-    indices = np.zeros(cap, np.uint32)
-    xp = np.zeros((4098, 4), np.float32); yp = np.zeros((4098, 4), np.float32); zp = np.zeros((4098, 4), np.float32)
+    indices = _scratch("cluster_indices", (cap,), np.uint32)
+    xp = _scratch("xp", (4098, 4), np.float32); yp = _scratch("yp", (4098, 4), np.float32); zp = _scratch("zp", (4098, 4), np.float32)
     rc = lib().orc_assign_lights_to_clusters(C.byref(view_in), L, _p(lights, C.c_float), _p(light_layers, C.c_uint64),
                                              C.byref(out), _p(offsets, C.c_uint32), _p(indices, C.c_uint32), cap,
                                              _p(xp, C.c_float), _p(yp, C.c_float), _p(zp, C.c_float))
