@@ -103,7 +103,7 @@ _SIGNATURES = {
     "b200vis_snapshot_frame_constants": (C.c_int32, [_vp, _vp, C.c_size_t, _P(C.c_size_t)]),
     "b200vis_use_frame_constants": (C.c_int32, [_vp, _vp]),
     "b200vis_set_profiling": (C.c_int32, [_vp, C.c_int32]),
-    "b200vis_last_stage_times_ms": (C.c_int32, [_vp, _P(C.c_float), _P(C.c_float), _P(C.c_float)]),
+    "b200vis_collect_stage_times_ms": (C.c_int32, [_vp, _P(C.c_float), _P(C.c_float), _P(C.c_float), _P(C.c_uint32)]),
     "b200vis_run": (C.c_int32, [_vp, C.c_uint32]),
     "b200vis_download_frame_stats": (C.c_int32, [_vp, _P(FrameStats)]),
     "b200vis_download_global_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, _vp]),
@@ -290,10 +290,11 @@ class Context:
     def set_profiling(self, enabled):
         self._check(self._lib.b200vis_set_profiling(self._h, int(bool(enabled))))
 
-    def last_stage_times_ms(self):
-        a, b_, c = C.c_float(0), C.c_float(0), C.c_float(0)
-        self._check(self._lib.b200vis_last_stage_times_ms(self._h, C.byref(a), C.byref(b_), C.byref(c)))
-        return a.value, b_.value, c.value
+    def collect_stage_times_ms(self):
+        """(tile_ms, expand_ms, cluster_ms, frames): sums over the runs recorded since the last collect."""
+        a, b_, c, n = C.c_float(0), C.c_float(0), C.c_float(0), C.c_uint32(0)
+        self._check(self._lib.b200vis_collect_stage_times_ms(self._h, C.byref(a), C.byref(b_), C.byref(c), C.byref(n)))
+        return a.value, b_.value, c.value, n.value
 
     def run(self, stages=STAGE_ALL):
         self._check(self._lib.b200vis_run(self._h, stages))

@@ -60,7 +60,9 @@ struct b200vis_ctx {
     const uint8_t *ext_blob = nullptr;  // caller-owned device blob (b200vis_use_frame_constants)
     // optional per-stage timing (b200vis_set_profiling)
     bool profiling = false;
-    cudaEvent_t prof_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kProfFrames = 256;
+    cudaEvent_t (*prof_ev)[4] = nullptr;   // [kProfFrames][4], created on first use
+    int prof_count = 0;
 
     // visible set
     VisibleBufs vis{};
@@ -119,7 +121,10 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
         if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
         if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
     }
-    for (cudaEvent_t e : ctx->prof_ev) if (e) cudaEventDestroy(e);
+    if (ctx->prof_ev) {
+        for (int i = 0; i < b200vis_ctx::kProfFrames; ++i) for (cudaEvent_t e : ctx->prof_ev[i]) if (e) cudaEventDestroy(e);
+        delete[] ctx->prof_ev;
+    }
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -167,7 +172,6 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
             CU(cudaMallocHost(&ctx->h_ring[i], ctx->blob_cap));
             CU(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
         }
-        for (cudaEvent_t &e : ctx->prof_ev) CU(cudaEventCreate(&e));
         // visible set buffers
         VisibleBufs &vb = ctx->vis;
         vb.words_stride = (uint32_t)((N + 31) / 32 + 2);
@@ -576,18 +580,27 @@ extern "C" int32_t b200vis_use_frame_constants(b200vis_ctx *ctx, const void *dev
 }
 
 extern "C" int32_t b200vis_set_profiling(b200vis_ctx *ctx, int32_t enabled) {
-    if (!ctx) return B200VIS_ERR_INVALID_ARG;
+    CHECK_CTX();
+    if (enabled && !ctx->prof_ev) {
+        ctx->prof_ev = new cudaEvent_t[b200vis_ctx::kProfFrames][4]();
+        for (int i = 0; i < b200vis_ctx::kProfFrames; ++i) for (cudaEvent_t &e : ctx->prof_ev[i]) CU(cudaEventCreate(&e));
+    }
     ctx->profiling = enabled != 0;
+    ctx->prof_count = 0;
     return B200VIS_OK;
 }
-extern "C" int32_t b200vis_last_stage_times_ms(b200vis_ctx *ctx, float *tile_ms, float *expand_ms, float *cluster_ms) {
+extern "C" int32_t b200vis_collect_stage_times_ms(b200vis_ctx *ctx, float *tile_ms, float *expand_ms, float *cluster_ms, uint32_t *frames) {
     CHECK_CTX();
-    if (!ctx->profiling) return fail(ctx, B200VIS_ERR_NOT_READY, "profiling is off");
-    CU(cudaEventSynchronize(ctx->prof_ev[3]));
-    float t = 0;
-    if (tile_ms) { CU(cudaEventElapsedTime(&t, ctx->prof_ev[0], ctx->prof_ev[1])); *tile_ms = t; }
-    if (expand_ms) { CU(cudaEventElapsedTime(&t, ctx->prof_ev[1], ctx->prof_ev[2])); *expand_ms = t; }
-    if (cluster_ms) { CU(cudaEventElapsedTime(&t, ctx->prof_ev[2], ctx->prof_ev[3])); *cluster_ms = t; }
+    if (!ctx->prof_ev) return fail(ctx, B200VIS_ERR_NOT_READY, "profiling was never enabled");
+    CU(cudaStreamSynchronize(ctx->stream));
+    double s[3] = {0, 0, 0};
+    for (int i = 0; i < ctx->prof_count; ++i)
+        for (int k = 0; k < 3; ++k) { float t = 0; CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][k], ctx->prof_ev[i][k + 1])); s[k] += t; }
+    if (tile_ms) *tile_ms = (float)s[0];
+    if (expand_ms) *expand_ms = (float)s[1];
+    if (cluster_ms) *cluster_ms = (float)s[2];
+    if (frames) *frames = (uint32_t)ctx->prof_count;
+    ctx->prof_count = 0;
     return B200VIS_OK;
 }
 
@@ -639,7 +652,8 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         launch_mark_dirty_global(st, R);
     }
     const uint32_t parity = ctx->parity;
-    if (ctx->profiling) CU(cudaEventRecord(ctx->prof_ev[0], st));
+    cudaEvent_t *pe = (ctx->profiling && ctx->prof_count < b200vis_ctx::kProfFrames) ? ctx->prof_ev[ctx->prof_count++] : nullptr;
+    if (pe) CU(cudaEventRecord(pe[0], st));
     if (do_prop || do_cull) {
         const uint32_t tile_stages = (do_prop ? 1u : 0u) | (do_cull ? 2u : 0u);
         if (do_prop) {
@@ -651,14 +665,14 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
                                   tile_stages, 0, parity);
         }
     }
-    if (ctx->profiling) CU(cudaEventRecord(ctx->prof_ev[1], st));
+    if (pe) CU(cudaEventRecord(pe[1], st));
     if (do_cull) launch_expand_visible(st, ctx->vis, R.row_of_rank, fc, ctx->d_stats, parity, ctx->n, ctx->cfg.max_views);
-    if (ctx->profiling) CU(cudaEventRecord(ctx->prof_ev[2], st));
+    if (pe) CU(cudaEventRecord(pe[2], st));
     if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
         launch_cluster_assign(st, R, ctx->lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if (stages & B200VIS_STAGE_CLUSTER_LISTS)
         launch_cluster_lists(st, fc, cl, ctx->d_stats, ctx->cfg.max_views);
-    if (ctx->profiling) CU(cudaEventRecord(ctx->prof_ev[3], st));
+    if (pe) CU(cudaEventRecord(pe[3], st));
     CU(cudaGetLastError());
     if (do_cull) { ctx->frame++; ctx->parity ^= 1u; }
     return B200VIS_OK;

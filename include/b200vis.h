@@ -200,10 +200,12 @@ B200VIS_API int32_t b200vis_snapshot_frame_constants(b200vis_ctx *ctx, void *dev
 B200VIS_API int32_t b200vis_use_frame_constants(b200vis_ctx *ctx, const void *device_blob);
 
 /* Optional per-stage device timing: when on, b200vis_run brackets its stages with CUDA events on the
- * context's stream; b200vis_last_stage_times_ms waits for the last run and returns the durations of the
- * tile kernel(s) (propagate+cull), the visible-list expansion and the cluster kernels. */
+ * context's stream (up to 256 runs are kept).  b200vis_collect_stage_times_ms synchronizes ONCE, returns the
+ * summed durations of the tile kernel(s) (propagate+cull), the visible-list expansion and the cluster kernels
+ * over the `frames` runs recorded since the last collect, and resets the recorder. */
 B200VIS_API int32_t b200vis_set_profiling(b200vis_ctx *ctx, int32_t enabled);
-B200VIS_API int32_t b200vis_last_stage_times_ms(b200vis_ctx *ctx, float *tile_ms, float *expand_ms, float *cluster_ms);
+B200VIS_API int32_t b200vis_collect_stage_times_ms(b200vis_ctx *ctx, float *tile_ms, float *expand_ms, float *cluster_ms,
+                                                   uint32_t *frames);
 
 /* ---- run ----------------------------------------------------------------------- */
 B200VIS_API int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages);
