@@ -282,7 +282,7 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
             while (c > start + 1 && parent[c] < n) --c;   // c = latest row in (start, end] that starts a tree
             if (c > start && !(parent[c] < n)) end = c;
         }
-        Tile t; t.base = start; t.n_rows = (uint16_t)(end - start); t.n_levels = 1;
+        Tile t; t.base = start; t.n_rows = (uint16_t)(end - start); t.n_levels = 1; t.warp_sync_mask = 0xFFFFFFFFu; t.pad = 0;
         for (uint32_t r = start; r < end; ++r) tile_of[r] = (uint32_t)tiles.size();
         tiles.push_back(t);
         start = end;
@@ -299,6 +299,9 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
             ldepth[r] = ldepth[p] + 1;
             w |= (p - tiles[ti].base) | (ldepth[r] << 9);
             tiles[ti].n_levels = std::max<uint16_t>(tiles[ti].n_levels, (uint16_t)(ldepth[r] + 1));
+            // a level keeps its warp-sync bit only while every parent->child edge into it stays inside one warp
+            if (ldepth[r] < 32 && ((p - tiles[ti].base) >> 5) != ((r - tiles[ti].base) >> 5))
+                tiles[ti].warp_sync_mask &= ~(1u << ldepth[r]);
         } else {
             w |= T_EXT_PARENT;
             tile_level[ti] = std::max(tile_level[ti], tile_level[tile_of[p]] + 1);

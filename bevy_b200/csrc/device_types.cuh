@@ -24,6 +24,9 @@ struct Tile {               // one CTA's work: a contiguous, (mostly) hierarchy-
     uint32_t base;
     uint16_t n_rows;
     uint16_t n_levels;      // in-tile depth levels (1 for flat rows)
+    uint32_t warp_sync_mask; // bit l (1 <= l < 32): every row of level l has its parent in the same warp,
+                             //   so __syncwarp orders the shared-memory hand-over instead of a CTA barrier
+    uint32_t pad;
 };
 
 // SoA mirror of the ECS columns in HBM.  Every array is indexed by row.

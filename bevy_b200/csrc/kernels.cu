@@ -58,50 +58,6 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 __device__ __forceinline__ float gl_min(float a, float b) { return a < b ? a : b; }   // glam / SSE min,max
 __device__ __forceinline__ float gl_max(float a, float b) { return a > b ? a : b; }
 
-// The closure of check_visibility_cpu_culling for one entity and one view
-// (crates/bevy_camera/src/visibility/mod.rs:804-844), frustum part.
-//   Aabb:   sphere pre-test (primitives.rs:255-268, planes 0..4) then OBB test (primitives.rs:272-294,
-//           planes 0..4: near included, far skipped); both use the same dot(plane, (center,1)).
-//   Sphere: sphere test only.
-__device__ __forceinline__ bool frustum_visible(const float4 *hs, uint32_t f, const Aff &g, float4 bA, float2 bB) {
-    if (f & F_AABB) {
-        const float cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;   // transform_point3a
-        const float cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
-        const float cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
-        const float hx = bA.w, hy = bB.x, hz = bB.y;
-        const float vx = (g.r0.x * hx + g.r0.y * hy) + g.r0.z * hz;                    // radius_vec3a
-        const float vy = (g.r1.x * hx + g.r1.y * hy) + g.r1.z * hz;
-        const float vz = (g.r2.x * hx + g.r2.y * hy) + g.r2.z * hz;
-        const float radius = sqrtf((vx * vx + vy * vy) + vz * vz);
-        float d[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            d[k] = plane_dot_point(hs[k], cx, cy, cz);
-            if (d[k] + radius <= 0.0f) return false;
-        }
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const float4 n = hs[k];
-            // Aabb::relative_radius (primitives.rs:109-119)
-            const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
-            const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
-            const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
-            const float rr = (dx * hx + dy * hy) + dz * hz;
-            if (d[k] + rr <= 0.0f) return false;
-        }
-        return true;
-    }
-    if (f & F_SPHERE) {
-        float cx = bA.x, cy = bA.y, cz = bA.z;
-        if (f & F_SPHERE_GT) { cx = g.r0.w; cy = g.r1.w; cz = g.r2.w; }
-        const float radius = bA.w;
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-            if (plane_dot_point(hs[k], cx, cy, cz) + radius <= 0.0f) return false;
-    }
-    return true;
-}
-
 // ------------------------------------------------------------------------------------------
 // Kernel 1: fused propagate -> cull over one tile of rows per CTA.
 //
@@ -109,37 +65,37 @@ __device__ __forceinline__ bool frustum_visible(const float4 *hs, uint32_t f, co
 // shared memory) or point at rows finished by an earlier pass (parents read from HBM).
 //   phase 1  all rows: coalesced float4 loads of Transform, old GlobalTransform, bounds, flags
 //            (everything a row needs is requested up front: ~11 independent loads per thread)
-//   phase 2  per in-tile depth level: GT = parentGT * local, parent tiles staged in shared memory
-//   phase 3  all rows: set_if_neq write-back, frustum tests for every view, warp-ballot bits into
-//            the rank-ordered visible mask, ViewVisibility state machine, change flags
+//   phase 2  per in-tile depth level: GT = parentGT * local, parent matrices staged in shared
+//            memory; a level whose parents all sit in the same warp only needs __syncwarp
+//            (the planner marks those levels), the others a CTA barrier
+//   phase 3  all rows: set_if_neq write-back, frustum tests for every view (branch-free sphere
+//            pre-test, OBB test for the survivors), warp-ballot bits into the rank-ordered
+//            visible mask, ViewVisibility state machine, change flags
+// Template flags: PROP / CULL = stages fused into this launch; SIMPLE = no per-row RenderLayers /
+// VisibleEntityRanges / rank columns (every entity on the default layer, rows already in
+// Entity::to_bits() order), which removes three loads and the per-lane atomics.
 // ------------------------------------------------------------------------------------------
 struct TileSmem {
     float4 g0[kTileRows], g1[kTileRows], g2[kTileRows];
     uint16_t parent[kTileRows];
     uint8_t st[kTileRows];       // bit0 visited, bit1 gt changed
     uint8_t dirty[kTileRows];    // TransformTreeChanged this frame (mark_dirty_trees)
-    DevView views[kMaxViews];
+    float4 planes[kMaxViews][5]; // the five half spaces culling uses (far is skipped, primitives.rs:255-294)
+    unsigned long long view_layers[kMaxViews];
+    int32_t view_range[kMaxViews];
+    uint32_t view_on[kMaxViews]; // bit0 participates (active [& default layer when SIMPLE]), bit1 NoCpuCulling camera
     uint32_t n_views;
 };
 
-__global__ void __launch_bounds__(kTileRows)
+template <bool PROP, bool CULL, bool SIMPLE>
+__global__ void __launch_bounds__(kTileRows, 4)
 k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__restrict__ fc, VisibleBufs vb,
-                 DevStats *__restrict__ stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
+                 DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity) {
     __shared__ TileSmem s;
     const Tile tile = tiles[blockIdx.x];
     const uint32_t lr = threadIdx.x;
     const bool active = lr < tile.n_rows;
     const uint32_t row = tile.base + lr;
-    const bool do_prop = stages & 1u, do_cull = stages & 2u;
-
-    if (do_cull) {   // stage the per-view constants once per CTA
-        const uint32_t nv = fc->n_views;
-        if (lr == 0) s.n_views = nv;
-        const uint32_t words = nv * (sizeof(DevView) / 4);
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(fc->views);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(s.views);
-        for (uint32_t i = lr; i < words; i += kTileRows) dst[i] = src[i];
-    }
 
     // ---- phase 1: loads -------------------------------------------------------------
     float4 A = make_float4(0, 0, 0, 0), q = A, bA = A;
@@ -151,14 +107,27 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__re
         f = R.flags[row];
         st8 = R.state[row];
         g.r0 = R.gt0[row]; g.r1 = R.gt1[row]; g.r2 = R.gt2[row];
-        if (do_prop) { topo = R.topo[row]; A = R.trsA[row]; q = R.trsB[row]; C = R.trsC[row]; }
-        if (do_cull) { bA = R.bndA[row]; bB = R.bndB[row]; }
+        if (PROP) { topo = R.topo[row]; A = R.trsA[row]; q = R.trsB[row]; C = R.trsC[row]; }
+        if (CULL) { bA = R.bndA[row]; bB = R.bndB[row]; }
+    }
+    if (CULL) {   // stage the per-view constants once per CTA
+        const uint32_t nv = fc->n_views;
+        if (lr == 0) s.n_views = nv;
+        if (lr < nv * 5u) s.planes[lr / 5u][lr % 5u] = fc->views[lr / 5u].hs[lr % 5u];
+        if (lr >= 64u && lr < 64u + nv) {
+            const DevView &dv = fc->views[lr - 64u];
+            const bool on = (dv.flags & 1u) && (!SIMPLE || (dv.layer_mask & 1ull));
+            s.view_on[lr - 64u] = (on ? 1u : 0u) | (dv.flags & 2u);
+            s.view_layers[lr - 64u] = dv.layer_mask;
+            s.view_range[lr - 64u] = dv.range_index;
+        }
     }
 
     bool visited = false, changed = false;
-    if (do_prop) {
+    if (PROP) {
         const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
         const bool tchanged = f & F_TCHANGED;
+        const bool has_children = topo & T_HAS_CHILDREN;
         // -- mark_dirty_trees (systems.rs:111-306) inside the tile: climb the staged parent links
         bool dirty = tchanged;
         if (static_opt && R.dirty != nullptr) {
@@ -180,39 +149,50 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__re
             dirty = s.dirty[lr];
         }
         const Aff l = affine_from_trs(A, q, C);
-        for (uint32_t lvl = 0; lvl < tile.n_levels; ++lvl) {
-            if (active && depth == lvl && !(topo & T_DETACHED)) {
-                Aff n = l;
-                if (topo & T_ROOT) {
-                    // flat entity: sync_simple_transforms (systems.rs:42-79); root with children:
-                    // unconditional write (systems.rs:525-530)
-                    visited = (topo & T_HAS_CHILDREN) ? (!static_opt || dirty) : tchanged;
-                    changed = visited;
-                } else {
-                    float4 p0, p1, p2; uint32_t pst;
-                    if (lvl == 0) {   // parent finished by an earlier pass: read it from HBM
-                        const uint32_t pr = R.parent[row];
-                        p0 = R.gt0[pr]; p1 = R.gt1[pr]; p2 = R.gt2[pr];
-                        const uint32_t ps = R.state[pr];
-                        pst = ((ps & S_VISITED) ? 1u : 0u) | ((ps & S_GT_CHANGED) ? 2u : 0u);
-                    } else {
-                        p0 = s.g0[plocal]; p1 = s.g1[plocal]; p2 = s.g2[plocal];
-                        pst = s.st[plocal];
-                    }
-                    // propagate_descendants_unchecked (systems.rs:706-727)
-                    visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
-                    if (visited) {
-                        n.r0 = affine_mul_row(p0, l); n.r1 = affine_mul_row(p1, l); n.r2 = affine_mul_row(p2, l);
-                        changed = row_neq(n.r0, g.r0) | row_neq(n.r1, g.r1) | row_neq(n.r2, g.r2);   // set_if_neq
-                    }
+        const uint32_t my_level = (active && !(topo & T_DETACHED)) ? depth : 0xFFFFFFFFu;
+        // a detached row (ChildOf without a usable parent) is never visited, and neither is its subtree
+        if (active && (topo & T_DETACHED) && has_children) s.st[lr] = 0;
+        // ---- level 0: roots, flat entities, rows whose parent was finished by an earlier pass
+        if (my_level == 0) {
+            if (topo & T_ROOT) {
+                // flat entity: sync_simple_transforms (systems.rs:42-79); root with children:
+                // unconditional write (systems.rs:525-530)
+                visited = has_children ? (!static_opt || dirty) : tchanged;
+                changed = visited;
+                if (changed) g = l;
+            } else {
+                const uint32_t pr = R.parent[row];
+                const uint32_t ps = R.state[pr];
+                visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
+                if (visited) {
+                    Aff n;
+                    n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
+                    changed = row_neq(n.r0, g.r0) | row_neq(n.r1, g.r1) | row_neq(n.r2, g.r2);
+                    if (changed) g = n;
                 }
-                if (changed) g = n;
-                if (topo & T_HAS_CHILDREN) {
+            }
+            if (has_children) {
+                s.g0[lr] = g.r0; s.g1[lr] = g.r1; s.g2[lr] = g.r2;
+                s.st[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+            }
+        }
+        // ---- deeper levels: propagate_descendants_unchecked (systems.rs:706-727)
+        for (uint32_t lvl = 1; lvl < tile.n_levels; ++lvl) {
+            if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) __syncwarp(); else __syncthreads();
+            if (my_level == lvl) {
+                const uint32_t pst = s.st[plocal];
+                visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                if (visited) {
+                    Aff n;
+                    n.r0 = affine_mul_row(s.g0[plocal], l); n.r1 = affine_mul_row(s.g1[plocal], l); n.r2 = affine_mul_row(s.g2[plocal], l);
+                    changed = row_neq(n.r0, g.r0) | row_neq(n.r1, g.r1) | row_neq(n.r2, g.r2);   // set_if_neq
+                    if (changed) g = n;
+                }
+                if (has_children) {
                     s.g0[lr] = g.r0; s.g1[lr] = g.r1; s.g2[lr] = g.r2;
                     s.st[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
                 }
             }
-            if (lvl + 1 < tile.n_levels) __syncthreads();
         }
         if (active) {
             if (changed) { R.gt0[row] = g.r0; R.gt1[row] = g.r1; R.gt2[row] = g.r2; }
@@ -220,46 +200,109 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__re
         }
     }
     uint32_t out = st8 & (S_VV | S_HAS_CLASS);
-    if (do_prop) out |= (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
+    if (PROP) out |= (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
     else out |= st8 & (S_GT_CHANGED | S_VISITED);
 
     // ---- phase 3: cull ----------------------------------------------------------------
     bool vv_changed = false;
-    if (do_cull) {
-        __syncthreads();   // s.views
+    if (CULL) {
+        __syncthreads();   // s.planes / s.view_*
         const bool in_query = active && !(f & F_NO_CPU_CULL);          // Without<NoCpuCulling>
+        const bool base = in_query && (f & F_INHERITED);
         const uint32_t prev = st8 & 1u;                                // reset_view_visibility: v = (v&1)<<1
-        bool any = false;
         const uint32_t nv = s.n_views;
         const uint32_t lane = lr & 31u;
-        const uint32_t rnk = (R.rank != nullptr && active) ? R.rank[row] : row;
-        const unsigned long long elayers = (R.layers != nullptr && active) ? R.layers[row] : 1ull;
-        const uint32_t erange = ((f & F_RANGE) && R.range != nullptr) ? R.range[row] : 0xFFFFFFFFu;
+        const bool has_aabb = f & F_AABB;
+        const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
+        // world-space bounding sphere (visibility/mod.rs:825-829): Aabb -> transform_point3a(center),
+        // radius_vec3a(half_extents); Sphere -> as stored (or the row's own translation)
+        float cx, cy, cz, radius;
+        const float hx = bA.w, hy = bB.x, hz = bB.y;
+        if (has_aabb) {
+            cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;
+            cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
+            cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+            const float vx = (g.r0.x * hx + g.r0.y * hy) + g.r0.z * hz;
+            const float vy = (g.r1.x * hx + g.r1.y * hy) + g.r1.z * hz;
+            const float vz = (g.r2.x * hx + g.r2.y * hy) + g.r2.z * hz;
+            radius = sqrtf((vx * vx + vy * vy) + vz * vz);
+        } else {
+            const bool from_gt = f & F_SPHERE_GT;
+            cx = from_gt ? g.r0.w : bA.x; cy = from_gt ? g.r1.w : bA.y; cz = from_gt ? g.r2.w : bA.z;
+            radius = bA.w;
+        }
+        unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
+        if (!SIMPLE && active) {
+            if (R.layers != nullptr) elayers = R.layers[row];
+            if ((f & F_RANGE) && R.range != nullptr) erange = R.range[row];
+            if (R.rank != nullptr) rnk = R.rank[row];
+        }
+        bool any = false;
+        uint32_t my_ballot = 0;
         for (uint32_t v = 0; v < nv; ++v) {
-            const DevView &view = s.views[v];
-            if (!(view.flags & 1u)) continue;                          // !camera.is_active
-            bool vis = in_query && (f & F_INHERITED) && (view.layer_mask & elayers) != 0ull;
-            if (vis && (f & F_RANGE) && R.range != nullptr)
-                vis = view.range_index >= 0 && ((erange >> view.range_index) & 1u);
-            if (vis && !(f & F_NO_FRUSTUM) && !(view.flags & 2u)) vis = frustum_visible(view.hs, f, g, bA, bB);
+            const uint32_t von = s.view_on[v];
+            if (!(von & 1u)) continue;                                 // !camera.is_active (CTA-uniform)
+            bool vis = base;
+            if (!SIMPLE) {
+                vis = vis && (s.view_layers[v] & elayers) != 0ull;
+                if ((f & F_RANGE) && R.range != nullptr) {
+                    const int32_t ri = s.view_range[v];
+                    vis = vis && ri >= 0 && ((erange >> ri) & 1u);
+                }
+            }
+            if (do_test && !(von & 2u)) {
+                const float4 *hs = s.planes[v];
+                // Frustum::intersects_sphere, planes 0..4 (primitives.rs:255-268), branch-free
+                const float d0 = plane_dot_point(hs[0], cx, cy, cz), d1 = plane_dot_point(hs[1], cx, cy, cz);
+                const float d2 = plane_dot_point(hs[2], cx, cy, cz), d3 = plane_dot_point(hs[3], cx, cy, cz);
+                const float d4 = plane_dot_point(hs[4], cx, cy, cz);
+                const bool out_s = (d0 + radius <= 0.0f) | (d1 + radius <= 0.0f) | (d2 + radius <= 0.0f) |
+                                   (d3 + radius <= 0.0f) | (d4 + radius <= 0.0f);
+                vis = vis && !out_s;
+                if (vis && has_aabb) {
+                    // Frustum::intersects_obb(aabb, affine, true, false) (primitives.rs:272-294);
+                    // the plane . (center,1) terms are the ones computed above, bit for bit
+                    const float d[5] = {d0, d1, d2, d3, d4};
+                    bool out_o = false;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const float4 n = hs[k];   // Aabb::relative_radius (primitives.rs:109-119)
+                        const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+                        const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+                        const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+                        const float rr = (dx * hx + dy * hy) + dz * hz;
+                        out_o |= (d[k] + rr <= 0.0f);
+                    }
+                    vis = !out_o;
+                }
+            }
             any |= vis;
             // entities without a VisibilityClass are set_visible() but not listed (mod.rs:846-857)
             const bool listed = vis && (st8 & S_HAS_CLASS);
-            uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
-            uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
-            if (R.rank == nullptr) {
-                // warp-ballot compaction: 32 consecutive rows -> at most two mask words
+            if (SIMPLE) {
                 const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
-                if (lane == 0 && b) {
-                    const uint32_t row0 = row, w0 = row0 >> 5, sh = row0 & 31u;
-                    const uint32_t lo = b << sh, hi = sh ? (b >> (32u - sh)) : 0u;
-                    if (lo) { atomicOr(mask + w0, lo); atomicAdd(cc + (w0 / kChunkWords), __popc(lo)); }
-                    if (hi) { atomicOr(mask + w0 + 1, hi); atomicAdd(cc + ((w0 + 1) / kChunkWords), __popc(hi)); }
+                if (lane == v) my_ballot = b;
+            } else {
+                uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
+                uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
+                if (R.rank == nullptr) {
+                    const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
+                    if (lane == v) my_ballot = b;
+                } else if (listed) {
+                    atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+                    atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
                 }
-            } else if (listed) {
-                atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
-                atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
             }
+        }
+        // warp-ballot compaction: lane v publishes view v's 32 bits; 32 consecutive rows touch at
+        // most two words of the rank-ordered mask
+        if (my_ballot) {
+            uint32_t *mask = vb.mask + (size_t)lane * vb.words_stride;
+            uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + lane) * vb.chunks_stride;
+            const uint32_t row0 = row - lane, w0 = row0 >> 5, sh = row0 & 31u;
+            const uint32_t lo = my_ballot << sh, hi = sh ? (my_ballot >> (32u - sh)) : 0u;
+            if (lo) { atomicOr(mask + w0, lo); atomicAdd(cc + (w0 / kChunkWords), __popc(lo)); }
+            if (hi) { atomicOr(mask + w0 + 1, hi); atomicAdd(cc + ((w0 + 1) / kChunkWords), __popc(hi)); }
         }
         if (in_query) {
             // set_visible + mark_newly_hidden_entities_invisible (mod.rs:292-306, 908-918):
@@ -273,12 +316,12 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__re
     }
     if (active && out != st8) R.state[row] = (uint8_t)out;
 
-    // per-frame change counters (one atomic per warp)
-    const uint32_t bg = __ballot_sync(0xFFFFFFFFu, do_prop && changed);
-    const uint32_t bv = __ballot_sync(0xFFFFFFFFu, vv_changed);
-    if ((lr & 31u) == 0) {
-        if (bg) atomicAdd(&stats->changed[parity][0], __popc(bg));
-        if (bv) atomicAdd(&stats->changed[parity][1], __popc(bv));
+    // per-frame change counters (one atomic per CTA)
+    const int n_gt = __syncthreads_count(PROP && changed);
+    const int n_vv = __syncthreads_count(vv_changed);
+    if (lr == 0) {
+        if (n_gt) atomicAdd(&stats->changed[parity][0], (uint32_t)n_gt);
+        if (n_vv) atomicAdd(&stats->changed[parity][1], (uint32_t)n_vv);
     }
 }
 
@@ -384,12 +427,29 @@ __device__ __forceinline__ uint3 ndc_to_cluster(const DevClusterView &cv, const 
     return make_uint3(min(x, cv.dims[0] - 1), min(y, cv.dims[1] - 1), min(z, cv.dims[2] - 1));
 }
 
+constexpr uint32_t kStagedPlanes = 512;   // plane tables up to this many entries are staged in shared memory
+
 __global__ void __launch_bounds__(256)
 k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__restrict__ stats) {
+    __shared__ float4 s_planes[kStagedPlanes];
+    __shared__ float s_thr[kStagedPlanes];
     const uint32_t v = blockIdx.y;
     if (v >= fc->n_views) return;
     const DevClusterView &cv = fc->cviews[v];
     if (!cv.enabled) return;
+    // stage this view's x/y/z plane tables and z thresholds once per CTA (all 8 warps share the view)
+    const uint32_t nx = cv.dims[0] + 1, ny_p = cv.dims[1] + 1, nz = cv.dims[2] + 1;
+    const bool staged = nx + ny_p + nz <= kStagedPlanes;
+    if (staged) {
+        const float4 *gx = reinterpret_cast<const float4 *>(cb.blob + cv.x_off);
+        const float4 *gy = reinterpret_cast<const float4 *>(cb.blob + cv.y_off);
+        const float4 *gz = reinterpret_cast<const float4 *>(cb.blob + cv.z_off);
+        for (uint32_t i = threadIdx.x; i < nx; i += 256) s_planes[i] = gx[i];
+        for (uint32_t i = threadIdx.x; i < ny_p; i += 256) s_planes[nx + i] = gy[i];
+        for (uint32_t i = threadIdx.x; i < nz; i += 256) s_planes[nx + ny_p + i] = gz[i];
+        for (uint32_t i = threadIdx.x; i + 1 < cv.dims[2]; i += 256) s_thr[i] = cb.blob[cv.thr_off + i];
+        __syncthreads();
+    }
     const uint32_t li = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
     if (li >= L.n) return;
     const uint32_t row = L.row[li];
@@ -402,7 +462,7 @@ k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBu
     for (int k = 0; k < 6; ++k)                                         // frustum.intersects_sphere(.., true)
         if (plane_dot_point(cv.frustum[k], px, py, pz) + range <= 0.0f) return;
 
-    const float *thr = cb.blob + cv.thr_off;
+    const float *thr = staged ? s_thr : cb.blob + cv.thr_off;
     const bool ortho = cv.is_ortho;
     // cluster_space_clusterable_object_aabb (assign.rs:948-1036)
     const float4 vc = mat4_mul_point(cv.vfw, px, py, pz);
@@ -440,9 +500,9 @@ k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBu
     else if (ndy < -1.0f) { has_yc = true; yc = cv.dims[1] + 1; }
     else { has_yc = true; yc = ccl.y; }
 
-    const float4 *xp = reinterpret_cast<const float4 *>(cb.blob + cv.x_off);
-    const float4 *yp = reinterpret_cast<const float4 *>(cb.blob + cv.y_off);
-    const float4 *zp = reinterpret_cast<const float4 *>(cb.blob + cv.z_off);
+    const float4 *xp = staged ? s_planes : reinterpret_cast<const float4 *>(cb.blob + cv.x_off);
+    const float4 *yp = staged ? s_planes + nx : reinterpret_cast<const float4 *>(cb.blob + cv.y_off);
+    const float4 *zp = staged ? s_planes + nx + ny_p : reinterpret_cast<const float4 *>(cb.blob + cv.z_off);
     uint32_t *mask = cb.send + ((size_t)v * cb.words + (li >> 5)) * kMaxClusters;
     const uint32_t bit = 1u << (li & 31u);
     const uint32_t ny = hi.y - lo.y + 1, npairs = (hi.z - lo.z + 1) * ny;
@@ -492,72 +552,89 @@ k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBu
 
 // ------------------------------------------------------------------------------------------
 // Kernel 4: cluster x light bitmask (all ranks' slabs) -> per-cluster ordered index lists.
-// One CTA per view: popcount -> block scan -> ordered emit.  Ascending (rank, light) order is
-// the reference's push order (the outer loop runs over lights, assign.rs:487).
+// kListBlocks CTAs per view, 1024 clusters each: popcount -> scan -> ordered emit.  A CTA gets the
+// offset of its first cluster by re-counting the clusters before it (L2-resident words, coalesced),
+// which is cheaper than a second launch or a cross-CTA hand-over.  Ascending (rank, light) order
+// is the reference's push order (the outer loop runs over lights, assign.rs:487).
 // ------------------------------------------------------------------------------------------
+constexpr uint32_t kListBlocks = kMaxClusters / 1024;
+
 __global__ void __launch_bounds__(1024)
 k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__restrict__ stats) {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    const uint32_t v = blockIdx.x, t = threadIdx.x;
+    __shared__ uint32_t s_red[32];
+    const uint32_t v = blockIdx.y, blk = blockIdx.x, t = threadIdx.x;
     if (v >= fc->n_views) return;
     const DevClusterView &cv = fc->cviews[v];
     uint32_t *offsets = cb.offsets + (size_t)v * (kMaxClusters + 1);
-    if (t == 0) {   // publish this frame's accumulators and re-arm them
-        stats->cl_index_count[v] = stats->cl_acc_index[v]; stats->cl_acc_index[v] = 0;
-        stats->cl_farthest_bits[v] = stats->cl_acc_far[v]; stats->cl_acc_far[v] = 0;
-    }
-    if (!cv.enabled) { if (t == 0) { offsets[0] = 0; stats->cl_overflow[v] = 0; } return; }
-    const uint32_t nc = cv.n_clusters;
+    const uint32_t nc = cv.enabled ? cv.n_clusters : 0u;
+    if (blk == 0 && t == 0 && !cv.enabled) { offsets[0] = 0; stats->cl_overflow[v] = 0; }
     const size_t rank_stride = (size_t)cb.max_views * cb.words * kMaxClusters;
     const uint32_t *base = cb.recv + (size_t)v * cb.words * kMaxClusters;
     uint32_t *indices = cb.indices + (size_t)v * cb.index_cap;
-    if (t == 0) s_carry = 0;
+    const uint32_t first = blk * 1024u;
+    // (a) this thread's cluster; (b) its share of the clusters in front of this CTA
+    const uint32_t c = first + t;
+    uint32_t cnt = 0, before = 0;
+    if (c < nc)
+        for (uint32_t r = 0; r < cb.world; ++r)
+            for (uint32_t w = 0; w < cb.words; ++w) cnt += __popc(base[r * rank_stride + (size_t)w * kMaxClusters + c]);
+    for (uint32_t p = t; p < first && p < nc; p += 1024)
+        for (uint32_t r = 0; r < cb.world; ++r)
+            for (uint32_t w = 0; w < cb.words; ++w) before += __popc(base[r * rank_stride + (size_t)w * kMaxClusters + p]);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((t & 31u) >= (uint32_t)o) incl += y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
+    if ((t & 31u) == 31u) s_warp[t >> 5] = incl;
+    if ((t & 31u) == 0u) s_red[t >> 5] = before;
     __syncthreads();
-    for (uint32_t c0 = 0; c0 < nc; c0 += 1024) {
-        const uint32_t c = c0 + t;
-        uint32_t cnt = 0;
-        if (c < nc)
-            for (uint32_t r = 0; r < cb.world; ++r)
-                for (uint32_t w = 0; w < cb.words; ++w) cnt += __popc(base[r * rank_stride + (size_t)w * kMaxClusters + c]);
-        uint32_t incl = cnt;
+    if (t < 32) {
+        uint32_t x = s_warp[t], b = s_red[t];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((t & 31u) >= (uint32_t)o) incl += y; }
-        if ((t & 31u) == 31u) s_warp[t >> 5] = incl;
-        __syncthreads();
-        if (t < 32) {
-            uint32_t x = s_warp[t];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
-            s_warp[t] = x;
-        }
-        __syncthreads();
-        const uint32_t carry = s_carry;
-        uint32_t pos = carry + (incl - cnt) + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
-        if (c < nc) {
-            offsets[c] = pos;
-            for (uint32_t r = 0; r < cb.world; ++r)
-                for (uint32_t w = 0; w < cb.words; ++w) {
-                    uint32_t m = base[r * rank_stride + (size_t)w * kMaxClusters + c];
-                    while (m) {
-                        const uint32_t b = __ffs(m) - 1; m &= m - 1;
-                        if (pos < cb.index_cap) indices[pos] = r * cb.max_lights + w * 32u + b;
-                        ++pos;
-                    }
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+        s_warp[t] = x;          // inclusive over warps
+        if (t == 0) s_red[0] = b;
+    }
+    __syncthreads();
+    uint32_t pos = s_red[0] + (incl - cnt) + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+    if (c < nc) {
+        offsets[c] = pos;
+        for (uint32_t r = 0; r < cb.world; ++r)
+            for (uint32_t w = 0; w < cb.words; ++w) {
+                uint32_t m = base[r * rank_stride + (size_t)w * kMaxClusters + c];
+                while (m) {
+                    const uint32_t b = __ffs(m) - 1; m &= m - 1;
+                    if (pos < cb.index_cap) indices[pos] = r * cb.max_lights + w * 32u + b;
+                    ++pos;
                 }
-            // leave this rank's slab zeroed for the next frame's assign kernel
-            uint32_t *mine = cb.send + (size_t)v * cb.words * kMaxClusters;
-            for (uint32_t w = 0; w < cb.words; ++w) mine[(size_t)w * kMaxClusters + c] = 0;
-        }
-        __syncthreads();
-        if (t == 1023) s_carry = carry + s_warp[31];
-        __syncthreads();
+            }
     }
-    if (t == 0) {
-        const uint32_t total = s_carry;
-        offsets[nc] = total;
-        stats->cl_overflow[v] = total > cb.index_cap ? 1u : 0u;
+    // the CTA holding the last cluster publishes the total; CTA 0 publishes / re-arms the accumulators
+    if (nc && c == nc - 1) {
+        offsets[nc] = pos;
+        stats->cl_overflow[v] = pos > cb.index_cap ? 1u : 0u;
     }
+    if (blk == 0 && t == 0) {
+        stats->cl_index_count[v] = stats->cl_acc_index[v]; stats->cl_acc_index[v] = 0;
+        stats->cl_farthest_bits[v] = stats->cl_acc_far[v]; stats->cl_acc_far[v] = 0;
+    }
+    // NOTE: the slab is zeroed for the next frame by k_cluster_clear (a CTA here may still be re-counting it)
+}
+
+// zero this rank's slab for the next frame's assign kernel (only the words in use)
+__global__ void k_cluster_clear(const FrameConsts *__restrict__ fc, ClusterBufs cb) {
+    const uint32_t v = blockIdx.y;
+    if (v >= fc->n_views) return;
+    const DevClusterView &cv = fc->cviews[v];
+    if (!cv.enabled) return;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cv.n_clusters) return;
+    uint32_t *mine = cb.send + (size_t)v * cb.words * kMaxClusters;
+    for (uint32_t w = 0; w < cb.words; ++w) mine[(size_t)w * kMaxClusters + c] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -643,7 +720,13 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const FrameConsts *fc,
                            const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
     if (n_tiles == 0) return;
-    k_propagate_cull<<<n_tiles, kTileRows, 0, st>>>(R, tiles, fc, vb, stats, stages, static_opt, parity);
+    const bool prop = stages & 1u, cull = stages & 2u;
+    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+#define B200VIS_LAUNCH(P, C, S) k_propagate_cull<P, C, S><<<n_tiles, kTileRows, 0, st>>>(R, tiles, fc, vb, stats, static_opt, parity)
+    if (prop && cull) { if (simple) B200VIS_LAUNCH(true, true, true); else B200VIS_LAUNCH(true, true, false); }
+    else if (prop) B200VIS_LAUNCH(true, false, true);
+    else if (cull) { if (simple) B200VIS_LAUNCH(false, true, true); else B200VIS_LAUNCH(false, true, false); }
+#undef B200VIS_LAUNCH
 }
 void launch_mark_dirty_global(cudaStream_t st, const Rows &R) {
     if (R.n) k_mark_dirty_global<<<cdiv(R.n, 256), 256, 0, st>>>(R);
@@ -659,7 +742,8 @@ void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, cons
     k_cluster_assign<<<dim3(cdiv(L.n, 8), max_views), 256, 0, st>>>(R, L, fc, cb, stats);
 }
 void launch_cluster_lists(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, DevStats *stats, uint32_t max_views) {
-    k_cluster_lists<<<max_views, 1024, 0, st>>>(fc, cb, stats);
+    k_cluster_lists<<<dim3(kListBlocks, max_views), 1024, 0, st>>>(fc, cb, stats);
+    k_cluster_clear<<<dim3(kMaxClusters / 256, max_views), 256, 0, st>>>(fc, cb);
 }
 void launch_unpack_trs(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *src, int mark_only) {
     if (count) k_unpack_trs<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, src, mark_only);

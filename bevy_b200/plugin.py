@@ -24,9 +24,9 @@ class VisibilityPipeline:
         c.upload_transforms(0, scene.trs)
         identity = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32), (n, 1))
         c.upload_global_transforms(0, identity)                       # GlobalTransform::IDENTITY at spawn
-        c.upload_bounds(0, scene.bounds, scene.flags, scene.class_mask)
+        c.upload_bounds(0, scene.bounds, scene.flags, scene.class_mask, scene.layer_mask, scene.range_mask)
         c.upload_view_visibility(0, np.zeros(n, np.uint8))             # ViewVisibility::HIDDEN
-        c.set_lights(scene.light_row, scene.light_range)
+        c.set_lights(scene.light_row, scene.light_range, scene.light_layers)
         self.cluster_config = cluster_config or abi.host_default_cluster_config(*scene.screen)
         self.feedback = [abi.ClusterFeedback() for _ in range(V)]
         self._scratch = [None] * V
@@ -39,9 +39,13 @@ class VisibilityPipeline:
         for v, cam in enumerate(self.scene.cameras):
             cfv = abi.host_perspective(cam.fov, cam.aspect, cam.near)
             frustum = abi.host_compute_frustum(cfv, cam.gt, cam.far)
-            views.append(abi.View.make(frustum))
+            sc = self.scene
+            layers = 1 if sc.view_layers is None else int(sc.view_layers[v])
+            views.append(abi.View.make(frustum, layers,
+                                       abi.VIEW_ACTIVE if sc.view_flags is None else int(sc.view_flags[v]),
+                                       -1 if sc.view_range_index is None else int(sc.view_range_index[v])))
             if clusters and len(self.scene.light_row):
-                cv, scratch = abi.host_cluster_view_setup(self.cluster_config, cam.gt, cfv, frustum, 1, self.feedback[v])
+                cv, scratch = abi.host_cluster_view_setup(self.cluster_config, cam.gt, cfv, frustum, layers, self.feedback[v])
                 self._scratch[v] = scratch
                 self.cluster_views[v] = cv
                 self.ctx.set_cluster_view(v, cv)

@@ -39,6 +39,12 @@ class Scene:
     cameras: list = field(default_factory=list)
     roots: np.ndarray = None       # rows of hierarchy roots (the per-frame movers)
     screen: tuple = (1920, 1080)
+    layer_mask: np.ndarray = None  # [n] u64 RenderLayers first block (None => default layer)
+    range_mask: np.ndarray = None  # [n] u32 VisibleEntityRanges bitmask (None => resource absent)
+    light_layers: np.ndarray = None
+    view_layers: list = None       # per camera u64
+    view_flags: list = None        # per camera B200VIS_VIEW_*
+    view_range_index: list = None  # per camera i8
 
     @property
     def n(self):

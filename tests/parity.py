@@ -22,6 +22,7 @@ class OracleWorld:
         self.tchanged = np.ones(n, np.uint8)     # Added<GlobalTransform> on the first frame
         self.static_opt = static_opt
         self.fb = [dict(far=None, cnt=None) for _ in scene.cameras]
+        self.last_lists = [np.zeros(0, np.uint32) for _ in scene.cameras]
 
     def frame(self, views_planes, view_flags=None, cluster=True, mt=False):
         sc = self.scene
@@ -29,16 +30,21 @@ class OracleWorld:
         assert rc == 0
         self.tchanged[:] = 0
         vv_changed, lists = orc.cull(self.gt, sc.bounds, sc.flags, sc.class_mask, sc.entity_bits, self.vv,
-                                     views_planes, view_flags=view_flags, mt=mt)
+                                     views_planes, view_layers=sc.view_layers,
+                                     view_flags=view_flags if view_flags is not None else sc.view_flags,
+                                     layer_mask=sc.layer_mask, range_mask=sc.range_mask,
+                                     view_range_index=sc.view_range_index, mt=mt)
         clusters = []
         if cluster and len(sc.light_row):
             vis = np.nonzero(self.vv[sc.light_row] & 1)[0]
             lights = np.concatenate([self.gt[sc.light_row[vis], 9:12], sc.light_range[vis, None]], 1).astype(np.float32)
+            ll = None if sc.light_layers is None else np.ascontiguousarray(sc.light_layers[vis], np.uint64)
             for v, cam in enumerate(sc.cameras):
                 cfv = orc.perspective(cam.fov, cam.aspect, cam.near)
                 vin = orc.default_cluster_view_in(cam.gt, cfv, views_planes[v], screen=sc.screen,
+                                                  view_layers=1 if sc.view_layers is None else int(sc.view_layers[v]),
                                                   last_farthest_z=self.fb[v]["far"], last_index_count=self.fb[v]["cnt"])
-                out, offsets, idx, _ = orc.assign_lights_to_clusters(vin, lights)
+                out, offsets, idx, _ = orc.assign_lights_to_clusters(vin, lights, ll)
                 self.fb[v]["far"] = out.farthest_z; self.fb[v]["cnt"] = out.total_index_count
                 clusters.append((out, offsets, vis[idx].astype(np.uint32)))
         return gt_changed, vv_changed, lists, clusters
@@ -65,8 +71,10 @@ def compare_frame(pipe, world, frame_no, cluster=True, check_gt=True):
     for v in range(len(sc.cameras)):
         got = pipe.ctx.download_visible(v)
         want = lists[v]
-        assert want is not None
+        if want is None:                      # inactive view: VisibleEntities keep last frame's contents
+            want = world.last_lists[v]
         assert len(got) == len(want) and (got == want).all(), f"{tag} view {v}: visible list differs ({len(got)} vs {len(want)})"
+    world.last_lists = [l if l is not None else world.last_lists[v] for v, l in enumerate(lists)]
     stats = pipe.read_feedback()
     if cluster and len(sc.light_row):
         for v in range(len(sc.cameras)):

@@ -1,0 +1,206 @@
+"""Edge cases the reference's code paths define, CUDA path vs oracle, bit exact."""
+import math
+
+import numpy as np
+import pytest
+
+import bevy_b200 as bb
+from bevy_b200 import scenes
+from bevy_b200.scenes import Scene, Camera
+
+from parity import OracleWorld, compare_frame, run_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_scene(seed, n_roots=60, max_children=4, max_depth=9, n_lights=24, shuffle_entities=True, views=3):
+    """Irregular forest with every per-row feature switched on somewhere."""
+    rng = np.random.default_rng(seed)
+    parent, depth = [], []
+    for _ in range(n_roots):
+        base = len(parent)
+        parent.append(scenes.NO_PARENT); depth.append(0)
+        frontier = [base]
+        while frontier:
+            nxt = []
+            for p in frontier:
+                if depth[p] >= max_depth or rng.random() < 0.25:
+                    continue
+                for _ in range(int(rng.integers(1, max_children + 1))):
+                    parent.append(p); depth.append(depth[p] + 1); nxt.append(len(parent) - 1)
+            frontier = nxt
+    parent = np.array(parent, np.int64)
+    # rows so far are in per-tree BFS-ish creation order with parent < child: keep that (topological)
+    n = len(parent)
+    parent = parent.astype(np.uint32)
+    # a few detached rows (ChildOf pointing outside the transform hierarchy) with their own children
+    for r in rng.choice(np.arange(1, n), size=5, replace=False):
+        if parent[r] != scenes.NO_PARENT:
+            parent[r] = bb.DETACHED
+    t = rng.uniform(-40, 40, (n, 3)); t[parent != scenes.NO_PARENT] *= 0.1
+    q = scenes.random_unit_quats(rng, n)
+    s = rng.uniform(0.5, 1.6, (n, 3))
+    s[rng.random(n) < 0.05] *= -1.0            # mirrored
+    s[rng.random(n) < 0.02] = 0.0              # degenerate scale: children's GT stops changing (set_if_neq)
+    trs = np.concatenate([t, q, s], 1).astype(np.float32)
+    bounds = np.zeros((n, 6), np.float32)
+    bounds[:, 0:3] = rng.uniform(-1, 1, (n, 3)); bounds[:, 3:6] = rng.uniform(0.1, 3.0, (n, 3))
+    kind = rng.integers(0, 10, n)
+    flags = np.full(n, scenes.F_INHERITED_VISIBLE, np.uint8)
+    flags[kind <= 6] |= scenes.F_HAS_AABB
+    flags[kind == 7] |= scenes.F_HAS_SPHERE                       # world-space sphere in bounds[0:4]
+    flags[kind == 8] |= scenes.F_HAS_AABB | scenes.F_HAS_SPHERE   # Aabb takes precedence
+    # kind 9: neither -> always passes the frustum stage
+    flags[rng.random(n) < 0.07] &= ~np.uint8(scenes.F_INHERITED_VISIBLE)
+    flags[rng.random(n) < 0.05] |= bb.F_NO_FRUSTUM_CULLING
+    flags[rng.random(n) < 0.04] |= bb.F_NO_CPU_CULLING
+    flags[rng.random(n) < 0.10] |= bb.F_HAS_VIS_RANGE
+    cls = rng.choice([0, 1, 1, 1, 3], n).astype(np.uint8)
+    layer_mask = rng.choice([1, 1, 1, 2, 3, 0, 1 << 40], n).astype(np.uint64)
+    range_mask = rng.integers(0, 8, n).astype(np.uint32)
+    ent = np.arange(n, dtype=np.uint64) + np.uint64(7)
+    if shuffle_entities:
+        ent = rng.permutation(ent) | (rng.integers(0, 3, n).astype(np.uint64) << np.uint64(32))   # generations too
+    cols = (parent, trs, bounds, flags, cls)
+    pos = rng.uniform(-30, 30, (n_lights, 3)).astype(np.float32)
+    lrange = np.exp(rng.uniform(math.log(0.5), math.log(40.0), n_lights)).astype(np.float32)
+    cols, light_row = scenes._append_lights(cols, pos, lrange)
+    parent, trs, bounds, flags, cls = cols
+    L = n_lights
+    layer_mask = np.concatenate([layer_mask, rng.choice([1, 1, 2, 3], L).astype(np.uint64)])
+    range_mask = np.concatenate([range_mask, np.zeros(L, np.uint32)])
+    ent = np.concatenate([ent, np.arange(L, dtype=np.uint64) + np.uint64(1 << 20)])
+    cams = []
+    for k in range(views):
+        qk = scenes.quat_mul(scenes.quat_axis("y", 2.1 * k), scenes.quat_axis("x", -0.2 * k))
+        cams.append(Camera(gt=scenes.quat_to_gt(qk, (3.0 * k, 1.0, -2.0 * k)), quat=qk, far=120.0))
+    sc = Scene(f"random_{seed}", parent, trs, bounds, flags, cls, ent, light_row, lrange, cams,
+               np.nonzero(parent == scenes.NO_PARENT)[0].astype(np.uint32))
+    sc.layer_mask, sc.range_mask = layer_mask, range_mask
+    sc.light_layers = layer_mask[light_row].copy()
+    sc.view_layers = [1, 3, 2][:views]
+    sc.view_flags = [bb.VIEW_ACTIVE, bb.VIEW_ACTIVE | bb.VIEW_NO_CPU_CULLING, bb.VIEW_ACTIVE][:views]
+    sc.view_range_index = [0, -1, 2][:views]
+    return sc
+
+
+@pytest.mark.parametrize("seed,static_opt", [(1, True), (2, False), (3, True)])
+def test_random_feature_rich_scene(seed, static_opt):
+    sc = _random_scene(seed)
+    pipe = bb.VisibilityPipeline(sc, static_transform_optimizations=static_opt)
+    world = OracleWorld(sc, static_opt)
+    rng = np.random.default_rng(100 + seed)
+    try:
+        for f in range(5):
+            if f > 0:
+                scenes.advance_cameras(sc, 0.05)
+                # a sparse, random set of Changed<Transform> rows (not only roots)
+                rows = np.unique(rng.integers(0, sc.n, max(sc.n // 50, 1))).astype(np.uint32)
+                sc.trs[rows, 0:3] += rng.uniform(-0.5, 0.5, (len(rows), 3)).astype(np.float32)
+                pipe.ctx.upload_transforms_scattered(rows, sc.trs[rows])
+                world.tchanged[rows] = 1
+                if f == 3:       # a frame with an inactive camera: its VisibleEntities must survive untouched
+                    sc.view_flags = [bb.VIEW_ACTIVE, 0, bb.VIEW_ACTIVE]
+                if f == 4:
+                    sc.view_flags = [bb.VIEW_ACTIVE, bb.VIEW_ACTIVE | bb.VIEW_NO_CPU_CULLING, bb.VIEW_ACTIVE]
+            pipe.update_views()
+            compare_frame(pipe, world, f)
+    finally:
+        pipe.close()
+
+
+def test_static_frames_change_nothing():
+    """Steady state with no input changes: no Changed<GlobalTransform>, no Changed<ViewVisibility>."""
+    sc = scenes.forest(n_trees=30, levels=5, n_lights=8)
+    pipe = bb.VisibilityPipeline(sc)
+    world = OracleWorld(sc)
+    try:
+        pipe.update_views()
+        compare_frame(pipe, world, 0)
+        for f in (1, 2):
+            s = compare_frame(pipe, world, f)
+            assert s.gt_changed_count == 0 and s.vv_changed_count == 0
+    finally:
+        pipe.close()
+
+
+def test_deep_chain_and_wide_fanout():
+    """A 700-deep chain (many tiles, many passes) next to one root with 3000 children (parents in other tiles)."""
+    chain = 700
+    parent = [scenes.NO_PARENT] + list(range(chain - 1))
+    root = len(parent)
+    parent += [scenes.NO_PARENT] + [root] * 3000
+    n = len(parent)
+    rng = np.random.default_rng(5)
+    trs = np.zeros((n, 10), np.float32)
+    trs[:, 0:3] = rng.uniform(-0.2, 0.2, (n, 3)); trs[:, 3:7] = scenes.random_unit_quats(rng, n); trs[:, 7:10] = 1.0
+    bounds = np.zeros((n, 6), np.float32); bounds[:, 3:6] = 0.5
+    sc = Scene("chain_fanout", np.array(parent, np.uint32), trs, bounds,
+               np.full(n, scenes.F_INHERITED_VISIBLE | scenes.F_HAS_AABB, np.uint8), np.ones(n, np.uint8),
+               np.arange(n, dtype=np.uint64), cameras=[scenes._camera(0.3)],
+               roots=np.array([0, root], np.uint32))
+    run_parity(sc, frames=3, cluster=False)
+    run_parity(sc, frames=2, cluster=False, static_opt=False)
+
+
+def test_hierarchy_errors():
+    ctx = bb.Context(8)
+    try:
+        with pytest.raises(bb.B200VisError) as e:
+            ctx.set_topology(np.array([1, 2, 0, bb.NO_PARENT], np.uint32), np.arange(4, dtype=np.uint64))
+        assert e.value.code == 4           # B200VIS_ERR_HIERARCHY_CYCLE (panic_when_hierarchy_cycle)
+        with pytest.raises(bb.B200VisError) as e:
+            ctx.set_topology(np.array([bb.NO_PARENT, 9], np.uint32), np.arange(2, dtype=np.uint64))
+        assert e.value.code == 5
+        with pytest.raises(bb.B200VisError) as e:
+            ctx.set_topology(np.zeros(9, np.uint32), np.arange(9, dtype=np.uint64))
+        assert e.value.code == 6
+        with pytest.raises(bb.B200VisError) as e:
+            ctx.run(bb.STAGE_ALL)
+        assert e.value.code == 7
+    finally:
+        ctx.close()
+
+
+def test_empty_world_and_no_lights():
+    sc = Scene("empty", np.zeros(0, np.uint32), np.zeros((0, 10), np.float32), np.zeros((0, 6), np.float32),
+               np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.uint64), cameras=[scenes._camera(0.0)])
+    ctx = bb.Context(1, max_views=1)
+    try:
+        ctx.set_topology(sc.parent, sc.entity_bits)
+        ctx.upload_bounds(0, sc.bounds, sc.flags, sc.class_mask)
+        ctx.set_views([bb.View.make(np.tile([0, 0, 1, 1], (6, 1)))])
+        ctx.run(bb.STAGE_PROPAGATE | bb.STAGE_CULL)
+        assert len(ctx.download_visible(0)) == 0
+    finally:
+        ctx.close()
+
+
+def test_recorded_frame_constants_replay_matches_live_path():
+    """b200vis_snapshot_frame_constants / use_frame_constants (the bench's device-resident replay) gives the
+    same results as uploading the constants from the host."""
+    torch = pytest.importorskip("torch")
+    sc = scenes.forest(n_trees=50, levels=6, n_lights=16)
+    pipe = bb.VisibilityPipeline(sc)
+    try:
+        pipe.run_frame(); pipe.read_feedback()
+        scenes.advance_cameras(sc, 0.02)
+        pipe.update_views()
+        blob = torch.zeros(64 * 1024, dtype=torch.uint8, device="cuda")
+        used = pipe.ctx.snapshot_frame_constants(blob.data_ptr(), blob.numel())
+        assert 0 < used <= blob.numel()
+        pipe.run_frame()
+        live = [pipe.ctx.download_visible(v).copy() for v in range(4)]
+        live_cl = [tuple(a.copy() for a in pipe.ctx.download_clusters(v)) for v in range(4)]
+        # perturb the host-side constants, then replay the recorded blob: results must equal the live frame
+        scenes.advance_cameras(sc, 0.7)
+        pipe.update_views()
+        pipe.ctx.use_frame_constants(blob.data_ptr())
+        pipe.run_frame()
+        for v in range(4):
+            assert (pipe.ctx.download_visible(v) == live[v]).all()
+            off, idx = pipe.ctx.download_clusters(v)
+            assert (off == live_cl[v][0]).all() and (idx == live_cl[v][1]).all()
+        pipe.ctx.use_frame_constants(0)
+    finally:
+        pipe.close()
