@@ -100,8 +100,8 @@ _SIGNATURES = {
     "b200vis_set_views": (C.c_int32, [_vp, C.c_uint32, _P(View)]),
     "b200vis_set_lights": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, _vp]),
     "b200vis_set_cluster_view": (C.c_int32, [_vp, C.c_uint32, _P(ClusterView)]),
-    "b200vis_snapshot_frame_constants": (C.c_int32, [_vp, _vp, C.c_size_t, _P(C.c_size_t)]),
-    "b200vis_use_frame_constants": (C.c_int32, [_vp, _vp]),
+    "b200vis_record_frame_constants": (C.c_int32, [_vp, _P(C.c_uint32)]),
+    "b200vis_use_recorded_frame_constants": (C.c_int32, [_vp, C.c_int32]),
     "b200vis_set_profiling": (C.c_int32, [_vp, C.c_int32]),
     "b200vis_collect_stage_times_ms": (C.c_int32, [_vp, _P(C.c_float), _P(C.c_float), _P(C.c_float), _P(C.c_uint32)]),
     "b200vis_run": (C.c_int32, [_vp, C.c_uint32]),
@@ -279,13 +279,13 @@ class Context:
     def set_cluster_view(self, view, cluster_view):
         self._check(self._lib.b200vis_set_cluster_view(self._h, view, C.byref(cluster_view)))
 
-    def snapshot_frame_constants(self, device_ptr, capacity):
-        n = C.c_size_t(0)
-        self._check(self._lib.b200vis_snapshot_frame_constants(self._h, _vp(device_ptr), capacity, C.byref(n)))
-        return n.value
+    def record_frame_constants(self):
+        slot = C.c_uint32(0)
+        self._check(self._lib.b200vis_record_frame_constants(self._h, C.byref(slot)))
+        return slot.value
 
-    def use_frame_constants(self, device_ptr):
-        self._check(self._lib.b200vis_use_frame_constants(self._h, _vp(device_ptr) if device_ptr else None))
+    def use_recorded_frame_constants(self, slot):
+        self._check(self._lib.b200vis_use_recorded_frame_constants(self._h, -1 if slot is None else int(slot)))
 
     def set_profiling(self, enabled):
         self._check(self._lib.b200vis_set_profiling(self._h, int(bool(enabled))))

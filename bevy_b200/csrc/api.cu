@@ -57,7 +57,9 @@ struct b200vis_ctx {
     FrameConsts *d_consts = nullptr;    // == d_blob
     bool consts_dirty = true;
     size_t blob_used = 0;               // bytes of the last packed blob
-    const uint8_t *ext_blob = nullptr;  // caller-owned device blob (b200vis_use_frame_constants)
+    struct Recorded { FrameConsts host; uint8_t *dev; size_t bytes; };
+    std::vector<Recorded> recorded;     // b200vis_record_frame_constants
+    int replay_slot = -1;               // >= 0: b200vis_run reads recorded[replay_slot] instead of the live copy
     // optional per-stage timing (b200vis_set_profiling)
     bool profiling = false;
     static constexpr int kProfFrames = 256;
@@ -127,6 +129,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     }
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (auto &r : ctx->recorded) if (r.dev) cudaFree(r.dev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -566,20 +569,37 @@ static int32_t flush_consts(b200vis_ctx *ctx) {
     return B200VIS_OK;
 }
 
-extern "C" int32_t b200vis_snapshot_frame_constants(b200vis_ctx *ctx, void *device_dst, size_t capacity, size_t *bytes) {
+extern "C" int32_t b200vis_record_frame_constants(b200vis_ctx *ctx, uint32_t *slot) {
     CHECK_CTX();
+    if (!slot) return fail(ctx, B200VIS_ERR_INVALID_ARG, "record_frame_constants: null");
+    ctx->consts_dirty = true;
     const int32_t rc = flush_consts(ctx); if (rc) return rc;
-    if (bytes) *bytes = ctx->blob_used;
-    if (device_dst) {
-        if (ctx->blob_used > capacity) return fail(ctx, B200VIS_ERR_CAPACITY, "snapshot_frame_constants: %zu > capacity %zu", ctx->blob_used, capacity);
-        CU(cudaMemcpyAsync(device_dst, ctx->d_blob, ctx->blob_used, cudaMemcpyDeviceToDevice, ctx->stream));
-    }
+    b200vis_ctx::Recorded r;
+    r.host = ctx->consts; r.bytes = ctx->blob_used; r.dev = nullptr;
+    CU(cudaMalloc(reinterpret_cast<void **>(&r.dev), r.bytes));
+    CU(cudaMemcpyAsync(r.dev, ctx->d_blob, r.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->recorded.push_back(r);
+    *slot = (uint32_t)ctx->recorded.size() - 1;
     return B200VIS_OK;
 }
-extern "C" int32_t b200vis_use_frame_constants(b200vis_ctx *ctx, const void *device_blob) {
+extern "C" int32_t b200vis_use_recorded_frame_constants(b200vis_ctx *ctx, int32_t slot) {
     if (!ctx) return B200VIS_ERR_INVALID_ARG;
-    ctx->ext_blob = static_cast<const uint8_t *>(device_blob);
+    if (slot >= (int32_t)ctx->recorded.size()) return fail(ctx, B200VIS_ERR_INVALID_ARG, "use_recorded_frame_constants: bad slot %d", slot);
+    ctx->replay_slot = slot < 0 ? -1 : slot;
     return B200VIS_OK;
+}
+static const FrameConsts &active_consts(const b200vis_ctx *ctx) {
+    return ctx->replay_slot >= 0 ? ctx->recorded[ctx->replay_slot].host : ctx->consts;
+}
+static CullViews make_cull_views(const FrameConsts &fc) {
+    CullViews c;
+    memset(&c, 0, sizeof c);
+    c.n_views = fc.n_views;
+    for (uint32_t v = 0; v < fc.n_views && v < (uint32_t)kMaxViews; ++v) {
+        c.on[v] = fc.views[v].flags & 3u; c.range_index[v] = fc.views[v].range_index; c.layers[v] = fc.views[v].layer_mask;
+        for (int k = 0; k < 5; ++k) c.planes[v][k] = fc.views[v].hs[k];
+    }
+    return c;
 }
 
 extern "C" int32_t b200vis_set_profiling(b200vis_ctx *ctx, int32_t enabled) {
@@ -637,10 +657,11 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     cudaStream_t st = ctx->stream;
     const FrameConsts *fc = ctx->d_consts;
     ClusterBufs cl = ctx->cl;
-    if (ctx->ext_blob) {   // constants already resident in HBM (recorded earlier): no host work, no copy
-        fc = reinterpret_cast<const FrameConsts *>(ctx->ext_blob);
-        cl.blob = reinterpret_cast<const float *>(ctx->ext_blob);
+    if (ctx->replay_slot >= 0) {   // constants already resident in HBM (recorded earlier): no host work, no copy
+        fc = reinterpret_cast<const FrameConsts *>(ctx->recorded[ctx->replay_slot].dev);
+        cl.blob = reinterpret_cast<const float *>(ctx->recorded[ctx->replay_slot].dev);
     } else { const int32_t rc = flush_consts(ctx); if (rc) return rc; }
+    const CullViews cvw = make_cull_views(active_consts(ctx));
     Rows R = ctx->rows;
     R.layers = ctx->have_layers ? ctx->d_layers : nullptr;
     R.range = ctx->have_range ? ctx->d_range : nullptr;
@@ -662,9 +683,9 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         if (do_prop) {
             for (uint32_t p = 0; p < n_pass; ++p)
                 launch_propagate_cull(st, R, ctx->d_tiles + ctx->pass_begin[p], ctx->pass_begin[p + 1] - ctx->pass_begin[p],
-                                      fc, ctx->vis, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, parity);
+                                      cvw, ctx->vis, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, parity);
         } else if (n_pass) {
-            launch_propagate_cull(st, R, ctx->d_tiles, ctx->pass_begin[n_pass], fc, ctx->vis, ctx->d_stats,
+            launch_propagate_cull(st, R, ctx->d_tiles, ctx->pass_begin[n_pass], cvw, ctx->vis, ctx->d_stats,
                                   tile_stages, 0, parity);
         }
     }
@@ -749,7 +770,7 @@ extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, ui
                                              uint32_t indices_capacity, uint32_t *total) {
     CHECK_CTX();
     if (view >= ctx->cfg.max_views || !offsets || !total) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_clusters: bad argument");
-    const DevClusterView &cv = ctx->consts.cviews[view];
+    const DevClusterView &cv = active_consts(ctx).cviews[view];
     const uint32_t nc = cv.enabled ? cv.n_clusters : 0;
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(offsets, ctx->cl.offsets + (size_t)view * (kMaxClusters + 1), (size_t)(nc + 1) * 4, cudaMemcpyDeviceToHost, st));

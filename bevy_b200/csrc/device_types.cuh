@@ -56,6 +56,16 @@ struct DevView {
     int32_t range_index;
 };
 
+// What the cull phase reads per view, passed BY VALUE as a __grid_constant__ kernel parameter so that
+// every plane component is a constant-bank operand (772 bytes of the 4 KB parameter space).
+struct CullViews {
+    uint32_t n_views;
+    uint32_t on[kMaxViews];            // bit0 camera.is_active, bit1 NoCpuCulling camera
+    int32_t range_index[kMaxViews];
+    unsigned long long layers[kMaxViews];
+    float4 planes[kMaxViews][5];       // L,R,T,B,Near (the far plane is never used by culling)
+};
+
 struct DevClusterView {
     uint32_t enabled, dims[3], is_ortho, n_clusters;
     uint32_t x_off, y_off;   // offsets (in floats) of the plane tables inside the frame blob

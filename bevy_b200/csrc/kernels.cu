@@ -80,16 +80,11 @@ struct TileSmem {
     uint16_t parent[kTileRows];
     uint8_t st[kTileRows];       // bit0 visited, bit1 gt changed
     uint8_t dirty[kTileRows];    // TransformTreeChanged this frame (mark_dirty_trees)
-    float4 planes[kMaxViews][5]; // the five half spaces culling uses (far is skipped, primitives.rs:255-294)
-    unsigned long long view_layers[kMaxViews];
-    int32_t view_range[kMaxViews];
-    uint32_t view_on[kMaxViews]; // bit0 participates (active [& default layer when SIMPLE]), bit1 NoCpuCulling camera
-    uint32_t n_views;
 };
 
 template <bool PROP, bool CULL, bool SIMPLE>
 __global__ void __launch_bounds__(kTileRows, 4)
-k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__restrict__ fc, VisibleBufs vb,
+k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const __grid_constant__ CullViews cvw, VisibleBufs vb,
                  DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity) {
     __shared__ TileSmem s;
     const Tile tile = tiles[blockIdx.x];
@@ -110,19 +105,6 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__re
         if (PROP) { topo = R.topo[row]; A = R.trsA[row]; q = R.trsB[row]; C = R.trsC[row]; }
         if (CULL) { bA = R.bndA[row]; bB = R.bndB[row]; }
     }
-    if (CULL) {   // stage the per-view constants once per CTA
-        const uint32_t nv = fc->n_views;
-        if (lr == 0) s.n_views = nv;
-        if (lr < nv * 5u) s.planes[lr / 5u][lr % 5u] = fc->views[lr / 5u].hs[lr % 5u];
-        if (lr >= 64u && lr < 64u + nv) {
-            const DevView &dv = fc->views[lr - 64u];
-            const bool on = (dv.flags & 1u) && (!SIMPLE || (dv.layer_mask & 1ull));
-            s.view_on[lr - 64u] = (on ? 1u : 0u) | (dv.flags & 2u);
-            s.view_layers[lr - 64u] = dv.layer_mask;
-            s.view_range[lr - 64u] = dv.range_index;
-        }
-    }
-
     bool visited = false, changed = false;
     if (PROP) {
         const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
@@ -206,11 +188,9 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__re
     // ---- phase 3: cull ----------------------------------------------------------------
     bool vv_changed = false;
     if (CULL) {
-        __syncthreads();   // s.planes / s.view_*
         const bool in_query = active && !(f & F_NO_CPU_CULL);          // Without<NoCpuCulling>
         const bool base = in_query && (f & F_INHERITED);
         const uint32_t prev = st8 & 1u;                                // reset_view_visibility: v = (v&1)<<1
-        const uint32_t nv = s.n_views;
         const uint32_t lane = lr & 31u;
         const bool has_aabb = f & F_AABB;
         const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
@@ -239,23 +219,27 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__re
         }
         bool any = false;
         uint32_t my_ballot = 0;
-        for (uint32_t v = 0; v < nv; ++v) {
-            const uint32_t von = s.view_on[v];
-            if (!(von & 1u)) continue;                                 // !camera.is_active (CTA-uniform)
+        // The per-view constants arrive as a __grid_constant__ kernel parameter: with the view loop
+        // unrolled every plane component is a constant-bank operand of the FMUL/FADD itself (no loads).
+#pragma unroll
+        for (uint32_t v = 0; v < kMaxViews; ++v) {
+            if (v >= cvw.n_views) break;
+            const uint32_t von = cvw.on[v];
+            if (!(von & 1u)) continue;                                 // !camera.is_active (grid-uniform)
+            if (SIMPLE && !(cvw.layers[v] & 1ull)) continue;          // every entity is on the default layer
             bool vis = base;
             if (!SIMPLE) {
-                vis = vis && (s.view_layers[v] & elayers) != 0ull;
+                vis = vis && (cvw.layers[v] & elayers) != 0ull;
                 if ((f & F_RANGE) && R.range != nullptr) {
-                    const int32_t ri = s.view_range[v];
+                    const int32_t ri = cvw.range_index[v];
                     vis = vis && ri >= 0 && ((erange >> ri) & 1u);
                 }
             }
             if (do_test && !(von & 2u)) {
-                const float4 *hs = s.planes[v];
                 // Frustum::intersects_sphere, planes 0..4 (primitives.rs:255-268), branch-free
-                const float d0 = plane_dot_point(hs[0], cx, cy, cz), d1 = plane_dot_point(hs[1], cx, cy, cz);
-                const float d2 = plane_dot_point(hs[2], cx, cy, cz), d3 = plane_dot_point(hs[3], cx, cy, cz);
-                const float d4 = plane_dot_point(hs[4], cx, cy, cz);
+                const float d0 = plane_dot_point(cvw.planes[v][0], cx, cy, cz), d1 = plane_dot_point(cvw.planes[v][1], cx, cy, cz);
+                const float d2 = plane_dot_point(cvw.planes[v][2], cx, cy, cz), d3 = plane_dot_point(cvw.planes[v][3], cx, cy, cz);
+                const float d4 = plane_dot_point(cvw.planes[v][4], cx, cy, cz);
                 const bool out_s = (d0 + radius <= 0.0f) | (d1 + radius <= 0.0f) | (d2 + radius <= 0.0f) |
                                    (d3 + radius <= 0.0f) | (d4 + radius <= 0.0f);
                 vis = vis && !out_s;
@@ -266,7 +250,7 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__re
                     bool out_o = false;
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
-                        const float4 n = hs[k];   // Aabb::relative_radius (primitives.rs:109-119)
+                        const float4 n = cvw.planes[v][k];   // Aabb::relative_radius (primitives.rs:109-119)
                         const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
                         const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
                         const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
@@ -279,19 +263,14 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const FrameConsts *__re
             any |= vis;
             // entities without a VisibilityClass are set_visible() but not listed (mod.rs:846-857)
             const bool listed = vis && (st8 & S_HAS_CLASS);
-            if (SIMPLE) {
+            if (SIMPLE || R.rank == nullptr) {
                 const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
                 if (lane == v) my_ballot = b;
-            } else {
+            } else if (listed) {
                 uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
                 uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
-                if (R.rank == nullptr) {
-                    const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
-                    if (lane == v) my_ballot = b;
-                } else if (listed) {
-                    atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
-                    atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
-                }
+                atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+                atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
             }
         }
         // warp-ballot compaction: lane v publishes view v's 32 bits; 32 consecutive rows touch at
@@ -717,12 +696,12 @@ __global__ void k_pack_state(Rows R, uint32_t first, uint32_t count, uint8_t *__
 // ------------------------------------------------------------------------------------------
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
-void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const FrameConsts *fc,
+void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                            const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
     if (n_tiles == 0) return;
     const bool prop = stages & 1u, cull = stages & 2u;
     const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
-#define B200VIS_LAUNCH(P, C, S) k_propagate_cull<P, C, S><<<n_tiles, kTileRows, 0, st>>>(R, tiles, fc, vb, stats, static_opt, parity)
+#define B200VIS_LAUNCH(P, C, S) k_propagate_cull<P, C, S><<<n_tiles, kTileRows, 0, st>>>(R, tiles, cvw, vb, stats, static_opt, parity)
     if (prop && cull) { if (simple) B200VIS_LAUNCH(true, true, true); else B200VIS_LAUNCH(true, true, false); }
     else if (prop) B200VIS_LAUNCH(true, false, true);
     else if (cull) { if (simple) B200VIS_LAUNCH(false, true, true); else B200VIS_LAUNCH(false, true, false); }

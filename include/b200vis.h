@@ -193,11 +193,12 @@ B200VIS_API int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, cons
                            const uint64_t *layer_mask /* nullable */);
 B200VIS_API int32_t b200vis_set_cluster_view(b200vis_ctx *ctx, uint32_t view, const b200vis_cluster_view *params);
 
-/* Frame constants kept in HBM: snapshot packs the current views / cluster views (one blob, `bytes` long) into
- * caller-owned device memory; use_frame_constants makes b200vis_run read that blob instead of uploading the
- * host copy (NULL returns to the normal path).  Lets a recorded frame sequence replay with no host work. */
-B200VIS_API int32_t b200vis_snapshot_frame_constants(b200vis_ctx *ctx, void *device_dst, size_t capacity, size_t *bytes);
-B200VIS_API int32_t b200vis_use_frame_constants(b200vis_ctx *ctx, const void *device_blob);
+/* Frame constants kept in HBM: record_frame_constants snapshots the current views / cluster views (device copy
+ * of the packed tables + the host copy the kernel parameters are built from) and returns a slot;
+ * use_recorded_frame_constants(slot) makes b200vis_run use that snapshot with no host maths and no upload
+ * (-1 returns to the live path).  Lets a recorded frame sequence replay with every input resident. */
+B200VIS_API int32_t b200vis_record_frame_constants(b200vis_ctx *ctx, uint32_t *slot);
+B200VIS_API int32_t b200vis_use_recorded_frame_constants(b200vis_ctx *ctx, int32_t slot);
 
 /* Optional per-stage device timing: when on, b200vis_run brackets its stages with CUDA events on the
  * context's stream (up to 256 runs are kept).  b200vis_collect_stage_times_ms synchronizes ONCE, returns the

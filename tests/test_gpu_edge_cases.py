@@ -118,6 +118,7 @@ def test_static_frames_change_nothing():
         pipe.update_views()
         compare_frame(pipe, world, 0)
         for f in (1, 2):
+            pipe.update_views()          # cluster constants follow last frame's feedback, as in the reference
             s = compare_frame(pipe, world, f)
             assert s.gt_changed_count == 0 and s.vv_changed_count == 0
     finally:
@@ -177,30 +178,27 @@ def test_empty_world_and_no_lights():
 
 
 def test_recorded_frame_constants_replay_matches_live_path():
-    """b200vis_snapshot_frame_constants / use_frame_constants (the bench's device-resident replay) gives the
-    same results as uploading the constants from the host."""
-    torch = pytest.importorskip("torch")
+    """b200vis_record_frame_constants / use_recorded_frame_constants (the bench's device-resident replay) gives
+    the same results as uploading the constants from the host."""
     sc = scenes.forest(n_trees=50, levels=6, n_lights=16)
     pipe = bb.VisibilityPipeline(sc)
     try:
         pipe.run_frame(); pipe.read_feedback()
         scenes.advance_cameras(sc, 0.02)
         pipe.update_views()
-        blob = torch.zeros(64 * 1024, dtype=torch.uint8, device="cuda")
-        used = pipe.ctx.snapshot_frame_constants(blob.data_ptr(), blob.numel())
-        assert 0 < used <= blob.numel()
+        slot = pipe.ctx.record_frame_constants()
         pipe.run_frame()
         live = [pipe.ctx.download_visible(v).copy() for v in range(4)]
         live_cl = [tuple(a.copy() for a in pipe.ctx.download_clusters(v)) for v in range(4)]
-        # perturb the host-side constants, then replay the recorded blob: results must equal the live frame
+        # perturb the host-side constants, then replay the recorded frame: results must equal the live frame
         scenes.advance_cameras(sc, 0.7)
         pipe.update_views()
-        pipe.ctx.use_frame_constants(blob.data_ptr())
+        pipe.ctx.use_recorded_frame_constants(slot)
         pipe.run_frame()
         for v in range(4):
             assert (pipe.ctx.download_visible(v) == live[v]).all()
             off, idx = pipe.ctx.download_clusters(v)
             assert (off == live_cl[v][0]).all() and (idx == live_cl[v][1]).all()
-        pipe.ctx.use_frame_constants(0)
+        pipe.ctx.use_recorded_frame_constants(None)
     finally:
         pipe.close()
