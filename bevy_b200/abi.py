@@ -83,6 +83,7 @@ _vp = C.c_void_p
 
 _SIGNATURES = {
     "b200vis_abi_version": (C.c_int32, []),
+    "b200vis_struct_sizes": (None, [_P(C.c_uint32)]),
     "b200vis_create": (C.c_int32, [_P(Config), _P(_vp)]),
     "b200vis_destroy": (None, [_vp]),
     "b200vis_last_error": (C.c_char_p, [_vp]),

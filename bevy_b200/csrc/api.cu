@@ -103,6 +103,10 @@ static cudaError_t dalloc(T **p, size_t count) {
 }
 
 extern "C" int32_t b200vis_abi_version(void) { return B200VIS_ABI_VERSION; }
+extern "C" void b200vis_struct_sizes(uint32_t out[6]) {
+    out[0] = sizeof(b200vis_config); out[1] = sizeof(b200vis_view); out[2] = sizeof(b200vis_cluster_view);
+    out[3] = sizeof(b200vis_frame_stats); out[4] = sizeof(b200vis_cluster_config); out[5] = sizeof(b200vis_cluster_feedback);
+}
 
 extern "C" const char *b200vis_last_error(const b200vis_ctx *ctx) {
     return ctx ? ctx->err.c_str() : g_create_error.c_str();

@@ -13,10 +13,10 @@ from . import abi
 
 class VisibilityPipeline:
     def __init__(self, scene, device=0, static_transform_optimizations=True, max_cluster_indices=0,
-                 world_size=1, rank=0, cluster_config=None):
+                 world_size=1, rank=0, cluster_config=None, max_lights=None):
         self.scene = scene
         n, L, V = scene.n, len(scene.light_row), max(len(scene.cameras), 1)
-        self.ctx = abi.Context(n, max_lights=max(L, 1), max_views=V, device=device,
+        self.ctx = abi.Context(n, max_lights=max(L, 1) if max_lights is None else max(max_lights, L, 1), max_views=V, device=device,
                                max_cluster_indices=max_cluster_indices, world_size=world_size, rank=rank)
         c = self.ctx
         c.set_static_transform_optimizations(static_transform_optimizations)

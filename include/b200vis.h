@@ -138,6 +138,9 @@ typedef struct b200vis_frame_stats {
 
 /* ---- lifetime ------------------------------------------------------------- */
 B200VIS_API int32_t b200vis_abi_version(void);
+/* sizeof of the ABI structs, in declaration order (config, view, cluster_view, frame_stats, cluster_config,
+ * cluster_feedback): lets a foreign-language binding verify its layout at start-up. */
+B200VIS_API void b200vis_struct_sizes(uint32_t out[6]);
 B200VIS_API int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out);
 B200VIS_API void b200vis_destroy(b200vis_ctx *ctx);
 B200VIS_API const char *b200vis_last_error(const b200vis_ctx *ctx); /* valid until the next call on ctx; ctx may be NULL */

@@ -1,0 +1,91 @@
+"""torchrun entry: N ranks, one GPU each; every rank runs the CUDA path on its shard, the cluster slabs are
+all-gathered over NCCL, and rank 0 checks the gathered cluster lists + merged visible lists against the
+single-process CPU oracle on the whole scene (bit exact)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import bevy_b200 as bb                      # noqa: E402
+from bevy_b200 import parallel, scenes      # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    per_tree, n_trees, n_lights = 63, 41, 37
+    full = scenes.forest(n_trees=n_trees, levels=6, n_lights=n_lights)
+    sub, rows, (l_lo, l_hi) = parallel.shard_scene(full, rank, world, per_tree)
+    max_lights = max(hi - lo for lo, hi in parallel.shard_bounds(n_lights, world))
+    # every rank is created with the same light capacity so the slabs have one size
+    pipe = bb.VisibilityPipeline(sub, device=local, world_size=world, rank=rank, max_lights=max_lights)
+    ctx = pipe.ctx
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    slab = ctx.cluster_exchange_bytes()
+    send = torch.zeros(slab // 4, dtype=torch.int32, device=dev)
+    recv = torch.zeros(world * slab // 4, dtype=torch.int32, device=dev)
+    ctx.set_cluster_exchange_buffers(send.data_ptr(), recv.data_ptr())
+    V = len(full.cameras)
+    ok = True
+    if rank == 0:
+        import oracle as orc
+        from parity import OracleWorld
+        world_o = OracleWorld(full)
+    for f in range(3):
+        if f:
+            scenes.advance_cameras(full)            # cameras are shared objects between full and sub
+            rws, trs = scenes.mutate_roots(sub, f)
+            ctx.upload_transforms_scattered(rws, trs)
+        pipe.update_views()
+        ctx.run(bb.STAGE_PROPAGATE | bb.STAGE_CULL | bb.STAGE_CLUSTER_ASSIGN)
+        parallel.all_gather_slabs(recv, send)
+        ctx.run(bb.STAGE_CLUSTER_LISTS)
+        stats = ctx.download_frame_stats()
+        far, cnt = parallel.reduce_feedback([stats.cluster_farthest_z[v] for v in range(V)],
+                                            [stats.cluster_index_count[v] for v in range(V)], device=dev)
+        for v in range(V):
+            fb = pipe.feedback[v]
+            fb.has_farthest_z, fb.farthest_z, fb.has_index_count, fb.index_count = 1, float(far[v]), 1, int(cnt[v])
+        vis_local = [sub.entity_bits[ctx.download_visible(v)] for v in range(V)]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [x.tolist() for x in vis_local])
+        clusters = [ctx.download_clusters(v) for v in range(V)]
+        if rank == 0:
+            if f:
+                # the oracle world holds the FULL scene: apply the same root mutation to it
+                full_rows, _ = scenes.mutate_roots(full, f)
+                world_o.tchanged[full_rows] = 1
+            planes = np.stack([np.ctypeslib.as_array(vw.half_spaces).reshape(6, 4).copy() for vw in pipe.views])
+            _, _, lists, cl = world_o.frame(planes)
+            ranges = parallel.shard_bounds(n_lights, world)
+            cap = ((max(1, max_lights) + 31) // 32) * 32
+            for v in range(V):
+                merged = parallel.merge_visible_lists([g[v] for g in gathered])
+                ok &= merged.tolist() == full.entity_bits[lists[v]].tolist()
+                out, off, idx = cl[v]
+                goff, gidx = clusters[v]
+                nc = out.dims[0] * out.dims[1] * out.dims[2]
+                ok &= bool((goff[:nc + 1] == off).all())
+                glob = parallel.global_light_ordinal(gidx, cap, ranges)
+                ok &= glob.tolist() == idx.tolist()
+                ok &= int(cnt[v]) == out.total_index_count
+                ok &= np.float32(far[v]).view(np.uint32) == np.float32(out.farthest_z).view(np.uint32)
+            print(f"frame {f}: {'OK' if ok else 'MISMATCH'}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    pipe.close()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
