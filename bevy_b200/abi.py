@@ -70,6 +70,12 @@ class ClusterFeedback(C.Structure):
                 ("index_count", C.c_uint32)]
 
 
+class CameraDesc(C.Structure):
+    _fields_ = [("global_transform", C.c_float * 12), ("fov_y", C.c_float), ("aspect", C.c_float), ("near_z", C.c_float),
+                ("far_z", C.c_float), ("layer_mask", C.c_uint64), ("flags", C.c_uint8), ("range_view_index", C.c_int8),
+                ("pad", C.c_uint8 * 6)]
+
+
 class FrameStats(C.Structure):
     _fields_ = [("visible_count", C.c_uint32 * MAX_VIEWS), ("cluster_index_count", C.c_uint32 * MAX_VIEWS),
                 ("cluster_farthest_z", C.c_float * MAX_VIEWS), ("cluster_index_overflow", C.c_uint32 * MAX_VIEWS),
@@ -99,6 +105,9 @@ _SIGNATURES = {
     "b200vis_upload_view_visibility": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "b200vis_set_static_transform_optimizations": (C.c_int32, [_vp, C.c_int32]),
     "b200vis_set_views": (C.c_int32, [_vp, C.c_uint32, _P(View)]),
+    "b200vis_set_view_count": (C.c_int32, [_vp, C.c_uint32]),
+    "b200vis_update_camera": (C.c_int32, [_vp, C.c_uint32, _P(CameraDesc), _P(ClusterConfig), _P(ClusterFeedback), _P(ClusterView)]),
+    "b200vis_download_frame": (C.c_int32, [_vp, _P(FrameStats), _vp, C.c_uint32, _vp, _vp, C.c_uint32]),
     "b200vis_set_lights": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, _vp]),
     "b200vis_set_cluster_view": (C.c_int32, [_vp, C.c_uint32, _P(ClusterView)]),
     "b200vis_record_frame_constants": (C.c_int32, [_vp, _P(C.c_uint32)]),
@@ -272,6 +281,23 @@ class Context:
         arr = (View * max(len(views), 1))(*views)
         self._check(self._lib.b200vis_set_views(self._h, len(views), arr))
         self.n_views = len(views)
+
+    def set_view_count(self, n):
+        self._check(self._lib.b200vis_set_view_count(self._h, n))
+        self.n_views = n
+
+    def update_camera(self, view, camera_desc, cluster_config=None, feedback=None, out=None):
+        self._check(self._lib.b200vis_update_camera(self._h, view, C.byref(camera_desc),
+                                                    None if cluster_config is None else C.byref(cluster_config),
+                                                    None if feedback is None else C.byref(feedback),
+                                                    None if out is None else C.byref(out)))
+
+    def download_frame(self, stats, visible_rows, cluster_offsets, cluster_indices):
+        """One batched read-back into caller-owned (ideally pinned) numpy arrays:
+        visible_rows [V, cap_v], cluster_offsets [V, 4097], cluster_indices [V, cap_c]."""
+        self._check(self._lib.b200vis_download_frame(
+            self._h, C.byref(stats), _ptr(visible_rows), 0 if visible_rows is None else visible_rows.shape[1],
+            _ptr(cluster_offsets), _ptr(cluster_indices), 0 if cluster_indices is None else cluster_indices.shape[1]))
 
     def set_lights(self, light_row, light_range, layer_mask=None):
         r = _arr(light_row, np.uint32); g = _arr(light_range, np.float32); l = _arr(layer_mask, np.uint64)

@@ -420,6 +420,16 @@ extern "C" int32_t b200vis_upload_transforms_scattered(b200vis_ctx *ctx, uint32_
     CHECK_CTX();
     if (count && (!rows || !trs)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_transforms_scattered: null");
     if (count > ctx->cfg.max_entities) return fail(ctx, B200VIS_ERR_CAPACITY, "upload_transforms_scattered: count > max_entities");
+    {   // sources already in device memory (a renderer / physics step on the same GPU): no staging copy
+        cudaPointerAttributes pa{}, pb{};
+        if (cudaPointerGetAttributes(&pa, rows) == cudaSuccess && cudaPointerGetAttributes(&pb, trs) == cudaSuccess &&
+            pa.type == cudaMemoryTypeDevice && pb.type == cudaMemoryTypeDevice) {
+            launch_scatter_trs(ctx->stream, ctx->rows, count, rows, trs);
+            CU(cudaGetLastError());
+            return B200VIS_OK;
+        }
+        cudaGetLastError();   // clear the error state cudaPointerGetAttributes leaves for unregistered host memory
+    }
     const size_t off_rows = ((size_t)count * 40 + 15) & ~(size_t)15;
     int32_t rc = stage_in(ctx, trs, (size_t)count * 40, 0); if (rc) return rc;
     rc = stage_in(ctx, rows, (size_t)count * 4, off_rows); if (rc) return rc;
@@ -501,6 +511,42 @@ extern "C" int32_t b200vis_set_views(b200vis_ctx *ctx, uint32_t n_views, const b
         d.layer_mask = views[v].layer_mask; d.flags = views[v].flags; d.range_index = views[v].range_view_index;
     }
     ctx->consts_dirty = true;
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_set_view_count(b200vis_ctx *ctx, uint32_t n_views) {
+    if (!ctx) return B200VIS_ERR_INVALID_ARG;
+    if (n_views > ctx->cfg.max_views) return fail(ctx, B200VIS_ERR_CAPACITY, "set_view_count: %u > max_views %u", n_views, ctx->cfg.max_views);
+    ctx->consts.n_views = n_views;
+    ctx->consts_dirty = true;
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_update_camera(b200vis_ctx *ctx, uint32_t view, const b200vis_camera *cam,
+                                         const b200vis_cluster_config *cfg, const b200vis_cluster_feedback *fb,
+                                         b200vis_cluster_view *out) {
+    if (!ctx) return B200VIS_ERR_INVALID_ARG;
+    if (view >= ctx->cfg.max_views || !cam) return fail(ctx, B200VIS_ERR_INVALID_ARG, "update_camera: bad view %u", view);
+    float cfv[16], hs[6][4];
+    host::perspective_infinite_reverse_rh(cam->fov_y, cam->aspect, cam->near_z, cfv);
+    host::compute_frustum(cfv, cam->global_transform, cam->far_z, hs);
+    DevView &d = ctx->consts.views[view];
+    memcpy(d.hs, hs, sizeof d.hs);
+    d.layer_mask = cam->layer_mask; d.flags = cam->flags; d.range_index = cam->range_view_index;
+    if (ctx->consts.n_views <= view) ctx->consts.n_views = view + 1;
+    ctx->consts_dirty = true;
+    if (cfg) {
+        static thread_local std::vector<float> scratch(3 * 4097 * 4);
+        b200vis_cluster_view cv;
+        int32_t rc = host::cluster_view_setup(cfg, cam->global_transform, cfv, hs, cam->layer_mask, fb, scratch.data(), &cv);
+        if (rc) return fail(ctx, rc, "update_camera: cluster grid of view %u exceeds %d clusters", view, kMaxClusters);
+        rc = b200vis_set_cluster_view(ctx, view, &cv);
+        if (rc) return rc;
+        if (out) *out = cv;
+    } else {
+        ctx->consts.cviews[view].enabled = 0;
+        if (out) memset(out, 0, sizeof *out);
+    }
     return B200VIS_OK;
 }
 
@@ -786,5 +832,42 @@ extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, ui
         CU(cudaMemcpyAsync(indices, ctx->cl.indices + (size_t)view * ctx->cl.index_cap, (size_t)*total * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_download_frame(b200vis_ctx *ctx, b200vis_frame_stats *stats, uint32_t *visible_rows,
+                                          uint32_t visible_capacity, uint32_t *cluster_offsets,
+                                          uint32_t *cluster_indices, uint32_t cluster_capacity) {
+    CHECK_CTX();
+    if (!stats) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_frame: null stats");
+    cudaStream_t st = ctx->stream;
+    const FrameConsts &fc = active_consts(ctx);
+    const uint32_t V = std::min<uint32_t>(fc.n_views, ctx->cfg.max_views);
+    // sync 1: the stats block and the cluster offsets (both small, fixed size) tell how much else to copy
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    if (cluster_offsets)
+        for (uint32_t v = 0; v < V; ++v) {
+            const uint32_t nc = fc.cviews[v].enabled ? fc.cviews[v].n_clusters : 0;
+            CU(cudaMemcpyAsync(cluster_offsets + (size_t)v * (kMaxClusters + 1), ctx->cl.offsets + (size_t)v * (kMaxClusters + 1),
+                               (size_t)(nc + 1) * 4, cudaMemcpyDeviceToHost, st));
+        }
+    CU(cudaStreamSynchronize(st));
+    int32_t rc = b200vis_download_frame_stats(ctx, stats);   // formats h_stats (re-copies 200 bytes)
+    if (rc) return rc;
+    // sync 2: exact-size list copies
+    for (uint32_t v = 0; v < V; ++v) {
+        if (visible_rows) {
+            const uint32_t c = stats->visible_count[v];
+            if (c > visible_capacity) return fail(ctx, B200VIS_ERR_CAPACITY, "download_frame: view %u has %u visible rows > capacity %u", v, c, visible_capacity);
+            CU(cudaMemcpyAsync(visible_rows + (size_t)v * visible_capacity, ctx->vis.lists + (size_t)v * ctx->vis.list_stride, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        }
+        if (cluster_indices && cluster_offsets && fc.cviews[v].enabled) {
+            const uint32_t total = cluster_offsets[(size_t)v * (kMaxClusters + 1) + fc.cviews[v].n_clusters];
+            if (total > cluster_capacity || total > ctx->cl.index_cap)
+                return fail(ctx, B200VIS_ERR_CAPACITY, "download_frame: view %u has %u cluster indices > capacity", v, total);
+            CU(cudaMemcpyAsync(cluster_indices + (size_t)v * cluster_capacity, ctx->cl.indices + (size_t)v * ctx->cl.index_cap, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaStreamSynchronize(st));
     return B200VIS_OK;
 }

@@ -52,6 +52,23 @@ class VisibilityPipeline:
         self.ctx.set_views(views)
         self.views = views
 
+    def update_views_fast(self):
+        """Same as update_views through b200vis_update_camera: one C call per camera, no numpy on the way."""
+        sc = self.scene
+        if not hasattr(self, "_cam_desc"):
+            self._cam_desc = [abi.CameraDesc() for _ in sc.cameras]
+            self.cluster_views = [abi.ClusterView() for _ in sc.cameras]
+            self.ctx.set_view_count(len(sc.cameras))
+        clusters = len(sc.light_row) > 0
+        for v, cam in enumerate(sc.cameras):
+            d = self._cam_desc[v]
+            d.global_transform[:] = cam.gt.tolist()
+            d.fov_y, d.aspect, d.near_z, d.far_z = cam.fov, cam.aspect, cam.near, cam.far
+            d.layer_mask = 1 if sc.view_layers is None else int(sc.view_layers[v])
+            d.flags = abi.VIEW_ACTIVE if sc.view_flags is None else int(sc.view_flags[v])
+            d.range_view_index = -1 if sc.view_range_index is None else int(sc.view_range_index[v])
+            self.ctx.update_camera(v, d, self.cluster_config if clusters else None, self.feedback[v], self.cluster_views[v])
+
     # -- the three systems, by the names BASELINE.json / the reference use -----------------------
     def propagate_transforms(self):
         """TransformSystems::Propagate: mark_dirty_trees + propagate_parent_transforms + sync_simple_transforms."""

@@ -136,6 +136,24 @@ typedef struct b200vis_frame_stats {
     uint32_t pad;
 } b200vis_frame_stats;
 
+/* ClusterConfig + GlobalClusterSettings + viewport, and last frame's Clusters feedback: inputs of the
+ * host-side per-view prologue (b200vis_update_camera / b200vis_host_cluster_view_setup). */
+typedef struct b200vis_cluster_config {      /* ClusterConfig + GlobalClusterSettings + viewport */
+    uint32_t kind;               /* 0 None, 1 Single, 2 XYZ, 3 FixedZ (cluster/mod.rs:107-139) */
+    uint32_t dims[3];            /* XYZ */
+    uint32_t total, z_slices;    /* FixedZ */
+    float    first_slice_depth;  /* ClusterZConfig */
+    uint32_t far_z_mode;         /* 0 MaxClusterableObjectRange, 1 Constant */
+    float    far_z_constant;
+    uint32_t dynamic_resizing;
+    uint32_t screen_w, screen_h; /* Camera::physical_viewport_size */
+    uint32_t view_cluster_bindings_max_indices;
+} b200vis_cluster_config;
+typedef struct b200vis_cluster_feedback {    /* Clusters::last_frame_* (cluster/mod.rs:155-161) */
+    uint32_t has_farthest_z;     float farthest_z;
+    uint32_t has_index_count;    uint32_t index_count;
+} b200vis_cluster_feedback;
+
 /* ---- lifetime ------------------------------------------------------------- */
 B200VIS_API int32_t b200vis_abi_version(void);
 /* sizeof of the ABI structs, in declaration order (config, view, cluster_view, frame_stats, cluster_config,
@@ -211,6 +229,23 @@ B200VIS_API int32_t b200vis_set_profiling(b200vis_ctx *ctx, int32_t enabled);
 B200VIS_API int32_t b200vis_collect_stage_times_ms(b200vis_ctx *ctx, float *tile_ms, float *expand_ms, float *cluster_ms,
                                                    uint32_t *frames);
 
+/* One call per camera per frame: the host-side work of update_frusta (visibility/mod.rs:627-636) and of the
+ * per-view prologue of assign_objects_to_clusters (assign.rs:324-485) for a perspective camera, written
+ * straight into the context's frame constants.  cfg == NULL leaves the view without clusters; `out` (nullable)
+ * receives the cluster view that was set (its plane pointers are only valid until the next call). */
+typedef struct b200vis_camera {
+    float    global_transform[12]; /* camera GlobalTransform, layout as in b200vis_upload_global_transforms */
+    float    fov_y, aspect, near_z, far_z; /* PerspectiveProjection (projection.rs:419-426) */
+    uint64_t layer_mask;
+    uint8_t  flags;                /* B200VIS_VIEW_* */
+    int8_t   range_view_index;
+    uint8_t  pad[6];
+} b200vis_camera;
+B200VIS_API int32_t b200vis_set_view_count(b200vis_ctx *ctx, uint32_t n_views);
+B200VIS_API int32_t b200vis_update_camera(b200vis_ctx *ctx, uint32_t view, const b200vis_camera *camera,
+                                          const b200vis_cluster_config *cfg, const b200vis_cluster_feedback *feedback,
+                                          b200vis_cluster_view *out);
+
 /* ---- run ----------------------------------------------------------------------- */
 B200VIS_API int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages);
 
@@ -232,6 +267,13 @@ B200VIS_API int32_t b200vis_download_visible(b200vis_ctx *ctx, uint32_t view, ui
 B200VIS_API int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, uint32_t *offsets, uint32_t *indices,
                                   uint32_t indices_capacity, uint32_t *total);
 
+/* Everything the shim writes back after a frame, with two stream synchronisations instead of one per list:
+ * the stats block, every view's sorted visible rows (visible_rows[v*visible_capacity ...]) and every view's
+ * cluster CSR (cluster_offsets[v*4097 ...], cluster_indices[v*cluster_capacity ...]).  Array pointers may be NULL. */
+B200VIS_API int32_t b200vis_download_frame(b200vis_ctx *ctx, b200vis_frame_stats *stats, uint32_t *visible_rows,
+                                           uint32_t visible_capacity, uint32_t *cluster_offsets,
+                                           uint32_t *cluster_indices, uint32_t cluster_capacity);
+
 /* ---- multi-GPU cluster exchange (one all-gather per frame, done by the host's collective) ------- */
 /* Each rank fills `slab_bytes` at `send`; after all-gathering the slabs rank-major into `recv`
  * (world_size * slab_bytes) the LISTS stage reads `recv`.  Buffers are caller-allocated device memory
@@ -246,21 +288,7 @@ B200VIS_API void b200vis_host_perspective(float fov_y, float aspect, float near_
 B200VIS_API void b200vis_host_compute_frustum(const float *clip_from_view16, const float *camera_gt12, float far_z,
                                   float half_spaces[6][4]);
 
-typedef struct b200vis_cluster_config {      /* ClusterConfig + GlobalClusterSettings + viewport */
-    uint32_t kind;               /* 0 None, 1 Single, 2 XYZ, 3 FixedZ (cluster/mod.rs:107-139) */
-    uint32_t dims[3];            /* XYZ */
-    uint32_t total, z_slices;    /* FixedZ */
-    float    first_slice_depth;  /* ClusterZConfig */
-    uint32_t far_z_mode;         /* 0 MaxClusterableObjectRange, 1 Constant */
-    float    far_z_constant;
-    uint32_t dynamic_resizing;
-    uint32_t screen_w, screen_h; /* Camera::physical_viewport_size */
-    uint32_t view_cluster_bindings_max_indices;
-} b200vis_cluster_config;
-typedef struct b200vis_cluster_feedback {    /* Clusters::last_frame_* (cluster/mod.rs:155-161) */
-    uint32_t has_farthest_z;     float farthest_z;
-    uint32_t has_index_count;    uint32_t index_count;
-} b200vis_cluster_feedback;
+
 B200VIS_API void b200vis_host_default_cluster_config(b200vis_cluster_config *cfg, uint32_t screen_w, uint32_t screen_h);
 /* The per-view prologue of assign_objects_to_clusters (assign.rs:324-485).  planes_scratch must hold
  * 3*4097*4 floats; out->x/y/z_planes point into it. */

@@ -202,3 +202,29 @@ def test_recorded_frame_constants_replay_matches_live_path():
         pipe.ctx.use_recorded_frame_constants(None)
     finally:
         pipe.close()
+
+
+def test_update_camera_and_batched_download_equal_the_piecewise_calls():
+    sc = scenes.forest(n_trees=40, levels=6, n_lights=20)
+    a, b = bb.VisibilityPipeline(sc), bb.VisibilityPipeline(sc)
+    try:
+        for f in range(3):
+            scenes.advance_cameras(sc, 0.03)
+            a.update_views(); b.update_views_fast()
+            a.run_frame(); b.run_frame()
+            sa = a.read_feedback()
+            V = len(sc.cameras)
+            vis = np.zeros((V, sc.n), np.uint32); off = np.zeros((V, 4097), np.uint32); idx = np.zeros((V, 1 << 16), np.uint32)
+            sb = bb.FrameStats()
+            b.ctx.download_frame(sb, vis, off, idx)
+            for v in range(V):
+                fb = b.feedback[v]
+                fb.has_farthest_z, fb.farthest_z, fb.has_index_count, fb.index_count = 1, sb.cluster_farthest_z[v], 1, sb.cluster_index_count[v]
+                assert sa.visible_count[v] == sb.visible_count[v] and sa.cluster_index_count[v] == sb.cluster_index_count[v]
+                assert (a.ctx.download_visible(v) == vis[v, :sb.visible_count[v]]).all()
+                o, i = a.ctx.download_clusters(v)
+                nc = a.cluster_views[v].dims[0] * a.cluster_views[v].dims[1] * a.cluster_views[v].dims[2]
+                assert tuple(a.cluster_views[v].dims) == tuple(b.cluster_views[v].dims)
+                assert (o[:nc + 1] == off[v, :nc + 1]).all() and (i == idx[v, :off[v, nc]]).all()
+    finally:
+        a.close(); b.close()
