@@ -161,10 +161,11 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         ctx->stream = ctx->own_stream;
         Rows &r = ctx->rows;
-        CU(dalloc(&r.trsA, N)); CU(dalloc(&r.trsB, N)); CU(dalloc(&r.trsC, N));
-        CU(dalloc(&r.gt0, N)); CU(dalloc(&r.gt1, N)); CU(dalloc(&r.gt2, N));
-        CU(dalloc(&r.bndA, N)); CU(dalloc(&r.bndB, N));
-        CU(dalloc(&r.flags, N)); CU(dalloc(&r.state, N)); CU(dalloc(&r.topo, N));
+        const size_t NP = N + 32;   // the TMA-staged tile kernel copies 16-row aligned windows: pad every staged column
+        CU(dalloc(&r.trsA, NP)); CU(dalloc(&r.trsB, NP)); CU(dalloc(&r.trsC, NP));
+        CU(dalloc(&r.gt0, NP)); CU(dalloc(&r.gt1, NP)); CU(dalloc(&r.gt2, NP));
+        CU(dalloc(&r.bndA, NP)); CU(dalloc(&r.bndB, NP));
+        CU(dalloc(&r.flags, NP)); CU(dalloc(&r.state, NP)); CU(dalloc(&r.topo, NP));
         CU(dalloc(&ctx->d_parent, N)); CU(dalloc(&ctx->d_layers, N)); CU(dalloc(&ctx->d_range, N));
         CU(dalloc(&ctx->d_rank, N)); CU(dalloc(&ctx->d_row_of_rank, N)); CU(dalloc(&ctx->d_dirty, N));
         r.parent = ctx->d_parent;

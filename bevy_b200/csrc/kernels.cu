@@ -8,6 +8,7 @@
 // reference's CPU systems.  These are HBM-bound byte/float streaming kernels:
 // no tensor cores on purpose (~1.3 flop/B).
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "device_types.cuh"
@@ -301,6 +302,304 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const __grid_constant__
     if (lr == 0) {
         if (n_gt) atomicAdd(&stats->changed[parity][0], (uint32_t)n_gt);
         if (n_vv) atomicAdd(&stats->changed[parity][1], (uint32_t)n_vv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 1b: the same fused propagate -> cull tile pass as a PERSISTENT, TMA-staged kernel.
+//
+// One CTA per SM slot loops over tiles.  A tile's columns (Transform, old GlobalTransform, bounds,
+// topo, flags, state: 11 arrays, 118 B/row) are pulled into shared memory with cp.async.bulk (the
+// TMA engine, SASS UBLKCP) by ONE elected thread and land on an mbarrier; two stages are kept, so
+// the next tile's 30 KB are in flight while the current tile is computed.  That takes the global
+// loads and their address arithmetic out of the 256 compute threads, keeps >= 2 tiles of loads
+// per CTA in flight independent of occupancy, and lets the hierarchy walk update the
+// GlobalTransform tile IN PLACE in shared memory: a child reads its parent's row of the tile
+// (already new if it changed, still the old bits if set_if_neq kept it), and the finished tile
+// goes back to HBM with one bulk store per matrix row array.
+// Bulk copies need 16-byte aligned addresses and sizes: the window is [base & ~15, round_up16(base + n)),
+// so every array's byte range is 16 B aligned whatever the element size; arrays carry 32 rows of padding.
+// ------------------------------------------------------------------------------------------
+constexpr int kWin = kTileRows + 16;     // rows per staged window (base misalignment <= 15)
+
+struct __align__(128) TileStage {
+    float4 trsA[kWin], trsB[kWin];
+    float4 gt0[kWin], gt1[kWin], gt2[kWin];
+    float4 bndA[kWin];
+    float2 trsC[kWin], bndB[kWin];
+    uint32_t topo[kWin];
+    uint8_t flags[kWin], state[kWin];
+};
+struct TmaSmem {
+    TileStage st[2];
+    unsigned long long bar[2];
+    uint16_t parent[kTileRows];
+    uint8_t pst[kTileRows];      // bit0 visited, bit1 gt changed
+    uint8_t dirty[kTileRows];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+
+template <bool PROP, bool CULL>
+__device__ __forceinline__ void issue_tile_loads(const Rows &R, const Tile &t, TileStage &S, unsigned long long *bar) {
+    const uint32_t a = t.base & ~15u;
+    const uint32_t cnt = ((t.base - a) + t.n_rows + 15u) & ~15u;
+    uint32_t bytes = cnt * (48u + 2u);
+    if (PROP) bytes += cnt * (40u + 4u);
+    if (CULL) bytes += cnt * 24u;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(S.gt0, R.gt0 + a, cnt * 16u, bar); bulk_g2s(S.gt1, R.gt1 + a, cnt * 16u, bar); bulk_g2s(S.gt2, R.gt2 + a, cnt * 16u, bar);
+    bulk_g2s(S.flags, R.flags + a, cnt, bar); bulk_g2s(S.state, R.state + a, cnt, bar);
+    if (PROP) {
+        bulk_g2s(S.trsA, R.trsA + a, cnt * 16u, bar); bulk_g2s(S.trsB, R.trsB + a, cnt * 16u, bar);
+        bulk_g2s(S.trsC, R.trsC + a, cnt * 8u, bar); bulk_g2s(S.topo, R.topo + a, cnt * 4u, bar);
+    }
+    if (CULL) { bulk_g2s(S.bndA, R.bndA + a, cnt * 16u, bar); bulk_g2s(S.bndB, R.bndB + a, cnt * 8u, bar); }
+}
+
+template <bool PROP, bool CULL, bool SIMPLE>
+__global__ void __launch_bounds__(kTileRows, 3)
+k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, const __grid_constant__ CullViews cvw,
+                     VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TmaSmem &s = *reinterpret_cast<TmaSmem *>(smem_raw);
+    const uint32_t lr = threadIdx.x;
+    if (lr == 0) {
+        mbar_init(&s.bar[0], 1); mbar_init(&s.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t t = blockIdx.x;
+    if (lr == 0 && t < n_tiles) issue_tile_loads<PROP, CULL>(R, tiles[t], s.st[0], &s.bar[0]);
+    uint32_t n_gt_total = 0, n_vv_total = 0;
+    for (uint32_t it = 0; t < n_tiles; t += gridDim.x, ++it) {
+        const uint32_t sidx = it & 1u;
+        const Tile tile = tiles[t];
+        if (lr == 0) {
+            const uint32_t tn = t + gridDim.x;
+            if (tn < n_tiles) {
+                // the other stage was last read by the bulk store of the previous tile: wait for its smem reads
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                issue_tile_loads<PROP, CULL>(R, tiles[tn], s.st[sidx ^ 1u], &s.bar[sidx ^ 1u]);
+            }
+        }
+        mbar_wait(&s.bar[sidx], (it >> 1) & 1u);
+        TileStage &S = s.st[sidx];
+        const uint32_t off = tile.base & 15u;
+        const uint32_t li = off + lr;                 // index into the staged window
+        const bool active = lr < tile.n_rows;
+        const uint32_t row = tile.base + lr;
+        const uint32_t f = active ? S.flags[li] : 0u;
+        const uint32_t st8 = active ? S.state[li] : 0u;
+
+        bool visited = false, changed = false;
+        if (PROP) {
+            const uint32_t topo = active ? S.topo[li] : T_DETACHED;
+            const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
+            const bool tchanged = f & F_TCHANGED;
+            const bool has_children = topo & T_HAS_CHILDREN;
+            bool dirty = tchanged;
+            if (static_opt && R.dirty != nullptr) {
+                dirty = active && R.dirty[row];
+            } else if (static_opt && tile.n_levels > 1) {
+                s.parent[lr] = (uint16_t)((depth > 0) ? plocal : 0xFFFFu);
+                s.dirty[lr] = 0;
+                __syncthreads();
+                if (active && tchanged) {
+                    uint32_t c = lr;
+                    while (!s.dirty[c]) {
+                        s.dirty[c] = 1;
+                        const uint32_t p = s.parent[c];
+                        if (p == 0xFFFFu) break;
+                        c = p;
+                    }
+                }
+                __syncthreads();
+                dirty = s.dirty[lr];
+            }
+            const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
+            const uint32_t my_level = (active && !(topo & T_DETACHED)) ? depth : 0xFFFFFFFFu;
+            if (active && (topo & T_DETACHED) && has_children) s.pst[lr] = 0;
+            if (my_level == 0) {
+                Aff n = l;
+                if (topo & T_ROOT) {
+                    visited = has_children ? (!static_opt || dirty) : tchanged;
+                    changed = visited;
+                } else {
+                    const uint32_t pr = R.parent[row];
+                    const uint32_t ps = R.state[pr];
+                    visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
+                    if (visited) {
+                        n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
+                        changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);
+                    }
+                }
+                if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+                if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+            }
+            for (uint32_t lvl = 1; lvl < tile.n_levels; ++lvl) {
+                if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) __syncwarp(); else __syncthreads();
+                if (my_level == lvl) {
+                    const uint32_t pst = s.pst[plocal];
+                    const uint32_t pi = off + plocal;
+                    visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                    if (visited) {
+                        Aff n;   // the parent's rows are the tile's own (in-place) GlobalTransform entries
+                        n.r0 = affine_mul_row(S.gt0[pi], l); n.r1 = affine_mul_row(S.gt1[pi], l); n.r2 = affine_mul_row(S.gt2[pi], l);
+                        changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);   // set_if_neq
+                        if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+                    }
+                    if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+                }
+            }
+            if (active && tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
+        }
+        uint32_t out = st8 & (S_VV | S_HAS_CLASS);
+        if (PROP) out |= (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
+        else out |= st8 & (S_GT_CHANGED | S_VISITED);
+
+        bool vv_changed = false;
+        if (CULL) {
+            Aff g; g.r0 = S.gt0[li]; g.r1 = S.gt1[li]; g.r2 = S.gt2[li];   // own row: written by this thread or untouched
+            const float4 bA = S.bndA[li];
+            const float2 bB = S.bndB[li];
+            const bool in_query = active && !(f & F_NO_CPU_CULL);
+            const bool base = in_query && (f & F_INHERITED);
+            const uint32_t prev = st8 & 1u;
+            const uint32_t lane = lr & 31u;
+            const bool has_aabb = f & F_AABB;
+            const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
+            float cx, cy, cz, radius;
+            const float hx = bA.w, hy = bB.x, hz = bB.y;
+            if (has_aabb) {
+                cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;
+                cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
+                cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+                const float vx = (g.r0.x * hx + g.r0.y * hy) + g.r0.z * hz;
+                const float vy = (g.r1.x * hx + g.r1.y * hy) + g.r1.z * hz;
+                const float vz = (g.r2.x * hx + g.r2.y * hy) + g.r2.z * hz;
+                radius = sqrtf((vx * vx + vy * vy) + vz * vz);
+            } else {
+                const bool from_gt = f & F_SPHERE_GT;
+                cx = from_gt ? g.r0.w : bA.x; cy = from_gt ? g.r1.w : bA.y; cz = from_gt ? g.r2.w : bA.z;
+                radius = bA.w;
+            }
+            unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
+            if (!SIMPLE && active) {
+                if (R.layers != nullptr) elayers = R.layers[row];
+                if ((f & F_RANGE) && R.range != nullptr) erange = R.range[row];
+                if (R.rank != nullptr) rnk = R.rank[row];
+            }
+            bool any = false;
+            uint32_t my_ballot = 0;
+#pragma unroll
+            for (uint32_t v = 0; v < kMaxViews; ++v) {
+                if (v >= cvw.n_views) break;
+                const uint32_t von = cvw.on[v];
+                if (!(von & 1u)) continue;
+                if (SIMPLE && !(cvw.layers[v] & 1ull)) continue;
+                bool vis = base;
+                if (!SIMPLE) {
+                    vis = vis && (cvw.layers[v] & elayers) != 0ull;
+                    if ((f & F_RANGE) && R.range != nullptr) {
+                        const int32_t ri = cvw.range_index[v];
+                        vis = vis && ri >= 0 && ((erange >> ri) & 1u);
+                    }
+                }
+                if (do_test && !(von & 2u)) {
+                    const float d0 = plane_dot_point(cvw.planes[v][0], cx, cy, cz), d1 = plane_dot_point(cvw.planes[v][1], cx, cy, cz);
+                    const float d2 = plane_dot_point(cvw.planes[v][2], cx, cy, cz), d3 = plane_dot_point(cvw.planes[v][3], cx, cy, cz);
+                    const float d4 = plane_dot_point(cvw.planes[v][4], cx, cy, cz);
+                    const bool out_s = (d0 + radius <= 0.0f) | (d1 + radius <= 0.0f) | (d2 + radius <= 0.0f) |
+                                       (d3 + radius <= 0.0f) | (d4 + radius <= 0.0f);
+                    vis = vis && !out_s;
+                    if (vis && has_aabb) {
+                        const float d[5] = {d0, d1, d2, d3, d4};
+                        bool out_o = false;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            const float4 n = cvw.planes[v][k];
+                            const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+                            const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+                            const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+                            const float rr = (dx * hx + dy * hy) + dz * hz;
+                            out_o |= (d[k] + rr <= 0.0f);
+                        }
+                        vis = !out_o;
+                    }
+                }
+                any |= vis;
+                const bool listed = vis && (st8 & S_HAS_CLASS);
+                if (SIMPLE || R.rank == nullptr) {
+                    const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
+                    if (lane == v) my_ballot = b;
+                } else if (listed) {
+                    uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
+                    uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
+                    atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+                    atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
+                }
+            }
+            if (my_ballot) {
+                uint32_t *mask = vb.mask + (size_t)lane * vb.words_stride;
+                uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + lane) * vb.chunks_stride;
+                const uint32_t row0 = row - lane, w0 = row0 >> 5, sh = row0 & 31u;
+                const uint32_t lo = my_ballot << sh, hi = sh ? (my_ballot >> (32u - sh)) : 0u;
+                if (lo) { atomicOr(mask + w0, lo); atomicAdd(cc + (w0 / kChunkWords), __popc(lo)); }
+                if (hi) { atomicOr(mask + w0 + 1, hi); atomicAdd(cc + ((w0 + 1) / kChunkWords), __popc(hi)); }
+            }
+            if (in_query) {
+                out = (out & ~S_VV) | (any ? (1u | (prev << 1)) : 0u);
+                vv_changed = (any ? 1u : 0u) != prev;
+                if (vv_changed) out |= S_VV_CHANGED;
+            }
+        } else {
+            out |= st8 & S_VV_CHANGED;
+        }
+        if (active && out != st8) R.state[row] = (uint8_t)out;
+
+        // end of tile: everybody is done with this stage; count changes; write the tile's matrices back
+        const int n_gt = __syncthreads_count(PROP && changed);
+        const int n_vv = CULL ? __syncthreads_count(vv_changed) : 0;
+        if (lr == 0) {
+            n_gt_total += (uint32_t)n_gt; n_vv_total += (uint32_t)n_vv;
+            if (PROP && n_gt) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
+                const uint32_t bytes = (uint32_t)tile.n_rows * 16u;
+                bulk_s2g(R.gt0 + tile.base, S.gt0 + off, bytes); bulk_s2g(R.gt1 + tile.base, S.gt1 + off, bytes);
+                bulk_s2g(R.gt2 + tile.base, S.gt2 + off, bytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (lr == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (n_gt_total) atomicAdd(&stats->changed[parity][0], n_gt_total);
+        if (n_vv_total) atomicAdd(&stats->changed[parity][1], n_vv_total);
     }
 }
 
@@ -696,11 +995,42 @@ __global__ void k_pack_state(Rows R, uint32_t first, uint32_t count, uint8_t *__
 // ------------------------------------------------------------------------------------------
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
+static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged
+static int tile_kernel_choice() {
+    if (g_tile_kernel < 0) {
+        const char *e = getenv("B200VIS_TILE_KERNEL");
+        g_tile_kernel = (e && e[0] == 'c') ? 0 : 1;
+    }
+    return g_tile_kernel;
+}
+template <bool P, bool C, bool S>
+static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
+                       const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity) {
+    static int grid = 0;
+    if (!grid) {
+        cudaFuncSetAttribute(k_propagate_cull_tma<P, C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem));
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate_cull_tma<P, C, S>, kTileRows, sizeof(TmaSmem));
+        grid = sms * (per_sm > 0 ? per_sm : 1);    // persistent: one CTA per resident slot
+    }
+    const uint32_t g = n_tiles < (uint32_t)grid ? n_tiles : (uint32_t)grid;
+    k_propagate_cull_tma<P, C, S><<<g, kTileRows, sizeof(TmaSmem), st>>>(R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
+}
 void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                            const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
     if (n_tiles == 0) return;
     const bool prop = stages & 1u, cull = stages & 2u;
     const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+    if (tile_kernel_choice() == 1) {
+#define B200VIS_LAUNCH_TMA(P, C, S) launch_tma<P, C, S>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity)
+        if (prop && cull) { if (simple) B200VIS_LAUNCH_TMA(true, true, true); else B200VIS_LAUNCH_TMA(true, true, false); }
+        else if (prop) B200VIS_LAUNCH_TMA(true, false, true);
+        else if (cull) { if (simple) B200VIS_LAUNCH_TMA(false, true, true); else B200VIS_LAUNCH_TMA(false, true, false); }
+#undef B200VIS_LAUNCH_TMA
+        return;
+    }
 #define B200VIS_LAUNCH(P, C, S) k_propagate_cull<P, C, S><<<n_tiles, kTileRows, 0, st>>>(R, tiles, cvw, vb, stats, static_opt, parity)
     if (prop && cull) { if (simple) B200VIS_LAUNCH(true, true, true); else B200VIS_LAUNCH(true, true, false); }
     else if (prop) B200VIS_LAUNCH(true, false, true);
