@@ -186,7 +186,11 @@ def main():
     V = len(scene.cameras)
     pipe = bb.VisibilityPipeline(scene, device=local_rank, world_size=world, rank=rank)
     ctx = pipe.ctx
-    stream = torch.cuda.current_stream()
+    # Everything (library kernels, copies, NCCL, timing events) runs on ONE explicit non-default stream: torch's
+    # default stream has handle 0, which b200vis_set_stream reads as "use the context's own stream".
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     send = recv = None
     if world > 1:
@@ -315,6 +319,7 @@ def main():
     th0 = time.perf_counter()
     for i in range(W, W + K):
         value_step(i)
+    ctx.join()                      # the last frame's tail (side stream) belongs to the timed region
     host_enqueue_ms = (time.perf_counter() - th0) * 1e3 / K
     ev1.record(stream)
     barrier()

@@ -95,6 +95,7 @@ _SIGNATURES = {
     "b200vis_last_error": (C.c_char_p, [_vp]),
     "b200vis_set_stream": (C.c_int32, [_vp, _vp]),
     "b200vis_synchronize": (C.c_int32, [_vp]),
+    "b200vis_join": (C.c_int32, [_vp]),
     "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
     "b200vis_plan_row_order": (C.c_int32, [C.c_uint32, _vp, _vp]),
     "b200vis_upload_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
@@ -232,6 +233,9 @@ class Context:
 
     def set_stream(self, cuda_stream):
         self._check(self._lib.b200vis_set_stream(self._h, _vp(cuda_stream)))
+
+    def join(self):
+        self._check(self._lib.b200vis_join(self._h))
 
     def synchronize(self):
         self._check(self._lib.b200vis_synchronize(self._h))

@@ -28,6 +28,13 @@ struct b200vis_ctx {
     b200vis_config cfg{};
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // Frame pipelining: the latency-bound tail of frame f (visible-list expansion, cluster kernels) runs on a side
+    // stream while frame f+1's tile pass already runs on the main stream (masks / counters / constants are
+    // double or triple buffered by frame number).
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_tile = nullptr, ev_side[2] = {nullptr, nullptr};
+    bool pipeline = true, side_pending = false;
+    float4 *d_light_snap = nullptr;     // [2][max_lights]
     std::string err;
 
     uint32_t n = 0;                 // current row count
@@ -53,7 +60,8 @@ struct b200vis_ctx {
     cudaEvent_t ring_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
     int ring_next = 0;
     size_t blob_cap = 0;
-    uint8_t *d_blob = nullptr;
+    uint8_t *d_blob2[2] = {nullptr, nullptr};   // live-mode device blobs, slot = frame % 2
+    uint8_t *d_blob = nullptr;          // the one the current frame uses
     FrameConsts *d_consts = nullptr;    // == d_blob
     bool consts_dirty = true;
     size_t blob_used = 0;               // bytes of the last packed blob
@@ -63,7 +71,7 @@ struct b200vis_ctx {
     // optional per-stage timing (b200vis_set_profiling)
     bool profiling = false;
     static constexpr int kProfFrames = 256;
-    cudaEvent_t (*prof_ev)[4] = nullptr;   // [kProfFrames][4], created on first use
+    cudaEvent_t (*prof_ev)[6] = nullptr;   // [kProfFrames][6]: main 0,1 (tile); side 2,3,4 (expand, cluster); created on first use
     int prof_count = 0;
 
     // visible set
@@ -119,7 +127,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     Rows &r = ctx->rows;
     void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
-                   ctx->d_tiles, ctx->d_blob,
+                   ctx->d_tiles, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_light_snap,
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage};
     for (void *p : dev) if (p) cudaFree(p);
@@ -134,6 +142,9 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto &r : ctx->recorded) if (r.dev) cudaFree(r.dev);
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->ev_tile) cudaEventDestroy(ctx->ev_tile);
+    for (cudaEvent_t e : ctx->ev_side) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -174,8 +185,13 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         CU(dalloc(&ctx->d_tiles, ctx->tiles_cap));
         // worst case tables: every view with three (kMaxClusters+1)-entry plane tables + kMaxClusters thresholds
         ctx->blob_cap = sizeof(FrameConsts) + V * (3 * (size_t)(kMaxClusters + 1) * 16 + (size_t)kMaxClusters * 4);
-        CU(dalloc(&ctx->d_blob, ctx->blob_cap));
+        CU(dalloc(&ctx->d_blob2[0], ctx->blob_cap)); CU(dalloc(&ctx->d_blob2[1], ctx->blob_cap));
+        ctx->d_blob = ctx->d_blob2[0];
         ctx->d_consts = reinterpret_cast<FrameConsts *>(ctx->d_blob);
+        CU(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_tile, cudaEventDisableTiming));
+        for (cudaEvent_t &e : ctx->ev_side) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        { const char *e = getenv("B200VIS_PIPELINE"); if (e && e[0] == '0') ctx->pipeline = false; }
         for (int i = 0; i < b200vis_ctx::kRing; ++i) {
             CU(cudaMallocHost(&ctx->h_ring[i], ctx->blob_cap));
             CU(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
@@ -185,13 +201,14 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         vb.words_stride = (uint32_t)((N + 31) / 32 + 2);
         vb.chunks_stride = (vb.words_stride + kChunkWords - 1) / kChunkWords + 1;
         vb.list_stride = (uint32_t)std::max<size_t>(N, 1);
-        CU(dalloc(&vb.mask, (size_t)vb.words_stride * V));
-        CU(dalloc(&vb.chunk_count, (size_t)2 * kMaxViews * vb.chunks_stride));
+        CU(dalloc(&vb.mask, (size_t)2 * vb.words_stride * V));
+        CU(dalloc(&vb.chunk_count, (size_t)3 * kMaxViews * vb.chunks_stride));
         CU(dalloc(&vb.lists, (size_t)vb.list_stride * V));
         CU(dalloc(&ctx->d_stats, 1));
         CU(cudaMallocHost(&ctx->h_stats, sizeof(DevStats)));
         // lights + clusters
         const size_t Lm = std::max<uint32_t>(cfg->max_lights, 1);
+        CU(dalloc(&ctx->d_light_snap, 2 * Lm));
         CU(dalloc(&ctx->d_light_row, Lm)); CU(dalloc(&ctx->d_light_range, Lm)); CU(dalloc(&ctx->d_light_layers, Lm));
         ClusterBufs &cl = ctx->cl;
         cl.words = (uint32_t)((Lm + 31) / 32); cl.max_lights = cl.words * 32; cl.world = ctx->cfg.world_size;
@@ -199,7 +216,7 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         ctx->slab_bytes = (size_t)V * cl.words * kMaxClusters * sizeof(uint32_t);
         CU(dalloc(&ctx->d_slab, ctx->slab_bytes / 4));
         cl.send = ctx->d_slab; cl.recv = ctx->d_slab;
-        cl.blob = reinterpret_cast<const float *>(ctx->d_blob);
+        cl.blob = reinterpret_cast<const float *>(ctx->d_blob);   // re-pointed per frame
         CU(dalloc(&cl.offsets, V * (kMaxClusters + 1)));
         CU(dalloc(&cl.indices, V * (size_t)cl.index_cap));
         ctx->stage_bytes = std::max<size_t>(N, 1) * 64;
@@ -216,6 +233,11 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
     if (!ctx) return B200VIS_ERR_INVALID_ARG;                              \
     CU(cudaSetDevice(ctx->device))
 
+static int32_t join_side(b200vis_ctx *ctx);
+#define CHECK_CTX_JOIN()                                                   \
+    CHECK_CTX();                                                           \
+    { const int32_t jrc_ = join_side(ctx); if (jrc_) return jrc_; }
+
 static int32_t check_range(b200vis_ctx *ctx, uint32_t first, uint32_t count, const char *what) {
     if ((uint64_t)first + count > ctx->cfg.max_entities)
         return fail(ctx, B200VIS_ERR_CAPACITY, "%s: rows [%u, %u) exceed max_entities %u", what, first, first + count,
@@ -224,13 +246,13 @@ static int32_t check_range(b200vis_ctx *ctx, uint32_t first, uint32_t count, con
 }
 
 extern "C" int32_t b200vis_set_stream(b200vis_ctx *ctx, void *cuda_stream) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_synchronize(b200vis_ctx *ctx) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     CU(cudaStreamSynchronize(ctx->stream));
     return B200VIS_OK;
 }
@@ -330,7 +352,7 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
 }
 
 extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, const uint64_t *entity_bits) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     if (n && (!parent || !entity_bits)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_topology: null array");
     if (n > ctx->cfg.max_entities) return fail(ctx, B200VIS_ERR_CAPACITY, "set_topology: %u rows > max_entities %u", n, ctx->cfg.max_entities);
     std::vector<uint32_t> topo; std::vector<Tile> tiles;
@@ -366,8 +388,8 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     ctx->vis.n_words = (n + 31) / 32;
     ctx->vis.n_chunks = (ctx->vis.n_words + kChunkWords - 1) / kChunkWords;
     // fresh accumulation state
-    CU(cudaMemset(ctx->vis.mask, 0, (size_t)ctx->vis.words_stride * ctx->cfg.max_views * 4));
-    CU(cudaMemset(ctx->vis.chunk_count, 0, (size_t)2 * kMaxViews * ctx->vis.chunks_stride * 4));
+    CU(cudaMemset(ctx->vis.mask, 0, (size_t)2 * ctx->vis.words_stride * ctx->cfg.max_views * 4));
+    CU(cudaMemset(ctx->vis.chunk_count, 0, (size_t)3 * kMaxViews * ctx->vis.chunks_stride * 4));
     CU(cudaMemset(ctx->d_stats, 0, sizeof(DevStats)));
     CU(cudaMemset(ctx->d_slab, 0, ctx->slab_bytes));
     ctx->topology_set = true;
@@ -656,7 +678,7 @@ static CullViews make_cull_views(const FrameConsts &fc) {
 extern "C" int32_t b200vis_set_profiling(b200vis_ctx *ctx, int32_t enabled) {
     CHECK_CTX();
     if (enabled && !ctx->prof_ev) {
-        ctx->prof_ev = new cudaEvent_t[b200vis_ctx::kProfFrames][4]();
+        ctx->prof_ev = new cudaEvent_t[b200vis_ctx::kProfFrames][6]();
         for (int i = 0; i < b200vis_ctx::kProfFrames; ++i) for (cudaEvent_t &e : ctx->prof_ev[i]) CU(cudaEventCreate(&e));
     }
     ctx->profiling = enabled != 0;
@@ -666,10 +688,15 @@ extern "C" int32_t b200vis_set_profiling(b200vis_ctx *ctx, int32_t enabled) {
 extern "C" int32_t b200vis_collect_stage_times_ms(b200vis_ctx *ctx, float *tile_ms, float *expand_ms, float *cluster_ms, uint32_t *frames) {
     CHECK_CTX();
     if (!ctx->prof_ev) return fail(ctx, B200VIS_ERR_NOT_READY, "profiling was never enabled");
+    { const int32_t rc = join_side(ctx); if (rc) return rc; }
     CU(cudaStreamSynchronize(ctx->stream));
     double s[3] = {0, 0, 0};
-    for (int i = 0; i < ctx->prof_count; ++i)
-        for (int k = 0; k < 3; ++k) { float t = 0; CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][k], ctx->prof_ev[i][k + 1])); s[k] += t; }
+    for (int i = 0; i < ctx->prof_count; ++i) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][0], ctx->prof_ev[i][1])); s[0] += t;   // tile pass (main stream)
+        CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][2], ctx->prof_ev[i][3])); s[1] += t;   // visible-list expansion
+        CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][3], ctx->prof_ev[i][4])); s[2] += t;   // cluster kernels
+    }
     if (tile_ms) *tile_ms = (float)s[0];
     if (expand_ms) *expand_ms = (float)s[1];
     if (cluster_ms) *cluster_ms = (float)s[2];
@@ -687,7 +714,7 @@ extern "C" int32_t b200vis_cluster_exchange_bytes(const b200vis_ctx *ctx, size_t
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_set_cluster_exchange_buffers(b200vis_ctx *ctx, void *send, void *recv) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     if ((send == nullptr) != (recv == nullptr)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "exchange buffers: both or neither");
     CU(cudaStreamSynchronize(ctx->stream));
     if (send) {
@@ -701,32 +728,62 @@ extern "C" int32_t b200vis_set_cluster_exchange_buffers(b200vis_ctx *ctx, void *
 // ------------------------------------------------------------------------------------------
 // run
 // ------------------------------------------------------------------------------------------
+// Makes the main stream wait for whatever the side stream still has in flight (cheap, asynchronous).
+static int32_t join_side(b200vis_ctx *ctx) {
+    if (ctx->side_pending) {
+        for (cudaEvent_t e : ctx->ev_side) CU(cudaStreamWaitEvent(ctx->stream, e, 0));
+        ctx->side_pending = false;
+    }
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_join(b200vis_ctx *ctx) {
+    CHECK_CTX();
+    return join_side(ctx);
+}
+
 extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     CHECK_CTX();
     if (!ctx->topology_set) return fail(ctx, B200VIS_ERR_NOT_READY, "run: b200vis_set_topology has not been called");
     if ((stages & B200VIS_STAGE_CULL) && !ctx->bounds_set) return fail(ctx, B200VIS_ERR_NOT_READY, "run: bounds/flags were never uploaded");
     cudaStream_t st = ctx->stream;
-    const FrameConsts *fc = ctx->d_consts;
+    const bool do_prop = stages & B200VIS_STAGE_PROPAGATE, do_cull = stages & B200VIS_STAGE_CULL;
+    // Pipelined mode: the whole frame in one call on one GPU.  The tail of frame f (expand + cluster) goes to the side
+    // stream and overlaps frame f+1's tile pass; frame f+2's tile pass waits for it (it reuses frame f's buffers).
+    const bool pipelined = ctx->pipeline && stages == B200VIS_STAGE_ALL && ctx->cl.world == 1;
+    const uint32_t frame = ctx->frame;
+    const uint32_t cslot = frame % 3u, mslot = frame & 1u;
+    if (pipelined) {
+        if (ctx->side_pending && frame >= 2) CU(cudaStreamWaitEvent(st, ctx->ev_side[mslot], 0));   // tail of frame f-2
+    } else {
+        const int32_t rc = join_side(ctx); if (rc) return rc;
+    }
     ClusterBufs cl = ctx->cl;
+    const FrameConsts *fc;
     if (ctx->replay_slot >= 0) {   // constants already resident in HBM (recorded earlier): no host work, no copy
         fc = reinterpret_cast<const FrameConsts *>(ctx->recorded[ctx->replay_slot].dev);
-        cl.blob = reinterpret_cast<const float *>(ctx->recorded[ctx->replay_slot].dev);
-    } else { const int32_t rc = flush_consts(ctx); if (rc) return rc; }
+    } else {
+        ctx->d_blob = ctx->d_blob2[mslot];          // the side stream may still read the other copy
+        ctx->d_consts = reinterpret_cast<FrameConsts *>(ctx->d_blob);
+        ctx->consts_dirty = ctx->consts_dirty || pipelined;   // each copy must be current
+        const int32_t rc = flush_consts(ctx); if (rc) return rc;
+        fc = ctx->d_consts;
+    }
+    cl.blob = reinterpret_cast<const float *>(fc);
     const CullViews cvw = make_cull_views(active_consts(ctx));
     Rows R = ctx->rows;
     R.layers = ctx->have_layers ? ctx->d_layers : nullptr;
     R.range = ctx->have_range ? ctx->d_range : nullptr;
     R.rank = ctx->rank_identity ? nullptr : ctx->d_rank;
     R.row_of_rank = ctx->rank_identity ? nullptr : ctx->d_row_of_rank;
+    VisibleBufs vb = ctx->vis;
+    vb.mask = ctx->vis.mask + (size_t)mslot * ctx->vis.words_stride * ctx->cfg.max_views;
     const uint32_t n_pass = ctx->pass_begin.empty() ? 0 : (uint32_t)ctx->pass_begin.size() - 1;
-    const bool do_prop = stages & B200VIS_STAGE_PROPAGATE, do_cull = stages & B200VIS_STAGE_CULL;
     R.dirty = nullptr;
     if (do_prop && ctx->static_opt && n_pass > 1) {
         CU(cudaMemsetAsync(ctx->d_dirty, 0, ctx->n, st));
         R.dirty = ctx->d_dirty;
         launch_mark_dirty_global(st, R);
     }
-    const uint32_t parity = ctx->parity;
     cudaEvent_t *pe = (ctx->profiling && ctx->prof_count < b200vis_ctx::kProfFrames) ? ctx->prof_ev[ctx->prof_count++] : nullptr;
     if (pe) CU(cudaEventRecord(pe[0], st));
     if (do_prop || do_cull) {
@@ -734,22 +791,33 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         if (do_prop) {
             for (uint32_t p = 0; p < n_pass; ++p)
                 launch_propagate_cull(st, R, ctx->d_tiles + ctx->pass_begin[p], ctx->pass_begin[p + 1] - ctx->pass_begin[p],
-                                      cvw, ctx->vis, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, parity);
+                                      cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot);
         } else if (n_pass) {
-            launch_propagate_cull(st, R, ctx->d_tiles, ctx->pass_begin[n_pass], cvw, ctx->vis, ctx->d_stats,
-                                  tile_stages, 0, parity);
+            launch_propagate_cull(st, R, ctx->d_tiles, ctx->pass_begin[n_pass], cvw, vb, ctx->d_stats, tile_stages, 0, cslot);
         }
     }
-    if (pe) CU(cudaEventRecord(pe[1], st));
-    if (do_cull) launch_expand_visible(st, ctx->vis, R.row_of_rank, fc, ctx->d_stats, parity, ctx->n, ctx->cfg.max_views);
-    if (pe) CU(cudaEventRecord(pe[2], st));
+    Lights lights = ctx->lights;
+    lights.snap = nullptr;
+    cudaStream_t tail = st;
+    if (pipelined) {
+        lights.snap = ctx->d_light_snap + (size_t)mslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
+        launch_snapshot_lights(st, R, lights, const_cast<float4 *>(lights.snap));
+        if (pe) CU(cudaEventRecord(pe[1], st));
+        CU(cudaEventRecord(ctx->ev_tile, st));
+        tail = ctx->side_stream;
+        CU(cudaStreamWaitEvent(tail, ctx->ev_tile, 0));
+    } else if (pe) CU(cudaEventRecord(pe[1], st));
+    if (pe) CU(cudaEventRecord(pe[2], tail));
+    if (do_cull) launch_expand_visible(tail, vb, R.row_of_rank, fc, ctx->d_stats, cslot, ctx->n, ctx->cfg.max_views);
+    if (pe) CU(cudaEventRecord(pe[3], tail));
     if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
-        launch_cluster_assign(st, R, ctx->lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+        launch_cluster_assign(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if (stages & B200VIS_STAGE_CLUSTER_LISTS)
-        launch_cluster_lists(st, fc, cl, ctx->d_stats, ctx->cfg.max_views);
-    if (pe) CU(cudaEventRecord(pe[3], st));
+        launch_cluster_lists(tail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+    if (pe) CU(cudaEventRecord(pe[4], tail));
+    if (pipelined) { CU(cudaEventRecord(ctx->ev_side[mslot], tail)); ctx->side_pending = true; }
     CU(cudaGetLastError());
-    if (do_cull) { ctx->frame++; ctx->parity ^= 1u; }
+    if (do_cull) { ctx->frame++; ctx->parity = ctx->frame % 3u; }
     return B200VIS_OK;
 }
 
@@ -757,7 +825,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
 // downloads (synchronous: the host buffers are valid on return)
 // ------------------------------------------------------------------------------------------
 extern "C" int32_t b200vis_download_frame_stats(b200vis_ctx *ctx, b200vis_frame_stats *out) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     if (!out) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_frame_stats: null");
     CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -769,14 +837,14 @@ extern "C" int32_t b200vis_download_frame_stats(b200vis_ctx *ctx, b200vis_frame_
         memcpy(&out->cluster_farthest_z[v], &s.cl_farthest_bits[v], 4);
         out->cluster_index_overflow[v] = s.cl_overflow[v];
     }
-    const uint32_t lp = ctx->parity ^ 1u;   // parity the last CULL frame accumulated into
+    const uint32_t lp = (ctx->frame + 2u) % 3u;   // slot the last CULL frame (frame - 1) accumulated into
     out->gt_changed_count = s.changed[lp][0]; out->vv_changed_count = s.changed[lp][1]; out->frame = ctx->frame;
     return B200VIS_OK;
 }
 
 extern "C" int32_t b200vis_download_global_transforms(b200vis_ctx *ctx, uint32_t first, uint32_t count, float *gt,
                                                       uint32_t stride, uint8_t *changed) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     int32_t rc = check_range(ctx, first, count, "download_global_transforms"); if (rc) return rc;
     if (gt && stride != 12 && stride != 16) return fail(ctx, B200VIS_ERR_INVALID_ARG, "stride_floats must be 12 or 16");
     cudaStream_t st = ctx->stream;
@@ -793,7 +861,7 @@ extern "C" int32_t b200vis_download_global_transforms(b200vis_ctx *ctx, uint32_t
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_download_view_visibility(b200vis_ctx *ctx, uint32_t first, uint32_t count, uint8_t *vv, uint8_t *changed) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     int32_t rc = check_range(ctx, first, count, "download_view_visibility"); if (rc) return rc;
     cudaStream_t st = ctx->stream;
     launch_pack_state(st, ctx->rows, first, count, ctx->d_stage, S_VV_CHANGED);
@@ -803,7 +871,7 @@ extern "C" int32_t b200vis_download_view_visibility(b200vis_ctx *ctx, uint32_t f
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_download_visible(b200vis_ctx *ctx, uint32_t view, uint32_t *rows, uint32_t capacity, uint32_t *count) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     if (view >= ctx->cfg.max_views || !count) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_visible: bad argument");
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
@@ -819,7 +887,7 @@ extern "C" int32_t b200vis_download_visible(b200vis_ctx *ctx, uint32_t view, uin
 }
 extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, uint32_t *offsets, uint32_t *indices,
                                              uint32_t indices_capacity, uint32_t *total) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     if (view >= ctx->cfg.max_views || !offsets || !total) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_clusters: bad argument");
     const DevClusterView &cv = active_consts(ctx).cviews[view];
     const uint32_t nc = cv.enabled ? cv.n_clusters : 0;
@@ -839,7 +907,7 @@ extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, ui
 extern "C" int32_t b200vis_download_frame(b200vis_ctx *ctx, b200vis_frame_stats *stats, uint32_t *visible_rows,
                                           uint32_t visible_capacity, uint32_t *cluster_offsets,
                                           uint32_t *cluster_indices, uint32_t cluster_capacity) {
-    CHECK_CTX();
+    CHECK_CTX_JOIN();
     if (!stats) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_frame: null stats");
     cudaStream_t st = ctx->stream;
     const FrameConsts &fc = active_consts(ctx);

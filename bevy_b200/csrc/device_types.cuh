@@ -92,8 +92,8 @@ struct DevStats {
     uint32_t cl_overflow[kMaxViews];
     uint32_t cl_acc_index[kMaxViews];      // accumulators of the assign kernel
     uint32_t cl_acc_far[kMaxViews];        // float bits; values > 0 only, so integer max == float max
-    uint32_t changed[2][2];                // [frame parity][0 = gt, 1 = vv]; the expand kernel of frame f
-                                           // zeroes the parity frame f+1 accumulates into
+    uint32_t changed[3][2];                // [frame % 3][0 = gt, 1 = vv]; the expand kernel of frame f zeroes the
+                                           // slot frame f+2 accumulates into (frame f+1 may already be running)
 };
 
 struct VisibleBufs {
@@ -101,14 +101,15 @@ struct VisibleBufs {
     uint32_t n_chunks;       // ceil(n_words / kChunkWords)
     uint32_t words_stride;   // words per view
     uint32_t chunks_stride;  // chunk counters per view
-    uint32_t *mask;          // [V][words_stride], bit = rank
-    uint32_t *chunk_count;   // [2][V][chunks_stride]
+    uint32_t *mask;          // [V][words_stride], bit = rank (two copies, the host passes frame % 2's)
+    uint32_t *chunk_count;   // [3][V][chunks_stride], slot = frame % 3
     uint32_t *lists;         // [V][list_stride] rows, ascending Entity::to_bits()
     uint32_t list_stride;
 };
 
 struct Lights {
     uint32_t n;
+    const float4 *snap;      // optional (pos.xyz, visible) snapshot taken right after the tile pass, or nullptr
     const uint32_t *row;
     const float *range;
     const uint64_t *layers;  // or nullptr

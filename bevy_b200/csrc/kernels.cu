@@ -633,9 +633,10 @@ k_expand_visible(VisibleBufs vb, const uint32_t *__restrict__ row_of_rank, const
     const uint32_t v = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
     if (v >= fc->n_views) return;
     uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
-    uint32_t *cc_next = vb.chunk_count + ((size_t)(parity ^ 1u) * kMaxViews + v) * vb.chunks_stride;
+    const uint32_t zslot = (parity + 2u) % 3u;   // the slot frame f+2 will accumulate into
+    uint32_t *cc_next = vb.chunk_count + ((size_t)zslot * kMaxViews + v) * vb.chunks_stride;
     if (t == 0) cc_next[chunk] = 0;
-    if (chunk == 0 && v == 0 && t < 2) stats->changed[parity ^ 1u][t] = 0;   // next frame's accumulators
+    if (chunk == 0 && v == 0 && t < 2) stats->changed[zslot][t] = 0;
     if (!(fc->views[v].flags & 1u)) return;   // inactive view: VisibleEntities untouched (mod.rs:780-782)
 
     const uint32_t word = chunk * kChunkWords + t;
@@ -730,11 +731,18 @@ k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBu
     }
     const uint32_t li = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
     if (li >= L.n) return;
-    const uint32_t row = L.row[li];
-    if (!(R.state[row] & 1u)) return;                                   // view_visibility.get() (assign.rs:195)
+    float px, py, pz;
+    if (L.snap != nullptr) {                                            // snapshot taken right after the tile pass
+        const float4 sp = L.snap[li];
+        if (sp.w == 0.0f) return;                                       // view_visibility.get() (assign.rs:195)
+        px = sp.x; py = sp.y; pz = sp.z;
+    } else {
+        const uint32_t row = L.row[li];
+        if (!(R.state[row] & 1u)) return;                               // view_visibility.get() (assign.rs:195)
+        px = R.gt0[row].w; py = R.gt1[row].w; pz = R.gt2[row].w;        // GlobalTransform::translation
+    }
     const unsigned long long ll = L.layers ? L.layers[li] : 1ull;
     if (!(cv.layer_mask & ll)) return;                                  // assign.rs:489
-    const float px = R.gt0[row].w, py = R.gt1[row].w, pz = R.gt2[row].w;   // GlobalTransform::translation
     const float range = L.range[li];
 #pragma unroll
     for (int k = 0; k < 6; ++k)                                         // frustum.intersects_sphere(.., true)
@@ -903,6 +911,15 @@ k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__
     // NOTE: the slab is zeroed for the next frame by k_cluster_clear (a CTA here may still be re-counting it)
 }
 
+// (pos, visible) of every light, copied right after the tile pass so that the cluster kernels of frame f can run
+// on a side stream while frame f+1's tile pass already rewrites GlobalTransform / ViewVisibility
+__global__ void k_snapshot_lights(Rows R, Lights L, float4 *__restrict__ snap) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= L.n) return;
+    const uint32_t row = L.row[li];
+    snap[li] = make_float4(R.gt0[row].w, R.gt1[row].w, R.gt2[row].w, (R.state[row] & 1u) ? 1.0f : 0.0f);
+}
+
 // zero this rank's slab for the next frame's assign kernel (only the words in use)
 __global__ void k_cluster_clear(const FrameConsts *__restrict__ fc, ClusterBufs cb) {
     const uint32_t v = blockIdx.y;
@@ -1049,6 +1066,9 @@ void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, cons
                            DevStats *stats, uint32_t max_views) {
     if (L.n == 0) return;
     k_cluster_assign<<<dim3(cdiv(L.n, 8), max_views), 256, 0, st>>>(R, L, fc, cb, stats);
+}
+void launch_snapshot_lights(cudaStream_t st, const Rows &R, const Lights &L, float4 *snap) {
+    if (L.n) k_snapshot_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, snap);
 }
 void launch_cluster_lists(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, DevStats *stats, uint32_t max_views) {
     k_cluster_lists<<<dim3(kListBlocks, max_views), 1024, 0, st>>>(fc, cb, stats);

@@ -11,6 +11,7 @@ void launch_expand_visible(cudaStream_t st, const VisibleBufs &vb, const uint32_
                            DevStats *stats, uint32_t parity, uint32_t n_rows, uint32_t max_views);
 void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
                            DevStats *stats, uint32_t max_views);
+void launch_snapshot_lights(cudaStream_t st, const Rows &R, const Lights &L, float4 *snap);
 void launch_cluster_lists(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, DevStats *stats, uint32_t max_views);
 void launch_unpack_trs(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *src, int mark_only);
 void launch_scatter_trs(cudaStream_t st, const Rows &R, uint32_t count, const uint32_t *rows, const float *src);

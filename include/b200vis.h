@@ -166,6 +166,11 @@ B200VIS_API const char *b200vis_last_error(const b200vis_ctx *ctx); /* valid unt
  * (a cudaStream_t; NULL => the context's own stream). */
 B200VIS_API int32_t b200vis_set_stream(b200vis_ctx *ctx, void *cuda_stream);
 B200VIS_API int32_t b200vis_synchronize(b200vis_ctx *ctx);
+/* b200vis_run(B200VIS_STAGE_ALL) pipelines frames: the latency-bound tail of frame f (visible-list expansion,
+ * cluster kernels) runs on an internal side stream and overlaps frame f+1's tile pass.  b200vis_join makes the
+ * context's stream wait (asynchronously) for that tail, e.g. before recording a timing event; every download and
+ * b200vis_synchronize join implicitly.  Set B200VIS_PIPELINE=0 to serialise everything on one stream. */
+B200VIS_API int32_t b200vis_join(b200vis_ctx *ctx);
 
 /* ---- mirroring the ECS columns --------------------------------------------- */
 /* Hierarchy + identity; call on spawn/despawn/Changed<ChildOf> only.

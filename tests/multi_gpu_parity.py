@@ -27,7 +27,8 @@ def main():
     # every rank is created with the same light capacity so the slabs have one size
     pipe = bb.VisibilityPipeline(sub, device=local, world_size=world, rank=rank, max_lights=max_lights)
     ctx = pipe.ctx
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     slab = ctx.cluster_exchange_bytes()
     send = torch.zeros(slab // 4, dtype=torch.int32, device=dev)

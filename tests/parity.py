@@ -14,8 +14,9 @@ IDENTITY = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32)
 class OracleWorld:
     """The reference-side world state for one scene, advanced by the oracle."""
 
-    def __init__(self, scene, static_opt=True):
+    def __init__(self, scene, static_opt=True, cluster_kwargs=None):
         self.scene = scene
+        self.cluster_kwargs = cluster_kwargs or {}
         n = scene.n
         self.gt = np.tile(IDENTITY, (n, 1))
         self.vv = np.zeros(n, np.uint8)
@@ -43,19 +44,21 @@ class OracleWorld:
                 cfv = orc.perspective(cam.fov, cam.aspect, cam.near)
                 vin = orc.default_cluster_view_in(cam.gt, cfv, views_planes[v], screen=sc.screen,
                                                   view_layers=1 if sc.view_layers is None else int(sc.view_layers[v]),
-                                                  last_farthest_z=self.fb[v]["far"], last_index_count=self.fb[v]["cnt"])
+                                                  last_farthest_z=self.fb[v]["far"], last_index_count=self.fb[v]["cnt"],
+                                                  **self.cluster_kwargs)
                 out, offsets, idx, _ = orc.assign_lights_to_clusters(vin, lights, ll)
                 self.fb[v]["far"] = out.farthest_z; self.fb[v]["cnt"] = out.total_index_count
                 clusters.append((out, offsets, vis[idx].astype(np.uint32)))
         return gt_changed, vv_changed, lists, clusters
 
 
-def compare_frame(pipe, world, frame_no, cluster=True, check_gt=True):
+def compare_frame(pipe, world, frame_no, cluster=True, check_gt=True, run_device=True):
     sc = pipe.scene
     n = sc.n
     planes = np.stack([np.ctypeslib.as_array(v.half_spaces).reshape(6, 4).copy() for v in pipe.views])
     gt_changed, vv_changed, lists, clusters = world.frame(planes, cluster=cluster)
-    pipe.run_frame()
+    if run_device:
+        pipe.run_frame()
     tag = f"[{sc.name} frame {frame_no}]"
     if check_gt:
         gt, ch = pipe.ctx.download_global_transforms(0, n)

@@ -228,3 +228,33 @@ def test_update_camera_and_batched_download_equal_the_piecewise_calls():
                 assert (o[:nc + 1] == off[v, :nc + 1]).all() and (i == idx[v, :off[v, nc]]).all()
     finally:
         a.close(); b.close()
+
+
+def test_back_to_back_frames_pipelined_tail_matches_oracle():
+    """Frames submitted back to back with no host synchronisation in between: the tail of frame f (visible-list
+    expansion, cluster kernels on the side stream) overlaps frame f+1's tile pass.  Only the LAST frame is read
+    back; it must equal the oracle stepped through the same frames.  The cluster config is feedback-free
+    (constant far plane, no dynamic resizing) so no per-frame read-back is needed."""
+    sc = scenes.forest(n_trees=300, levels=8, n_lights=48)
+    cfg = bb.host_default_cluster_config(*sc.screen)
+    cfg.far_z_mode, cfg.far_z_constant, cfg.dynamic_resizing = 1, 90.0, 0
+    kw = dict(far_z_mode=1, far_z_constant=90.0, dynamic_resizing=False)
+    pipe = bb.VisibilityPipeline(sc, cluster_config=cfg)
+    world = OracleWorld(sc, cluster_kwargs=kw)
+    try:
+        frames = 7
+        for f in range(frames):
+            if f:
+                scenes.advance_cameras(sc, 0.01)
+                rows, trs = scenes.mutate_roots(sc, f)
+                pipe.ctx.upload_transforms_scattered(rows, trs)
+                world.tchanged[rows] = 1
+            pipe.update_views()
+            if f < frames - 1:
+                planes = np.stack([np.ctypeslib.as_array(v.half_spaces).reshape(6, 4).copy() for v in pipe.views])
+                world.frame(planes)
+                pipe.run_frame()             # no download, no sync: the next frame is enqueued right behind
+            else:
+                compare_frame(pipe, world, f)
+    finally:
+        pipe.close()

@@ -9,7 +9,7 @@ from bevy_b200 import scenes
 sc = scenes.forest()
 pipe = bb.VisibilityPipeline(sc)
 ctx = pipe.ctx
-ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+_s = torch.cuda.Stream(); torch.cuda.set_stream(_s); ctx.set_stream(_s.cuda_stream)
 pipe.run_frame(); pipe.read_feedback()
 rows, trs = scenes.mutate_roots(sc, 1)
 rows_d = torch.from_numpy(rows.astype(np.int32)).cuda(); trs_d = torch.from_numpy(trs).cuda()
