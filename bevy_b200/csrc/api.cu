@@ -312,7 +312,7 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
             while (c > start + 1 && parent[c] < n) --c;   // c = latest row in (start, end] that starts a tree
             if (c > start && !(parent[c] < n)) end = c;
         }
-        Tile t; t.base = start; t.n_rows = (uint16_t)(end - start); t.n_levels = 1; t.warp_sync_mask = 0xFFFFFFFFu; t.pad = 0; memset(t.level_threads, 0, sizeof t.level_threads);
+        Tile t; t.base = start; t.n_rows = (uint16_t)(end - start); t.n_levels = 1; t.warp_sync_mask = 0xFFFFFFFFu; t.pad = 0;
         for (uint32_t r = start; r < end; ++r) tile_of[r] = (uint32_t)tiles.size();
         tiles.push_back(t);
         start = end;
@@ -338,19 +338,6 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
         }
         if (has_children[r]) w |= T_HAS_CHILDREN;
         topo[r] = w;
-    }
-    // named-barrier participants per level: warps holding level-l rows (consumers) or level-(l-1) rows with children
-    for (auto &t : tiles) {
-        if (t.n_levels <= 1) continue;
-        for (uint32_t lvl = 1; lvl < 16 && lvl < t.n_levels; ++lvl) {
-            uint32_t warps = 0;
-            for (uint32_t r = t.base; r < t.base + t.n_rows; ++r) {
-                if (topo[r] & (T_DETACHED)) continue;
-                const uint32_t dpt = (topo[r] >> 9) & 0x1FFu;
-                if (dpt == lvl || (dpt + 1 == lvl && (topo[r] & T_HAS_CHILDREN))) warps |= 1u << ((r - t.base) >> 5);
-            }
-            t.level_threads[lvl] = (uint16_t)(32u * __builtin_popcount(warps));
-        }
     }
     // NOTE: tile_level of tile t only depends on tiles with a smaller index (topological rows), and
     // those are final by the time a row of t is visited, because rows are visited in ascending order.

@@ -27,9 +27,6 @@ struct Tile {               // one CTA's work: a contiguous, (mostly) hierarchy-
     uint32_t warp_sync_mask; // bit l (1 <= l < 32): every row of level l has its parent in the same warp,
                              //   so __syncwarp orders the shared-memory hand-over instead of a CTA barrier
     uint32_t pad;
-    // named-barrier plan for levels 1..15: threads (32 x warps) that produce level l-1 rows with children or consume
-    // level l rows; a producer-only warp just ARRIVES and moves on to culling its own rows
-    uint16_t level_threads[16];
 };
 
 // SoA mirror of the ECS columns in HBM.  Every array is indexed by row.

@@ -462,19 +462,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
                 if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
             }
             for (uint32_t lvl = 1; lvl < tile.n_levels; ++lvl) {
-                // hand-over of level lvl-1's matrices to level lvl: producers arrive, consumers wait, everyone
-                // else (warps with neither) skips the barrier altogether and goes on to cull its rows
-                if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) {
-                    __syncwarp();
-                } else if (lvl < 16u) {
-                    const bool consume = __any_sync(0xFFFFFFFFu, my_level == lvl);
-                    const bool produce = __any_sync(0xFFFFFFFFu, my_level + 1u == lvl && has_children);
-                    const uint32_t nthr = tile.level_threads[lvl];
-                    if (consume) asm volatile("bar.sync %0, %1;" ::"r"(lvl), "r"(nthr) : "memory");
-                    else if (produce) asm volatile("bar.arrive %0, %1;" ::"r"(lvl), "r"(nthr) : "memory");
-                } else {
-                    __syncthreads();
-                }
+                if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) __syncwarp(); else __syncthreads();
                 if (my_level == lvl) {
                     const uint32_t pst = s.pst[plocal];
                     const uint32_t pi = off + plocal;
