@@ -669,7 +669,7 @@ static CullViews make_cull_views(const FrameConsts &fc) {
     memset(&c, 0, sizeof c);
     c.n_views = fc.n_views;
     for (uint32_t v = 0; v < fc.n_views && v < (uint32_t)kMaxViews; ++v) {
-        c.on[v] = fc.views[v].flags & 3u; c.range_index[v] = fc.views[v].range_index; c.layers[v] = fc.views[v].layer_mask;
+        c.on[v] = (fc.views[v].flags & 3u) | ((fc.views[v].layer_mask & 1ull) ? 4u : 0u); c.range_index[v] = fc.views[v].range_index; c.layers[v] = fc.views[v].layer_mask;
         for (int k = 0; k < 5; ++k) c.planes[v][k] = fc.views[v].hs[k];
     }
     return c;

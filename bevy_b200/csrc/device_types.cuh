@@ -60,7 +60,7 @@ struct DevView {
 // every plane component is a constant-bank operand (772 bytes of the 4 KB parameter space).
 struct CullViews {
     uint32_t n_views;
-    uint32_t on[kMaxViews];            // bit0 camera.is_active, bit1 NoCpuCulling camera
+    uint32_t on[kMaxViews];            // bit0 camera.is_active, bit1 NoCpuCulling camera, bit2 default layer in the view's mask
     int32_t range_index[kMaxViews];
     unsigned long long layers[kMaxViews];
     float4 planes[kMaxViews][5];       // L,R,T,B,Near (the far plane is never used by culling)

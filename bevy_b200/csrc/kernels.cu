@@ -227,7 +227,7 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const __grid_constant__
             if (v >= cvw.n_views) break;
             const uint32_t von = cvw.on[v];
             if (!(von & 1u)) continue;                                 // !camera.is_active (grid-uniform)
-            if (SIMPLE && !(cvw.layers[v] & 1ull)) continue;          // every entity is on the default layer
+            if (SIMPLE && !(von & 4u)) continue;                       // bit2: the view includes the default layer
             bool vis = base;
             if (!SIMPLE) {
                 vis = vis && (cvw.layers[v] & elayers) != 0ull;
@@ -399,14 +399,6 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
     for (uint32_t it = 0; t < n_tiles; t += gridDim.x, ++it) {
         const uint32_t sidx = it & 1u;
         const Tile tile = tiles[t];
-        if (lr == 0) {
-            const uint32_t tn = t + gridDim.x;
-            if (tn < n_tiles) {
-                // the other stage was last read by the bulk store of the previous tile: wait for its smem reads
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                issue_tile_loads<PROP, CULL>(R, tiles[tn], s.st[sidx ^ 1u], &s.bar[sidx ^ 1u]);
-            }
-        }
         mbar_wait(&s.bar[sidx], (it >> 1) & 1u);
         TileStage &S = s.st[sidx];
         const uint32_t off = tile.base & 15u;
@@ -478,6 +470,16 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
             }
             if (active && tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
         }
+        // Prefetch the NEXT tile into the other stage.  That stage was last read by the previous tile's bulk store,
+        // issued most of an iteration ago, so the wait below is (almost always) already satisfied: putting the
+        // prefetch here instead of at the top of the loop keeps the store drain off every warp's critical path.
+        if (lr == 0) {
+            const uint32_t tn = t + gridDim.x;
+            if (tn < n_tiles) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                issue_tile_loads<PROP, CULL>(R, tiles[tn], s.st[sidx ^ 1u], &s.bar[sidx ^ 1u]);
+            }
+        }
         uint32_t out = st8 & (S_VV | S_HAS_CLASS);
         if (PROP) out |= (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
         else out |= st8 & (S_GT_CHANGED | S_VISITED);
@@ -521,7 +523,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
                 if (v >= cvw.n_views) break;
                 const uint32_t von = cvw.on[v];
                 if (!(von & 1u)) continue;
-                if (SIMPLE && !(cvw.layers[v] & 1ull)) continue;
+                if (SIMPLE && !(von & 4u)) continue;   // bit2: the view includes the default layer
                 bool vis = base;
                 if (!SIMPLE) {
                     vis = vis && (cvw.layers[v] & elayers) != 0ull;
@@ -583,11 +585,11 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         if (active && out != st8) R.state[row] = (uint8_t)out;
 
         // end of tile: everybody is done with this stage; count changes; write the tile's matrices back
-        const int n_gt = __syncthreads_count(PROP && changed);
-        const int n_vv = CULL ? __syncthreads_count(vv_changed) : 0;
+        n_gt_total += (PROP && changed) ? 1u : 0u;      // per-thread tallies, reduced once at the end of the kernel
+        n_vv_total += vv_changed ? 1u : 0u;
+        const int any_gt = __syncthreads_or(PROP && changed);
         if (lr == 0) {
-            n_gt_total += (uint32_t)n_gt; n_vv_total += (uint32_t)n_vv;
-            if (PROP && n_gt) {
+            if (PROP && any_gt) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
                 const uint32_t bytes = (uint32_t)tile.n_rows * 16u;
                 bulk_s2g(R.gt0 + tile.base, S.gt0 + off, bytes); bulk_s2g(R.gt1 + tile.base, S.gt1 + off, bytes);
@@ -596,10 +598,18 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
             }
         }
     }
+    if (lr == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // block-reduce the per-thread tallies (warp shuffle, then one shared-memory atomic per warp)
+    __shared__ uint32_t s_cnt[2];
+    if (lr < 2) s_cnt[lr] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n_gt_total += __shfl_xor_sync(0xFFFFFFFFu, n_gt_total, o); n_vv_total += __shfl_xor_sync(0xFFFFFFFFu, n_vv_total, o); }
+    if ((lr & 31u) == 0) { if (n_gt_total) atomicAdd(&s_cnt[0], n_gt_total); if (n_vv_total) atomicAdd(&s_cnt[1], n_vv_total); }
+    __syncthreads();
     if (lr == 0) {
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        if (n_gt_total) atomicAdd(&stats->changed[parity][0], n_gt_total);
-        if (n_vv_total) atomicAdd(&stats->changed[parity][1], n_vv_total);
+        if (s_cnt[0]) atomicAdd(&stats->changed[parity][0], s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&stats->changed[parity][1], s_cnt[1]);
     }
 }
 
