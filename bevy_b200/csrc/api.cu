@@ -35,6 +35,8 @@ struct b200vis_ctx {
     cudaEvent_t ev_tile = nullptr, ev_side[2] = {nullptr, nullptr};
     bool pipeline = true, side_pending = false;
     float4 *d_light_snap = nullptr;     // [2][max_lights]
+    uint32_t *d_tag_flag = nullptr;     // 1 if every light row carries its ordinal (k_tag_lights)
+    bool lights_tag_dirty = true, lights_tagged = false;
     std::string err;
 
     uint32_t n = 0;                 // current row count
@@ -127,7 +129,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     Rows &r = ctx->rows;
     void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
-                   ctx->d_tiles, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_light_snap,
+                   ctx->d_tiles, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_light_snap, ctx->d_tag_flag,
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage};
     for (void *p : dev) if (p) cudaFree(p);
@@ -209,6 +211,7 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         // lights + clusters
         const size_t Lm = std::max<uint32_t>(cfg->max_lights, 1);
         CU(dalloc(&ctx->d_light_snap, 2 * Lm));
+        CU(dalloc(&ctx->d_tag_flag, 1));
         CU(dalloc(&ctx->d_light_row, Lm)); CU(dalloc(&ctx->d_light_range, Lm)); CU(dalloc(&ctx->d_light_layers, Lm));
         ClusterBufs &cl = ctx->cl;
         cl.words = (uint32_t)((Lm + 31) / 32); cl.max_lights = cl.words * 32; cl.world = ctx->cfg.world_size;
@@ -507,6 +510,7 @@ extern "C" int32_t b200vis_upload_bounds(b200vis_ctx *ctx, uint32_t first, uint3
         ctx->have_range = true;
     }
     ctx->bounds_set = true;
+    ctx->lights_tag_dirty = true;   // bounds were rewritten: the light ordinals stored in them are gone
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_upload_view_visibility(b200vis_ctx *ctx, uint32_t first, uint32_t count, const uint8_t *vv) {
@@ -585,6 +589,7 @@ extern "C" int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, const
     if (layer_mask) CU(cudaMemcpyAsync(ctx->d_light_layers, layer_mask, (size_t)n_lights * 8, cudaMemcpyHostToDevice, ctx->stream));
     ctx->lights.n = n_lights; ctx->lights.row = ctx->d_light_row; ctx->lights.range = ctx->d_light_range;
     ctx->lights.layers = layer_mask ? ctx->d_light_layers : nullptr;
+    ctx->lights_tag_dirty = true;
     return B200VIS_OK;
 }
 
@@ -779,10 +784,26 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     vb.mask = ctx->vis.mask + (size_t)mslot * ctx->vis.words_stride * ctx->cfg.max_views;
     const uint32_t n_pass = ctx->pass_begin.empty() ? 0 : (uint32_t)ctx->pass_begin.size() - 1;
     R.dirty = nullptr;
+    R.light_snap = nullptr;
     if (do_prop && ctx->static_opt && n_pass > 1) {
         CU(cudaMemsetAsync(ctx->d_dirty, 0, ctx->n, st));
         R.dirty = ctx->d_dirty;
         launch_mark_dirty_global(st, R);
+    }
+    // Light snapshot by the tile kernel itself: needs every light row tagged with its ordinal (one-off, on change).
+    bool tile_snap = false;
+    if (pipelined && ctx->lights.n) {
+        if (ctx->lights_tag_dirty) {
+            const uint32_t one = 1;
+            CU(cudaMemcpyAsync(ctx->d_tag_flag, &one, 4, cudaMemcpyHostToDevice, st));
+            launch_tag_lights(st, R, ctx->lights, ctx->d_tag_flag);
+            uint32_t ok = 0;
+            CU(cudaMemcpyAsync(&ok, ctx->d_tag_flag, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            ctx->lights_tagged = ok != 0; ctx->lights_tag_dirty = false;
+        }
+        tile_snap = ctx->lights_tagged && tile_kernel_is_tma();
+        if (tile_snap) R.light_snap = ctx->d_light_snap + (size_t)mslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
     }
     cudaEvent_t *pe = (ctx->profiling && ctx->prof_count < b200vis_ctx::kProfFrames) ? ctx->prof_ev[ctx->prof_count++] : nullptr;
     if (pe) CU(cudaEventRecord(pe[0], st));
@@ -801,7 +822,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     cudaStream_t tail = st;
     if (pipelined) {
         lights.snap = ctx->d_light_snap + (size_t)mslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
-        launch_snapshot_lights(st, R, lights, const_cast<float4 *>(lights.snap));
+        if (!tile_snap) launch_snapshot_lights(st, R, lights, const_cast<float4 *>(lights.snap));
         if (pe) CU(cudaEventRecord(pe[1], st));
         CU(cudaEventRecord(ctx->ev_tile, st));
         tail = ctx->side_stream;

@@ -47,6 +47,8 @@ struct Rows {
     const uint32_t *rank;    // position in Entity::to_bits() order, or nullptr when rank == row
     const uint32_t *row_of_rank;
     uint8_t *dirty;          // global TransformTreeChanged bytes (multi-pass plans only), or nullptr
+    float4 *light_snap;      // when non-null, rows flagged F_SPHERE_GT carry their light ordinal in bndA.x (tagged by
+                             //   k_tag_lights) and publish (translation, visible) here at the end of the tile pass
 };
 
 struct DevView {

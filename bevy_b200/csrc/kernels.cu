@@ -325,8 +325,7 @@ constexpr int kWin = kTileRows + 16;     // rows per staged window (base misalig
 struct __align__(128) TileStage {
     float4 trsA[kWin], trsB[kWin];
     float4 gt0[kWin], gt1[kWin], gt2[kWin];
-    float4 bndA[kWin];
-    float2 trsC[kWin], bndB[kWin];
+    float2 trsC[kWin];
     uint32_t topo[kWin];
     uint8_t flags[kWin], state[kWin];
 };
@@ -370,7 +369,6 @@ __device__ __forceinline__ void issue_tile_loads(const Rows &R, const Tile &t, T
     const uint32_t cnt = ((t.base - a) + t.n_rows + 15u) & ~15u;
     uint32_t bytes = cnt * (48u + 2u);
     if (PROP) bytes += cnt * (40u + 4u);
-    if (CULL) bytes += cnt * 24u;
     mbar_expect_tx(bar, bytes);
     bulk_g2s(S.gt0, R.gt0 + a, cnt * 16u, bar); bulk_g2s(S.gt1, R.gt1 + a, cnt * 16u, bar); bulk_g2s(S.gt2, R.gt2 + a, cnt * 16u, bar);
     bulk_g2s(S.flags, R.flags + a, cnt, bar); bulk_g2s(S.state, R.state + a, cnt, bar);
@@ -378,11 +376,10 @@ __device__ __forceinline__ void issue_tile_loads(const Rows &R, const Tile &t, T
         bulk_g2s(S.trsA, R.trsA + a, cnt * 16u, bar); bulk_g2s(S.trsB, R.trsB + a, cnt * 16u, bar);
         bulk_g2s(S.trsC, R.trsC + a, cnt * 8u, bar); bulk_g2s(S.topo, R.topo + a, cnt * 4u, bar);
     }
-    if (CULL) { bulk_g2s(S.bndA, R.bndA + a, cnt * 16u, bar); bulk_g2s(S.bndB, R.bndB + a, cnt * 8u, bar); }
 }
 
 template <bool PROP, bool CULL, bool SIMPLE>
-__global__ void __launch_bounds__(kTileRows, 3)
+__global__ void __launch_bounds__(kTileRows, 4)
 k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, const __grid_constant__ CullViews cvw,
                      VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -407,6 +404,10 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         const uint32_t row = tile.base + lr;
         const uint32_t f = active ? S.flags[li] : 0u;
         const uint32_t st8 = active ? S.state[li] : 0u;
+        // bounds are only needed after the hierarchy walk: plain coalesced loads issued now, consumed in phase 3
+        // (keeping them out of the staged window lets a fourth CTA fit in shared memory)
+        float4 bA = make_float4(0, 0, 0, 0); float2 bB = make_float2(0, 0);
+        if (CULL && active) { bA = R.bndA[row]; bB = R.bndB[row]; }
 
         bool visited = false, changed = false;
         if (PROP) {
@@ -487,8 +488,6 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         bool vv_changed = false;
         if (CULL) {
             Aff g; g.r0 = S.gt0[li]; g.r1 = S.gt1[li]; g.r2 = S.gt2[li];   // own row: written by this thread or untouched
-            const float4 bA = S.bndA[li];
-            const float2 bB = S.bndB[li];
             const bool in_query = active && !(f & F_NO_CPU_CULL);
             const bool base = in_query && (f & F_INHERITED);
             const uint32_t prev = st8 & 1u;
@@ -583,6 +582,10 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
             out |= st8 & S_VV_CHANGED;
         }
         if (active && out != st8) R.state[row] = (uint8_t)out;
+        // a light row publishes what assign_objects_to_clusters needs of it (GlobalTransform::translation,
+        // ViewVisibility::get) so that the cluster kernels never touch the row arrays again
+        if (CULL && R.light_snap != nullptr && (f & F_SPHERE_GT) && active)
+            R.light_snap[__float_as_uint(bA.x)] = make_float4(S.gt0[li].w, S.gt1[li].w, S.gt2[li].w, (out & 1u) ? 1.0f : 0.0f);
 
         // end of tile: everybody is done with this stage; count changes; write the tile's matrices back
         n_gt_total += (PROP && changed) ? 1u : 0u;      // per-thread tallies, reduced once at the end of the kernel
@@ -921,6 +924,20 @@ k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__
     // NOTE: the slab is zeroed for the next frame by k_cluster_clear (a CTA here may still be re-counting it)
 }
 
+// set_lights: store each light's ordinal in the (unused) centre.x of its sphere-from-GT bounds so the tile kernel can
+// publish the light snapshot itself; *all_tagged is cleared if some light row is not F_SPHERE_GT (then the separate
+// snapshot kernel is used instead)
+__global__ void k_tag_lights(Rows R, Lights L, uint32_t *__restrict__ all_tagged) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= L.n) return;
+    const uint32_t row = L.row[li];
+    if (row < R.n && (R.flags[row] & F_SPHERE_GT) && !(R.flags[row] & F_AABB)) {
+        float4 b = R.bndA[row]; b.x = __uint_as_float(li); R.bndA[row] = b;
+    } else {
+        *all_tagged = 0;
+    }
+}
+
 // (pos, visible) of every light, copied right after the tile pass so that the cluster kernels of frame f can run
 // on a side stream while frame f+1's tile pass already rewrites GlobalTransform / ViewVisibility
 __global__ void k_snapshot_lights(Rows R, Lights L, float4 *__restrict__ snap) {
@@ -1030,6 +1047,7 @@ static int tile_kernel_choice() {
     }
     return g_tile_kernel;
 }
+bool tile_kernel_is_tma() { return tile_kernel_choice() == 1; }
 template <bool P, bool C, bool S>
 static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                        const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity) {
@@ -1076,6 +1094,9 @@ void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, cons
                            DevStats *stats, uint32_t max_views) {
     if (L.n == 0) return;
     k_cluster_assign<<<dim3(cdiv(L.n, 8), max_views), 256, 0, st>>>(R, L, fc, cb, stats);
+}
+void launch_tag_lights(cudaStream_t st, const Rows &R, const Lights &L, uint32_t *all_tagged) {
+    if (L.n) k_tag_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, all_tagged);
 }
 void launch_snapshot_lights(cudaStream_t st, const Rows &R, const Lights &L, float4 *snap) {
     if (L.n) k_snapshot_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, snap);
