@@ -390,6 +390,8 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // launched with programmatic stream serialization: everything above overlapped the previous kernel's tail
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     uint32_t t = blockIdx.x;
     if (lr == 0 && t < n_tiles) issue_tile_loads<PROP, CULL>(R, tiles[t], s.st[0], &s.bar[0]);
     uint32_t n_gt_total = 0, n_vv_total = 0;
@@ -418,7 +420,9 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
             bool dirty = tchanged;
             if (static_opt && R.dirty != nullptr) {
                 dirty = active && R.dirty[row];
-            } else if (static_opt && tile.n_levels > 1) {
+            } else if (static_opt && tile.n_levels > 1 && __syncthreads_or(tchanged && depth > 0)) {
+                // only when a non-root row of the tile changed does anything have to climb: otherwise every row's
+                // TransformTreeChanged bit equals its own Changed<Transform> bit (one barrier instead of two + a climb)
                 s.parent[lr] = (uint16_t)((depth > 0) ? plocal : 0xFFFFu);
                 s.dirty[lr] = 0;
                 __syncthreads();
@@ -975,6 +979,7 @@ __global__ void k_unpack_trs(Rows R, uint32_t first, uint32_t count, const float
     R.flags[row] = (uint8_t)(R.flags[row] | F_TCHANGED);
 }
 __global__ void k_scatter_trs(Rows R, uint32_t count, const uint32_t *__restrict__ rows, const float *__restrict__ src) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: the previous frame's tile pass still reads these columns
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const uint32_t row = rows[i];
@@ -1061,7 +1066,15 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
         grid = sms * (per_sm > 0 ? per_sm : 1);    // persistent: one CTA per resident slot
     }
     const uint32_t g = n_tiles < (uint32_t)grid ? n_tiles : (uint32_t)grid;
-    k_propagate_cull_tma<P, C, S><<<g, kTileRows, sizeof(TmaSmem), st>>>(R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
+    // programmatic dependent launch: this kernel's CTAs may become resident (barrier init, parameter loads) while the
+    // previous kernel in the stream drains; griddepcontrol.wait in the kernel orders the actual data accesses
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g); cfg.blockDim = dim3(kTileRows); cfg.dynamicSmemBytes = sizeof(TmaSmem); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_propagate_cull_tma<P, C, S>, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
 }
 void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                            const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
@@ -1109,7 +1122,14 @@ void launch_unpack_trs(cudaStream_t st, const Rows &R, uint32_t first, uint32_t 
     if (count) k_unpack_trs<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, src, mark_only);
 }
 void launch_scatter_trs(cudaStream_t st, const Rows &R, uint32_t count, const uint32_t *rows, const float *src) {
-    if (count) k_scatter_trs<<<cdiv(count, 256), 256, 0, st>>>(R, count, rows, src);
+    if (!count) return;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cdiv(count, 256)); cfg.blockDim = dim3(256); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_scatter_trs, R, count, rows, src);
 }
 void launch_unpack_gt(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *src) {
     if (count) k_unpack_gt<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, src);
