@@ -251,18 +251,21 @@ def main():
     e2e_h2d = n_roots * 44 + 8192         # root TRS + row ids + the frame-constant blob (upper bound of its used part)
     d2h_bytes = []
 
-    # pinned host buffers the results land in (what a shim would hand to VisibleEntities / Clusters)
+    # pinned host buffers the results land in (what a shim would hand to VisibleEntities / Clusters): registered as the
+    # context's result sink, the GPU writes them itself and one stream synchronisation per frame makes them readable
     vis_h = torch.empty((V, n), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     coff_h = torch.empty((V, 4097), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     cidx_h = torch.empty((V, 1 << 18), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-    stats_buf = bb.FrameStats()
+    stats_t = torch.zeros(ctypes.sizeof(bb.FrameStats), dtype=torch.uint8).pin_memory()
+    stats_buf = bb.FrameStats.from_address(stats_t.data_ptr())
+    ctx.set_result_sink(stats_t.data_ptr(), vis_h, coff_h, cidx_h)
 
     def e2e_step(f):
         set_cameras(f)
         ctx.upload_transforms_scattered_raw(n_roots, rows_h.data_ptr(), trs_frames_h[f].data_ptr())   # pinned host -> HBM
         pipe.update_views_fast()                    # host: update_frusta + per-view cluster prologue (last frame's feedback)
         run_stages()
-        ctx.download_frame(stats_buf, vis_h, coff_h, cidx_h)   # D2H: stats + sorted VisibleEntities + Clusters of every view
+        ctx.synchronize()                           # results (stats, sorted VisibleEntities, Clusters) are now in host memory
         stats = stats_buf
         nb = ctypes.sizeof(stats)
         for v in range(V):
@@ -288,6 +291,8 @@ def main():
     e2e_sec = max(e2e_wall, ev0.elapsed_time(ev1) / 1e3)
     visible_pairs = sum(last_stats.visible_count[v] for v in range(V))
     cluster_indices = sum(last_stats.cluster_index_count[v] for v in range(V))
+
+    ctx.set_result_sink(None, None, None, None)
 
     # ---- pass B: run the next K+W frames once with the feedback loop closed and record each frame's
     # constants (views, cluster tables) as a blob in HBM, so the timed replay has every input resident ----
@@ -368,7 +373,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "entities/s", "h2d_bytes_per_step": int(e2e_h2d),
                     "d2h_bytes_per_step": int(np.mean(d2h_bytes)), "ms_per_step": e2e_ms / K,
-                    "note": "GlobalTransforms stay device-resident; visible lists, cluster lists and the stats block are read back"},
+                    "note": "GlobalTransforms stay device-resident; the GPU writes stats, sorted visible lists and cluster lists into pinned host memory (result sink), one stream sync per frame"},
             "gpu_launches": 6 * K, "host_enqueue_ms_per_step": host_enqueue_ms,
             "roofline": {"bound": "hbm", "kernel": "k_propagate_cull", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

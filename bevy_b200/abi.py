@@ -83,6 +83,11 @@ class FrameStats(C.Structure):
                 ("pad", C.c_uint32)]
 
 
+class ResultSink(C.Structure):
+    _fields_ = [("stats", C.POINTER(FrameStats)), ("visible_rows", C.c_void_p), ("visible_capacity", C.c_uint32),
+                ("cluster_offsets", C.c_void_p), ("cluster_indices", C.c_void_p), ("cluster_capacity", C.c_uint32)]
+
+
 _lib = None
 _P = C.POINTER
 _vp = C.c_void_p
@@ -121,6 +126,7 @@ _SIGNATURES = {
     "b200vis_download_view_visibility": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "b200vis_download_visible": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_download_clusters": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _P(C.c_uint32)]),
+    "b200vis_set_result_sink": (C.c_int32, [_vp, _P(ResultSink)]),
     "b200vis_cluster_exchange_bytes": (C.c_int32, [_vp, _P(C.c_size_t)]),
     "b200vis_set_cluster_exchange_buffers": (C.c_int32, [_vp, _vp, _vp]),
     "b200vis_host_perspective": (None, [C.c_float, C.c_float, C.c_float, _vp]),
@@ -357,6 +363,21 @@ class Context:
         offsets = np.zeros(MAX_CLUSTERS + 1, np.uint32); idx = np.zeros(capacity, np.uint32); tot = C.c_uint32(0)
         self._check(self._lib.b200vis_download_clusters(self._h, view, _ptr(offsets), _ptr(idx), capacity, C.byref(tot)))
         return offsets, idx[:tot.value]
+
+    def set_result_sink(self, stats_ptr, visible_rows, cluster_offsets, cluster_indices):
+        """Pinned host numpy arrays: visible_rows [V, cap], cluster_offsets [V, 4097], cluster_indices [V, cap]; stats_ptr
+        is the address of a pinned FrameStats-sized block.  Pass stats_ptr=None to remove the sink."""
+        if stats_ptr is None:
+            self._check(self._lib.b200vis_set_result_sink(self._h, None)); return
+        s = ResultSink()
+        s.stats = C.cast(stats_ptr, C.POINTER(FrameStats))
+        s.visible_rows = None if visible_rows is None else visible_rows.ctypes.data
+        s.visible_capacity = 0 if visible_rows is None else visible_rows.shape[1]
+        s.cluster_offsets = None if cluster_offsets is None else cluster_offsets.ctypes.data
+        s.cluster_indices = None if cluster_indices is None else cluster_indices.ctypes.data
+        s.cluster_capacity = 0 if cluster_indices is None else cluster_indices.shape[1]
+        self._sink = (s, visible_rows, cluster_offsets, cluster_indices)
+        self._check(self._lib.b200vis_set_result_sink(self._h, C.byref(s)))
 
     def cluster_exchange_bytes(self):
         n = C.c_size_t(0)

@@ -86,6 +86,10 @@ struct b200vis_ctx {
     ClusterBufs cl{}; uint32_t *d_slab = nullptr; void *ext_send = nullptr, *ext_recv = nullptr;
     size_t slab_bytes = 0;
 
+    // result sink (mapped pinned host memory written by publish kernels)
+    b200vis_result_sink sink{}; bool have_sink = false;
+    uint32_t *sink_rows_d = nullptr, *sink_off_d = nullptr, *sink_idx_d = nullptr, *sink_stats_d = nullptr;
+
     // staging for AoS <-> SoA conversion
     uint8_t *d_stage = nullptr; size_t stage_bytes = 0;
     uint8_t *h_stage = nullptr;         // pinned, same size (downloads)
@@ -814,7 +818,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
                 launch_propagate_cull(st, R, ctx->d_tiles + ctx->pass_begin[p], ctx->pass_begin[p + 1] - ctx->pass_begin[p],
                                       cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot);
         } else if (n_pass) {
-            launch_propagate_cull(st, R, ctx->d_tiles, ctx->pass_begin[n_pass], cvw, vb, ctx->d_stats, tile_stages, 0, cslot);
+            launch_cull(st, R, cvw, vb, ctx->d_stats, cslot);
         }
     }
     Lights lights = ctx->lights;
@@ -830,11 +834,16 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     } else if (pe) CU(cudaEventRecord(pe[1], st));
     if (pe) CU(cudaEventRecord(pe[2], tail));
     if (do_cull) launch_expand_visible(tail, vb, R.row_of_rank, fc, ctx->d_stats, cslot, ctx->n, ctx->cfg.max_views);
+    if (do_cull && ctx->have_sink && ctx->sink_rows_d)
+        launch_publish_visible(tail, vb, ctx->d_stats, ctx->sink_rows_d, ctx->sink.visible_capacity, ctx->n, active_consts(ctx).n_views);
     if (pe) CU(cudaEventRecord(pe[3], tail));
     if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
         launch_cluster_assign(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if (stages & B200VIS_STAGE_CLUSTER_LISTS)
         launch_cluster_lists(tail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+    if (ctx->have_sink && (do_cull || (stages & B200VIS_STAGE_CLUSTER_LISTS)))
+        launch_publish_clusters(tail, fc, cl, (stages & B200VIS_STAGE_CLUSTER_LISTS) ? ctx->sink_off_d : nullptr, ctx->sink_idx_d,
+                                ctx->sink.cluster_capacity, ctx->d_stats, ctx->sink_stats_d, cslot, frame + (do_cull ? 1u : 0u), ctx->cfg.max_views);
     if (pe) CU(cudaEventRecord(pe[4], tail));
     if (pipelined) { CU(cudaEventRecord(ctx->ev_side[mslot], tail)); ctx->side_pending = true; }
     CU(cudaGetLastError());
@@ -922,6 +931,37 @@ extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, ui
         CU(cudaMemcpyAsync(indices, ctx->cl.indices + (size_t)view * ctx->cl.index_cap, (size_t)*total * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
+    return B200VIS_OK;
+}
+
+static int32_t map_host(b200vis_ctx *ctx, void *p, size_t bytes, uint32_t **dev) {
+    *dev = nullptr;
+    if (!p) return B200VIS_OK;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered)
+        return fail(ctx, B200VIS_ERR_CUDA, "set_result_sink: cudaHostRegister failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    void *d = nullptr;
+    CU(cudaHostGetDevicePointer(&d, p, 0));
+    *dev = static_cast<uint32_t *>(d);
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_set_result_sink(b200vis_ctx *ctx, const b200vis_result_sink *sink) {
+    CHECK_CTX_JOIN();
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_sink = false;
+    if (!sink) return B200VIS_OK;
+    if (!sink->stats) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_result_sink: stats is required");
+    const size_t V = ctx->cfg.max_views;
+    int32_t rc;
+    if ((rc = map_host(ctx, sink->stats, sizeof(b200vis_frame_stats), &ctx->sink_stats_d))) return rc;
+    if ((rc = map_host(ctx, sink->visible_rows, V * sink->visible_capacity * 4, &ctx->sink_rows_d))) return rc;
+    if ((rc = map_host(ctx, sink->cluster_offsets, V * (kMaxClusters + 1) * 4, &ctx->sink_off_d))) return rc;
+    if ((rc = map_host(ctx, sink->cluster_indices, V * (size_t)sink->cluster_capacity * 4, &ctx->sink_idx_d))) return rc;
+    if ((sink->cluster_offsets == nullptr) != (sink->cluster_indices == nullptr))
+        return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_result_sink: cluster_offsets and cluster_indices go together");
+    ctx->sink = *sink;
+    ctx->have_sink = true;
     return B200VIS_OK;
 }
 

@@ -620,6 +620,128 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Kernel 1c: check_visibility as a pure streaming kernel (no hierarchy, no shared memory, no barriers).
+// One thread per row, CTAs of 256 rows starting at multiples of 256, so a warp covers exactly one
+// 32-bit word of the rank-ordered visible mask: when rows are in Entity::to_bits() order (SIMPLE) the
+// ballot is STORED (no atomics, no zeroing of the mask between frames).
+// ------------------------------------------------------------------------------------------
+template <bool SIMPLE>
+__global__ void __launch_bounds__(256, 4)
+k_cull(Rows R, const __grid_constant__ CullViews cvw, VisibleBufs vb, DevStats *__restrict__ stats, uint32_t parity) {
+    const uint32_t row = blockIdx.x * 256u + threadIdx.x;
+    const bool active = row < R.n;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t f = 0, st8 = 0;
+    Aff g; g.r0 = g.r1 = g.r2 = make_float4(0, 0, 0, 0);
+    float4 bA = g.r0; float2 bB = make_float2(0, 0);
+    if (active) {
+        f = R.flags[row]; st8 = R.state[row];
+        g.r0 = R.gt0[row]; g.r1 = R.gt1[row]; g.r2 = R.gt2[row];
+        bA = R.bndA[row]; bB = R.bndB[row];
+    }
+    const bool in_query = active && !(f & F_NO_CPU_CULL);
+    const bool base = in_query && (f & F_INHERITED);
+    const uint32_t prev = st8 & 1u;
+    const bool has_aabb = f & F_AABB;
+    const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
+    float cx, cy, cz, radius;
+    const float hx = bA.w, hy = bB.x, hz = bB.y;
+    if (has_aabb) {
+        cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;
+        cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
+        cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+        const float vx = (g.r0.x * hx + g.r0.y * hy) + g.r0.z * hz;
+        const float vy = (g.r1.x * hx + g.r1.y * hy) + g.r1.z * hz;
+        const float vz = (g.r2.x * hx + g.r2.y * hy) + g.r2.z * hz;
+        radius = sqrtf((vx * vx + vy * vy) + vz * vz);
+    } else {
+        const bool from_gt = f & F_SPHERE_GT;
+        cx = from_gt ? g.r0.w : bA.x; cy = from_gt ? g.r1.w : bA.y; cz = from_gt ? g.r2.w : bA.z;
+        radius = bA.w;
+    }
+    unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
+    if (!SIMPLE && active) {
+        if (R.layers != nullptr) elayers = R.layers[row];
+        if ((f & F_RANGE) && R.range != nullptr) erange = R.range[row];
+        if (R.rank != nullptr) rnk = R.rank[row];
+    }
+    bool any = false;
+    uint32_t my_ballot = 0;
+#pragma unroll
+    for (uint32_t v = 0; v < kMaxViews; ++v) {
+        if (v >= cvw.n_views) break;
+        const uint32_t von = cvw.on[v];
+        if (!(von & 1u)) continue;
+        if (SIMPLE && !(von & 4u)) { continue; }
+        bool vis = base;
+        if (!SIMPLE) {
+            vis = vis && (cvw.layers[v] & elayers) != 0ull;
+            if ((f & F_RANGE) && R.range != nullptr) {
+                const int32_t ri = cvw.range_index[v];
+                vis = vis && ri >= 0 && ((erange >> ri) & 1u);
+            }
+        }
+        if (do_test && !(von & 2u)) {
+            const float d0 = plane_dot_point(cvw.planes[v][0], cx, cy, cz), d1 = plane_dot_point(cvw.planes[v][1], cx, cy, cz);
+            const float d2 = plane_dot_point(cvw.planes[v][2], cx, cy, cz), d3 = plane_dot_point(cvw.planes[v][3], cx, cy, cz);
+            const float d4 = plane_dot_point(cvw.planes[v][4], cx, cy, cz);
+            const bool out_s = (d0 + radius <= 0.0f) | (d1 + radius <= 0.0f) | (d2 + radius <= 0.0f) |
+                               (d3 + radius <= 0.0f) | (d4 + radius <= 0.0f);
+            vis = vis && !out_s;
+            if (vis && has_aabb) {
+                const float d[5] = {d0, d1, d2, d3, d4};
+                bool out_o = false;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float4 n = cvw.planes[v][k];
+                    const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+                    const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+                    const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+                    const float rr = (dx * hx + dy * hy) + dz * hz;
+                    out_o |= (d[k] + rr <= 0.0f);
+                }
+                vis = !out_o;
+            }
+        }
+        any |= vis;
+        const bool listed = vis && (st8 & S_HAS_CLASS);
+        if (SIMPLE || R.rank == nullptr) {
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
+            if (lane == v) my_ballot = b;
+        } else if (listed) {
+            uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
+            uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
+            atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+            atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
+        }
+    }
+    if (SIMPLE || R.rank == nullptr) {
+        // lane v owns view v's word: the CTA's rows start at a multiple of 256, so (row - lane) >> 5 is the word
+        if (lane < cvw.n_views && (cvw.on[lane] & 1u) && (!SIMPLE || (cvw.on[lane] & 4u))) {
+            const uint32_t w0 = (row - lane) >> 5;
+            if (w0 < vb.n_words) {
+                vb.mask[(size_t)lane * vb.words_stride + w0] = my_ballot;
+                if (my_ballot) atomicAdd(vb.chunk_count + ((size_t)parity * kMaxViews + lane) * vb.chunks_stride + (w0 / kChunkWords), __popc(my_ballot));
+            }
+        }
+    }
+    uint32_t out = st8;
+    bool vv_changed = false;
+    if (in_query) {
+        out = (st8 & ~(S_VV | S_VV_CHANGED)) | (any ? (1u | (prev << 1)) : 0u);
+        vv_changed = (any ? 1u : 0u) != prev;
+        if (vv_changed) out |= S_VV_CHANGED;
+    } else {
+        out = st8 & ~S_VV_CHANGED;
+    }
+    if (active && out != st8) R.state[row] = (uint8_t)out;
+    if (R.light_snap != nullptr && (f & F_SPHERE_GT) && active)
+        R.light_snap[__float_as_uint(bA.x)] = make_float4(g.r0.w, g.r1.w, g.r2.w, (out & 1u) ? 1.0f : 0.0f);
+    const uint32_t bv = __ballot_sync(0xFFFFFFFFu, vv_changed);
+    if (lane == 0 && bv) atomicAdd(&stats->changed[parity][1], __popc(bv));
+}
+
 // mark_dirty_trees for plans whose tiles have parents in other tiles: every Changed row climbs its
 // ancestor chain through HBM, stopping at the first already-dirty ancestor (the reference's
 // fetch_or early exit, systems.rs:208-223).  `dirty` is zeroed by the caller.
@@ -951,6 +1073,45 @@ __global__ void k_snapshot_lights(Rows R, Lights L, float4 *__restrict__ snap) {
     snap[li] = make_float4(R.gt0[row].w, R.gt1[row].w, R.gt2[row].w, (R.state[row] & 1u) ? 1.0f : 0.0f);
 }
 
+// ---- result sink: coalesced copies of a frame's results into mapped pinned host memory ----------------------
+// visible lists: grid (blocks, views); each thread moves 4 rows (16 B), blocks beyond the view's count exit at once
+__global__ void k_publish_visible(const uint32_t *__restrict__ lists, uint32_t list_stride, const DevStats *__restrict__ stats,
+                                  uint32_t *__restrict__ host_rows, uint32_t host_stride, uint32_t n_views) {
+    const uint32_t v = blockIdx.y;
+    if (v >= n_views) return;
+    const uint32_t count = min(stats->visible_count[v], host_stride);
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i >= count) return;
+    const uint32_t *src = lists + (size_t)v * list_stride + i;
+    uint32_t *dst = host_rows + (size_t)v * host_stride + i;
+    if (i + 4u <= count) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
+    else for (uint32_t k = 0; i + k < count; ++k) dst[k] = src[k];
+}
+// cluster CSR + the stats block (also formats b200vis_frame_stats, whose layout the host passes as offsets)
+__global__ void k_publish_clusters(const FrameConsts *__restrict__ fc, const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ indices,
+                                   uint32_t index_cap, uint32_t *__restrict__ host_offsets, uint32_t *__restrict__ host_indices,
+                                   uint32_t host_cap, const DevStats *__restrict__ stats, uint32_t *__restrict__ host_stats,
+                                   uint32_t changed_slot, uint32_t frame) {
+    const uint32_t v = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0 && blockIdx.x == 0 && host_stats != nullptr) {
+        // b200vis_frame_stats: visible_count[8] cluster_index_count[8] cluster_farthest_z[8] overflow[8] gt vv frame pad
+        if (threadIdx.x < 8) {
+            host_stats[threadIdx.x] = stats->visible_count[threadIdx.x];
+            host_stats[8 + threadIdx.x] = stats->cl_index_count[threadIdx.x];
+            host_stats[16 + threadIdx.x] = stats->cl_farthest_bits[threadIdx.x];
+            host_stats[24 + threadIdx.x] = stats->cl_overflow[threadIdx.x];
+        }
+        if (threadIdx.x == 8) { host_stats[32] = stats->changed[changed_slot][0]; host_stats[33] = stats->changed[changed_slot][1]; host_stats[34] = frame; host_stats[35] = 0; }
+    }
+    if (v >= fc->n_views || host_offsets == nullptr) return;
+    const DevClusterView &cv = fc->cviews[v];
+    const uint32_t nc = cv.enabled ? cv.n_clusters : 0u;
+    const uint32_t *off = offsets + (size_t)v * (kMaxClusters + 1);
+    if (t <= nc) host_offsets[(size_t)v * (kMaxClusters + 1) + t] = off[t];
+    const uint32_t total = min(min(off[nc], index_cap), host_cap);
+    for (uint32_t i = t; i < total; i += gridDim.x * blockDim.x) host_indices[(size_t)v * host_cap + i] = indices[(size_t)v * index_cap + i];
+}
+
 // zero this rank's slab for the next frame's assign kernel (only the words in use)
 __global__ void k_cluster_clear(const FrameConsts *__restrict__ fc, ClusterBufs cb) {
     const uint32_t v = blockIdx.y;
@@ -1095,6 +1256,12 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
     else if (cull) { if (simple) B200VIS_LAUNCH(false, true, true); else B200VIS_LAUNCH(false, true, false); }
 #undef B200VIS_LAUNCH
 }
+void launch_cull(cudaStream_t st, const Rows &R, const CullViews &cvw, const VisibleBufs &vb, DevStats *stats, uint32_t parity) {
+    if (!R.n) return;
+    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+    if (simple) k_cull<true><<<cdiv(R.n, 256), 256, 0, st>>>(R, cvw, vb, stats, parity);
+    else k_cull<false><<<cdiv(R.n, 256), 256, 0, st>>>(R, cvw, vb, stats, parity);
+}
 void launch_mark_dirty_global(cudaStream_t st, const Rows &R) {
     if (R.n) k_mark_dirty_global<<<cdiv(R.n, 256), 256, 0, st>>>(R);
 }
@@ -1107,6 +1274,16 @@ void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, cons
                            DevStats *stats, uint32_t max_views) {
     if (L.n == 0) return;
     k_cluster_assign<<<dim3(cdiv(L.n, 8), max_views), 256, 0, st>>>(R, L, fc, cb, stats);
+}
+void launch_publish_visible(cudaStream_t st, const VisibleBufs &vb, const DevStats *stats, uint32_t *host_rows, uint32_t host_stride,
+                            uint32_t n_rows, uint32_t n_views) {
+    if (!n_views || !n_rows) return;
+    k_publish_visible<<<dim3(cdiv(cdiv(n_rows, 4), 256), n_views), 256, 0, st>>>(vb.lists, vb.list_stride, stats, host_rows, host_stride, n_views);
+}
+void launch_publish_clusters(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, uint32_t *host_offsets, uint32_t *host_indices,
+                             uint32_t host_cap, const DevStats *stats, uint32_t *host_stats, uint32_t changed_slot, uint32_t frame, uint32_t max_views) {
+    k_publish_clusters<<<dim3(kMaxClusters / 256 + 1, max_views), 256, 0, st>>>(fc, cb.offsets, cb.indices, cb.index_cap, host_offsets, host_indices,
+                                                                                host_cap, stats, host_stats, changed_slot, frame);
 }
 void launch_tag_lights(cudaStream_t st, const Rows &R, const Lights &L, uint32_t *all_tagged) {
     if (L.n) k_tag_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, all_tagged);

@@ -279,6 +279,21 @@ B200VIS_API int32_t b200vis_download_frame(b200vis_ctx *ctx, b200vis_frame_stats
                                            uint32_t visible_capacity, uint32_t *cluster_offsets,
                                            uint32_t *cluster_indices, uint32_t cluster_capacity);
 
+/* Result sink: caller-owned PINNED host memory that the frame's results are written into by the GPU itself (small
+ * "publish" kernels doing coalesced posted writes over PCIe right after the producing kernels), so that reading a
+ * frame back needs ONE stream synchronisation and no size round trip:
+ *   stats            the b200vis_frame_stats block
+ *   visible_rows     [max_views][visible_capacity]  sorted visible rows per view (count in stats->visible_count)
+ *   cluster_offsets  [max_views][4097], cluster_indices [max_views][cluster_capacity]
+ * The library registers the ranges with cudaHostRegister if they are not already pinned.  NULL removes the sink. */
+typedef struct b200vis_result_sink {
+    b200vis_frame_stats *stats;
+    uint32_t *visible_rows;   uint32_t visible_capacity;
+    uint32_t *cluster_offsets;
+    uint32_t *cluster_indices; uint32_t cluster_capacity;
+} b200vis_result_sink;
+B200VIS_API int32_t b200vis_set_result_sink(b200vis_ctx *ctx, const b200vis_result_sink *sink);
+
 /* ---- multi-GPU cluster exchange (one all-gather per frame, done by the host's collective) ------- */
 /* Each rank fills `slab_bytes` at `send`; after all-gathering the slabs rank-major into `recv`
  * (world_size * slab_bytes) the LISTS stage reads `recv`.  Buffers are caller-allocated device memory

@@ -258,3 +258,41 @@ def test_back_to_back_frames_pipelined_tail_matches_oracle():
                 compare_frame(pipe, world, f)
     finally:
         pipe.close()
+
+
+def test_result_sink_matches_downloads():
+    """The publish kernels write the same stats / visible rows / cluster CSR into pinned host memory that the
+    download calls return."""
+    torch = pytest.importorskip("torch")
+    import ctypes
+    sc = scenes.forest(n_trees=60, levels=6, n_lights=24)
+    pipe = bb.VisibilityPipeline(sc)
+    V = len(sc.cameras)
+    vis = torch.zeros((V, sc.n), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    off = torch.zeros((V, 4097), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    idx = torch.zeros((V, 1 << 16), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    st_t = torch.zeros(ctypes.sizeof(bb.FrameStats), dtype=torch.uint8).pin_memory()
+    st = bb.FrameStats.from_address(st_t.data_ptr())
+    try:
+        pipe.ctx.set_result_sink(st_t.data_ptr(), vis, off, idx)
+        for f in range(3):
+            scenes.advance_cameras(sc, 0.05)
+            rows, trs = scenes.mutate_roots(sc, f + 1)
+            pipe.ctx.upload_transforms_scattered(rows, trs)
+            pipe.update_views_fast()
+            pipe.run_frame()
+            pipe.ctx.synchronize()
+            ref = pipe.ctx.download_frame_stats()
+            assert st.frame == ref.frame and st.gt_changed_count == ref.gt_changed_count and st.vv_changed_count == ref.vv_changed_count
+            for v in range(V):
+                assert st.visible_count[v] == ref.visible_count[v] and st.cluster_index_count[v] == ref.cluster_index_count[v]
+                assert st.cluster_farthest_z[v] == ref.cluster_farthest_z[v]
+                assert (vis[v, :st.visible_count[v]] == pipe.ctx.download_visible(v)).all()
+                o, i = pipe.ctx.download_clusters(v)
+                nc = pipe.cluster_views[v].dims[0] * pipe.cluster_views[v].dims[1] * pipe.cluster_views[v].dims[2]
+                assert (off[v, :nc + 1] == o[:nc + 1]).all() and (idx[v, :off[v, nc]] == i).all()
+                fb = pipe.feedback[v]
+                fb.has_farthest_z, fb.farthest_z, fb.has_index_count, fb.index_count = 1, st.cluster_farthest_z[v], 1, st.cluster_index_count[v]
+        pipe.ctx.set_result_sink(None, None, None, None)
+    finally:
+        pipe.close()
