@@ -120,6 +120,7 @@ _SIGNATURES = {
     "b200vis_use_recorded_frame_constants": (C.c_int32, [_vp, C.c_int32]),
     "b200vis_set_profiling": (C.c_int32, [_vp, C.c_int32]),
     "b200vis_collect_stage_times_ms": (C.c_int32, [_vp, _P(C.c_float), _P(C.c_float), _P(C.c_float), _P(C.c_uint32)]),
+    "b200vis_step": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _P(CameraDesc), _P(ClusterConfig), C.c_uint32]),
     "b200vis_run": (C.c_int32, [_vp, C.c_uint32]),
     "b200vis_download_frame_stats": (C.c_int32, [_vp, _P(FrameStats)]),
     "b200vis_download_global_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, _vp]),
@@ -332,6 +333,11 @@ class Context:
         a, b_, c, n = C.c_float(0), C.c_float(0), C.c_float(0), C.c_uint32(0)
         self._check(self._lib.b200vis_collect_stage_times_ms(self._h, C.byref(a), C.byref(b_), C.byref(c), C.byref(n)))
         return a.value, b_.value, c.value, n.value
+
+    def step(self, n_changed, rows_ptr, trs_ptr, cameras, n_cameras, cluster_config=None, wait=True):
+        """b200vis_step: `cameras` is a ctypes array of CameraDesc."""
+        self._check(self._lib.b200vis_step(self._h, n_changed, _vp(rows_ptr), _vp(trs_ptr), n_cameras, cameras,
+                                           None if cluster_config is None else C.byref(cluster_config), 1 if wait else 0))
 
     def run(self, stages=STAGE_ALL):
         self._check(self._lib.b200vis_run(self._h, stages))

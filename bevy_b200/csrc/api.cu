@@ -90,6 +90,8 @@ struct b200vis_ctx {
     b200vis_result_sink sink{}; bool have_sink = false;
     uint32_t *sink_rows_d = nullptr, *sink_off_d = nullptr, *sink_idx_d = nullptr, *sink_stats_d = nullptr;
 
+    b200vis_cluster_feedback auto_fb[kMaxViews]{};   // b200vis_step: last frame's Clusters feedback
+
     // staging for AoS <-> SoA conversion
     uint8_t *d_stage = nullptr; size_t stage_bytes = 0;
     uint8_t *h_stage = nullptr;         // pinned, same size (downloads)
@@ -937,12 +939,16 @@ extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, ui
 static int32_t map_host(b200vis_ctx *ctx, void *p, size_t bytes, uint32_t **dev) {
     *dev = nullptr;
     if (!p) return B200VIS_OK;
-    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
-    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered)
-        return fail(ctx, B200VIS_ERR_CUDA, "set_result_sink: cudaHostRegister failed: %s", cudaGetErrorString(e));
-    cudaGetLastError();
+    // already pinned (cudaHostAlloc / a previous cudaHostRegister, e.g. torch pinned tensors): UVA gives the device alias
     void *d = nullptr;
-    CU(cudaHostGetDevicePointer(&d, p, 0));
+    if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) {
+        cudaGetLastError();
+        cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+        if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered)
+            return fail(ctx, B200VIS_ERR_CUDA, "set_result_sink: memory is not pinned and cudaHostRegister failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        CU(cudaHostGetDevicePointer(&d, p, 0));
+    }
     *dev = static_cast<uint32_t *>(d);
     return B200VIS_OK;
 }
@@ -999,5 +1005,32 @@ extern "C" int32_t b200vis_download_frame(b200vis_ctx *ctx, b200vis_frame_stats 
         }
     }
     CU(cudaStreamSynchronize(st));
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_step(b200vis_ctx *ctx, uint32_t n_changed, const uint32_t *rows, const float *trs,
+                                uint32_t n_cameras, const b200vis_camera *cameras, const b200vis_cluster_config *cfg, uint32_t flags) {
+    CHECK_CTX();
+    if (n_cameras > ctx->cfg.max_views || (n_cameras && !cameras)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "step: bad camera array");
+    int32_t rc;
+    if (n_changed && (rc = b200vis_upload_transforms_scattered(ctx, n_changed, rows, trs))) return rc;
+    if ((rc = b200vis_set_view_count(ctx, n_cameras))) return rc;
+    const bool clusters = cfg != nullptr && ctx->lights.n > 0;
+    for (uint32_t v = 0; v < n_cameras; ++v)
+        if ((rc = b200vis_update_camera(ctx, v, &cameras[v], clusters ? cfg : nullptr, &ctx->auto_fb[v], nullptr))) return rc;
+    if ((rc = b200vis_run(ctx, clusters ? B200VIS_STAGE_ALL : (B200VIS_STAGE_PROPAGATE | B200VIS_STAGE_CULL)))) return rc;
+    if (!(flags & B200VIS_STEP_WAIT)) return B200VIS_OK;
+    if ((rc = join_side(ctx))) return rc;
+    const b200vis_frame_stats *st = nullptr;
+    b200vis_frame_stats local;
+    if (ctx->have_sink) { CU(cudaStreamSynchronize(ctx->stream)); st = ctx->sink.stats; }
+    else { if ((rc = b200vis_download_frame_stats(ctx, &local))) return rc; st = &local; }
+    if (clusters)
+        for (uint32_t v = 0; v < n_cameras; ++v) {   // Clusters::last_frame_* (assign.rs:810-811)
+            b200vis_cluster_feedback &fb = ctx->auto_fb[v];
+            if (!ctx->consts.cviews[v].enabled) continue;
+            fb.has_farthest_z = 1; fb.farthest_z = st->cluster_farthest_z[v];
+            fb.has_index_count = 1; fb.index_count = st->cluster_index_count[v];
+        }
     return B200VIS_OK;
 }

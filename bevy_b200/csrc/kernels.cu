@@ -1074,18 +1074,15 @@ __global__ void k_snapshot_lights(Rows R, Lights L, float4 *__restrict__ snap) {
 }
 
 // ---- result sink: coalesced copies of a frame's results into mapped pinned host memory ----------------------
-// visible lists: grid (blocks, views); each thread moves 4 rows (16 B), blocks beyond the view's count exit at once
+// visible lists: grid (blocks, views), grid-stride over the view's count
 __global__ void k_publish_visible(const uint32_t *__restrict__ lists, uint32_t list_stride, const DevStats *__restrict__ stats,
                                   uint32_t *__restrict__ host_rows, uint32_t host_stride, uint32_t n_views) {
     const uint32_t v = blockIdx.y;
     if (v >= n_views) return;
     const uint32_t count = min(stats->visible_count[v], host_stride);
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    if (i >= count) return;
-    const uint32_t *src = lists + (size_t)v * list_stride + i;
-    uint32_t *dst = host_rows + (size_t)v * host_stride + i;
-    if (i + 4u <= count) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
-    else for (uint32_t k = 0; i + k < count; ++k) dst[k] = src[k];
+    // one row per thread: a warp writes 128 contiguous bytes (view strides need not be 16-byte multiples)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        host_rows[(size_t)v * host_stride + i] = lists[(size_t)v * list_stride + i];
 }
 // cluster CSR + the stats block (also formats b200vis_frame_stats, whose layout the host passes as offsets)
 __global__ void k_publish_clusters(const FrameConsts *__restrict__ fc, const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ indices,
@@ -1278,7 +1275,7 @@ void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, cons
 void launch_publish_visible(cudaStream_t st, const VisibleBufs &vb, const DevStats *stats, uint32_t *host_rows, uint32_t host_stride,
                             uint32_t n_rows, uint32_t n_views) {
     if (!n_views || !n_rows) return;
-    k_publish_visible<<<dim3(cdiv(cdiv(n_rows, 4), 256), n_views), 256, 0, st>>>(vb.lists, vb.list_stride, stats, host_rows, host_stride, n_views);
+    k_publish_visible<<<dim3(min(cdiv(n_rows, 256), 296u), n_views), 256, 0, st>>>(vb.lists, vb.list_stride, stats, host_rows, host_stride, n_views);
 }
 void launch_publish_clusters(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, uint32_t *host_offsets, uint32_t *host_indices,
                              uint32_t host_cap, const DevStats *stats, uint32_t *host_stats, uint32_t changed_slot, uint32_t frame, uint32_t max_views) {

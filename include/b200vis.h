@@ -254,6 +254,15 @@ B200VIS_API int32_t b200vis_update_camera(b200vis_ctx *ctx, uint32_t view, const
 /* ---- run ----------------------------------------------------------------------- */
 B200VIS_API int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages);
 
+/* One call per frame for a single-GPU host loop: upload the changed Transforms, recompute every camera's frame
+ * constants (b200vis_update_camera with the library's own copy of last frame's Clusters feedback), run all stages
+ * and -- with B200VIS_STEP_WAIT -- synchronise and refresh that feedback from the frame's statistics.  With a result
+ * sink set, the frame's results are in the caller's pinned buffers when the call returns. */
+#define B200VIS_STEP_WAIT 0x1u
+B200VIS_API int32_t b200vis_step(b200vis_ctx *ctx, uint32_t n_changed, const uint32_t *rows, const float *trs,
+                                 uint32_t n_cameras, const b200vis_camera *cameras, const b200vis_cluster_config *cfg,
+                                 uint32_t flags);
+
 /* ---- results --------------------------------------------------------------------- */
 B200VIS_API int32_t b200vis_download_frame_stats(b200vis_ctx *ctx, b200vis_frame_stats *out);
 /* gt[count][stride_floats] (stride 12, or 16 for glam's padded Affine3A layout); changed[count]:

@@ -296,3 +296,35 @@ def test_result_sink_matches_downloads():
         pipe.ctx.set_result_sink(None, None, None, None)
     finally:
         pipe.close()
+
+
+def test_step_call_equals_the_piecewise_sequence():
+    """b200vis_step (upload + cameras with internal feedback + run + wait) against the explicit call sequence."""
+    sc_a = scenes.forest(n_trees=40, levels=6, n_lights=20)
+    sc_b = scenes.forest(n_trees=40, levels=6, n_lights=20)
+    a, b = bb.VisibilityPipeline(sc_a), bb.VisibilityPipeline(sc_b)
+    V = len(sc_a.cameras)
+    try:
+        for f in range(4):
+            for sc in (sc_a, sc_b):
+                scenes.advance_cameras(sc, 0.03)
+            rows, trs = scenes.mutate_roots(sc_a, f + 1)
+            scenes.mutate_roots(sc_b, f + 1)
+            a.ctx.upload_transforms_scattered(rows, trs)
+            a.update_views(); a.run_frame(); sa = a.read_feedback()
+            arr = (bb.CameraDesc * V)()
+            for v, cam in enumerate(sc_b.cameras):
+                arr[v].global_transform[:] = cam.gt.tolist()
+                arr[v].fov_y, arr[v].aspect, arr[v].near_z, arr[v].far_z = cam.fov, cam.aspect, cam.near, cam.far
+                arr[v].layer_mask, arr[v].flags, arr[v].range_view_index = 1, bb.VIEW_ACTIVE, -1
+            r = np.ascontiguousarray(rows, np.uint32); t_ = np.ascontiguousarray(trs, np.float32)
+            b.ctx.step(len(r), r.ctypes.data, t_.ctypes.data, arr, V, b.cluster_config, wait=True)
+            sb = b.ctx.download_frame_stats()
+            for v in range(V):
+                assert sa.visible_count[v] == sb.visible_count[v] and sa.cluster_index_count[v] == sb.cluster_index_count[v]
+                assert sa.cluster_farthest_z[v] == sb.cluster_farthest_z[v]
+                assert (a.ctx.download_visible(v) == b.ctx.download_visible(v)).all()
+                oa, ia = a.ctx.download_clusters(v); ob, ib = b.ctx.download_clusters(v)
+                assert (oa == ob).all() and (ia == ib).all()
+    finally:
+        a.close(); b.close()
