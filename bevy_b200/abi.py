@@ -132,6 +132,7 @@ _SIGNATURES = {
     "b200vis_set_cluster_exchange_buffers": (C.c_int32, [_vp, _vp, _vp]),
     "b200vis_host_perspective": (None, [C.c_float, C.c_float, C.c_float, _vp]),
     "b200vis_host_compute_frustum": (None, [_vp, _vp, C.c_float, _vp]),
+    "b200vis_host_z_slice_thresholds": (None, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "b200vis_host_default_cluster_config": (None, [_P(ClusterConfig), C.c_uint32, C.c_uint32]),
     "b200vis_host_cluster_view_setup": (C.c_int32, [_P(ClusterConfig), _vp, _vp, _vp, C.c_uint64,
                                                     _P(ClusterFeedback), _vp, _P(ClusterView)]),
@@ -181,6 +182,12 @@ def host_compute_frustum(clip_from_view, camera_gt12, far):
     cfv = _arr(clip_from_view, np.float32); g = _arr(camera_gt12, np.float32); out = np.zeros((6, 4), np.float32)
     load_library().b200vis_host_compute_frustum(_ptr(cfv), _ptr(g), far, _ptr(out))
     return out
+
+
+def host_z_slice_thresholds(factors, z_slices, ortho=False):
+    f = _arr(factors, np.float32); out = np.zeros(max(z_slices - 1, 1), np.float32)
+    load_library().b200vis_host_z_slice_thresholds(_ptr(f), z_slices, int(ortho), _ptr(out))
+    return out[:max(z_slices - 1, 0)]
 
 
 def host_default_cluster_config(w=1920, h=1080):

@@ -1016,9 +1016,16 @@ extern "C" int32_t b200vis_step(b200vis_ctx *ctx, uint32_t n_changed, const uint
     if (n_changed && (rc = b200vis_upload_transforms_scattered(ctx, n_changed, rows, trs))) return rc;
     if ((rc = b200vis_set_view_count(ctx, n_cameras))) return rc;
     const bool clusters = cfg != nullptr && ctx->lights.n > 0;
+    // frusta first, so the tile pass starts at once; the per-view cluster prologue (plane tables, z thresholds: tens of
+    // microseconds of host maths) is computed while that kernel runs, then the cluster stage is enqueued behind it
     for (uint32_t v = 0; v < n_cameras; ++v)
-        if ((rc = b200vis_update_camera(ctx, v, &cameras[v], clusters ? cfg : nullptr, &ctx->auto_fb[v], nullptr))) return rc;
-    if ((rc = b200vis_run(ctx, clusters ? B200VIS_STAGE_ALL : (B200VIS_STAGE_PROPAGATE | B200VIS_STAGE_CULL)))) return rc;
+        if ((rc = b200vis_update_camera(ctx, v, &cameras[v], nullptr, nullptr, nullptr))) return rc;
+    if ((rc = b200vis_run(ctx, B200VIS_STAGE_PROPAGATE | B200VIS_STAGE_CULL))) return rc;
+    if (clusters) {
+        for (uint32_t v = 0; v < n_cameras; ++v)
+            if ((rc = b200vis_update_camera(ctx, v, &cameras[v], cfg, &ctx->auto_fb[v], nullptr))) return rc;
+        if ((rc = b200vis_run(ctx, B200VIS_STAGE_CLUSTER))) return rc;
+    }
     if (!(flags & B200VIS_STEP_WAIT)) return B200VIS_OK;
     if ((rc = join_side(ctx))) return rc;
     const b200vis_frame_stats *st = nullptr;

@@ -299,9 +299,22 @@ void z_slice_thresholds(const float factors[2], uint32_t z_slices, bool ortho, f
     for (uint32_t k = 1; k < z_slices; ++k) {
         // smallest key in [lo_key, hi_key] with slice_of >= k; NaN threshold if none
         if (slice_of(INFINITY, factors, ortho) < k) { thresholds[k - 1] = NAN; continue; }
-        uint32_t lo = lo_key, hi = hi_key;   // invariant: slice_of(hi) >= k
+        uint32_t lo = lo_key, hi = hi_key;   // invariant: slice_of(lo) < k <= slice_of(hi)
         if (slice_of(key2f(lo), factors, ortho) >= k) { thresholds[k - 1] = -INFINITY; continue; }
-        while (hi - lo > 1) {                 // invariant: slice_of(lo) < k <= slice_of(hi)
+        // Start from the analytic inverse of the slice formula and bracket it tightly: the exact step lies within a
+        // few hundred ulps of it, so ~10 evaluations of the host libm replace a 32-step bisection over all floats.
+        // (Any failure of the bracket falls back to the full range: the result is the same exact threshold.)
+        {
+            const float guess = ortho ? -(static_cast<float>(k) / factors[1] + factors[0])
+                                      : std::exp((static_cast<float>(k) - 1.0f + factors[1]) / factors[0]);
+            if (std::isfinite(guess)) {
+                const uint32_t g = f2key(guess);
+                const uint32_t span = 512;
+                const uint32_t blo = g > lo_key + span ? g - span : lo_key, bhi = g < hi_key - span ? g + span : hi_key;
+                if (slice_of(key2f(blo), factors, ortho) < k && slice_of(key2f(bhi), factors, ortho) >= k) { lo = blo; hi = bhi; }
+            }
+        }
+        while (hi - lo > 1) {
             const uint32_t mid = lo + (hi - lo) / 2;
             if (slice_of(key2f(mid), factors, ortho) >= k) hi = mid; else lo = mid;
         }
@@ -318,6 +331,9 @@ void b200vis_host_perspective(float fov_y, float aspect, float near_z, float *ou
 }
 void b200vis_host_compute_frustum(const float *cfv16, const float *cam12, float far_z, float hs[6][4]) {
     b200vis::host::compute_frustum(cfv16, cam12, far_z, hs);
+}
+void b200vis_host_z_slice_thresholds(const float f[2], uint32_t z_slices, uint32_t ortho, float *thr) {
+    b200vis::host::z_slice_thresholds(f, z_slices, ortho != 0, thr);
 }
 void b200vis_host_default_cluster_config(b200vis_cluster_config *cfg, uint32_t w, uint32_t h) {
     b200vis::host::default_cluster_config(cfg, w, h);

@@ -318,6 +318,11 @@ B200VIS_API void b200vis_host_compute_frustum(const float *clip_from_view16, con
                                   float half_spaces[6][4]);
 
 
+/* The thresholds the device uses in place of view_z_to_z_slice (assign.rs:1046-1062): thresholds[k-1] is the smallest
+ * u = -view_z whose slice index (computed with the HOST's libm, exactly the reference's float expression) is >= k;
+ * slice(u) = number of thresholds <= u.  z_slices-1 values (NaN where the slice is never reached). */
+B200VIS_API void b200vis_host_z_slice_thresholds(const float cluster_factors[2], uint32_t z_slices, uint32_t is_orthographic,
+                                                 float *thresholds);
 B200VIS_API void b200vis_host_default_cluster_config(b200vis_cluster_config *cfg, uint32_t screen_w, uint32_t screen_h);
 /* The per-view prologue of assign_objects_to_clusters (assign.rs:324-485).  planes_scratch must hold
  * 3*4097*4 floats; out->x/y/z_planes point into it. */

@@ -127,3 +127,34 @@ def test_scene_generators_match_the_config_sizes():
     sc = scenes.many_cubes(1000)
     assert np.allclose(np.linalg.norm(sc.trs[:, 0:3], axis=1), 500.0, rtol=1e-5)
     assert np.allclose(np.linalg.norm(sc.trs[:, 3:7], axis=1), 1.0, atol=1e-6)
+
+
+def test_z_slice_thresholds_reproduce_libm_view_z_to_z_slice():
+    """The device never calls logf: it counts host-computed thresholds.  That count must equal the reference's
+    view_z_to_z_slice (oracle = the platform libm, as Rust's f32::ln) for every view_z, including the neighbours of
+    every threshold, zero, negatives behind the camera, infinities and NaN."""
+    import ctypes as C
+    lib = orc.lib()
+    rng = np.random.default_rng(9)
+    cases = []
+    for _ in range(40):
+        near = float(rng.uniform(0.05, 20)); far = near * float(np.exp(rng.uniform(0.0, 7.0)))
+        zs = int(rng.integers(1, 40))
+        k = (np.float32(zs) - np.float32(1)) / np.float32(orc.lib().orc_logf(np.float32(far) / np.float32(near)))
+        cases.append((np.array([k, np.float32(orc.lib().orc_logf(np.float32(near))) * k], np.float32), zs, False))
+        cases.append((np.array([-near, zs / (-far + near)], np.float32), zs, True))
+    cases.append((np.array([np.inf, np.nan], np.float32), 24, False))       # far == near degenerate
+    cases.append((np.array([0.0, 0.0], np.float32), 1, False))
+    for factors, zs, ortho in cases:
+        thr = bb.host_z_slice_thresholds(factors, zs, ortho)
+        fin = thr[np.isfinite(thr)]
+        probe = [0.0, -0.0, 1e-30, 1e30, np.inf, -np.inf, np.nan, -1.0, -1e-3]
+        for t_ in fin:
+            probe += [t_, np.nextafter(np.float32(t_), np.float32(-np.inf)), np.nextafter(np.float32(t_), np.float32(np.inf))]
+        probe += list(np.exp(rng.uniform(-5, 9, 200)))
+        fp = factors.ctypes.data_as(C.POINTER(C.c_float))
+        for u in np.array(probe, np.float32):
+            want = lib.orc_view_z_to_z_slice(fp, zs, C.c_float(-u), int(ortho))
+            got = 0 if np.isnan(u) else int(np.sum(u >= thr[~np.isnan(thr)]))
+            got = min(got, zs - 1)
+            assert got == want, (factors, zs, ortho, u, got, want)
