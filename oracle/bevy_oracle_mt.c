@@ -19,27 +19,47 @@
 #include <omp.h>
 
 ORC_API int orc_mt_threads(void) { return omp_get_max_threads(); }
+ORC_API void orc_mt_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
+/* Persistent per-topology state, like the reference's Children components and Local<> scratch buffers: the children
+ * lists and the scratch arrays are built once per hierarchy (orc_mt_prepare), not once per frame. */
+static uint32_t g_n = 0, *g_first = NULL, *g_kids = NULL;
+static uint8_t *g_dirty = NULL;
+static sort_item *g_items = NULL;
+static const uint32_t *g_parent = NULL;
+
+ORC_API int orc_mt_prepare(uint32_t n, const uint32_t *parent) {
+    free(g_first); free(g_kids); free(g_dirty); free(g_items);
+    g_first = (uint32_t *)calloc((size_t)n + 1, sizeof(uint32_t));
+    g_kids = (uint32_t *)malloc((size_t)(n ? n : 1) * sizeof(uint32_t));
+    g_dirty = (uint8_t *)calloc(n ? n : 1, 1);
+    g_items = (sort_item *)malloc((size_t)(n ? n : 1) * sizeof(sort_item));
+    g_n = n; g_parent = parent;
+    for (uint32_t r = 0; r < n; ++r) {
+        uint32_t p = parent[r];
+        if (p < n) g_first[p + 1]++;
+        else if (p != ORC_NO_PARENT && p != ORC_DETACHED) return -1;
+    }
+    for (uint32_t r = 0; r < n; ++r) g_first[r + 1] += g_first[r];
+    uint32_t *cur = (uint32_t *)malloc((size_t)(n ? n : 1) * sizeof(uint32_t));
+    memcpy(cur, g_first, (size_t)n * sizeof(uint32_t));
+    for (uint32_t r = 0; r < n; ++r) { uint32_t p = parent[r]; if (p < n) g_kids[cur[p]++] = r; }
+    free(cur);
+    /* first touch of the scratch arrays in parallel */
+    #pragma omp parallel for schedule(static)
+    for (uint32_t r = 0; r < n; ++r) { g_items[r].key = 0; g_items[r].row = 0; }
+    return 0;
+}
 
 ORC_API int orc_propagate_mt(uint32_t n, const uint32_t *parent, const float *trs, float *gt,
                              const uint8_t *tchanged, const uint8_t *gt_ext_changed, int static_opt,
                              uint8_t *changed) {
-    memset(changed, 0, n);
     if (n == 0) return 0;
-    uint32_t *first = (uint32_t *)calloc((size_t)n + 1, sizeof(uint32_t));
-    uint32_t *kids = (uint32_t *)malloc((size_t)n * sizeof(uint32_t));
-    uint8_t *dirty = (uint8_t *)calloc(n, 1);
-    for (uint32_t r = 0; r < n; ++r) {
-        uint32_t p = parent[r];
-        if (p < n) first[p + 1]++;
-        else if (p != ORC_NO_PARENT && p != ORC_DETACHED) { free(first); free(kids); free(dirty); return -1; }
-    }
-    for (uint32_t r = 0; r < n; ++r) first[r + 1] += first[r];
-    {
-        uint32_t *cur = (uint32_t *)malloc((size_t)n * sizeof(uint32_t));
-        memcpy(cur, first, (size_t)n * sizeof(uint32_t));
-        for (uint32_t r = 0; r < n; ++r) { uint32_t p = parent[r]; if (p < n) kids[cur[p]++] = r; }
-        free(cur);
-    }
+    if (g_n != n || g_parent != parent) { int rc = orc_mt_prepare(n, parent); if (rc) return rc; }
+    uint32_t *first = g_first, *kids = g_kids;
+    uint8_t *dirty = g_dirty;
+    #pragma omp parallel for schedule(static)
+    for (uint32_t r = 0; r < n; ++r) { changed[r] = 0; dirty[r] = 0; }
     if (static_opt) {
         /* mark_dirty_trees: benign-race ancestor marking (the reference uses fetch_or, systems.rs:208-223) */
         #pragma omp parallel for schedule(static)
@@ -100,7 +120,6 @@ ORC_API int orc_propagate_mt(uint32_t n, const uint32_t *parent, const float *tr
         }
         free(stack);
     }
-    free(first); free(kids); free(dirty);
     return 0;
 }
 
@@ -116,7 +135,7 @@ ORC_API int orc_cull_mt(uint32_t n, const float *gt, const float *bounds, const 
         vv_changed[r] = 0;
     }
     int nt = omp_get_max_threads();
-    sort_item *items = (sort_item *)malloc((size_t)(n ? n : 1) * sizeof(sort_item));
+    sort_item *items = (g_n == n && g_items) ? g_items : (sort_item *)malloc((size_t)(n ? n : 1) * sizeof(sort_item));
     uint32_t *tcount = (uint32_t *)calloc((size_t)nt + 1, sizeof(uint32_t));
     for (uint32_t v = 0; v < n_views; ++v) {
         if (!(view_flags[v] & VIEW_ACTIVE)) { visible_count[v] = 0xFFFFFFFFu; continue; }
@@ -161,6 +180,7 @@ ORC_API int orc_cull_mt(uint32_t n, const float *gt, const float *bounds, const 
         if (flags[r] & F_NO_CPU_CULLING) continue;
         if ((vv[r] & 3u) == 2u) { vv[r] = 0; vv_changed[r] = 1; }
     }
-    free(items); free(tcount);
+    if (items != g_items) free(items);
+    free(tcount);
     return 0;
 }

@@ -51,6 +51,9 @@ def lib_mt():
         _lib_mt = C.CDLL(os.path.join(_HERE, "libbevy_oracle_mt.so"))
         _declare(_lib_mt)
         _lib_mt.orc_mt_threads.restype = C.c_int
+        _lib_mt.orc_mt_set_threads.argtypes = [C.c_int]
+        _lib_mt.orc_mt_prepare.restype = C.c_int
+        _lib_mt.orc_mt_prepare.argtypes = [C.c_uint32, C.POINTER(C.c_uint32)]
     return _lib_mt
 
 
