@@ -101,6 +101,7 @@ _SIGNATURES = {
     "b200vis_set_stream": (C.c_int32, [_vp, _vp]),
     "b200vis_synchronize": (C.c_int32, [_vp]),
     "b200vis_join": (C.c_int32, [_vp]),
+    "b200vis_tail_stream": (C.c_int32, [_vp, _P(_vp)]),
     "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
     "b200vis_plan_row_order": (C.c_int32, [C.c_uint32, _vp, _vp]),
     "b200vis_upload_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
@@ -247,6 +248,11 @@ class Context:
 
     def set_stream(self, cuda_stream):
         self._check(self._lib.b200vis_set_stream(self._h, _vp(cuda_stream)))
+
+    def tail_stream(self):
+        s = _vp()
+        self._check(self._lib.b200vis_tail_stream(self._h, C.byref(s)))
+        return s.value or 0
 
     def join(self):
         self._check(self._lib.b200vis_join(self._h))

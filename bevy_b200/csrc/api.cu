@@ -34,6 +34,9 @@ struct b200vis_ctx {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_tile = nullptr, ev_side[2] = {nullptr, nullptr};
     bool pipeline = true, side_pending = false;
+    // a frame whose tail was started (expand + cluster assign on the side stream) but whose CLUSTER_LISTS stage is
+    // still to come in a later b200vis_run call (multi-GPU: the host all-gathers the slabs in between)
+    bool tail_open = false; uint32_t open_frame = 0; const FrameConsts *open_fc = nullptr;
     float4 *d_light_snap = nullptr;     // [2][max_lights]
     uint32_t *d_tag_flag = nullptr;     // 1 if every light row carries its ordinal (k_tag_lights)
     bool lights_tag_dirty = true, lights_tagged = false;
@@ -741,10 +744,19 @@ extern "C" int32_t b200vis_set_cluster_exchange_buffers(b200vis_ctx *ctx, void *
 // ------------------------------------------------------------------------------------------
 // Makes the main stream wait for whatever the side stream still has in flight (cheap, asynchronous).
 static int32_t join_side(b200vis_ctx *ctx) {
+    if (ctx->tail_open) {   // work of an unfinished tail is on the side stream too
+        CU(cudaEventRecord(ctx->ev_tile, ctx->side_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_tile, 0));
+    }
     if (ctx->side_pending) {
         for (cudaEvent_t e : ctx->ev_side) CU(cudaStreamWaitEvent(ctx->stream, e, 0));
         ctx->side_pending = false;
     }
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_tail_stream(b200vis_ctx *ctx, void **cuda_stream) {
+    if (!ctx || !cuda_stream) return B200VIS_ERR_INVALID_ARG;
+    *cuda_stream = ctx->pipeline ? static_cast<void *>(ctx->side_stream) : static_cast<void *>(ctx->stream);
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_join(b200vis_ctx *ctx) {
@@ -758,14 +770,33 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     if ((stages & B200VIS_STAGE_CULL) && !ctx->bounds_set) return fail(ctx, B200VIS_ERR_NOT_READY, "run: bounds/flags were never uploaded");
     cudaStream_t st = ctx->stream;
     const bool do_prop = stages & B200VIS_STAGE_PROPAGATE, do_cull = stages & B200VIS_STAGE_CULL;
-    // Pipelined mode: the whole frame in one call on one GPU.  The tail of frame f (expand + cluster) goes to the side
-    // stream and overlaps frame f+1's tile pass; frame f+2's tile pass waits for it (it reuses frame f's buffers).
-    const bool pipelined = ctx->pipeline && stages == B200VIS_STAGE_ALL && ctx->cl.world == 1;
+    const bool has_assign = stages & B200VIS_STAGE_CLUSTER_ASSIGN, has_lists = stages & B200VIS_STAGE_CLUSTER_LISTS;
+    // ---- continuation of an open tail: CLUSTER_LISTS after the host's all-gather, still on the side stream --------
+    if (ctx->pipeline && ctx->tail_open && stages == B200VIS_STAGE_CLUSTER_LISTS) {
+        ClusterBufs cl = ctx->cl;
+        cl.blob = reinterpret_cast<const float *>(ctx->open_fc);
+        cudaStream_t tail = ctx->side_stream;
+        launch_cluster_lists(tail, ctx->open_fc, cl, ctx->d_stats, ctx->cfg.max_views);
+        if (ctx->have_sink)
+            launch_publish_clusters(tail, ctx->open_fc, cl, ctx->sink_off_d, ctx->sink_idx_d, ctx->sink.cluster_capacity, ctx->d_stats,
+                                    ctx->sink_stats_d, ctx->open_frame % 3u, ctx->open_frame + 1u, ctx->cfg.max_views);
+        CU(cudaEventRecord(ctx->ev_side[ctx->open_frame & 1u], tail));
+        ctx->side_pending = true; ctx->tail_open = false;
+        CU(cudaGetLastError());
+        return B200VIS_OK;
+    }
+    // Pipelined mode: a whole frame (or a frame up to the cluster exchange).  The tail of frame f (expand + cluster) goes to
+    // the side stream and overlaps frame f+1's tile pass; frame f+2's tile pass waits for it (it reuses frame f's buffers).
+    const bool pipelined = ctx->pipeline && do_prop && do_cull && has_assign && !ctx->tail_open;
     const uint32_t frame = ctx->frame;
     const uint32_t cslot = frame % 3u, mslot = frame & 1u;
     if (pipelined) {
         if (ctx->side_pending && frame >= 2) CU(cudaStreamWaitEvent(st, ctx->ev_side[mslot], 0));   // tail of frame f-2
     } else {
+        if (ctx->tail_open) {   // an abandoned open tail: close it so that the event chain stays consistent
+            CU(cudaEventRecord(ctx->ev_side[ctx->open_frame & 1u], ctx->side_stream));
+            ctx->side_pending = true; ctx->tail_open = false;
+        }
         const int32_t rc = join_side(ctx); if (rc) return rc;
     }
     ClusterBufs cl = ctx->cl;
@@ -847,7 +878,10 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         launch_publish_clusters(tail, fc, cl, (stages & B200VIS_STAGE_CLUSTER_LISTS) ? ctx->sink_off_d : nullptr, ctx->sink_idx_d,
                                 ctx->sink.cluster_capacity, ctx->d_stats, ctx->sink_stats_d, cslot, frame + (do_cull ? 1u : 0u), ctx->cfg.max_views);
     if (pe) CU(cudaEventRecord(pe[4], tail));
-    if (pipelined) { CU(cudaEventRecord(ctx->ev_side[mslot], tail)); ctx->side_pending = true; }
+    if (pipelined) {
+        if (has_lists) { CU(cudaEventRecord(ctx->ev_side[mslot], tail)); ctx->side_pending = true; }
+        else { ctx->tail_open = true; ctx->open_frame = frame; ctx->open_fc = fc; }
+    }
     CU(cudaGetLastError());
     if (do_cull) { ctx->frame++; ctx->parity = ctx->frame % 3u; }
     return B200VIS_OK;

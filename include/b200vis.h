@@ -171,6 +171,10 @@ B200VIS_API int32_t b200vis_synchronize(b200vis_ctx *ctx);
  * context's stream wait (asynchronously) for that tail, e.g. before recording a timing event; every download and
  * b200vis_synchronize join implicitly.  Set B200VIS_PIPELINE=0 to serialise everything on one stream. */
 B200VIS_API int32_t b200vis_join(b200vis_ctx *ctx);
+/* Multi-GPU: b200vis_run(PROPAGATE|CULL|CLUSTER_ASSIGN) leaves the frame's tail open on this stream; the host issues
+ * its all-gather of the cluster slabs ON THIS STREAM (so it is ordered after CLUSTER_ASSIGN) and then calls
+ * b200vis_run(CLUSTER_LISTS), which continues there.  Equals the context's stream when pipelining is off. */
+B200VIS_API int32_t b200vis_tail_stream(b200vis_ctx *ctx, void **cuda_stream);
 
 /* ---- mirroring the ECS columns --------------------------------------------- */
 /* Hierarchy + identity; call on spawn/despawn/Changed<ChildOf> only.

@@ -43,11 +43,15 @@ def main():
     for f in range(3):
         if f:
             scenes.advance_cameras(full)            # cameras are shared objects between full and sub
-            rws, trs = scenes.mutate_roots(sub, f)
-            ctx.upload_transforms_scattered(rws, trs)
+            full_rows, _ = scenes.mutate_roots(full, f)     # ONE animation, defined on the full scene ...
+            mine = np.isin(full_rows, rows)                 # ... of which this rank uploads its own roots
+            local = np.searchsorted(rows, full_rows[mine]).astype(np.uint32)
+            sub.trs[local] = full.trs[full_rows[mine]]
+            ctx.upload_transforms_scattered(local, sub.trs[local])
         pipe.update_views()
         ctx.run(bb.STAGE_PROPAGATE | bb.STAGE_CULL | bb.STAGE_CLUSTER_ASSIGN)
-        parallel.all_gather_slabs(recv, send)
+        with torch.cuda.stream(torch.cuda.ExternalStream(ctx.tail_stream(), device=dev)):
+            parallel.all_gather_slabs(recv, send)          # on the stream the frame's tail runs on
         ctx.run(bb.STAGE_CLUSTER_LISTS)
         stats = ctx.download_frame_stats()
         far, cnt = parallel.reduce_feedback([stats.cluster_farthest_z[v] for v in range(V)],
@@ -61,9 +65,7 @@ def main():
         clusters = [ctx.download_clusters(v) for v in range(V)]
         if rank == 0:
             if f:
-                # the oracle world holds the FULL scene: apply the same root mutation to it
-                full_rows, _ = scenes.mutate_roots(full, f)
-                world_o.tchanged[full_rows] = 1
+                world_o.tchanged[full_rows] = 1             # the oracle world holds the FULL scene
             planes = np.stack([np.ctypeslib.as_array(vw.half_spaces).reshape(6, 4).copy() for vw in pipe.views])
             _, _, lists, cl = world_o.frame(planes)
             ranges = parallel.shard_bounds(n_lights, world)

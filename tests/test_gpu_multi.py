@@ -17,4 +17,5 @@ def test_two_gpu_shard_gather_matches_oracle():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(here, "multi_gpu_parity.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(res.stdout[-2000:]); print(res.stderr[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
