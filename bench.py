@@ -215,12 +215,11 @@ def main():
         ctx.set_cluster_exchange_buffers(send.data_ptr(), recv.data_ptr())
 
     tail_stream = torch.cuda.ExternalStream(ctx.tail_stream(), device=dev) if world > 1 else None
-
     def run_stages():
         if world > 1:
             ctx.run(bb.STAGE_PROPAGATE | bb.STAGE_CULL | bb.STAGE_CLUSTER_ASSIGN)   # tile pass on `stream`, tail on the side stream
-            with torch.cuda.stream(tail_stream):
-                dist.all_gather_into_tensor(recv, send)    # the single NCCL all-gather of the cluster slabs, ordered after ASSIGN
+            with torch.cuda.stream(tail_stream):           # the single NCCL all-gather of the cluster slabs, ordered after ASSIGN
+                dist.all_gather_into_tensor(recv, send)
             ctx.run(bb.STAGE_CLUSTER_LISTS)
         else:
             ctx.run(bb.STAGE_ALL)
