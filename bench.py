@@ -207,22 +207,17 @@ def main():
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
-    send = recv = None
     if world > 1:
-        slab = ctx.cluster_exchange_bytes()
-        send = torch.zeros(slab // 4, dtype=torch.int32, device=dev)
-        recv = torch.zeros(world * slab // 4, dtype=torch.int32, device=dev)
-        ctx.set_cluster_exchange_buffers(send.data_ptr(), recv.data_ptr())
+        # built-in exchange: the library issues the one ncclAllGather of the cluster slabs itself (same NCCL the process
+        # already loaded for torch.distributed); the 128-byte unique id travels over torch.distributed
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.from_numpy(bb.Context.comm_unique_id()))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(uid.cpu().numpy())
 
-    tail_stream = torch.cuda.ExternalStream(ctx.tail_stream(), device=dev) if world > 1 else None
     def run_stages():
-        if world > 1:
-            ctx.run(bb.STAGE_PROPAGATE | bb.STAGE_CULL | bb.STAGE_CLUSTER_ASSIGN)   # tile pass on `stream`, tail on the side stream
-            with torch.cuda.stream(tail_stream):           # the single NCCL all-gather of the cluster slabs, ordered after ASSIGN
-                dist.all_gather_into_tensor(recv, send)
-            ctx.run(bb.STAGE_CLUSTER_LISTS)
-        else:
-            ctx.run(bb.STAGE_ALL)
+        ctx.run(bb.STAGE_ALL)      # N > 1: PROPAGATE, CULL, CLUSTER_ASSIGN, ncclAllGather of the slabs, CLUSTER_LISTS
 
     fb_buf = torch.zeros(2 * V, dtype=torch.float32, device=dev)
 

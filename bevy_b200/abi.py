@@ -129,6 +129,8 @@ _SIGNATURES = {
     "b200vis_download_visible": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_download_clusters": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_set_result_sink": (C.c_int32, [_vp, _P(ResultSink)]),
+    "b200vis_comm_unique_id": (C.c_int32, [_vp]),
+    "b200vis_comm_init": (C.c_int32, [_vp, _vp]),
     "b200vis_cluster_exchange_bytes": (C.c_int32, [_vp, _P(C.c_size_t)]),
     "b200vis_set_cluster_exchange_buffers": (C.c_int32, [_vp, _vp, _vp]),
     "b200vis_host_perspective": (None, [C.c_float, C.c_float, C.c_float, _vp]),
@@ -397,6 +399,19 @@ class Context:
         s.cluster_capacity = 0 if cluster_indices is None else cluster_indices.shape[1]
         self._sink = (s, visible_rows, cluster_offsets, cluster_indices)
         self._check(self._lib.b200vis_set_result_sink(self._h, C.byref(s)))
+
+    @staticmethod
+    def comm_unique_id():
+        buf = np.zeros(128, np.uint8)
+        rc = load_library().b200vis_comm_unique_id(_ptr(buf))
+        if rc:
+            raise B200VisError(rc, load_library().b200vis_last_error(None).decode())
+        return buf
+
+    def comm_init(self, unique_id):
+        uid = _arr(unique_id, np.uint8)
+        assert uid.size == 128
+        self._check(self._lib.b200vis_comm_init(self._h, _ptr(uid)))
 
     def cluster_exchange_bytes(self):
         n = C.c_size_t(0)

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include "../../include/b200vis.h"
 #include "device_types.cuh"
@@ -23,6 +24,34 @@
 using namespace b200vis;
 
 static thread_local std::string g_create_error;
+
+// ---- NCCL through dlopen: no link-time dependency, and the process keeps ONE NCCL (the one torch already loaded) ----
+namespace {
+struct NcclId { char b[128]; };   // ncclUniqueId (passed BY VALUE to ncclCommInitRank)
+struct NcclApi {
+    using Id = NcclId;
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(lib, "ncclAllGather"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        return GetUniqueId && CommInitRank && AllGather && CommDestroy && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclUint32 = 3;   // ncclUint32 in nccl.h's ncclDataType_t
+}
 
 struct b200vis_ctx {
     b200vis_config cfg{};
@@ -93,6 +122,8 @@ struct b200vis_ctx {
     b200vis_result_sink sink{}; bool have_sink = false;
     uint32_t *sink_rows_d = nullptr, *sink_off_d = nullptr, *sink_idx_d = nullptr, *sink_stats_d = nullptr;
 
+    void *nccl_comm = nullptr;          // b200vis_comm_init
+    uint32_t *d_gather = nullptr;       // [world][slab] when the library owns the exchange
     b200vis_cluster_feedback auto_fb[kMaxViews]{};   // b200vis_step: last frame's Clusters feedback
 
     // staging for AoS <-> SoA conversion
@@ -152,6 +183,8 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     }
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
     for (auto &r : ctx->recorded) if (r.dev) cudaFree(r.dev);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->ev_tile) cudaEventDestroy(ctx->ev_tile);
@@ -722,6 +755,26 @@ extern "C" int32_t b200vis_collect_stage_times_ms(b200vis_ctx *ctx, float *tile_
 // ------------------------------------------------------------------------------------------
 // multi-GPU exchange buffers
 // ------------------------------------------------------------------------------------------
+extern "C" int32_t b200vis_comm_unique_id(uint8_t id[B200VIS_COMM_ID_BYTES]) {
+    if (!id) return B200VIS_ERR_INVALID_ARG;
+    if (!g_nccl.load()) return fail(nullptr, B200VIS_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded: %s", dlerror());
+    const int rc = g_nccl.GetUniqueId(id);
+    if (rc) return fail(nullptr, B200VIS_ERR_CUDA, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_comm_init(b200vis_ctx *ctx, const uint8_t id[B200VIS_COMM_ID_BYTES]) {
+    CHECK_CTX_JOIN();
+    if (!id) return fail(ctx, B200VIS_ERR_INVALID_ARG, "comm_init: null id");
+    if (ctx->cl.world <= 1) return fail(ctx, B200VIS_ERR_INVALID_ARG, "comm_init: the context was created with world_size <= 1");
+    if (!g_nccl.load()) return fail(ctx, B200VIS_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded: %s", dlerror());
+    NcclApi::Id uid; memcpy(uid.b, id, sizeof uid.b);
+    const int rc = g_nccl.CommInitRank(&ctx->nccl_comm, (int)ctx->cl.world, uid, (int)ctx->cl.rank);
+    if (rc) { ctx->nccl_comm = nullptr; return fail(ctx, B200VIS_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc)); }
+    if (!ctx->d_gather) CU(dalloc(&ctx->d_gather, (size_t)ctx->cl.world * ctx->slab_bytes / 4));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cl.send = ctx->d_slab; ctx->cl.recv = ctx->d_gather;
+    return B200VIS_OK;
+}
 extern "C" int32_t b200vis_cluster_exchange_bytes(const b200vis_ctx *ctx, size_t *slab_bytes) {
     if (!ctx || !slab_bytes) return B200VIS_ERR_INVALID_ARG;
     *slab_bytes = ctx->slab_bytes;
@@ -872,6 +925,12 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     if (pe) CU(cudaEventRecord(pe[3], tail));
     if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
         launch_cluster_assign(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+    if (has_assign && has_lists && cl.world > 1) {
+        // the ONE data-path collective: rank-major all-gather of the fixed-size cluster x light slabs over NVLink
+        if (!ctx->nccl_comm) return fail(ctx, B200VIS_ERR_NOT_READY, "run(ALL) with world_size > 1 needs b200vis_comm_init (or run ASSIGN and LISTS separately around your own all-gather)");
+        const int nrc = g_nccl.AllGather(cl.send, const_cast<uint32_t *>(cl.recv), ctx->slab_bytes / 4, kNcclUint32, ctx->nccl_comm, tail);
+        if (nrc) return fail(ctx, B200VIS_ERR_CUDA, "ncclAllGather: %s", g_nccl.GetErrorString(nrc));
+    }
     if (stages & B200VIS_STAGE_CLUSTER_LISTS)
         launch_cluster_lists(tail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if (ctx->have_sink && (do_cull || (stages & B200VIS_STAGE_CLUSTER_LISTS)))

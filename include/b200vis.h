@@ -311,6 +311,13 @@ B200VIS_API int32_t b200vis_set_result_sink(b200vis_ctx *ctx, const b200vis_resu
 /* Each rank fills `slab_bytes` at `send`; after all-gathering the slabs rank-major into `recv`
  * (world_size * slab_bytes) the LISTS stage reads `recv`.  Buffers are caller-allocated device memory
  * (e.g. torch tensors); with world_size <= 1 the library uses its own buffer and no exchange. */
+/* Built-in exchange: the library dlopen()s libnccl.so.2 (the copy the host process already loaded, e.g. torch's), rank 0
+ * makes a unique id, the host broadcasts those 128 bytes by any means, every rank calls b200vis_comm_init (a collective),
+ * and from then on b200vis_run(B200VIS_STAGE_ALL) issues the ncclAllGather of the slabs itself, on the frame's tail
+ * stream, between CLUSTER_ASSIGN and CLUSTER_LISTS -- one call per frame, pipelined like the single-GPU path. */
+#define B200VIS_COMM_ID_BYTES 128
+B200VIS_API int32_t b200vis_comm_unique_id(uint8_t id[B200VIS_COMM_ID_BYTES]);
+B200VIS_API int32_t b200vis_comm_init(b200vis_ctx *ctx, const uint8_t id[B200VIS_COMM_ID_BYTES]);
 B200VIS_API int32_t b200vis_cluster_exchange_bytes(const b200vis_ctx *ctx, size_t *slab_bytes);
 B200VIS_API int32_t b200vis_set_cluster_exchange_buffers(b200vis_ctx *ctx, void *send_device, void *recv_device);
 

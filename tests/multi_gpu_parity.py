@@ -30,10 +30,18 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    slab = ctx.cluster_exchange_bytes()
-    send = torch.zeros(slab // 4, dtype=torch.int32, device=dev)
-    recv = torch.zeros(world * slab // 4, dtype=torch.int32, device=dev)
-    ctx.set_cluster_exchange_buffers(send.data_ptr(), recv.data_ptr())
+    builtin = "--builtin" in sys.argv        # the library's own ncclAllGather instead of the host's collective
+    if builtin:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.from_numpy(bb.Context.comm_unique_id()))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(uid.cpu().numpy())
+    else:
+        slab = ctx.cluster_exchange_bytes()
+        send = torch.zeros(slab // 4, dtype=torch.int32, device=dev)
+        recv = torch.zeros(world * slab // 4, dtype=torch.int32, device=dev)
+        ctx.set_cluster_exchange_buffers(send.data_ptr(), recv.data_ptr())
     V = len(full.cameras)
     ok = True
     if rank == 0:
@@ -49,10 +57,13 @@ def main():
             sub.trs[local] = full.trs[full_rows[mine]]
             ctx.upload_transforms_scattered(local, sub.trs[local])
         pipe.update_views()
-        ctx.run(bb.STAGE_PROPAGATE | bb.STAGE_CULL | bb.STAGE_CLUSTER_ASSIGN)
-        with torch.cuda.stream(torch.cuda.ExternalStream(ctx.tail_stream(), device=dev)):
-            parallel.all_gather_slabs(recv, send)          # on the stream the frame's tail runs on
-        ctx.run(bb.STAGE_CLUSTER_LISTS)
+        if builtin:
+            ctx.run(bb.STAGE_ALL)
+        else:
+            ctx.run(bb.STAGE_PROPAGATE | bb.STAGE_CULL | bb.STAGE_CLUSTER_ASSIGN)
+            with torch.cuda.stream(torch.cuda.ExternalStream(ctx.tail_stream(), device=dev)):
+                parallel.all_gather_slabs(recv, send)          # on the stream the frame's tail runs on
+            ctx.run(bb.STAGE_CLUSTER_LISTS)
         stats = ctx.download_frame_stats()
         far, cnt = parallel.reduce_feedback([stats.cluster_farthest_z[v] for v in range(V)],
                                             [stats.cluster_index_count[v] for v in range(V)], device=dev)
