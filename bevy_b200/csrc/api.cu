@@ -232,7 +232,11 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         CU(dalloc(&ctx->d_blob2[0], ctx->blob_cap)); CU(dalloc(&ctx->d_blob2[1], ctx->blob_cap));
         ctx->d_blob = ctx->d_blob2[0];
         ctx->d_consts = reinterpret_cast<FrameConsts *>(ctx->d_blob);
-        CU(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        {   // the tail kernels are small and latency-bound: give their CTAs priority over the bulk tile pass
+            int lo = 0, hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+        }
         CU(cudaEventCreateWithFlags(&ctx->ev_tile, cudaEventDisableTiming));
         for (cudaEvent_t &e : ctx->ev_side) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         { const char *e = getenv("B200VIS_PIPELINE"); if (e && e[0] == '0') ctx->pipeline = false; }

@@ -1223,7 +1223,13 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate_cull_tma<P, C, S>, kTileRows, sizeof(TmaSmem));
         grid = sms * (per_sm > 0 ? per_sm : 1);    // persistent: one CTA per resident slot
     }
-    const uint32_t g = n_tiles < (uint32_t)grid ? n_tiles : (uint32_t)grid;
+    uint32_t g = n_tiles < (uint32_t)grid ? n_tiles : (uint32_t)grid;
+    // B200VIS_TILES_PER_CTA=k (default 2; 0 = fully persistent) bounds the tiles one CTA processes (grid = n_tiles / k):
+    // CTAs then retire continuously, which lets the (higher priority) tail kernels of the previous frame and the
+    // all-gather slip in between instead of waiting for the whole persistent grid to drain
+    static int tiles_per_cta = -1;
+    if (tiles_per_cta < 0) { const char *e = getenv("B200VIS_TILES_PER_CTA"); tiles_per_cta = e ? atoi(e) : 2; }
+    if (tiles_per_cta > 0) { const uint32_t want = (n_tiles + tiles_per_cta - 1) / tiles_per_cta; if (want > g) g = want; }
     // programmatic dependent launch: this kernel's CTAs may become resident (barrier init, parameter loads) while the
     // previous kernel in the stream drains; griddepcontrol.wait in the kernel orders the actual data accesses
     cudaLaunchConfig_t cfg = {};
