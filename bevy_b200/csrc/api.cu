@@ -61,7 +61,8 @@ struct b200vis_ctx {
     // stream while frame f+1's tile pass already runs on the main stream (masks / counters / constants are
     // double or triple buffered by frame number).
     cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_tile = nullptr, ev_side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_tile = nullptr, ev_side[2] = {nullptr, nullptr}, ev_pub = nullptr;
+    bool pub_pending = false;           // a publish_visible copy is in flight on the side stream
     bool pipeline = true, side_pending = false;
     // a frame whose tail was started (expand + cluster assign on the side stream) but whose CLUSTER_LISTS stage is
     // still to come in a later b200vis_run call (multi-GPU: the host all-gathers the slabs in between)
@@ -188,6 +189,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     for (auto &r : ctx->recorded) if (r.dev) cudaFree(r.dev);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->ev_tile) cudaEventDestroy(ctx->ev_tile);
+    if (ctx->ev_pub) cudaEventDestroy(ctx->ev_pub);
     for (cudaEvent_t e : ctx->ev_side) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -238,6 +240,7 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
             CU(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
         }
         CU(cudaEventCreateWithFlags(&ctx->ev_tile, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_pub, cudaEventDisableTiming));
         for (cudaEvent_t &e : ctx->ev_side) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         { const char *e = getenv("B200VIS_PIPELINE"); if (e && e[0] == '0') ctx->pipeline = false; }
         for (int i = 0; i < b200vis_ctx::kRing; ++i) {
@@ -283,9 +286,10 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
     CU(cudaSetDevice(ctx->device))
 
 static int32_t join_side(b200vis_ctx *ctx);
+static int32_t join_all(b200vis_ctx *ctx);
 #define CHECK_CTX_JOIN()                                                   \
     CHECK_CTX();                                                           \
-    { const int32_t jrc_ = join_side(ctx); if (jrc_) return jrc_; }
+    { const int32_t jrc_ = join_all(ctx); if (jrc_) return jrc_; }
 
 static int32_t check_range(b200vis_ctx *ctx, uint32_t first, uint32_t count, const char *what) {
     if ((uint64_t)first + count > ctx->cfg.max_entities)
@@ -494,11 +498,20 @@ extern "C" int32_t b200vis_upload_transforms_scattered(b200vis_ctx *ctx, uint32_
     if (count > ctx->cfg.max_entities) return fail(ctx, B200VIS_ERR_CAPACITY, "upload_transforms_scattered: count > max_entities");
     {   // sources already in device memory (a renderer / physics step on the same GPU): no staging copy
         cudaPointerAttributes pa{}, pb{};
-        if (cudaPointerGetAttributes(&pa, rows) == cudaSuccess && cudaPointerGetAttributes(&pb, trs) == cudaSuccess &&
-            pa.type == cudaMemoryTypeDevice && pb.type == cudaMemoryTypeDevice) {
-            launch_scatter_trs(ctx->stream, ctx->rows, count, rows, trs);
-            CU(cudaGetLastError());
-            return B200VIS_OK;
+        if (cudaPointerGetAttributes(&pa, rows) == cudaSuccess && cudaPointerGetAttributes(&pb, trs) == cudaSuccess) {
+            if (pa.type == cudaMemoryTypeDevice && pb.type == cudaMemoryTypeDevice) {
+                launch_scatter_trs(ctx->stream, ctx->rows, count, rows, trs);
+                CU(cudaGetLastError());
+                return B200VIS_OK;
+            }
+            // pinned (page-locked, mapped) host memory: the scatter kernel reads it over PCIe itself -- one launch instead
+            // of two staging copies plus a launch.  The caller must not rewrite the buffers until the stream has passed.
+            if (pa.type == cudaMemoryTypeHost && pb.type == cudaMemoryTypeHost && pa.devicePointer && pb.devicePointer) {
+                launch_scatter_trs(ctx->stream, ctx->rows, count, static_cast<const uint32_t *>(pa.devicePointer),
+                                   static_cast<const float *>(pb.devicePointer));
+                CU(cudaGetLastError());
+                return B200VIS_OK;
+            }
         }
         cudaGetLastError();   // clear the error state cudaPointerGetAttributes leaves for unregistered host memory
     }
@@ -811,6 +824,11 @@ static int32_t join_side(b200vis_ctx *ctx) {
     }
     return B200VIS_OK;
 }
+// additionally waits for an in-flight publish of the visible rows (readers of the sink / of the lists call this)
+static int32_t join_all(b200vis_ctx *ctx) {
+    if (ctx->pub_pending) { CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pub, 0)); ctx->pub_pending = false; }
+    return join_side(ctx);
+}
 extern "C" int32_t b200vis_tail_stream(b200vis_ctx *ctx, void **cuda_stream) {
     if (!ctx || !cuda_stream) return B200VIS_ERR_INVALID_ARG;
     *cuda_stream = ctx->pipeline ? static_cast<void *>(ctx->side_stream) : static_cast<void *>(ctx->stream);
@@ -818,7 +836,7 @@ extern "C" int32_t b200vis_tail_stream(b200vis_ctx *ctx, void **cuda_stream) {
 }
 extern "C" int32_t b200vis_join(b200vis_ctx *ctx) {
     CHECK_CTX();
-    return join_side(ctx);
+    return join_all(ctx);
 }
 
 extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
@@ -923,9 +941,20 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         CU(cudaStreamWaitEvent(tail, ctx->ev_tile, 0));
     } else if (pe) CU(cudaEventRecord(pe[1], st));
     if (pe) CU(cudaEventRecord(pe[2], tail));
+    if (do_cull && ctx->pub_pending) { CU(cudaStreamWaitEvent(tail, ctx->ev_pub, 0)); ctx->pub_pending = false; }   // lists are rewritten
     if (do_cull) launch_expand_visible(tail, vb, R.row_of_rank, fc, ctx->d_stats, cslot, ctx->n, ctx->cfg.max_views);
-    if (do_cull && ctx->have_sink && ctx->sink_rows_d)
-        launch_publish_visible(tail, vb, ctx->d_stats, ctx->sink_rows_d, ctx->sink.visible_capacity, ctx->n, active_consts(ctx).n_views);
+    if (do_cull && ctx->have_sink && ctx->sink_rows_d) {
+        // posting ~1 MB of visible rows over PCIe takes tens of microseconds: in the serial (non-pipelined) case do it on the
+        // side stream so it overlaps the cluster kernels; every later consumer joins the side stream
+        cudaStream_t pub = tail;
+        if (!pipelined) {
+            CU(cudaEventRecord(ctx->ev_tile, tail));
+            CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_tile, 0));
+            pub = ctx->side_stream;
+        }
+        launch_publish_visible(pub, vb, ctx->d_stats, ctx->sink_rows_d, ctx->sink.visible_capacity, ctx->n, active_consts(ctx).n_views);
+        if (!pipelined) { CU(cudaEventRecord(ctx->ev_pub, pub)); ctx->pub_pending = true; }
+    }
     if (pe) CU(cudaEventRecord(pe[3], tail));
     if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
         launch_cluster_assign(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
@@ -1124,7 +1153,7 @@ extern "C" int32_t b200vis_step(b200vis_ctx *ctx, uint32_t n_changed, const uint
         if ((rc = b200vis_run(ctx, B200VIS_STAGE_CLUSTER))) return rc;
     }
     if (!(flags & B200VIS_STEP_WAIT)) return B200VIS_OK;
-    if ((rc = join_side(ctx))) return rc;
+    if ((rc = join_all(ctx))) return rc;
     const b200vis_frame_stats *st = nullptr;
     b200vis_frame_stats local;
     if (ctx->have_sink) { CU(cudaStreamSynchronize(ctx->stream)); st = ctx->sink.stats; }
