@@ -321,6 +321,14 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - t0
     e2e_sec = max(e2e_wall, ev0.elapsed_time(ev1) / 1e3)
+    # where the e2e frame goes on the device (CUDA events around the stages, a few extra frames, not part of the timing)
+    ctx.set_profiling(True)
+    for f in range(40):
+        e2e_step((W + K + f) % WIN)
+    pt, pe_, pc, pn = ctx.collect_stage_times_ms()
+    ctx.set_profiling(False)
+    e2e_breakdown = {"tile_ms": pt / max(pn, 1) * (2 if world == 1 else 1), "expand_ms": pe_ / max(pn, 1) * (2 if world == 1 else 1),
+                     "cluster_ms": pc / max(pn, 1) * (2 if world == 1 else 1), "host_wall_ms": e2e_wall * 1e3 / K}
     visible_pairs = sum(last_stats.visible_count[v] for v in range(V))
     cluster_indices = sum(last_stats.cluster_index_count[v] for v in range(V))
 
@@ -404,7 +412,7 @@ def main():
                        "visible_pairs_last_frame": int(visible_pairs), "cluster_indices_last_frame": int(cluster_indices)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "entities/s", "h2d_bytes_per_step": int(e2e_h2d),
-                    "d2h_bytes_per_step": int(np.mean(d2h_bytes)), "ms_per_step": e2e_ms / K,
+                    "d2h_bytes_per_step": int(np.mean(d2h_bytes)), "ms_per_step": e2e_ms / K, "device_breakdown": e2e_breakdown,
                     "note": "GlobalTransforms stay device-resident; the GPU writes stats, sorted visible lists and cluster lists into pinned host memory (result sink), one stream sync per frame"},
             "gpu_launches": 6 * K, "host_enqueue_ms_per_step": host_enqueue_ms,
             "roofline": {"bound": "hbm", "kernel": "k_propagate_cull", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -123,6 +124,7 @@ struct b200vis_ctx {
     b200vis_result_sink sink{}; bool have_sink = false;
     uint32_t *sink_rows_d = nullptr, *sink_off_d = nullptr, *sink_idx_d = nullptr, *sink_stats_d = nullptr;
 
+    double step_t[6] = {0, 0, 0, 0, 0, 0}; uint64_t step_n = 0;   // B200VIS_STEP_TRACE: host time per phase of b200vis_step
     void *nccl_comm = nullptr;          // b200vis_comm_init
     uint32_t *d_gather = nullptr;       // [world][slab] when the library owns the exchange
     b200vis_cluster_feedback auto_fb[kMaxViews]{};   // b200vis_step: last frame's Clusters feedback
@@ -184,6 +186,10 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     }
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->step_n && getenv("B200VIS_STEP_TRACE"))
+        fprintf(stderr, "[b200vis_step] %llu steps, host us/step: upload %.1f  frusta %.1f  run(prop|cull) %.1f  cluster prologue %.1f  run(cluster) %.1f  wait %.1f\n",
+                (unsigned long long)ctx->step_n, 1e6 * ctx->step_t[0] / ctx->step_n, 1e6 * ctx->step_t[1] / ctx->step_n, 1e6 * ctx->step_t[2] / ctx->step_n,
+                1e6 * ctx->step_t[3] / ctx->step_n, 1e6 * ctx->step_t[4] / ctx->step_n, 1e6 * ctx->step_t[5] / ctx->step_n);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->d_gather) cudaFree(ctx->d_gather);
     for (auto &r : ctx->recorded) if (r.dev) cudaFree(r.dev);
@@ -1139,25 +1145,35 @@ extern "C" int32_t b200vis_step(b200vis_ctx *ctx, uint32_t n_changed, const uint
     CHECK_CTX();
     if (n_cameras > ctx->cfg.max_views || (n_cameras && !cameras)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "step: bad camera array");
     int32_t rc;
+    using clk = std::chrono::steady_clock;
+    auto t0 = clk::now();
+    auto lap = [&](int i) { auto t1 = clk::now(); ctx->step_t[i] += std::chrono::duration<double>(t1 - t0).count(); t0 = t1; };
     if (n_changed && (rc = b200vis_upload_transforms_scattered(ctx, n_changed, rows, trs))) return rc;
+    lap(0);
     if ((rc = b200vis_set_view_count(ctx, n_cameras))) return rc;
     const bool clusters = cfg != nullptr && ctx->lights.n > 0;
     // frusta first, so the tile pass starts at once; the per-view cluster prologue (plane tables, z thresholds: tens of
     // microseconds of host maths) is computed while that kernel runs, then the cluster stage is enqueued behind it
     for (uint32_t v = 0; v < n_cameras; ++v)
         if ((rc = b200vis_update_camera(ctx, v, &cameras[v], nullptr, nullptr, nullptr))) return rc;
+    lap(1);
     if ((rc = b200vis_run(ctx, B200VIS_STAGE_PROPAGATE | B200VIS_STAGE_CULL))) return rc;
+    lap(2);
     if (clusters) {
         for (uint32_t v = 0; v < n_cameras; ++v)
             if ((rc = b200vis_update_camera(ctx, v, &cameras[v], cfg, &ctx->auto_fb[v], nullptr))) return rc;
+        lap(3);
         if ((rc = b200vis_run(ctx, B200VIS_STAGE_CLUSTER))) return rc;
+        lap(4);
     }
+    ctx->step_n++;
     if (!(flags & B200VIS_STEP_WAIT)) return B200VIS_OK;
     if ((rc = join_all(ctx))) return rc;
     const b200vis_frame_stats *st = nullptr;
     b200vis_frame_stats local;
     if (ctx->have_sink) { CU(cudaStreamSynchronize(ctx->stream)); st = ctx->sink.stats; }
     else { if ((rc = b200vis_download_frame_stats(ctx, &local))) return rc; st = &local; }
+    lap(5);
     if (clusters)
         for (uint32_t v = 0; v < n_cameras; ++v) {   // Clusters::last_frame_* (assign.rs:810-811)
             b200vis_cluster_feedback &fb = ctx->auto_fb[v];
