@@ -103,6 +103,7 @@ _SIGNATURES = {
     "b200vis_join": (C.c_int32, [_vp]),
     "b200vis_tail_stream": (C.c_int32, [_vp, _P(_vp)]),
     "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
+    "b200vis_host_plan_summary": (C.c_int32, [C.c_uint32, _vp, _P(C.c_uint32)]),
     "b200vis_plan_row_order": (C.c_int32, [C.c_uint32, _vp, _vp]),
     "b200vis_upload_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "b200vis_upload_transforms_scattered": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
@@ -210,6 +211,15 @@ def host_cluster_view_setup(cfg, camera_gt12, clip_from_view, frustum, layer_mas
     if rc:
         raise B200VisError(rc, "b200vis_host_cluster_view_setup")
     return out, scratch
+
+
+def host_plan_summary(parent):
+    """(tiles, passes, max in-tile levels, rows with a parent in another tile) of the execution plan."""
+    parent = _arr(parent, np.uint32); out = (C.c_uint32 * 4)()
+    rc = load_library().b200vis_host_plan_summary(len(parent), _ptr(parent), out)
+    if rc:
+        raise B200VisError(rc, load_library().b200vis_last_error(None).decode())
+    return tuple(out)
 
 
 def plan_row_order(parent):

@@ -329,7 +329,7 @@ extern "C" int32_t b200vis_set_static_transform_optimizations(b200vis_ctx *ctx, 
 // orders the tiles into passes so that a tile's out-of-tile parents are finished by an earlier
 // launch.  Forests of small trees need one pass; a tree larger than a tile needs a few.
 static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, std::vector<uint32_t> &topo,
-                          std::vector<Tile> &tiles_sorted) {
+                          std::vector<Tile> &tiles_sorted, std::vector<uint32_t> &pass_begin) {
     for (uint32_t r = 0; r < n; ++r) {
         const uint32_t p = parent[r];
         if (p == kNoParent || p == kDetached) continue;
@@ -401,11 +401,11 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
     // NOTE: tile_level of tile t only depends on tiles with a smaller index (topological rows), and
     // those are final by the time a row of t is visited, because rows are visited in ascending order.
     const uint32_t n_pass = tiles.empty() ? 0 : *std::max_element(tile_level.begin(), tile_level.end()) + 1;
-    ctx->pass_begin.assign(n_pass + 1, 0);
-    for (uint32_t lv : tile_level) ctx->pass_begin[lv + 1]++;
-    for (uint32_t p = 0; p < n_pass; ++p) ctx->pass_begin[p + 1] += ctx->pass_begin[p];
+    pass_begin.assign(n_pass + 1, 0);
+    for (uint32_t lv : tile_level) pass_begin[lv + 1]++;
+    for (uint32_t p = 0; p < n_pass; ++p) pass_begin[p + 1] += pass_begin[p];
     tiles_sorted.resize(tiles.size());
-    std::vector<uint32_t> cursor(ctx->pass_begin.begin(), ctx->pass_begin.end() - (n_pass ? 1 : 0));
+    std::vector<uint32_t> cursor(pass_begin.begin(), pass_begin.end() - (n_pass ? 1 : 0));
     for (size_t i = 0; i < tiles.size(); ++i) tiles_sorted[cursor[tile_level[i]]++] = tiles[i];
     return B200VIS_OK;
 }
@@ -415,7 +415,8 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     if (n && (!parent || !entity_bits)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_topology: null array");
     if (n > ctx->cfg.max_entities) return fail(ctx, B200VIS_ERR_CAPACITY, "set_topology: %u rows > max_entities %u", n, ctx->cfg.max_entities);
     std::vector<uint32_t> topo; std::vector<Tile> tiles;
-    int32_t rc = build_plan(ctx, n, parent, topo, tiles);
+    std::vector<uint32_t> pass_begin;
+    int32_t rc = build_plan(ctx, n, parent, topo, tiles, pass_begin);
     if (rc != B200VIS_OK) return rc;
     if (tiles.size() > ctx->tiles_cap) {
         if (ctx->d_tiles) cudaFree(ctx->d_tiles);
@@ -441,6 +442,7 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
         CU(cudaMemcpy(ctx->d_rank, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(ctx->d_row_of_rank, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
     }
+    ctx->pass_begin = pass_begin;
     ctx->rank_identity = sorted;
     ctx->n = n;
     ctx->rows.n = n;
@@ -452,6 +454,18 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     CU(cudaMemset(ctx->d_stats, 0, sizeof(DevStats)));
     CU(cudaMemset(ctx->d_slab, 0, ctx->slab_bytes));
     ctx->topology_set = true;
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_host_plan_summary(uint32_t n, const uint32_t *parent, uint32_t out[4]) {
+    if ((n && !parent) || !out) return B200VIS_ERR_INVALID_ARG;
+    std::vector<uint32_t> topo, pass_begin; std::vector<Tile> tiles;
+    const int32_t rc = build_plan(nullptr, n, parent, topo, tiles, pass_begin);
+    if (rc) return rc;
+    uint32_t max_levels = 0, ext = 0;
+    for (const Tile &t : tiles) max_levels = std::max<uint32_t>(max_levels, t.n_levels);
+    for (uint32_t w : topo) ext += (w & T_EXT_PARENT) ? 1u : 0u;
+    out[0] = (uint32_t)tiles.size(); out[1] = pass_begin.empty() ? 0u : (uint32_t)pass_begin.size() - 1; out[2] = max_levels; out[3] = ext;
     return B200VIS_OK;
 }
 

@@ -188,6 +188,9 @@ B200VIS_API int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n_rows, cons
 /* Helper for the shim: a permutation (new_row -> old_row) that is topological and
  * keeps every tree contiguous in BFS order (the layout the tile kernel likes). */
 B200VIS_API int32_t b200vis_plan_row_order(uint32_t n_rows, const uint32_t *parent_row, uint32_t *new_to_old);
+/* What b200vis_set_topology would plan for this hierarchy (no GPU needed): out = { tiles, passes (kernel launches per
+ * propagate), deepest in-tile level count, rows whose parent lives in another tile }.  Same error codes. */
+B200VIS_API int32_t b200vis_host_plan_summary(uint32_t n_rows, const uint32_t *parent_row, uint32_t out[4]);
 
 /* Transform column, dirty ranges: trs[count][10] = translation.xyz, rotation.xyzw, scale.xyz
  * (components/transform.rs:86-105).  Marks the rows Changed<Transform>. */

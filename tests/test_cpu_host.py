@@ -158,3 +158,28 @@ def test_z_slice_thresholds_reproduce_libm_view_z_to_z_slice():
             got = 0 if np.isnan(u) else int(np.sum(u >= thr[~np.isnan(thr)]))
             got = min(got, zs - 1)
             assert got == want, (factors, zs, ortho, u, got, want)
+
+
+def test_execution_plan_shapes():
+    """The planner (no GPU needed): tiles, passes and error codes for the hierarchies the configs use."""
+    sc = scenes.forest(n_trees=100, levels=8, n_lights=10)           # config #3 shape: one 255-node tree per tile
+    tiles, passes, levels, ext = bb.host_plan_summary(sc.parent)
+    assert (tiles, passes, levels, ext) == (101, 1, 8, 0)            # 100 trees + one tile of 10 flat light rows
+    sc = scenes.propagate_bench_scene()                              # config #1: 1077-node trees span tiles
+    tiles, passes, levels, ext = bb.host_plan_summary(sc.parent)
+    assert passes == 3 and ext > 0 and tiles >= sc.n // 256
+    flat = np.full(1000, bb.NO_PARENT, np.uint32)                    # config #2 shape: flat
+    assert bb.host_plan_summary(flat) == (4, 1, 1, 0)
+    chain = np.array([bb.NO_PARENT] + list(range(599)), np.uint32)   # a 600-deep chain: one pass per tile
+    tiles, passes, levels, ext = bb.host_plan_summary(chain)
+    assert tiles == 3 and passes == 3 and levels == 256 and ext == 2
+    with pytest.raises(bb.B200VisError) as e:
+        bb.host_plan_summary(np.array([1, 2, 0], np.uint32))
+    assert e.value.code == 4                                         # cycle
+    with pytest.raises(bb.B200VisError) as e:
+        bb.host_plan_summary(np.array([bb.NO_PARENT, 7], np.uint32))
+    assert e.value.code == 5                                         # parent out of range
+    with pytest.raises(bb.B200VisError) as e:
+        bb.host_plan_summary(np.array([1, bb.NO_PARENT], np.uint32))
+    assert e.value.code == 8                                         # not in topological order
+    assert bb.host_plan_summary(np.zeros(0, np.uint32)) == (0, 0, 0, 0)
