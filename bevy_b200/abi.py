@@ -145,7 +145,8 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
 def library_path():
-    return os.path.join(_HERE, "libb200vis.so")
+    # B200VIS_LIB selects another build of the same ABI (kernel tuning experiments); the default is the in-tree library
+    return os.environ.get("B200VIS_LIB") or os.path.join(_HERE, "libb200vis.so")
 
 
 def load_library():

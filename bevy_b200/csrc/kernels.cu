@@ -1229,7 +1229,16 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
     // all-gather slip in between instead of waiting for the whole persistent grid to drain
     static int tiles_per_cta = -1;
     if (tiles_per_cta < 0) { const char *e = getenv("B200VIS_TILES_PER_CTA"); tiles_per_cta = e ? atoi(e) : 2; }
-    if (tiles_per_cta > 0) { const uint32_t want = (n_tiles + tiles_per_cta - 1) / tiles_per_cta; if (want > g) g = want; }
+    if (tiles_per_cta > 0) {
+        // round the grid up to whole waves of resident CTAs: the surplus CTAs then take one tile fewer, so the last
+        // wave is made of short CTAs instead of a few full-length ones running on a mostly idle chip
+        uint32_t want = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+        static int balance = -1;
+        if (balance < 0) { const char *e = getenv("B200VIS_BALANCE_WAVES"); balance = e ? atoi(e) : 1; }
+        if (balance) want = ((want + (uint32_t)grid - 1) / (uint32_t)grid) * (uint32_t)grid;
+        if (want > n_tiles) want = n_tiles;
+        if (want > g) g = want;
+    }
     // programmatic dependent launch: this kernel's CTAs may become resident (barrier init, parameter loads) while the
     // previous kernel in the stream drains; griddepcontrol.wait in the kernel orders the actual data accesses
     cudaLaunchConfig_t cfg = {};

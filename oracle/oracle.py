@@ -26,9 +26,7 @@ VIEW_NO_CPU_CULLING = 0x02
 
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
-    targets = ["libbevy_oracle.so", "libbevy_oracle_mt.so"]
-    if force or not all(os.path.exists(os.path.join(_HERE, t)) for t in targets):
-        subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
+    subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))   # no-op when up to date
 
 
 _lib = None
@@ -127,6 +125,18 @@ def _declare(l):
     l.orc_powf.argtypes = [C.c_float, C.c_float]
     l.orc_view_z_to_z_slice.restype = C.c_uint32
     l.orc_view_z_to_z_slice.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.c_float, C.c_int]
+    if hasattr(l, "orc_update_cpu_culled_entities"):   # bevy_oracle_next.c (not part of the MT baseline library)
+        U64P, U32P, U8P = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+        l.orc_sort_pairs_by_main.argtypes = [U64P, U64P, C.c_uint32]
+        l.orc_update_cpu_culled_entities.argtypes = [U64P, U64P, C.c_uint32, U64P, U64P, C.c_uint32,
+                                                     U64P, U64P, U32P, U64P, U64P, U32P]
+        l.orc_entity_pair_is_visible.restype = C.c_int
+        l.orc_entity_pair_is_visible.argtypes = [U64P, U64P, C.c_uint32, C.c_uint64, C.c_uint64]
+        l.orc_cluster_bindings.argtypes = [C.c_uint32, U32P, U32P, U32P, C.c_int, U32P, U32P, U32P, U32P]
+        l.orc_check_visibility_ranges.argtypes = [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), U8P,
+                                                  C.POINTER(C.c_float), U8P, C.c_uint32, C.POINTER(C.c_float), U32P]
+        l.orc_visibility_propagate.restype = C.c_int
+        l.orc_visibility_propagate.argtypes = [C.c_uint32, U32P, U8P, U8P, U8P, C.c_uint32, U32P, C.c_uint32, U32P]
     for name in ("orc_half_space_new", "orc_affine_from_trs", "orc_affine_inverse", "orc_mat4_inverse"):
         getattr(l, name).argtypes = [C.POINTER(C.c_float)] * 2
     for name in ("orc_affine_mul", "orc_mat4_mul"):
@@ -337,3 +347,84 @@ def clusters_update(w, h, req):
     r = (C.c_uint32 * 3)(*req); tile = (C.c_uint32 * 2)(); dims = (C.c_uint32 * 3)()
     lib().orc_clusters_update(w, h, r, tile, dims)
     return tuple(tile), tuple(dims)
+
+
+# ---- SURVEY.md section 8(f) rows (bevy_oracle_next.c) -------------------------------------------------
+VIS_INHERITED, VIS_HIDDEN, VIS_VISIBLE, VIS_NO_COMPONENTS = 0, 1, 2, 4
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def sort_pairs_by_main(render, main):
+    """collect_visible_cpu_culled_entities_for_subview's sort (view/visibility/mod.rs:425-427)."""
+    render, main = _u64(render).copy(), _u64(main).copy()
+    lib().orc_sort_pairs_by_main(_p(render, C.c_uint64), _p(main, C.c_uint64), len(main))
+    return render, main
+
+
+def update_cpu_culled_entities(old_render, old_main, new_render, new_main):
+    """RenderVisibleEntitiesClass::update_cpu_culled_entities -> (added_render, added_main, removed_render, removed_main)."""
+    o_r, o_m, n_r, n_m = _u64(old_render), _u64(old_main), _u64(new_render), _u64(new_main)
+    a_r, a_m = np.zeros(len(n_m), np.uint64), np.zeros(len(n_m), np.uint64)
+    r_r, r_m = np.zeros(len(o_m), np.uint64), np.zeros(len(o_m), np.uint64)
+    na, nr = C.c_uint32(0), C.c_uint32(0)
+    U = C.c_uint64
+    lib().orc_update_cpu_culled_entities(_p(o_r, U), _p(o_m, U), len(o_m), _p(n_r, U), _p(n_m, U), len(n_m),
+                                         _p(a_r, U), _p(a_m, U), C.byref(na), _p(r_r, U), _p(r_m, U), C.byref(nr))
+    return a_r[:na.value], a_m[:na.value], r_r[:nr.value], r_m[:nr.value]
+
+
+def entity_pair_is_visible(render, main, entity, main_entity):
+    render, main = _u64(render), _u64(main)
+    return bool(lib().orc_entity_pair_is_visible(_p(render, C.c_uint64), _p(main, C.c_uint64), len(main),
+                                                 int(entity), int(main_entity)))
+
+
+def cluster_bindings(offsets, indices, gpu_index_of_light=None, storage=True):
+    """Clusters (CSR) -> ViewClusterBindings buffers: (offsets_and_counts, index_lists, n_offsets, n_indices)."""
+    offsets = np.ascontiguousarray(offsets, np.uint32)
+    indices = np.ascontiguousarray(indices, np.uint32)
+    n = len(offsets) - 1
+    if storage:
+        oc = np.zeros((n, 8), np.uint32)
+        il = np.zeros(max(int(offsets[-1]), 1), np.uint32)
+    else:
+        oc = np.zeros(4096, np.uint32)
+        il = np.zeros(4096, np.uint32)
+    gi = None if gpu_index_of_light is None else np.ascontiguousarray(gpu_index_of_light, np.uint32)
+    no, ni = C.c_uint32(0), C.c_uint32(0)
+    U = C.c_uint32
+    lib().orc_cluster_bindings(n, _p(offsets, U), _p(indices, U), None if gi is None else _p(gi, U), int(bool(storage)),
+                               _p(oc, U), _p(il, U), C.byref(no), C.byref(ni))
+    if storage:
+        il = il[:ni.value]
+    return oc, il, no.value, ni.value
+
+
+def check_visibility_ranges(gt, bounds, flags, range_se, use_aabb, view_pos):
+    """check_visibility_ranges -> per-row u32 view bitmask (0 = no VisibleEntityRanges entry)."""
+    gt, bounds = _f32(gt), _f32(bounds)
+    flags = np.ascontiguousarray(flags, np.uint8)
+    range_se, view_pos = _f32(range_se), _f32(view_pos).reshape(-1, 3)
+    use_aabb = np.ascontiguousarray(use_aabb, np.uint8)
+    out = np.zeros(len(flags), np.uint32)
+    lib().orc_check_visibility_ranges(len(flags), _p(gt, C.c_float), _p(bounds, C.c_float), _p(flags, C.c_uint8),
+                                      _p(range_se, C.c_float), _p(use_aabb, C.c_uint8), len(view_pos),
+                                      _p(view_pos, C.c_float), _p(out, C.c_uint32))
+    return out
+
+
+def visibility_propagate(parent, vis, inherited, changed_rows, removed_rows=()):
+    """visibility_propagate_system: returns (inherited, changed) after one run."""
+    parent = np.ascontiguousarray(parent, np.uint32)
+    vis = np.ascontiguousarray(vis, np.uint8)
+    inh = np.ascontiguousarray(inherited, np.uint8).copy()
+    ch = np.zeros(len(parent), np.uint8)
+    cr = np.ascontiguousarray(changed_rows, np.uint32)
+    rr = np.ascontiguousarray(removed_rows, np.uint32)
+    rc = lib().orc_visibility_propagate(len(parent), _p(parent, C.c_uint32), _p(vis, C.c_uint8), _p(inh, C.c_uint8),
+                                        _p(ch, C.c_uint8), len(cr), _p(cr, C.c_uint32), len(rr), _p(rr, C.c_uint32))
+    assert rc == 0
+    return inh, ch
