@@ -130,6 +130,11 @@ _SIGNATURES = {
     "b200vis_download_visible": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_download_clusters": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_set_result_sink": (C.c_int32, [_vp, _P(ResultSink)]),
+    "b200vis_set_cluster_bindings": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32]),
+    "b200vis_download_cluster_bindings": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32), _P(C.c_uint32)]),
+    "b200vis_enable_visible_diff": (C.c_int32, [_vp, C.c_int32]),
+    "b200vis_download_visible_diff": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32), _vp, C.c_uint32, _P(C.c_uint32)]),
+    "b200vis_set_visible_diff_sink": (C.c_int32, [_vp, _vp, C.c_uint32, _vp]),
     "b200vis_comm_unique_id": (C.c_int32, [_vp]),
     "b200vis_comm_init": (C.c_int32, [_vp, _vp]),
     "b200vis_cluster_exchange_bytes": (C.c_int32, [_vp, _P(C.c_size_t)]),
@@ -390,6 +395,43 @@ class Context:
         rows = np.zeros(max(cnt.value, 1), np.uint32)
         self._check(self._lib.b200vis_download_visible(self._h, view, _ptr(rows), len(rows), C.byref(cnt)))
         return rows[:cnt.value]
+
+    # ---- SURVEY 8(f) N2 ----
+    def set_cluster_bindings(self, mode, gpu_index_of_light=None):
+        """mode: 0 off, 1 storage, 2 uniform (ViewClusterBindings, bevy_pbr/src/cluster/mod.rs:584-800)."""
+        m = None if gpu_index_of_light is None else np.ascontiguousarray(gpu_index_of_light, np.uint32)
+        self._check(self._lib.b200vis_set_cluster_bindings(self._h, mode, None if m is None else _ptr(m), 0 if m is None else len(m)))
+        self._bind_mode = mode
+
+    def download_cluster_bindings(self, view):
+        """(offsets_and_counts, index_lists, n_offsets, n_indices) in the mode's wire format."""
+        no, ni = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.b200vis_download_cluster_bindings(self._h, view, None, 0, None, 0, C.byref(no), C.byref(ni)))
+        storage = self._bind_mode == 1
+        oc = np.zeros(max(no.value * 8, 1) if storage else 4096, np.uint32)
+        il = np.zeros(max(ni.value, 1) if storage else 4096, np.uint32)
+        self._check(self._lib.b200vis_download_cluster_bindings(self._h, view, _ptr(oc), len(oc), _ptr(il), len(il), C.byref(no), C.byref(ni)))
+        if storage:
+            oc, il = oc[:no.value * 8].reshape(-1, 8), il[:ni.value]
+        return oc, il, no.value, ni.value
+
+    # ---- SURVEY 8(f) N1 ----
+    def enable_visible_diff(self, enabled=True):
+        self._check(self._lib.b200vis_enable_visible_diff(self._h, int(bool(enabled))))
+
+    def download_visible_diff(self, view):
+        """(added_rows, removed_rows) of `view` against the last frame it was active, both ascending by Entity bits."""
+        na, nr = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.b200vis_download_visible_diff(self._h, view, None, 0, C.byref(na), None, 0, C.byref(nr)))
+        a, r = np.zeros(max(na.value, 1), np.uint32), np.zeros(max(nr.value, 1), np.uint32)
+        self._check(self._lib.b200vis_download_visible_diff(self._h, view, _ptr(a), len(a), C.byref(na), _ptr(r), len(r), C.byref(nr)))
+        return a[:na.value], r[:nr.value]
+
+    def set_visible_diff_sink(self, rows, counts):
+        """Pinned host numpy arrays rows [2, max_views, cap] and counts [max_views, 2]; (None, None) removes the sink."""
+        if rows is None:
+            self._check(self._lib.b200vis_set_visible_diff_sink(self._h, None, 0, None)); return
+        self._check(self._lib.b200vis_set_visible_diff_sink(self._h, _ptr(rows), rows.shape[2], _ptr(counts)))
 
     def download_clusters(self, view, capacity=1 << 20):
         offsets = np.zeros(MAX_CLUSTERS + 1, np.uint32); idx = np.zeros(capacity, np.uint32); tot = C.c_uint32(0)

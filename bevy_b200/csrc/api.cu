@@ -112,6 +112,9 @@ struct b200vis_ctx {
 
     // visible set
     VisibleBufs vis{};
+    DiffBufs diff{}; bool diff_on = false;      // SURVEY 8(f) N1 (b200vis_enable_visible_diff)
+    uint32_t *diff_sink_rows_d = nullptr, *diff_sink_counts_d = nullptr; uint32_t diff_sink_cap = 0;
+    BindingBufs bind{}; uint32_t *d_bind_map = nullptr; uint32_t bind_map_cap = 0;   // SURVEY 8(f) N2 (b200vis_set_cluster_bindings)
     DevStats *d_stats = nullptr; DevStats *h_stats = nullptr;   // h pinned
     uint32_t frame = 0, parity = 0;
 
@@ -174,7 +177,9 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
                    ctx->d_tiles, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_light_snap, ctx->d_tag_flag,
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->d_stats, ctx->d_light_row,
-                   ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage};
+                   ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage,
+                   ctx->diff.prev, ctx->diff.words, ctx->diff.chunk, ctx->diff.lists, ctx->diff.count,
+                   ctx->bind.oc, ctx->bind.il, ctx->bind.count, ctx->d_bind_map};
     for (void *p : dev) if (p) cudaFree(p);
     for (int i = 0; i < b200vis_ctx::kRing; ++i) {
         if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
@@ -453,6 +458,7 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     CU(cudaMemset(ctx->vis.chunk_count, 0, (size_t)3 * kMaxViews * ctx->vis.chunks_stride * 4));
     CU(cudaMemset(ctx->d_stats, 0, sizeof(DevStats)));
     CU(cudaMemset(ctx->d_slab, 0, ctx->slab_bytes));
+    if (ctx->diff.prev) CU(cudaMemset(ctx->diff.prev, 0, (size_t)ctx->vis.words_stride * ctx->cfg.max_views * 4));   // ranks changed: old list = empty
     ctx->topology_set = true;
     return B200VIS_OK;
 }
@@ -962,7 +968,12 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     } else if (pe) CU(cudaEventRecord(pe[1], st));
     if (pe) CU(cudaEventRecord(pe[2], tail));
     if (do_cull && ctx->pub_pending) { CU(cudaStreamWaitEvent(tail, ctx->ev_pub, 0)); ctx->pub_pending = false; }   // lists are rewritten
-    if (do_cull) launch_expand_visible(tail, vb, R.row_of_rank, fc, ctx->d_stats, cslot, ctx->n, ctx->cfg.max_views);
+    if (do_cull) {
+        launch_expand_visible(tail, vb, ctx->diff_on ? ctx->diff : DiffBufs{}, R.row_of_rank, fc, ctx->d_stats, cslot, ctx->n, ctx->cfg.max_views);
+        if (ctx->diff_on && ctx->diff_sink_rows_d)
+            launch_publish_visible_diff(tail, vb, ctx->diff, ctx->diff_sink_rows_d, ctx->diff_sink_cap, ctx->diff_sink_counts_d,
+                                        active_consts(ctx).n_views, ctx->cfg.max_views);
+    }
     if (do_cull && ctx->have_sink && ctx->sink_rows_d) {
         // posting ~1 MB of visible rows over PCIe takes tens of microseconds: in the serial (non-pipelined) case do it on the
         // side stream so it overlaps the cluster kernels; every later consumer joins the side stream
@@ -986,6 +997,8 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     }
     if (stages & B200VIS_STAGE_CLUSTER_LISTS)
         launch_cluster_lists(tail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+    if ((stages & B200VIS_STAGE_CLUSTER_LISTS) && ctx->bind.mode)
+        launch_pack_cluster_bindings(tail, fc, cl, ctx->bind, ctx->cfg.max_views);
     if (ctx->have_sink && (do_cull || (stages & B200VIS_STAGE_CLUSTER_LISTS)))
         launch_publish_clusters(tail, fc, cl, (stages & B200VIS_STAGE_CLUSTER_LISTS) ? ctx->sink_off_d : nullptr, ctx->sink_idx_d,
                                 ctx->sink.cluster_capacity, ctx->d_stats, ctx->sink_stats_d, cslot, frame + (do_cull ? 1u : 0u), ctx->cfg.max_views);
@@ -1079,6 +1092,110 @@ extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, ui
         CU(cudaMemcpyAsync(indices, ctx->cl.indices + (size_t)view * ctx->cl.index_cap, (size_t)*total * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
+    return B200VIS_OK;
+}
+
+// ---- Clusters -> ViewClusterBindings buffers ---------------------------------------------------
+extern "C" int32_t b200vis_set_cluster_bindings(b200vis_ctx *ctx, uint32_t mode, const uint32_t *gpu_index_of_light, uint32_t n_map) {
+    CHECK_CTX_JOIN();
+    if (mode > B200VIS_BINDINGS_UNIFORM) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_cluster_bindings: mode %u", mode);
+    if (gpu_index_of_light && !n_map) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_cluster_bindings: empty index map");
+    const size_t V = ctx->cfg.max_views;
+    if (mode && !ctx->bind.oc) {
+        ctx->bind.il_stride = std::max<uint32_t>(ctx->cl.index_cap, 4096u);
+        CU(dalloc(&ctx->bind.oc, V * kMaxClusters * 8));
+        CU(dalloc(&ctx->bind.il, V * (size_t)ctx->bind.il_stride));
+        CU(dalloc(&ctx->bind.count, V * 2));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (gpu_index_of_light) {
+        if (n_map > ctx->bind_map_cap) {
+            if (ctx->d_bind_map) cudaFree(ctx->d_bind_map);
+            ctx->d_bind_map = nullptr; ctx->bind_map_cap = n_map;
+            CU(dalloc(&ctx->d_bind_map, n_map));
+        }
+        CU(cudaMemcpy(ctx->d_bind_map, gpu_index_of_light, (size_t)n_map * 4, cudaMemcpyHostToDevice));
+        ctx->bind.map = ctx->d_bind_map; ctx->bind.n_map = n_map;
+    } else { ctx->bind.map = nullptr; ctx->bind.n_map = 0; }
+    ctx->bind.mode = mode;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_download_cluster_bindings(b200vis_ctx *ctx, uint32_t view, uint32_t *offsets_and_counts, uint32_t oc_capacity,
+                                                     uint32_t *index_lists, uint32_t il_capacity, uint32_t *n_offsets, uint32_t *n_indices) {
+    CHECK_CTX_JOIN();
+    if (view >= ctx->cfg.max_views || !n_offsets || !n_indices) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_cluster_bindings: bad argument");
+    if (!ctx->bind.mode) return fail(ctx, B200VIS_ERR_NOT_READY, "download_cluster_bindings: call b200vis_set_cluster_bindings first");
+    cudaStream_t st = ctx->stream;
+    uint32_t cnt[2] = {0, 0};
+    CU(cudaMemcpyAsync(cnt, ctx->bind.count + view * 2, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_offsets = cnt[0]; *n_indices = cnt[1];
+    const bool storage = ctx->bind.mode == B200VIS_BINDINGS_STORAGE;
+    const uint32_t oc_words = storage ? cnt[0] * 8u : 4096u, il_words = storage ? cnt[1] : 4096u;
+    if ((offsets_and_counts && oc_words > oc_capacity) || (index_lists && il_words > il_capacity))
+        return fail(ctx, B200VIS_ERR_CAPACITY, "download_cluster_bindings: needs %u + %u words, capacities %u + %u", oc_words, il_words, oc_capacity, il_capacity);
+    if (offsets_and_counts && oc_words)
+        CU(cudaMemcpyAsync(offsets_and_counts, ctx->bind.oc + (size_t)view * kMaxClusters * 8, (size_t)oc_words * 4, cudaMemcpyDeviceToHost, st));
+    if (index_lists && il_words)
+        CU(cudaMemcpyAsync(index_lists, ctx->bind.il + (size_t)view * ctx->bind.il_stride, (size_t)il_words * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return B200VIS_OK;
+}
+
+// ---- added / removed rows of each view's VisibleEntities against last frame -----------------
+static int32_t reset_visible_diff(b200vis_ctx *ctx) {
+    if (ctx->diff.prev)
+        CU(cudaMemsetAsync(ctx->diff.prev, 0, (size_t)ctx->vis.words_stride * ctx->cfg.max_views * 4, ctx->stream));
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_enable_visible_diff(b200vis_ctx *ctx, int32_t enabled) {
+    CHECK_CTX_JOIN();
+    if (enabled && !ctx->diff.prev) {
+        const size_t V = ctx->cfg.max_views, W = ctx->vis.words_stride;
+        CU(dalloc(&ctx->diff.prev, W * V));
+        CU(dalloc(&ctx->diff.words, 2 * W * V));
+        CU(dalloc(&ctx->diff.chunk, (size_t)ctx->vis.chunks_stride * V));
+        CU(dalloc(&ctx->diff.lists, 2 * (size_t)ctx->vis.list_stride * V));
+        CU(dalloc(&ctx->diff.count, 2 * V));
+    }
+    if (enabled && !ctx->diff_on) { const int32_t rc = reset_visible_diff(ctx); if (rc) return rc; }   // old list = empty
+    ctx->diff_on = enabled != 0;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_download_visible_diff(b200vis_ctx *ctx, uint32_t view, uint32_t *added_rows, uint32_t added_capacity,
+                                                 uint32_t *n_added, uint32_t *removed_rows, uint32_t removed_capacity,
+                                                 uint32_t *n_removed) {
+    CHECK_CTX_JOIN();
+    if (view >= ctx->cfg.max_views || !n_added || !n_removed) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_visible_diff: bad argument");
+    if (!ctx->diff_on) return fail(ctx, B200VIS_ERR_NOT_READY, "download_visible_diff: call b200vis_enable_visible_diff first");
+    cudaStream_t st = ctx->stream;
+    uint32_t cnt[2] = {0, 0};
+    CU(cudaMemcpyAsync(cnt, ctx->diff.count + view * 2, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_added = cnt[0]; *n_removed = cnt[1];
+    if ((added_rows && cnt[0] > added_capacity) || (removed_rows && cnt[1] > removed_capacity))
+        return fail(ctx, B200VIS_ERR_CAPACITY, "download_visible_diff: %u added / %u removed rows exceed the capacities %u / %u",
+                    cnt[0], cnt[1], added_capacity, removed_capacity);
+    const size_t V = ctx->cfg.max_views, LS = ctx->vis.list_stride;
+    if (added_rows && cnt[0]) CU(cudaMemcpyAsync(added_rows, ctx->diff.lists + (size_t)view * LS, (size_t)cnt[0] * 4, cudaMemcpyDeviceToHost, st));
+    if (removed_rows && cnt[1]) CU(cudaMemcpyAsync(removed_rows, ctx->diff.lists + (V + view) * LS, (size_t)cnt[1] * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return B200VIS_OK;
+}
+
+static int32_t map_host(b200vis_ctx *ctx, void *p, size_t bytes, uint32_t **dev);
+extern "C" int32_t b200vis_set_visible_diff_sink(b200vis_ctx *ctx, uint32_t *rows, uint32_t capacity, uint32_t *counts) {
+    CHECK_CTX_JOIN();
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->diff_sink_rows_d = ctx->diff_sink_counts_d = nullptr; ctx->diff_sink_cap = 0;
+    if (!rows && !counts) return B200VIS_OK;
+    if (!rows || !counts || !capacity) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_visible_diff_sink: rows, counts and a capacity go together");
+    const size_t V = ctx->cfg.max_views;
+    int32_t rc;
+    uint32_t *dr = nullptr, *dc = nullptr;
+    if ((rc = map_host(ctx, rows, 2 * V * (size_t)capacity * 4, &dr))) return rc;
+    if ((rc = map_host(ctx, counts, 2 * V * 4, &dc))) return rc;
+    ctx->diff_sink_rows_d = dr; ctx->diff_sink_counts_d = dc; ctx->diff_sink_cap = capacity;
     return B200VIS_OK;
 }
 

@@ -109,6 +109,16 @@ struct VisibleBufs {
     uint32_t list_stride;
 };
 
+// RenderVisibleEntitiesClass::update_cpu_culled_entities on the device -- the added / removed
+// lists between last frame's and this frame's sorted visible list of a view (all pointers null = disabled)
+struct DiffBufs {
+    uint32_t *prev;          // [V][words_stride] visible set of the last frame the view was active, bit = rank
+    uint32_t *words;         // [2][V][words_stride] added / removed bits of this frame
+    uint32_t *chunk;         // [V][chunks_stride] per chunk: added count | removed count << 16
+    uint32_t *lists;         // [2][V][list_stride] rows: added, removed (ascending Entity::to_bits())
+    uint32_t *count;         // [V][2]
+};
+
 struct Lights {
     uint32_t n;
     const float4 *snap;      // optional (pos.xyz, visible) snapshot taken right after the tile pass, or nullptr
@@ -128,6 +138,17 @@ struct ClusterBufs {
     const float *blob;       // frame blob base: FrameConsts, then the packed per-view tables
     uint32_t *offsets;       // [V][kMaxClusters+1]
     uint32_t *indices;       // [V][index_cap]
+};
+
+// the ViewClusterBindings wire format (bevy_pbr/src/cluster/mod.rs:584-800) packed on the device
+struct BindingBufs {
+    uint32_t mode;           // 0 off, 1 storage buffers, 2 uniform buffers
+    const uint32_t *map;     // GlobalClusterableObjectMeta::entity_to_index per light ordinal, or nullptr (identity)
+    uint32_t n_map;
+    uint32_t *oc;            // [V][kMaxClusters * 8]  storage: 2 x uvec4 per cluster; uniform: the first 4096 words
+    uint32_t *il;            // [V][il_stride]         storage: one u32 per index; uniform: the first 4096 words
+    uint32_t il_stride;
+    uint32_t *count;         // [V][2] n_offsets, n_indices
 };
 
 }  // namespace b200vis

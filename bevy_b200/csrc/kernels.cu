@@ -765,9 +765,9 @@ __global__ void k_mark_dirty_global(Rows R) {
 // consumed and the counters of the NEXT frame's parity.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kChunkWords)
-k_expand_visible(VisibleBufs vb, const uint32_t *__restrict__ row_of_rank, const FrameConsts *__restrict__ fc,
+k_expand_visible(VisibleBufs vb, DiffBufs db, const uint32_t *__restrict__ row_of_rank, const FrameConsts *__restrict__ fc,
                  DevStats *__restrict__ stats, uint32_t parity, uint32_t n_rows) {
-    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_warp[32], s_diff[32];
     __shared__ uint32_t s_base, s_total;
     const uint32_t v = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
     if (v >= fc->n_views) return;
@@ -776,13 +776,33 @@ k_expand_visible(VisibleBufs vb, const uint32_t *__restrict__ row_of_rank, const
     uint32_t *cc_next = vb.chunk_count + ((size_t)zslot * kMaxViews + v) * vb.chunks_stride;
     if (t == 0) cc_next[chunk] = 0;
     if (chunk == 0 && v == 0 && t < 2) stats->changed[zslot][t] = 0;
-    if (!(fc->views[v].flags & 1u)) return;   // inactive view: VisibleEntities untouched (mod.rs:780-782)
+    if (!(fc->views[v].flags & 1u)) {         // inactive view: VisibleEntities untouched (mod.rs:780-782)
+        if (db.prev != nullptr && t == 0) db.chunk[(size_t)v * vb.chunks_stride + chunk] = 0;   // ... so nothing added / removed
+        return;
+    }
 
     const uint32_t word = chunk * kChunkWords + t;
     uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
     uint32_t w = 0;
     if (word < vb.n_words) { w = mask[word]; if (w) mask[word] = 0; }
     const uint32_t c = __popc(w);
+    if (db.prev != nullptr) {
+        // the lock-step march of update_cpu_culled_entities (bevy_render/src/view/visibility/mod.rs:194-249) as set
+        // algebra on the rank-ordered bit sets: added = new & ~old, removed = old & ~new
+        uint32_t a = 0, r = 0;
+        if (word < vb.n_words) {
+            uint32_t *pv = db.prev + (size_t)v * vb.words_stride + word;
+            const uint32_t old = *pv;
+            a = w & ~old; r = old & ~w;
+            if (old != w) *pv = w;
+            db.words[(size_t)v * vb.words_stride + word] = a;
+            db.words[((size_t)gridDim.y + v) * vb.words_stride + word] = r;
+        }
+        uint32_t d = __popc(a) | (__popc(r) << 16);   // a chunk holds 32768 rows: both sums fit 16 bits
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+        if ((t & 31u) == 0) s_diff[t >> 5] = d;
+    }
     // block exclusive scan of c
     uint32_t incl = c;
 #pragma unroll
@@ -798,6 +818,12 @@ k_expand_visible(VisibleBufs vb, const uint32_t *__restrict__ row_of_rank, const
     }
     __syncthreads();
     if (t < 32) {
+        if (db.prev != nullptr) {
+            uint32_t d = s_diff[t];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+            if (t == 0) db.chunk[(size_t)v * vb.chunks_stride + chunk] = d;
+        }
         uint32_t x = s_warp[t];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
@@ -813,6 +839,73 @@ k_expand_visible(VisibleBufs vb, const uint32_t *__restrict__ row_of_rank, const
     }
     if (chunk == 0 && t == 0) stats->visible_count[v] = s_total;
     (void)n_rows;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 2b: ordered emit of the added / removed rows of each view from the bit sets and per-chunk
+// counts k_expand_visible left behind.  Same chunking, one packed (added | removed << 16) block scan.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kChunkWords)
+k_emit_visible_diff(VisibleBufs vb, DiffBufs db, const uint32_t *__restrict__ row_of_rank, const FrameConsts *__restrict__ fc) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base[2], s_total[2];
+    const uint32_t v = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+    if (v >= fc->n_views || !(fc->views[v].flags & 1u)) {
+        if (chunk == 0 && t < 2) db.count[v * 2 + t] = 0;
+        return;
+    }
+    const uint32_t word = chunk * kChunkWords + t;
+    uint32_t a = 0, r = 0;
+    if (word < vb.n_words) {
+        a = db.words[(size_t)v * vb.words_stride + word];
+        r = db.words[((size_t)gridDim.y + v) * vb.words_stride + word];
+    }
+    const uint32_t c = __popc(a) | (__popc(r) << 16);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((t & 31u) >= (uint32_t)o) incl += y; }
+    if ((t & 31u) == 31u) s_warp[t >> 5] = incl;
+    if (t < 32) {   // bases: the chunk counts before this one (unpacked: totals may exceed 16 bits)
+        const uint32_t *cc = db.chunk + (size_t)v * vb.chunks_stride;
+        uint32_t pa = 0, pr = 0, ta = 0, tr = 0;
+        for (uint32_t i = t; i < vb.n_chunks; i += 32) {
+            const uint32_t x = cc[i], xa = x & 0xFFFFu, xr = x >> 16;
+            ta += xa; tr += xr;
+            if (i < chunk) { pa += xa; pr += xr; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pa += __shfl_xor_sync(0xFFFFFFFFu, pa, o); pr += __shfl_xor_sync(0xFFFFFFFFu, pr, o);
+            ta += __shfl_xor_sync(0xFFFFFFFFu, ta, o); tr += __shfl_xor_sync(0xFFFFFFFFu, tr, o);
+        }
+        if (t == 0) { s_base[0] = pa; s_base[1] = pr; s_total[0] = ta; s_total[1] = tr; }
+    }
+    __syncthreads();
+    if (t < 32) {
+        uint32_t x = s_warp[t];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
+        s_warp[t] = x;
+    }
+    __syncthreads();
+    const uint32_t excl = (incl - c) + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+    uint32_t pos_a = s_base[0] + (excl & 0xFFFFu), pos_r = s_base[1] + (excl >> 16);
+    uint32_t *out_a = db.lists + (size_t)v * vb.list_stride;
+    uint32_t *out_r = db.lists + ((size_t)gridDim.y + v) * vb.list_stride;
+    while (a) { const uint32_t b = __ffs(a) - 1; a &= a - 1; const uint32_t rk = word * 32u + b; out_a[pos_a++] = row_of_rank ? row_of_rank[rk] : rk; }
+    while (r) { const uint32_t b = __ffs(r) - 1; r &= r - 1; const uint32_t rk = word * 32u + b; out_r[pos_r++] = row_of_rank ? row_of_rank[rk] : rk; }
+    if (chunk == 0 && t < 2) db.count[v * 2 + t] = s_total[t];
+}
+// added / removed rows into the result sink: host_rows[2][max_views][host_stride], host_counts[max_views][2]
+__global__ void k_publish_visible_diff(DiffBufs db, uint32_t list_stride, uint32_t *__restrict__ host_rows, uint32_t host_stride,
+                                       uint32_t *__restrict__ host_counts, uint32_t n_views, uint32_t max_views) {
+    const uint32_t v = blockIdx.y, which = blockIdx.z;
+    if (v >= n_views) return;
+    const uint32_t n = db.count[v * 2 + which], count = min(n, host_stride);
+    const uint32_t *src = db.lists + ((size_t)which * max_views + v) * list_stride;
+    uint32_t *dst = host_rows + ((size_t)which * max_views + v) * host_stride;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) dst[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) host_counts[v * 2 + which] = n;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1122,6 +1215,60 @@ __global__ void k_cluster_clear(const FrameConsts *__restrict__ fc, ClusterBufs 
 }
 
 // ------------------------------------------------------------------------------------------
+// Kernel 4b: Clusters -> ViewClusterBindings.  The reference walks a record stream
+// (ClusterHeader, Light, Light, ..., bevy_pbr/src/cluster/mod.rs:419-470) and pushes offsets-and-counts / indices
+// one by one (:494-520, :609-697); with the CSR already on the device every output word is independent.
+// ------------------------------------------------------------------------------------------
+__global__ void k_pack_cluster_bindings(const FrameConsts *__restrict__ fc, ClusterBufs cb, BindingBufs bb) {
+    constexpr uint32_t kMaxIndices = 16384u;               // ViewClusterBindings::MAX_INDICES (:587)
+    constexpr uint32_t kUniformWords = 16384u / 4u;        // MAX_UNIFORM_ITEMS uvec4 = 4096 u32 (:585-586)
+    constexpr uint32_t kCountSize = 9u;                    // CLUSTER_COUNT_SIZE (:43)
+    const uint32_t v = blockIdx.y;
+    if (v >= fc->n_views) return;
+    const DevClusterView &cv = fc->cviews[v];
+    const uint32_t nc = cv.enabled ? cv.n_clusters : 0u;
+    const uint32_t *off = cb.offsets + (size_t)v * (kMaxClusters + 1);
+    const uint32_t *idx = cb.indices + (size_t)v * cb.index_cap;
+    const uint32_t total = nc ? off[nc] : 0u, avail = min(total, cb.index_cap);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    uint32_t *oc = bb.oc + (size_t)v * kMaxClusters * 8, *il = bb.il + (size_t)v * bb.il_stride;
+    auto gpu_index = [&](uint32_t ordinal) -> uint32_t {
+        if (bb.map == nullptr) return ordinal;
+        return ordinal < bb.n_map ? bb.map[ordinal] : 0xFFFFFFFFu;   // push_dummy_index (:703-705)
+    };
+    if (bb.mode == 1u) {   // storage: (offset, point, spot, rect | probes, volumes, decals, 0) per cluster (:636-652)
+        for (uint32_t c = tid; c < nc; c += nth) {
+            reinterpret_cast<uint4 *>(oc)[c * 2] = make_uint4(off[c], off[c + 1] - off[c], 0u, 0u);
+            reinterpret_cast<uint4 *>(oc)[c * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (uint32_t i = tid; i < avail; i += nth) il[i] = gpu_index(idx[i]);
+        if (tid == 0) { bb.count[v * 2] = nc; bb.count[v * 2 + 1] = avail; }
+    } else {               // uniform: packed offset|counts words and 8-bit indices, truncated at MAX_INDICES (:505-514)
+        const uint32_t n_ind = min(avail, kMaxIndices);
+        // the record loop breaks at the first Light with n_indices >= MAX_INDICES: headers exist exactly for the
+        // clusters whose offset is <= MAX_INDICES (offsets are monotone)
+        for (uint32_t c = tid; c < kUniformWords; c += nth) {
+            uint32_t w = 0;
+            if (c < nc && off[c] <= kMaxIndices)
+                w = ((off[c] & ((1u << (32u - 2u * kCountSize)) - 1u)) << (2u * kCountSize)) |
+                    (((off[c + 1] - off[c]) & ((1u << kCountSize) - 1u)) << kCountSize);   // pack_offset_and_counts (:855-859)
+            oc[c] = w;
+        }
+        for (uint32_t w = tid; w < kUniformWords; w += nth) {
+            uint32_t word = 0;
+#pragma unroll
+            for (uint32_t s = 0; s < 4; ++s) { const uint32_t i = w * 4 + s; if (i < n_ind) word |= gpu_index(idx[i]) << (8u * s); }   // (:676-686)
+            il[w] = word;
+        }
+        if (tid == 0) {
+            uint32_t lo = 0, hi = nc;   // number of clusters with off[c] <= kMaxIndices
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= kMaxIndices) lo = mid + 1; else hi = mid; }
+            bb.count[v * 2] = lo; bb.count[v * 2 + 1] = n_ind;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // pack / unpack kernels for the C ABI's AoS <-> device SoA conversion
 // ------------------------------------------------------------------------------------------
 __global__ void k_unpack_trs(Rows R, uint32_t first, uint32_t count, const float *__restrict__ src, int mark_only) {
@@ -1277,10 +1424,16 @@ void launch_cull(cudaStream_t st, const Rows &R, const CullViews &cvw, const Vis
 void launch_mark_dirty_global(cudaStream_t st, const Rows &R) {
     if (R.n) k_mark_dirty_global<<<cdiv(R.n, 256), 256, 0, st>>>(R);
 }
-void launch_expand_visible(cudaStream_t st, const VisibleBufs &vb, const uint32_t *row_of_rank, const FrameConsts *fc,
+void launch_expand_visible(cudaStream_t st, const VisibleBufs &vb, const DiffBufs &db, const uint32_t *row_of_rank, const FrameConsts *fc,
                            DevStats *stats, uint32_t parity, uint32_t n_rows, uint32_t max_views) {
     if (vb.n_chunks == 0) return;
-    k_expand_visible<<<dim3(vb.n_chunks, max_views), kChunkWords, 0, st>>>(vb, row_of_rank, fc, stats, parity, n_rows);
+    k_expand_visible<<<dim3(vb.n_chunks, max_views), kChunkWords, 0, st>>>(vb, db, row_of_rank, fc, stats, parity, n_rows);
+    if (db.prev != nullptr) k_emit_visible_diff<<<dim3(vb.n_chunks, max_views), kChunkWords, 0, st>>>(vb, db, row_of_rank, fc);
+}
+void launch_publish_visible_diff(cudaStream_t st, const VisibleBufs &vb, const DiffBufs &db, uint32_t *host_rows, uint32_t host_stride,
+                                 uint32_t *host_counts, uint32_t n_views, uint32_t max_views) {
+    if (!n_views || db.prev == nullptr) return;
+    k_publish_visible_diff<<<dim3(32, n_views, 2), 256, 0, st>>>(db, vb.list_stride, host_rows, host_stride, host_counts, n_views, max_views);
 }
 void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
                            DevStats *stats, uint32_t max_views) {
@@ -1296,6 +1449,9 @@ void launch_publish_clusters(cudaStream_t st, const FrameConsts *fc, const Clust
                              uint32_t host_cap, const DevStats *stats, uint32_t *host_stats, uint32_t changed_slot, uint32_t frame, uint32_t max_views) {
     k_publish_clusters<<<dim3(kMaxClusters / 256 + 1, max_views), 256, 0, st>>>(fc, cb.offsets, cb.indices, cb.index_cap, host_offsets, host_indices,
                                                                                 host_cap, stats, host_stats, changed_slot, frame);
+}
+void launch_pack_cluster_bindings(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, const BindingBufs &bb, uint32_t max_views) {
+    if (bb.mode) k_pack_cluster_bindings<<<dim3(16, max_views), 256, 0, st>>>(fc, cb, bb);
 }
 void launch_tag_lights(cudaStream_t st, const Rows &R, const Lights &L, uint32_t *all_tagged) {
     if (L.n) k_tag_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, all_tagged);

@@ -9,8 +9,11 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
 bool tile_kernel_is_tma();
 void launch_cull(cudaStream_t st, const Rows &R, const CullViews &cvw, const VisibleBufs &vb, DevStats *stats, uint32_t parity);
 void launch_mark_dirty_global(cudaStream_t st, const Rows &R);
-void launch_expand_visible(cudaStream_t st, const VisibleBufs &vb, const uint32_t *row_of_rank, const FrameConsts *fc,
+void launch_expand_visible(cudaStream_t st, const VisibleBufs &vb, const DiffBufs &db, const uint32_t *row_of_rank, const FrameConsts *fc,
                            DevStats *stats, uint32_t parity, uint32_t n_rows, uint32_t max_views);
+void launch_pack_cluster_bindings(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, const BindingBufs &bb, uint32_t max_views);
+void launch_publish_visible_diff(cudaStream_t st, const VisibleBufs &vb, const DiffBufs &db, uint32_t *host_rows, uint32_t host_stride,
+                                 uint32_t *host_counts, uint32_t n_views, uint32_t max_views);
 void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
                            DevStats *stats, uint32_t max_views);
 void launch_publish_visible(cudaStream_t st, const VisibleBufs &vb, const DevStats *stats, uint32_t *host_rows, uint32_t host_stride,

@@ -86,6 +86,12 @@ class VisibilityPipeline:
         """The fused per-frame path: one launch sequence for all three systems."""
         self.ctx.run(abi.STAGE_ALL if len(self.scene.light_row) else (abi.STAGE_PROPAGATE | abi.STAGE_CULL))
 
+    def enable_visible_diff(self, enabled=True):
+        """have the CULL stage also produce each view's added / removed rows
+        (RenderVisibleEntitiesClass::update_cpu_culled_entities, bevy_render/src/view/visibility/mod.rs:194-249)."""
+        self.ctx.enable_visible_diff(enabled)
+        self.visible_diff = bool(enabled)
+
     def read_feedback(self):
         """Clusters::last_frame_* (assign.rs:810-811): feeds next frame's far_z and dynamic resizing."""
         s = self.ctx.download_frame_stats()

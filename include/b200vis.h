@@ -310,6 +310,43 @@ typedef struct b200vis_result_sink {
 } b200vis_result_sink;
 B200VIS_API int32_t b200vis_set_result_sink(b200vis_ctx *ctx, const b200vis_result_sink *sink);
 
+/* ---- the render world's visible-entity diff ---------------------------------------------
+ * RenderVisibleEntitiesClass::update_cpu_culled_entities (crates/bevy_render/src/view/visibility/mod.rs:194-249)
+ * marches over last frame's and this frame's sorted list to find the newly added and newly removed entities.  With
+ * the diff enabled the CULL stage produces both lists on the device (set algebra on the rank-ordered bit sets, ordered
+ * emit), so the shim can feed `added_entities` / `removed_entities` directly and skip the download of the full lists.
+ * Rows ascend by Entity::to_bits() like the lists themselves.  "Last frame" = the last frame the view was active; an
+ * inactive view reports nothing.  Enabling the diff and b200vis_set_topology (row identities change) reset the old
+ * list to empty: the next frame reports every visible row as added, and the shim drops its render-world list. */
+B200VIS_API int32_t b200vis_enable_visible_diff(b200vis_ctx *ctx, int32_t enabled);
+B200VIS_API int32_t b200vis_download_visible_diff(b200vis_ctx *ctx, uint32_t view, uint32_t *added_rows, uint32_t added_capacity,
+                                                  uint32_t *n_added, uint32_t *removed_rows, uint32_t removed_capacity,
+                                                  uint32_t *n_removed);
+/* Sink form (pinned host memory written by the GPU right after the CULL stage, like b200vis_set_result_sink):
+ * rows[2][max_views][capacity] (0 = added, 1 = removed), counts[max_views][2]; a list longer than `capacity` is
+ * truncated (the count still says how long it was).  A result sink whose visible_rows is NULL then keeps the full
+ * lists on the device.  NULL, 0, NULL removes the sink. */
+B200VIS_API int32_t b200vis_set_visible_diff_sink(b200vis_ctx *ctx, uint32_t *rows, uint32_t capacity, uint32_t *counts);
+
+/* ---- Clusters -> ViewClusterBindings ----------------------------------------------------------
+ * extract_clusters_for_cpu_clustering + prepare_clusters_for_cpu_clustering (crates/bevy_pbr/src/cluster/mod.rs:394-582)
+ * flatten each view's per-cluster Vec<Entity> into the two GPU buffers of ViewClusterBindings (:584-800).  With a mode
+ * set, the CLUSTER_LISTS stage emits that wire format directly from the device CSR:
+ *   STORAGE  offsets_and_counts[n_clusters][8] = (offset, point_lights, spot, rect | probes, volumes, decals, 0);
+ *            index_lists[n_indices] u32
+ *   UNIFORM  offsets_and_counts[4096] = pack_offset_and_counts (:855-859); index_lists[4096] = 16384 8-bit slots,
+ *            truncated at ViewClusterBindings::MAX_INDICES exactly like the reference's record loop (:505-514)
+ * gpu_index_of_light[n_map] = GlobalClusterableObjectMeta::entity_to_index for each light ordinal (NULL = the ordinal
+ * itself); ordinals without an entry get the dummy index !0 (:703-705). */
+#define B200VIS_BINDINGS_OFF 0u
+#define B200VIS_BINDINGS_STORAGE 1u
+#define B200VIS_BINDINGS_UNIFORM 2u
+B200VIS_API int32_t b200vis_set_cluster_bindings(b200vis_ctx *ctx, uint32_t mode, const uint32_t *gpu_index_of_light, uint32_t n_map);
+/* capacities in 32-bit words; n_offsets / n_indices = ViewClusterBindings::n_offsets / n_indices */
+B200VIS_API int32_t b200vis_download_cluster_bindings(b200vis_ctx *ctx, uint32_t view, uint32_t *offsets_and_counts, uint32_t oc_capacity,
+                                                      uint32_t *index_lists, uint32_t il_capacity, uint32_t *n_offsets,
+                                                      uint32_t *n_indices);
+
 /* ---- multi-GPU cluster exchange (one all-gather per frame, done by the host's collective) ------- */
 /* Each rank fills `slab_bytes` at `send`; after all-gathering the slabs rank-major into `recv`
  * (world_size * slab_bytes) the LISTS stage reads `recv`.  Buffers are caller-allocated device memory

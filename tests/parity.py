@@ -77,6 +77,15 @@ def compare_frame(pipe, world, frame_no, cluster=True, check_gt=True, run_device
         if want is None:                      # inactive view: VisibleEntities keep last frame's contents
             want = world.last_lists[v]
         assert len(got) == len(want) and (got == want).all(), f"{tag} view {v}: visible list differs ({len(got)} vs {len(want)})"
+        if getattr(pipe, "visible_diff", False):   # the render world's added / removed lists
+            old = world.last_lists[v]
+            bits = sc.entity_bits
+            a_r, _, r_r, _ = orc.update_cpu_culled_entities(old, bits[old], want, bits[want])
+            if lists[v] is None:
+                assert len(a_r) == 0 and len(r_r) == 0
+            g_a, g_r = pipe.ctx.download_visible_diff(v)
+            assert len(g_a) == len(a_r) and (g_a == a_r).all(), f"{tag} view {v}: added rows differ ({len(g_a)} vs {len(a_r)})"
+            assert len(g_r) == len(r_r) and (g_r == r_r).all(), f"{tag} view {v}: removed rows differ ({len(g_r)} vs {len(r_r)})"
     world.last_lists = [l if l is not None else world.last_lists[v] for v, l in enumerate(lists)]
     stats = pipe.read_feedback()
     if cluster and len(sc.light_row):
@@ -94,9 +103,11 @@ def compare_frame(pipe, world, frame_no, cluster=True, check_gt=True, run_device
     return stats
 
 
-def run_parity(scene, frames=3, static_opt=True, animate=True, cluster=True):
+def run_parity(scene, frames=3, static_opt=True, animate=True, cluster=True, visible_diff=False):
     pipe = bb.VisibilityPipeline(scene, static_transform_optimizations=static_opt)
     world = OracleWorld(scene, static_opt)
+    if visible_diff:
+        pipe.enable_visible_diff()
     try:
         for f in range(frames):
             if f > 0 and animate:

@@ -1,0 +1,124 @@
+"""SURVEY.md 8(f) rows on the device, against the oracle restatements (bevy_oracle_next.c), bit exact."""
+import numpy as np
+import pytest
+import torch
+
+import bevy_b200 as bb
+from bevy_b200 import scenes
+
+from parity import OracleWorld, compare_frame, run_parity
+from test_gpu_edge_cases import _random_scene
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- N1: render-world visible-entity diff ------------------------------------------------------------
+def test_n1_visible_diff_forest_moving_cameras():
+    run_parity(scenes.forest(n_trees=60, levels=6, n_lights=8), frames=5, visible_diff=True)
+
+
+@pytest.mark.parametrize("seed", [2, 3])
+def test_n1_visible_diff_random_scene_with_inactive_view_and_shuffled_entities(seed):
+    sc = _random_scene(seed)
+    pipe = bb.VisibilityPipeline(sc)
+    world = OracleWorld(sc, True)
+    pipe.enable_visible_diff()
+    rng = np.random.default_rng(seed)
+    try:
+        for f in range(6):
+            if f > 0:
+                scenes.advance_cameras(sc, 0.08)
+                rows = np.unique(rng.integers(0, sc.n, max(sc.n // 30, 1))).astype(np.uint32)
+                sc.trs[rows, 0:3] += rng.uniform(-1.5, 1.5, (len(rows), 3)).astype(np.float32)
+                pipe.ctx.upload_transforms_scattered(rows, sc.trs[rows])
+                world.tchanged[rows] = 1
+                sc.view_flags = [bb.VIEW_ACTIVE, 0 if f in (2, 3) else bb.VIEW_ACTIVE, bb.VIEW_ACTIVE]
+            pipe.update_views()
+            compare_frame(pipe, world, f)
+    finally:
+        pipe.close()
+
+
+def test_n1_diff_sink_and_reset_on_enable():
+    sc = scenes.forest(n_trees=40, levels=6, n_lights=4)
+    pipe = bb.VisibilityPipeline(sc)
+    V = pipe.ctx.max_views
+    cap = sc.n
+    rows = torch.zeros((2, V, cap), dtype=torch.int32).pin_memory()
+    counts = torch.zeros((V, 2), dtype=torch.int32).pin_memory()
+    try:
+        pipe.enable_visible_diff()
+        pipe.ctx.set_visible_diff_sink(rows.numpy().view(np.uint32), counts.numpy().view(np.uint32))
+        prev = [np.zeros(0, np.uint32) for _ in sc.cameras]
+        for f in range(4):
+            if f:
+                scenes.advance_cameras(sc, 0.1)
+            pipe.update_views()
+            pipe.run_frame()
+            pipe.ctx.synchronize()
+            for v in range(len(sc.cameras)):
+                cur = pipe.ctx.download_visible(v)
+                na, nr = counts[v, 0].item(), counts[v, 1].item()
+                assert np.array_equal(rows[0, v, :na].numpy().view(np.uint32), np.setdiff1d(cur, prev[v]))
+                assert np.array_equal(rows[1, v, :nr].numpy().view(np.uint32), np.setdiff1d(prev[v], cur))
+                if f == 0:
+                    assert nr == 0 and na == len(cur)
+                prev[v] = cur
+        # re-enabling resets the old list: everything visible is reported as added again
+        pipe.enable_visible_diff(False)
+        pipe.enable_visible_diff(True)
+        pipe.run_frame()
+        a, r = pipe.ctx.download_visible_diff(0)
+        assert len(r) == 0 and np.array_equal(a, pipe.ctx.download_visible(0))
+    finally:
+        pipe.ctx.set_visible_diff_sink(None, None)
+        pipe.close()
+
+
+# ---- N2: Clusters -> ViewClusterBindings wire format -----------------------------------------------------
+def _big_light_scene(n_lights, light_range):
+    sc = scenes.forest(n_trees=30, levels=5, n_lights=n_lights)
+    sc.light_range[:] = light_range
+    sc.bounds[sc.light_row, 3] = light_range
+    return sc
+
+
+@pytest.mark.parametrize("mode,n_lights,light_range,no_resize", [
+    (1, 64, 12.0, False),     # storage buffers
+    (2, 64, 6.0, False),      # uniform buffers, fits
+    (2, 200, 45.0, True),     # uniform buffers, more than MAX_INDICES index slots: the record loop breaks
+    (1, 200, 45.0, True),
+])
+def test_n2_cluster_bindings_match_the_reference_packing(mode, n_lights, light_range, no_resize):
+    import oracle as orc
+    from bevy_b200 import abi
+    sc = _big_light_scene(n_lights, light_range)
+    cfg = abi.host_default_cluster_config(*sc.screen)
+    if no_resize:
+        cfg.dynamic_resizing = 0
+        cfg.view_cluster_bindings_max_indices = 1 << 22
+    pipe = bb.VisibilityPipeline(sc, cluster_config=cfg, max_cluster_indices=1 << 20)
+    rng = np.random.default_rng(5)
+    gmap = rng.permutation(n_lights).astype(np.uint32) if mode == 1 else None   # uniform mode: 8-bit slots, ids < 256
+    try:
+        pipe.ctx.set_cluster_bindings(mode, gmap)
+        saw_overflow = False
+        for f in range(3):
+            if f:
+                scenes.advance_cameras(sc, 0.2)
+            pipe.update_views()
+            pipe.run_frame()
+            pipe.read_feedback()
+            for v in range(len(sc.cameras)):
+                offsets, idx = pipe.ctx.download_clusters(v)
+                cv = pipe.cluster_views[v]
+                nc = cv.dims[0] * cv.dims[1] * cv.dims[2]
+                w_oc, w_il, w_no, w_ni = orc.cluster_bindings(offsets[:nc + 1], idx, gmap, storage=(mode == 1))
+                g_oc, g_il, g_no, g_ni = pipe.ctx.download_cluster_bindings(v)
+                assert (g_no, g_ni) == (w_no, w_ni), f"frame {f} view {v}: n_offsets/n_indices {(g_no, g_ni)} vs {(w_no, w_ni)}"
+                assert np.array_equal(g_oc, w_oc), f"frame {f} view {v}: offsets_and_counts differ"
+                assert np.array_equal(g_il, w_il), f"frame {f} view {v}: index lists differ"
+                saw_overflow |= len(idx) > 16384
+        assert saw_overflow == no_resize
+    finally:
+        pipe.close()
