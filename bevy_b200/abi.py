@@ -130,6 +130,12 @@ _SIGNATURES = {
     "b200vis_download_visible": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_download_clusters": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_set_result_sink": (C.c_int32, [_vp, _P(ResultSink)]),
+    "b200vis_upload_visibility_ranges": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "b200vis_set_visibility_range_views": (C.c_int32, [_vp, C.c_uint32, _vp]),
+    "b200vis_download_visibility_ranges": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "b200vis_upload_visibility": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "b200vis_propagate_visibility": (C.c_int32, [_vp]),
+    "b200vis_download_inherited_visibility": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "b200vis_set_cluster_bindings": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32]),
     "b200vis_download_cluster_bindings": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32), _P(C.c_uint32)]),
     "b200vis_enable_visible_diff": (C.c_int32, [_vp, C.c_int32]),
@@ -395,6 +401,32 @@ class Context:
         rows = np.zeros(max(cnt.value, 1), np.uint32)
         self._check(self._lib.b200vis_download_visible(self._h, view, _ptr(rows), len(rows), C.byref(cnt)))
         return rows[:cnt.value]
+
+    # ---- SURVEY 8(f) N4 ----
+    def upload_visibility_ranges(self, first, start_end, use_aabb):
+        se = np.ascontiguousarray(start_end, np.float32); ua = np.ascontiguousarray(use_aabb, np.uint8)
+        self._check(self._lib.b200vis_upload_visibility_ranges(self._h, first, len(ua), _ptr(se), _ptr(ua)))
+
+    def set_visibility_range_views(self, positions):
+        p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        self._check(self._lib.b200vis_set_visibility_range_views(self._h, len(p), _ptr(p)))
+
+    def download_visibility_ranges(self, first, count):
+        out = np.zeros(count, np.uint32)
+        self._check(self._lib.b200vis_download_visibility_ranges(self._h, first, count, _ptr(out)))
+        return out
+
+    def upload_visibility(self, first, visibility):
+        v = np.ascontiguousarray(visibility, np.uint8)
+        self._check(self._lib.b200vis_upload_visibility(self._h, first, len(v), _ptr(v)))
+
+    def propagate_visibility(self):
+        self._check(self._lib.b200vis_propagate_visibility(self._h))
+
+    def download_inherited_visibility(self, first, count):
+        inh, ch = np.zeros(count, np.uint8), np.zeros(count, np.uint8)
+        self._check(self._lib.b200vis_download_inherited_visibility(self._h, first, count, _ptr(inh), _ptr(ch)))
+        return inh, ch
 
     # ---- SURVEY 8(f) N2 ----
     def set_cluster_bindings(self, mode, gpu_index_of_light=None):

@@ -115,6 +115,9 @@ struct b200vis_ctx {
     DiffBufs diff{}; bool diff_on = false;      // SURVEY 8(f) N1 (b200vis_enable_visible_diff)
     uint32_t *diff_sink_rows_d = nullptr, *diff_sink_counts_d = nullptr; uint32_t diff_sink_cap = 0;
     BindingBufs bind{}; uint32_t *d_bind_map = nullptr; uint32_t bind_map_cap = 0;   // SURVEY 8(f) N2 (b200vis_set_cluster_bindings)
+    // VisibilityRange columns + range views; Visibility column + the rows the last propagate wrote
+    float2 *d_range_se = nullptr; uint8_t *d_range_ua = nullptr; float4 *d_range_views = nullptr; uint32_t n_range_views = 0;
+    uint8_t *d_visibility = nullptr, *d_iv_changed = nullptr; bool iv_ran = false;
     DevStats *d_stats = nullptr; DevStats *h_stats = nullptr;   // h pinned
     uint32_t frame = 0, parity = 0;
 
@@ -179,7 +182,8 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage,
                    ctx->diff.prev, ctx->diff.words, ctx->diff.chunk, ctx->diff.lists, ctx->diff.count,
-                   ctx->bind.oc, ctx->bind.il, ctx->bind.count, ctx->d_bind_map};
+                   ctx->bind.oc, ctx->bind.il, ctx->bind.count, ctx->d_bind_map,
+                   ctx->d_range_se, ctx->d_range_ua, ctx->d_range_views, ctx->d_visibility, ctx->d_iv_changed};
     for (void *p : dev) if (p) cudaFree(p);
     for (int i = 0; i < b200vis_ctx::kRing; ++i) {
         if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
@@ -916,6 +920,8 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     Rows R = ctx->rows;
     R.layers = ctx->have_layers ? ctx->d_layers : nullptr;
     R.range = ctx->have_range ? ctx->d_range : nullptr;
+    R.range_se = ctx->d_range_se; R.range_use_aabb = ctx->d_range_ua;
+    R.range_views = ctx->d_range_views; R.n_range_views = ctx->n_range_views;
     R.rank = ctx->rank_identity ? nullptr : ctx->d_rank;
     R.row_of_rank = ctx->rank_identity ? nullptr : ctx->d_row_of_rank;
     VisibleBufs vb = ctx->vis;
@@ -1092,6 +1098,83 @@ extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, ui
         CU(cudaMemcpyAsync(indices, ctx->cl.indices + (size_t)view * ctx->cl.index_cap, (size_t)*total * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
+    return B200VIS_OK;
+}
+
+// ---- check_visibility_ranges and visibility_propagate_system --------------------------------------
+extern "C" int32_t b200vis_upload_visibility_ranges(b200vis_ctx *ctx, uint32_t first, uint32_t count, const float *start_end,
+                                                    const uint8_t *use_aabb) {
+    CHECK_CTX();
+    if (count && (!start_end || !use_aabb)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_visibility_ranges: null");
+    int32_t rc = check_range(ctx, first, count, "upload_visibility_ranges"); if (rc) return rc;
+    if (!ctx->d_range_se) {
+        CU(dalloc(&ctx->d_range_se, ctx->cfg.max_entities));
+        CU(dalloc(&ctx->d_range_ua, ctx->cfg.max_entities));
+        CU(dalloc(&ctx->d_range_views, 32));
+    }
+    const size_t ou = (size_t)count * 8;
+    rc = stage_in(ctx, start_end, (size_t)count * 8, 0); if (rc) return rc;
+    rc = stage_in(ctx, use_aabb, count, ou); if (rc) return rc;
+    launch_unpack_range_params(ctx->stream, ctx->d_range_se, ctx->d_range_ua, first, count,
+                               reinterpret_cast<const float *>(ctx->d_stage), ctx->d_stage + ou);
+    CU(cudaGetLastError());
+    ctx->have_range = true;   // the cull kernels now take the non-SIMPLE path and fill d_range themselves
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_set_visibility_range_views(b200vis_ctx *ctx, uint32_t n_views, const float *positions) {
+    CHECK_CTX();
+    if (n_views && !positions) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_visibility_range_views: null");
+    if (!ctx->d_range_views) return fail(ctx, B200VIS_ERR_NOT_READY, "set_visibility_range_views: upload the VisibilityRange columns first");
+    if (n_views > 32) n_views = 32;   // view_query.iter().take(32) (range.rs:247)
+    float4 h[32];
+    for (uint32_t v = 0; v < n_views; ++v) h[v] = make_float4(positions[v * 3], positions[v * 3 + 1], positions[v * 3 + 2], 0.0f);
+    // pageable source: the copy is staged before the call returns, and is ordered before the next frame on the stream
+    if (n_views) CU(cudaMemcpyAsync(ctx->d_range_views, h, n_views * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_range_views = n_views;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_download_visibility_ranges(b200vis_ctx *ctx, uint32_t first, uint32_t count, uint32_t *mask) {
+    CHECK_CTX_JOIN();
+    if (count && !mask) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_visibility_ranges: null");
+    int32_t rc = check_range(ctx, first, count, "download_visibility_ranges"); if (rc) return rc;
+    if (!ctx->have_range) return fail(ctx, B200VIS_ERR_NOT_READY, "download_visibility_ranges: no VisibilityRange data was uploaded");
+    Rows R = ctx->rows; R.range = ctx->d_range;
+    launch_pack_ranges(ctx->stream, R, first, count, reinterpret_cast<uint32_t *>(ctx->d_stage));
+    CU(cudaMemcpyAsync(mask, ctx->d_stage, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_upload_visibility(b200vis_ctx *ctx, uint32_t first, uint32_t count, const uint8_t *visibility) {
+    CHECK_CTX();
+    if (count && !visibility) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_visibility: null");
+    int32_t rc = check_range(ctx, first, count, "upload_visibility"); if (rc) return rc;
+    if (!ctx->d_visibility) {   // rows never uploaded: Visibility::Inherited (the component default)
+        CU(dalloc(&ctx->d_visibility, ctx->cfg.max_entities));
+        CU(dalloc(&ctx->d_iv_changed, ctx->cfg.max_entities));
+    }
+    CU(cudaMemcpyAsync(ctx->d_visibility + first, visibility, count, cudaMemcpyHostToDevice, ctx->stream));
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_propagate_visibility(b200vis_ctx *ctx) {
+    CHECK_CTX_JOIN();   // the tail of an earlier frame may still read the flags column
+    if (!ctx->topology_set) return fail(ctx, B200VIS_ERR_NOT_READY, "propagate_visibility: set_topology first");
+    if (!ctx->d_visibility) return fail(ctx, B200VIS_ERR_NOT_READY, "propagate_visibility: upload the Visibility column first");
+    const uint32_t n_pass = ctx->pass_begin.empty() ? 0 : (uint32_t)ctx->pass_begin.size() - 1;
+    for (uint32_t p = 0; p < n_pass; ++p)
+        launch_visibility_propagate(ctx->stream, ctx->rows, ctx->d_tiles + ctx->pass_begin[p], ctx->pass_begin[p + 1] - ctx->pass_begin[p],
+                                    ctx->d_visibility, ctx->d_iv_changed);
+    CU(cudaGetLastError());
+    ctx->iv_ran = true;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_download_inherited_visibility(b200vis_ctx *ctx, uint32_t first, uint32_t count, uint8_t *inherited, uint8_t *changed) {
+    CHECK_CTX_JOIN();
+    int32_t rc = check_range(ctx, first, count, "download_inherited_visibility"); if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    launch_pack_inherited(st, ctx->rows, first, count, ctx->iv_ran ? ctx->d_iv_changed : nullptr, ctx->d_stage);
+    if (inherited) CU(cudaMemcpyAsync(inherited, ctx->d_stage, count, cudaMemcpyDeviceToHost, st));
+    if (changed) CU(cudaMemcpyAsync(changed, ctx->d_stage + count, count, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return B200VIS_OK;
 }
 

@@ -43,7 +43,12 @@ struct Rows {
     uint32_t *topo;          // T_* | local parent | local depth
     const uint32_t *parent;  // global parent row (read only for T_EXT_PARENT rows)
     const uint64_t *layers;  // RenderLayers first block, or nullptr
-    const uint32_t *range;   // VisibleEntityRanges bitmask, or nullptr
+    uint32_t *range;         // VisibleEntityRanges bitmask, or nullptr
+    // VisibilityRange columns; when resident the cull phase computes `range` itself
+    const float2 *range_se;      // (start_margin.start, end_margin.end), or nullptr
+    const uint8_t *range_use_aabb;
+    const float4 *range_views;   // translations of the (<= 32) views check_visibility_ranges indexes
+    uint32_t n_range_views;
     const uint32_t *rank;    // position in Entity::to_bits() order, or nullptr when rank == row
     const uint32_t *row_of_rank;
     uint8_t *dirty;          // global TransformTreeChanged bytes (multi-pass plans only), or nullptr

@@ -83,6 +83,26 @@ struct TileSmem {
     uint8_t dirty[kTileRows];    // TransformTreeChanged this frame (mark_dirty_trees)
 };
 
+// VisibleEntityRanges bits of one row: the uploaded column, or -- when the VisibilityRange columns are resident
+//  -- check_visibility_ranges itself (crates/bevy_camera/src/visibility/range.rs:230-284) on this
+// frame's GlobalTransform, stored so that the shim can rebuild the resource from it.
+__device__ __forceinline__ uint32_t range_mask_of(const Rows &R, uint32_t row, bool has_aabb, float cx, float cy, float cz, const Aff &g) {
+    if (R.range_se == nullptr) return R.range[row];
+    const float2 se = R.range_se[row];
+    // (use_aabb, Some(aabb)) => transform_point3a(aabb.center) -- the cull phase's centre; otherwise the translation
+    const bool centre = has_aabb && R.range_use_aabb[row];
+    const float mx = centre ? cx : g.r0.w, my = centre ? cy : g.r1.w, mz = centre ? cz : g.r2.w;
+    uint32_t m = 0;
+    for (uint32_t v = 0; v < R.n_range_views; ++v) {
+        const float4 p = R.range_views[v];
+        const float dx = p.x - mx, dy = p.y - my, dz = p.z - mz;
+        const float d = sqrtf((dx * dx + dy * dy) + dz * dz);            // Vec3A::length
+        if (d >= se.x && d < se.y) m |= 1u << v;                         // is_visible_at_all (range.rs:157-159)
+    }
+    R.range[row] = m;
+    return m;
+}
+
 template <bool PROP, bool CULL, bool SIMPLE>
 __global__ void __launch_bounds__(kTileRows, 4)
 k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const __grid_constant__ CullViews cvw, VisibleBufs vb,
@@ -215,7 +235,7 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const __grid_constant__
         unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
         if (!SIMPLE && active) {
             if (R.layers != nullptr) elayers = R.layers[row];
-            if ((f & F_RANGE) && R.range != nullptr) erange = R.range[row];
+            if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
             if (R.rank != nullptr) rnk = R.rank[row];
         }
         bool any = false;
@@ -516,7 +536,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
             unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
             if (!SIMPLE && active) {
                 if (R.layers != nullptr) elayers = R.layers[row];
-                if ((f & F_RANGE) && R.range != nullptr) erange = R.range[row];
+                if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
                 if (R.rank != nullptr) rnk = R.rank[row];
             }
             bool any = false;
@@ -663,7 +683,7 @@ k_cull(Rows R, const __grid_constant__ CullViews cvw, VisibleBufs vb, DevStats *
     unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
     if (!SIMPLE && active) {
         if (R.layers != nullptr) elayers = R.layers[row];
-        if ((f & F_RANGE) && R.range != nullptr) erange = R.range[row];
+        if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
         if (R.rank != nullptr) rnk = R.rank[row];
     }
     bool any = false;
@@ -1335,6 +1355,65 @@ __global__ void k_unpack_vv(Rows R, uint32_t first, uint32_t count, const uint8_
     const uint32_t row = first + i;
     R.state[row] = (uint8_t)((R.state[row] & ~S_VV) | (vv[i] & S_VV));
 }
+// ------------------------------------------------------------------------------------------
+// visibility_propagate_system (crates/bevy_camera/src/visibility/mod.rs:638-729) as a level walk
+// over the transform plan's tiles.  The reference is change-driven; this computes the state it converges to:
+// Visible -> true, Hidden -> false, Inherited -> the parent's InheritedVisibility, or true when there is no parent or
+// the parent lacks the components (:655-659).  Writes only where the value differs (:667) and flags those rows.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t V_HIDDEN = 1u, V_VISIBLE = 2u, V_NO_COMPONENTS = 4u;
+__global__ void __launch_bounds__(kTileRows)
+k_visibility_propagate(Rows R, const Tile *__restrict__ tiles, const uint8_t *__restrict__ vis, uint8_t *__restrict__ changed) {
+    __shared__ uint8_t s_inh[kTileRows];   // 0 / 1, or 2 = the row lacks the components
+    const Tile tile = tiles[blockIdx.x];
+    const uint32_t lr = threadIdx.x, row = tile.base + lr;
+    const bool active = lr < tile.n_rows;
+    const uint32_t topo = active ? R.topo[row] : 0u, f = active ? R.flags[row] : 0u, v = active ? vis[row] : V_NO_COMPONENTS;
+    const uint32_t my_level = active ? ((topo >> 9) & 0x1FFu) : 0xFFFFFFFFu;
+    uint32_t inh = 0;
+    for (uint32_t lvl = 0; lvl < tile.n_levels; ++lvl) {
+        if (lvl) __syncthreads();
+        if (my_level == lvl) {
+            uint32_t parent_inh = 1u;   // no parent (root) or a parent outside the hierarchy the library knows
+            if (topo & T_EXT_PARENT) {
+                const uint32_t pr = R.parent[row];
+                if (!(vis[pr] & V_NO_COMPONENTS)) parent_inh = R.flags[pr] & F_INHERITED;   // settled by an earlier pass
+            } else if (!(topo & (T_ROOT | T_DETACHED))) {
+                const uint32_t p = s_inh[topo & 0x1FFu];
+                parent_inh = p == 2u ? 1u : p;
+            }
+            inh = (v & 3u) == V_VISIBLE ? 1u : (v & 3u) == V_HIDDEN ? 0u : parent_inh;
+            s_inh[lr] = (v & V_NO_COMPONENTS) ? 2u : (uint8_t)inh;
+        }
+    }
+    if (active) {
+        const bool write = !(v & V_NO_COMPONENTS) && (f & F_INHERITED) != inh;
+        if (write) R.flags[row] = (uint8_t)(f ^ F_INHERITED);
+        changed[row] = write ? 1 : 0;
+    }
+}
+// out[0..count) = InheritedVisibility, out[count..2count) = written by the last k_visibility_propagate
+__global__ void k_pack_inherited(Rows R, uint32_t first, uint32_t count, const uint8_t *__restrict__ changed, uint8_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    out[i] = (uint8_t)(R.flags[first + i] & F_INHERITED);
+    out[count + i] = changed ? changed[first + i] : 0;
+}
+// VisibleEntityRanges::entities values: 0 (= no entry) unless the row is in check_visibility_ranges' query
+__global__ void k_pack_ranges(Rows R, uint32_t first, uint32_t count, uint32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t f = R.flags[first + i];
+    out[i] = ((f & F_RANGE) && !(f & F_NO_CPU_CULL)) ? R.range[first + i] : 0u;
+}
+__global__ void k_unpack_range_params(float2 *__restrict__ se, uint8_t *__restrict__ ua, uint32_t first, uint32_t count,
+                                      const float *__restrict__ src_se, const uint8_t *__restrict__ src_ua) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    se[first + i] = make_float2(src_se[i * 2], src_se[i * 2 + 1]);
+    ua[first + i] = src_ua[i];
+}
+
 // out[0..count) = vv byte, out[count..2count) = changed byte selected by `changed_bit`
 __global__ void k_pack_state(Rows R, uint32_t first, uint32_t count, uint8_t *__restrict__ out, uint32_t changed_bit) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1488,6 +1567,18 @@ void launch_unpack_bounds(cudaStream_t st, const Rows &R, uint32_t first, uint32
 }
 void launch_unpack_vv(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const uint8_t *vv) {
     if (count) k_unpack_vv<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, vv);
+}
+void launch_visibility_propagate(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const uint8_t *vis, uint8_t *changed) {
+    if (n_tiles) k_visibility_propagate<<<n_tiles, kTileRows, 0, st>>>(R, tiles, vis, changed);
+}
+void launch_pack_inherited(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const uint8_t *changed, uint8_t *out) {
+    if (count) k_pack_inherited<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, changed, out);
+}
+void launch_pack_ranges(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, uint32_t *out) {
+    if (count) k_pack_ranges<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, out);
+}
+void launch_unpack_range_params(cudaStream_t st, float2 *se, uint8_t *ua, uint32_t first, uint32_t count, const float *src_se, const uint8_t *src_ua) {
+    if (count) k_unpack_range_params<<<cdiv(count, 256), 256, 0, st>>>(se, ua, first, count, src_se, src_ua);
 }
 void launch_pack_state(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, uint8_t *out, uint32_t changed_bit) {
     if (count) k_pack_state<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, out, changed_bit);

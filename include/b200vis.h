@@ -328,6 +328,33 @@ B200VIS_API int32_t b200vis_download_visible_diff(b200vis_ctx *ctx, uint32_t vie
  * lists on the device.  NULL, 0, NULL removes the sink. */
 B200VIS_API int32_t b200vis_set_visible_diff_sink(b200vis_ctx *ctx, uint32_t *rows, uint32_t capacity, uint32_t *counts);
 
+/* ---- the two per-entity passes that feed the cull kernel's flag byte ---------------------------
+ * (a) check_visibility_ranges (crates/bevy_camera/src/visibility/range.rs:230-284).  With the VisibilityRange columns
+ *     resident -- start_end[count][2] = (start_margin.start, end_margin.end), the two values is_visible_at_all reads
+ *     (range.rs:157-159), and use_aabb[count] -- the cull phase evaluates the distance test itself on this frame's
+ *     GlobalTransform instead of taking an uploaded range_mask, and keeps the masks for download
+ *     (VisibleEntityRanges::entities; 0 = no entry).  Range views: the translations of the views the system indexes, in
+ *     its view-query order (only the first 32 count, :247); b200vis_view.range_view_index maps a culled view to its bit. */
+B200VIS_API int32_t b200vis_upload_visibility_ranges(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const float *start_end,
+                                                     const uint8_t *use_aabb);
+B200VIS_API int32_t b200vis_set_visibility_range_views(b200vis_ctx *ctx, uint32_t n_views, const float *positions /* [n][3] */);
+B200VIS_API int32_t b200vis_download_visibility_ranges(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, uint32_t *mask);
+/* (b) visibility_propagate_system (crates/bevy_camera/src/visibility/mod.rs:638-729).  visibility[count]: 0 Inherited,
+ *     1 Hidden, 2 Visible (the enum's order, :83-96), | 4 when the entity lacks Visibility / InheritedVisibility.
+ *     b200vis_propagate_visibility walks the same level-ordered tiles as the transform propagation and leaves every
+ *     InheritedVisibility (bit 0 of the flags column the cull phase reads) at the value the reference's change-driven
+ *     system converges to; a parent that is a root's absence, lacks the components, or is B200VIS_DETACHED counts as
+ *     visible (:655-659).  changed[i] = 1 where the value was rewritten (set-if-different, :667), i.e. where the shim
+ *     stamps InheritedVisibility's change tick. */
+#define B200VIS_VISIBILITY_INHERITED 0u
+#define B200VIS_VISIBILITY_HIDDEN 1u
+#define B200VIS_VISIBILITY_VISIBLE 2u
+#define B200VIS_VISIBILITY_NO_COMPONENTS 4u
+B200VIS_API int32_t b200vis_upload_visibility(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const uint8_t *visibility);
+B200VIS_API int32_t b200vis_propagate_visibility(b200vis_ctx *ctx);
+B200VIS_API int32_t b200vis_download_inherited_visibility(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, uint8_t *inherited,
+                                                          uint8_t *changed);
+
 /* ---- Clusters -> ViewClusterBindings ----------------------------------------------------------
  * extract_clusters_for_cpu_clustering + prepare_clusters_for_cpu_clustering (crates/bevy_pbr/src/cluster/mod.rs:394-582)
  * flatten each view's per-cluster Vec<Entity> into the two GPU buffers of ViewClusterBindings (:584-800).  With a mode

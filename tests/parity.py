@@ -30,6 +30,8 @@ class OracleWorld:
         rc, gt_changed = orc.propagate(sc.parent, sc.trs, self.gt, self.tchanged, self.static_opt, mt=mt)
         assert rc == 0
         self.tchanged[:] = 0
+        if getattr(sc, "range_se", None) is not None:   # check_visibility_ranges runs before the cull
+            sc.range_mask = orc.check_visibility_ranges(self.gt, sc.bounds, sc.flags, sc.range_se, sc.range_use_aabb, sc.range_view_pos)
         vv_changed, lists = orc.cull(self.gt, sc.bounds, sc.flags, sc.class_mask, sc.entity_bits, self.vv,
                                      views_planes, view_layers=sc.view_layers,
                                      view_flags=view_flags if view_flags is not None else sc.view_flags,
@@ -87,6 +89,9 @@ def compare_frame(pipe, world, frame_no, cluster=True, check_gt=True, run_device
             assert len(g_a) == len(a_r) and (g_a == a_r).all(), f"{tag} view {v}: added rows differ ({len(g_a)} vs {len(a_r)})"
             assert len(g_r) == len(r_r) and (g_r == r_r).all(), f"{tag} view {v}: removed rows differ ({len(g_r)} vs {len(r_r)})"
     world.last_lists = [l if l is not None else world.last_lists[v] for v, l in enumerate(lists)]
+    if getattr(sc, "range_se", None) is not None:
+        got = pipe.ctx.download_visibility_ranges(0, n)
+        assert (got == sc.range_mask).all(), f"{tag} VisibleEntityRanges masks differ on rows {np.nonzero(got != sc.range_mask)[0][:8]}"
     stats = pipe.read_feedback()
     if cluster and len(sc.light_row):
         for v in range(len(sc.cameras)):

@@ -122,3 +122,82 @@ def test_n2_cluster_bindings_match_the_reference_packing(mode, n_lights, light_r
         assert saw_overflow == no_resize
     finally:
         pipe.close()
+
+
+# ---- N4a: check_visibility_ranges inside the cull phase -----------------------------------------------------
+@pytest.mark.parametrize("seed", [4, 5])
+def test_n4_visibility_ranges_computed_on_device(seed):
+    sc = _random_scene(seed)
+    rng = np.random.default_rng(seed)
+    n = sc.n
+    # every row gets VisibilityRange parameters; only rows flagged F_HAS_VIS_RANGE are in the query
+    start = rng.uniform(0, 60, n).astype(np.float32)
+    sc.range_se = np.stack([start, start + rng.uniform(0, 120, n).astype(np.float32)], 1)
+    sc.range_use_aabb = rng.integers(0, 2, n).astype(np.uint8)
+    sc.flags = sc.flags | (rng.random(n) < 0.5).astype(np.uint8) * bb.F_HAS_VIS_RANGE
+    extra = rng.uniform(-60, 60, (33, 3)).astype(np.float32)     # 36 range views: only the first 32 count
+
+    def view_positions():
+        return np.concatenate([np.stack([np.asarray(c.gt, np.float32)[9:12] for c in sc.cameras]), extra])
+
+    sc.view_range_index = np.arange(len(sc.cameras), dtype=np.int8)
+    sc.range_view_pos = view_positions()
+    sc.range_mask = np.zeros(n, np.uint32)
+    pipe = bb.VisibilityPipeline(sc)
+    world = OracleWorld(sc, True)
+    try:
+        pipe.ctx.upload_visibility_ranges(0, sc.range_se, sc.range_use_aabb)
+        for f in range(4):
+            if f:
+                scenes.advance_cameras(sc, 0.1)
+                for c in sc.cameras:                       # move the cameras too: distances change
+                    c.gt = np.asarray(c.gt, np.float32).copy(); c.gt[9:12] += rng.uniform(-8, 8, 3).astype(np.float32)
+                rows = np.unique(rng.integers(0, n, n // 20)).astype(np.uint32)
+                sc.trs[rows, 0:3] += rng.uniform(-3, 3, (len(rows), 3)).astype(np.float32)
+                pipe.ctx.upload_transforms_scattered(rows, sc.trs[rows])
+                world.tchanged[rows] = 1
+            sc.range_view_pos = view_positions()
+            pipe.ctx.set_visibility_range_views(sc.range_view_pos)
+            pipe.update_views()
+            compare_frame(pipe, world, f)
+        assert sc.range_mask.any() and (sc.range_mask[(sc.flags & bb.F_HAS_VIS_RANGE) != 0] == 0).any()
+    finally:
+        pipe.close()
+
+
+# ---- N4b: visibility_propagate_system ------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [6, 7])
+def test_n4_visibility_propagation_matches_the_change_driven_system(seed):
+    import oracle as orc
+    sc = _random_scene(seed, n_roots=80, max_depth=12)
+    rng = np.random.default_rng(seed)
+    n = sc.n
+    parent = sc.parent.copy()
+    parent[parent == bb.DETACHED] = scenes.NO_PARENT          # a parent the hierarchy does not know: falls back to true
+    vis = rng.choice([orc.VIS_INHERITED] * 3 + [orc.VIS_HIDDEN, orc.VIS_VISIBLE], n).astype(np.uint8)
+    vis[rng.random(n) < 0.03] |= orc.VIS_NO_COMPONENTS
+    pipe = bb.VisibilityPipeline(sc)
+    world = OracleWorld(sc, True)
+    try:
+        inh = (sc.flags & 1).astype(np.uint8)
+        edited = np.arange(n, dtype=np.uint32)               # first run: every Visibility is Added
+        for step in range(6):
+            if step:
+                edited = np.unique(rng.integers(0, n, 25)).astype(np.uint32)
+                vis[edited] = (vis[edited] & 4) | rng.choice([0, 1, 2], len(edited)).astype(np.uint8)
+            pipe.ctx.upload_visibility(0, vis)
+            pipe.ctx.propagate_visibility()
+            want, want_ch = orc.visibility_propagate(parent, vis, inh, edited)
+            got, got_ch = pipe.ctx.download_inherited_visibility(0, n)
+            assert (got == want).all(), f"step {step}: InheritedVisibility differs on rows {np.nonzero(got != want)[0][:8]}"
+            assert (got_ch == want_ch).all(), f"step {step}: change flags differ on rows {np.nonzero(got_ch != want_ch)[0][:8]}"
+            assert step == 0 or want_ch.any()
+            inh = want
+            # the cull phase sees the new column
+            sc.flags = ((sc.flags & ~np.uint8(1)) | inh).astype(np.uint8)
+            if step:
+                scenes.advance_cameras(sc, 0.05)
+            pipe.update_views()
+            compare_frame(pipe, world, step)
+    finally:
+        pipe.close()
