@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--lights", type=int, default=N_LIGHTS)
     ap.add_argument("--cpu-frames", type=int, default=12, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the SURVEY 8(f) row measurements (N1, N2, N4)")
     return ap.parse_args()
 
 
@@ -171,6 +172,99 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 def emit(line):
     os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+def measure_next_rows(torch, bb, pipe, ctx, scene, stream, value_step, live_step, e2e_step_single, stats_t, coff_h, cidx_h,
+                      tile_ms, expand_ms, cluster_ms, e2e_ms, WIN, W):
+    """Cost of the SURVEY.md 8(f) rows on the bench workload (1 GPU): stage times with the row switched on against the
+    base numbers measured above (same CUDA-event stage timers), plus the e2e frame when the shim takes the added /
+    removed lists (N1) instead of the full visible lists."""
+    n, V, F = scene.n, len(scene.cameras), 100
+    out = {}
+
+    def staged(frames=F, step=None):
+        step = step or value_step
+        ctx.set_profiling(True)
+        for i in range(frames):
+            step(i)
+        t, e, c, nf = ctx.collect_stage_times_ms()
+        ctx.set_profiling(False)
+        return t / nf, e / nf, c / nf
+
+    # N1: device-side added / removed lists
+    ctx.enable_visible_diff(True)
+    for i in range(W):
+        value_step(i)
+    _, e_ms, _ = staged()
+    diff_counts = [tuple(len(x) for x in ctx.download_visible_diff(v)) for v in range(V)]
+    ctx.use_recorded_frame_constants(None)
+    cap = 1 << 16
+    rows_h = torch.zeros((2, V, cap), dtype=torch.int32).pin_memory()
+    counts_h = torch.zeros((V, 2), dtype=torch.int32).pin_memory()
+    ctx.set_visible_diff_sink(rows_h.numpy().view(np.uint32), counts_h.numpy().view(np.uint32))
+    ctx.set_result_sink(stats_t.data_ptr(), None, coff_h, cidx_h)      # full visible lists stay on the device
+    for f in range(W):
+        e2e_step_single(f % WIN)
+    torch.cuda.synchronize()
+    KD = 300
+    t0 = time.perf_counter()
+    for f in range(W, W + KD):
+        e2e_step_single(f % WIN)
+    torch.cuda.synchronize()
+    e2e_diff_ms = (time.perf_counter() - t0) * 1e3 / KD
+    d2h = int(np.mean([4 * (counts_h[v, 0].item() + counts_h[v, 1].item()) for v in range(V)]) * V)
+    ctx.set_result_sink(None, None, None, None)
+    ctx.set_visible_diff_sink(None, None)
+    ctx.enable_visible_diff(False)
+    out["N1_visible_diff"] = {"expand_plus_diff_ms": e_ms, "expand_only_ms": expand_ms,
+                              "added_removed_last_frame": diff_counts,
+                              "e2e_ms_per_step_with_diff_sink": e2e_diff_ms, "e2e_ms_per_step_full_lists": e2e_ms,
+                              "e2e_entities_per_s_with_diff_sink": n / (e2e_diff_ms * 1e-3),
+                              "visible_d2h_bytes_per_step_with_diff_sink": d2h}
+
+    # N2: ViewClusterBindings wire format straight from the cluster CSR
+    for mode, name in ((1, "storage"), (2, "uniform")):
+        ctx.set_cluster_bindings(mode)
+        _, _, c_ms = staged()
+        oc, il, no, ni = ctx.download_cluster_bindings(0)
+        out[f"N2_cluster_bindings_{name}"] = {"cluster_ms": c_ms, "cluster_only_ms": cluster_ms, "n_offsets_view0": no, "n_indices_view0": ni}
+    ctx.set_cluster_bindings(0)
+
+    # N4b: visibility_propagate_system over all rows (CUDA events on the launching stream)
+    rng = np.random.default_rng(7)
+    vis = rng.choice([0, 0, 0, 1, 2], n).astype(np.uint8)
+    ctx.upload_visibility(0, vis)
+    ctx.propagate_visibility()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    reps = 50
+    ev[0].record(stream)
+    for _ in range(reps):
+        ctx.propagate_visibility()
+    ev[1].record(stream)
+    torch.cuda.synchronize()
+    vp_ms = ev[0].elapsed_time(ev[1]) / reps
+    inh, _ = ctx.download_inherited_visibility(0, n)
+    out["N4_visibility_propagate"] = {"ms": vp_ms, "algorithmic_bytes_per_entity": 7,
+                                      "achieved_GBps": n * 7 / (vp_ms * 1e-3) / 1e9, "inherited_visible_rows": int(inh.sum()),
+                                      "note": "topo 4 B + Visibility 1 B + flags 1 B read + changed 1 B written per row; steady state (no flag flips)"}
+    ctx.upload_visibility(0, np.zeros(n, np.uint8)); ctx.propagate_visibility()      # everything visible again
+
+    # N4a: check_visibility_ranges inside the cull phase, VisibilityRange on EVERY row, range views = the 4 cameras
+    se = np.stack([np.zeros(n, np.float32), np.full(n, 700.0, np.float32)], 1)
+    ctx.upload_visibility_ranges(0, se, np.ones(n, np.uint8))
+    flags = (scene.flags | bb.F_HAS_VIS_RANGE).astype(np.uint8)
+    ctx.upload_bounds(0, scene.bounds, flags, scene.class_mask, scene.layer_mask, None)
+    ctx.set_visibility_range_views(np.stack([np.asarray(c.gt, np.float32)[9:12] for c in scene.cameras]))
+    ctx.use_recorded_frame_constants(None)
+    scene.view_range_index = list(range(V))  # each culled view reads its own bit of the range mask
+    for i in range(W):
+        live_step(i)
+    t_ms, _, _ = staged(step=live_step)
+    masks = ctx.download_visibility_ranges(0, n)
+    out["N4_visibility_ranges"] = {"tile_ms_all_rows_ranged": t_ms, "tile_ms_base": tile_ms, "rows_in_range_of_view0": int((masks & 1).sum()),
+                                   "note": "worst case: every row carries a VisibilityRange (general cull path: per-row layers/range gathers, 4 distance tests)"}
+    return out
 
 
 def main():
@@ -392,6 +486,19 @@ def main():
     tile_ms_avg, expand_ms_avg, cluster_ms_avg = t_tile / nf, t_expand / nf, t_cluster / nf
     visible_pairs = sum(sanity.visible_count[v] for v in range(V))
 
+    # ---- SURVEY 8(f) rows (N1, N2, N4): what each costs on this workload; outside every timed region above ------------
+    next_rows = None
+    if world == 1 and not args.no_next_rows:
+        def live_step(i):
+            f = WIN + i % WIN
+            set_cameras(f)
+            ctx.upload_transforms_scattered_raw(n_roots, rows_d.data_ptr(), trs_frames_d[f].data_ptr())
+            pipe.update_views_fast()
+            run_stages()
+
+        next_rows = measure_next_rows(torch, bb, pipe, ctx, scene, stream, value_step, live_step, e2e_step_single, stats_t, coff_h,
+                                      cidx_h, tile_ms_avg, expand_ms_avg, cluster_ms_avg, e2e_ms / K, WIN, W)
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -421,6 +528,8 @@ def main():
                          "gt_changed_rows_last_frame": int(sanity.gt_changed_count),
                          "algorithmic_bytes_per_entity": ALGO_BYTES_PER_ENTITY, "note": EXTRA_BYTES_NOTE},
         }
+        if next_rows is not None:
+            line["next_rows"] = next_rows
         if not args.no_cpu_baseline:
             cpu_scene = scenes.forest(args.trees, LEVELS, args.lights)
             sec, threads = cpu_frames(cpu_scene, args.cpu_frames)

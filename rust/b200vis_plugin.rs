@@ -50,6 +50,19 @@ extern "C" {
     fn b200vis_run(ctx: *mut b200vis_ctx, stages: u32) -> i32;
     fn b200vis_download_frame(ctx: *mut b200vis_ctx, stats: *mut b200vis_frame_stats, visible_rows: *mut u32, visible_cap: u32,
                               cluster_offsets: *mut u32, cluster_indices: *mut u32, cluster_cap: u32) -> i32;
+    // the systems either side of the path
+    fn b200vis_upload_visibility(ctx: *mut b200vis_ctx, first: u32, count: u32, visibility: *const u8) -> i32;
+    fn b200vis_propagate_visibility(ctx: *mut b200vis_ctx) -> i32;
+    fn b200vis_download_inherited_visibility(ctx: *mut b200vis_ctx, first: u32, count: u32, inherited: *mut u8, changed: *mut u8) -> i32;
+    fn b200vis_upload_visibility_ranges(ctx: *mut b200vis_ctx, first: u32, count: u32, start_end: *const f32, use_aabb: *const u8) -> i32;
+    fn b200vis_set_visibility_range_views(ctx: *mut b200vis_ctx, n_views: u32, positions: *const f32) -> i32;
+    fn b200vis_download_visibility_ranges(ctx: *mut b200vis_ctx, first: u32, count: u32, mask: *mut u32) -> i32;
+    fn b200vis_enable_visible_diff(ctx: *mut b200vis_ctx, enabled: i32) -> i32;
+    fn b200vis_download_visible_diff(ctx: *mut b200vis_ctx, view: u32, added: *mut u32, added_cap: u32, n_added: *mut u32,
+                                     removed: *mut u32, removed_cap: u32, n_removed: *mut u32) -> i32;
+    fn b200vis_set_cluster_bindings(ctx: *mut b200vis_ctx, mode: u32, gpu_index_of_light: *const u32, n_map: u32) -> i32;
+    fn b200vis_download_cluster_bindings(ctx: *mut b200vis_ctx, view: u32, offsets_and_counts: *mut u32, oc_cap: u32,
+                                         index_lists: *mut u32, il_cap: u32, n_offsets: *mut u32, n_indices: *mut u32) -> i32;
     fn b200vis_download_global_transforms(ctx: *mut b200vis_ctx, first: u32, count: u32, gt: *mut f32, stride: u32, changed: *mut u8) -> i32;
     fn b200vis_download_view_visibility(ctx: *mut b200vis_ctx, first: u32, count: u32, vv: *mut u8, changed: *mut u8) -> i32;
 }
