@@ -130,6 +130,11 @@ _SIGNATURES = {
     "b200vis_download_visible": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_download_clusters": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_set_result_sink": (C.c_int32, [_vp, _P(ResultSink)]),
+    "b200vis_upload_shadow_casters": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "b200vis_set_shadow_lights": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, _vp, C.c_int32, C.c_uint32]),
+    "b200vis_run_shadow_culling": (C.c_int32, [_vp]),
+    "b200vis_download_shadow_visible": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32)]),
+    "b200vis_host_point_light_frusta": (None, [_vp, C.c_float, C.c_float, _vp]),
     "b200vis_upload_visibility_ranges": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "b200vis_set_visibility_range_views": (C.c_int32, [_vp, C.c_uint32, _vp]),
     "b200vis_download_visibility_ranges": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
@@ -153,6 +158,14 @@ _SIGNATURES = {
                                                     _P(ClusterFeedback), _vp, _P(ClusterView)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def host_point_light_frusta(light_gt12, light_range, shadow_map_near_z=0.1):
+    """update_point_light_frusta for one light -> [6, 6, 4] (no GPU needed)."""
+    g = np.ascontiguousarray(light_gt12, np.float32)
+    out = np.zeros((6, 6, 4), np.float32)
+    load_library().b200vis_host_point_light_frusta(_ptr(g), float(light_range), float(shadow_map_near_z), _ptr(out))
+    return out
 
 
 def library_path():
@@ -400,6 +413,28 @@ class Context:
         self._check(self._lib.b200vis_download_visible(self._h, view, None, 0, C.byref(cnt)))
         rows = np.zeros(max(cnt.value, 1), np.uint32)
         self._check(self._lib.b200vis_download_visible(self._h, view, _ptr(rows), len(rows), C.byref(cnt)))
+        return rows[:cnt.value]
+
+    # ---- SURVEY 8(f) N3 ----
+    def upload_shadow_casters(self, first, caster):
+        c = np.ascontiguousarray(caster, np.uint8)
+        self._check(self._lib.b200vis_upload_shadow_casters(self._h, first, len(c), _ptr(c)))
+
+    def set_shadow_lights(self, light_ordinals, frusta, layer_mask=None, lod_origin_range_index=-1, list_capacity=0):
+        o = np.ascontiguousarray(light_ordinals, np.uint32)
+        fr = np.ascontiguousarray(frusta, np.float32).reshape(-1, 6, 6, 4)
+        lm = None if layer_mask is None else np.ascontiguousarray(layer_mask, np.uint64)
+        self._check(self._lib.b200vis_set_shadow_lights(self._h, len(o), _ptr(o), _ptr(fr), None if lm is None else _ptr(lm),
+                                                        int(lod_origin_range_index), int(list_capacity)))
+
+    def run_shadow_culling(self):
+        self._check(self._lib.b200vis_run_shadow_culling(self._h))
+
+    def download_shadow_visible(self, shadow_light, face):
+        cnt = C.c_uint32(0)
+        self._check(self._lib.b200vis_download_shadow_visible(self._h, shadow_light, face, None, 0, C.byref(cnt)))
+        rows = np.zeros(max(cnt.value, 1), np.uint32)
+        self._check(self._lib.b200vis_download_shadow_visible(self._h, shadow_light, face, _ptr(rows), len(rows), C.byref(cnt)))
         return rows[:cnt.value]
 
     # ---- SURVEY 8(f) N4 ----

@@ -115,6 +115,9 @@ struct b200vis_ctx {
     DiffBufs diff{}; bool diff_on = false;      // SURVEY 8(f) N1 (b200vis_enable_visible_diff)
     uint32_t *diff_sink_rows_d = nullptr, *diff_sink_counts_d = nullptr; uint32_t diff_sink_cap = 0;
     BindingBufs bind{}; uint32_t *d_bind_map = nullptr; uint32_t bind_map_cap = 0;   // SURVEY 8(f) N2 (b200vis_set_cluster_bindings)
+    // shadow-view culling (b200vis_set_shadow_lights / b200vis_run_shadow_culling)
+    ShadowBufs shadow{}; ShadowLight *d_shadow_lights = nullptr; uint8_t *d_caster = nullptr;
+    uint32_t shadow_cap_lights = 0, shadow_cap_list = 0; std::vector<ShadowLight> h_shadow;
     // VisibilityRange columns + range views; Visibility column + the rows the last propagate wrote
     float2 *d_range_se = nullptr; uint8_t *d_range_ua = nullptr; float4 *d_range_views = nullptr; uint32_t n_range_views = 0;
     uint8_t *d_visibility = nullptr, *d_iv_changed = nullptr; bool iv_ran = false;
@@ -183,7 +186,9 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage,
                    ctx->diff.prev, ctx->diff.words, ctx->diff.chunk, ctx->diff.lists, ctx->diff.count,
                    ctx->bind.oc, ctx->bind.il, ctx->bind.count, ctx->d_bind_map,
-                   ctx->d_range_se, ctx->d_range_ua, ctx->d_range_views, ctx->d_visibility, ctx->d_iv_changed};
+                   ctx->d_range_se, ctx->d_range_ua, ctx->d_range_views, ctx->d_visibility, ctx->d_iv_changed,
+                   ctx->d_shadow_lights, ctx->d_caster, ctx->shadow.mask, ctx->shadow.chunk_count, ctx->shadow.lists,
+                   ctx->shadow.count, ctx->shadow.active};
     for (void *p : dev) if (p) cudaFree(p);
     for (int i = 0; i < b200vis_ctx::kRing; ++i) {
         if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
@@ -1096,6 +1101,92 @@ extern "C" int32_t b200vis_download_clusters(b200vis_ctx *ctx, uint32_t view, ui
     if (indices) {
         if (*total > indices_capacity) return fail(ctx, B200VIS_ERR_CAPACITY, "download_clusters: %u indices > capacity %u", *total, indices_capacity);
         CU(cudaMemcpyAsync(indices, ctx->cl.indices + (size_t)view * ctx->cl.index_cap, (size_t)*total * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200VIS_OK;
+}
+
+// ---- check_point_light_mesh_visibility (point lights) ------------------------------------------------
+extern "C" int32_t b200vis_enable_visible_diff(b200vis_ctx *ctx, int32_t enabled);
+extern "C" int32_t b200vis_upload_shadow_casters(b200vis_ctx *ctx, uint32_t first, uint32_t count, const uint8_t *caster) {
+    CHECK_CTX();
+    if (count && !caster) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_shadow_casters: null");
+    int32_t rc = check_range(ctx, first, count, "upload_shadow_casters"); if (rc) return rc;
+    if (!ctx->d_caster) CU(dalloc(&ctx->d_caster, ctx->cfg.max_entities));
+    // the stage reads each view's VisibleEntities as a bit set: the sets the visible-diff bookkeeping keeps.  Switched on
+    // here, with the first column upload, so that the CULL stage of the coming frame already records them.
+    if (!ctx->diff_on) { const int32_t rc2 = b200vis_enable_visible_diff(ctx, 1); if (rc2) return rc2; }
+    CU(cudaMemcpyAsync(ctx->d_caster + first, caster, count, cudaMemcpyHostToDevice, ctx->stream));
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_set_shadow_lights(b200vis_ctx *ctx, uint32_t n_lights, const uint32_t *light_ordinals, const float *frusta,
+                                             const uint64_t *layer_mask, int32_t lod_origin_range_index, uint32_t list_capacity) {
+    CHECK_CTX_JOIN();
+    if (n_lights && (!light_ordinals || !frusta)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_shadow_lights: null");
+    if (!ctx->d_caster) return fail(ctx, B200VIS_ERR_NOT_READY, "set_shadow_lights: upload the shadow-caster column first");
+    for (uint32_t i = 0; i < n_lights; ++i)
+        if (light_ordinals[i] >= ctx->lights.n) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_shadow_lights: light ordinal %u >= %u lights", light_ordinals[i], ctx->lights.n);
+    if (!list_capacity) list_capacity = std::max<uint32_t>(ctx->cfg.max_entities, 1);
+    if (!ctx->diff_on) return fail(ctx, B200VIS_ERR_NOT_READY, "set_shadow_lights: the visible-set bookkeeping was switched off after upload_shadow_casters");
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n_lights > ctx->shadow_cap_lights || list_capacity > ctx->shadow_cap_list) {
+        void *old[] = {ctx->d_shadow_lights, ctx->shadow.mask, ctx->shadow.chunk_count, ctx->shadow.lists, ctx->shadow.count, ctx->shadow.active};
+        for (void *p : old) if (p) cudaFree(p);
+        ctx->d_shadow_lights = nullptr; ctx->shadow = ShadowBufs{};
+        const size_t nl = std::max<uint32_t>(n_lights, ctx->shadow_cap_lights), lc = std::max<uint32_t>(list_capacity, ctx->shadow_cap_list);
+        CU(dalloc(&ctx->d_shadow_lights, nl));
+        CU(dalloc(&ctx->shadow.mask, nl * 6 * ctx->vis.words_stride));
+        CU(dalloc(&ctx->shadow.chunk_count, nl * 6 * ctx->vis.chunks_stride));
+        CU(dalloc(&ctx->shadow.lists, nl * 6 * lc));
+        CU(dalloc(&ctx->shadow.count, nl * 6));
+        CU(dalloc(&ctx->shadow.active, nl));
+        ctx->shadow_cap_lights = (uint32_t)nl; ctx->shadow_cap_list = (uint32_t)lc;
+    }
+    ctx->h_shadow.resize(n_lights);
+    for (uint32_t i = 0; i < n_lights; ++i) {
+        ShadowLight &s = ctx->h_shadow[i];
+        memcpy(s.planes, frusta + (size_t)i * 144, sizeof s.planes);
+        s.layers = layer_mask ? layer_mask[i] : 1ull; s.light = light_ordinals[i]; s.pad = 0;
+    }
+    if (n_lights) CU(cudaMemcpy(ctx->d_shadow_lights, ctx->h_shadow.data(), n_lights * sizeof(ShadowLight), cudaMemcpyHostToDevice));
+    ctx->shadow.n_lights = n_lights; ctx->shadow.lights = ctx->d_shadow_lights; ctx->shadow.caster = ctx->d_caster;
+    ctx->shadow.lod_origin = (lod_origin_range_index >= 0 && lod_origin_range_index < 32) ? lod_origin_range_index : -1;
+    ctx->shadow.list_cap = ctx->shadow_cap_list;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_run_shadow_culling(b200vis_ctx *ctx) {
+    CHECK_CTX_JOIN();   // reads what the frame's CULL stage (incl. its tail on the side stream) left behind
+    if (!ctx->d_caster || !ctx->diff.prev) return fail(ctx, B200VIS_ERR_NOT_READY, "run_shadow_culling: call b200vis_set_shadow_lights first");
+    if (ctx->frame == 0) return fail(ctx, B200VIS_ERR_NOT_READY, "run_shadow_culling: run the CULL stage first");
+    if (!ctx->shadow.n_lights) return B200VIS_OK;
+    cudaStream_t st = ctx->stream;
+    Rows R = ctx->rows;
+    R.layers = ctx->have_layers ? ctx->d_layers : nullptr;
+    R.range = ctx->have_range ? ctx->d_range : nullptr;
+    R.rank = ctx->rank_identity ? nullptr : ctx->d_rank;
+    R.row_of_rank = ctx->rank_identity ? nullptr : ctx->d_row_of_rank;
+    ShadowBufs sb = ctx->shadow;
+    sb.has_ranges = ctx->have_range ? 1u : 0u;
+    CU(cudaMemsetAsync(sb.chunk_count, 0, (size_t)sb.n_lights * 6 * ctx->vis.chunks_stride * 4, st));
+    launch_shadow_cull(st, R, sb, ctx->lights, ctx->diff.prev, active_consts(ctx).n_views, ctx->vis.n_words, ctx->vis.n_chunks,
+                       ctx->vis.words_stride, ctx->vis.chunks_stride, ctx->d_stats, (ctx->frame + 2u) % 3u);
+    CU(cudaGetLastError());
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_download_shadow_visible(b200vis_ctx *ctx, uint32_t shadow_light, uint32_t face, uint32_t *rows, uint32_t capacity,
+                                                   uint32_t *count) {
+    CHECK_CTX_JOIN();
+    if (shadow_light >= ctx->shadow.n_lights || face >= 6 || !count) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_shadow_visible: bad argument");
+    cudaStream_t st = ctx->stream;
+    const uint32_t list = shadow_light * 6 + face;
+    uint32_t c = 0;
+    CU(cudaMemcpyAsync(&c, ctx->shadow.count + list, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *count = c;
+    if (rows) {
+        if (c > capacity || c > ctx->shadow.list_cap)
+            return fail(ctx, B200VIS_ERR_CAPACITY, "download_shadow_visible: %u rows > capacity %u (list capacity %u)", c, capacity, ctx->shadow.list_cap);
+        if (c) CU(cudaMemcpyAsync(rows, ctx->shadow.lists + (size_t)list * ctx->shadow.list_cap, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return B200VIS_OK;

@@ -145,6 +145,27 @@ struct ClusterBufs {
     uint32_t *indices;       // [V][index_cap]
 };
 
+// check_point_light_mesh_visibility (bevy_light/src/lib.rs:517-668) for the shadow-casting point lights
+struct ShadowLight {
+    float4 planes[6][6];     // CubemapFrusta: face, half space (normal, d)
+    unsigned long long layers;
+    uint32_t light;          // ordinal in the b200vis_set_lights arrays
+    uint32_t pad;
+};
+struct ShadowBufs {
+    uint32_t n_lights;       // shadow lights this frame
+    const ShadowLight *lights;
+    const uint8_t *caster;   // per row: in visible_entity_query (Mesh3d, no NotShadowCaster, no DirectionalLight)
+    int32_t lod_origin;      // bit of the shadow LOD origin in the range masks, -1 = none
+    uint32_t has_ranges;     // a VisibleEntityRanges resource exists
+    uint32_t *mask;          // [n_lights * 6][words_stride], bit = rank; zeroed by the expand kernel as it reads
+    uint32_t *chunk_count;   // [n_lights * 6][chunks_stride]
+    uint32_t *lists;         // [n_lights * 6][list_cap]
+    uint32_t *count;         // [n_lights * 6]
+    uint32_t list_cap;
+    uint32_t *active;        // [n_lights]: the light is in some view's VisibleEntities (written by k_shadow_select)
+};
+
 // the ViewClusterBindings wire format (bevy_pbr/src/cluster/mod.rs:584-800) packed on the device
 struct BindingBufs {
     uint32_t mode;           // 0 off, 1 storage buffers, 2 uniform buffers

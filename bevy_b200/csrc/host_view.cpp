@@ -140,6 +140,75 @@ void compute_frustum(const float *clip_from_view16, const float *camera_gt12, fl
     store(hs[5], half_space(extend(back, -dot(back, far_center))));
 }
 
+// ---- CubemapFrusta of a point light --------------------------------------------------------------
+// update_point_light_frusta (crates/bevy_light/src/point_light.rs:212-265): six 90-degree views along the world axes
+// (CUBE_MAP_FACES, bevy_camera/src/primitives.rs:348-379) at the light's translation; every face shares one far
+// plane, `range` behind the light along the LIGHT's back direction.  For hosts without glam; a Rust shim passes the
+// CubemapFrusta component instead.
+namespace {
+// glam Quat::from_rotation_axes on the columns (right, up, back) that Transform::look_to builds (transform.rs:475-484)
+F4 rotation_from_axes(F3 xa, F3 ya, F3 za) {
+    if (za.z <= 0.0f) {
+        const float dif10 = ya.y - xa.x, omm22 = 1.0f - za.z;
+        if (dif10 <= 0.0f) {
+            const float four_xsq = omm22 - dif10, inv = 0.5f / std::sqrt(four_xsq);
+            return {four_xsq * inv, (xa.y + ya.x) * inv, (xa.z + za.x) * inv, (ya.z - za.y) * inv};
+        }
+        const float four_ysq = omm22 + dif10, inv = 0.5f / std::sqrt(four_ysq);
+        return {(xa.y + ya.x) * inv, four_ysq * inv, (ya.z + za.y) * inv, (za.x - xa.z) * inv};
+    }
+    const float sum10 = ya.y + xa.x, opm22 = 1.0f + za.z;
+    if (sum10 <= 0.0f) {
+        const float four_zsq = opm22 - sum10, inv = 0.5f / std::sqrt(four_zsq);
+        return {(xa.z + za.x) * inv, (ya.z + za.y) * inv, four_zsq * inv, (xa.y - ya.x) * inv};
+    }
+    const float four_wsq = opm22 + sum10, inv = 0.5f / std::sqrt(four_wsq);
+    return {(ya.z - za.y) * inv, (za.x - xa.z) * inv, (xa.y - ya.x) * inv, four_wsq * inv};
+}
+// Affine3A::from_scale_rotation_translation(ONE, q, t)  (Mat3A::from_quat, each column * 1.0)
+Affine affine_from_rotation_translation(F4 q, F3 t) {
+    const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
+    const float xx = q.x * x2, xy = q.x * y2, xz = q.x * z2, yy = q.y * y2, yz = q.y * z2, zz = q.z * z2;
+    const float wx = q.w * x2, wy = q.w * y2, wz = q.w * z2;
+    Affine a;
+    a.m.x = F3{1.0f - (yy + zz), xy + wz, xz - wy} * 1.0f;
+    a.m.y = F3{xy - wz, 1.0f - (xx + zz), yz + wx} * 1.0f;
+    a.m.z = F3{xz + wy, yz - wx, 1.0f - (xx + yy)} * 1.0f;
+    a.t = t;
+    return a;
+}
+}  // namespace
+void point_light_frusta(const float *light_gt12, float range, float shadow_map_near_z, float hs[6][6][4]) {
+    struct Face { F3 target, up; };
+    static const Face kFaces[6] = {{{1, 0, 0}, {0, 1, 0}},  {{-1, 0, 0}, {0, 1, 0}}, {{0, 1, 0}, {0, 0, 1}},
+                                   {{0, -1, 0}, {0, 0, -1}}, {{0, 0, -1}, {0, 1, 0}}, {{0, 0, 1}, {0, 1, 0}}};
+    const Affine light = load_affine(light_gt12);
+    float cfv16[16];
+    perspective_infinite_reverse_rh(1.57079632679489661923f, 1.0f, shadow_map_near_z, cfv16);
+    const Cols4 cfv = load_mat4(cfv16);
+    const F3 zaxis = mul(light.m, F3{0.0f, 0.0f, 1.0f});
+    const F3 view_backward = zaxis * (1.0f / length(zaxis));              // GlobalTransform::back()
+    const F3 far_center = light.t - view_backward * range;
+    const F4 far_plane = half_space(extend(view_backward, -dot(view_backward, far_center)));
+    for (int f = 0; f < 6; ++f) {
+        const F3 dir = kFaces[f].target * (1.0f / length(kFaces[f].target));   // Dir3::new (unit axes: exact)
+        const F3 back = -dir;
+        const F3 up0 = kFaces[f].up * (1.0f / length(kFaces[f].up));
+        F3 right = cross(up0, back);
+        right = right * (1.0f / length(right));
+        const F3 up = cross(back, right);
+        const Affine world_from_view = affine_from_rotation_translation(rotation_from_axes(right, up, back), light.t);
+        const Cols4 cfw = mul(cfv, to_mat4(inverse(world_from_view)));
+        const F4 r0 = row(cfw, 0), r1 = row(cfw, 1), r2 = row(cfw, 2), r3 = row(cfw, 3);
+        store(hs[f][0], half_space(r3 + r0));
+        store(hs[f][1], half_space(r3 - r0));
+        store(hs[f][2], half_space(r3 + r1));
+        store(hs[f][3], half_space(r3 - r1));
+        store(hs[f][4], half_space(r3 + r2));
+        store(hs[f][5], far_plane);
+    }
+}
+
 void default_cluster_config(b200vis_cluster_config *c, uint32_t w, uint32_t h) {
     // ClusterConfig::default() + ClusterZConfig::default() (cluster/mod.rs:288-307)
     std::memset(c, 0, sizeof *c);
@@ -331,6 +400,9 @@ void b200vis_host_perspective(float fov_y, float aspect, float near_z, float *ou
 }
 void b200vis_host_compute_frustum(const float *cfv16, const float *cam12, float far_z, float hs[6][4]) {
     b200vis::host::compute_frustum(cfv16, cam12, far_z, hs);
+}
+void b200vis_host_point_light_frusta(const float *light_gt12, float range, float shadow_map_near_z, float hs[6][6][4]) {
+    b200vis::host::point_light_frusta(light_gt12, range, shadow_map_near_z, hs);
 }
 void b200vis_host_z_slice_thresholds(const float f[2], uint32_t z_slices, uint32_t ortho, float *thr) {
     b200vis::host::z_slice_thresholds(f, z_slices, ortho != 0, thr);

@@ -6,6 +6,7 @@
 namespace b200vis { namespace host {
 void perspective_infinite_reverse_rh(float fov_y, float aspect, float near_z, float *out16);
 void compute_frustum(const float *clip_from_view16, const float *camera_gt12, float far_z, float hs[6][4]);
+void point_light_frusta(const float *light_gt12, float range, float shadow_map_near_z, float hs[6][6][4]);
 void default_cluster_config(b200vis_cluster_config *c, uint32_t w, uint32_t h);
 int32_t cluster_view_setup(const b200vis_cluster_config *cfg, const float *camera_gt12,
                            const float *clip_from_view16, const float frustum[6][4], uint64_t layer_mask,

@@ -1235,6 +1235,175 @@ __global__ void k_cluster_clear(const FrameConsts *__restrict__ fc, ClusterBufs 
 }
 
 // ------------------------------------------------------------------------------------------
+// Kernels 5a-c: check_point_light_mesh_visibility for point lights
+// (crates/bevy_light/src/lib.rs:517-668).  One thread per row loops over the frame's shadow lights (staged through
+// shared memory a few at a time): layers / visibility-range gates, Sphere::intersects_obb against the light's range
+// sphere (primitives.rs:219-226), then Frustum::intersects_obb with near and far planes on each of the six cubemap
+// faces (primitives.rs:272-294).  Visible (row, light, face) triples go into rank-ordered bit sets that
+// k_expand_shadow turns into the sorted CubemapVisibleEntities lists; a row seen by any light gets
+// ViewVisibility::set_visible (visibility/mod.rs:292-306) applied on top of what the camera cull left.
+// ------------------------------------------------------------------------------------------
+constexpr int kShadowChunk = 4;   // lights staged per round (4 x 592 B)
+// a light takes part only if it is in some view's VisibleEntities (lib.rs:561-563): its rank bit in the per-view sets
+__global__ void k_shadow_select(ShadowBufs sb, Lights L, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ view_sets,
+                                uint32_t words_stride, uint32_t n_views) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= sb.n_lights) return;
+    const uint32_t row = L.row[sb.lights[s].light], rk = rank ? rank[row] : row;
+    uint32_t on = 0;
+    for (uint32_t v = 0; v < n_views; ++v) on |= (view_sets[(size_t)v * words_stride + (rk >> 5)] >> (rk & 31u)) & 1u;
+    sb.active[s] = on;
+}
+__global__ void __launch_bounds__(256)
+k_shadow_cull(Rows R, ShadowBufs sb, Lights L, uint32_t words_stride, uint32_t chunks_stride, DevStats *__restrict__ stats,
+              uint32_t changed_slot) {
+    __shared__ ShadowLight s_light[kShadowChunk];
+    __shared__ float4 s_sphere[kShadowChunk];
+    __shared__ uint32_t s_on[kShadowChunk];
+    const uint32_t row = blockIdx.x * 256u + threadIdx.x, lane = threadIdx.x & 31u;
+    const bool active = row < R.n;
+    uint32_t f = 0, st8 = 0;
+    Aff g; g.r0 = g.r1 = g.r2 = make_float4(0, 0, 0, 0);
+    float4 bA = g.r0; float2 bB = make_float2(0, 0);
+    bool eligible = false;
+    unsigned long long elayers = 1ull;
+    uint32_t rnk = row;
+    if (active) {
+        f = R.flags[row]; st8 = R.state[row];
+        eligible = sb.caster[row] && !(f & F_NO_CPU_CULL) && (f & F_INHERITED);
+        if (eligible && (f & F_RANGE) && sb.has_ranges)   // visible range gate against the shadow LOD origin (lib.rs:607-616)
+            eligible = sb.lod_origin >= 0 && R.range != nullptr && ((R.range[row] >> sb.lod_origin) & 1u);
+        if (eligible) {
+            g.r0 = R.gt0[row]; g.r1 = R.gt1[row]; g.r2 = R.gt2[row];
+            bA = R.bndA[row]; bB = R.bndB[row];
+            if (R.layers != nullptr) elayers = R.layers[row];
+        }
+        if (R.rank != nullptr) rnk = R.rank[row];
+    }
+    const bool has_aabb = f & F_AABB, no_fc = f & F_NO_FRUSTUM;
+    const float hx = bA.w, hy = bB.x, hz = bB.y;
+    // transform_point3a(aabb.center)
+    const float cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;
+    const float cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
+    const float cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+    bool any = false;
+    for (uint32_t s0 = 0; s0 < sb.n_lights; s0 += kShadowChunk) {
+        const uint32_t nl = min((uint32_t)kShadowChunk, sb.n_lights - s0);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nl * (sizeof(ShadowLight) / 16); i += 256u)
+            reinterpret_cast<float4 *>(s_light)[i] = reinterpret_cast<const float4 *>(sb.lights + s0)[i];
+        if (threadIdx.x < nl) {
+            const uint32_t ord = sb.lights[s0 + threadIdx.x].light;
+            s_on[threadIdx.x] = sb.active[s0 + threadIdx.x];
+            const uint32_t lrow = L.row[ord];   // light_sphere = (GlobalTransform translation, range) (lib.rs:575-578)
+            s_sphere[threadIdx.x] = make_float4(R.gt0[lrow].w, R.gt1[lrow].w, R.gt2[lrow].w, L.range[ord]);
+        }
+        __syncthreads();
+        for (uint32_t i = 0; i < nl; ++i) {
+            if (!s_on[i]) continue;                                  // warp-uniform
+            const ShadowLight &sl = s_light[i];
+            bool in = eligible && (sl.layers & elayers) != 0ull;
+            uint32_t faces = 0x3Fu;                                  // no Aabb: pushed to all six faces (lib.rs:639-645)
+            if (in && has_aabb) {
+                if (!no_fc) {
+                    // Sphere::intersects_obb: d_sq <= radius * d + relative_radius(v)
+                    const float4 sp = s_sphere[i];
+                    const float vx = cx - sp.x, vy = cy - sp.y, vz = cz - sp.z;
+                    const float d_sq = (vx * vx + vy * vy) + vz * vz, d = sqrtf(d_sq);
+                    const float ax = fabsf(dot3(vx, vy, vz, g.r0.x, g.r1.x, g.r2.x));
+                    const float ay = fabsf(dot3(vx, vy, vz, g.r0.y, g.r1.y, g.r2.y));
+                    const float az = fabsf(dot3(vx, vy, vz, g.r0.z, g.r1.z, g.r2.z));
+                    const float rr = (ax * hx + ay * hy) + az * hz;
+                    in = d_sq <= sp.w * d + rr;
+                    if (in) {
+                        faces = 0;
+                        for (uint32_t fc = 0; fc < 6; ++fc) {
+                            bool inside = true;
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) {   // intersect_near = intersect_far = true
+                                const float4 n = sl.planes[fc][k];
+                                const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+                                const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+                                const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+                                const float prr = (dx * hx + dy * hy) + dz * hz;
+                                inside = inside && !(plane_dot_point(n, cx, cy, cz) + prr <= 0.0f);
+                            }
+                            faces |= inside ? (1u << fc) : 0u;
+                        }
+                    }
+                }
+            }
+            if (!in) faces = 0;
+            any |= faces != 0u;
+            if (__any_sync(0xFFFFFFFFu, faces != 0u)) {
+                for (uint32_t fc = 0; fc < 6; ++fc) {
+                    const uint32_t list = (s0 + i) * 6u + fc;
+                    uint32_t *mask = sb.mask + (size_t)list * words_stride;
+                    uint32_t *cc = sb.chunk_count + (size_t)list * chunks_stride;
+                    if (R.rank == nullptr) {
+                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, (faces >> fc) & 1u);
+                        if (lane == 0 && b) { mask[row >> 5] = b; atomicAdd(cc + ((row >> 5) / kChunkWords), __popc(b)); }
+                    } else if ((faces >> fc) & 1u) {
+                        atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+                        atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
+                    }
+                }
+            }
+        }
+    }
+    // set_visible on top of the camera cull's result.  A row the cameras left hidden has state 0 (+ S_VV_CHANGED when it was
+    // visible last frame): visible now means (1 | prev << 1), and the change flag fires iff it was NOT visible last frame.
+    if (any && !(st8 & 1u)) {
+        const uint32_t prev = (st8 & S_VV_CHANGED) ? 1u : 0u;
+        const uint32_t out = (st8 & ~(S_VV | S_VV_CHANGED)) | 1u | (prev << 1) | (prev ? 0u : S_VV_CHANGED);
+        R.state[row] = (uint8_t)out;
+        atomicAdd(&stats->changed[changed_slot][1], prev ? 0xFFFFFFFFu : 1u);
+    }
+}
+// the sorted CubemapVisibleEntities lists from the bit sets (same chunked scan as k_expand_visible)
+__global__ void __launch_bounds__(kChunkWords)
+k_expand_shadow(ShadowBufs sb, uint32_t n_words, uint32_t n_chunks, uint32_t words_stride, uint32_t chunks_stride,
+                const uint32_t *__restrict__ row_of_rank) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base, s_total;
+    const uint32_t list = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+    const uint32_t *cc = sb.chunk_count + (size_t)list * chunks_stride;
+    const uint32_t word = chunk * kChunkWords + t;
+    uint32_t *mask = sb.mask + (size_t)list * words_stride;
+    uint32_t w = 0;
+    if (word < n_words) { w = mask[word]; if (w) mask[word] = 0; }
+    const uint32_t c = __popc(w);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((t & 31u) >= (uint32_t)o) incl += y; }
+    if ((t & 31u) == 31u) s_warp[t >> 5] = incl;
+    if (t < 32) {
+        uint32_t part = 0, tot = 0;
+        for (uint32_t i = t; i < n_chunks; i += 32) { const uint32_t x = cc[i]; tot += x; if (i < chunk) part += x; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xFFFFFFFFu, part, o); tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o); }
+        if (t == 0) { s_base = part; s_total = tot; }
+    }
+    __syncthreads();
+    if (t < 32) {
+        uint32_t x = s_warp[t];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
+        s_warp[t] = x;
+    }
+    __syncthreads();
+    uint32_t pos = s_base + (incl - c) + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+    uint32_t *out = sb.lists + (size_t)list * sb.list_cap;
+    while (w) {
+        const uint32_t b = __ffs(w) - 1; w &= w - 1;
+        const uint32_t rk = word * 32u + b;
+        if (pos < sb.list_cap) out[pos] = row_of_rank ? row_of_rank[rk] : rk;
+        ++pos;
+    }
+    if (chunk == 0 && t == 0) sb.count[list] = s_total;
+}
+
+// ------------------------------------------------------------------------------------------
 // Kernel 4b: Clusters -> ViewClusterBindings.  The reference walks a record stream
 // (ClusterHeader, Light, Light, ..., bevy_pbr/src/cluster/mod.rs:419-470) and pushes offsets-and-counts / indices
 // one by one (:494-520, :609-697); with the CSR already on the device every output word is independent.
@@ -1528,6 +1697,13 @@ void launch_publish_clusters(cudaStream_t st, const FrameConsts *fc, const Clust
                              uint32_t host_cap, const DevStats *stats, uint32_t *host_stats, uint32_t changed_slot, uint32_t frame, uint32_t max_views) {
     k_publish_clusters<<<dim3(kMaxClusters / 256 + 1, max_views), 256, 0, st>>>(fc, cb.offsets, cb.indices, cb.index_cap, host_offsets, host_indices,
                                                                                 host_cap, stats, host_stats, changed_slot, frame);
+}
+void launch_shadow_cull(cudaStream_t st, const Rows &R, const ShadowBufs &sb, const Lights &L, const uint32_t *view_sets, uint32_t n_views,
+                        uint32_t n_words, uint32_t n_chunks, uint32_t words_stride, uint32_t chunks_stride, DevStats *stats, uint32_t changed_slot) {
+    if (!sb.n_lights || !R.n) return;
+    k_shadow_select<<<cdiv(sb.n_lights, 128), 128, 0, st>>>(sb, L, R.rank, view_sets, words_stride, n_views);
+    k_shadow_cull<<<cdiv(R.n, 256), 256, 0, st>>>(R, sb, L, words_stride, chunks_stride, stats, changed_slot);
+    k_expand_shadow<<<dim3(n_chunks, sb.n_lights * 6), kChunkWords, 0, st>>>(sb, n_words, n_chunks, words_stride, chunks_stride, R.row_of_rank);
 }
 void launch_pack_cluster_bindings(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, const BindingBufs &bb, uint32_t max_views) {
     if (bb.mode) k_pack_cluster_bindings<<<dim3(16, max_views), 256, 0, st>>>(fc, cb, bb);

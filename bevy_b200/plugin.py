@@ -86,6 +86,19 @@ class VisibilityPipeline:
         """The fused per-frame path: one launch sequence for all three systems."""
         self.ctx.run(abi.STAGE_ALL if len(self.scene.light_row) else (abi.STAGE_PROPAGATE | abi.STAGE_CULL))
 
+    def check_point_light_mesh_visibility(self, shadow_ordinals, shadow_map_near_z=0.1, lod_origin_range_index=-1):
+        """SURVEY 8(f) N3 (bevy_light/src/lib.rs:517): call after run_frame().  The CubemapFrusta come from the lights'
+        GlobalTransforms of this frame (update_point_light_frusta), as a shim would read them from the component."""
+        sc = self.scene
+        ords = np.asarray(shadow_ordinals, np.uint32)
+        frusta = np.zeros((len(ords), 6, 6, 4), np.float32)
+        for i, o in enumerate(ords):
+            gt, _ = self.ctx.download_global_transforms(int(sc.light_row[o]), 1, want_changed=False)
+            frusta[i] = abi.host_point_light_frusta(gt[0], float(sc.light_range[o]), shadow_map_near_z)
+        layers = None if sc.light_layers is None else sc.light_layers[ords]
+        self.ctx.set_shadow_lights(ords, frusta, layers, lod_origin_range_index)
+        self.ctx.run_shadow_culling()
+
     def enable_visible_diff(self, enabled=True):
         """have the CULL stage also produce each view's added / removed rows
         (RenderVisibleEntitiesClass::update_cpu_culled_entities, bevy_render/src/view/visibility/mod.rs:194-249)."""

@@ -328,6 +328,36 @@ B200VIS_API int32_t b200vis_download_visible_diff(b200vis_ctx *ctx, uint32_t vie
  * lists on the device.  NULL, 0, NULL removes the sink. */
 B200VIS_API int32_t b200vis_set_visible_diff_sink(b200vis_ctx *ctx, uint32_t *rows, uint32_t capacity, uint32_t *counts);
 
+/* ---- shadow-view culling of point lights -------------------------------------------------------
+ * check_point_light_mesh_visibility (crates/bevy_light/src/lib.rs:517-668): for every point light that is in some
+ * view's VisibleEntities and has shadow maps enabled, every shadow-casting mesh is tested against the light's range
+ * sphere (Sphere::intersects_obb, bevy_camera/src/primitives.rs:219-226) and the six CubemapFrusta
+ * (Frustum::intersects_obb with near and far planes, :272-294); survivors are set_visible() and land in the light's
+ * six sorted CubemapVisibleEntities lists.
+ *   caster[count]   1 = the row is in visible_entity_query (Mesh3d, no NotShadowCaster, no DirectionalLight);
+ *                   NoCpuCulling, InheritedVisibility, RenderLayers, Aabb, NoFrustumCulling, VisibilityRange come from
+ *                   the columns already resident
+ *   shadow lights   ordinals into the b200vis_set_lights arrays (the lights with shadow_maps_enabled), their
+ *                   CubemapFrusta frusta[n][6 faces][6 half spaces][4] (update_point_light_frusta,
+ *                   bevy_light/src/point_light.rs:212-265; b200vis_host_point_light_frusta computes them for hosts
+ *                   without glam), RenderLayers (NULL = default), and the bit of get_shadow_lod_origin's view in the
+ *                   VisibleEntityRanges masks (-1 = none).  Whether a light is in some view's VisibleEntities is
+ *                   decided on the device from the per-view sets of the visible-diff bookkeeping (which
+ *                   b200vis_upload_shadow_casters switches on: call it before the frame's CULL stage); the light's
+ *                   sphere is its row's GlobalTransform translation and its range.
+ *   b200vis_run_shadow_culling  after b200vis_run(.. CULL ..) of the same frame; also folds set_visible() into the
+ *                   ViewVisibility column / change flags (download them afterwards).
+ *   lists           rows ascending by Entity::to_bits() (sort_unstable, lib.rs:650-661); list_capacity rows per list
+ *                   are kept (0 = max_entities). */
+B200VIS_API int32_t b200vis_upload_shadow_casters(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const uint8_t *caster);
+B200VIS_API int32_t b200vis_set_shadow_lights(b200vis_ctx *ctx, uint32_t n_lights, const uint32_t *light_ordinals, const float *frusta,
+                                              const uint64_t *layer_mask, int32_t lod_origin_range_index, uint32_t list_capacity);
+B200VIS_API int32_t b200vis_run_shadow_culling(b200vis_ctx *ctx);
+B200VIS_API int32_t b200vis_download_shadow_visible(b200vis_ctx *ctx, uint32_t shadow_light, uint32_t face, uint32_t *rows,
+                                                    uint32_t capacity, uint32_t *count);
+/* update_point_light_frusta for one light (no GPU needed): light_gt12 as in upload_global_transforms */
+B200VIS_API void b200vis_host_point_light_frusta(const float *light_gt12, float range, float shadow_map_near_z, float frusta[6][6][4]);
+
 /* ---- the two per-entity passes that feed the cull kernel's flag byte ---------------------------
  * (a) check_visibility_ranges (crates/bevy_camera/src/visibility/range.rs:230-284).  With the VisibilityRange columns
  *     resident -- start_end[count][2] = (start_margin.start, end_margin.end), the two values is_visible_at_all reads

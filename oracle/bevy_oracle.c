@@ -340,25 +340,31 @@ ORC_API void orc_perspective_infinite_reverse_rh(float fov_y, float aspect, floa
 }
 /* CameraProjection::compute_frustum (projection.rs:72-80) +
  * ViewFrustum::from_clip_from_world_custom_far (view_frustum.rs:51-62, 92-107) */
-ORC_API void orc_compute_frustum(const float *clip_from_view16, const float *camera_gt12, float far, float *planes24) {
-    m4 cfv = m4_load(clip_from_view16);
-    aff cam = aff_load(camera_gt12), inv = aff_inverse(&cam);
-    m4 vfw = m4_from_aff(&inv);
-    m4 cfw = m4_mul(&cfv, &vfw);
-    v4 r0 = m4_row(&cfw, 0), r1 = m4_row(&cfw, 1), r2 = m4_row(&cfw, 2), r3 = m4_row(&cfw, 3);
-    v4 hs[6];
+/* GlobalTransform::back (global_transform.rs): matrix3 * Vec3::Z, normalised */
+static inline v3 gt_back(const aff *g) {
+    v3 zt = m3_mul_v3(&g->m, V3(0.0f, 0.0f, 1.0f));   /* matrix3 * Vec3::Z */
+    float len_recip = 1.0f / v3_length(zt);
+    return v3_scale(zt, len_recip);
+}
+/* ViewFrustum::from_clip_from_world_custom_far (view_frustum.rs:51-62, 92-107) */
+static inline void view_frustum_custom_far(const m4 *cfw, v3 view_translation, v3 view_backward, float far, v4 *hs) {
+    v4 r0 = m4_row(cfw, 0), r1 = m4_row(cfw, 1), r2 = m4_row(cfw, 2), r3 = m4_row(cfw, 3);
     hs[0] = half_space_new(v4_add(r3, r0));
     hs[1] = half_space_new(v4_sub(r3, r0));
     hs[2] = half_space_new(v4_add(r3, r1));
     hs[3] = half_space_new(v4_sub(r3, r1));
     hs[4] = half_space_new(v4_add(r3, r2));
-    /* custom far: view_translation - far * view_backward; back() = matrix3.z_axis normalised
-     * (GlobalTransform::back -> Dir3::new_unchecked(self.0.matrix3.z_axis.normalize())) */
-    v3 zt = m3_mul_v3(&cam.m, V3(0.0f, 0.0f, 1.0f));   /* matrix3 * Vec3::Z */
-    float len_recip = 1.0f / v3_length(zt);
-    v3 back = v3_scale(zt, len_recip);
-    v3 far_center = v3_sub(cam.t, v3_scale(back, far));
-    hs[5] = half_space_new(v3_extend(back, -v3_dot(back, far_center)));
+    /* custom far: the plane through view_translation - far * view_backward facing view_backward */
+    v3 far_center = v3_sub(view_translation, v3_scale(view_backward, far));
+    hs[5] = half_space_new(v3_extend(view_backward, -v3_dot(view_backward, far_center)));
+}
+ORC_API void orc_compute_frustum(const float *clip_from_view16, const float *camera_gt12, float far, float *planes24) {
+    m4 cfv = m4_load(clip_from_view16);
+    aff cam = aff_load(camera_gt12), inv = aff_inverse(&cam);
+    m4 vfw = m4_from_aff(&inv);
+    m4 cfw = m4_mul(&cfv, &vfw);
+    v4 hs[6];
+    view_frustum_custom_far(&cfw, cam.t, gt_back(&cam), far, hs);
     memcpy(planes24, hs, sizeof hs);
 }
 
@@ -541,6 +547,17 @@ static inline int entity_visible_in_view(uint32_t r, const float *gt, const floa
  *                  (0xFFFFFFFF for an inactive view: its VisibleEntities are left untouched,
  *                  visibility/mod.rs:780-782)
  */
+/* mark_newly_hidden_entities_invisible (visibility/mod.rs:908-918).  The light-visibility systems
+ * (check_point_light_mesh_visibility, bevy_light/src/lib.rs:517) run between check_visibility and this pass and OR
+ * into the same bytes: orc_set_defer_mark_newly_hidden(1) makes orc_cull stop before it so a test can run them. */
+static int g_defer_mark_newly_hidden = 0;
+ORC_API void orc_set_defer_mark_newly_hidden(int on) { g_defer_mark_newly_hidden = on; }
+ORC_API void orc_mark_newly_hidden(uint32_t n, const uint8_t *flags, uint8_t *vv, uint8_t *vv_changed) {
+    for (uint32_t r = 0; r < n; ++r) {
+        if (flags[r] & F_NO_CPU_CULLING) continue;
+        if ((vv[r] & 3u) == 2u) { vv[r] = 0; vv_changed[r] = 1; }
+    }
+}
 ORC_API int orc_cull(uint32_t n, const float *gt, const float *bounds, const uint8_t *flags,
                      const uint64_t *layer_mask, const uint32_t *range_mask, const uint8_t *class_mask,
                      const uint64_t *entity_bits, uint8_t *vv, uint8_t *vv_changed,
@@ -578,10 +595,7 @@ ORC_API int orc_cull(uint32_t n, const float *gt, const float *bounds, const uin
         visible_count[v] = cnt;
     }
     /* mark_newly_hidden_entities_invisible */
-    for (uint32_t r = 0; r < n; ++r) {
-        if (flags[r] & F_NO_CPU_CULLING) continue;
-        if ((vv[r] & 3u) == 2u) { vv[r] = 0; vv_changed[r] = 1; }
-    }
+    if (!g_defer_mark_newly_hidden) orc_mark_newly_hidden(n, flags, vv, vv_changed);
     free(items); free(old);
     return 0;
 }
@@ -930,4 +944,121 @@ ORC_API float orc_logf(float x) { return logf(x); }
 ORC_API float orc_powf(float x, float y) { return powf(x, y); }
 ORC_API uint32_t orc_view_z_to_z_slice(const float *factors2, uint32_t z_slices, float view_z, int ortho) {
     return view_z_to_z_slice(factors2, z_slices, view_z, ortho);
+}
+
+
+/* ------------------------------------------------------------------------ */
+/* shadow-view culling for point lights                   */
+/* ------------------------------------------------------------------------ */
+/* Quat::from_rotation_axes (glam f32/scalar quat.rs; Quat::from_mat3 forwards the three columns).
+ * PARITY UNPINNED: restated from glam's published algorithm, no reference vector exercises it. */
+static v4 quat_from_rotation_axes(v3 xa, v3 ya, v3 za) {
+    float m00 = xa.x, m01 = xa.y, m02 = xa.z, m10 = ya.x, m11 = ya.y, m12 = ya.z, m20 = za.x, m21 = za.y, m22 = za.z;
+    if (m22 <= 0.0f) {                       /* x^2 + y^2 >= z^2 + w^2 */
+        float dif10 = m11 - m00, omm22 = 1.0f - m22;
+        if (dif10 <= 0.0f) {                 /* x^2 >= y^2 */
+            float four_xsq = omm22 - dif10, inv4x = 0.5f / sqrtf(four_xsq);
+            return V4(four_xsq * inv4x, (m01 + m10) * inv4x, (m02 + m20) * inv4x, (m12 - m21) * inv4x);
+        } else {                             /* y^2 >= x^2 */
+            float four_ysq = omm22 + dif10, inv4y = 0.5f / sqrtf(four_ysq);
+            return V4((m01 + m10) * inv4y, four_ysq * inv4y, (m12 + m21) * inv4y, (m20 - m02) * inv4y);
+        }
+    } else {                                 /* z^2 + w^2 >= x^2 + y^2 */
+        float sum10 = m11 + m00, opm22 = 1.0f + m22;
+        if (sum10 <= 0.0f) {                 /* z^2 >= w^2 */
+            float four_zsq = opm22 - sum10, inv4z = 0.5f / sqrtf(four_zsq);
+            return V4((m02 + m20) * inv4z, (m12 + m21) * inv4z, four_zsq * inv4z, (m01 - m10) * inv4z);
+        } else {                             /* w^2 >= z^2 */
+            float four_wsq = opm22 + sum10, inv4w = 0.5f / sqrtf(four_wsq);
+            return V4((m12 - m21) * inv4w, (m20 - m02) * inv4w, (m01 - m10) * inv4w, four_wsq * inv4w);
+        }
+    }
+}
+/* Transform::IDENTITY.looking_at(target, up) -> look_to (transform.rs:475-484); Dir3::new = v / |v|,
+ * try_normalize = v * (1 / |v|) -- both exact for the axis-aligned CUBE_MAP_FACES */
+static v4 look_to_rotation(v3 direction, v3 up_in) {
+    float dl = v3_length(direction), ul = v3_length(up_in);
+    v3 back = v3_neg(v3_div_s(direction, dl));
+    v3 up = v3_div_s(up_in, ul);
+    v3 right = v3_cross(up, back);
+    right = v3_scale(right, 1.0f / v3_length(right));
+    up = v3_cross(back, right);
+    return quat_from_rotation_axes(right, up, back);
+}
+/* update_point_light_frusta (crates/bevy_light/src/point_light.rs:212-265) for one light: planes[6][6][4] */
+ORC_API void orc_point_light_frusta(const float *light_gt12, float range, float shadow_map_near_z, float *planes) {
+    static const float faces[6][6] = {   /* CUBE_MAP_FACES target, up (bevy_camera/src/primitives.rs:348-379) */
+        {1, 0, 0, 0, 1, 0}, {-1, 0, 0, 0, 1, 0}, {0, 1, 0, 0, 0, 1}, {0, -1, 0, 0, 0, -1}, {0, 0, -1, 0, 1, 0}, {0, 0, 1, 0, 1, 0}};
+    aff light = aff_load(light_gt12);
+    float cfv16[16];
+    orc_perspective_infinite_reverse_rh(1.57079632679489661923f, 1.0f, shadow_map_near_z, cfv16);   /* FRAC_PI_2 */
+    m4 cfv = m4_load(cfv16);
+    v3 view_backward = gt_back(&light);
+    for (int f = 0; f < 6; ++f) {
+        v4 q = look_to_rotation(V3(faces[f][0], faces[f][1], faces[f][2]), V3(faces[f][3], faces[f][4], faces[f][5]));
+        /* world_from_view = Transform::from_translation(t) * view_rotation: rotation IDENTITY * q = q, scale 1, translation t */
+        float trs[10] = {light.t.x, light.t.y, light.t.z, q.x, q.y, q.z, q.w, 1.0f, 1.0f, 1.0f};
+        aff wfv = aff_from_trs(trs), inv = aff_inverse(&wfv);
+        m4 vfw = m4_from_aff(&inv);
+        m4 cfw = m4_mul(&cfv, &vfw);
+        v4 hs[6];
+        view_frustum_custom_far(&cfw, light.t, view_backward, range, hs);
+        memcpy(planes + (size_t)f * 24, hs, sizeof hs);
+    }
+}
+/* check_point_light_mesh_visibility, point-light half (crates/bevy_light/src/lib.rs:517-668).
+ * caster[r] != 0: the row is in visible_entity_query (Mesh3d, no NotShadowCaster, no DirectionalLight);
+ * NoCpuCulling comes from flags.  The caller passes the lights that are in some view's VisibleEntities and have
+ * shadow_maps_enabled (:561-580): light_sphere[L][4] = GlobalTransform translation, range; frusta[L][6][6][4].
+ * lod_origin_index: bit of get_shadow_lod_origin's view in the range masks, -1 = none / not in the views map.
+ * vv / vv_changed: in the state check_visibility left them (before mark_newly_hidden).
+ * Out: visible_rows[(l*6+face)*n ...] ascending by entity bits (sort_unstable, :650-661), visible_count[L*6]. */
+ORC_API int orc_check_point_light_mesh_visibility(uint32_t n, const float *gt, const float *bounds, const uint8_t *flags,
+                                                  const uint8_t *caster, const uint64_t *layer_mask, const uint32_t *range_mask,
+                                                  int lod_origin_index, const uint64_t *entity_bits, uint8_t *vv,
+                                                  uint8_t *vv_changed, uint32_t n_lights, const float *light_sphere,
+                                                  const uint64_t *light_layers, const float *frusta, uint32_t *visible_rows,
+                                                  uint32_t *visible_count) {
+    sort_item *items = (sort_item *)malloc((size_t)(n ? n : 1) * 6 * sizeof(sort_item));
+    if (!items) return 1;
+    for (uint32_t l = 0; l < n_lights; ++l) {
+        uint32_t cnt[6] = {0, 0, 0, 0, 0, 0};
+        const uint64_t view_mask = light_layers ? light_layers[l] : 1ull;
+        const float *ls = light_sphere + (size_t)l * 4;
+        v4 hs[6][6]; memcpy(hs, frusta + (size_t)l * 144, sizeof hs);
+        for (uint32_t r = 0; r < n; ++r) {
+            const uint8_t f = flags[r];
+            if (!caster[r] || (f & F_NO_CPU_CULLING)) continue;
+            if (!(f & F_INHERITED_VISIBLE)) continue;
+            if (!(view_mask & (layer_mask ? layer_mask[r] : 1ull))) continue;
+            if ((f & F_HAS_VIS_RANGE) && range_mask &&
+                (lod_origin_index < 0 || lod_origin_index > 31 || !((range_mask[r] >> lod_origin_index) & 1u)))
+                continue;
+            int face_vis[6] = {1, 1, 1, 1, 1, 1};
+            if (f & F_HAS_AABB) {   /* (Some(aabb), Some(transform)) */
+                const float *b = bounds + (size_t)r * 6;
+                const int no_fc = (f & F_NO_FRUSTUM_CULLING) != 0;
+                if (!no_fc && !orc_sphere_intersects_obb(ls, ls[3], b, b + 3, gt + (size_t)r * 12)) continue;
+                aff a = aff_load(gt + (size_t)r * 12);
+                for (int k = 0; k < 6; ++k)
+                    face_vis[k] = no_fc || frustum_intersects_obb(hs[k], V3(b[0], b[1], b[2]), V3(b[3], b[4], b[5]), &a, 1, 1);
+            }
+            for (int k = 0; k < 6; ++k) {
+                if (!face_vis[k]) continue;
+                if (!(vv[r] & 1u)) {   /* set_visible (visibility/mod.rs:292-306) */
+                    if (!(vv[r] & 2u)) vv_changed[r] = 1;
+                    vv[r] |= 1u;
+                }
+                items[(size_t)k * n + cnt[k]].key = entity_bits[r]; items[(size_t)k * n + cnt[k]].row = r; cnt[k]++;
+            }
+        }
+        for (int k = 0; k < 6; ++k) {
+            qsort(items + (size_t)k * n, cnt[k], sizeof(sort_item), cmp_sort_item);
+            uint32_t *dst = visible_rows + ((size_t)l * 6 + k) * n;
+            for (uint32_t i = 0; i < cnt[k]; ++i) dst[i] = items[(size_t)k * n + i].row;
+            visible_count[l * 6 + k] = cnt[k];
+        }
+    }
+    free(items);
+    return 0;
 }

@@ -125,6 +125,15 @@ def _declare(l):
     l.orc_powf.argtypes = [C.c_float, C.c_float]
     l.orc_view_z_to_z_slice.restype = C.c_uint32
     l.orc_view_z_to_z_slice.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.c_float, C.c_int]
+    l.orc_set_defer_mark_newly_hidden.argtypes = [C.c_int]
+    l.orc_mark_newly_hidden.argtypes = [C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+    l.orc_point_light_frusta.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_float, C.POINTER(C.c_float)]
+    l.orc_check_point_light_mesh_visibility.restype = C.c_int
+    l.orc_check_point_light_mesh_visibility.argtypes = [
+        C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8),
+        C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint8),
+        C.POINTER(C.c_uint8), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_float),
+        C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     if hasattr(l, "orc_update_cpu_culled_entities"):   # bevy_oracle_next.c (not part of the MT baseline library)
         U64P, U32P, U8P = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
         l.orc_sort_pairs_by_main.argtypes = [U64P, U64P, C.c_uint32]
@@ -428,3 +437,44 @@ def visibility_propagate(parent, vis, inherited, changed_rows, removed_rows=()):
                                         _p(ch, C.c_uint8), len(cr), _p(cr, C.c_uint32), len(rr), _p(rr, C.c_uint32))
     assert rc == 0
     return inh, ch
+
+
+# ---- N3: shadow-view culling for point lights (bevy_oracle.c) ----------------------------------------
+def set_defer_mark_newly_hidden(on):
+    """Make cull() stop before mark_newly_hidden_entities_invisible so the light-visibility systems can run in between."""
+    lib().orc_set_defer_mark_newly_hidden(int(bool(on)))
+
+
+def mark_newly_hidden(flags, vv, vv_changed):
+    flags = np.ascontiguousarray(flags, np.uint8)
+    assert vv.dtype == np.uint8 and vv_changed.dtype == np.uint8 and vv.flags.c_contiguous and vv_changed.flags.c_contiguous
+    lib().orc_mark_newly_hidden(len(flags), _p(flags, C.c_uint8), _p(vv, C.c_uint8), _p(vv_changed, C.c_uint8))
+
+
+def point_light_frusta(light_gt12, light_range, shadow_map_near_z=0.1):
+    """update_point_light_frusta for one light -> [6 faces][6 half spaces][4]."""
+    g = _f32(light_gt12)
+    out = np.zeros((6, 6, 4), np.float32)
+    lib().orc_point_light_frusta(_p(g, C.c_float), float(light_range), float(shadow_map_near_z), _p(out, C.c_float))
+    return out
+
+
+def check_point_light_mesh_visibility(gt, bounds, flags, caster, entity_bits, vv, vv_changed, light_sphere, frusta,
+                                      layer_mask=None, range_mask=None, lod_origin_index=-1, light_layers=None):
+    """check_point_light_mesh_visibility (point lights): vv / vv_changed are updated in place; returns the per
+    (light, face) sorted row lists as a list of 6-lists."""
+    gt, bounds = _f32(gt), _f32(bounds)
+    flags = np.ascontiguousarray(flags, np.uint8); caster = np.ascontiguousarray(caster, np.uint8)
+    bits = np.ascontiguousarray(entity_bits, np.uint64)
+    ls = _f32(light_sphere).reshape(-1, 4); fr = _f32(frusta).reshape(-1, 6, 6, 4)
+    n, L = len(flags), len(ls)
+    lm = None if layer_mask is None else np.ascontiguousarray(layer_mask, np.uint64)
+    rm = None if range_mask is None else np.ascontiguousarray(range_mask, np.uint32)
+    ll = None if light_layers is None else np.ascontiguousarray(light_layers, np.uint64)
+    rows = np.zeros((max(L, 1) * 6, max(n, 1)), np.uint32); cnt = np.zeros(max(L, 1) * 6, np.uint32)
+    rc = lib().orc_check_point_light_mesh_visibility(
+        n, _p(gt, C.c_float), _p(bounds, C.c_float), _p(flags, C.c_uint8), _p(caster, C.c_uint8), _p(lm, C.c_uint64),
+        _p(rm, C.c_uint32), int(lod_origin_index), _p(bits, C.c_uint64), _p(vv, C.c_uint8), _p(vv_changed, C.c_uint8), L,
+        _p(ls, C.c_float), _p(ll, C.c_uint64), _p(fr, C.c_float), _p(rows, C.c_uint32), _p(cnt, C.c_uint32))
+    assert rc == 0
+    return [[rows[l * 6 + k, :cnt[l * 6 + k]].copy() for k in range(6)] for l in range(L)]

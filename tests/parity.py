@@ -32,11 +32,31 @@ class OracleWorld:
         self.tchanged[:] = 0
         if getattr(sc, "range_se", None) is not None:   # check_visibility_ranges runs before the cull
             sc.range_mask = orc.check_visibility_ranges(self.gt, sc.bounds, sc.flags, sc.range_se, sc.range_use_aabb, sc.range_view_pos)
-        vv_changed, lists = orc.cull(self.gt, sc.bounds, sc.flags, sc.class_mask, sc.entity_bits, self.vv,
-                                     views_planes, view_layers=sc.view_layers,
-                                     view_flags=view_flags if view_flags is not None else sc.view_flags,
-                                     layer_mask=sc.layer_mask, range_mask=sc.range_mask,
-                                     view_range_index=sc.view_range_index, mt=mt)
+        shadow = getattr(sc, "shadow_lights", None) is not None
+        orc.set_defer_mark_newly_hidden(shadow)   # the light-visibility systems run before mark_newly_hidden_entities_invisible
+        try:
+            vv_changed, lists = orc.cull(self.gt, sc.bounds, sc.flags, sc.class_mask, sc.entity_bits, self.vv,
+                                         views_planes, view_layers=sc.view_layers,
+                                         view_flags=view_flags if view_flags is not None else sc.view_flags,
+                                         layer_mask=sc.layer_mask, range_mask=sc.range_mask,
+                                         view_range_index=sc.view_range_index, mt=mt)
+        finally:
+            orc.set_defer_mark_newly_hidden(False)
+        if shadow:   # check_point_light_mesh_visibility for the shadow lights some view's VisibleEntities hold
+            cur = [l if l is not None else self.last_lists[v] for v, l in enumerate(lists)]
+            listed = np.unique(np.concatenate(cur)) if len(cur) else np.zeros(0, np.uint32)
+            sel = [int(o) for o in sc.shadow_lights if sc.light_row[o] in set(listed.tolist())]
+            rows = sc.light_row[sel]
+            sphere = np.concatenate([self.gt[rows, 9:12], sc.light_range[sel, None]], 1).astype(np.float32).reshape(-1, 4)
+            frusta = np.stack([orc.point_light_frusta(self.gt[r], sc.light_range[o], sc.shadow_near_z) for r, o in zip(rows, sel)]) \
+                if len(sel) else np.zeros((0, 6, 6, 4), np.float32)
+            ll = None if sc.light_layers is None else np.ascontiguousarray(sc.light_layers[sel], np.uint64)
+            sh = orc.check_point_light_mesh_visibility(self.gt, sc.bounds, sc.flags, sc.shadow_caster, sc.entity_bits, self.vv,
+                                                       vv_changed, sphere, frusta, layer_mask=sc.layer_mask,
+                                                       range_mask=sc.range_mask, lod_origin_index=sc.shadow_lod_origin,
+                                                       light_layers=ll)
+            self.shadow_result = dict(zip(sel, sh))
+            orc.mark_newly_hidden(sc.flags, self.vv, vv_changed)
         clusters = []
         if cluster and len(sc.light_row):
             vis = np.nonzero(self.vv[sc.light_row] & 1)[0]
@@ -61,6 +81,8 @@ def compare_frame(pipe, world, frame_no, cluster=True, check_gt=True, run_device
     gt_changed, vv_changed, lists, clusters = world.frame(planes, cluster=cluster)
     if run_device:
         pipe.run_frame()
+        if getattr(sc, "shadow_lights", None) is not None:
+            pipe.check_point_light_mesh_visibility(sc.shadow_lights, sc.shadow_near_z, sc.shadow_lod_origin)
     tag = f"[{sc.name} frame {frame_no}]"
     if check_gt:
         gt, ch = pipe.ctx.download_global_transforms(0, n)
@@ -89,6 +111,14 @@ def compare_frame(pipe, world, frame_no, cluster=True, check_gt=True, run_device
             assert len(g_a) == len(a_r) and (g_a == a_r).all(), f"{tag} view {v}: added rows differ ({len(g_a)} vs {len(a_r)})"
             assert len(g_r) == len(r_r) and (g_r == r_r).all(), f"{tag} view {v}: removed rows differ ({len(g_r)} vs {len(r_r)})"
     world.last_lists = [l if l is not None else world.last_lists[v] for v, l in enumerate(lists)]
+    if getattr(sc, "shadow_lights", None) is not None:
+        for i, o in enumerate(sc.shadow_lights):
+            want6 = world.shadow_result.get(int(o))
+            for face in range(6):
+                got = pipe.ctx.download_shadow_visible(i, face)
+                want = want6[face] if want6 is not None else np.zeros(0, np.uint32)   # light in no view's list: not processed
+                assert len(got) == len(want) and (got == want).all(), \
+                    f"{tag} shadow light {o} face {face}: CubemapVisibleEntities differ ({len(got)} vs {len(want)})"
     if getattr(sc, "range_se", None) is not None:
         got = pipe.ctx.download_visibility_ranges(0, n)
         assert (got == sc.range_mask).all(), f"{tag} VisibleEntityRanges masks differ on rows {np.nonzero(got != sc.range_mask)[0][:8]}"

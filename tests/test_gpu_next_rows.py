@@ -201,3 +201,64 @@ def test_n4_visibility_propagation_matches_the_change_driven_system(seed):
             compare_frame(pipe, world, step)
     finally:
         pipe.close()
+
+
+# ---- N3: check_point_light_mesh_visibility (shadow-view culling of point lights) --------------------------------
+@pytest.mark.parametrize("seed,shuffle", [(8, True), (9, False)])
+def test_n3_point_light_shadow_culling(seed, shuffle):
+    sc = _random_scene(seed, n_roots=90, n_lights=20, shuffle_entities=shuffle)
+    rng = np.random.default_rng(seed)
+    n = sc.n
+    sc.shadow_lights = np.sort(rng.choice(len(sc.light_row), 9, replace=False)).astype(np.uint32)   # shadow_maps_enabled
+    sc.shadow_caster = (rng.random(n) < 0.8).astype(np.uint8)
+    sc.shadow_caster[sc.light_row] = 0                       # lights are not Mesh3d
+    sc.shadow_near_z = 0.1
+    sc.shadow_lod_origin = 0                                 # view 0 is the shadow LOD origin
+    pipe = bb.VisibilityPipeline(sc)
+    world = OracleWorld(sc, True)
+    try:
+        pipe.ctx.upload_shadow_casters(0, sc.shadow_caster)
+        seen = 0
+        for f in range(5):
+            if f:
+                scenes.advance_cameras(sc, 0.15)
+                rows = np.unique(rng.integers(0, n, n // 25)).astype(np.uint32)
+                sc.trs[rows, 0:3] += rng.uniform(-2, 2, (len(rows), 3)).astype(np.float32)
+                pipe.ctx.upload_transforms_scattered(rows, sc.trs[rows])
+                world.tchanged[rows] = 1
+                sc.view_flags = [bb.VIEW_ACTIVE, 0 if f == 3 else bb.VIEW_ACTIVE, bb.VIEW_ACTIVE]
+            pipe.update_views()
+            compare_frame(pipe, world, f)
+            seen += sum(len(l) for six in world.shadow_result.values() for l in six)
+            assert len(world.shadow_result) > 0
+        assert seen > 100       # the lists are not trivially empty
+    finally:
+        pipe.close()
+
+
+def test_n3_rows_only_lights_see_become_visible():
+    """A mesh outside every camera frustum but inside a shadow light's range: ViewVisibility comes from set_visible()
+    of the light pass alone, with the change flag firing on the hidden -> visible transition only."""
+    sc = scenes.forest(n_trees=80, levels=5, n_lights=6)
+    sc.trs[sc.roots, 0:3] *= np.float32(0.12)                # pull the trees inside the lights' reach
+    sc.light_range[:] = 45.0
+    sc.bounds[sc.light_row, 3] = 45.0
+    sc.shadow_lights = np.arange(6, dtype=np.uint32)
+    sc.shadow_caster = np.ones(sc.n, np.uint8); sc.shadow_caster[sc.light_row] = 0
+    sc.shadow_near_z = 0.1
+    sc.shadow_lod_origin = -1
+    sc.cameras = sc.cameras[:1]                              # one camera: most meshes are outside its frustum
+    pipe = bb.VisibilityPipeline(sc)
+    world = OracleWorld(sc, True)
+    try:
+        pipe.ctx.upload_shadow_casters(0, sc.shadow_caster)
+        for f in range(4):
+            if f:
+                scenes.advance_cameras(sc, 0.3)
+            pipe.update_views()
+            compare_frame(pipe, world, f)
+        vv, _ = pipe.ctx.download_view_visibility(0, sc.n)
+        cam = pipe.ctx.download_visible(0)
+        assert (vv & 1).sum() > len(cam)                     # rows visible to lights only
+    finally:
+        pipe.close()

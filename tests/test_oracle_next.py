@@ -199,3 +199,81 @@ def test_n4_change_driven_equals_fixpoint_on_random_edits(seed):
         inh, ch = _run(parent, vis, inh, np.sort(rows))
         assert np.array_equal(inh, fixpoint(parent, vis))
         assert np.array_equal(ch != 0, inh != before)
+
+
+# ---- N3 ---------------------------------------------------------------------------------------------
+def test_n3_cubemap_frusta_host_equals_oracle_and_faces_look_along_their_axes():
+    """update_point_light_frusta (bevy_light/src/point_light.rs:212-265): the product's host helper and the oracle are
+    separate restatements and must agree bit for bit; each face sees a point 5 units along its own axis only."""
+    from bevy_b200 import abi
+    rng = np.random.default_rng(0)
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, -1], [0, 0, 1]], np.float32)   # CUBE_MAP_FACES
+    for i in range(40):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        trs = np.concatenate([rng.uniform(-50, 50, 3), q, rng.uniform(0.5, 2, 3)]).astype(np.float32)
+        gt = orc.affine_from_trs(trs)
+        a = orc.point_light_frusta(gt, 17.5, 0.1)
+        b = abi.host_point_light_frusta(gt, 17.5, 0.1)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert np.allclose(np.linalg.norm(a[..., :3], axis=-1), 1.0, atol=1e-6)
+        for f in range(6):
+            for k in range(6):
+                p = gt[9:12] + 5 * axes[k]
+                assert orc.intersects_sphere(a[f], p, 0.01, True) == (f == k)
+            # the far plane is shared by the six faces: `range` behind the light along the light's own back direction
+            assert np.array_equal(a[f, 5], a[0, 5])
+
+
+def test_n3_point_light_mesh_visibility_against_a_plain_loop():
+    rng = np.random.default_rng(11)
+    n, L = 500, 5
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    trs = np.concatenate([rng.uniform(-30, 30, (n, 3)), q, rng.uniform(0.5, 2, (n, 3))], 1).astype(np.float32)
+    gt = np.stack([orc.affine_from_trs(t) for t in trs])
+    bounds = np.concatenate([rng.normal(size=(n, 3)) * 0.3, rng.uniform(0.2, 2.0, (n, 3))], 1).astype(np.float32)
+    flags = (orc.F_INHERITED_VISIBLE * (rng.random(n) < 0.9) | orc.F_HAS_AABB * (rng.random(n) < 0.85)
+             | orc.F_NO_FRUSTUM_CULLING * (rng.random(n) < 0.05) | orc.F_HAS_VIS_RANGE * (rng.random(n) < 0.3)
+             | orc.F_NO_CPU_CULLING * (rng.random(n) < 0.05)).astype(np.uint8)
+    caster = (rng.random(n) < 0.8).astype(np.uint8)
+    layers = rng.integers(1, 4, n).astype(np.uint64)
+    range_mask = rng.integers(0, 4, n).astype(np.uint32)
+    bits = rng.permutation(n).astype(np.uint64) + 100
+    vv0 = rng.choice([0, 2], n).astype(np.uint8)             # after reset_view_visibility: only the "previous" bit
+    lpos = rng.uniform(-20, 20, (L, 3)).astype(np.float32); lrange = rng.uniform(8, 30, L).astype(np.float32)
+    llayers = rng.integers(1, 4, L).astype(np.uint64)
+    ident = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)
+    frusta = np.stack([orc.point_light_frusta(np.concatenate([ident, lpos[l]]), lrange[l], 0.1) for l in range(L)])
+    vv, ch = vv0.copy(), np.zeros(n, np.uint8)
+    got = orc.check_point_light_mesh_visibility(gt, bounds, flags, caster, bits, vv, ch, np.concatenate([lpos, lrange[:, None]], 1),
+                                                frusta, layer_mask=layers, range_mask=range_mask, lod_origin_index=1,
+                                                light_layers=llayers)
+    want_vis = np.zeros(n, bool)
+    total = 0
+    for l in range(L):
+        lists = [[] for _ in range(6)]
+        for r in range(n):
+            f = int(flags[r])
+            if not caster[r] or f & orc.F_NO_CPU_CULLING or not f & orc.F_INHERITED_VISIBLE:
+                continue
+            if not int(llayers[l]) & int(layers[r]):
+                continue
+            if f & orc.F_HAS_VIS_RANGE and not (range_mask[r] >> 1) & 1:
+                continue
+            faces = range(6)
+            if f & orc.F_HAS_AABB:
+                no_fc = bool(f & orc.F_NO_FRUSTUM_CULLING)
+                if not no_fc and not orc.sphere_intersects_obb(lpos[l], lrange[l], bounds[r, :3], bounds[r, 3:], gt[r]):
+                    continue
+                faces = [k for k in range(6) if no_fc or orc.intersects_obb(frusta[l, k], bounds[r, :3], bounds[r, 3:], gt[r], True, True)]
+            for k in faces:
+                lists[k].append(r); want_vis[r] = True
+        for k in range(6):
+            want = np.array(sorted(lists[k], key=lambda r: bits[r]), np.uint32)
+            assert np.array_equal(got[l][k], want)
+            total += len(want)
+    assert total > 50
+    assert np.array_equal((vv & 1) != 0, want_vis)
+    assert np.array_equal(ch != 0, want_vis & (vv0 == 0))    # change fires on hidden -> visible only
+    orc.mark_newly_hidden(flags, vv, ch)
+    gone = ((vv0 == 2) & ~want_vis & ((flags & orc.F_NO_CPU_CULLING) == 0))
+    assert np.array_equal(vv[gone], np.zeros(gone.sum(), np.uint8)) and ch[gone].all()
