@@ -230,6 +230,38 @@ def measure_next_rows(torch, bb, pipe, ctx, scene, stream, value_step, live_step
         out[f"N2_cluster_bindings_{name}"] = {"cluster_ms": c_ms, "cluster_only_ms": cluster_ms, "n_offsets_view0": no, "n_indices_view0": ni}
     ctx.set_cluster_bindings(0)
 
+    # N3: shadow-view culling, 16 of the lights cast shadows, every tree mesh is a caster (CUDA events on the launching stream)
+    from bevy_b200 import abi as _abi
+    S = min(16, len(scene.light_row))
+    if S:
+        caster = np.ones(n, np.uint8); caster[scene.light_row] = 0
+        ctx.upload_shadow_casters(0, caster)
+        for i in range(W):
+            value_step(i)                                  # the view sets are recorded from here on
+        ctx.join()
+        ords = np.arange(S, dtype=np.uint32)
+        frusta = np.zeros((S, 6, 6, 4), np.float32)
+        for i in range(S):
+            gt, _ = ctx.download_global_transforms(int(scene.light_row[i]), 1, want_changed=False)
+            frusta[i] = _abi.host_point_light_frusta(gt[0], float(scene.light_range[i]), 0.1)
+        ctx.set_shadow_lights(ords, frusta, None, -1, 1 << 16)
+        ctx.run_shadow_culling()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        reps = 20
+        ev[0].record(stream)
+        for _ in range(reps):
+            ctx.run_shadow_culling()
+        ev[1].record(stream)
+        torch.cuda.synchronize()
+        sh_ms = ev[0].elapsed_time(ev[1]) / reps
+        pairs = sum(len(ctx.download_shadow_visible(i, f)) for i in range(S) for f in range(6))
+        out["N3_point_light_shadow_culling"] = {
+            "ms": sh_ms, "shadow_lights": S, "caster_rows": int(caster.sum()), "row_light_pairs_per_s": S * float(caster.sum()) / (sh_ms * 1e-3),
+            "visible_row_face_pairs": int(pairs),
+            "note": "select + cull (one thread per row, loop over the lights) + list expansion; 72 B/row read once, so the stage is compute-bound in the number of (row, light) sphere tests"}
+        ctx.enable_visible_diff(False)
+
     # N4b: visibility_propagate_system over all rows (CUDA events on the launching stream)
     rng = np.random.default_rng(7)
     vis = rng.choice([0, 0, 0, 1, 2], n).astype(np.uint8)

@@ -21,6 +21,12 @@
  *     - translation-only propagation    crates/bevy_transform/src/systems.rs:855-1096
  *     - ViewVisibility 5-frame lifecycle crates/bevy_camera/src/visibility/mod.rs:1314-1448
  *     - cluster grid tiling invariants  crates/bevy_light/src/cluster/test.rs:5-54
+ *     - sphere vs OBB known answers      crates/bevy_camera/src/primitives.rs:614-685 (also pins the
+ *       pre-test of the SURVEY 8(f) N3 shadow-view culling at the end of this file)
+ *   N3's CubemapFrusta derivation (update_point_light_frusta -> Transform::look_to -> glam
+ *   Quat::from_rotation_axes) has no reference vector: "parity unpinned" for the frusta VALUES; the
+ *   culling that consumes them is pinned through intersects_obb / Sphere::intersects_obb above and
+ *   cross-checked against a plain loop (tests/test_oracle_next.py).
  *   Cluster MEMBERSHIP (which light lands in which cluster) has no reference
  *   test at all: for that part the oracle says "parity unpinned" and is
  *   cross-checked by a brute-force superset/subset test instead

@@ -57,6 +57,11 @@ extern "C" {
     fn b200vis_upload_visibility_ranges(ctx: *mut b200vis_ctx, first: u32, count: u32, start_end: *const f32, use_aabb: *const u8) -> i32;
     fn b200vis_set_visibility_range_views(ctx: *mut b200vis_ctx, n_views: u32, positions: *const f32) -> i32;
     fn b200vis_download_visibility_ranges(ctx: *mut b200vis_ctx, first: u32, count: u32, mask: *mut u32) -> i32;
+    fn b200vis_upload_shadow_casters(ctx: *mut b200vis_ctx, first: u32, count: u32, caster: *const u8) -> i32;
+    fn b200vis_set_shadow_lights(ctx: *mut b200vis_ctx, n: u32, light_ordinals: *const u32, frusta: *const f32, layers: *const u64,
+                                 lod_origin_range_index: i32, list_capacity: u32) -> i32;
+    fn b200vis_run_shadow_culling(ctx: *mut b200vis_ctx) -> i32;
+    fn b200vis_download_shadow_visible(ctx: *mut b200vis_ctx, shadow_light: u32, face: u32, rows: *mut u32, cap: u32, count: *mut u32) -> i32;
     fn b200vis_enable_visible_diff(ctx: *mut b200vis_ctx, enabled: i32) -> i32;
     fn b200vis_download_visible_diff(ctx: *mut b200vis_ctx, view: u32, added: *mut u32, added_cap: u32, n_added: *mut u32,
                                      removed: *mut u32, removed_cap: u32, n_removed: *mut u32) -> i32;
