@@ -398,6 +398,16 @@ __device__ __forceinline__ void issue_tile_loads(const Rows &R, const Tile &t, T
     }
 }
 
+#ifdef B200VIS_TILE_TIMING
+// debug build only (tools/tile_timing.py): per-CTA phase timestamps of the tile kernel, read back through
+// b200vis_debug_tile_timing; not compiled into the product library
+__device__ unsigned long long g_tile_timing[8192 * 16];
+#define TT(slot) do { if (lr == 0 && blockIdx.x < 8192u) g_tile_timing[blockIdx.x * 16u + (slot)] = clock64(); } while (0)
+#define TTW(slot) do { if (lr == 224u && blockIdx.x < 8192u) g_tile_timing[blockIdx.x * 16u + (slot)] = clock64(); } while (0)
+#else
+#define TT(slot) do { } while (0)
+#define TTW(slot) do { } while (0)
+#endif
 template <bool PROP, bool CULL, bool SIMPLE>
 __global__ void __launch_bounds__(kTileRows, 4)
 k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, const __grid_constant__ CullViews cvw,
@@ -411,7 +421,9 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
     }
     __syncthreads();
     // launched with programmatic stream serialization: everything above overlapped the previous kernel's tail
+    TT(0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    TT(1);
     uint32_t t = blockIdx.x;
     if (lr == 0 && t < n_tiles) issue_tile_loads<PROP, CULL>(R, tiles[t], s.st[0], &s.bar[0]);
     uint32_t n_gt_total = 0, n_vv_total = 0;
@@ -419,6 +431,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         const uint32_t sidx = it & 1u;
         const Tile tile = tiles[t];
         mbar_wait(&s.bar[sidx], (it >> 1) & 1u);
+        if (it == 1) { TT(2); }
         TileStage &S = s.st[sidx];
         const uint32_t off = tile.base & 15u;
         const uint32_t li = off + lr;                 // index into the staged window
@@ -458,6 +471,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
                 __syncthreads();
                 dirty = s.dirty[lr];
             }
+            if (it == 1) { TT(3); }    // dirty phase done
             const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
             const uint32_t my_level = (active && !(topo & T_DETACHED)) ? depth : 0xFFFFFFFFu;
             if (active && (topo & T_DETACHED) && has_children) s.pst[lr] = 0;
@@ -478,6 +492,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
                 if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
                 if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
             }
+            if (it == 1) { TT(4); }    // local affine + level 0 done
             for (uint32_t lvl = 1; lvl < tile.n_levels; ++lvl) {
                 if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) __syncwarp(); else __syncthreads();
                 if (my_level == lvl) {
@@ -492,9 +507,11 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
                     }
                     if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
                 }
+                if (it == 1 && lvl <= 7) { TT(4 + lvl); }   // thread 0 after the level's barrier and (for level-lvl rows) work
             }
             if (active && tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
         }
+        if (it == 1) { TT(12); }   // walk done
         // Prefetch the NEXT tile into the other stage.  That stage was last read by the previous tile's bulk store,
         // issued most of an iteration ago, so the wait below is (almost always) already satisfied: putting the
         // prefetch here instead of at the top of the loop keeps the store drain off every warp's critical path.
@@ -614,7 +631,9 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         // end of tile: everybody is done with this stage; count changes; write the tile's matrices back
         n_gt_total += (PROP && changed) ? 1u : 0u;      // per-thread tallies, reduced once at the end of the kernel
         n_vv_total += vv_changed ? 1u : 0u;
+        if (it == 1) { TT(13); }   // cull done
         const int any_gt = __syncthreads_or(PROP && changed);
+        if (it == 1) { TT(15); }
         if (lr == 0) {
             if (PROP && any_gt) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
@@ -626,6 +645,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         }
     }
     if (lr == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    TT(14);
     // block-reduce the per-thread tallies (warp shuffle, then one shared-memory atomic per warp)
     __shared__ uint32_t s_cnt[2];
     if (lr < 2) s_cnt[lr] = 0;
@@ -1761,3 +1781,10 @@ void launch_pack_state(cudaStream_t st, const Rows &R, uint32_t first, uint32_t 
 }
 
 }  // namespace b200vis
+
+#ifdef B200VIS_TILE_TIMING
+extern "C" __attribute__((visibility("default"))) int b200vis_debug_tile_timing(unsigned long long *out, unsigned n_ctas) {
+    if (n_ctas > 8192u) n_ctas = 8192u;
+    return (int)cudaMemcpyFromSymbol(out, b200vis::g_tile_timing, (size_t)n_ctas * 16 * sizeof(unsigned long long));
+}
+#endif
