@@ -239,11 +239,11 @@ def measure_next_rows(torch, bb, pipe, ctx, scene, stream, value_step, live_step
         for i in range(W):
             value_step(i)                                  # the view sets are recorded from here on
         ctx.join()
-        ords = np.arange(S, dtype=np.uint32)
+        ords = np.sort(np.argsort(-scene.light_range)[:S]).astype(np.uint32)     # the S lights with the largest range
         frusta = np.zeros((S, 6, 6, 4), np.float32)
-        for i in range(S):
-            gt, _ = ctx.download_global_transforms(int(scene.light_row[i]), 1, want_changed=False)
-            frusta[i] = _abi.host_point_light_frusta(gt[0], float(scene.light_range[i]), 0.1)
+        for i, o in enumerate(ords):
+            gt, _ = ctx.download_global_transforms(int(scene.light_row[o]), 1, want_changed=False)
+            frusta[i] = _abi.host_point_light_frusta(gt[0], float(scene.light_range[o]), 0.1)
         ctx.set_shadow_lights(ords, frusta, None, -1, 1 << 16)
         ctx.run_shadow_culling()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -537,6 +537,13 @@ def main():
             peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
         else:
             peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+        # DRAM bytes of one launch of the dominant kernel, from the committed `ncu --set full` capture of this workload
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "tile_kernel_traffic.json")
+        if os.path.exists(tp) and world == 1:
+            tj = json.load(open(tp))
+            if tj.get("entities") == n:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         algo_bytes = n * ALGO_BYTES_PER_ENTITY + 4 * visible_pairs
         achieved = algo_bytes / (tile_ms_avg * 1e-3) / 1e9
         line = {
@@ -555,7 +562,7 @@ def main():
                     "note": "GlobalTransforms stay device-resident; the GPU writes stats, sorted visible lists and cluster lists into pinned host memory (result sink), one stream sync per frame"},
             "gpu_launches": 6 * K, "host_enqueue_ms_per_step": host_enqueue_ms,
             "roofline": {"bound": "hbm", "kernel": "k_propagate_cull", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel_ms": tile_ms_avg, "expand_ms": expand_ms_avg, "cluster_ms": cluster_ms_avg,
                          "gt_changed_rows_last_frame": int(sanity.gt_changed_count),
                          "algorithmic_bytes_per_entity": ALGO_BYTES_PER_ENTITY, "note": EXTRA_BYTES_NOTE},
