@@ -148,6 +148,8 @@ _SIGNATURES = {
     "b200vis_set_visible_diff_sink": (C.c_int32, [_vp, _vp, C.c_uint32, _vp]),
     "b200vis_comm_unique_id": (C.c_int32, [_vp]),
     "b200vis_comm_init": (C.c_int32, [_vp, _vp]),
+    "b200vis_p2p_export": (C.c_int32, [_vp, _vp]),
+    "b200vis_p2p_import": (C.c_int32, [_vp, _vp]),
     "b200vis_cluster_exchange_bytes": (C.c_int32, [_vp, _P(C.c_size_t)]),
     "b200vis_set_cluster_exchange_buffers": (C.c_int32, [_vp, _vp, _vp]),
     "b200vis_host_perspective": (None, [C.c_float, C.c_float, C.c_float, _vp]),
@@ -519,6 +521,17 @@ class Context:
         s.cluster_capacity = 0 if cluster_indices is None else cluster_indices.shape[1]
         self._sink = (s, visible_rows, cluster_offsets, cluster_indices)
         self._check(self._lib.b200vis_set_result_sink(self._h, C.byref(s)))
+
+    def p2p_export(self):
+        """CUDA IPC handle (64 bytes) of this rank's gathered buffer."""
+        buf = np.zeros(64, np.uint8)
+        self._check(self._lib.b200vis_p2p_export(self._h, _ptr(buf)))
+        return buf
+
+    def p2p_import(self, handles):
+        """handles: uint8 [world, 64], rank-major (as all-gathered by the host)."""
+        h = np.ascontiguousarray(handles, np.uint8).reshape(-1, 64)
+        self._check(self._lib.b200vis_p2p_import(self._h, _ptr(h)))
 
     @staticmethod
     def comm_unique_id():

@@ -62,13 +62,13 @@ struct b200vis_ctx {
     // stream while frame f+1's tile pass already runs on the main stream (masks / counters / constants are
     // double or triple buffered by frame number).
     cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_tile = nullptr, ev_side[2] = {nullptr, nullptr}, ev_pub = nullptr;
+    cudaEvent_t ev_tile = nullptr, ev_side[3] = {nullptr, nullptr, nullptr}, ev_expand[2] = {nullptr, nullptr}, ev_pub = nullptr;
     bool pub_pending = false;           // a publish_visible copy is in flight on the side stream
     bool pipeline = true, side_pending = false;
     // a frame whose tail was started (expand + cluster assign on the side stream) but whose CLUSTER_LISTS stage is
     // still to come in a later b200vis_run call (multi-GPU: the host all-gathers the slabs in between)
     bool tail_open = false; uint32_t open_frame = 0; const FrameConsts *open_fc = nullptr;
-    float4 *d_light_snap = nullptr;     // [2][max_lights]
+    float4 *d_light_snap = nullptr;     // [3][max_lights]
     uint32_t *d_tag_flag = nullptr;     // 1 if every light row carries its ordinal (k_tag_lights)
     bool lights_tag_dirty = true, lights_tagged = false;
     std::string err;
@@ -96,7 +96,7 @@ struct b200vis_ctx {
     cudaEvent_t ring_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
     int ring_next = 0;
     size_t blob_cap = 0;
-    uint8_t *d_blob2[2] = {nullptr, nullptr};   // live-mode device blobs, slot = frame % 2
+    uint8_t *d_blob2[3] = {nullptr, nullptr, nullptr};   // live-mode device blobs, slot = frame % 3
     uint8_t *d_blob = nullptr;          // the one the current frame uses
     FrameConsts *d_consts = nullptr;    // == d_blob
     bool consts_dirty = true;
@@ -136,6 +136,9 @@ struct b200vis_ctx {
     double step_t[6] = {0, 0, 0, 0, 0, 0}; uint64_t step_n = 0;   // B200VIS_STEP_TRACE: host time per phase of b200vis_step
     void *nccl_comm = nullptr;          // b200vis_comm_init
     uint32_t *d_gather = nullptr;       // [world][slab] when the library owns the exchange
+    // peer-memory exchange (b200vis_p2p_export / _import): [2][world][slab] + flags [2][world], mapped into every rank
+    uint32_t *d_xbuf = nullptr; size_t xbuf_flag_offset = 0; void *peer_map[8] = {}; bool p2p_ready = false;
+    uint32_t *d_push_done = nullptr;
     b200vis_cluster_feedback auto_fb[kMaxViews]{};   // b200vis_step: last frame's Clusters feedback
 
     // staging for AoS <-> SoA conversion
@@ -181,7 +184,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     Rows &r = ctx->rows;
     void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
-                   ctx->d_tiles, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_light_snap, ctx->d_tag_flag,
+                   ctx->d_tiles, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_light_snap, ctx->d_tag_flag,
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage,
                    ctx->diff.prev, ctx->diff.words, ctx->diff.chunk, ctx->diff.lists, ctx->diff.count,
@@ -206,11 +209,15 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
                 1e6 * ctx->step_t[3] / ctx->step_n, 1e6 * ctx->step_t[4] / ctx->step_n, 1e6 * ctx->step_t[5] / ctx->step_n);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->d_gather) cudaFree(ctx->d_gather);
+    for (uint32_t r = 0; r < 8; ++r) if (ctx->peer_map[r] && r != ctx->cl.rank) cudaIpcCloseMemHandle(ctx->peer_map[r]);
+    if (ctx->d_xbuf) cudaFree(ctx->d_xbuf);
+    if (ctx->d_push_done) cudaFree(ctx->d_push_done);
     for (auto &r : ctx->recorded) if (r.dev) cudaFree(r.dev);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->ev_tile) cudaEventDestroy(ctx->ev_tile);
     if (ctx->ev_pub) cudaEventDestroy(ctx->ev_pub);
     for (cudaEvent_t e : ctx->ev_side) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_expand) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -251,7 +258,7 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         CU(dalloc(&ctx->d_tiles, ctx->tiles_cap));
         // worst case tables: every view with three (kMaxClusters+1)-entry plane tables + kMaxClusters thresholds
         ctx->blob_cap = sizeof(FrameConsts) + V * (3 * (size_t)(kMaxClusters + 1) * 16 + (size_t)kMaxClusters * 4);
-        CU(dalloc(&ctx->d_blob2[0], ctx->blob_cap)); CU(dalloc(&ctx->d_blob2[1], ctx->blob_cap));
+        CU(dalloc(&ctx->d_blob2[0], ctx->blob_cap)); CU(dalloc(&ctx->d_blob2[1], ctx->blob_cap)); CU(dalloc(&ctx->d_blob2[2], ctx->blob_cap));
         ctx->d_blob = ctx->d_blob2[0];
         ctx->d_consts = reinterpret_cast<FrameConsts *>(ctx->d_blob);
         {   // the tail kernels are small and latency-bound: give their CTAs priority over the bulk tile pass
@@ -262,6 +269,7 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         CU(cudaEventCreateWithFlags(&ctx->ev_tile, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_pub, cudaEventDisableTiming));
         for (cudaEvent_t &e : ctx->ev_side) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (cudaEvent_t &e : ctx->ev_expand) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         { const char *e = getenv("B200VIS_PIPELINE"); if (e && e[0] == '0') ctx->pipeline = false; }
         for (int i = 0; i < b200vis_ctx::kRing; ++i) {
             CU(cudaMallocHost(&ctx->h_ring[i], ctx->blob_cap));
@@ -279,7 +287,7 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         CU(cudaMallocHost(&ctx->h_stats, sizeof(DevStats)));
         // lights + clusters
         const size_t Lm = std::max<uint32_t>(cfg->max_lights, 1);
-        CU(dalloc(&ctx->d_light_snap, 2 * Lm));
+        CU(dalloc(&ctx->d_light_snap, 3 * Lm));
         CU(dalloc(&ctx->d_tag_flag, 1));
         CU(dalloc(&ctx->d_light_row, Lm)); CU(dalloc(&ctx->d_light_range, Lm)); CU(dalloc(&ctx->d_light_layers, Lm));
         ClusterBufs &cl = ctx->cl;
@@ -793,8 +801,9 @@ extern "C" int32_t b200vis_collect_stage_times_ms(b200vis_ctx *ctx, float *tile_
     for (int i = 0; i < ctx->prof_count; ++i) {
         float t = 0;
         CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][0], ctx->prof_ev[i][1])); s[0] += t;   // tile pass (main stream)
-        CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][2], ctx->prof_ev[i][3])); s[1] += t;   // visible-list expansion
-        CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][3], ctx->prof_ev[i][4])); s[2] += t;   // cluster kernels
+        CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][5], ctx->prof_ev[i][3])); s[1] += t;   // visible-list expansion
+        CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][3], ctx->prof_ev[i][4])); s[2] += t;   // cluster kernels ...
+        CU(cudaEventElapsedTime(&t, ctx->prof_ev[i][2], ctx->prof_ev[i][5])); s[2] += t;   // ... incl. assign + exchange when issued first
     }
     if (tile_ms) *tile_ms = (float)s[0];
     if (expand_ms) *expand_ms = (float)s[1];
@@ -825,6 +834,50 @@ extern "C" int32_t b200vis_comm_init(b200vis_ctx *ctx, const uint8_t id[B200VIS_
     if (!ctx->d_gather) CU(dalloc(&ctx->d_gather, (size_t)ctx->cl.world * ctx->slab_bytes / 4));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->cl.send = ctx->d_slab; ctx->cl.recv = ctx->d_gather;
+    return B200VIS_OK;
+}
+// Peer-memory exchange: export allocates this rank's gathered buffer and returns its CUDA IPC handle; the host gathers the
+// handles of all ranks by any means; import maps the other ranks' buffers.  From then on b200vis_run(B200VIS_STAGE_ALL)
+// pushes the slab into every rank's buffer with plain NVLink stores (k_slab_push) instead of calling ncclAllGather.
+extern "C" int32_t b200vis_p2p_export(b200vis_ctx *ctx, uint8_t handle[B200VIS_P2P_HANDLE_BYTES]) {
+    CHECK_CTX_JOIN();
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200VIS_P2P_HANDLE_BYTES, "IPC handle size");
+    if (!handle) return fail(ctx, B200VIS_ERR_INVALID_ARG, "p2p_export: null");
+    if (ctx->cl.world <= 1 || ctx->cl.world > 8) return fail(ctx, B200VIS_ERR_INVALID_ARG, "p2p_export: world_size must be 2..8");
+    if (!ctx->d_xbuf) {
+        const size_t data_words = (size_t)2 * ctx->cl.world * ctx->slab_bytes / 4;
+        ctx->xbuf_flag_offset = data_words;
+        void *p = nullptr;   // plain cudaMalloc: the allocation must be exportable through cudaIpcGetMemHandle
+        CU(cudaMalloc(&p, (data_words + 64) * 4));
+        CU(cudaMemset(p, 0, (data_words + 64) * 4));
+        ctx->d_xbuf = static_cast<uint32_t *>(p);
+        CU(dalloc(&ctx->d_push_done, 1));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_xbuf));
+    memcpy(handle, &h, sizeof h);
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_p2p_import(b200vis_ctx *ctx, const uint8_t *handles) {
+    CHECK_CTX_JOIN();
+    if (!handles) return fail(ctx, B200VIS_ERR_INVALID_ARG, "p2p_import: null");
+    if (!ctx->d_xbuf) return fail(ctx, B200VIS_ERR_NOT_READY, "p2p_import: call b200vis_p2p_export first");
+    for (uint32_t r = 0; r < ctx->cl.world; ++r) {
+        if (r == ctx->cl.rank) { ctx->peer_map[r] = ctx->d_xbuf; continue; }
+        if (ctx->peer_map[r]) continue;
+        cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)r * B200VIS_P2P_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, B200VIS_ERR_UNSUPPORTED, "p2p_import: cudaIpcOpenMemHandle(rank %u): %s", r, cudaGetErrorString(e)); }
+        ctx->peer_map[r] = p;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t r = 0; r < ctx->cl.world; ++r) {
+        ctx->cl.peer[r] = static_cast<uint32_t *>(ctx->peer_map[r]);
+        ctx->cl.peer_flags[r] = ctx->cl.peer[r] + ctx->xbuf_flag_offset;
+    }
+    ctx->cl.send = ctx->d_slab;
+    ctx->p2p_ready = true;
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_cluster_exchange_bytes(const b200vis_ctx *ctx, size_t *slab_bytes) {
@@ -890,21 +943,25 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         if (ctx->have_sink)
             launch_publish_clusters(tail, ctx->open_fc, cl, ctx->sink_off_d, ctx->sink_idx_d, ctx->sink.cluster_capacity, ctx->d_stats,
                                     ctx->sink_stats_d, ctx->open_frame % 3u, ctx->open_frame + 1u, ctx->cfg.max_views);
-        CU(cudaEventRecord(ctx->ev_side[ctx->open_frame & 1u], tail));
+        CU(cudaEventRecord(ctx->ev_side[ctx->open_frame % 3u], tail));
         ctx->side_pending = true; ctx->tail_open = false;
         CU(cudaGetLastError());
         return B200VIS_OK;
     }
     // Pipelined mode: a whole frame (or a frame up to the cluster exchange).  The tail of frame f (expand + cluster) goes to
-    // the side stream and overlaps frame f+1's tile pass; frame f+2's tile pass waits for it (it reuses frame f's buffers).
+    // the side stream and overlaps the tile passes of frames f+1 AND f+2: frame f+2's tile pass only waits for frame f's
+    // list EXPANSION (it reuses frame f's visible masks and counters, two / three copies), frame f+3's for frame f's whole
+    // tail (frame constants and light snapshots: three copies).  So a tail may take up to two frame periods -- which is what
+    // the multi-GPU case needs, where the tail contains the cluster exchange and waits on other GPUs.
     const bool pipelined = ctx->pipeline && do_prop && do_cull && has_assign && !ctx->tail_open;
     const uint32_t frame = ctx->frame;
     const uint32_t cslot = frame % 3u, mslot = frame & 1u;
     if (pipelined) {
-        if (ctx->side_pending && frame >= 2) CU(cudaStreamWaitEvent(st, ctx->ev_side[mslot], 0));   // tail of frame f-2
+        if (ctx->side_pending && frame >= 2) CU(cudaStreamWaitEvent(st, ctx->ev_expand[mslot], 0));   // expansion of frame f-2
+        if (ctx->side_pending && frame >= 3) CU(cudaStreamWaitEvent(st, ctx->ev_side[cslot], 0));     // tail of frame f-3
     } else {
         if (ctx->tail_open) {   // an abandoned open tail: close it so that the event chain stays consistent
-            CU(cudaEventRecord(ctx->ev_side[ctx->open_frame & 1u], ctx->side_stream));
+            CU(cudaEventRecord(ctx->ev_side[ctx->open_frame % 3u], ctx->side_stream));
             ctx->side_pending = true; ctx->tail_open = false;
         }
         const int32_t rc = join_side(ctx); if (rc) return rc;
@@ -914,7 +971,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     if (ctx->replay_slot >= 0) {   // constants already resident in HBM (recorded earlier): no host work, no copy
         fc = reinterpret_cast<const FrameConsts *>(ctx->recorded[ctx->replay_slot].dev);
     } else {
-        ctx->d_blob = ctx->d_blob2[mslot];          // the side stream may still read the other copy
+        ctx->d_blob = ctx->d_blob2[cslot];          // the side stream may still read the other two copies
         ctx->d_consts = reinterpret_cast<FrameConsts *>(ctx->d_blob);
         ctx->consts_dirty = ctx->consts_dirty || pipelined;   // each copy must be current
         const int32_t rc = flush_consts(ctx); if (rc) return rc;
@@ -952,7 +1009,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
             ctx->lights_tagged = ok != 0; ctx->lights_tag_dirty = false;
         }
         tile_snap = ctx->lights_tagged && tile_kernel_is_tma();
-        if (tile_snap) R.light_snap = ctx->d_light_snap + (size_t)mslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
+        if (tile_snap) R.light_snap = ctx->d_light_snap + (size_t)cslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
     }
     cudaEvent_t *pe = (ctx->profiling && ctx->prof_count < b200vis_ctx::kProfFrames) ? ctx->prof_ev[ctx->prof_count++] : nullptr;
     if (pe) CU(cudaEventRecord(pe[0], st));
@@ -970,7 +1027,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     lights.snap = nullptr;
     cudaStream_t tail = st;
     if (pipelined) {
-        lights.snap = ctx->d_light_snap + (size_t)mslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
+        lights.snap = ctx->d_light_snap + (size_t)cslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
         if (!tile_snap) launch_snapshot_lights(st, R, lights, const_cast<float4 *>(lights.snap));
         if (pe) CU(cudaEventRecord(pe[1], st));
         CU(cudaEventRecord(ctx->ev_tile, st));
@@ -978,9 +1035,34 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         CU(cudaStreamWaitEvent(tail, ctx->ev_tile, 0));
     } else if (pe) CU(cudaEventRecord(pe[1], st));
     if (pe) CU(cudaEventRecord(pe[2], tail));
+    // Multi-GPU: the cluster exchange is the one step of the tail that waits on other GPUs, so it goes FIRST -- assign and
+    // the slab push / all-gather are issued before the visible-list expansion (they do not depend on it), and the peers'
+    // data travels while this rank expands its lists.
+    const bool exchange_first = has_assign && has_lists && cl.world > 1;
+    auto issue_assign_and_exchange = [&]() -> int32_t {
+        if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
+            launch_cluster_assign(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+        if (has_assign && has_lists && cl.world > 1) {
+            if (ctx->p2p_ready) {
+                // peer stores over NVLink + stamps; k_cluster_lists waits for every rank's stamp of this frame
+                cl.p2p = 1; cl.xparity = mslot; cl.stamp = frame + 1u;
+                cl.recv = ctx->d_xbuf + (size_t)mslot * cl.world * (ctx->slab_bytes / 4);
+                launch_slab_push(tail, fc, cl, ctx->d_push_done, ctx->cfg.max_views);
+            } else {
+                // the ONE data-path collective: rank-major all-gather of the fixed-size cluster x light slabs over NVLink
+                if (!ctx->nccl_comm) return fail(ctx, B200VIS_ERR_NOT_READY, "run(ALL) with world_size > 1 needs b200vis_p2p_import or b200vis_comm_init (or run ASSIGN and LISTS separately around your own all-gather)");
+                const int nrc = g_nccl.AllGather(cl.send, const_cast<uint32_t *>(cl.recv), ctx->slab_bytes / 4, kNcclUint32, ctx->nccl_comm, tail);
+                if (nrc) return fail(ctx, B200VIS_ERR_CUDA, "ncclAllGather: %s", g_nccl.GetErrorString(nrc));
+            }
+        }
+        return B200VIS_OK;
+    };
+    if (exchange_first) { const int32_t rc = issue_assign_and_exchange(); if (rc) return rc; }
+    if (pe) CU(cudaEventRecord(pe[5], tail));
     if (do_cull && ctx->pub_pending) { CU(cudaStreamWaitEvent(tail, ctx->ev_pub, 0)); ctx->pub_pending = false; }   // lists are rewritten
     if (do_cull) {
         launch_expand_visible(tail, vb, ctx->diff_on ? ctx->diff : DiffBufs{}, R.row_of_rank, fc, ctx->d_stats, cslot, ctx->n, ctx->cfg.max_views);
+        if (pipelined) CU(cudaEventRecord(ctx->ev_expand[mslot], tail));   // this frame's masks / counters are free again
         if (ctx->diff_on && ctx->diff_sink_rows_d)
             launch_publish_visible_diff(tail, vb, ctx->diff, ctx->diff_sink_rows_d, ctx->diff_sink_cap, ctx->diff_sink_counts_d,
                                         active_consts(ctx).n_views, ctx->cfg.max_views);
@@ -998,14 +1080,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         if (!pipelined) { CU(cudaEventRecord(ctx->ev_pub, pub)); ctx->pub_pending = true; }
     }
     if (pe) CU(cudaEventRecord(pe[3], tail));
-    if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
-        launch_cluster_assign(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
-    if (has_assign && has_lists && cl.world > 1) {
-        // the ONE data-path collective: rank-major all-gather of the fixed-size cluster x light slabs over NVLink
-        if (!ctx->nccl_comm) return fail(ctx, B200VIS_ERR_NOT_READY, "run(ALL) with world_size > 1 needs b200vis_comm_init (or run ASSIGN and LISTS separately around your own all-gather)");
-        const int nrc = g_nccl.AllGather(cl.send, const_cast<uint32_t *>(cl.recv), ctx->slab_bytes / 4, kNcclUint32, ctx->nccl_comm, tail);
-        if (nrc) return fail(ctx, B200VIS_ERR_CUDA, "ncclAllGather: %s", g_nccl.GetErrorString(nrc));
-    }
+    if (!exchange_first) { const int32_t rc = issue_assign_and_exchange(); if (rc) return rc; }
     if (stages & B200VIS_STAGE_CLUSTER_LISTS)
         launch_cluster_lists(tail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if ((stages & B200VIS_STAGE_CLUSTER_LISTS) && ctx->bind.mode)
@@ -1015,7 +1090,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
                                 ctx->sink.cluster_capacity, ctx->d_stats, ctx->sink_stats_d, cslot, frame + (do_cull ? 1u : 0u), ctx->cfg.max_views);
     if (pe) CU(cudaEventRecord(pe[4], tail));
     if (pipelined) {
-        if (has_lists) { CU(cudaEventRecord(ctx->ev_side[mslot], tail)); ctx->side_pending = true; }
+        if (has_lists) { CU(cudaEventRecord(ctx->ev_side[cslot], tail)); ctx->side_pending = true; }
         else { ctx->tail_open = true; ctx->open_frame = frame; ctx->open_fc = fc; }
     }
     CU(cudaGetLastError());

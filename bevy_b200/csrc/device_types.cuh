@@ -143,6 +143,11 @@ struct ClusterBufs {
     const float *blob;       // frame blob base: FrameConsts, then the packed per-view tables
     uint32_t *offsets;       // [V][kMaxClusters+1]
     uint32_t *indices;       // [V][index_cap]
+    // peer-memory exchange (b200vis_p2p_import): every rank's gathered buffer [2 parities][world][slab] as mapped into this
+    // process, the flag words behind it [2][world], and this frame's parity / stamp.  p2p == 0: recv was filled by a collective.
+    uint32_t p2p, xparity, stamp, pad;
+    uint32_t *peer[8];
+    uint32_t *peer_flags[8];
 };
 
 // check_point_light_mesh_visibility (bevy_light/src/lib.rs:517-668) for the shadow-casting point lights

@@ -1117,6 +1117,49 @@ k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBu
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kListBlocks = kMaxClusters / 1024;
 
+// ------------------------------------------------------------------------------------------
+// Kernel 3b: the cluster exchange as peer stores.  Instead of an ncclAllGather of the cluster x light slabs, every rank
+// WRITES the words of its slab that are in use straight into every rank's gathered buffer over NVLink (buffers of the
+// other processes are mapped through CUDA IPC), then publishes a per-(parity, rank) stamp with system-scope release
+// semantics; k_cluster_lists spins on the stamps of all ranks (acquire) before it reads.  Two parities: a rank can be
+// at most one frame ahead of the slowest one, because its next-but-one push comes after its own list build, which
+// waited for everybody's stamp of the frame in between.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256)
+k_slab_push(const FrameConsts *__restrict__ fc, ClusterBufs cb, uint32_t *__restrict__ done) {
+    const uint32_t v = blockIdx.y;
+    const size_t slab_words = (size_t)cb.max_views * cb.words * kMaxClusters;
+    if (v < fc->n_views && fc->cviews[v].enabled) {
+        const uint32_t nc = fc->cviews[v].n_clusters;
+        const uint32_t *mine = cb.send + (size_t)v * cb.words * kMaxClusters;
+        const size_t dst0 = ((size_t)cb.xparity * cb.world + cb.rank) * slab_words + (size_t)v * cb.words * kMaxClusters;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cb.words * nc; i += gridDim.x * blockDim.x) {
+            const uint32_t w = i / nc, c = i - w * nc;
+            const uint32_t val = mine[(size_t)w * kMaxClusters + c];
+            for (uint32_t r = 0; r < cb.world; ++r) cb.peer[r][dst0 + (size_t)w * kMaxClusters + c] = val;
+        }
+    }
+    // last CTA out publishes the stamp: every CTA's stores are fenced at system scope before it counts itself in
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = gridDim.x * gridDim.y;
+        if (atomicAdd(done, 1u) == total - 1u) {
+            *done = 0;
+            __threadfence_system();
+            for (uint32_t r = 0; r < cb.world; ++r) st_release_sys(cb.peer_flags[r] + cb.xparity * cb.world + cb.rank, cb.stamp);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__restrict__ stats) {
     __shared__ uint32_t s_warp[32];
@@ -1126,6 +1169,19 @@ k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__
     const DevClusterView &cv = fc->cviews[v];
     uint32_t *offsets = cb.offsets + (size_t)v * (kMaxClusters + 1);
     const uint32_t nc = cv.enabled ? cv.n_clusters : 0u;
+    if (cb.p2p) {   // wait until every rank's slab of this frame has landed in this rank's gathered buffer
+        // (spinning here, in the 16 CTAs of the list build, measured faster than a separate one-warp wait kernel: one
+        // scheduling delay on a GPU that is busy with the next frame's tile pass instead of two)
+        if (t < cb.world) {
+            const uint32_t *flag = cb.peer_flags[cb.rank] + cb.xparity * cb.world + t;
+            uint32_t spins = 0;
+            while ((int32_t)(ld_acquire_sys(flag) - cb.stamp) < 0) {
+                __nanosleep(64);
+                if (++spins > (1u << 26)) { stats->cl_overflow[v] = 2u; break; }   // a peer never arrived: report, do not hang
+            }
+        }
+        __syncthreads();
+    }
     if (blk == 0 && t == 0 && !cv.enabled) { offsets[0] = 0; stats->cl_overflow[v] = 0; }
     const size_t rank_stride = (size_t)cb.max_views * cb.words * kMaxClusters;
     const uint32_t *base = cb.recv + (size_t)v * cb.words * kMaxClusters;
@@ -1174,7 +1230,7 @@ k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__
     // the CTA holding the last cluster publishes the total; CTA 0 publishes / re-arms the accumulators
     if (nc && c == nc - 1) {
         offsets[nc] = pos;
-        stats->cl_overflow[v] = pos > cb.index_cap ? 1u : 0u;
+        if (!(cb.p2p && stats->cl_overflow[v] == 2u)) stats->cl_overflow[v] = pos > cb.index_cap ? 1u : 0u;
     }
     if (blk == 0 && t == 0) {
         stats->cl_index_count[v] = stats->cl_acc_index[v]; stats->cl_acc_index[v] = 0;
@@ -1733,6 +1789,9 @@ void launch_tag_lights(cudaStream_t st, const Rows &R, const Lights &L, uint32_t
 }
 void launch_snapshot_lights(cudaStream_t st, const Rows &R, const Lights &L, float4 *snap) {
     if (L.n) k_snapshot_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, snap);
+}
+void launch_slab_push(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, uint32_t *done, uint32_t max_views) {
+    k_slab_push<<<dim3(8, max_views), 256, 0, st>>>(fc, cb, done);
 }
 void launch_cluster_lists(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, DevStats *stats, uint32_t max_views) {
     k_cluster_lists<<<dim3(kListBlocks, max_views), 1024, 0, st>>>(fc, cb, stats);

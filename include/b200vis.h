@@ -415,6 +415,15 @@ B200VIS_API int32_t b200vis_download_cluster_bindings(b200vis_ctx *ctx, uint32_t
 #define B200VIS_COMM_ID_BYTES 128
 B200VIS_API int32_t b200vis_comm_unique_id(uint8_t id[B200VIS_COMM_ID_BYTES]);
 B200VIS_API int32_t b200vis_comm_init(b200vis_ctx *ctx, const uint8_t id[B200VIS_COMM_ID_BYTES]);
+/* Peer-memory exchange (the default in bench.py): no collective call at all.  Every rank exports the CUDA IPC handle of its
+ * gathered buffer, the host all-gathers the 64-byte handles (rank-major) by any means, every rank imports them; from then on
+ * b200vis_run(B200VIS_STAGE_ALL) has the rank WRITE its slab into every rank's buffer with plain NVLink stores right after
+ * CLUSTER_ASSIGN and publish a per-frame stamp (release, system scope); CLUSTER_LISTS spins on all ranks' stamps (acquire)
+ * before reading.  world_size 2..8, all ranks on one node with peer access.  A rank that never arrives is reported as
+ * cluster_index_overflow[v] == 2 after a few seconds instead of hanging the GPU. */
+#define B200VIS_P2P_HANDLE_BYTES 64
+B200VIS_API int32_t b200vis_p2p_export(b200vis_ctx *ctx, uint8_t handle[B200VIS_P2P_HANDLE_BYTES]);
+B200VIS_API int32_t b200vis_p2p_import(b200vis_ctx *ctx, const uint8_t *handles /* [world_size][64], rank-major */);
 B200VIS_API int32_t b200vis_cluster_exchange_bytes(const b200vis_ctx *ctx, size_t *slab_bytes);
 B200VIS_API int32_t b200vis_set_cluster_exchange_buffers(b200vis_ctx *ctx, void *send_device, void *recv_device);
 

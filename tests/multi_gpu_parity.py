@@ -30,8 +30,15 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    builtin = "--builtin" in sys.argv        # the library's own ncclAllGather instead of the host's collective
-    if builtin:
+    p2p = "--p2p" in sys.argv                # peer stores over NVLink (CUDA IPC), no collective on the data path
+    builtin = "--builtin" in sys.argv or p2p   # the library's own exchange instead of the host's collective
+    if p2p:
+        mine = torch.from_numpy(ctx.p2p_export()).to(dev)
+        handles = torch.zeros((world, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(handles.view(-1), mine)
+        ctx.p2p_import(handles.cpu().numpy())
+        dist.barrier()                       # nobody pushes before everybody has mapped everybody
+    elif builtin:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             uid.copy_(torch.from_numpy(bb.Context.comm_unique_id()))
