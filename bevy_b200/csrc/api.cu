@@ -83,6 +83,7 @@ struct b200vis_ctx {
     // plan
     Tile *d_tiles = nullptr; uint32_t tiles_cap = 0;
     std::vector<uint32_t> pass_begin;   // tile index ranges per pass: [pass_begin[p], pass_begin[p+1])
+    std::vector<uint32_t> pass_small;   // the first pass_small[p] tiles of pass p have <= 32 rows (B200VIS_SPLIT_DEEP_TILES)
     int static_opt = 1;
 
     // per-frame constants
@@ -351,7 +352,8 @@ extern "C" int32_t b200vis_set_static_transform_optimizations(b200vis_ctx *ctx, 
 // orders the tiles into passes so that a tile's out-of-tile parents are finished by an earlier
 // launch.  Forests of small trees need one pass; a tree larger than a tile needs a few.
 static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, std::vector<uint32_t> &topo,
-                          std::vector<Tile> &tiles_sorted, std::vector<uint32_t> &pass_begin) {
+                          std::vector<Tile> &tiles_sorted, std::vector<uint32_t> &pass_begin,
+                          std::vector<uint32_t> *pass_small = nullptr) {
     for (uint32_t r = 0; r < n; ++r) {
         const uint32_t p = parent[r];
         if (p == kNoParent || p == kDetached) continue;
@@ -383,6 +385,9 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
     std::vector<uint8_t> has_children(n, 0);
     for (uint32_t r = 0; r < n; ++r) if (parent[r] < n) has_children[parent[r]] = 1;
     // greedy tiling, cutting at the latest tree boundary inside a full tile
+    static int split_env = -1;
+    if (split_env < 0) { const char *e = getenv("B200VIS_SPLIT_DEEP_TILES"); split_env = (e && atoi(e)) ? 1 : 0; }
+    const bool split_deep = split_env == 1;
     std::vector<Tile> tiles;
     std::vector<uint32_t> tile_of(n);
     uint32_t start = 0;
@@ -393,9 +398,37 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
             while (c > start + 1 && parent[c] < n) --c;   // c = latest row in (start, end] that starts a tree
             if (c > start && !(parent[c] < n)) end = c;
         }
-        Tile t; t.base = start; t.n_rows = (uint16_t)(end - start); t.n_levels = 1; t.warp_sync_mask = 0xFFFFFFFFu; t.pad = 0;
-        for (uint32_t r = start; r < end; ++r) tile_of[r] = (uint32_t)tiles.size();
-        tiles.push_back(t);
+        // EXPERIMENT (B200VIS_SPLIT_DEEP_TILES=1, off by default): the hierarchy walk of a tile is a serial chain of its
+        // levels (~680 cycles per level).  When the first <= 32 rows of a deep tile are exactly its top
+        // K levels (level-ordered rows, e.g. one tree in BFS order), cut there: the top becomes a tile of its own, one pass
+        // earlier (run by 32-thread CTAs), and the bottom keeps only n_levels - K levels with external parents.
+        uint32_t cut = 0;
+        if (split_deep && end - start > 64) {
+            std::vector<uint32_t> dep(end - start, 0), cnt;
+            for (uint32_t r = start; r < end; ++r) {
+                const uint32_t p = parent[r];
+                dep[r - start] = (p < n && p >= start) ? dep[p - start] + 1 : 0;
+                if (dep[r - start] >= cnt.size()) cnt.resize(dep[r - start] + 1, 0);
+                cnt[dep[r - start]]++;
+            }
+            const uint32_t levels = (uint32_t)cnt.size();
+            if (levels >= 6) {
+                uint32_t rows_above = 0;
+                for (uint32_t K = 1; K + 2 <= levels; ++K) {       // rows with depth < K
+                    rows_above += cnt[K - 1];
+                    if (rows_above > 32) break;
+                    bool prefix = true;                              // they must be exactly the first rows_above rows
+                    for (uint32_t i = 0; i < end - start && prefix; ++i) prefix = (dep[i] < K) == (i < rows_above);
+                    if (prefix && K >= 2) cut = rows_above;
+                }
+            }
+        }
+        for (uint32_t part = 0; part < (cut ? 2u : 1u); ++part) {
+            const uint32_t b = (part == 0) ? start : start + cut, e = (cut && part == 0) ? start + cut : end;
+            Tile t; t.base = b; t.n_rows = (uint16_t)(e - b); t.n_levels = 1; t.warp_sync_mask = 0xFFFFFFFFu; t.pad = 0;
+            for (uint32_t r = b; r < e; ++r) tile_of[r] = (uint32_t)tiles.size();
+            tiles.push_back(t);
+        }
         start = end;
     }
     // topo words, in-tile depth, tile levels
@@ -428,7 +461,15 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
     for (uint32_t p = 0; p < n_pass; ++p) pass_begin[p + 1] += pass_begin[p];
     tiles_sorted.resize(tiles.size());
     std::vector<uint32_t> cursor(pass_begin.begin(), pass_begin.end() - (n_pass ? 1 : 0));
-    for (size_t i = 0; i < tiles.size(); ++i) tiles_sorted[cursor[tile_level[i]]++] = tiles[i];
+    if (pass_small) pass_small->assign(n_pass, 0);
+    // within a pass: the small tiles (<= 32 rows, only produced by the split above) first, then the rest
+    for (int small = 1; small >= 0; --small)
+        for (size_t i = 0; i < tiles.size(); ++i) {
+            const bool is_small = split_deep && tiles[i].n_rows <= 32;
+            if ((int)is_small != small) continue;
+            tiles_sorted[cursor[tile_level[i]]++] = tiles[i];
+            if (is_small && pass_small) (*pass_small)[tile_level[i]]++;
+        }
     return B200VIS_OK;
 }
 
@@ -437,8 +478,8 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     if (n && (!parent || !entity_bits)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_topology: null array");
     if (n > ctx->cfg.max_entities) return fail(ctx, B200VIS_ERR_CAPACITY, "set_topology: %u rows > max_entities %u", n, ctx->cfg.max_entities);
     std::vector<uint32_t> topo; std::vector<Tile> tiles;
-    std::vector<uint32_t> pass_begin;
-    int32_t rc = build_plan(ctx, n, parent, topo, tiles, pass_begin);
+    std::vector<uint32_t> pass_begin, pass_small;
+    int32_t rc = build_plan(ctx, n, parent, topo, tiles, pass_begin, &pass_small);
     if (rc != B200VIS_OK) return rc;
     if (tiles.size() > ctx->tiles_cap) {
         if (ctx->d_tiles) cudaFree(ctx->d_tiles);
@@ -465,6 +506,7 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
         CU(cudaMemcpy(ctx->d_row_of_rank, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
     }
     ctx->pass_begin = pass_begin;
+    ctx->pass_small = pass_small;
     ctx->rank_identity = sorted;
     ctx->n = n;
     ctx->rows.n = n;
@@ -1008,7 +1050,9 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
             CU(cudaStreamSynchronize(st));
             ctx->lights_tagged = ok != 0; ctx->lights_tag_dirty = false;
         }
-        tile_snap = ctx->lights_tagged && tile_kernel_is_tma();
+        bool any_small = false;
+        for (uint32_t x : ctx->pass_small) any_small |= x != 0;
+        tile_snap = ctx->lights_tagged && tile_kernel_is_tma() && !any_small;   // the 32-thread kernel does not publish snapshots
         if (tile_snap) R.light_snap = ctx->d_light_snap + (size_t)cslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
     }
     cudaEvent_t *pe = (ctx->profiling && ctx->prof_count < b200vis_ctx::kProfFrames) ? ctx->prof_ev[ctx->prof_count++] : nullptr;
@@ -1016,9 +1060,12 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     if (do_prop || do_cull) {
         const uint32_t tile_stages = (do_prop ? 1u : 0u) | (do_cull ? 2u : 0u);
         if (do_prop) {
-            for (uint32_t p = 0; p < n_pass; ++p)
-                launch_propagate_cull(st, R, ctx->d_tiles + ctx->pass_begin[p], ctx->pass_begin[p + 1] - ctx->pass_begin[p],
+            for (uint32_t p = 0; p < n_pass; ++p) {
+                const uint32_t ns = p < ctx->pass_small.size() ? ctx->pass_small[p] : 0u, b = ctx->pass_begin[p];
+                if (ns) launch_propagate_cull_small(st, R, ctx->d_tiles + b, ns, cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot);
+                launch_propagate_cull(st, R, ctx->d_tiles + b + ns, ctx->pass_begin[p + 1] - b - ns,
                                       cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot);
+            }
         } else if (n_pass) {
             launch_cull(st, R, cvw, vb, ctx->d_stats, cslot);
         }

@@ -1720,6 +1720,18 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, k_propagate_cull_tma<P, C, S>, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
 }
+// tiles of <= 32 rows (the tops of split deep tiles): the classic kernel with one warp per tile, 16 CTAs per SM
+void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
+                                 const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
+    if (n_tiles == 0) return;
+    const bool prop = stages & 1u, cull = stages & 2u;
+    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+#define B200VIS_LAUNCH_SMALL(P, C, S) k_propagate_cull<P, C, S><<<n_tiles, 32, 0, st>>>(R, tiles, cvw, vb, stats, static_opt, parity)
+    if (prop && cull) { if (simple) B200VIS_LAUNCH_SMALL(true, true, true); else B200VIS_LAUNCH_SMALL(true, true, false); }
+    else if (prop) B200VIS_LAUNCH_SMALL(true, false, true);
+    else if (cull) { if (simple) B200VIS_LAUNCH_SMALL(false, true, true); else B200VIS_LAUNCH_SMALL(false, true, false); }
+#undef B200VIS_LAUNCH_SMALL
+}
 void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                            const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
     if (n_tiles == 0) return;

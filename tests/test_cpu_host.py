@@ -183,3 +183,22 @@ def test_execution_plan_shapes():
         bb.host_plan_summary(np.array([1, bb.NO_PARENT], np.uint32))
     assert e.value.code == 8                                         # not in topological order
     assert bb.host_plan_summary(np.zeros(0, np.uint32)) == (0, 0, 0, 0)
+
+
+def test_deep_tile_split_experiment_plan_structure():
+    """B200VIS_SPLIT_DEEP_TILES=1 (off by default): a BFS-ordered 255-node tree is cut after its top five levels (31 rows);
+    the bottoms become 3-level tiles with 32 external parents each, one pass later.  The flag is read once per process."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from bevy_b200 import abi, scenes; "
+            "print(abi.host_plan_summary(scenes.forest(n_trees=10, levels=8, n_lights=0).parent)); "
+            "print(abi.host_plan_summary(scenes.forest(n_trees=10, levels=4, n_lights=0).parent))") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, B200VIS_SPLIT_DEEP_TILES=flag)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stderr[-2000:]
+        out[flag] = res.stdout.strip().splitlines()
+    assert out["0"][0] == "(10, 1, 8, 0)"            # tiles, passes, max levels per tile, rows with an external parent
+    assert out["1"][0] == "(20, 2, 5, 320)"
+    assert out["0"][1] == out["1"][1]                # shallow trees are left alone
