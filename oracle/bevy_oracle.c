@@ -1068,3 +1068,93 @@ ORC_API int orc_check_point_light_mesh_visibility(uint32_t n, const float *gt, c
     free(items);
     return 0;
 }
+
+/* check_point_light_mesh_visibility, spot-light half (crates/bevy_light/src/lib.rs:670-748): one Frustum per light
+ * (near and far planes checked), the same range-sphere pre-test and gates as the point-light half.
+ * Out: visible_rows[l*n ...] ascending by entity bits, visible_count[L].  (Device side: not built yet.) */
+ORC_API int orc_check_spot_light_mesh_visibility(uint32_t n, const float *gt, const float *bounds, const uint8_t *flags,
+                                                 const uint8_t *caster, const uint64_t *layer_mask, const uint32_t *range_mask,
+                                                 int lod_origin_index, const uint64_t *entity_bits, uint8_t *vv,
+                                                 uint8_t *vv_changed, uint32_t n_lights, const float *light_sphere,
+                                                 const uint64_t *light_layers, const float *frusta, uint32_t *visible_rows,
+                                                 uint32_t *visible_count) {
+    sort_item *items = (sort_item *)malloc((size_t)(n ? n : 1) * sizeof(sort_item));
+    if (!items) return 1;
+    for (uint32_t l = 0; l < n_lights; ++l) {
+        uint32_t cnt = 0;
+        const uint64_t view_mask = light_layers ? light_layers[l] : 1ull;
+        const float *ls = light_sphere + (size_t)l * 4;
+        v4 hs[6]; memcpy(hs, frusta + (size_t)l * 24, sizeof hs);
+        for (uint32_t r = 0; r < n; ++r) {
+            const uint8_t f = flags[r];
+            if (!caster[r] || (f & F_NO_CPU_CULLING) || !(f & F_INHERITED_VISIBLE)) continue;
+            if (!(view_mask & (layer_mask ? layer_mask[r] : 1ull))) continue;
+            if ((f & F_HAS_VIS_RANGE) && range_mask &&
+                (lod_origin_index < 0 || lod_origin_index > 31 || !((range_mask[r] >> lod_origin_index) & 1u)))
+                continue;
+            if (f & F_HAS_AABB) {
+                const float *b = bounds + (size_t)r * 6;
+                const int no_fc = (f & F_NO_FRUSTUM_CULLING) != 0;
+                if (!no_fc && !orc_sphere_intersects_obb(ls, ls[3], b, b + 3, gt + (size_t)r * 12)) continue;
+                aff a = aff_load(gt + (size_t)r * 12);
+                if (!(no_fc || frustum_intersects_obb(hs, V3(b[0], b[1], b[2]), V3(b[3], b[4], b[5]), &a, 1, 1))) continue;
+            }
+            if (!(vv[r] & 1u)) { if (!(vv[r] & 2u)) vv_changed[r] = 1; vv[r] |= 1u; }   /* set_visible */
+            items[cnt].key = entity_bits[r]; items[cnt].row = r; cnt++;
+        }
+        qsort(items, cnt, sizeof(sort_item), cmp_sort_item);
+        for (uint32_t i = 0; i < cnt; ++i) visible_rows[(size_t)l * n + i] = items[i].row;
+        visible_count[l] = cnt;
+    }
+    free(items);
+    return 0;
+}
+/* check_dir_light_mesh_visibility (crates/bevy_light/src/lib.rs:342-510) for the (directional light, view) pairs whose
+ * light has shadow_maps_enabled and is visible (:395-399): item i has n_cascades[i] frusta (CascadesFrusta of that
+ * view, concatenated in `frusta`), the light's RenderLayers and the view's bit in the VisibleEntityRanges masks
+ * (-1 = the view is not in the map => entity_is_in_range_of_view is false).  The near plane is NOT tested (a caster may
+ * lie before it, :455-458).  Out: per cascade (in item order) rows ascending by entity bits; set_visible is applied
+ * (the reference defers it to a command, same result).  (Device side: not built yet.) */
+ORC_API int orc_check_dir_light_mesh_visibility(uint32_t n, const float *gt, const float *bounds, const uint8_t *flags,
+                                                const uint8_t *caster, const uint64_t *layer_mask, const uint32_t *range_mask,
+                                                const uint64_t *entity_bits, uint8_t *vv, uint8_t *vv_changed, uint32_t n_items,
+                                                const int32_t *view_range_index, const uint64_t *light_layers,
+                                                const uint32_t *n_cascades, const float *frusta, uint32_t *visible_rows,
+                                                uint32_t *visible_count) {
+    sort_item *items = (sort_item *)malloc((size_t)(n ? n : 1) * sizeof(sort_item));
+    uint8_t *hit = (uint8_t *)malloc(n ? n : 1);
+    if (!items || !hit) { free(items); free(hit); return 1; }
+    uint32_t casc0 = 0;
+    for (uint32_t it = 0; it < n_items; ++it) {
+        const uint64_t view_mask = light_layers ? light_layers[it] : 1ull;
+        const int vri = view_range_index ? view_range_index[it] : -1;
+        for (uint32_t c = 0; c < n_cascades[it]; ++c) {
+            v4 hs[6]; memcpy(hs, frusta + (size_t)(casc0 + c) * 24, sizeof hs);
+            uint32_t cnt = 0;
+            for (uint32_t r = 0; r < n; ++r) {
+                const uint8_t f = flags[r];
+                hit[r] = 0;
+                if (!caster[r] || (f & F_NO_CPU_CULLING) || !(f & F_INHERITED_VISIBLE)) continue;
+                if (!(view_mask & (layer_mask ? layer_mask[r] : 1ull))) continue;
+                if ((f & F_HAS_VIS_RANGE) && range_mask && (vri < 0 || vri > 31 || !((range_mask[r] >> vri) & 1u))) continue;
+                if (f & F_HAS_AABB) {
+                    const float *b = bounds + (size_t)r * 6;
+                    aff a = aff_load(gt + (size_t)r * 12);
+                    if (!(f & F_NO_FRUSTUM_CULLING) &&
+                        !frustum_intersects_obb(hs, V3(b[0], b[1], b[2]), V3(b[3], b[4], b[5]), &a, 0, 1))
+                        continue;
+                }
+                hit[r] = 1;
+                items[cnt].key = entity_bits[r]; items[cnt].row = r; cnt++;
+            }
+            for (uint32_t r = 0; r < n; ++r)
+                if (hit[r] && !(vv[r] & 1u)) { if (!(vv[r] & 2u)) vv_changed[r] = 1; vv[r] |= 1u; }
+            qsort(items, cnt, sizeof(sort_item), cmp_sort_item);
+            for (uint32_t i = 0; i < cnt; ++i) visible_rows[(size_t)(casc0 + c) * n + i] = items[i].row;
+            visible_count[casc0 + c] = cnt;
+        }
+        casc0 += n_cascades[it];
+    }
+    free(items); free(hit);
+    return 0;
+}

@@ -134,6 +134,14 @@ def _declare(l):
         C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint8),
         C.POINTER(C.c_uint8), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_float),
         C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    l.orc_check_spot_light_mesh_visibility.restype = C.c_int
+    l.orc_check_spot_light_mesh_visibility.argtypes = l.orc_check_point_light_mesh_visibility.argtypes
+    l.orc_check_dir_light_mesh_visibility.restype = C.c_int
+    l.orc_check_dir_light_mesh_visibility.argtypes = [
+        C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8),
+        C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8),
+        C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_float),
+        C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     if hasattr(l, "orc_update_cpu_culled_entities"):   # bevy_oracle_next.c (not part of the MT baseline library)
         U64P, U32P, U8P = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
         l.orc_sort_pairs_by_main.argtypes = [U64P, U64P, C.c_uint32]
@@ -478,3 +486,49 @@ def check_point_light_mesh_visibility(gt, bounds, flags, caster, entity_bits, vv
         _p(ls, C.c_float), _p(ll, C.c_uint64), _p(fr, C.c_float), _p(rows, C.c_uint32), _p(cnt, C.c_uint32))
     assert rc == 0
     return [[rows[l * 6 + k, :cnt[l * 6 + k]].copy() for k in range(6)] for l in range(L)]
+
+
+def check_spot_light_mesh_visibility(gt, bounds, flags, caster, entity_bits, vv, vv_changed, light_sphere, frusta,
+                                     layer_mask=None, range_mask=None, lod_origin_index=-1, light_layers=None):
+    """Spot-light half of check_point_light_mesh_visibility: one frustum [6, 4] per light; returns one row list per light."""
+    gt, bounds = _f32(gt), _f32(bounds)
+    flags = np.ascontiguousarray(flags, np.uint8); caster = np.ascontiguousarray(caster, np.uint8)
+    bits = np.ascontiguousarray(entity_bits, np.uint64)
+    ls = _f32(light_sphere).reshape(-1, 4); fr = _f32(frusta).reshape(-1, 6, 4)
+    n, L = len(flags), len(ls)
+    lm = None if layer_mask is None else np.ascontiguousarray(layer_mask, np.uint64)
+    rm = None if range_mask is None else np.ascontiguousarray(range_mask, np.uint32)
+    ll = None if light_layers is None else np.ascontiguousarray(light_layers, np.uint64)
+    rows = np.zeros((max(L, 1), max(n, 1)), np.uint32); cnt = np.zeros(max(L, 1), np.uint32)
+    rc = lib().orc_check_spot_light_mesh_visibility(
+        n, _p(gt, C.c_float), _p(bounds, C.c_float), _p(flags, C.c_uint8), _p(caster, C.c_uint8), _p(lm, C.c_uint64),
+        _p(rm, C.c_uint32), int(lod_origin_index), _p(bits, C.c_uint64), _p(vv, C.c_uint8), _p(vv_changed, C.c_uint8), L,
+        _p(ls, C.c_float), _p(ll, C.c_uint64), _p(fr, C.c_float), _p(rows, C.c_uint32), _p(cnt, C.c_uint32))
+    assert rc == 0
+    return [rows[l, :cnt[l]].copy() for l in range(L)]
+
+
+def check_dir_light_mesh_visibility(gt, bounds, flags, caster, entity_bits, vv, vv_changed, items, layer_mask=None,
+                                    range_mask=None):
+    """items: list of (cascade frusta [C, 6, 4], light_layers, view_range_index) per (directional light, view) pair;
+    returns a list (per item) of lists (per cascade) of rows."""
+    gt, bounds = _f32(gt), _f32(bounds)
+    flags = np.ascontiguousarray(flags, np.uint8); caster = np.ascontiguousarray(caster, np.uint8)
+    bits = np.ascontiguousarray(entity_bits, np.uint64)
+    n = len(flags)
+    ncasc = np.array([len(np.asarray(f).reshape(-1, 6, 4)) for f, _, _ in items], np.uint32)
+    fr = _f32(np.concatenate([np.asarray(f, np.float32).reshape(-1, 6, 4) for f, _, _ in items])) if len(items) else np.zeros((0, 6, 4), np.float32)
+    ll = np.array([l for _, l, _ in items], np.uint64); vri = np.array([v for _, _, v in items], np.int32)
+    lm = None if layer_mask is None else np.ascontiguousarray(layer_mask, np.uint64)
+    rm = None if range_mask is None else np.ascontiguousarray(range_mask, np.uint32)
+    tot = int(ncasc.sum())
+    rows = np.zeros((max(tot, 1), max(n, 1)), np.uint32); cnt = np.zeros(max(tot, 1), np.uint32)
+    rc = lib().orc_check_dir_light_mesh_visibility(
+        n, _p(gt, C.c_float), _p(bounds, C.c_float), _p(flags, C.c_uint8), _p(caster, C.c_uint8), _p(lm, C.c_uint64),
+        _p(rm, C.c_uint32), _p(bits, C.c_uint64), _p(vv, C.c_uint8), _p(vv_changed, C.c_uint8), len(items),
+        _p(vri, C.c_int32), _p(ll, C.c_uint64), _p(ncasc, C.c_uint32), _p(fr, C.c_float), _p(rows, C.c_uint32), _p(cnt, C.c_uint32))
+    assert rc == 0
+    out, k = [], 0
+    for c in ncasc:
+        out.append([rows[k + j, :cnt[k + j]].copy() for j in range(int(c))]); k += int(c)
+    return out

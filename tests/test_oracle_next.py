@@ -277,3 +277,87 @@ def test_n3_point_light_mesh_visibility_against_a_plain_loop():
     orc.mark_newly_hidden(flags, vv, ch)
     gone = ((vv0 == 2) & ~want_vis & ((flags & orc.F_NO_CPU_CULLING) == 0))
     assert np.array_equal(vv[gone], np.zeros(gone.sum(), np.uint8)) and ch[gone].all()
+
+
+def _shadow_world(seed, n=400):
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    trs = np.concatenate([rng.uniform(-30, 30, (n, 3)), q, rng.uniform(0.5, 2, (n, 3))], 1).astype(np.float32)
+    gt = np.stack([orc.affine_from_trs(t) for t in trs])
+    bounds = np.concatenate([rng.normal(size=(n, 3)) * 0.3, rng.uniform(0.2, 2.0, (n, 3))], 1).astype(np.float32)
+    flags = (orc.F_INHERITED_VISIBLE * (rng.random(n) < 0.9) | orc.F_HAS_AABB * (rng.random(n) < 0.85)
+             | orc.F_NO_FRUSTUM_CULLING * (rng.random(n) < 0.05) | orc.F_HAS_VIS_RANGE * (rng.random(n) < 0.3)
+             | orc.F_NO_CPU_CULLING * (rng.random(n) < 0.05)).astype(np.uint8)
+    return dict(rng=rng, n=n, gt=gt, bounds=bounds, flags=flags, caster=(rng.random(n) < 0.8).astype(np.uint8),
+                layers=rng.integers(1, 4, n).astype(np.uint64), range_mask=rng.integers(0, 4, n).astype(np.uint32),
+                bits=rng.permutation(n).astype(np.uint64) + 100, vv0=rng.choice([0, 2], n).astype(np.uint8))
+
+
+def _gate(w, r, light_layers, range_bit):
+    f = int(w["flags"][r])
+    if not w["caster"][r] or f & orc.F_NO_CPU_CULLING or not f & orc.F_INHERITED_VISIBLE:
+        return False
+    if not int(light_layers) & int(w["layers"][r]):
+        return False
+    if f & orc.F_HAS_VIS_RANGE and (range_bit < 0 or not (w["range_mask"][r] >> range_bit) & 1):
+        return False
+    return True
+
+
+def test_n3_spot_light_half_against_a_plain_loop():
+    w = _shadow_world(21)
+    rng, n = w["rng"], w["n"]
+    L = 4
+    lpos = rng.uniform(-15, 15, (L, 3)).astype(np.float32); lrange = rng.uniform(10, 35, L).astype(np.float32)
+    llayers = rng.integers(1, 4, L).astype(np.uint64)
+    ident = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)
+    frusta = np.stack([orc.point_light_frusta(np.concatenate([ident, lpos[l]]), lrange[l], 0.1)[l % 6] for l in range(L)])
+    vv, ch = w["vv0"].copy(), np.zeros(n, np.uint8)
+    got = orc.check_spot_light_mesh_visibility(w["gt"], w["bounds"], w["flags"], w["caster"], w["bits"], vv, ch,
+                                               np.concatenate([lpos, lrange[:, None]], 1), frusta, layer_mask=w["layers"],
+                                               range_mask=w["range_mask"], lod_origin_index=0, light_layers=llayers)
+    seen = np.zeros(n, bool)
+    for l in range(L):
+        rows = []
+        for r in range(n):
+            if not _gate(w, r, llayers[l], 0):
+                continue
+            f = int(w["flags"][r])
+            if f & orc.F_HAS_AABB and not f & orc.F_NO_FRUSTUM_CULLING:
+                b = w["bounds"][r]
+                if not orc.sphere_intersects_obb(lpos[l], lrange[l], b[:3], b[3:], w["gt"][r]):
+                    continue
+                if not orc.intersects_obb(frusta[l], b[:3], b[3:], w["gt"][r], True, True):
+                    continue
+            rows.append(r); seen[r] = True
+        assert np.array_equal(got[l], np.array(sorted(rows, key=lambda r: w["bits"][r]), np.uint32))
+    assert seen.sum() > 20 and np.array_equal((vv & 1) != 0, seen) and np.array_equal(ch != 0, seen & (w["vv0"] == 0))
+
+
+def test_n3_directional_light_half_against_a_plain_loop():
+    w = _shadow_world(22)
+    rng, n = w["rng"], w["n"]
+    ident = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)
+
+    def cascade(center, r):   # any six half spaces will do: reuse a cubemap face
+        return orc.point_light_frusta(np.concatenate([ident, center]).astype(np.float32), r, 0.1)[int(rng.integers(0, 6))]
+    items = [(np.stack([cascade(rng.uniform(-10, 10, 3), rr) for rr in (15.0, 30.0, 60.0)]), 3, 1),
+             (np.stack([cascade(rng.uniform(-10, 10, 3), rr) for rr in (20.0, 50.0)]), 1, -1)]
+    vv, ch = w["vv0"].copy(), np.zeros(n, np.uint8)
+    got = orc.check_dir_light_mesh_visibility(w["gt"], w["bounds"], w["flags"], w["caster"], w["bits"], vv, ch, items,
+                                              layer_mask=w["layers"], range_mask=w["range_mask"])
+    seen = np.zeros(n, bool)
+    for (fr, ll, vri), lists in zip(items, got):
+        for c in range(len(fr)):
+            rows = []
+            for r in range(n):
+                if not _gate(w, r, ll, vri):
+                    continue
+                f = int(w["flags"][r])
+                if f & orc.F_HAS_AABB and not f & orc.F_NO_FRUSTUM_CULLING:
+                    b = w["bounds"][r]
+                    if not orc.intersects_obb(fr[c], b[:3], b[3:], w["gt"][r], False, True):   # near plane not tested
+                        continue
+                rows.append(r); seen[r] = True
+            assert np.array_equal(lists[c], np.array(sorted(rows, key=lambda r: w["bits"][r]), np.uint32))
+    assert seen.sum() > 20 and np.array_equal((vv & 1) != 0, seen) and np.array_equal(ch != 0, seen & (w["vv0"] == 0))
