@@ -144,6 +144,11 @@ def cpu_frames(scene, frames, warm=1):
     return float(np.median(times)), best_n
 
 
+def workload_name(trees, lights, n_roots):
+    return (f"config#3 forest {trees}x255 (BFS, depth 8) + {lights} point lights per GPU, 4 views 1920x1080, "
+            f"default ClusterConfig, all {n_roots} roots move every frame")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -158,8 +163,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "entities/s", "n_gpus": args.gpus,
         "steps": frames, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"forest {args.trees}x255 BFS depth-8 + {args.lights} point lights, 4 views, all roots move",
-                   "entities": n, "lights": args.lights, "views": 4},
+        "config": {"workload": workload_name(args.trees, args.lights, len(scene.roots)),
+                   "entities_per_gpu": n, "lights_per_gpu": args.lights, "views": 4,
+                   "note": "the same workload as the b200 arm, timed on the host cores of rank 0 (a CPU has no per-GPU shards)"},
         "cpu_baseline": {"value": val, "unit": "entities/s", "cores": threads, "kind": "port",
                          "sample": f"{frames} full frames of the same 1M-entity workload, median, OpenMP over row ranges/roots; "
                                    "Rust toolchain absent: C restatement of the reference algorithm, not Bevy itself"},
@@ -559,8 +565,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "entities/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config#3 forest {args.trees}x255 (BFS, depth 8) + {args.lights} point lights per GPU, "
-                                   f"4 views 1920x1080, default ClusterConfig, all {n_roots} roots move every frame",
+            "config": {"workload": workload_name(args.trees, args.lights, n_roots),
                        "entities_per_gpu": n, "lights_per_gpu": args.lights, "views": V,
                        "l2": "working set 167 MB/frame/GPU > 126 MB L2 (inputs larger than L2, no flush)",
                        "sharding": ("contiguous row ranges (whole trees) per GPU; cluster slabs exchanged by " +
