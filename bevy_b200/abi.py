@@ -104,6 +104,7 @@ _SIGNATURES = {
     "b200vis_tail_stream": (C.c_int32, [_vp, _P(_vp)]),
     "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
     "b200vis_host_plan_summary": (C.c_int32, [C.c_uint32, _vp, _P(C.c_uint32)]),
+    "b200vis_host_warp_plan": (C.c_int32, [C.c_uint32, _vp, C.c_uint32, C.c_uint32, _P(C.c_uint32), _vp, _vp, _vp, _vp]),
     "b200vis_plan_row_order": (C.c_int32, [C.c_uint32, _vp, _vp]),
     "b200vis_upload_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "b200vis_upload_transforms_scattered": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
@@ -247,6 +248,23 @@ def host_plan_summary(parent):
     if rc:
         raise B200VisError(rc, load_library().b200vis_last_error(None).decode())
     return tuple(out)
+
+
+def host_warp_plan(parent, tile_rows=0):
+    """The warp-per-tile plan (b200vis_host_warp_plan): (tile_desc[T,4], nonroot[T,8], sched[T,256], wtopo[n])."""
+    parent = _arr(parent, np.uint32)
+    lib = load_library()
+    nt = C.c_uint32(0)
+    rc = lib.b200vis_host_warp_plan(len(parent), _ptr(parent), tile_rows, 0, C.byref(nt), None, None, None, None)
+    if rc:
+        raise B200VisError(rc, "host_warp_plan")
+    T = nt.value
+    desc = np.zeros((T, 4), np.uint32); nonroot = np.zeros((T, 8), np.uint32)
+    sched = np.zeros((T, 256), np.uint8); wtopo = np.zeros(len(parent), np.uint32)
+    rc = lib.b200vis_host_warp_plan(len(parent), _ptr(parent), tile_rows, T, C.byref(nt), _ptr(desc), _ptr(nonroot), _ptr(sched), _ptr(wtopo))
+    if rc:
+        raise B200VisError(rc, "host_warp_plan")
+    return desc, nonroot, sched, wtopo
 
 
 def plan_row_order(parent):

@@ -70,6 +70,7 @@ struct b200vis_ctx {
     bool tail_open = false; uint32_t open_frame = 0; const FrameConsts *open_fc = nullptr;
     float4 *d_light_snap = nullptr;     // [3][max_lights]
     uint32_t *d_tag_flag = nullptr;     // 1 if every light row carries its ordinal (k_tag_lights)
+    uint32_t *d_light_ord = nullptr;    // [max_entities] light ordinal per row, 0xFFFFFFFF = not a light (rewritten on set_lights)
     bool lights_tag_dirty = true, lights_tagged = false;
     std::string err;
 
@@ -82,6 +83,8 @@ struct b200vis_ctx {
 
     // plan
     Tile *d_tiles = nullptr; uint32_t tiles_cap = 0;
+    WarpTile *d_wtiles = nullptr; uint8_t *d_sched = nullptr; uint32_t *d_wtopo = nullptr;   // k_tile_warp's view of the plan
+    uint32_t *d_tile_counter = nullptr;
     std::vector<uint32_t> pass_begin;   // tile index ranges per pass: [pass_begin[p], pass_begin[p+1])
     std::vector<uint32_t> pass_small;   // the first pass_small[p] tiles of pass p have <= 32 rows (B200VIS_SPLIT_DEEP_TILES)
     int static_opt = 1;
@@ -185,7 +188,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     Rows &r = ctx->rows;
     void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
-                   ctx->d_tiles, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_light_snap, ctx->d_tag_flag,
+                   ctx->d_tiles, ctx->d_wtiles, ctx->d_sched, ctx->d_wtopo, ctx->d_tile_counter, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_light_snap, ctx->d_tag_flag, ctx->d_light_ord,
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage,
                    ctx->diff.prev, ctx->diff.words, ctx->diff.chunk, ctx->diff.lists, ctx->diff.count,
@@ -257,6 +260,11 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         ctx->tiles_cap = (uint32_t)(N / 1 + 1);   // worst case one tile per row is never reached; see planner
         ctx->tiles_cap = (uint32_t)std::min<size_t>(N + 1, (N / 8) + 1024);
         CU(dalloc(&ctx->d_tiles, ctx->tiles_cap));
+        CU(dalloc(&ctx->d_wtiles, ctx->tiles_cap));
+        CU(dalloc(&ctx->d_sched, (size_t)ctx->tiles_cap * kTileRows));
+        CU(dalloc(&ctx->d_wtopo, NP));
+        CU(dalloc(&ctx->d_tile_counter, 1));
+        r.wtopo = ctx->d_wtopo;
         // worst case tables: every view with three (kMaxClusters+1)-entry plane tables + kMaxClusters thresholds
         ctx->blob_cap = sizeof(FrameConsts) + V * (3 * (size_t)(kMaxClusters + 1) * 16 + (size_t)kMaxClusters * 4);
         CU(dalloc(&ctx->d_blob2[0], ctx->blob_cap)); CU(dalloc(&ctx->d_blob2[1], ctx->blob_cap)); CU(dalloc(&ctx->d_blob2[2], ctx->blob_cap));
@@ -290,6 +298,8 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         const size_t Lm = std::max<uint32_t>(cfg->max_lights, 1);
         CU(dalloc(&ctx->d_light_snap, 3 * Lm));
         CU(dalloc(&ctx->d_tag_flag, 1));
+        CU(dalloc(&ctx->d_light_ord, N));
+        CU(cudaMemset(ctx->d_light_ord, 0xFF, std::max<size_t>(N, 1) * 4));
         CU(dalloc(&ctx->d_light_row, Lm)); CU(dalloc(&ctx->d_light_range, Lm)); CU(dalloc(&ctx->d_light_layers, Lm));
         ClusterBufs &cl = ctx->cl;
         cl.words = (uint32_t)((Lm + 31) / 32); cl.max_lights = cl.words * 32; cl.world = ctx->cfg.world_size;
@@ -351,9 +361,21 @@ extern "C" int32_t b200vis_set_static_transform_optimizations(b200vis_ctx *ctx, 
 // preferring cuts at tree boundaries so parents sit in the same tile as their children -- and
 // orders the tiles into passes so that a tile's out-of-tile parents are finished by an earlier
 // launch.  Forests of small trees need one pass; a tree larger than a tile needs a few.
-static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, std::vector<uint32_t> &topo,
-                          std::vector<Tile> &tiles_sorted, std::vector<uint32_t> &pass_begin,
-                          std::vector<uint32_t> *pass_small = nullptr) {
+struct Plan {
+    std::vector<uint32_t> topo;          // per row, CTA-per-tile kernels (device_types.cuh T_*)
+    std::vector<uint32_t> wtopo;         // per row, k_tile_warp
+    std::vector<Tile> tiles;             // sorted by pass
+    std::vector<WarpTile> wtiles;        // the same tiles, same order, as warp work items
+    std::vector<uint8_t> sched;          // kTileRows bytes per tile: schedule slot -> local row, 0xFF = padding
+    std::vector<uint32_t> pass_begin;    // tile index ranges per pass: [pass_begin[p], pass_begin[p+1])
+    std::vector<uint32_t> pass_small;
+    uint32_t n_ext = 0;                  // rows whose parent sits in another tile
+};
+static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, uint32_t cap, Plan &plan) {
+    std::vector<uint32_t> &topo = plan.topo; std::vector<Tile> &tiles_sorted = plan.tiles;
+    std::vector<uint32_t> &pass_begin = plan.pass_begin; std::vector<uint32_t> *pass_small = &plan.pass_small;
+    if (cap < 32) cap = 32;
+    if (cap > (uint32_t)kTileRows) cap = kTileRows;
     for (uint32_t r = 0; r < n; ++r) {
         const uint32_t p = parent[r];
         if (p == kNoParent || p == kDetached) continue;
@@ -382,21 +404,31 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
             return fail(ctx, B200VIS_ERR_UNSUPPORTED,
                         "row %u has parent %u >= itself: rows must be in topological order (use b200vis_plan_row_order)", r,
                         parent[r]);
-    std::vector<uint8_t> has_children(n, 0);
-    for (uint32_t r = 0; r < n; ++r) if (parent[r] < n) has_children[parent[r]] = 1;
     // greedy tiling, cutting at the latest tree boundary inside a full tile
     static int split_env = -1;
     if (split_env < 0) { const char *e = getenv("B200VIS_SPLIT_DEEP_TILES"); split_env = (e && atoi(e)) ? 1 : 0; }
     const bool split_deep = split_env == 1;
     std::vector<Tile> tiles;
     std::vector<uint32_t> tile_of(n);
+    std::vector<uint8_t> marked(n, 0);
     uint32_t start = 0;
     while (start < n) {
-        uint32_t end = std::min<uint32_t>(n, start + kTileRows);
+        uint32_t end = std::min<uint32_t>(n, start + cap);
         if (end < n && parent[end] < n) {          // the cut would split a tree: back up to a boundary
             uint32_t c = end;
             while (c > start + 1 && parent[c] < n) --c;   // c = latest row in (start, end] that starts a tree
             if (c > start && !(parent[c] < n)) end = c;
+        }
+        {   // k_tile_warp keeps the GlobalTransforms of the rows WITH in-tile children in kWarpParentSlots shared-memory
+            // slots: cut the tile before the child that would need one more (only chains and unary-heavy trees get there)
+            uint32_t parents = 0;
+            for (uint32_t c = start; c < end; ++c) {
+                const uint32_t p = parent[c];
+                if (p < n && p >= start && !marked[p]) {
+                    if (parents == (uint32_t)kWarpParentSlots) { end = c; break; }
+                    marked[p] = 1; ++parents;
+                }
+            }
         }
         // EXPERIMENT (B200VIS_SPLIT_DEEP_TILES=1, off by default): the hierarchy walk of a tile is a serial chain of its
         // levels (~680 cycles per level).  When the first <= 32 rows of a deep tile are exactly its top
@@ -431,8 +463,13 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
         }
         start = end;
     }
+    // rows with children IN THEIR OWN TILE (a child in a later tile reads its parent from HBM, an earlier pass)
+    std::vector<uint8_t> has_children(n, 0), has_local_children(n, 0);
+    for (uint32_t r = 0; r < n; ++r)
+        if (parent[r] < n) { has_children[parent[r]] = 1; if (tile_of[parent[r]] == tile_of[r]) has_local_children[parent[r]] = 1; }
     // topo words, in-tile depth, tile levels
     topo.assign(n, 0);
+    plan.n_ext = 0;
     std::vector<uint32_t> ldepth(n, 0), tile_level(tiles.size(), 0);
     for (uint32_t r = 0; r < n; ++r) {
         const uint32_t p = parent[r], ti = tile_of[r];
@@ -448,10 +485,66 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
                 tiles[ti].warp_sync_mask &= ~(1u << ldepth[r]);
         } else {
             w |= T_EXT_PARENT;
+            ++plan.n_ext;
             tile_level[ti] = std::max(tile_level[ti], tile_level[tile_of[p]] + 1);
         }
         if (has_children[r]) w |= T_HAS_CHILDREN;
         topo[r] = w;
+    }
+    // ---- warp work items: schedule, parent slots, wtopo ------------------------------------------------------------
+    std::vector<WarpTile> wtiles(tiles.size());
+    std::vector<uint8_t> sched_all(tiles.size() * (size_t)kTileRows, 0xFF);
+    plan.wtopo.assign(n, 0);
+    {
+        std::vector<uint32_t> slot_of(n, 0);     // parent slot of the rows with in-tile children
+        std::vector<uint32_t> level_count, order;
+        for (size_t ti = 0; ti < tiles.size(); ++ti) {
+            const Tile &t = tiles[ti];
+            const uint32_t b = t.base, nr = t.n_rows;
+            // rows in (depth, row) order: counting sort by in-tile depth
+            level_count.assign((size_t)t.n_levels + 1, 0);
+            for (uint32_t r = b; r < b + nr; ++r) level_count[ldepth[r] + 1]++;
+            for (uint32_t l = 0; l < t.n_levels; ++l) level_count[l + 1] += level_count[l];
+            order.assign(nr, 0);
+            { std::vector<uint32_t> cur(level_count.begin(), level_count.end() - 1);
+              for (uint32_t r = b; r < b + nr; ++r) order[cur[ldepth[r]]++] = r - b; }
+            // slots: a level with >= 32 rows starts on a chunk boundary when the padding still fits into kTileRows slots
+            uint8_t *sch = sched_all.data() + ti * (size_t)kTileRows;
+            uint32_t pos = 0, next_slot = 0;
+            for (uint32_t l = 0; l < t.n_levels; ++l) {
+                const uint32_t lb = level_count[l], le = level_count[l + 1], cnt = le - lb;
+                if ((pos & 31u) && cnt >= 32u) {
+                    const uint32_t padded = (pos + 31u) & ~31u;
+                    if (padded + (nr - lb) <= (uint32_t)kTileRows) pos = padded;
+                }
+                for (uint32_t i = lb; i < le; ++i) {
+                    const uint32_t r = b + order[i];
+                    sch[pos++] = (uint8_t)order[i];
+                    if (has_local_children[r]) slot_of[r] = next_slot++;
+                }
+            }
+            WarpTile &w = wtiles[ti];
+            memset(&w, 0, sizeof w);
+            w.base = b; w.n_rows = (uint16_t)nr; w.n_chunks = (uint8_t)((pos + 31u) / 32u); w.sched = (uint32_t)ti;
+            for (uint32_t c = 0; c < w.n_chunks; ++c) {
+                bool contig = true; int64_t delta = 0; bool have = false;
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    const uint8_t lr = sch[c * 32 + lane];
+                    if (lr == 0xFF && nr != (uint32_t)kTileRows) continue;   // padding (a full tile has none: 0xFF is row 255)
+                    const int64_t d = (int64_t)lr - (int64_t)lane;
+                    if (!have) { delta = d; have = true; } else if (d != delta) contig = false;
+                    if (ldepth[b + lr] > 0) w.nonroot[c] |= 1u << lane;
+                }
+                if (contig) w.contig |= (uint8_t)(1u << c);
+            }
+        }
+        for (uint32_t r = 0; r < n; ++r) {
+            uint32_t w = topo[r] & 0xF0000000u;      // T_HAS_CHILDREN stays the reference's "has a Children component"
+            if (has_local_children[r]) w |= W_HAS_SLOT | (slot_of[r] << 8);
+            w |= ldepth[r] & 0xFFu;
+            if (ldepth[r]) w |= slot_of[parent[r]] << 15;
+            plan.wtopo[r] = w;
+        }
     }
     // NOTE: tile_level of tile t only depends on tiles with a smaller index (topological rows), and
     // those are final by the time a row of t is visited, because rows are visited in ascending order.
@@ -460,6 +553,7 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
     for (uint32_t lv : tile_level) pass_begin[lv + 1]++;
     for (uint32_t p = 0; p < n_pass; ++p) pass_begin[p + 1] += pass_begin[p];
     tiles_sorted.resize(tiles.size());
+    plan.wtiles.resize(tiles.size());
     std::vector<uint32_t> cursor(pass_begin.begin(), pass_begin.end() - (n_pass ? 1 : 0));
     if (pass_small) pass_small->assign(n_pass, 0);
     // within a pass: the small tiles (<= 32 rows, only produced by the split above) first, then the rest
@@ -467,9 +561,12 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
         for (size_t i = 0; i < tiles.size(); ++i) {
             const bool is_small = split_deep && tiles[i].n_rows <= 32;
             if ((int)is_small != small) continue;
-            tiles_sorted[cursor[tile_level[i]]++] = tiles[i];
+            const uint32_t at = cursor[tile_level[i]]++;
+            tiles_sorted[at] = tiles[i];
+            plan.wtiles[at] = wtiles[i];       // .sched keeps pointing at the tile's block in creation order
             if (is_small && pass_small) (*pass_small)[tile_level[i]]++;
         }
+    plan.sched.swap(sched_all);
     return B200VIS_OK;
 }
 
@@ -477,14 +574,31 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     CHECK_CTX_JOIN();
     if (n && (!parent || !entity_bits)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_topology: null array");
     if (n > ctx->cfg.max_entities) return fail(ctx, B200VIS_ERR_CAPACITY, "set_topology: %u rows > max_entities %u", n, ctx->cfg.max_entities);
-    std::vector<uint32_t> topo; std::vector<Tile> tiles;
-    std::vector<uint32_t> pass_begin, pass_small;
-    int32_t rc = build_plan(ctx, n, parent, topo, tiles, pass_begin, &pass_small);
+    // Tile size: a tile is one WARP's work item, and the machine has ~4700 resident warps: small scenes get smaller tiles
+    // (more warps busy) as long as that does not split trees across tiles (more passes / parents read from HBM).
+    Plan plan;
+    int32_t rc = build_plan(ctx, n, parent, kTileRows, plan);
     if (rc != B200VIS_OK) return rc;
+    {
+        static int cap_env = -1;
+        if (cap_env < 0) { const char *e = getenv("B200VIS_TILE_ROWS"); cap_env = e ? atoi(e) : 0; }
+        uint32_t target = cap_env > 0 ? (uint32_t)cap_env : (uint32_t)std::min<uint64_t>(kTileRows, (((uint64_t)n / 9472u) + 31u) / 32u * 32u);
+        if (target < 32) target = 32;
+        for (uint32_t cap = target; cap < (uint32_t)kTileRows; cap *= 2) {
+            Plan q;
+            if (build_plan(ctx, n, parent, cap, q) != B200VIS_OK) break;
+            if (q.pass_begin.size() <= plan.pass_begin.size() && q.n_ext <= plan.n_ext) { plan = std::move(q); break; }
+        }
+    }
+    std::vector<uint32_t> &topo = plan.topo; std::vector<Tile> &tiles = plan.tiles;
+    std::vector<uint32_t> &pass_begin = plan.pass_begin, &pass_small = plan.pass_small;
     if (tiles.size() > ctx->tiles_cap) {
-        if (ctx->d_tiles) cudaFree(ctx->d_tiles);
-        ctx->d_tiles = nullptr; ctx->tiles_cap = (uint32_t)tiles.size() + 1024;
+        void *old[] = {ctx->d_tiles, ctx->d_wtiles, ctx->d_sched};
+        for (void *q : old) if (q) cudaFree(q);
+        ctx->d_tiles = nullptr; ctx->d_wtiles = nullptr; ctx->d_sched = nullptr; ctx->tiles_cap = (uint32_t)tiles.size() + 1024;
         CU(dalloc(&ctx->d_tiles, ctx->tiles_cap));
+        CU(dalloc(&ctx->d_wtiles, ctx->tiles_cap));
+        CU(dalloc(&ctx->d_sched, (size_t)ctx->tiles_cap * kTileRows));
     }
     // Entity::to_bits() order -> rank
     bool sorted = true;
@@ -501,6 +615,9 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     CU(cudaMemcpy(ctx->rows.topo, topo.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_parent, parent, (size_t)n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_wtiles, plan.wtiles.data(), plan.wtiles.size() * sizeof(WarpTile), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_sched, plan.sched.data(), plan.sched.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_wtopo, plan.wtopo.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
     if (!sorted) {
         CU(cudaMemcpy(ctx->d_rank, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(ctx->d_row_of_rank, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
@@ -524,13 +641,37 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
 
 extern "C" int32_t b200vis_host_plan_summary(uint32_t n, const uint32_t *parent, uint32_t out[4]) {
     if ((n && !parent) || !out) return B200VIS_ERR_INVALID_ARG;
-    std::vector<uint32_t> topo, pass_begin; std::vector<Tile> tiles;
-    const int32_t rc = build_plan(nullptr, n, parent, topo, tiles, pass_begin);
+    Plan plan;
+    const int32_t rc = build_plan(nullptr, n, parent, kTileRows, plan);
     if (rc) return rc;
+    std::vector<uint32_t> &topo = plan.topo, &pass_begin = plan.pass_begin; std::vector<Tile> &tiles = plan.tiles;
     uint32_t max_levels = 0, ext = 0;
     for (const Tile &t : tiles) max_levels = std::max<uint32_t>(max_levels, t.n_levels);
     for (uint32_t w : topo) ext += (w & T_EXT_PARENT) ? 1u : 0u;
     out[0] = (uint32_t)tiles.size(); out[1] = pass_begin.empty() ? 0u : (uint32_t)pass_begin.size() - 1; out[2] = max_levels; out[3] = ext;
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_host_warp_plan(uint32_t n, const uint32_t *parent, uint32_t tile_rows, uint32_t tiles_capacity, uint32_t *n_tiles,
+                                          uint32_t *tile_desc, uint32_t *nonroot, uint8_t *sched, uint32_t *wtopo) {
+    if ((n && !parent) || !n_tiles) return B200VIS_ERR_INVALID_ARG;
+    Plan plan;
+    const int32_t rc = build_plan(nullptr, n, parent, tile_rows ? tile_rows : kTileRows, plan);
+    if (rc) return rc;
+    *n_tiles = (uint32_t)plan.wtiles.size();
+    if (!tile_desc) return B200VIS_OK;
+    if (plan.wtiles.size() > tiles_capacity || !nonroot || !sched || (n && !wtopo)) return B200VIS_ERR_CAPACITY;
+    std::vector<uint32_t> pass_of(plan.wtiles.size(), 0);
+    for (size_t p = 0; p + 1 < plan.pass_begin.size(); ++p)
+        for (uint32_t i = plan.pass_begin[p]; i < plan.pass_begin[p + 1]; ++i) pass_of[i] = (uint32_t)p;
+    for (size_t i = 0; i < plan.wtiles.size(); ++i) {
+        const WarpTile &w = plan.wtiles[i];
+        tile_desc[i * 4 + 0] = w.base; tile_desc[i * 4 + 1] = w.n_rows;
+        tile_desc[i * 4 + 2] = w.n_chunks | ((uint32_t)w.contig << 8); tile_desc[i * 4 + 3] = pass_of[i];
+        memcpy(nonroot + i * kWarpChunks, w.nonroot, sizeof w.nonroot);
+        memcpy(sched + i * (size_t)kTileRows, plan.sched.data() + (size_t)w.sched * kTileRows, kTileRows);
+    }
+    if (n) memcpy(wtopo, plan.wtopo.data(), (size_t)n * 4);
     return B200VIS_OK;
 }
 
@@ -654,7 +795,7 @@ extern "C" int32_t b200vis_upload_bounds(b200vis_ctx *ctx, uint32_t first, uint3
         ctx->have_range = true;
     }
     ctx->bounds_set = true;
-    ctx->lights_tag_dirty = true;   // bounds were rewritten: the light ordinals stored in them are gone
+    ctx->lights_tag_dirty = true;   // flags were rewritten: re-verify that every light row is a sphere-from-GT row
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_upload_view_visibility(b200vis_ctx *ctx, uint32_t first, uint32_t count, const uint8_t *vv) {
@@ -1032,7 +1173,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     vb.mask = ctx->vis.mask + (size_t)mslot * ctx->vis.words_stride * ctx->cfg.max_views;
     const uint32_t n_pass = ctx->pass_begin.empty() ? 0 : (uint32_t)ctx->pass_begin.size() - 1;
     R.dirty = nullptr;
-    R.light_snap = nullptr;
+    R.light_snap = nullptr; R.light_ord = nullptr; R.n_lights = 0;
     if (do_prop && ctx->static_opt && n_pass > 1) {
         CU(cudaMemsetAsync(ctx->d_dirty, 0, ctx->n, st));
         R.dirty = ctx->d_dirty;
@@ -1044,7 +1185,9 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         if (ctx->lights_tag_dirty) {
             const uint32_t one = 1;
             CU(cudaMemcpyAsync(ctx->d_tag_flag, &one, 4, cudaMemcpyHostToDevice, st));
-            launch_tag_lights(st, R, ctx->lights, ctx->d_tag_flag);
+            // rows that were lights under the previous list lose their ordinal: the whole column is rewritten
+            CU(cudaMemsetAsync(ctx->d_light_ord, 0xFF, std::max<size_t>(ctx->cfg.max_entities, 1) * 4, st));
+            launch_tag_lights(st, R, ctx->lights, ctx->d_light_ord, ctx->d_tag_flag);
             uint32_t ok = 0;
             CU(cudaMemcpyAsync(&ok, ctx->d_tag_flag, 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
@@ -1052,8 +1195,11 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         }
         bool any_small = false;
         for (uint32_t x : ctx->pass_small) any_small |= x != 0;
-        tile_snap = ctx->lights_tagged && tile_kernel_is_tma() && !any_small;   // the 32-thread kernel does not publish snapshots
-        if (tile_snap) R.light_snap = ctx->d_light_snap + (size_t)cslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
+        tile_snap = ctx->lights_tagged && tile_kernel_publishes_light_snapshot() && !any_small;   // the 32-thread kernel does not publish snapshots
+        if (tile_snap) {
+            R.light_snap = ctx->d_light_snap + (size_t)cslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
+            R.light_ord = ctx->d_light_ord; R.n_lights = ctx->lights.n;
+        }
     }
     cudaEvent_t *pe = (ctx->profiling && ctx->prof_count < b200vis_ctx::kProfFrames) ? ctx->prof_ev[ctx->prof_count++] : nullptr;
     if (pe) CU(cudaEventRecord(pe[0], st));
@@ -1063,8 +1209,12 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
             for (uint32_t p = 0; p < n_pass; ++p) {
                 const uint32_t ns = p < ctx->pass_small.size() ? ctx->pass_small[p] : 0u, b = ctx->pass_begin[p];
                 if (ns) launch_propagate_cull_small(st, R, ctx->d_tiles + b, ns, cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot);
-                launch_propagate_cull(st, R, ctx->d_tiles + b + ns, ctx->pass_begin[p + 1] - b - ns,
-                                      cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot);
+                if (tile_kernel_is_warp())
+                    launch_tile_warp(st, R, ctx->d_wtiles + b + ns, ctx->d_sched, ctx->pass_begin[p + 1] - b - ns,
+                                     cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot, ctx->d_tile_counter);
+                else
+                    launch_propagate_cull(st, R, ctx->d_tiles + b + ns, ctx->pass_begin[p + 1] - b - ns,
+                                          cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot);
             }
         } else if (n_pass) {
             launch_cull(st, R, cvw, vb, ctx->d_stats, cslot);
@@ -1134,7 +1284,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         launch_pack_cluster_bindings(tail, fc, cl, ctx->bind, ctx->cfg.max_views);
     if (ctx->have_sink && (do_cull || (stages & B200VIS_STAGE_CLUSTER_LISTS)))
         launch_publish_clusters(tail, fc, cl, (stages & B200VIS_STAGE_CLUSTER_LISTS) ? ctx->sink_off_d : nullptr, ctx->sink_idx_d,
-                                ctx->sink.cluster_capacity, ctx->d_stats, ctx->sink_stats_d, cslot, frame + (do_cull ? 1u : 0u), ctx->cfg.max_views);
+                                ctx->sink.cluster_capacity, ctx->d_stats, ctx->sink_stats_d, do_cull ? cslot : (frame + 2u) % 3u, frame + (do_cull ? 1u : 0u), ctx->cfg.max_views);
     if (pe) CU(cudaEventRecord(pe[4], tail));
     if (pipelined) {
         if (has_lists) { CU(cudaEventRecord(ctx->ev_side[cslot], tail)); ctx->side_pending = true; }

@@ -29,6 +29,24 @@ struct Tile {               // one CTA's work: a contiguous, (mostly) hierarchy-
     uint32_t pad;
 };
 
+// The same tile as one WARP's work (k_tile_warp): the warp walks the tile in chunks of 32 schedule slots.  The schedule
+// (one byte per slot: local row, 0xFF = padding) lists the tile's rows in (in-tile depth, row) order, so that a row's
+// parent always sits in an earlier chunk or at a lower level of the same chunk; rows with in-tile children own one of
+// the warp's kWarpParentSlots shared-memory GlobalTransform slots.
+constexpr int kWarpParentSlots = 128;
+constexpr int kWarpChunks = kTileRows / 32;
+struct WarpTile {
+    uint32_t base;
+    uint16_t n_rows;
+    uint8_t n_chunks;         // schedule slots / 32
+    uint8_t contig;           // bit c: in chunk c, row - lane is the same for all occupied lanes (ballot bits map to mask bits)
+    uint32_t sched;           // index of the tile's 256-byte block in the schedule array
+    uint32_t pad;
+    uint32_t nonroot[kWarpChunks];   // per chunk: slots holding a row whose parent is in this tile
+};
+// wtopo word of k_tile_warp: depth[0:8) own parent-slot[8:15) parent's parent-slot[15:22) W_HAS_SLOT | T_* flags (bits 28-31)
+constexpr uint32_t W_HAS_SLOT = 1u << 22;   // the row has children in its own tile: it parks its GlobalTransform in a slot
+
 // SoA mirror of the ECS columns in HBM.  Every array is indexed by row.
 struct Rows {
     uint32_t n;
@@ -41,6 +59,7 @@ struct Rows {
     uint8_t *flags;          // B200VIS_F_* | F_TCHANGED
     uint8_t *state;          // S_*
     uint32_t *topo;          // T_* | local parent | local depth
+    const uint32_t *wtopo;   // T_* | depth | parent slots, for k_tile_warp
     const uint32_t *parent;  // global parent row (read only for T_EXT_PARENT rows)
     const uint64_t *layers;  // RenderLayers first block, or nullptr
     uint32_t *range;         // VisibleEntityRanges bitmask, or nullptr
@@ -52,8 +71,11 @@ struct Rows {
     const uint32_t *rank;    // position in Entity::to_bits() order, or nullptr when rank == row
     const uint32_t *row_of_rank;
     uint8_t *dirty;          // global TransformTreeChanged bytes (multi-pass plans only), or nullptr
-    float4 *light_snap;      // when non-null, rows flagged F_SPHERE_GT carry their light ordinal in bndA.x (tagged by
-                             //   k_tag_lights) and publish (translation, visible) here at the end of the tile pass
+    float4 *light_snap;      // when non-null, rows flagged F_SPHERE_GT look up their light ordinal in light_ord (written by
+                             //   k_tag_lights; 0xFFFFFFFF = not a light) and publish (translation, visible) here at the end
+                             //   of the tile pass
+    const uint32_t *light_ord;   // per row: ordinal in the b200vis_set_lights arrays, or 0xFFFFFFFF
+    uint32_t n_lights;
 };
 
 struct DevView {

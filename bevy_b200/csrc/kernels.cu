@@ -625,8 +625,10 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         if (active && out != st8) R.state[row] = (uint8_t)out;
         // a light row publishes what assign_objects_to_clusters needs of it (GlobalTransform::translation,
         // ViewVisibility::get) so that the cluster kernels never touch the row arrays again
-        if (CULL && R.light_snap != nullptr && (f & F_SPHERE_GT) && active)
-            R.light_snap[__float_as_uint(bA.x)] = make_float4(S.gt0[li].w, S.gt1[li].w, S.gt2[li].w, (out & 1u) ? 1.0f : 0.0f);
+        if (CULL && R.light_snap != nullptr && (f & F_SPHERE_GT) && active) {
+            const uint32_t ord = R.light_ord[row];     // 0xFFFFFFFF: a sphere-from-GT row that is not a current light
+            if (ord < R.n_lights) R.light_snap[ord] = make_float4(S.gt0[li].w, S.gt1[li].w, S.gt2[li].w, (out & 1u) ? 1.0f : 0.0f);
+        }
 
         // end of tile: everybody is done with this stage; count changes; write the tile's matrices back
         n_gt_total += (PROP && changed) ? 1u : 0u;      // per-thread tallies, reduced once at the end of the kernel
@@ -655,6 +657,283 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
     if ((lr & 31u) == 0) { if (n_gt_total) atomicAdd(&s_cnt[0], n_gt_total); if (n_vv_total) atomicAdd(&s_cnt[1], n_vv_total); }
     __syncthreads();
     if (lr == 0) {
+        if (s_cnt[0]) atomicAdd(&stats->changed[parity][0], s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&stats->changed[parity][1], s_cnt[1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 1w (default): the fused propagate -> cull pass with one WARP per tile and no CTA barrier at all.
+//
+// Why: the CTA-per-tile kernels above spend their time waiting -- the hierarchy walk of a 255-node tree is a chain of
+// 8 levels with one warp on the critical path and seven parked at a barrier (ncu round 1: barrier 28 % of stalls, issue
+// slots 62 % busy, ~1060 warp instructions per 32 rows of which ~100 only spin through empty level iterations).  Here a
+// warp owns a whole tile (<= 256 rows, <= 128 rows with children) and walks it in chunks of 32 schedule slots
+// (planner: rows in (depth, row) order, padded so that wide levels start on a chunk boundary).  Per chunk: coalesced
+// loads of the 32 rows' columns straight into registers, local affine, one matrix product per level present in the
+// chunk (one for all but the top chunk of a tree; __syncwarp between levels), set_if_neq, coalesced store of the changed
+// GlobalTransforms, then the cull of the same 32 rows from registers, one ballot per view.  Only rows WITH children
+// park their (new) GlobalTransform in shared memory (128 slots of 48 B per warp), where their children find it.
+// 32 independent warps per SM hide each other's load latency; nothing ever waits for another warp.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) WarpSmem {
+    float4 g0[kWarpParentSlots], g1[kWarpParentSlots], g2[kWarpParentSlots];
+    uint8_t pst[kWarpParentSlots];      // bit0 visited, bit1 gt changed
+    uint8_t dirty[kWarpParentSlots];    // TransformTreeChanged of the rows with children (slow path of the dirty phase)
+    uint8_t ppar[kWarpParentSlots];     // parent slot of each slot's row, 0xFF = none
+};
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+template <bool CULL, bool SIMPLE>
+__global__ void __launch_bounds__(kTileRows, 4)
+k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restrict__ sched, uint32_t n_tiles,
+            const __grid_constant__ CullViews cvw, VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity,
+            uint32_t *__restrict__ tile_counter) {
+    extern __shared__ __align__(16) uint8_t smem_warp[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    WarpSmem &s = reinterpret_cast<WarpSmem *>(smem_warp)[warp];
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything above overlapped the previous kernel's tail
+    uint32_t n_gt_total = 0, n_vv_total = 0;
+    const uint32_t wstride = gridDim.x * (kTileRows / 32);
+    uint32_t t = warp * gridDim.x + blockIdx.x;           // consecutive tiles go to different SMs
+    if (tile_counter != nullptr) { if (lane == 0) t = atomicAdd(tile_counter, 1u); t = __shfl_sync(kFull, t, 0); }
+    while (t < n_tiles) {
+        const WarpTile *tp = tiles + t;
+        const uint32_t base = tp->base, n_chunks = tp->n_chunks, contig_bits = tp->contig;
+        const uint32_t pad = (tp->n_rows == kTileRows) ? 0x100u : 0xFFu;   // a full tile has no padding: 0xFF is local row 255
+        const uint8_t *sch = sched + (size_t)tp->sched * kTileRows;
+        // ---- mark_dirty_trees (systems.rs:111-306) inside the tile.  Fast path: no row WITH an in-tile parent changed,
+        // so every row's TransformTreeChanged bit equals its own Changed<Transform> bit.
+        bool slow = false;
+        if (static_opt && R.dirty == nullptr) {
+            uint32_t any = 0;
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                const uint32_t local = sch[c * 32u + lane];
+                const uint32_t fl = (local != pad) ? R.flags[base + local] : 0u;
+                any |= __ballot_sync(kFull, fl & F_TCHANGED) & tp->nonroot[c];
+            }
+            slow = any != 0u;
+            if (slow) {
+                for (uint32_t c = 0; c < n_chunks; ++c) {       // parent-slot links of the rows with children
+                    const uint32_t local = sch[c * 32u + lane];
+                    if (local != pad) {
+                        const uint32_t wt = R.wtopo[base + local];
+                        if (wt & W_HAS_SLOT) {
+                            const uint32_t own = (wt >> 8) & 127u;
+                            s.ppar[own] = (uint8_t)((wt & 0xFFu) ? ((wt >> 15) & 127u) : 0xFFu);
+                            s.dirty[own] = 0;
+                        }
+                    }
+                }
+                __syncwarp();
+                for (uint32_t c = 0; c < n_chunks; ++c) {       // every Changed row marks its ancestors
+                    const uint32_t local = sch[c * 32u + lane];
+                    if (local != pad && (R.flags[base + local] & F_TCHANGED)) {
+                        const uint32_t wt = R.wtopo[base + local];
+                        uint32_t sl = (wt & W_HAS_SLOT) ? ((wt >> 8) & 127u) : ((wt & 0xFFu) ? ((wt >> 15) & 127u) : 0xFFu);
+                        while (sl != 0xFFu && !s.dirty[sl]) {   // benign race: every writer stores 1, every chain finishes
+                            s.dirty[sl] = 1;
+                            sl = s.ppar[sl];
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t local = sch[c * 32u + lane];
+            const bool active = local != pad;
+            const uint32_t row = base + (active ? local : 0u);
+            // ---- loads: everything the chunk needs, requested up front (11 independent coalesced loads per lane)
+            uint32_t f = 0, st8 = 0, wt = T_DETACHED;
+            float4 A = make_float4(0, 0, 0, 0), q = A, bA = A;
+            float2 C = make_float2(0, 0), bB = C;
+            Aff g; g.r0 = g.r1 = g.r2 = A;       // current GlobalTransform (old value until overwritten)
+            if (active) {
+                f = R.flags[row]; st8 = R.state[row]; wt = R.wtopo[row];
+                A = R.trsA[row]; q = R.trsB[row]; C = R.trsC[row];
+                g.r0 = R.gt0[row]; g.r1 = R.gt1[row]; g.r2 = R.gt2[row];
+            }
+            const uint32_t depth = wt & 0xFFu, own = (wt >> 8) & 127u, pp = (wt >> 15) & 127u;
+            const bool tchanged = f & F_TCHANGED;
+            const bool has_children = wt & T_HAS_CHILDREN;     // the reference's "has a Children component"
+            const bool has_slot = wt & W_HAS_SLOT;             // ... with children in this tile: they read this row's slot
+            bool dirty = tchanged;
+            if (static_opt) {
+                if (R.dirty != nullptr) dirty = active && R.dirty[row];      // multi-pass plan: k_mark_dirty_global ran first
+                else if (slow && has_slot) dirty = tchanged || s.dirty[own];
+            }
+            const Aff l = affine_from_trs(A, q, C);
+            const bool walk = active && !(wt & T_DETACHED);
+            // a detached row (ChildOf without a usable parent) is never visited, and neither is its subtree
+            if (active && (wt & T_DETACHED) && has_slot) s.pst[own] = 0;
+            const uint32_t lo = __reduce_min_sync(kFull, walk ? depth : 0xFFFFu), hi = __reduce_max_sync(kFull, walk ? depth : 0u);
+            bool visited = false, changed = false;
+            for (uint32_t lvl = lo; lvl <= hi; ++lvl) {        // lo == 0xFFFF (no row to walk) > hi: no iteration
+                __syncwarp();                                   // the parents' slots (earlier chunk / lower level) are written
+                if (walk && depth == lvl) {
+                    Aff n = l;
+                    if (depth == 0u) {
+                        if (wt & T_ROOT) {
+                            // flat entity: sync_simple_transforms (systems.rs:42-79); root with children:
+                            // unconditional write (systems.rs:525-530)
+                            visited = has_children ? (!static_opt || dirty) : tchanged;
+                            changed = visited;
+                        } else {                                // parent finished by an earlier pass: read it from HBM
+                            const uint32_t pr = R.parent[row];
+                            const uint32_t ps = R.state[pr];
+                            visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
+                            if (visited) {
+                                n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
+                                changed = row_neq(n.r0, g.r0) | row_neq(n.r1, g.r1) | row_neq(n.r2, g.r2);
+                            }
+                        }
+                    } else {                                    // propagate_descendants_unchecked (systems.rs:706-727)
+                        const uint32_t pst = s.pst[pp];
+                        visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                        if (visited) {
+                            n.r0 = affine_mul_row(s.g0[pp], l); n.r1 = affine_mul_row(s.g1[pp], l); n.r2 = affine_mul_row(s.g2[pp], l);
+                            changed = row_neq(n.r0, g.r0) | row_neq(n.r1, g.r1) | row_neq(n.r2, g.r2);   // set_if_neq
+                        }
+                    }
+                    if (changed) g = n;
+                    if (has_slot) {
+                        s.g0[own] = g.r0; s.g1[own] = g.r1; s.g2[own] = g.r2;
+                        s.pst[own] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+                    }
+                }
+            }
+            if (active) {
+                if (CULL) { bA = R.bndA[row]; bB = R.bndB[row]; }   // needed from here on: 32 warps per SM hide the latency
+                if (changed) { R.gt0[row] = g.r0; R.gt1[row] = g.r1; R.gt2[row] = g.r2; }
+                if (tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
+            }
+            uint32_t out = (st8 & (S_VV | S_HAS_CLASS)) | (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
+            bool vv_changed = false;
+            if (CULL) {
+                const bool in_query = active && !(f & F_NO_CPU_CULL);          // Without<NoCpuCulling>
+                const bool base_vis = in_query && (f & F_INHERITED);
+                const uint32_t prev = st8 & 1u;                                // reset_view_visibility: v = (v&1)<<1
+                const bool has_aabb = f & F_AABB;
+                const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
+                float cx, cy, cz, radius;
+                const float hx = bA.w, hy = bB.x, hz = bB.y;
+                if (has_aabb) {
+                    cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;
+                    cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
+                    cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+                    const float vx = (g.r0.x * hx + g.r0.y * hy) + g.r0.z * hz;
+                    const float vy = (g.r1.x * hx + g.r1.y * hy) + g.r1.z * hz;
+                    const float vz = (g.r2.x * hx + g.r2.y * hy) + g.r2.z * hz;
+                    radius = sqrtf((vx * vx + vy * vy) + vz * vz);
+                } else {
+                    const bool from_gt = f & F_SPHERE_GT;
+                    cx = from_gt ? g.r0.w : bA.x; cy = from_gt ? g.r1.w : bA.y; cz = from_gt ? g.r2.w : bA.z;
+                    radius = bA.w;
+                }
+                unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
+                if (!SIMPLE && active) {
+                    if (R.layers != nullptr) elayers = R.layers[row];
+                    if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
+                    if (R.rank != nullptr) rnk = R.rank[row];
+                }
+                // ballot bits map to mask bits when the occupied lanes hold consecutive rows (and rank == row)
+                const bool ballots = (SIMPLE || R.rank == nullptr) && ((contig_bits >> c) & 1u);
+                bool any = false;
+                uint32_t my_ballot = 0;
+#pragma unroll
+                for (uint32_t v = 0; v < kMaxViews; ++v) {
+                    if (v >= cvw.n_views) break;
+                    const uint32_t von = cvw.on[v];
+                    if (!(von & 1u)) continue;                                 // !camera.is_active (grid-uniform)
+                    if (SIMPLE && !(von & 4u)) continue;                       // bit2: the view includes the default layer
+                    bool vis = base_vis;
+                    if (!SIMPLE) {
+                        vis = vis && (cvw.layers[v] & elayers) != 0ull;
+                        if ((f & F_RANGE) && R.range != nullptr) {
+                            const int32_t ri = cvw.range_index[v];
+                            vis = vis && ri >= 0 && ((erange >> ri) & 1u);
+                        }
+                    }
+                    if (do_test && !(von & 2u)) {
+                        // Frustum::intersects_sphere, planes 0..4 (primitives.rs:255-268), branch-free
+                        const float d0 = plane_dot_point(cvw.planes[v][0], cx, cy, cz), d1 = plane_dot_point(cvw.planes[v][1], cx, cy, cz);
+                        const float d2 = plane_dot_point(cvw.planes[v][2], cx, cy, cz), d3 = plane_dot_point(cvw.planes[v][3], cx, cy, cz);
+                        const float d4 = plane_dot_point(cvw.planes[v][4], cx, cy, cz);
+                        const bool out_s = (d0 + radius <= 0.0f) | (d1 + radius <= 0.0f) | (d2 + radius <= 0.0f) |
+                                           (d3 + radius <= 0.0f) | (d4 + radius <= 0.0f);
+                        vis = vis && !out_s;
+                        if (vis && has_aabb) {
+                            // Frustum::intersects_obb(aabb, affine, true, false) (primitives.rs:272-294)
+                            const float d[5] = {d0, d1, d2, d3, d4};
+                            bool out_o = false;
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                const float4 n = cvw.planes[v][k];   // Aabb::relative_radius (primitives.rs:109-119)
+                                const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+                                const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+                                const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+                                const float rr = (dx * hx + dy * hy) + dz * hz;
+                                out_o |= (d[k] + rr <= 0.0f);
+                            }
+                            vis = !out_o;
+                        }
+                    }
+                    any |= vis;
+                    // entities without a VisibilityClass are set_visible() but not listed (mod.rs:846-857)
+                    const bool listed = vis && (st8 & S_HAS_CLASS);
+                    if (ballots) {
+                        const uint32_t b = __ballot_sync(kFull, listed);
+                        if (lane == v) my_ballot = b;
+                    } else if (listed) {
+                        uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
+                        uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
+                        atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+                        atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
+                    }
+                }
+                // warp-ballot compaction: lane v publishes view v's bits; the occupied lanes hold consecutive rows, so
+                // they touch at most two words of the rank-ordered mask
+                const uint32_t occupied = __ballot_sync(kFull, active);
+                const uint32_t first = occupied ? (uint32_t)__ffs(occupied) - 1u : 0u;
+                const uint32_t row_first = __shfl_sync(kFull, row, first);
+                if (my_ballot) {
+                    uint32_t *mask = vb.mask + (size_t)lane * vb.words_stride;
+                    uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + lane) * vb.chunks_stride;
+                    const uint32_t bits = my_ballot >> first, w0 = row_first >> 5, sh = row_first & 31u;
+                    const uint32_t lo_w = bits << sh, hi_w = sh ? (bits >> (32u - sh)) : 0u;
+                    if (lo_w) { atomicOr(mask + w0, lo_w); atomicAdd(cc + (w0 / kChunkWords), __popc(lo_w)); }
+                    if (hi_w) { atomicOr(mask + w0 + 1, hi_w); atomicAdd(cc + ((w0 + 1) / kChunkWords), __popc(hi_w)); }
+                }
+                if (in_query) {
+                    // set_visible + mark_newly_hidden_entities_invisible (mod.rs:292-306, 908-918)
+                    out = (out & ~S_VV) | (any ? (1u | (prev << 1)) : 0u);
+                    vv_changed = (any ? 1u : 0u) != prev;
+                    if (vv_changed) out |= S_VV_CHANGED;
+                }
+                if (R.light_snap != nullptr && (f & F_SPHERE_GT) && active) {
+                    const uint32_t ord = R.light_ord[row];     // 0xFFFFFFFF: a sphere-from-GT row that is not a current light
+                    if (ord < R.n_lights) R.light_snap[ord] = make_float4(g.r0.w, g.r1.w, g.r2.w, (out & 1u) ? 1.0f : 0.0f);
+                }
+            } else {
+                out |= st8 & S_VV_CHANGED;
+            }
+            if (active && out != st8) R.state[row] = (uint8_t)out;
+            n_gt_total += changed ? 1u : 0u;
+            n_vv_total += vv_changed ? 1u : 0u;
+        }
+        if (tile_counter != nullptr) { if (lane == 0) t = atomicAdd(tile_counter, 1u); t = __shfl_sync(kFull, t, 0); }
+        else t += wstride;
+    }
+    // block-reduce the per-thread tallies (warp shuffle, then one shared-memory atomic per warp)
+    __shared__ uint32_t s_cnt[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n_gt_total += __shfl_xor_sync(kFull, n_gt_total, o); n_vv_total += __shfl_xor_sync(kFull, n_vv_total, o); }
+    if (lane == 0) { if (n_gt_total) atomicAdd(&s_cnt[0], n_gt_total); if (n_vv_total) atomicAdd(&s_cnt[1], n_vv_total); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         if (s_cnt[0]) atomicAdd(&stats->changed[parity][0], s_cnt[0]);
         if (s_cnt[1]) atomicAdd(&stats->changed[parity][1], s_cnt[1]);
     }
@@ -776,8 +1055,10 @@ k_cull(Rows R, const __grid_constant__ CullViews cvw, VisibleBufs vb, DevStats *
         out = st8 & ~S_VV_CHANGED;
     }
     if (active && out != st8) R.state[row] = (uint8_t)out;
-    if (R.light_snap != nullptr && (f & F_SPHERE_GT) && active)
-        R.light_snap[__float_as_uint(bA.x)] = make_float4(g.r0.w, g.r1.w, g.r2.w, (out & 1u) ? 1.0f : 0.0f);
+    if (R.light_snap != nullptr && (f & F_SPHERE_GT) && active) {
+        const uint32_t ord = R.light_ord[row];
+        if (ord < R.n_lights) R.light_snap[ord] = make_float4(g.r0.w, g.r1.w, g.r2.w, (out & 1u) ? 1.0f : 0.0f);
+    }
     const uint32_t bv = __ballot_sync(0xFFFFFFFFu, vv_changed);
     if (lane == 0 && bv) atomicAdd(&stats->changed[parity][1], __popc(bv));
 }
@@ -810,12 +1091,17 @@ k_expand_visible(VisibleBufs vb, DiffBufs db, const uint32_t *__restrict__ row_o
     __shared__ uint32_t s_warp[32], s_diff[32];
     __shared__ uint32_t s_base, s_total;
     const uint32_t v = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
-    if (v >= fc->n_views) return;
     uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
     const uint32_t zslot = (parity + 2u) % 3u;   // the slot frame f+2 will accumulate into
     uint32_t *cc_next = vb.chunk_count + ((size_t)zslot * kMaxViews + v) * vb.chunks_stride;
+    // every view of the grid re-arms its counters, also the ones beyond this frame's view count: the count may rise
+    // again by frame f+2, and nothing else clears the slot
     if (t == 0) cc_next[chunk] = 0;
     if (chunk == 0 && v == 0 && t < 2) stats->changed[zslot][t] = 0;
+    if (v >= fc->n_views) {
+        if (db.prev != nullptr && t == 0) db.chunk[(size_t)v * vb.chunks_stride + chunk] = 0;
+        return;
+    }
     if (!(fc->views[v].flags & 1u)) {         // inactive view: VisibleEntities untouched (mod.rs:780-782)
         if (db.prev != nullptr && t == 0) db.chunk[(size_t)v * vb.chunks_stride + chunk] = 0;   // ... so nothing added / removed
         return;
@@ -1239,15 +1525,15 @@ k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__
     // NOTE: the slab is zeroed for the next frame by k_cluster_clear (a CTA here may still be re-counting it)
 }
 
-// set_lights: store each light's ordinal in the (unused) centre.x of its sphere-from-GT bounds so the tile kernel can
-// publish the light snapshot itself; *all_tagged is cleared if some light row is not F_SPHERE_GT (then the separate
-// snapshot kernel is used instead)
-__global__ void k_tag_lights(Rows R, Lights L, uint32_t *__restrict__ all_tagged) {
+// set_lights: write each light's ordinal into the per-row light_ord column (cleared to 0xFFFFFFFF by the caller) so that the
+// tile kernel can publish the light snapshot itself; *all_tagged is cleared if some light row is not a sphere-from-GT row or
+// two lights share a row (then the separate snapshot kernel is used instead)
+__global__ void k_tag_lights(Rows R, Lights L, uint32_t *__restrict__ light_ord, uint32_t *__restrict__ all_tagged) {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= L.n) return;
     const uint32_t row = L.row[li];
     if (row < R.n && (R.flags[row] & F_SPHERE_GT) && !(R.flags[row] & F_AABB)) {
-        float4 b = R.bndA[row]; b.x = __uint_as_float(li); R.bndA[row] = b;
+        if (atomicCAS(light_ord + row, 0xFFFFFFFFu, li) != 0xFFFFFFFFu) *all_tagged = 0;
     } else {
         *all_tagged = 0;
     }
@@ -1673,15 +1959,56 @@ __global__ void k_pack_state(Rows R, uint32_t first, uint32_t count, uint8_t *__
 // ------------------------------------------------------------------------------------------
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
-static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged
+static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile, 2 warp per tile (default)
 static int tile_kernel_choice() {
     if (g_tile_kernel < 0) {
         const char *e = getenv("B200VIS_TILE_KERNEL");
-        g_tile_kernel = (e && e[0] == 'c') ? 0 : 1;
+        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 't') ? 1 : 2;
     }
     return g_tile_kernel;
 }
 bool tile_kernel_is_tma() { return tile_kernel_choice() == 1; }
+bool tile_kernel_publishes_light_snapshot() { return tile_kernel_choice() != 0; }
+template <bool C, bool S>
+static void launch_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, const uint8_t *sched, uint32_t n_tiles, const CullViews &cvw,
+                        const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity, uint32_t *counter) {
+    constexpr size_t smem = (kTileRows / 32) * sizeof(WarpSmem);
+    static int grid = 0, dynamic = 0;
+    if (!grid) {
+        cudaFuncSetAttribute(k_tile_warp<C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_warp<C, S>, kTileRows, smem);
+        // B200VIS_WARP_CTAS_PER_SM=k (< occupancy) leaves part of every SM to the previous frame's tail kernels
+        const char *e = getenv("B200VIS_WARP_CTAS_PER_SM");
+        if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e);
+        grid = sms * (per_sm > 0 ? per_sm : 1);
+        const char *d = getenv("B200VIS_WARP_DYNAMIC");   // tiles handed out by an atomic counter instead of a fixed stride
+        dynamic = (d && atoi(d)) ? 1 : 0;
+    }
+    const uint32_t need = (n_tiles + (kTileRows / 32) - 1) / (kTileRows / 32);
+    const uint32_t g = need < (uint32_t)grid ? need : (uint32_t)grid;
+    uint32_t *ctr = nullptr;
+    if (dynamic && counter != nullptr) { cudaMemsetAsync(counter, 0, 4, st); ctr = counter; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g); cfg.blockDim = dim3(kTileRows); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_tile_warp<C, S>, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, ctr);
+}
+void launch_tile_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, const uint8_t *sched, uint32_t n_tiles, const CullViews &cvw,
+                      const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity, uint32_t *counter) {
+    if (n_tiles == 0) return;
+    const bool cull = stages & 2u;
+    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+    if (cull) { if (simple) launch_warp<true, true>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter);
+                else launch_warp<true, false>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter); }
+    else launch_warp<false, true>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter);
+}
+bool tile_kernel_is_warp() { return tile_kernel_choice() == 2; }
 template <bool P, bool C, bool S>
 static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                        const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity) {
@@ -1796,8 +2123,8 @@ void launch_shadow_cull(cudaStream_t st, const Rows &R, const ShadowBufs &sb, co
 void launch_pack_cluster_bindings(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, const BindingBufs &bb, uint32_t max_views) {
     if (bb.mode) k_pack_cluster_bindings<<<dim3(16, max_views), 256, 0, st>>>(fc, cb, bb);
 }
-void launch_tag_lights(cudaStream_t st, const Rows &R, const Lights &L, uint32_t *all_tagged) {
-    if (L.n) k_tag_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, all_tagged);
+void launch_tag_lights(cudaStream_t st, const Rows &R, const Lights &L, uint32_t *light_ord, uint32_t *all_tagged) {
+    if (L.n) k_tag_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, light_ord, all_tagged);
 }
 void launch_snapshot_lights(cudaStream_t st, const Rows &R, const Lights &L, float4 *snap) {
     if (L.n) k_snapshot_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, snap);

@@ -170,9 +170,9 @@ def test_execution_plan_shapes():
     assert passes == 3 and ext > 0 and tiles >= sc.n // 256
     flat = np.full(1000, bb.NO_PARENT, np.uint32)                    # config #2 shape: flat
     assert bb.host_plan_summary(flat) == (4, 1, 1, 0)
-    chain = np.array([bb.NO_PARENT] + list(range(599)), np.uint32)   # a 600-deep chain: one pass per tile
-    tiles, passes, levels, ext = bb.host_plan_summary(chain)
-    assert tiles == 3 and passes == 3 and levels == 256 and ext == 2
+    chain = np.array([bb.NO_PARENT] + list(range(599)), np.uint32)   # a 600-deep chain: one pass per tile; a tile holds
+    tiles, passes, levels, ext = bb.host_plan_summary(chain)         # at most 128 rows WITH in-tile children (+ the last child)
+    assert tiles == 5 and passes == 5 and levels == 129 and ext == 4
     with pytest.raises(bb.B200VisError) as e:
         bb.host_plan_summary(np.array([1, 2, 0], np.uint32))
     assert e.value.code == 4                                         # cycle

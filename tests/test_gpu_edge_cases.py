@@ -328,3 +328,92 @@ def test_step_call_equals_the_piecewise_sequence():
                 assert (oa == ob).all() and (ia == ib).all()
     finally:
         a.close(); b.close()
+
+
+def test_sphere_from_gt_rows_that_are_not_lights_and_changing_light_lists():
+    """Rows flagged F_SPHERE_FROM_GT that were never passed to set_lights (e.g. spot lights, whose Sphere is GT-centred too,
+    spot_light.rs:221) must not disturb the light snapshot the tile kernel publishes; neither may rows that stop being
+    lights when the list changes.  (The snapshot is keyed on a per-row light-ordinal column, not on the bounds.)"""
+    sc = scenes.forest(n_trees=30, levels=6, n_lights=24)
+    L = len(sc.light_row)
+    keep = np.arange(0, L, 2)                      # only every other sphere-from-GT row is a clustered light
+    sc.bounds[sc.light_row, 0] = np.linspace(0.0, 1.0, L, dtype=np.float32)   # centre.x is user data now (0.0f and 1.0f included)
+    all_rows, all_range = sc.light_row.copy(), sc.light_range.copy()
+    sc.light_row, sc.light_range = all_rows[keep], all_range[keep]
+    pipe = bb.VisibilityPipeline(sc, max_lights=L)
+    world = OracleWorld(sc)
+    try:
+        for f in range(4):
+            if f == 2:                             # the list changes: the other half becomes the light set
+                other = np.arange(1, L, 2)
+                sc.light_row, sc.light_range = all_rows[other], all_range[other]
+                pipe.ctx.set_lights(sc.light_row, sc.light_range, None)
+            if f:
+                scenes.advance_cameras(sc, 0.05)
+                rows, trs = scenes.mutate_roots(sc, f)
+                pipe.ctx.upload_transforms_scattered(rows, trs)
+                world.tchanged[rows] = 1
+            pipe.update_views()
+            compare_frame(pipe, world, f)
+    finally:
+        pipe.close()
+
+
+def test_view_count_drops_and_rises_again():
+    """2 -> 1 -> 2 cameras through b200vis_step (which sets the view count every frame): the per-view chunk counters of the
+    view that paused must not carry counts over (visible_count / list bases would be inflated)."""
+    sc = scenes.forest(n_trees=150, levels=6, n_lights=8)
+    sc.cameras = sc.cameras[:2]
+    pipe = bb.VisibilityPipeline(sc)
+    ref = bb.VisibilityPipeline(scenes.forest(n_trees=150, levels=6, n_lights=8))     # never pauses a view
+    ref.scene.cameras = ref.scene.cameras[:2]
+    try:
+        def cams(scene, k):
+            arr = (bb.CameraDesc * k)()
+            for v, cam in enumerate(scene.cameras[:k]):
+                arr[v].global_transform[:] = cam.gt.tolist()
+                arr[v].fov_y, arr[v].aspect, arr[v].near_z, arr[v].far_z = cam.fov, cam.aspect, cam.near, cam.far
+                arr[v].layer_mask, arr[v].flags, arr[v].range_view_index = 1, bb.VIEW_ACTIVE, -1
+            return arr
+        for f, k in enumerate([2, 2, 1, 1, 1, 2, 2, 2]):
+            for p in (pipe, ref):
+                scenes.advance_cameras(p.scene, 0.04)
+            pipe.ctx.step(0, 0, 0, cams(sc, k), k, None, wait=True)
+            ref.ctx.step(0, 0, 0, cams(ref.scene, 2), 2, None, wait=True)
+            for v in range(k):
+                got, want = pipe.ctx.download_visible(v), ref.ctx.download_visible(v)
+                assert len(got) == len(want) and (got == want).all(), f"frame {f} view {v}: {len(got)} vs {len(want)}"
+    finally:
+        pipe.close(); ref.close()
+
+
+def test_result_sink_stats_through_step_with_clusters():
+    """b200vis_step runs the cluster stages in a second b200vis_run call: the change counters in the sink must still be the
+    CULL frame's (they were read from the next frame's already-zeroed slot)."""
+    torch = pytest.importorskip("torch")
+    import ctypes
+    sc = scenes.forest(n_trees=60, levels=6, n_lights=24)
+    pipe = bb.VisibilityPipeline(sc)
+    V = len(sc.cameras)
+    st_t = torch.zeros(ctypes.sizeof(bb.FrameStats), dtype=torch.uint8).pin_memory()
+    st = bb.FrameStats.from_address(st_t.data_ptr())
+    try:
+        pipe.ctx.set_result_sink(st_t.data_ptr(), None, None, None)
+        for f in range(4):
+            scenes.advance_cameras(sc, 0.05)
+            rows, trs = scenes.mutate_roots(sc, f + 1)
+            r = np.ascontiguousarray(rows, np.uint32); t_ = np.ascontiguousarray(trs, np.float32)
+            arr = (bb.CameraDesc * V)()
+            for v, cam in enumerate(sc.cameras):
+                arr[v].global_transform[:] = cam.gt.tolist()
+                arr[v].fov_y, arr[v].aspect, arr[v].near_z, arr[v].far_z = cam.fov, cam.aspect, cam.near, cam.far
+                arr[v].layer_mask, arr[v].flags, arr[v].range_view_index = 1, bb.VIEW_ACTIVE, -1
+            pipe.ctx.step(len(r), r.ctypes.data, t_.ctypes.data, arr, V, pipe.cluster_config, wait=True)
+            got = (st.gt_changed_count, st.vv_changed_count, st.frame)
+            ref = pipe.ctx.download_frame_stats()
+            assert got == (ref.gt_changed_count, ref.vv_changed_count, ref.frame), (f, got)
+            _, ch = pipe.ctx.download_global_transforms(0, sc.n)
+            assert got[0] == int(ch.sum()) and got[0] > 0
+        pipe.ctx.set_result_sink(None, None, None, None)
+    finally:
+        pipe.close()
