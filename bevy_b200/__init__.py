@@ -7,7 +7,7 @@ systems.  It never imports ``oracle`` and has no CPU fallback: creating a
 context without a CUDA device raises.
 """
 from .abi import (  # noqa: F401
-    B200VisError, CameraDesc, ResultSink, Context, ClusterConfig, ClusterFeedback, ClusterView, FrameStats, View,
+    B200VisError, CameraDesc, ColumnSinks, ResultSink, Context, ClusterConfig, ClusterFeedback, ClusterView, FrameStats, View,
     abi_version, host_cluster_view_setup, host_compute_frustum, host_default_cluster_config,
     host_perspective, host_plan_summary, host_z_slice_thresholds, load_library, plan_row_order,
     NO_PARENT, DETACHED, F_INHERITED_VISIBLE, F_HAS_AABB, F_HAS_SPHERE, F_NO_FRUSTUM_CULLING,

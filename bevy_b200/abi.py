@@ -83,6 +83,11 @@ class FrameStats(C.Structure):
                 ("pad", C.c_uint32)]
 
 
+class ColumnSinks(C.Structure):
+    _fields_ = [("global_transforms", C.c_void_p), ("gt_stride_floats", C.c_uint32), ("gt_changed_bits", C.c_void_p),
+                ("view_visibility", C.c_void_p), ("vv_changed_bits", C.c_void_p)]
+
+
 class ResultSink(C.Structure):
     _fields_ = [("stats", C.POINTER(FrameStats)), ("visible_rows", C.c_void_p), ("visible_capacity", C.c_uint32),
                 ("cluster_offsets", C.c_void_p), ("cluster_indices", C.c_void_p), ("cluster_capacity", C.c_uint32)]
@@ -103,6 +108,8 @@ _SIGNATURES = {
     "b200vis_join": (C.c_int32, [_vp]),
     "b200vis_tail_stream": (C.c_int32, [_vp, _P(_vp)]),
     "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
+    "b200vis_set_column_sinks": (C.c_int32, [_vp, _P(ColumnSinks)]),
+    "b200vis_writeback_columns": (C.c_int32, [_vp]),
     "b200vis_host_plan_summary": (C.c_int32, [C.c_uint32, _vp, _P(C.c_uint32)]),
     "b200vis_host_warp_plan": (C.c_int32, [C.c_uint32, _vp, C.c_uint32, C.c_uint32, _P(C.c_uint32), _vp, _vp, _vp, _vp]),
     "b200vis_plan_row_order": (C.c_int32, [C.c_uint32, _vp, _vp]),
@@ -404,10 +411,11 @@ class Context:
         self._check(self._lib.b200vis_collect_stage_times_ms(self._h, C.byref(a), C.byref(b_), C.byref(c), C.byref(n)))
         return a.value, b_.value, c.value, n.value
 
-    def step(self, n_changed, rows_ptr, trs_ptr, cameras, n_cameras, cluster_config=None, wait=True):
+    def step(self, n_changed, rows_ptr, trs_ptr, cameras, n_cameras, cluster_config=None, wait=True, writeback=False):
         """b200vis_step: `cameras` is a ctypes array of CameraDesc."""
         self._check(self._lib.b200vis_step(self._h, n_changed, _vp(rows_ptr), _vp(trs_ptr), n_cameras, cameras,
-                                           None if cluster_config is None else C.byref(cluster_config), 1 if wait else 0))
+                                           None if cluster_config is None else C.byref(cluster_config),
+                                           (1 if wait else 0) | (2 if writeback else 0)))
 
     def run(self, stages=STAGE_ALL):
         self._check(self._lib.b200vis_run(self._h, stages))
@@ -539,6 +547,25 @@ class Context:
         s.cluster_capacity = 0 if cluster_indices is None else cluster_indices.shape[1]
         self._sink = (s, visible_rows, cluster_offsets, cluster_indices)
         self._check(self._lib.b200vis_set_result_sink(self._h, C.byref(s)))
+
+    def set_column_sinks(self, gt=None, gt_changed_bits=None, view_visibility=None, vv_changed_bits=None):
+        """b200vis_set_column_sinks: numpy arrays over (ideally pinned) host memory; gt is [n, 12] or [n, 16] float32.
+        All None removes the sinks."""
+        if gt is None and gt_changed_bits is None and view_visibility is None and vv_changed_bits is None:
+            self._check(self._lib.b200vis_set_column_sinks(self._h, None))
+            self._colsink_keep = None
+            return
+        s = ColumnSinks()
+        s.global_transforms = None if gt is None else gt.ctypes.data
+        s.gt_stride_floats = 0 if gt is None else gt.shape[1]
+        s.gt_changed_bits = None if gt_changed_bits is None else gt_changed_bits.ctypes.data
+        s.view_visibility = None if view_visibility is None else view_visibility.ctypes.data
+        s.vv_changed_bits = None if vv_changed_bits is None else vv_changed_bits.ctypes.data
+        self._colsink_keep = (gt, gt_changed_bits, view_visibility, vv_changed_bits)
+        self._check(self._lib.b200vis_set_column_sinks(self._h, C.byref(s)))
+
+    def writeback_columns(self):
+        self._check(self._lib.b200vis_writeback_columns(self._h))
 
     def p2p_export(self):
         """CUDA IPC handle (64 bytes) of this rank's gathered buffer."""

@@ -137,6 +137,8 @@ struct b200vis_ctx {
     b200vis_result_sink sink{}; bool have_sink = false;
     uint32_t *sink_rows_d = nullptr, *sink_off_d = nullptr, *sink_idx_d = nullptr, *sink_stats_d = nullptr;
 
+    b200vis_column_sinks colsink{}; bool have_colsink = false;          // b200vis_set_column_sinks (device aliases below)
+    float *col_gt_d = nullptr; uint32_t *col_gt_bits_d = nullptr, *col_vv_bits_d = nullptr; uint8_t *col_vv_d = nullptr;
     double step_t[6] = {0, 0, 0, 0, 0, 0}; uint64_t step_n = 0;   // B200VIS_STEP_TRACE: host time per phase of b200vis_step
     void *nccl_comm = nullptr;          // b200vis_comm_init
     uint32_t *d_gather = nullptr;       // [world][slab] when the library owns the exchange
@@ -1236,8 +1238,11 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     // the slab push / all-gather are issued before the visible-list expansion (they do not depend on it), and the peers'
     // data travels while this rank expands its lists.
     const bool exchange_first = has_assign && has_lists && cl.world > 1;
+    bool fused_clusters = false;     // single GPU, both cluster stages in this call: one launch does assign + lists
     auto issue_assign_and_exchange = [&]() -> int32_t {
-        if (stages & B200VIS_STAGE_CLUSTER_ASSIGN)
+        if (has_assign && has_lists && cl.world == 1 && ctx->ext_send == nullptr && lights.n)
+            fused_clusters = launch_cluster_fused(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+        if ((stages & B200VIS_STAGE_CLUSTER_ASSIGN) && !fused_clusters)
             launch_cluster_assign(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
         if (has_assign && has_lists && cl.world > 1) {
             if (ctx->p2p_ready) {
@@ -1278,7 +1283,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     }
     if (pe) CU(cudaEventRecord(pe[3], tail));
     if (!exchange_first) { const int32_t rc = issue_assign_and_exchange(); if (rc) return rc; }
-    if (stages & B200VIS_STAGE_CLUSTER_LISTS)
+    if ((stages & B200VIS_STAGE_CLUSTER_LISTS) && !fused_clusters)
         launch_cluster_lists(tail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if ((stages & B200VIS_STAGE_CLUSTER_LISTS) && ctx->bind.mode)
         launch_pack_cluster_bindings(tail, fc, cl, ctx->bind, ctx->cfg.max_views);
@@ -1680,6 +1685,38 @@ extern "C" int32_t b200vis_set_result_sink(b200vis_ctx *ctx, const b200vis_resul
     return B200VIS_OK;
 }
 
+extern "C" int32_t b200vis_set_column_sinks(b200vis_ctx *ctx, const b200vis_column_sinks *sinks) {
+    CHECK_CTX_JOIN();
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_colsink = false;
+    ctx->col_gt_d = nullptr; ctx->col_gt_bits_d = nullptr; ctx->col_vv_bits_d = nullptr; ctx->col_vv_d = nullptr;
+    if (!sinks) return B200VIS_OK;
+    if (sinks->global_transforms && sinks->gt_stride_floats != 12 && sinks->gt_stride_floats != 16)
+        return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_column_sinks: gt_stride_floats must be 12 or 16");
+    const size_t N = ctx->cfg.max_entities, W = (N + 31) / 32;
+    int32_t rc;
+    uint32_t *d = nullptr;
+    if ((rc = map_host(ctx, sinks->global_transforms, N * sinks->gt_stride_floats * 4, &d))) return rc;
+    ctx->col_gt_d = reinterpret_cast<float *>(d);
+    if ((rc = map_host(ctx, sinks->gt_changed_bits, W * 4, &ctx->col_gt_bits_d))) return rc;
+    if ((rc = map_host(ctx, sinks->view_visibility, N, &d))) return rc;
+    ctx->col_vv_d = reinterpret_cast<uint8_t *>(d);
+    if ((rc = map_host(ctx, sinks->vv_changed_bits, W * 4, &ctx->col_vv_bits_d))) return rc;
+    ctx->colsink = *sinks;
+    ctx->have_colsink = true;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_writeback_columns(b200vis_ctx *ctx) {
+    CHECK_CTX();
+    if (!ctx->have_colsink) return fail(ctx, B200VIS_ERR_NOT_READY, "writeback_columns: call b200vis_set_column_sinks first");
+    // on the main stream, right behind the tile pass (and the shadow-culling stage, if the caller ran it): the tail of the
+    // frame (list expansion, clusters) runs beside it on the side stream, the next frame's tile pass behind it
+    launch_writeback_columns(ctx->stream, ctx->rows, ctx->col_gt_d, ctx->colsink.gt_stride_floats, ctx->col_gt_bits_d, ctx->col_vv_d,
+                             ctx->col_vv_bits_d);
+    CU(cudaGetLastError());
+    return B200VIS_OK;
+}
+
 extern "C" int32_t b200vis_download_frame(b200vis_ctx *ctx, b200vis_frame_stats *stats, uint32_t *visible_rows,
                                           uint32_t visible_capacity, uint32_t *cluster_offsets,
                                           uint32_t *cluster_indices, uint32_t cluster_capacity) {
@@ -1735,6 +1772,7 @@ extern "C" int32_t b200vis_step(b200vis_ctx *ctx, uint32_t n_changed, const uint
         if ((rc = b200vis_update_camera(ctx, v, &cameras[v], nullptr, nullptr, nullptr))) return rc;
     lap(1);
     if ((rc = b200vis_run(ctx, B200VIS_STAGE_PROPAGATE | B200VIS_STAGE_CULL))) return rc;
+    if ((flags & B200VIS_STEP_WRITEBACK) && (rc = b200vis_writeback_columns(ctx))) return rc;
     lap(2);
     if (clusters) {
         for (uint32_t v = 0; v < n_cameras; ++v)

@@ -1266,6 +1266,96 @@ __device__ __forceinline__ uint3 ndc_to_cluster(const DevClusterView &cv, const 
 
 constexpr uint32_t kStagedPlanes = 512;   // plane tables up to this many entries are staged in shared memory
 
+// One light against one view's froxel grid, executed by a warp (lanes split the (z, y) rows): frustum test, view-space
+// AABB -> cluster range, iterative sphere refinement; `set(ci)` is called for every cluster the light touches.  Returns
+// false if the light is rejected before the grid walk; `far_out` (lane 0) receives the light's farthest_z candidate.
+struct ClusterTables { const float *thr; const float4 *xp, *yp, *zp; };
+template <typename SetBit>
+__device__ __forceinline__ bool assign_one_light(const DevClusterView &cv, const ClusterTables &tb, float px, float py, float pz, float range,
+                                                 uint32_t lane, float &far_out, uint32_t &count, SetBit set) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)                                         // frustum.intersects_sphere(.., true)
+        if (plane_dot_point(cv.frustum[k], px, py, pz) + range <= 0.0f) return false;
+    const float *thr = tb.thr;
+    const bool ortho = cv.is_ortho;
+    // cluster_space_clusterable_object_aabb (assign.rs:948-1036)
+    const float4 vc = mat4_mul_point(cv.vfw, px, py, pz);
+    const float hx = range * fabsf(cv.scale[0]), hy = range * fabsf(cv.scale[1]), hz = range * fabsf(cv.scale[2]);
+    const float minx = vc.x - hx, miny = vc.y - hy, maxx = vc.x + hx, maxy = vc.y + hy;
+    const float minz = fminf(vc.z - hz, -1.17549435e-38f), maxz = fminf(vc.z + hz, -1.17549435e-38f);
+    float nminx, nminy, nmaxx, nmaxy;
+    {
+        const float4 a = mat4_mul_point(cv.cfv, minx, miny, minz), b = mat4_mul_point(cv.cfv, minx, miny, maxz);
+        const float4 c = mat4_mul_point(cv.cfv, maxx, maxy, minz), d = mat4_mul_point(cv.cfv, maxx, maxy, maxz);
+        const float ax = a.x / a.w, ay = a.y / a.w, bx = b.x / b.w, by = b.y / b.w;
+        const float cx = c.x / c.w, cy = c.y / c.w, dx = d.x / d.w, dy = d.y / d.w;
+        nminx = gl_min(gl_min(gl_min(ax, bx), cx), dx); nminy = gl_min(gl_min(gl_min(ay, by), cy), dy);
+        nmaxx = gl_max(gl_max(gl_max(ax, bx), cx), dx); nmaxy = gl_max(gl_max(gl_max(ay, by), cy), dy);
+        nminx = gl_min(gl_max(nminx, -1.0f), 1.0f); nminy = gl_min(gl_max(nminy, -1.0f), 1.0f);
+        nmaxx = gl_min(gl_max(nmaxx, -1.0f), 1.0f); nmaxy = gl_min(gl_max(nmaxy, -1.0f), 1.0f);
+    }
+    const uint3 c0 = ndc_to_cluster(cv, thr, nminx, nminy, minz), c1 = ndc_to_cluster(cv, thr, nmaxx, nmaxy, maxz);
+    const uint3 lo = make_uint3(min(c0.x, c1.x), min(c0.y, c1.y), min(c0.z, c1.z));
+    const uint3 hi = make_uint3(max(c0.x, c1.x), max(c0.y, c1.y), max(c0.z, c1.z));
+    // view-space sphere (assign.rs:551-556)
+    const float sr = range * cv.scale_max;
+    {
+        // farthest_z (assign.rs:558-561): -row2 . (t,1) + range*scale.z ; fmax against 0
+        const float4 r2 = make_float4(cv.vfw[2], cv.vfw[6], cv.vfw[10], cv.vfw[14]);
+        far_out = -plane_dot_point(r2, px, py, pz) + range * cv.scale[2];
+    }
+    const float4 cc = mat4_mul_point(cv.cfv, vc.x, vc.y, vc.z);
+    const float ndx = cc.x / cc.w, ndy = cc.y / cc.w, ndz = cc.z / cc.w;
+    const uint3 ccl = ndc_to_cluster(cv, thr, ndx, ndy, vc.z);
+    const bool has_zc = ndz <= 1.0f; const uint32_t zc = ccl.z;
+    bool has_yc; uint32_t yc = 0;
+    if (ndy > 1.0f) has_yc = false;
+    else if (ndy < -1.0f) { has_yc = true; yc = cv.dims[1] + 1; }
+    else { has_yc = true; yc = ccl.y; }
+
+    const float4 *xp = tb.xp, *yp = tb.yp, *zp = tb.zp;
+    const uint32_t ny = hi.y - lo.y + 1, npairs = (hi.z - lo.z + 1) * ny;
+    for (uint32_t p = lane; p < npairs; p += 32) {
+        const uint32_t z = lo.z + p / ny, y = lo.y + p % ny;
+        float ox = vc.x, oy = vc.y, oz = vc.z, orad = sr;
+        if (!has_zc || z != zc) {                                  // project_to_plane_z (assign.rs:1094-1113)
+            const float4 pl = (has_zc && z < zc) ? zp[z + 1] : zp[z];
+            const float zz = pl.w / pl.z;
+            const float dist = zz - oz;
+            if (fabsf(dist) > orad) continue;
+            oz = zz;
+            orad = sqrtf(orad * orad - dist * dist);
+        }
+        if (!has_yc || y != yc) {                                  // project_to_plane_y (assign.rs:1116-1134)
+            const float4 pl = (has_yc && y < yc) ? yp[y + 1] : yp[y];
+            const float dist = ortho ? pl.w - oy : -(oy * pl.y + oz * pl.z);
+            if (fabsf(dist) > orad) continue;
+            ox = ox + dist * pl.x; oy = oy + dist * pl.y; oz = oz + dist * pl.z;
+            orad = sqrtf(orad * orad - dist * dist);
+        }
+        uint32_t min_x = lo.x;                                     // assign.rs:647-675, get_distance_x :1081-1091
+        while (true) {
+            if (min_x >= hi.x) break;
+            const float4 pl = xp[min_x + 1];
+            const float dx = ortho ? ox - pl.w : pl.x * ox + pl.z * oz;
+            if (-dx + orad > 0.0f) break;
+            ++min_x;
+        }
+        uint32_t max_x = hi.x;
+        while (true) {
+            if (max_x <= min_x) break;
+            const float4 pl = xp[max_x];
+            const float dx = ortho ? ox - pl.w : pl.x * ox + pl.z * oz;
+            if (dx + orad > 0.0f) break;
+            --max_x;
+        }
+        uint32_t ci = (y * cv.dims[0] + min_x) * cv.dims[2] + z;   // assign.rs:676-678
+        for (uint32_t x = min_x; x <= max_x; ++x) { set(ci); ci += cv.dims[2]; }
+        count += max_x - min_x + 1;
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(256)
 k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__restrict__ stats) {
     __shared__ float4 s_planes[kStagedPlanes];
@@ -1302,96 +1392,165 @@ k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBu
     const unsigned long long ll = L.layers ? L.layers[li] : 1ull;
     if (!(cv.layer_mask & ll)) return;                                  // assign.rs:489
     const float range = L.range[li];
-#pragma unroll
-    for (int k = 0; k < 6; ++k)                                         // frustum.intersects_sphere(.., true)
-        if (plane_dot_point(cv.frustum[k], px, py, pz) + range <= 0.0f) return;
-
-    const float *thr = staged ? s_thr : cb.blob + cv.thr_off;
-    const bool ortho = cv.is_ortho;
-    // cluster_space_clusterable_object_aabb (assign.rs:948-1036)
-    const float4 vc = mat4_mul_point(cv.vfw, px, py, pz);
-    const float hx = range * fabsf(cv.scale[0]), hy = range * fabsf(cv.scale[1]), hz = range * fabsf(cv.scale[2]);
-    const float minx = vc.x - hx, miny = vc.y - hy, maxx = vc.x + hx, maxy = vc.y + hy;
-    const float minz = fminf(vc.z - hz, -1.17549435e-38f), maxz = fminf(vc.z + hz, -1.17549435e-38f);
-    float nminx, nminy, nmaxx, nmaxy;
-    {
-        const float4 a = mat4_mul_point(cv.cfv, minx, miny, minz), b = mat4_mul_point(cv.cfv, minx, miny, maxz);
-        const float4 c = mat4_mul_point(cv.cfv, maxx, maxy, minz), d = mat4_mul_point(cv.cfv, maxx, maxy, maxz);
-        const float ax = a.x / a.w, ay = a.y / a.w, bx = b.x / b.w, by = b.y / b.w;
-        const float cx = c.x / c.w, cy = c.y / c.w, dx = d.x / d.w, dy = d.y / d.w;
-        nminx = gl_min(gl_min(gl_min(ax, bx), cx), dx); nminy = gl_min(gl_min(gl_min(ay, by), cy), dy);
-        nmaxx = gl_max(gl_max(gl_max(ax, bx), cx), dx); nmaxy = gl_max(gl_max(gl_max(ay, by), cy), dy);
-        nminx = gl_min(gl_max(nminx, -1.0f), 1.0f); nminy = gl_min(gl_max(nminy, -1.0f), 1.0f);
-        nmaxx = gl_min(gl_max(nmaxx, -1.0f), 1.0f); nmaxy = gl_min(gl_max(nmaxy, -1.0f), 1.0f);
-    }
-    const uint3 c0 = ndc_to_cluster(cv, thr, nminx, nminy, minz), c1 = ndc_to_cluster(cv, thr, nmaxx, nmaxy, maxz);
-    const uint3 lo = make_uint3(min(c0.x, c1.x), min(c0.y, c1.y), min(c0.z, c1.z));
-    const uint3 hi = make_uint3(max(c0.x, c1.x), max(c0.y, c1.y), max(c0.z, c1.z));
-    // view-space sphere (assign.rs:551-556)
-    const float sr = range * cv.scale_max;
-    if (lane == 0) {
-        // farthest_z (assign.rs:558-561): -row2 . (t,1) + range*scale.z ; fmax against 0
-        const float4 r2 = make_float4(cv.vfw[2], cv.vfw[6], cv.vfw[10], cv.vfw[14]);
-        const float this_far = -plane_dot_point(r2, px, py, pz) + range * cv.scale[2];
-        if (this_far > 0.0f) atomicMax(&stats->cl_acc_far[v], __float_as_uint(this_far));
-    }
-    const float4 cc = mat4_mul_point(cv.cfv, vc.x, vc.y, vc.z);
-    const float ndx = cc.x / cc.w, ndy = cc.y / cc.w, ndz = cc.z / cc.w;
-    const uint3 ccl = ndc_to_cluster(cv, thr, ndx, ndy, vc.z);
-    const bool has_zc = ndz <= 1.0f; const uint32_t zc = ccl.z;
-    bool has_yc; uint32_t yc = 0;
-    if (ndy > 1.0f) has_yc = false;
-    else if (ndy < -1.0f) { has_yc = true; yc = cv.dims[1] + 1; }
-    else { has_yc = true; yc = ccl.y; }
-
-    const float4 *xp = staged ? s_planes : reinterpret_cast<const float4 *>(cb.blob + cv.x_off);
-    const float4 *yp = staged ? s_planes + nx : reinterpret_cast<const float4 *>(cb.blob + cv.y_off);
-    const float4 *zp = staged ? s_planes + nx + ny_p : reinterpret_cast<const float4 *>(cb.blob + cv.z_off);
+    ClusterTables tb;
+    tb.thr = staged ? s_thr : cb.blob + cv.thr_off;
+    tb.xp = staged ? s_planes : reinterpret_cast<const float4 *>(cb.blob + cv.x_off);
+    tb.yp = staged ? s_planes + nx : reinterpret_cast<const float4 *>(cb.blob + cv.y_off);
+    tb.zp = staged ? s_planes + nx + ny_p : reinterpret_cast<const float4 *>(cb.blob + cv.z_off);
     uint32_t *mask = cb.send + ((size_t)v * cb.words + (li >> 5)) * kMaxClusters;
     const uint32_t bit = 1u << (li & 31u);
-    const uint32_t ny = hi.y - lo.y + 1, npairs = (hi.z - lo.z + 1) * ny;
     uint32_t count = 0;
-    for (uint32_t p = lane; p < npairs; p += 32) {
-        const uint32_t z = lo.z + p / ny, y = lo.y + p % ny;
-        float ox = vc.x, oy = vc.y, oz = vc.z, orad = sr;
-        if (!has_zc || z != zc) {                                  // project_to_plane_z (assign.rs:1094-1113)
-            const float4 pl = (has_zc && z < zc) ? zp[z + 1] : zp[z];
-            const float zz = pl.w / pl.z;
-            const float dist = zz - oz;
-            if (fabsf(dist) > orad) continue;
-            oz = zz;
-            orad = sqrtf(orad * orad - dist * dist);
-        }
-        if (!has_yc || y != yc) {                                  // project_to_plane_y (assign.rs:1116-1134)
-            const float4 pl = (has_yc && y < yc) ? yp[y + 1] : yp[y];
-            const float dist = ortho ? pl.w - oy : -(oy * pl.y + oz * pl.z);
-            if (fabsf(dist) > orad) continue;
-            ox = ox + dist * pl.x; oy = oy + dist * pl.y; oz = oz + dist * pl.z;
-            orad = sqrtf(orad * orad - dist * dist);
-        }
-        uint32_t min_x = lo.x;                                     // assign.rs:647-675, get_distance_x :1081-1091
-        while (true) {
-            if (min_x >= hi.x) break;
-            const float4 pl = xp[min_x + 1];
-            const float dx = ortho ? ox - pl.w : pl.x * ox + pl.z * oz;
-            if (-dx + orad > 0.0f) break;
-            ++min_x;
-        }
-        uint32_t max_x = hi.x;
-        while (true) {
-            if (max_x <= min_x) break;
-            const float4 pl = xp[max_x];
-            const float dx = ortho ? ox - pl.w : pl.x * ox + pl.z * oz;
-            if (dx + orad > 0.0f) break;
-            --max_x;
-        }
-        uint32_t ci = (y * cv.dims[0] + min_x) * cv.dims[2] + z;   // assign.rs:676-678
-        for (uint32_t x = min_x; x <= max_x; ++x) { atomicOr(mask + ci, bit); ci += cv.dims[2]; }
-        count += max_x - min_x + 1;
-    }
+    float this_far = 0.0f;
+    if (!assign_one_light(cv, tb, px, py, pz, range, lane, this_far, count, [&](uint32_t ci) { atomicOr(mask + ci, bit); })) return;
+    if (lane == 0 && this_far > 0.0f) atomicMax(&stats->cl_acc_far[v], __float_as_uint(this_far));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xFFFFFFFFu, count, o);
     if (lane == 0 && count) atomicAdd(&stats->cl_acc_index[v], count);
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 3+4 fused (single GPU): assign_objects_to_clusters for one view in ONE launch by a thread-block CLUSTER.
+// The view's cluster x light bit matrix lives in the distributed shared memory of the cluster's CTAs: CTA j owns the
+// clusters [j * per, (j+1) * per) (all mask words of those clusters), every CTA takes a share of the LIGHTS and sets
+// bits with shared-memory atomics in whichever CTA owns the cluster (DSMEM).  After a cluster barrier each CTA
+// popcounts its own clusters, the CTA totals are exchanged through DSMEM, and every CTA emits its part of the CSR:
+// no global bit matrix, no clear kernel, no re-count.  Ascending light ordinal per cluster = the reference's push order
+// (the outer loop runs over lights, assign.rs:487).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kFusedThreads = 1024;
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void *p, uint32_t cta) {       // shared::cluster address of p in CTA `cta`
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void dsmem_or(uint32_t addr, uint32_t v) {
+    asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_ld(uint32_t addr) {
+    uint32_t v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
+}
+
+__global__ void __launch_bounds__(kFusedThreads)
+k_cluster_fused(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__restrict__ stats) {
+    extern __shared__ __align__(16) uint8_t smem_fused[];
+    __shared__ float4 s_planes[kStagedPlanes];
+    __shared__ float s_thr[kStagedPlanes];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total, s_far, s_base, s_farmax;
+    const uint32_t v = blockIdx.y, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t rank = cluster_ctarank(), nrank = cluster_nctarank();
+    uint32_t *offsets = cb.offsets + (size_t)v * (kMaxClusters + 1);
+    // early outs are uniform over the cluster (they depend on the view only): nobody is left waiting at a cluster barrier
+    if (v >= fc->n_views) return;
+    const DevClusterView &cv = fc->cviews[v];
+    if (!cv.enabled) {
+        if (rank == 0 && t == 0) { offsets[0] = 0; stats->cl_overflow[v] = 0; stats->cl_index_count[v] = 0; stats->cl_farthest_bits[v] = 0; }
+        return;
+    }
+    const uint32_t nc = cv.n_clusters, per = (nc + nrank - 1) / nrank, words = (L.n + 31u) / 32u;
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem_fused);      // [words][per]
+    for (uint32_t i = t; i < words * per; i += kFusedThreads) s_mask[i] = 0;
+    if (t == 0) { s_total = 0; s_far = 0; }
+    const uint32_t nx = cv.dims[0] + 1, ny_p = cv.dims[1] + 1, nz = cv.dims[2] + 1;
+    const bool staged = nx + ny_p + nz <= kStagedPlanes;
+    if (staged) {
+        const float4 *gx = reinterpret_cast<const float4 *>(cb.blob + cv.x_off);
+        const float4 *gy = reinterpret_cast<const float4 *>(cb.blob + cv.y_off);
+        const float4 *gz = reinterpret_cast<const float4 *>(cb.blob + cv.z_off);
+        for (uint32_t i = t; i < nx; i += kFusedThreads) s_planes[i] = gx[i];
+        for (uint32_t i = t; i < ny_p; i += kFusedThreads) s_planes[nx + i] = gy[i];
+        for (uint32_t i = t; i < nz; i += kFusedThreads) s_planes[nx + ny_p + i] = gz[i];
+        for (uint32_t i = t; i + 1 < cv.dims[2]; i += kFusedThreads) s_thr[i] = cb.blob[cv.thr_off + i];
+    }
+    cluster_sync_all();                    // every CTA's matrix is zeroed before the first remote bit arrives
+    ClusterTables tb;
+    tb.thr = staged ? s_thr : cb.blob + cv.thr_off;
+    tb.xp = staged ? s_planes : reinterpret_cast<const float4 *>(cb.blob + cv.x_off);
+    tb.yp = staged ? s_planes + nx : reinterpret_cast<const float4 *>(cb.blob + cv.y_off);
+    tb.zp = staged ? s_planes + nx + ny_p : reinterpret_cast<const float4 *>(cb.blob + cv.z_off);
+    // ---- assign: light li is handled by warp (li / nrank) % 32 of CTA li % nrank
+    for (uint32_t li = rank + nrank * warp; li < L.n; li += nrank * (kFusedThreads / 32)) {
+        float px, py, pz;
+        if (L.snap != nullptr) {
+            const float4 sp = L.snap[li];
+            if (sp.w == 0.0f) continue;                                     // view_visibility.get() (assign.rs:195)
+            px = sp.x; py = sp.y; pz = sp.z;
+        } else {
+            const uint32_t row = L.row[li];
+            if (!(R.state[row] & 1u)) continue;
+            px = R.gt0[row].w; py = R.gt1[row].w; pz = R.gt2[row].w;
+        }
+        const unsigned long long ll = L.layers ? L.layers[li] : 1ull;
+        if (!(cv.layer_mask & ll)) continue;                                // assign.rs:489
+        const uint32_t bit = 1u << (li & 31u), wbase = (li >> 5) * per;
+        uint32_t count = 0;
+        float this_far = 0.0f;
+        const bool in = assign_one_light(cv, tb, px, py, pz, L.range[li], lane, this_far, count, [&](uint32_t ci) {
+            const uint32_t owner = ci / per;
+            dsmem_or(dsmem_addr(&s_mask[wbase + (ci - owner * per)], owner), bit);
+        });
+        if (in && lane == 0 && this_far > 0.0f) atomicMax(&s_far, __float_as_uint(this_far));
+    }
+    cluster_sync_all();                    // all bits of all lights have landed
+    // ---- popcount -> scan -> ordered emit, per owned cluster
+    const uint32_t first = rank * per, c = first + t;
+    uint32_t cnt = 0;
+    if (t < per && c < nc)
+        for (uint32_t w = 0; w < words; ++w) cnt += __popc(s_mask[w * per + t]);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += y; }
+    if (lane == 31u) s_warp[warp] = incl;
+    __syncthreads();
+    if (t < 32) {
+        uint32_t x = s_warp[t];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
+        s_warp[t] = x;          // inclusive over warps
+        if (t == 31) s_total = x;
+    }
+    cluster_sync_all();                    // every CTA's total (and farthest-z candidate) is published
+    if (t < 32) {
+        uint32_t tot_r = 0, far_r = 0;
+        if (t < nrank) { tot_r = dsmem_ld(dsmem_addr(&s_total, t)); far_r = dsmem_ld(dsmem_addr(&s_far, t)); }
+        uint32_t b = (t < rank) ? tot_r : 0u, fm = far_r;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+            fm = max(fm, __shfl_xor_sync(0xFFFFFFFFu, fm, o));
+        }
+        if (t == 0) { s_base = b; s_farmax = fm; }
+    }
+    // this CTA has read its peers' shared memory; the matching wait sits at the very end, so that no CTA exits (and
+    // frees its shared memory) while a peer may still be reading it, and the emit below overlaps the barrier
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    __syncthreads();
+    const uint32_t base = s_base;
+    uint32_t pos = base + (incl - cnt) + (warp ? s_warp[warp - 1] : 0u);
+    uint32_t *indices = cb.indices + (size_t)v * cb.index_cap;
+    if (t < per && c < nc) {
+        offsets[c] = pos;
+        for (uint32_t w = 0; w < words; ++w) {
+            uint32_t m = s_mask[w * per + t];
+            while (m) {
+                const uint32_t b = __ffs(m) - 1; m &= m - 1;
+                if (pos < cb.index_cap) indices[pos] = w * 32u + b;
+                ++pos;
+            }
+        }
+        if (c == nc - 1) {                // the CTA holding the last cluster publishes the totals
+            offsets[nc] = pos;
+            stats->cl_overflow[v] = pos > cb.index_cap ? 1u : 0u;
+            stats->cl_index_count[v] = pos;                  // every (cluster, light) pair is one index: the reference's count
+        }
+    }
+    if (rank == 0 && t == 0) stats->cl_farthest_bits[v] = s_farmax;
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1582,6 +1741,52 @@ __global__ void k_publish_clusters(const FrameConsts *__restrict__ fc, const uin
     if (t <= nc) host_offsets[(size_t)v * (kMaxClusters + 1) + t] = off[t];
     const uint32_t total = min(min(off[nc], index_cap), host_cap);
     for (uint32_t i = t; i < total; i += gridDim.x * blockDim.x) host_indices[(size_t)v * host_cap + i] = indices[(size_t)v * index_cap + i];
+}
+
+// ---- column write-back: the frame's GlobalTransform / ViewVisibility results into the caller's ECS columns (mapped host
+// memory, PCIe posted writes).  One warp per 32 rows: the changed rows' matrices are transposed through shared memory so
+// that every store instruction covers 512 contiguous bytes of the host column (whole PCIe write bursts), the change flags
+// travel as bit sets (one word per warp), the ViewVisibility bytes as they are.
+template <int STRIDE>
+__global__ void __launch_bounds__(256)
+k_writeback_columns(Rows R, float *__restrict__ host_gt, uint32_t *__restrict__ host_gt_bits, uint8_t *__restrict__ host_vv,
+                    uint32_t *__restrict__ host_vv_bits) {
+    __shared__ float4 s_t[8][32 * (STRIDE / 4)];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n_groups = (R.n + 31u) / 32u;
+    for (uint32_t grp = blockIdx.x * 8u + warp; grp < n_groups; grp += gridDim.x * 8u) {
+        const uint32_t row = grp * 32u + lane;
+        const bool active = row < R.n;
+        const uint32_t st = active ? R.state[row] : 0u;
+        const uint32_t gbits = __ballot_sync(0xFFFFFFFFu, st & S_GT_CHANGED), vbits = __ballot_sync(0xFFFFFFFFu, st & S_VV_CHANGED);
+        if (lane == 0) {
+            if (host_gt_bits != nullptr) host_gt_bits[grp] = gbits;
+            if (host_vv_bits != nullptr) host_vv_bits[grp] = vbits;
+        }
+        if (host_vv != nullptr && active) host_vv[row] = (uint8_t)(st & S_VV);
+        if (host_gt != nullptr && gbits) {
+            constexpr int Q = STRIDE / 4;                 // float4 per row in the host layout
+            if (st & S_GT_CHANGED) {
+                const float4 a = R.gt0[row], b = R.gt1[row], c = R.gt2[row];
+                float4 *o = &s_t[warp][lane * Q];
+                if (STRIDE == 16) {                       // glam Affine3A: x_axis, y_axis, z_axis, translation as Vec3A
+                    o[0] = make_float4(a.x, b.x, c.x, 0.0f); o[1] = make_float4(a.y, b.y, c.y, 0.0f);
+                    o[2] = make_float4(a.z, b.z, c.z, 0.0f); o[3] = make_float4(a.w, b.w, c.w, 0.0f);
+                } else {                                  // packed X.xyz Y.xyz Z.xyz T.xyz
+                    o[0] = make_float4(a.x, b.x, c.x, a.y); o[1] = make_float4(b.y, c.y, a.z, b.z);
+                    o[2] = make_float4(c.z, a.w, b.w, c.w);
+                }
+            }
+            __syncwarp();
+            float4 *dst = reinterpret_cast<float4 *>(host_gt) + (size_t)grp * 32u * Q;
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {
+                const uint32_t idx = k * 32u + lane;      // consecutive lanes -> consecutive 16-byte pieces of the column
+                if ((gbits >> (idx / Q)) & 1u) dst[idx] = s_t[warp][idx];
+            }
+            __syncwarp();
+        }
+    }
 }
 
 // zero this rank's slab for the next frame's assign kernel (only the words in use)
@@ -2103,6 +2308,32 @@ void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, cons
     if (L.n == 0) return;
     k_cluster_assign<<<dim3(cdiv(L.n, 8), max_views), 256, 0, st>>>(R, L, fc, cb, stats);
 }
+// assign + lists of every view in one launch (single GPU): thread-block clusters of 8 (16 beyond ~3200 lights) CTAs per view
+bool launch_cluster_fused(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
+                          DevStats *stats, uint32_t max_views) {
+    static int enabled = -1, nrank_env = 0;
+    if (enabled < 0) {
+        const char *e = getenv("B200VIS_CLUSTER_KERNEL");
+        enabled = (e && e[0] == 's') ? 0 : 1;                 // "split": the assign / lists / clear kernels
+        const char *r = getenv("B200VIS_CLUSTER_CTAS");
+        nrank_env = r ? atoi(r) : 0;
+        cudaFuncSetAttribute(k_cluster_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_cluster_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    }
+    if (!enabled) return false;
+    const uint32_t words = (L.n + 31u) / 32u;
+    uint32_t nrank = (nrank_env == 2 || nrank_env == 4 || nrank_env == 8 || nrank_env == 16) ? (uint32_t)nrank_env : 8u;
+    size_t smem = (size_t)words * (kMaxClusters / nrank) * 4;
+    if (smem > 200u * 1024u) { nrank = 16; smem = (size_t)words * (kMaxClusters / nrank) * 4; }
+    if (smem > 200u * 1024u) return false;                    // more lights than the distributed matrix can hold: split path
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nrank, max_views); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nrank; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_cluster_fused, R, L, fc, cb, stats) == cudaSuccess;
+}
 void launch_publish_visible(cudaStream_t st, const VisibleBufs &vb, const DevStats *stats, uint32_t *host_rows, uint32_t host_stride,
                             uint32_t n_rows, uint32_t n_views) {
     if (!n_views || !n_rows) return;
@@ -2128,6 +2359,13 @@ void launch_tag_lights(cudaStream_t st, const Rows &R, const Lights &L, uint32_t
 }
 void launch_snapshot_lights(cudaStream_t st, const Rows &R, const Lights &L, float4 *snap) {
     if (L.n) k_snapshot_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, snap);
+}
+void launch_writeback_columns(cudaStream_t st, const Rows &R, float *host_gt, uint32_t stride, uint32_t *host_gt_bits, uint8_t *host_vv,
+                              uint32_t *host_vv_bits) {
+    if (!R.n) return;
+    const unsigned groups = cdiv(R.n, 32), grid = groups < 8u * 1184u ? cdiv(groups, 8) : 1184u;
+    if (stride == 16) k_writeback_columns<16><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits);
+    else k_writeback_columns<12><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits);
 }
 void launch_slab_push(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, uint32_t *done, uint32_t max_views) {
     k_slab_push<<<dim3(8, max_views), 256, 0, st>>>(fc, cb, done);

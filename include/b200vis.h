@@ -317,6 +317,30 @@ typedef struct b200vis_result_sink {
 } b200vis_result_sink;
 B200VIS_API int32_t b200vis_set_result_sink(b200vis_ctx *ctx, const b200vis_result_sink *sink);
 
+/* ---- write-back of the frame's column results into the caller's ECS columns -------------------------------------------
+ * The reference systems leave their results IN the ECS: GlobalTransform (+ Changed<GlobalTransform>) and ViewVisibility
+ * (+ Changed<ViewVisibility>) are read downstream (e.g. crates/bevy_pbr/src/render/mesh.rs:1933-1955).  With column sinks
+ * registered, b200vis_writeback_columns (or b200vis_step with B200VIS_STEP_WRITEBACK) has the GPU write, over PCIe and
+ * straight into host memory -- typically the table column slices `ContiguousMut::bypass_change_detection()` hands out
+ * (crates/bevy_ecs/src/change_detection/params.rs:1079-1142):
+ *   global_transforms [n][gt_stride_floats]  ONLY the rows whose GlobalTransform changed this frame (set_if_neq semantics:
+ *                                            the other rows keep their bytes); stride 16 = glam Affine3A (four 16-byte
+ *                                            Vec3A lanes, padding lanes written as 0), stride 12 = packed X,Y,Z,T
+ *   gt_changed_bits   [ceil(n/32)]           bit r%32 of word r/32: stamp changed_ticks[r] = this_run
+ *   view_visibility   [n]                    the ViewVisibility byte of every row (bit0 current, bit1 previous)
+ *   vv_changed_bits   [ceil(n/32)]           Changed<ViewVisibility>
+ * Any pointer may be NULL (that column is not delivered).  The memory is registered with cudaHostRegister if it is not
+ * pinned already.  Results are complete after b200vis_synchronize (or b200vis_step(.., WAIT)).  NULL removes the sinks. */
+typedef struct b200vis_column_sinks {
+    float *global_transforms; uint32_t gt_stride_floats;
+    uint32_t *gt_changed_bits;
+    uint8_t *view_visibility;
+    uint32_t *vv_changed_bits;
+} b200vis_column_sinks;
+B200VIS_API int32_t b200vis_set_column_sinks(b200vis_ctx *ctx, const b200vis_column_sinks *sinks);
+B200VIS_API int32_t b200vis_writeback_columns(b200vis_ctx *ctx);
+#define B200VIS_STEP_WRITEBACK 0x2u  /* b200vis_step: enqueue the column write-back right behind the tile pass */
+
 /* ---- the render world's visible-entity diff ---------------------------------------------
  * RenderVisibleEntitiesClass::update_cpu_culled_entities (crates/bevy_render/src/view/visibility/mod.rs:194-249)
  * marches over last frame's and this frame's sorted list to find the newly added and newly removed entities.  With

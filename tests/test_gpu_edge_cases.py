@@ -417,3 +417,58 @@ def test_result_sink_stats_through_step_with_clusters():
         pipe.ctx.set_result_sink(None, None, None, None)
     finally:
         pipe.close()
+
+
+@pytest.mark.parametrize("stride", [16, 12])
+def test_column_write_back_keeps_a_host_mirror_identical_to_the_device(stride):
+    """b200vis_set_column_sinks + b200vis_step(WRITEBACK): the GPU writes only the CHANGED GlobalTransforms into the host
+    column (glam Affine3A stride 16 or packed 12), the ViewVisibility bytes, and both change-flag bit sets.  A host mirror
+    updated only through the sink must stay identical to a full download, frame after frame (static frames included)."""
+    torch = pytest.importorskip("torch")
+    sc = scenes.forest(n_trees=70, levels=6, n_lights=12)
+    pipe = bb.VisibilityPipeline(sc)
+    n, V = sc.n, len(sc.cameras)
+    W = (n + 31) // 32
+    gt_h = torch.zeros((n, stride), dtype=torch.float32).pin_memory().numpy()
+    ident = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32)
+    gt_h[:] = ident if stride == 12 else np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0], np.float32)
+    gbits = torch.zeros(W, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    vbits = torch.zeros(W, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    vv_h = torch.zeros(n, dtype=torch.uint8).pin_memory().numpy()
+
+    def unpack(bits):
+        return np.unpackbits(bits.view(np.uint8), bitorder="little")[:n]
+    try:
+        pipe.ctx.set_column_sinks(gt_h, gbits, vv_h, vbits)
+        for f in range(5):
+            moving = f not in (2,)                          # frame 2 is static: nothing may be written
+            if moving:
+                scenes.advance_cameras(sc, 0.05)
+                rows, trs = scenes.mutate_roots(sc, f + 1)
+                if f == 3:                                  # the reference bench's pattern: only 8 roots move
+                    rows, trs = rows[:8], trs[:8]
+            else:
+                rows, trs = np.zeros(0, np.uint32), np.zeros((0, 10), np.float32)
+            r = np.ascontiguousarray(rows, np.uint32); t_ = np.ascontiguousarray(trs, np.float32)
+            arr = (bb.CameraDesc * V)()
+            for v, cam in enumerate(sc.cameras):
+                arr[v].global_transform[:] = cam.gt.tolist()
+                arr[v].fov_y, arr[v].aspect, arr[v].near_z, arr[v].far_z = cam.fov, cam.aspect, cam.near, cam.far
+                arr[v].layer_mask, arr[v].flags, arr[v].range_view_index = 1, bb.VIEW_ACTIVE, -1
+            before = gt_h.copy()
+            pipe.ctx.step(len(r), r.ctypes.data if len(r) else 0, t_.ctypes.data if len(r) else 0, arr, V, pipe.cluster_config,
+                          wait=True, writeback=True)
+            pipe.ctx.synchronize()
+            gt, ch = pipe.ctx.download_global_transforms(0, n, stride=stride)
+            vv, vch = pipe.ctx.download_view_visibility(0, n)
+            assert (unpack(gbits) == ch).all() and (unpack(vbits) == vch).all(), f
+            assert (gt_h.view(np.uint32) == gt.view(np.uint32)).all(), f"frame {f}: host mirror differs from the device column"
+            assert (gt_h[ch == 0].view(np.uint32) == before[ch == 0].view(np.uint32)).all()
+            assert (vv_h == vv).all()
+            if f == 2:
+                assert ch.sum() == 0
+            if f == 3:
+                assert 0 < ch.sum() <= 8 * 63
+        pipe.ctx.set_column_sinks()
+    finally:
+        pipe.close()
