@@ -108,6 +108,8 @@ _SIGNATURES = {
     "b200vis_join": (C.c_int32, [_vp]),
     "b200vis_tail_stream": (C.c_int32, [_vp, _P(_vp)]),
     "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
+    "b200vis_kernel_launch_count": (C.c_uint64, []),
+    "b200vis_cluster_view_dims": (C.c_int32, [_vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_set_column_sinks": (C.c_int32, [_vp, _P(ColumnSinks)]),
     "b200vis_writeback_columns": (C.c_int32, [_vp]),
     "b200vis_host_plan_summary": (C.c_int32, [C.c_uint32, _vp, _P(C.c_uint32)]),
@@ -197,6 +199,10 @@ def load_library():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def kernel_launch_count():
+    return int(load_library().b200vis_kernel_launch_count())
 
 
 def abi_version():
@@ -390,6 +396,12 @@ class Context:
     def set_lights(self, light_row, light_range, layer_mask=None):
         r = _arr(light_row, np.uint32); g = _arr(light_range, np.float32); l = _arr(layer_mask, np.uint64)
         self._check(self._lib.b200vis_set_lights(self._h, len(r), _ptr(r), _ptr(g), _ptr(l)))
+
+    def cluster_dims(self, view):
+        """Number of clusters of the view's current grid (0 = clustering off)."""
+        d = (C.c_uint32 * 3)()
+        self._check(self._lib.b200vis_cluster_view_dims(self._h, view, d))
+        return int(d[0]) * int(d[1]) * int(d[2])
 
     def set_cluster_view(self, view, cluster_view):
         self._check(self._lib.b200vis_set_cluster_view(self._h, view, C.byref(cluster_view)))

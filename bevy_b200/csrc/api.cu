@@ -174,6 +174,7 @@ static cudaError_t dalloc(T **p, size_t count) {
 }
 
 extern "C" int32_t b200vis_abi_version(void) { return B200VIS_ABI_VERSION; }
+extern "C" uint64_t b200vis_kernel_launch_count(void) { return kernel_launch_count(); }
 extern "C" void b200vis_struct_sizes(uint32_t out[6]) {
     out[0] = sizeof(b200vis_config); out[1] = sizeof(b200vis_view); out[2] = sizeof(b200vis_cluster_view);
     out[3] = sizeof(b200vis_frame_stats); out[4] = sizeof(b200vis_cluster_config); out[5] = sizeof(b200vis_cluster_feedback);
@@ -306,7 +307,8 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         ClusterBufs &cl = ctx->cl;
         cl.words = (uint32_t)((Lm + 31) / 32); cl.max_lights = cl.words * 32; cl.world = ctx->cfg.world_size;
         cl.rank = cfg->rank; cl.max_views = (uint32_t)V; cl.index_cap = ctx->cfg.max_cluster_indices;
-        ctx->slab_bytes = (size_t)V * cl.words * kMaxClusters * sizeof(uint32_t);
+        cl.slab_words = (uint32_t)(V * cl.words * kMaxClusters + kMaxViews);   // bit matrix + per-view farthest_z trailer
+        ctx->slab_bytes = (size_t)cl.slab_words * sizeof(uint32_t);
         CU(dalloc(&ctx->d_slab, ctx->slab_bytes / 4));
         cl.send = ctx->d_slab; cl.recv = ctx->d_slab;
         cl.blob = reinterpret_cast<const float *>(ctx->d_blob);   // re-pointed per frame
@@ -880,6 +882,12 @@ extern "C" int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, const
     return B200VIS_OK;
 }
 
+extern "C" int32_t b200vis_cluster_view_dims(const b200vis_ctx *ctx, uint32_t view, uint32_t dims[3]) {
+    if (!ctx || !dims || view >= ctx->cfg.max_views) return B200VIS_ERR_INVALID_ARG;
+    const DevClusterView &d = ctx->consts.cviews[view];
+    for (int i = 0; i < 3; ++i) dims[i] = d.enabled ? d.dims[i] : 0u;
+    return B200VIS_OK;
+}
 extern "C" int32_t b200vis_set_cluster_view(b200vis_ctx *ctx, uint32_t view, const b200vis_cluster_view *p) {
     if (!ctx) return B200VIS_ERR_INVALID_ARG;
     if (view >= ctx->cfg.max_views || !p) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_cluster_view: bad view %u", view);

@@ -160,8 +160,10 @@ struct ClusterBufs {
     uint32_t world, rank;
     uint32_t max_views;
     uint32_t index_cap;      // per view
-    uint32_t *send;          // this rank's slab: [V][words][kMaxClusters]
-    const uint32_t *recv;    // gathered: [world][V][words][kMaxClusters]
+    uint32_t *send;          // this rank's slab: [V][words][kMaxClusters] + trailer [kMaxViews] (the rank's farthest_z candidate per
+                             //   view, float bits: it travels with the slab, so that Clusters::last_frame_* are identical on all ranks)
+    const uint32_t *recv;    // gathered: [world] slabs
+    uint32_t slab_words;     // words per slab incl. the trailer == the rank stride of recv
     const float *blob;       // frame blob base: FrameConsts, then the packed per-view tables
     uint32_t *offsets;       // [V][kMaxClusters+1]
     uint32_t *indices;       // [V][index_cap]

@@ -683,9 +683,14 @@ struct __align__(16) WarpSmem {
     uint8_t ppar[kWarpParentSlots];     // parent slot of each slot's row, 0xFF = none
 };
 constexpr uint32_t kFull = 0xFFFFFFFFu;
+// byte c (0..7) of the register pair (w0, w1)
+__device__ __forceinline__ uint32_t sel_byte(uint32_t w0, uint32_t w1, uint32_t c) { return ((c < 4u ? w0 : w1) >> (8u * (c & 3u))) & 0xFFu; }
 
-template <bool CULL, bool SIMPLE>
-__global__ void __launch_bounds__(kTileRows, 4)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// PIPE: the next chunk's columns are loaded into registers while the current chunk is culled (needs ~100 registers);
+// !PIPE: they are only prefetched into L2 (no registers), and loaded at the top of their own iteration
+template <bool CULL, bool SIMPLE, int MINB, bool PIPE>
+__global__ void __launch_bounds__(kTileRows, MINB)
 k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restrict__ sched, uint32_t n_tiles,
             const __grid_constant__ CullViews cvw, VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity,
             uint32_t *__restrict__ tile_counter) {
@@ -702,20 +707,32 @@ k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restric
         const uint32_t base = tp->base, n_chunks = tp->n_chunks, contig_bits = tp->contig;
         const uint32_t pad = (tp->n_rows == kTileRows) ? 0x100u : 0xFFu;   // a full tile has no padding: 0xFF is local row 255
         const uint8_t *sch = sched + (size_t)tp->sched * kTileRows;
+        // ---- the whole schedule and the flag bytes of the tile's rows up front: 8 + 8 independent byte loads per lane, kept
+        // packed in four registers (the address chain schedule -> row -> columns is paid once per tile, not per chunk)
+        uint32_t sch_w[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, fl_w[2] = {0u, 0u};
+#pragma unroll
+        for (uint32_t c = 0; c < (uint32_t)kWarpChunks; ++c)
+            if (c < n_chunks) sch_w[c >> 2] = (sch_w[c >> 2] & ~(0xFFu << (8u * (c & 3u)))) | ((uint32_t)sch[c * 32u + lane] << (8u * (c & 3u)));
+#pragma unroll
+        for (uint32_t c = 0; c < (uint32_t)kWarpChunks; ++c) {
+            const uint32_t local = sel_byte(sch_w[0], sch_w[1], c);
+            if (c < n_chunks && local != pad) fl_w[c >> 2] |= (uint32_t)R.flags[base + local] << (8u * (c & 3u));
+        }
         // ---- mark_dirty_trees (systems.rs:111-306) inside the tile.  Fast path: no row WITH an in-tile parent changed,
         // so every row's TransformTreeChanged bit equals its own Changed<Transform> bit.
         bool slow = false;
         if (static_opt && R.dirty == nullptr) {
+            const uint32_t nonroot_l = (lane < (uint32_t)kWarpChunks) ? tp->nonroot[lane] : 0u;
             uint32_t any = 0;
-            for (uint32_t c = 0; c < n_chunks; ++c) {
-                const uint32_t local = sch[c * 32u + lane];
-                const uint32_t fl = (local != pad) ? R.flags[base + local] : 0u;
-                any |= __ballot_sync(kFull, fl & F_TCHANGED) & tp->nonroot[c];
+#pragma unroll
+            for (uint32_t c = 0; c < (uint32_t)kWarpChunks; ++c) {
+                const uint32_t fl = sel_byte(fl_w[0], fl_w[1], c);
+                any |= __ballot_sync(kFull, fl & F_TCHANGED) & __shfl_sync(kFull, nonroot_l, c);
             }
             slow = any != 0u;
             if (slow) {
                 for (uint32_t c = 0; c < n_chunks; ++c) {       // parent-slot links of the rows with children
-                    const uint32_t local = sch[c * 32u + lane];
+                    const uint32_t local = sel_byte(sch_w[0], sch_w[1], c);
                     if (local != pad) {
                         const uint32_t wt = R.wtopo[base + local];
                         if (wt & W_HAS_SLOT) {
@@ -727,8 +744,9 @@ k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restric
                 }
                 __syncwarp();
                 for (uint32_t c = 0; c < n_chunks; ++c) {       // every Changed row marks its ancestors
-                    const uint32_t local = sch[c * 32u + lane];
-                    if (local != pad && (R.flags[base + local] & F_TCHANGED)) {
+                    const uint32_t local = sel_byte(sch_w[0], sch_w[1], c);
+                    const uint32_t fl = sel_byte(fl_w[0], fl_w[1], c);
+                    if (local != pad && (fl & F_TCHANGED)) {
                         const uint32_t wt = R.wtopo[base + local];
                         uint32_t sl = (wt & W_HAS_SLOT) ? ((wt >> 8) & 127u) : ((wt & 0xFFu) ? ((wt >> 15) & 127u) : 0xFFu);
                         while (sl != 0xFFu && !s.dirty[sl]) {   // benign race: every writer stores 1, every chain finishes
@@ -740,20 +758,41 @@ k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restric
                 __syncwarp();
             }
         }
+        // ---- software pipeline over the chunks: the columns of chunk c+1 are requested right after the walk of chunk c and
+        // arrive while chunk c is culled (all warps of an SM run the same phases at the same time, so other warps alone do
+        // not hide the latency)
+        uint32_t n_st = 0, n_wt = T_DETACHED;
+        float4 nA = make_float4(0, 0, 0, 0), nq = nA, ng0 = nA, ng1 = nA, ng2 = nA;
+        float2 nC = make_float2(0, 0);
+        if (PIPE) {
+            const uint32_t local = sch_w[0] & 0xFFu;
+            if (local != pad) {
+                const uint32_t row = base + local;
+                n_st = R.state[row]; n_wt = R.wtopo[row];
+                nA = R.trsA[row]; nq = R.trsB[row]; nC = R.trsC[row];
+                ng0 = R.gt0[row]; ng1 = R.gt1[row]; ng2 = R.gt2[row];
+            }
+        }
         for (uint32_t c = 0; c < n_chunks; ++c) {
-            const uint32_t local = sch[c * 32u + lane];
+            const uint32_t local = sel_byte(sch_w[0], sch_w[1], c);
             const bool active = local != pad;
             const uint32_t row = base + (active ? local : 0u);
-            // ---- loads: everything the chunk needs, requested up front (11 independent coalesced loads per lane)
-            uint32_t f = 0, st8 = 0, wt = T_DETACHED;
-            float4 A = make_float4(0, 0, 0, 0), q = A, bA = A;
-            float2 C = make_float2(0, 0), bB = C;
-            Aff g; g.r0 = g.r1 = g.r2 = A;       // current GlobalTransform (old value until overwritten)
-            if (active) {
-                f = R.flags[row]; st8 = R.state[row]; wt = R.wtopo[row];
-                A = R.trsA[row]; q = R.trsB[row]; C = R.trsC[row];
-                g.r0 = R.gt0[row]; g.r1 = R.gt1[row]; g.r2 = R.gt2[row];
+            if (!PIPE) {
+                n_st = 0; n_wt = T_DETACHED;
+                if (active) {
+                    n_st = R.state[row]; n_wt = R.wtopo[row];
+                    nA = R.trsA[row]; nq = R.trsB[row]; nC = R.trsC[row];
+                    ng0 = R.gt0[row]; ng1 = R.gt1[row]; ng2 = R.gt2[row];
+                }
             }
+            const uint32_t f = sel_byte(fl_w[0], fl_w[1], c), st8 = n_st, wt = n_wt;
+            const float4 A = nA, q = nq;
+            const float2 C = nC;
+            Aff g; g.r0 = ng0; g.r1 = ng1; g.r2 = ng2;       // current GlobalTransform (old value until overwritten)
+            float4 bA = make_float4(0, 0, 0, 0);
+            float2 bB = make_float2(0, 0);
+            if (CULL && active) { bA = R.bndA[row]; bB = R.bndB[row]; }   // needed after the walk: in flight during it
+
             const uint32_t depth = wt & 0xFFu, own = (wt >> 8) & 127u, pp = (wt >> 15) & 127u;
             const bool tchanged = f & F_TCHANGED;
             const bool has_children = wt & T_HAS_CHILDREN;     // the reference's "has a Children component"
@@ -804,9 +843,25 @@ k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restric
                 }
             }
             if (active) {
-                if (CULL) { bA = R.bndA[row]; bB = R.bndB[row]; }   // needed from here on: 32 warps per SM hide the latency
                 if (changed) { R.gt0[row] = g.r0; R.gt1[row] = g.r1; R.gt2[row] = g.r2; }
                 if (tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
+            }
+            // request the next chunk's columns: they land while this chunk is culled
+            if (PIPE) { n_st = 0; n_wt = T_DETACHED; }
+            if (c + 1u < n_chunks) {
+                const uint32_t nl = sel_byte(sch_w[0], sch_w[1], c + 1u);
+                if (nl != pad) {
+                    const uint32_t nrow = base + nl;
+                    if (PIPE) {
+                        n_st = R.state[nrow]; n_wt = R.wtopo[nrow];
+                        nA = R.trsA[nrow]; nq = R.trsB[nrow]; nC = R.trsC[nrow];
+                        ng0 = R.gt0[nrow]; ng1 = R.gt1[nrow]; ng2 = R.gt2[nrow];
+                    } else if (!(nl & 1u)) {      // one prefetch covers a 32-byte sector: two rows of a float4 column
+                        prefetch_l2(R.trsA + nrow); prefetch_l2(R.trsB + nrow); prefetch_l2(R.gt0 + nrow);
+                        prefetch_l2(R.gt1 + nrow); prefetch_l2(R.gt2 + nrow);
+                        if (CULL) prefetch_l2(R.bndA + nrow);
+                    }
+                }
             }
             uint32_t out = (st8 & (S_VV | S_HAS_CLASS)) | (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
             bool vv_changed = false;
@@ -1402,10 +1457,9 @@ k_cluster_assign(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBu
     uint32_t count = 0;
     float this_far = 0.0f;
     if (!assign_one_light(cv, tb, px, py, pz, range, lane, this_far, count, [&](uint32_t ci) { atomicOr(mask + ci, bit); })) return;
-    if (lane == 0 && this_far > 0.0f) atomicMax(&stats->cl_acc_far[v], __float_as_uint(this_far));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xFFFFFFFFu, count, o);
-    if (lane == 0 && count) atomicAdd(&stats->cl_acc_index[v], count);
+    // farthest_z candidates accumulate in the slab's trailer (values > 0 only: integer max == float max)
+    if (lane == 0 && this_far > 0.0f) atomicMax(cb.send + (cb.slab_words - kMaxViews) + v, __float_as_uint(this_far));
+    (void)count; (void)stats;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1581,7 +1635,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
 __global__ void __launch_bounds__(256)
 k_slab_push(const FrameConsts *__restrict__ fc, ClusterBufs cb, uint32_t *__restrict__ done) {
     const uint32_t v = blockIdx.y;
-    const size_t slab_words = (size_t)cb.max_views * cb.words * kMaxClusters;
+    const size_t slab_words = cb.slab_words;
+    if (blockIdx.x == 0 && threadIdx.x < cb.world && v < kMaxViews) {   // the trailer: this view's farthest_z candidate
+        const size_t tr = ((size_t)cb.xparity * cb.world + cb.rank) * slab_words + (slab_words - kMaxViews) + v;
+        cb.peer[threadIdx.x][tr] = cb.send[(slab_words - kMaxViews) + v];
+    }
     if (v < fc->n_views && fc->cviews[v].enabled) {
         const uint32_t nc = fc->cviews[v].n_clusters;
         const uint32_t *mine = cb.send + (size_t)v * cb.words * kMaxClusters;
@@ -1628,7 +1686,7 @@ k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__
         __syncthreads();
     }
     if (blk == 0 && t == 0 && !cv.enabled) { offsets[0] = 0; stats->cl_overflow[v] = 0; }
-    const size_t rank_stride = (size_t)cb.max_views * cb.words * kMaxClusters;
+    const size_t rank_stride = cb.slab_words;
     const uint32_t *base = cb.recv + (size_t)v * cb.words * kMaxClusters;
     uint32_t *indices = cb.indices + (size_t)v * cb.index_cap;
     const uint32_t first = blk * 1024u;
@@ -1677,9 +1735,12 @@ k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__
         offsets[nc] = pos;
         if (!(cb.p2p && stats->cl_overflow[v] == 2u)) stats->cl_overflow[v] = pos > cb.index_cap ? 1u : 0u;
     }
+    if (nc && c == nc - 1) stats->cl_index_count[v] = pos;     // every (cluster, light) pair is one index: the reference's count
     if (blk == 0 && t == 0) {
-        stats->cl_index_count[v] = stats->cl_acc_index[v]; stats->cl_acc_index[v] = 0;
-        stats->cl_farthest_bits[v] = stats->cl_acc_far[v]; stats->cl_acc_far[v] = 0;
+        if (!nc) stats->cl_index_count[v] = 0;
+        uint32_t far = 0;                                       // max over the ranks' candidates (gathered trailers)
+        for (uint32_t r = 0; r < cb.world; ++r) far = max(far, cb.recv[r * rank_stride + (rank_stride - kMaxViews) + v]);
+        stats->cl_farthest_bits[v] = far;
     }
     // NOTE: the slab is zeroed for the next frame by k_cluster_clear (a CTA here may still be re-counting it)
 }
@@ -1796,6 +1857,7 @@ __global__ void k_cluster_clear(const FrameConsts *__restrict__ fc, ClusterBufs 
     const DevClusterView &cv = fc->cviews[v];
     if (!cv.enabled) return;
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0) cb.send[(cb.slab_words - kMaxViews) + v] = 0;
     if (c >= cv.n_clusters) return;
     uint32_t *mine = cb.send + (size_t)v * cb.words * kMaxClusters;
     for (uint32_t w = 0; w < cb.words; ++w) mine[(size_t)w * kMaxClusters + c] = 0;
@@ -2163,6 +2225,9 @@ __global__ void k_pack_state(Rows R, uint32_t first, uint32_t count, uint8_t *__
 // launchers
 // ------------------------------------------------------------------------------------------
 static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+// kernel launches issued by this library since load (bench.py reports the difference over its timed region)
+static unsigned long long g_launches = 0;
+unsigned long long kernel_launch_count() { return g_launches; }
 
 static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile, 2 warp per tile (default)
 static int tile_kernel_choice() {
@@ -2174,20 +2239,18 @@ static int tile_kernel_choice() {
 }
 bool tile_kernel_is_tma() { return tile_kernel_choice() == 1; }
 bool tile_kernel_publishes_light_snapshot() { return tile_kernel_choice() != 0; }
-template <bool C, bool S>
+template <bool C, bool S, int MINB, bool PIPE>
 static void launch_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, const uint8_t *sched, uint32_t n_tiles, const CullViews &cvw,
                         const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity, uint32_t *counter) {
     constexpr size_t smem = (kTileRows / 32) * sizeof(WarpSmem);
     static int grid = 0, dynamic = 0;
     if (!grid) {
-        cudaFuncSetAttribute(k_tile_warp<C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_tile_warp<C, S, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_warp<C, S>, kTileRows, smem);
-        // B200VIS_WARP_CTAS_PER_SM=k (< occupancy) leaves part of every SM to the previous frame's tail kernels
-        const char *e = getenv("B200VIS_WARP_CTAS_PER_SM");
-        if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_warp<C, S, MINB, PIPE>, kTileRows, smem);
+        if (per_sm > MINB) per_sm = MINB;
         grid = sms * (per_sm > 0 ? per_sm : 1);
         const char *d = getenv("B200VIS_WARP_DYNAMIC");   // tiles handed out by an atomic counter instead of a fixed stride
         dynamic = (d && atoi(d)) ? 1 : 0;
@@ -2202,16 +2265,35 @@ static void launch_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, c
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_tile_warp<C, S>, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, ctr);
+    ++g_launches; cudaLaunchKernelEx(&cfg, k_tile_warp<C, S, MINB, PIPE>, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, ctr);
+}
+template <int MINB, bool PIPE>
+static void launch_tile_warp_m(cudaStream_t st, const Rows &R, const WarpTile *tiles, const uint8_t *sched, uint32_t n_tiles, const CullViews &cvw,
+                               const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity, uint32_t *counter) {
+    const bool cull = stages & 2u;
+    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+    if (cull) { if (simple) launch_warp<true, true, MINB, PIPE>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter);
+                else launch_warp<true, false, MINB, PIPE>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter); }
+    else launch_warp<false, true, MINB, PIPE>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter);
 }
 void launch_tile_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, const uint8_t *sched, uint32_t n_tiles, const CullViews &cvw,
                       const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity, uint32_t *counter) {
     if (n_tiles == 0) return;
-    const bool cull = stages & 2u;
-    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
-    if (cull) { if (simple) launch_warp<true, true>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter);
-                else launch_warp<true, false>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter); }
-    else launch_warp<false, true>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter);
+    // B200VIS_WARP_VARIANT = <CTAs per SM><p|n>: 4 = 32 warps per SM at 64 registers, 3 = 24 at 80, 2 = 16 at 128;
+    // p = next chunk loaded into registers during the cull, n = only prefetched into L2
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("B200VIS_WARP_VARIANT");
+        const int b = (e && e[0] >= '2' && e[0] <= '4') ? e[0] - '0' : 3;
+        const int pipe = (e && e[0] && e[1] == 'n') ? 0 : 1;
+        variant = b * 2 + pipe;
+    }
+#define B200VIS_WARP_CASE(B, P) case (B) * 2 + (P): launch_tile_warp_m<B, P != 0>(st, R, tiles, sched, n_tiles, cvw, vb, stats, stages, static_opt, parity, counter); break
+    switch (variant) {
+        B200VIS_WARP_CASE(4, 1); B200VIS_WARP_CASE(4, 0); B200VIS_WARP_CASE(3, 1); B200VIS_WARP_CASE(3, 0);
+        B200VIS_WARP_CASE(2, 1); B200VIS_WARP_CASE(2, 0);
+    }
+#undef B200VIS_WARP_CASE
 }
 bool tile_kernel_is_warp() { return tile_kernel_choice() == 2; }
 template <bool P, bool C, bool S>
@@ -2250,7 +2332,7 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_propagate_cull_tma<P, C, S>, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
+    ++g_launches; cudaLaunchKernelEx(&cfg, k_propagate_cull_tma<P, C, S>, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
 }
 // tiles of <= 32 rows (the tops of split deep tiles): the classic kernel with one warp per tile, 16 CTAs per SM
 void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
@@ -2258,7 +2340,7 @@ void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *til
     if (n_tiles == 0) return;
     const bool prop = stages & 1u, cull = stages & 2u;
     const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
-#define B200VIS_LAUNCH_SMALL(P, C, S) k_propagate_cull<P, C, S><<<n_tiles, 32, 0, st>>>(R, tiles, cvw, vb, stats, static_opt, parity)
+#define B200VIS_LAUNCH_SMALL(P, C, S) ++g_launches, k_propagate_cull<P, C, S><<<n_tiles, 32, 0, st>>>(R, tiles, cvw, vb, stats, static_opt, parity)
     if (prop && cull) { if (simple) B200VIS_LAUNCH_SMALL(true, true, true); else B200VIS_LAUNCH_SMALL(true, true, false); }
     else if (prop) B200VIS_LAUNCH_SMALL(true, false, true);
     else if (cull) { if (simple) B200VIS_LAUNCH_SMALL(false, true, true); else B200VIS_LAUNCH_SMALL(false, true, false); }
@@ -2277,7 +2359,7 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
 #undef B200VIS_LAUNCH_TMA
         return;
     }
-#define B200VIS_LAUNCH(P, C, S) k_propagate_cull<P, C, S><<<n_tiles, kTileRows, 0, st>>>(R, tiles, cvw, vb, stats, static_opt, parity)
+#define B200VIS_LAUNCH(P, C, S) ++g_launches, k_propagate_cull<P, C, S><<<n_tiles, kTileRows, 0, st>>>(R, tiles, cvw, vb, stats, static_opt, parity)
     if (prop && cull) { if (simple) B200VIS_LAUNCH(true, true, true); else B200VIS_LAUNCH(true, true, false); }
     else if (prop) B200VIS_LAUNCH(true, false, true);
     else if (cull) { if (simple) B200VIS_LAUNCH(false, true, true); else B200VIS_LAUNCH(false, true, false); }
@@ -2286,27 +2368,27 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
 void launch_cull(cudaStream_t st, const Rows &R, const CullViews &cvw, const VisibleBufs &vb, DevStats *stats, uint32_t parity) {
     if (!R.n) return;
     const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
-    if (simple) k_cull<true><<<cdiv(R.n, 256), 256, 0, st>>>(R, cvw, vb, stats, parity);
-    else k_cull<false><<<cdiv(R.n, 256), 256, 0, st>>>(R, cvw, vb, stats, parity);
+    if (simple) { ++g_launches; k_cull<true><<<cdiv(R.n, 256), 256, 0, st>>>(R, cvw, vb, stats, parity); }
+    else { ++g_launches; k_cull<false><<<cdiv(R.n, 256), 256, 0, st>>>(R, cvw, vb, stats, parity); }
 }
 void launch_mark_dirty_global(cudaStream_t st, const Rows &R) {
-    if (R.n) k_mark_dirty_global<<<cdiv(R.n, 256), 256, 0, st>>>(R);
+    if (R.n) { ++g_launches; k_mark_dirty_global<<<cdiv(R.n, 256), 256, 0, st>>>(R); }
 }
 void launch_expand_visible(cudaStream_t st, const VisibleBufs &vb, const DiffBufs &db, const uint32_t *row_of_rank, const FrameConsts *fc,
                            DevStats *stats, uint32_t parity, uint32_t n_rows, uint32_t max_views) {
     if (vb.n_chunks == 0) return;
-    k_expand_visible<<<dim3(vb.n_chunks, max_views), kChunkWords, 0, st>>>(vb, db, row_of_rank, fc, stats, parity, n_rows);
-    if (db.prev != nullptr) k_emit_visible_diff<<<dim3(vb.n_chunks, max_views), kChunkWords, 0, st>>>(vb, db, row_of_rank, fc);
+    ++g_launches; k_expand_visible<<<dim3(vb.n_chunks, max_views), kChunkWords, 0, st>>>(vb, db, row_of_rank, fc, stats, parity, n_rows);
+    if (db.prev != nullptr) { ++g_launches; k_emit_visible_diff<<<dim3(vb.n_chunks, max_views), kChunkWords, 0, st>>>(vb, db, row_of_rank, fc); }
 }
 void launch_publish_visible_diff(cudaStream_t st, const VisibleBufs &vb, const DiffBufs &db, uint32_t *host_rows, uint32_t host_stride,
                                  uint32_t *host_counts, uint32_t n_views, uint32_t max_views) {
     if (!n_views || db.prev == nullptr) return;
-    k_publish_visible_diff<<<dim3(32, n_views, 2), 256, 0, st>>>(db, vb.list_stride, host_rows, host_stride, host_counts, n_views, max_views);
+    ++g_launches; k_publish_visible_diff<<<dim3(32, n_views, 2), 256, 0, st>>>(db, vb.list_stride, host_rows, host_stride, host_counts, n_views, max_views);
 }
 void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
                            DevStats *stats, uint32_t max_views) {
     if (L.n == 0) return;
-    k_cluster_assign<<<dim3(cdiv(L.n, 8), max_views), 256, 0, st>>>(R, L, fc, cb, stats);
+    ++g_launches; k_cluster_assign<<<dim3(cdiv(L.n, 8), max_views), 256, 0, st>>>(R, L, fc, cb, stats);
 }
 // assign + lists of every view in one launch (single GPU): thread-block clusters of 8 (16 beyond ~3200 lights) CTAs per view
 bool launch_cluster_fused(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
@@ -2332,50 +2414,50 @@ bool launch_cluster_fused(cudaStream_t st, const Rows &R, const Lights &L, const
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = nrank; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_cluster_fused, R, L, fc, cb, stats) == cudaSuccess;
+    ++g_launches; return cudaLaunchKernelEx(&cfg, k_cluster_fused, R, L, fc, cb, stats) == cudaSuccess;
 }
 void launch_publish_visible(cudaStream_t st, const VisibleBufs &vb, const DevStats *stats, uint32_t *host_rows, uint32_t host_stride,
                             uint32_t n_rows, uint32_t n_views) {
     if (!n_views || !n_rows) return;
-    k_publish_visible<<<dim3(min(cdiv(n_rows, 256), 296u), n_views), 256, 0, st>>>(vb.lists, vb.list_stride, stats, host_rows, host_stride, n_views);
+    ++g_launches; k_publish_visible<<<dim3(min(cdiv(n_rows, 256), 296u), n_views), 256, 0, st>>>(vb.lists, vb.list_stride, stats, host_rows, host_stride, n_views);
 }
 void launch_publish_clusters(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, uint32_t *host_offsets, uint32_t *host_indices,
                              uint32_t host_cap, const DevStats *stats, uint32_t *host_stats, uint32_t changed_slot, uint32_t frame, uint32_t max_views) {
-    k_publish_clusters<<<dim3(kMaxClusters / 256 + 1, max_views), 256, 0, st>>>(fc, cb.offsets, cb.indices, cb.index_cap, host_offsets, host_indices,
+    ++g_launches; k_publish_clusters<<<dim3(kMaxClusters / 256 + 1, max_views), 256, 0, st>>>(fc, cb.offsets, cb.indices, cb.index_cap, host_offsets, host_indices,
                                                                                 host_cap, stats, host_stats, changed_slot, frame);
 }
 void launch_shadow_cull(cudaStream_t st, const Rows &R, const ShadowBufs &sb, const Lights &L, const uint32_t *view_sets, uint32_t n_views,
                         uint32_t n_words, uint32_t n_chunks, uint32_t words_stride, uint32_t chunks_stride, DevStats *stats, uint32_t changed_slot) {
     if (!sb.n_lights || !R.n) return;
-    k_shadow_select<<<cdiv(sb.n_lights, 128), 128, 0, st>>>(sb, L, R.rank, view_sets, words_stride, n_views);
-    k_shadow_cull<<<cdiv(R.n, 256), 256, 0, st>>>(R, sb, L, words_stride, chunks_stride, stats, changed_slot);
-    k_expand_shadow<<<dim3(n_chunks, sb.n_lights * 6), kChunkWords, 0, st>>>(sb, n_words, n_chunks, words_stride, chunks_stride, R.row_of_rank);
+    ++g_launches; k_shadow_select<<<cdiv(sb.n_lights, 128), 128, 0, st>>>(sb, L, R.rank, view_sets, words_stride, n_views);
+    ++g_launches; k_shadow_cull<<<cdiv(R.n, 256), 256, 0, st>>>(R, sb, L, words_stride, chunks_stride, stats, changed_slot);
+    ++g_launches; k_expand_shadow<<<dim3(n_chunks, sb.n_lights * 6), kChunkWords, 0, st>>>(sb, n_words, n_chunks, words_stride, chunks_stride, R.row_of_rank);
 }
 void launch_pack_cluster_bindings(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, const BindingBufs &bb, uint32_t max_views) {
-    if (bb.mode) k_pack_cluster_bindings<<<dim3(16, max_views), 256, 0, st>>>(fc, cb, bb);
+    if (bb.mode) { ++g_launches; k_pack_cluster_bindings<<<dim3(16, max_views), 256, 0, st>>>(fc, cb, bb); }
 }
 void launch_tag_lights(cudaStream_t st, const Rows &R, const Lights &L, uint32_t *light_ord, uint32_t *all_tagged) {
-    if (L.n) k_tag_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, light_ord, all_tagged);
+    if (L.n) { ++g_launches; k_tag_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, light_ord, all_tagged); }
 }
 void launch_snapshot_lights(cudaStream_t st, const Rows &R, const Lights &L, float4 *snap) {
-    if (L.n) k_snapshot_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, snap);
+    if (L.n) { ++g_launches; k_snapshot_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, snap); }
 }
 void launch_writeback_columns(cudaStream_t st, const Rows &R, float *host_gt, uint32_t stride, uint32_t *host_gt_bits, uint8_t *host_vv,
                               uint32_t *host_vv_bits) {
     if (!R.n) return;
     const unsigned groups = cdiv(R.n, 32), grid = groups < 8u * 1184u ? cdiv(groups, 8) : 1184u;
-    if (stride == 16) k_writeback_columns<16><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits);
-    else k_writeback_columns<12><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits);
+    if (stride == 16) { ++g_launches; k_writeback_columns<16><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits); }
+    else { ++g_launches; k_writeback_columns<12><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits); }
 }
 void launch_slab_push(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, uint32_t *done, uint32_t max_views) {
-    k_slab_push<<<dim3(8, max_views), 256, 0, st>>>(fc, cb, done);
+    ++g_launches; k_slab_push<<<dim3(8, max_views), 256, 0, st>>>(fc, cb, done);
 }
 void launch_cluster_lists(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, DevStats *stats, uint32_t max_views) {
-    k_cluster_lists<<<dim3(kListBlocks, max_views), 1024, 0, st>>>(fc, cb, stats);
-    k_cluster_clear<<<dim3(kMaxClusters / 256, max_views), 256, 0, st>>>(fc, cb);
+    ++g_launches; k_cluster_lists<<<dim3(kListBlocks, max_views), 1024, 0, st>>>(fc, cb, stats);
+    ++g_launches; k_cluster_clear<<<dim3(kMaxClusters / 256, max_views), 256, 0, st>>>(fc, cb);
 }
 void launch_unpack_trs(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *src, int mark_only) {
-    if (count) k_unpack_trs<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, src, mark_only);
+    if (count) { ++g_launches; k_unpack_trs<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, src, mark_only); }
 }
 void launch_scatter_trs(cudaStream_t st, const Rows &R, uint32_t count, const uint32_t *rows, const float *src) {
     if (!count) return;
@@ -2385,35 +2467,35 @@ void launch_scatter_trs(cudaStream_t st, const Rows &R, uint32_t count, const ui
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_scatter_trs, R, count, rows, src);
+    ++g_launches; cudaLaunchKernelEx(&cfg, k_scatter_trs, R, count, rows, src);
 }
 void launch_unpack_gt(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *src) {
-    if (count) k_unpack_gt<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, src);
+    if (count) { ++g_launches; k_unpack_gt<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, src); }
 }
 void launch_pack_gt(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, float *dst, uint32_t stride) {
-    if (count) k_pack_gt<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, dst, stride);
+    if (count) { ++g_launches; k_pack_gt<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, dst, stride); }
 }
 void launch_unpack_bounds(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *bounds,
                           const uint8_t *flags, const uint8_t *cls) {
-    if (count) k_unpack_bounds<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, bounds, flags, cls);
+    if (count) { ++g_launches; k_unpack_bounds<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, bounds, flags, cls); }
 }
 void launch_unpack_vv(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const uint8_t *vv) {
-    if (count) k_unpack_vv<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, vv);
+    if (count) { ++g_launches; k_unpack_vv<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, vv); }
 }
 void launch_visibility_propagate(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const uint8_t *vis, uint8_t *changed) {
-    if (n_tiles) k_visibility_propagate<<<n_tiles, kTileRows, 0, st>>>(R, tiles, vis, changed);
+    if (n_tiles) { ++g_launches; k_visibility_propagate<<<n_tiles, kTileRows, 0, st>>>(R, tiles, vis, changed); }
 }
 void launch_pack_inherited(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const uint8_t *changed, uint8_t *out) {
-    if (count) k_pack_inherited<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, changed, out);
+    if (count) { ++g_launches; k_pack_inherited<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, changed, out); }
 }
 void launch_pack_ranges(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, uint32_t *out) {
-    if (count) k_pack_ranges<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, out);
+    if (count) { ++g_launches; k_pack_ranges<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, out); }
 }
 void launch_unpack_range_params(cudaStream_t st, float2 *se, uint8_t *ua, uint32_t first, uint32_t count, const float *src_se, const uint8_t *src_ua) {
-    if (count) k_unpack_range_params<<<cdiv(count, 256), 256, 0, st>>>(se, ua, first, count, src_se, src_ua);
+    if (count) { ++g_launches; k_unpack_range_params<<<cdiv(count, 256), 256, 0, st>>>(se, ua, first, count, src_se, src_ua); }
 }
 void launch_pack_state(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, uint8_t *out, uint32_t changed_bit) {
-    if (count) k_pack_state<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, out, changed_bit);
+    if (count) { ++g_launches; k_pack_state<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, out, changed_bit); }
 }
 
 }  // namespace b200vis

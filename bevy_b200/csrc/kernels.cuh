@@ -8,6 +8,7 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
                            const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity);
 void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                                  const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity);
+unsigned long long kernel_launch_count();
 bool tile_kernel_is_tma();
 bool tile_kernel_is_warp();
 bool tile_kernel_publishes_light_snapshot();

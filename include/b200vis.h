@@ -156,6 +156,9 @@ typedef struct b200vis_cluster_feedback {    /* Clusters::last_frame_* (cluster/
 
 /* ---- lifetime ------------------------------------------------------------- */
 B200VIS_API int32_t b200vis_abi_version(void);
+/* Kernel launches this library has issued since it was loaded (all contexts); bench.py reports the difference over its
+ * timed regions as `gpu_launches`. */
+B200VIS_API uint64_t b200vis_kernel_launch_count(void);
 /* sizeof of the ABI structs, in declaration order (config, view, cluster_view, frame_stats, cluster_config,
  * cluster_feedback): lets a foreign-language binding verify its layout at start-up. */
 B200VIS_API void b200vis_struct_sizes(uint32_t out[6]);
@@ -232,6 +235,9 @@ B200VIS_API int32_t b200vis_set_views(b200vis_ctx *ctx, uint32_t n_views, const 
 B200VIS_API int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, const uint32_t *light_row, const float *range,
                            const uint64_t *layer_mask /* nullable */);
 B200VIS_API int32_t b200vis_set_cluster_view(b200vis_ctx *ctx, uint32_t view, const b200vis_cluster_view *params);
+/* Cluster grid dimensions of the view as last set (b200vis_set_cluster_view / b200vis_update_camera / b200vis_step);
+ * zeros when clustering is off for the view.  The shim sizes Clusters::clusterable_objects from it. */
+B200VIS_API int32_t b200vis_cluster_view_dims(const b200vis_ctx *ctx, uint32_t view, uint32_t dims[3]);
 
 /* Frame constants kept in HBM: record_frame_constants snapshots the current views / cluster views (device copy
  * of the packed tables + the host copy the kernel parameters are built from) and returns a slot;

@@ -72,8 +72,14 @@ def main():
                 parallel.all_gather_slabs(recv, send)          # on the stream the frame's tail runs on
             ctx.run(bb.STAGE_CLUSTER_LISTS)
         stats = ctx.download_frame_stats()
-        far, cnt = parallel.reduce_feedback([stats.cluster_farthest_z[v] for v in range(V)],
-                                            [stats.cluster_index_count[v] for v in range(V)], device=dev)
+        # Clusters::last_frame_* come out of the list kernel identical on every rank: the index count is the total of the
+        # gathered bit matrix, the farthest z is the max over the trailers that travelled with the slabs -- no reduction here
+        far = np.array([stats.cluster_farthest_z[v] for v in range(V)], np.float32)
+        cnt = np.array([stats.cluster_index_count[v] for v in range(V)], np.int64)
+        chk = torch.from_numpy(np.concatenate([far.view(np.int32).astype(np.int64), cnt])).to(dev)
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        ok &= bool((lo_ == hi_).all().item())
         for v in range(V):
             fb = pipe.feedback[v]
             fb.has_farthest_z, fb.farthest_z, fb.has_index_count, fb.index_count = 1, float(far[v]), 1, int(cnt[v])

@@ -21,7 +21,14 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"].startswith("config#3 forest 300x255")
-    assert d["config"]["entities_per_gpu"] == 300 * 255 + 32
+    assert d["config"]["entities_total"] == 300 * 255 + 32 and d["config"]["scaling"] == "strong"
+    assert d["steps"] == 2 and d["warmup"] == 1                      # the arm honours --steps / --warmup exactly
+    # both arms print the same `config` object: it is a function of the command line only
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--print-config", "--trees", "300", "--lights", "32"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert res.returncode == 0 and json.loads(res.stdout) == d["config"]
+    for k in ("ms_per_step_median", "ms_per_step_min", "ms_per_step_max"):
+        assert d["cpu_baseline"][k] > 0
     # ranks other than 0 print nothing and exit 0
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
