@@ -675,6 +675,9 @@ def main():
     # first frame: everything is "Added"; run it once so steady state starts from real GlobalTransforms
     ctx.run(bb.STAGE_ALL)
     rig.pipe.read_feedback()
+    # the host columns start as a copy of the device's (spawn-time state); from here on only the write-back touches them
+    rig.gt_h[:n] = ctx.download_global_transforms(0, n, stride=16, want_changed=False)[0]
+    rig.vv_h[:n] = ctx.download_view_visibility(0, n)[0]
     pcie = measure_pcie(torch, dev, stream) if rank == 0 else None
 
     # ---- pass A: e2e through the plugin API with host buffers, every result written back ----------------------------------
@@ -810,7 +813,8 @@ def main():
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         algo_bytes = n * ALGO_BYTES_PER_ENTITY + 4 * visible_pairs_rank
         achieved = algo_bytes / (tile_ms_avg * 1e-3) / 1e9
-        tile_kernel = {"c": "k_propagate_cull", "t": "k_propagate_cull_tma"}.get(os.environ.get("B200VIS_TILE_KERNEL", "w")[:1], "k_tile_warp")
+        tile_kernel = {"c": "k_propagate_cull", "t": "k_propagate_cull_tma", "w": "k_tile_warp"}.get(
+            os.environ.get("B200VIS_TILE_KERNEL", "s")[:1], "k_propagate_cull_scout")
         cfg_out = dict(cfg)
         line = {
             "metric": METRIC, "value": value, "unit": "entities/s", "n_gpus": world, "steps": K, "warmup": W,

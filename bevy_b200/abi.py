@@ -90,7 +90,7 @@ class ColumnSinks(C.Structure):
 
 class ResultSink(C.Structure):
     _fields_ = [("stats", C.POINTER(FrameStats)), ("visible_rows", C.c_void_p), ("visible_capacity", C.c_uint32),
-                ("cluster_offsets", C.c_void_p), ("cluster_indices", C.c_void_p), ("cluster_capacity", C.c_uint32)]
+                ("visible_classes", C.c_void_p), ("cluster_offsets", C.c_void_p), ("cluster_indices", C.c_void_p), ("cluster_capacity", C.c_uint32)]
 
 
 _lib = None
@@ -109,6 +109,7 @@ _SIGNATURES = {
     "b200vis_tail_stream": (C.c_int32, [_vp, _P(_vp)]),
     "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
     "b200vis_kernel_launch_count": (C.c_uint64, []),
+    "b200vis_download_visible_classes": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_cluster_view_dims": (C.c_int32, [_vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_set_column_sinks": (C.c_int32, [_vp, _P(ColumnSinks)]),
     "b200vis_writeback_columns": (C.c_int32, [_vp]),
@@ -540,12 +541,22 @@ class Context:
             self._check(self._lib.b200vis_set_visible_diff_sink(self._h, None, 0, None)); return
         self._check(self._lib.b200vis_set_visible_diff_sink(self._h, _ptr(rows), rows.shape[2], _ptr(counts)))
 
+    def download_visible_by_class(self, view):
+        """VisibleEntities::entities of the view as {class k: sorted rows}: the list + class masks, split the way the shim does."""
+        rows = self.download_visible(view)
+        cls = np.zeros(max(len(rows), 1), np.uint8)
+        cnt = C.c_uint32(0)
+        self._check(self._lib.b200vis_download_visible_classes(self._h, view, _ptr(cls), len(cls), C.byref(cnt)))
+        assert cnt.value == len(rows)
+        cls = cls[:len(rows)]
+        return {k: rows[(cls >> k) & 1 == 1] for k in range(8) if ((cls >> k) & 1).any()}
+
     def download_clusters(self, view, capacity=1 << 20):
         offsets = np.zeros(MAX_CLUSTERS + 1, np.uint32); idx = np.zeros(capacity, np.uint32); tot = C.c_uint32(0)
         self._check(self._lib.b200vis_download_clusters(self._h, view, _ptr(offsets), _ptr(idx), capacity, C.byref(tot)))
         return offsets, idx[:tot.value]
 
-    def set_result_sink(self, stats_ptr, visible_rows, cluster_offsets, cluster_indices):
+    def set_result_sink(self, stats_ptr, visible_rows, cluster_offsets, cluster_indices, visible_classes=None):
         """Pinned host numpy arrays: visible_rows [V, cap], cluster_offsets [V, 4097], cluster_indices [V, cap]; stats_ptr
         is the address of a pinned FrameStats-sized block.  Pass stats_ptr=None to remove the sink."""
         if stats_ptr is None:
@@ -554,10 +565,11 @@ class Context:
         s.stats = C.cast(stats_ptr, C.POINTER(FrameStats))
         s.visible_rows = None if visible_rows is None else visible_rows.ctypes.data
         s.visible_capacity = 0 if visible_rows is None else visible_rows.shape[1]
+        s.visible_classes = None if visible_classes is None else visible_classes.ctypes.data
         s.cluster_offsets = None if cluster_offsets is None else cluster_offsets.ctypes.data
         s.cluster_indices = None if cluster_indices is None else cluster_indices.ctypes.data
         s.cluster_capacity = 0 if cluster_indices is None else cluster_indices.shape[1]
-        self._sink = (s, visible_rows, cluster_offsets, cluster_indices)
+        self._sink = (s, visible_rows, cluster_offsets, cluster_indices, visible_classes)
         self._check(self._lib.b200vis_set_result_sink(self._h, C.byref(s)))
 
     def set_column_sinks(self, gt=None, gt_changed_bits=None, view_visibility=None, vv_changed_bits=None):

@@ -136,6 +136,7 @@ struct b200vis_ctx {
     // result sink (mapped pinned host memory written by publish kernels)
     b200vis_result_sink sink{}; bool have_sink = false;
     uint32_t *sink_rows_d = nullptr, *sink_off_d = nullptr, *sink_idx_d = nullptr, *sink_stats_d = nullptr;
+    uint8_t *sink_cls_d = nullptr; uint8_t *d_cls = nullptr;   // VisibilityClass masks: sink alias, per-row column
 
     b200vis_column_sinks colsink{}; bool have_colsink = false;          // b200vis_set_column_sinks (device aliases below)
     float *col_gt_d = nullptr; uint32_t *col_gt_bits_d = nullptr, *col_vv_bits_d = nullptr; uint8_t *col_vv_d = nullptr;
@@ -192,7 +193,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
                    ctx->d_tiles, ctx->d_wtiles, ctx->d_sched, ctx->d_wtopo, ctx->d_tile_counter, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_light_snap, ctx->d_tag_flag, ctx->d_light_ord,
-                   ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->d_stats, ctx->d_light_row,
+                   ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->vis.classes, ctx->d_cls, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage,
                    ctx->diff.prev, ctx->diff.words, ctx->diff.chunk, ctx->diff.lists, ctx->diff.count,
                    ctx->bind.oc, ctx->bind.il, ctx->bind.count, ctx->d_bind_map,
@@ -295,6 +296,9 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         CU(dalloc(&vb.mask, (size_t)2 * vb.words_stride * V));
         CU(dalloc(&vb.chunk_count, (size_t)3 * kMaxViews * vb.chunks_stride));
         CU(dalloc(&vb.lists, (size_t)vb.list_stride * V));
+        CU(dalloc(&vb.classes, (size_t)vb.list_stride * V));
+        CU(dalloc(&ctx->d_cls, NP));
+        vb.cls = ctx->d_cls;
         CU(dalloc(&ctx->d_stats, 1));
         CU(cudaMallocHost(&ctx->h_stats, sizeof(DevStats)));
         // lights + clusters
@@ -461,7 +465,7 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
         }
         for (uint32_t part = 0; part < (cut ? 2u : 1u); ++part) {
             const uint32_t b = (part == 0) ? start : start + cut, e = (cut && part == 0) ? start + cut : end;
-            Tile t; t.base = b; t.n_rows = (uint16_t)(e - b); t.n_levels = 1; t.warp_sync_mask = 0xFFFFFFFFu; t.pad = 0;
+            Tile t; t.base = b; t.n_rows = (uint16_t)(e - b); t.n_levels = 1; t.warp_sync_mask = 0xFFFFFFFFu; t.top_levels = 0;
             for (uint32_t r = b; r < e; ++r) tile_of[r] = (uint32_t)tiles.size();
             tiles.push_back(t);
         }
@@ -494,6 +498,17 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
         }
         if (has_children[r]) w |= T_HAS_CHILDREN;
         topo[r] = w;
+    }
+    {   // top_levels: the leading depth levels whose rows all sit among the tile's first 32 rows
+        std::vector<uint32_t> max_local;
+        for (size_t ti = 0; ti < tiles.size(); ++ti) {
+            Tile &t = tiles[ti];
+            max_local.assign(t.n_levels, 0);
+            for (uint32_t r = t.base; r < t.base + t.n_rows; ++r) max_local[ldepth[r]] = std::max(max_local[ldepth[r]], r - t.base);
+            uint32_t K = 0;
+            while (K < t.n_levels && max_local[K] < 32u) ++K;
+            t.top_levels = (t.n_levels > 1) ? K : 0u;       // flat tiles have nothing to walk ahead
+        }
     }
     // ---- warp work items: schedule, parent slots, wtopo ------------------------------------------------------------
     std::vector<WarpTile> wtiles(tiles.size());
@@ -780,7 +795,7 @@ extern "C" int32_t b200vis_upload_bounds(b200vis_ctx *ctx, uint32_t first, uint3
     rc = stage_in(ctx, flags, count, of); if (rc) return rc;
     rc = stage_in(ctx, class_mask, count, oc); if (rc) return rc;
     launch_unpack_bounds(ctx->stream, ctx->rows, first, count, reinterpret_cast<const float *>(ctx->d_stage + ob),
-                         ctx->d_stage + of, ctx->d_stage + oc);
+                         ctx->d_stage + of, ctx->d_stage + oc, ctx->d_cls);
     CU(cudaGetLastError());
     if (layer_mask) {
         CU(cudaMemcpyAsync(ctx->d_layers + first, layer_mask, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1286,7 +1301,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
             CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_tile, 0));
             pub = ctx->side_stream;
         }
-        launch_publish_visible(pub, vb, ctx->d_stats, ctx->sink_rows_d, ctx->sink.visible_capacity, ctx->n, active_consts(ctx).n_views);
+        launch_publish_visible(pub, vb, ctx->d_stats, ctx->sink_rows_d, ctx->sink.visible_capacity, ctx->n, active_consts(ctx).n_views, ctx->sink_cls_d);
         if (!pipelined) { CU(cudaEventRecord(ctx->ev_pub, pub)); ctx->pub_pending = true; }
     }
     if (pe) CU(cudaEventRecord(pe[3], tail));
@@ -1368,6 +1383,21 @@ extern "C" int32_t b200vis_download_visible(b200vis_ctx *ctx, uint32_t view, uin
     if (rows) {
         if (c > capacity) return fail(ctx, B200VIS_ERR_CAPACITY, "download_visible: %u rows > capacity %u", c, capacity);
         CU(cudaMemcpyAsync(rows, ctx->vis.lists + (size_t)view * ctx->vis.list_stride, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_download_visible_classes(b200vis_ctx *ctx, uint32_t view, uint8_t *classes, uint32_t capacity, uint32_t *count) {
+    CHECK_CTX_JOIN();
+    if (view >= ctx->cfg.max_views || !count) return fail(ctx, B200VIS_ERR_INVALID_ARG, "download_visible_classes: bad argument");
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint32_t c = ctx->h_stats->visible_count[view];
+    *count = c;
+    if (classes) {
+        if (c > capacity) return fail(ctx, B200VIS_ERR_CAPACITY, "download_visible_classes: %u entries > capacity %u", c, capacity);
+        CU(cudaMemcpyAsync(classes, ctx->vis.classes + (size_t)view * ctx->vis.list_stride, c, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return B200VIS_OK;
@@ -1684,6 +1714,7 @@ extern "C" int32_t b200vis_set_result_sink(b200vis_ctx *ctx, const b200vis_resul
     int32_t rc;
     if ((rc = map_host(ctx, sink->stats, sizeof(b200vis_frame_stats), &ctx->sink_stats_d))) return rc;
     if ((rc = map_host(ctx, sink->visible_rows, V * sink->visible_capacity * 4, &ctx->sink_rows_d))) return rc;
+    { uint32_t *d = nullptr; if ((rc = map_host(ctx, sink->visible_classes, V * (size_t)sink->visible_capacity, &d))) return rc; ctx->sink_cls_d = reinterpret_cast<uint8_t *>(d); }
     if ((rc = map_host(ctx, sink->cluster_offsets, V * (kMaxClusters + 1) * 4, &ctx->sink_off_d))) return rc;
     if ((rc = map_host(ctx, sink->cluster_indices, V * (size_t)sink->cluster_capacity * 4, &ctx->sink_idx_d))) return rc;
     if ((sink->cluster_offsets == nullptr) != (sink->cluster_indices == nullptr))

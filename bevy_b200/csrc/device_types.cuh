@@ -26,7 +26,8 @@ struct Tile {               // one CTA's work: a contiguous, (mostly) hierarchy-
     uint16_t n_levels;      // in-tile depth levels (1 for flat rows)
     uint32_t warp_sync_mask; // bit l (1 <= l < 32): every row of level l has its parent in the same warp,
                              //   so __syncwarp orders the shared-memory hand-over instead of a CTA barrier
-    uint32_t pad;
+    uint32_t top_levels;     // K: every row of in-tile depth < K is one of the tile's first 32 rows (a BFS-ordered tree: its top
+                             //   5 levels), so ONE warp can walk those levels on its own (k_propagate_cull_scout), a tile ahead
 };
 
 // The same tile as one WARP's work (k_tile_warp): the warp walks the tile in chunks of 32 schedule slots.  The schedule
@@ -134,6 +135,8 @@ struct VisibleBufs {
     uint32_t *chunk_count;   // [3][V][chunks_stride], slot = frame % 3
     uint32_t *lists;         // [V][list_stride] rows, ascending Entity::to_bits()
     uint32_t list_stride;
+    uint8_t *classes;        // [V][list_stride] VisibilityClass mask of each listed row (the shim splits the list per class)
+    const uint8_t *cls;      // per row: VisibilityClass mask (bit k = class k of the shim's registry)
 };
 
 // RenderVisibleEntitiesClass::update_cpu_culled_entities on the device -- the added / removed

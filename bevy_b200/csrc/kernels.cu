@@ -663,6 +663,391 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
 }
 
 // ------------------------------------------------------------------------------------------
+// Kernel 1s: the TMA-staged CTA-per-tile pass with a SCOUT warp.
+//
+// ncu on kernel 1b (round 1): the hierarchy walk of a 255-node tree is a chain of 8 levels; levels 0-4 (31 rows) keep ONE
+// warp busy while seven wait at the CTA barrier, and that chain (~6 k cycles) is longer than the tile's parallel work.  Here
+// a ninth warp -- the scout -- runs one tile AHEAD of the 256 workers: it owns the TMA traffic (loads of tile k+1, store of
+// tile k-1: one thread, so the bulk-group waits are its own), decides the tile's mark_dirty_trees state, and walks the tile's
+// top levels (planner: Tile::top_levels = the leading levels that fit the first 32 rows) in place in the staged tile while
+// the workers are still culling the previous tile.  The workers then start at level K: three level rounds instead of eight
+// for a binary tree, no dirty-phase barrier, no load/store issue on their path.
+//   full[s]  TMA -> everybody        the tile's columns have landed in stage s
+//   top[s]   scout -> workers        dirty state + levels < K of stage s are final
+//   done[s]  workers -> scout        stage s may be stored and reused
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr int kScoutThreads = kTileRows + 32;
+struct ScoutSmem {
+    TileStage st[2];
+    unsigned long long full[2], top[2], done[2];
+    uint16_t parent[kTileRows];      // scout only: the ancestor climb of the slow dirty path
+    uint8_t pst[2][kTileRows];       // bit0 visited, bit1 gt changed
+    uint8_t dirty[2][kTileRows];     // TransformTreeChanged, valid when slow[s]
+    uint32_t slow[2];                // a row with an in-tile parent changed: workers read dirty[] instead of their own Changed bit
+    uint32_t any_gt[2];              // a worker row's GlobalTransform changed: the tile must be stored
+};
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ bool workers_or(bool p) {
+    uint32_t r;
+    asm volatile("{\n.reg .pred p, q;\nsetp.ne.u32 p, %1, 0;\nbar.red.or.pred q, 1, 256, p;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(r) : "r"((uint32_t)p) : "memory");
+    return r != 0;
+}
+
+template <bool CULL, bool SIMPLE, int MINB>
+__global__ void __launch_bounds__(kScoutThreads, MINB)
+k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, const __grid_constant__ CullViews cvw,
+                       VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity) {
+    extern __shared__ __align__(128) uint8_t smem_scout[];
+    ScoutSmem &s = *reinterpret_cast<ScoutSmem *>(smem_scout);
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.top[i], 1); mbar_init(&s.done[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything above overlapped the previous kernel's tail
+    uint32_t n_gt_total = 0, n_vv_total = 0;
+    if (tid >= (uint32_t)kTileRows) {
+        // ================================ scout warp ================================
+        const uint32_t lane = tid - kTileRows;
+        uint32_t it = 0, t = blockIdx.x;
+        Tile prev_tile = {};
+        bool prev_top_changed = false;
+        if (t < n_tiles && lane == 0) issue_tile_loads<true, CULL>(R, tiles[t], s.st[0], &s.full[0]);
+        for (; t < n_tiles; t += gridDim.x, ++it) {
+            const uint32_t sidx = it & 1u, ph = (it >> 1) & 1u;
+            const Tile tile = tiles[t];
+            mbar_wait(&s.full[sidx], ph);
+            TileStage &S = s.st[sidx];
+            const uint32_t off = tile.base & 15u;
+            // ---- mark_dirty_trees for the whole tile (systems.rs:111-306): each lane looks at 8 rows
+            bool slow = false;
+            if (static_opt && R.dirty == nullptr && tile.n_levels > 1) {
+                bool mine = false;
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) {
+                    const uint32_t r = lane * 8u + j;
+                    if (r < tile.n_rows) mine |= (S.flags[off + r] & F_TCHANGED) && (((S.topo[off + r] >> 9) & 0x1FFu) > 0u);
+                }
+                slow = __any_sync(kFull, mine);
+                if (slow) {       // a row below a root changed: climb the staged parent links
+                    for (uint32_t j = 0; j < 8; ++j) {
+                        const uint32_t r = lane * 8u + j;
+                        if (r < tile.n_rows) {
+                            const uint32_t tp = S.topo[off + r];
+                            s.parent[r] = (uint16_t)((((tp >> 9) & 0x1FFu) > 0u) ? (tp & 0x1FFu) : 0xFFFFu);
+                            s.dirty[sidx][r] = 0;
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t j = 0; j < 8; ++j) {
+                        const uint32_t r = lane * 8u + j;
+                        if (r < tile.n_rows && (S.flags[off + r] & F_TCHANGED)) {
+                            uint32_t c = r;
+                            while (!s.dirty[sidx][c]) {       // benign race: every writer stores 1, every chain finishes
+                                s.dirty[sidx][c] = 1;
+                                const uint32_t p = s.parent[c];
+                                if (p == 0xFFFFu) break;
+                                c = p;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) s.slow[sidx] = slow ? 1u : 0u;
+            // ---- the tile's top levels (depth < K), lane = row
+            const uint32_t K = tile.top_levels;
+            bool top_changed = false;
+            if (K > 0) {
+                const bool act = lane < tile.n_rows;
+                const uint32_t li = off + lane, row = tile.base + lane;
+                const uint32_t topo = act ? S.topo[li] : T_DETACHED, f = act ? S.flags[li] : 0u;
+                const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
+                const bool tchanged = f & F_TCHANGED, has_children = topo & T_HAS_CHILDREN;
+                const bool in_top = act && !(topo & T_DETACHED) && depth < K;
+                bool dirty = tchanged;
+                if (static_opt) {
+                    if (R.dirty != nullptr) dirty = act && R.dirty[row];
+                    else if (slow) dirty = act && s.dirty[sidx][lane];
+                }
+                const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
+                if (act && (topo & T_DETACHED)) s.pst[sidx][lane] = 0;     // never visited, and neither is its subtree
+                bool changed = false;
+                for (uint32_t lvl = 0; lvl < K; ++lvl) {
+                    __syncwarp();
+                    if (in_top && depth == lvl) {
+                        bool visited = false;
+                        Aff n = l;
+                        if (depth == 0u) {
+                            if (topo & T_ROOT) {
+                                visited = has_children ? (!static_opt || dirty) : tchanged;
+                                changed = visited;
+                            } else {
+                                const uint32_t pr = R.parent[row];
+                                const uint32_t ps = R.state[pr];
+                                visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
+                                if (visited) {
+                                    n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
+                                    changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);
+                                }
+                            }
+                        } else {
+                            const uint32_t pst = s.pst[sidx][plocal];
+                            const uint32_t pi = off + plocal;
+                            visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                            if (visited) {
+                                n.r0 = affine_mul_row(S.gt0[pi], l); n.r1 = affine_mul_row(S.gt1[pi], l); n.r2 = affine_mul_row(S.gt2[pi], l);
+                                changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);   // set_if_neq
+                            }
+                        }
+                        if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+                        s.pst[sidx][lane] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+                    }
+                }
+                top_changed = __any_sync(kFull, changed);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.top[sidx]);         // the workers may start this tile
+            // ---- the stage the previous tile used: store it once the workers are done with it, then load the next tile
+            const uint32_t tn = t + gridDim.x;
+            if (it >= 1u) {
+                mbar_wait(&s.done[sidx ^ 1u], ((it - 1u) >> 1) & 1u);
+                if (lane == 0 && (prev_top_changed || s.any_gt[sidx ^ 1u])) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
+                    TileStage &P = s.st[sidx ^ 1u];
+                    const uint32_t poff = prev_tile.base & 15u, bytes = (uint32_t)prev_tile.n_rows * 16u;
+                    bulk_s2g(R.gt0 + prev_tile.base, P.gt0 + poff, bytes); bulk_s2g(R.gt1 + prev_tile.base, P.gt1 + poff, bytes);
+                    bulk_s2g(R.gt2 + prev_tile.base, P.gt2 + poff, bytes);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            if (tn < n_tiles && lane == 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has left the stage
+                issue_tile_loads<true, CULL>(R, tiles[tn], s.st[sidx ^ 1u], &s.full[sidx ^ 1u]);
+            }
+            prev_tile = tile; prev_top_changed = top_changed;
+        }
+        if (it >= 1u) {       // the last tile
+            const uint32_t ls = (it - 1u) & 1u;
+            mbar_wait(&s.done[ls], ((it - 1u) >> 1) & 1u);
+            if (lane == 0 && (prev_top_changed || s.any_gt[ls])) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                TileStage &P = s.st[ls];
+                const uint32_t poff = prev_tile.base & 15u, bytes = (uint32_t)prev_tile.n_rows * 16u;
+                bulk_s2g(R.gt0 + prev_tile.base, P.gt0 + poff, bytes); bulk_s2g(R.gt1 + prev_tile.base, P.gt1 + poff, bytes);
+                bulk_s2g(R.gt2 + prev_tile.base, P.gt2 + poff, bytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+        // ================================ 256 workers ================================
+        const uint32_t lr = tid;
+        uint32_t it = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const uint32_t sidx = it & 1u, ph = (it >> 1) & 1u;
+            const Tile tile = tiles[t];
+            mbar_wait(&s.full[sidx], ph);
+            mbar_wait(&s.top[sidx], ph);
+            TileStage &S = s.st[sidx];
+            const uint32_t off = tile.base & 15u;
+            const uint32_t li = off + lr;                 // index into the staged window
+            const bool active = lr < tile.n_rows;
+            const uint32_t row = tile.base + lr;
+            const uint32_t f = active ? S.flags[li] : 0u;
+            const uint32_t st8 = active ? S.state[li] : 0u;
+            float4 bA = make_float4(0, 0, 0, 0); float2 bB = make_float2(0, 0);
+            if (CULL && active) { bA = R.bndA[row]; bB = R.bndB[row]; }
+            const uint32_t K = tile.top_levels;
+            const uint32_t topo = active ? S.topo[li] : T_DETACHED;
+            const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
+            const bool tchanged = f & F_TCHANGED;
+            const bool has_children = topo & T_HAS_CHILDREN;
+            bool dirty = tchanged;
+            if (static_opt) {
+                if (R.dirty != nullptr) dirty = active && R.dirty[row];
+                else if (s.slow[sidx]) dirty = active && s.dirty[sidx][lr];
+            }
+            const uint32_t my_level = (active && !(topo & T_DETACHED)) ? depth : 0xFFFFFFFFu;
+            bool visited = false, changed = false;
+            if (my_level < K) {                           // walked by the scout: take its verdict
+                const uint32_t pst = s.pst[sidx][lr];
+                visited = pst & 1u; changed = pst & 2u;
+            } else {
+                if (active && (topo & T_DETACHED) && has_children) s.pst[sidx][lr] = 0;
+                if (my_level != 0xFFFFFFFFu) {
+                    const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
+                    if (my_level == 0u) {                 // only when K == 0: roots, flat entities, rows with a parent in another tile
+                        Aff n = l;
+                        if (topo & T_ROOT) {
+                            visited = has_children ? (!static_opt || dirty) : tchanged;
+                            changed = visited;
+                        } else {
+                            const uint32_t pr = R.parent[row];
+                            const uint32_t ps = R.state[pr];
+                            visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
+                            if (visited) {
+                                n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
+                                changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);
+                            }
+                        }
+                        if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+                        if (has_children) s.pst[sidx][lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+                    }
+                    // the loop below needs `l` for the deeper levels: recomputed there (it is cheap) to keep it out of the registers
+                }
+            }
+            {
+                const uint32_t first = K > 1u ? K : 1u;
+                for (uint32_t lvl = first; lvl < tile.n_levels; ++lvl) {
+                    if (!(K > 0u && lvl == K)) {          // the scout's levels are ordered by top[]: no round needed before level K
+                        if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) __syncwarp(); else workers_sync();
+                    }
+                    if (my_level == lvl) {
+                        const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
+                        const uint32_t pst = s.pst[sidx][plocal];
+                        const uint32_t pi = off + plocal;
+                        visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                        if (visited) {
+                            Aff n;   // the parent's rows are the tile's own (in-place) GlobalTransform entries
+                            n.r0 = affine_mul_row(S.gt0[pi], l); n.r1 = affine_mul_row(S.gt1[pi], l); n.r2 = affine_mul_row(S.gt2[pi], l);
+                            changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);   // set_if_neq
+                            if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+                        }
+                        if (has_children) s.pst[sidx][lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+                    }
+                }
+            }
+            if (active && tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
+            uint32_t out = (st8 & (S_VV | S_HAS_CLASS)) | (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
+            bool vv_changed = false;
+            if (CULL) {
+                Aff g; g.r0 = S.gt0[li]; g.r1 = S.gt1[li]; g.r2 = S.gt2[li];   // own row: written by this thread, the scout, or untouched
+                const bool in_query = active && !(f & F_NO_CPU_CULL);
+                const bool base = in_query && (f & F_INHERITED);
+                const uint32_t prev = st8 & 1u;
+                const uint32_t lane = lr & 31u;
+                const bool has_aabb = f & F_AABB;
+                const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
+                float cx, cy, cz, radius;
+                const float hx = bA.w, hy = bB.x, hz = bB.y;
+                if (has_aabb) {
+                    cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;
+                    cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
+                    cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+                    const float vx = (g.r0.x * hx + g.r0.y * hy) + g.r0.z * hz;
+                    const float vy = (g.r1.x * hx + g.r1.y * hy) + g.r1.z * hz;
+                    const float vz = (g.r2.x * hx + g.r2.y * hy) + g.r2.z * hz;
+                    radius = sqrtf((vx * vx + vy * vy) + vz * vz);
+                } else {
+                    const bool from_gt = f & F_SPHERE_GT;
+                    cx = from_gt ? g.r0.w : bA.x; cy = from_gt ? g.r1.w : bA.y; cz = from_gt ? g.r2.w : bA.z;
+                    radius = bA.w;
+                }
+                unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
+                if (!SIMPLE && active) {
+                    if (R.layers != nullptr) elayers = R.layers[row];
+                    if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
+                    if (R.rank != nullptr) rnk = R.rank[row];
+                }
+                bool any = false;
+                uint32_t my_ballot = 0;
+#pragma unroll
+                for (uint32_t v = 0; v < kMaxViews; ++v) {
+                    if (v >= cvw.n_views) break;
+                    const uint32_t von = cvw.on[v];
+                    if (!(von & 1u)) continue;
+                    if (SIMPLE && !(von & 4u)) continue;   // bit2: the view includes the default layer
+                    bool vis = base;
+                    if (!SIMPLE) {
+                        vis = vis && (cvw.layers[v] & elayers) != 0ull;
+                        if ((f & F_RANGE) && R.range != nullptr) {
+                            const int32_t ri = cvw.range_index[v];
+                            vis = vis && ri >= 0 && ((erange >> ri) & 1u);
+                        }
+                    }
+                    if (do_test && !(von & 2u)) {
+                        const float d0 = plane_dot_point(cvw.planes[v][0], cx, cy, cz), d1 = plane_dot_point(cvw.planes[v][1], cx, cy, cz);
+                        const float d2 = plane_dot_point(cvw.planes[v][2], cx, cy, cz), d3 = plane_dot_point(cvw.planes[v][3], cx, cy, cz);
+                        const float d4 = plane_dot_point(cvw.planes[v][4], cx, cy, cz);
+                        const bool out_s = (d0 + radius <= 0.0f) | (d1 + radius <= 0.0f) | (d2 + radius <= 0.0f) |
+                                           (d3 + radius <= 0.0f) | (d4 + radius <= 0.0f);
+                        vis = vis && !out_s;
+                        if (vis && has_aabb) {
+                            const float d[5] = {d0, d1, d2, d3, d4};
+                            bool out_o = false;
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                const float4 n = cvw.planes[v][k];
+                                const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+                                const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+                                const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+                                const float rr = (dx * hx + dy * hy) + dz * hz;
+                                out_o |= (d[k] + rr <= 0.0f);
+                            }
+                            vis = !out_o;
+                        }
+                    }
+                    any |= vis;
+                    const bool listed = vis && (st8 & S_HAS_CLASS);
+                    if (SIMPLE || R.rank == nullptr) {
+                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
+                        if (lane == v) my_ballot = b;
+                    } else if (listed) {
+                        uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
+                        uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
+                        atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+                        atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
+                    }
+                }
+                if (my_ballot) {
+                    uint32_t *mask = vb.mask + (size_t)lane * vb.words_stride;
+                    uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + lane) * vb.chunks_stride;
+                    const uint32_t row0 = row - lane, w0 = row0 >> 5, sh = row0 & 31u;
+                    const uint32_t lo = my_ballot << sh, hi = sh ? (my_ballot >> (32u - sh)) : 0u;
+                    if (lo) { atomicOr(mask + w0, lo); atomicAdd(cc + (w0 / kChunkWords), __popc(lo)); }
+                    if (hi) { atomicOr(mask + w0 + 1, hi); atomicAdd(cc + ((w0 + 1) / kChunkWords), __popc(hi)); }
+                }
+                if (in_query) {
+                    out = (out & ~S_VV) | (any ? (1u | (prev << 1)) : 0u);
+                    vv_changed = (any ? 1u : 0u) != prev;
+                    if (vv_changed) out |= S_VV_CHANGED;
+                }
+                if (R.light_snap != nullptr && (f & F_SPHERE_GT) && active) {
+                    const uint32_t ord = R.light_ord[row];     // 0xFFFFFFFF: a sphere-from-GT row that is not a current light
+                    if (ord < R.n_lights) R.light_snap[ord] = make_float4(g.r0.w, g.r1.w, g.r2.w, (out & 1u) ? 1.0f : 0.0f);
+                }
+            } else {
+                out |= st8 & S_VV_CHANGED;
+            }
+            if (active && out != st8) R.state[row] = (uint8_t)out;
+            n_gt_total += changed ? 1u : 0u;
+            n_vv_total += vv_changed ? 1u : 0u;
+            // end of tile: everybody is done with this stage; the scout stores it and reuses the stage
+            const bool any_gt = workers_or(changed && !(my_level < K));
+            if (lr == 0) { s.any_gt[sidx] = any_gt ? 1u : 0u; mbar_arrive(&s.done[sidx]); }
+        }
+    }
+    // block-reduce the per-thread tallies (warp shuffle, then one shared-memory atomic per warp)
+    __shared__ uint32_t s_cnt[2];
+    if (tid < 2) s_cnt[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n_gt_total += __shfl_xor_sync(kFull, n_gt_total, o); n_vv_total += __shfl_xor_sync(kFull, n_vv_total, o); }
+    if ((tid & 31u) == 0) { if (n_gt_total) atomicAdd(&s_cnt[0], n_gt_total); if (n_vv_total) atomicAdd(&s_cnt[1], n_vv_total); }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_cnt[0]) atomicAdd(&stats->changed[parity][0], s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&stats->changed[parity][1], s_cnt[1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Kernel 1w (default): the fused propagate -> cull pass with one WARP per tile and no CTA barrier at all.
 //
 // Why: the CTA-per-tile kernels above spend their time waiting -- the hierarchy walk of a 255-node tree is a chain of
@@ -682,7 +1067,6 @@ struct __align__(16) WarpSmem {
     uint8_t dirty[kWarpParentSlots];    // TransformTreeChanged of the rows with children (slow path of the dirty phase)
     uint8_t ppar[kWarpParentSlots];     // parent slot of each slot's row, 0xFF = none
 };
-constexpr uint32_t kFull = 0xFFFFFFFFu;
 // byte c (0..7) of the register pair (w0, w1)
 __device__ __forceinline__ uint32_t sel_byte(uint32_t w0, uint32_t w1, uint32_t c) { return ((c < 4u ? w0 : w1) >> (8u * (c & 3u))) & 0xFFu; }
 
@@ -1213,10 +1597,13 @@ k_expand_visible(VisibleBufs vb, DiffBufs db, const uint32_t *__restrict__ row_o
     __syncthreads();
     uint32_t pos = s_base + (incl - c) + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
     uint32_t *out = vb.lists + (size_t)v * vb.list_stride;
+    uint8_t *out_cls = vb.classes ? vb.classes + (size_t)v * vb.list_stride : nullptr;
     while (w) {
         const uint32_t b = __ffs(w) - 1; w &= w - 1;
         const uint32_t rk = word * 32u + b;
-        out[pos++] = row_of_rank ? row_of_rank[rk] : rk;
+        const uint32_t rw = row_of_rank ? row_of_rank[rk] : rk;
+        if (out_cls) out_cls[pos] = vb.cls[rw];       // one push per class of the row (visibility/mod.rs:852-857): the shim splits
+        out[pos++] = rw;
     }
     if (chunk == 0 && t == 0) stats->visible_count[v] = s_total;
     (void)n_rows;
@@ -1771,13 +2158,17 @@ __global__ void k_snapshot_lights(Rows R, Lights L, float4 *__restrict__ snap) {
 // ---- result sink: coalesced copies of a frame's results into mapped pinned host memory ----------------------
 // visible lists: grid (blocks, views), grid-stride over the view's count
 __global__ void k_publish_visible(const uint32_t *__restrict__ lists, uint32_t list_stride, const DevStats *__restrict__ stats,
-                                  uint32_t *__restrict__ host_rows, uint32_t host_stride, uint32_t n_views) {
+                                  uint32_t *__restrict__ host_rows, uint32_t host_stride, uint32_t n_views,
+                                  const uint8_t *__restrict__ classes, uint8_t *__restrict__ host_classes) {
     const uint32_t v = blockIdx.y;
     if (v >= n_views) return;
     const uint32_t count = min(stats->visible_count[v], host_stride);
     // one row per thread: a warp writes 128 contiguous bytes (view strides need not be 16-byte multiples)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
         host_rows[(size_t)v * host_stride + i] = lists[(size_t)v * list_stride + i];
+    if (host_classes != nullptr && classes != nullptr)      // 4 class bytes per thread: 128 contiguous bytes per warp
+        for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; i < count; i += gridDim.x * blockDim.x * 4u)
+            for (uint32_t k = i; k < min(i + 4u, count); ++k) host_classes[(size_t)v * host_stride + k] = classes[(size_t)v * list_stride + k];
 }
 // cluster CSR + the stats block (also formats b200vis_frame_stats, whose layout the host passes as offsets)
 __global__ void k_publish_clusters(const FrameConsts *__restrict__ fc, const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ indices,
@@ -2137,7 +2528,7 @@ __global__ void k_pack_gt(Rows R, uint32_t first, uint32_t count, float *__restr
     }
 }
 __global__ void k_unpack_bounds(Rows R, uint32_t first, uint32_t count, const float *__restrict__ bounds,
-                                const uint8_t *__restrict__ flags, const uint8_t *__restrict__ cls) {
+                                const uint8_t *__restrict__ flags, const uint8_t *__restrict__ cls, uint8_t *__restrict__ cls_col) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const uint32_t row = first + i;
@@ -2146,6 +2537,7 @@ __global__ void k_unpack_bounds(Rows R, uint32_t first, uint32_t count, const fl
     R.bndB[row] = make_float2(b[4], b[5]);
     R.flags[row] = (uint8_t)((flags[i] & 0x7Fu) | (R.flags[row] & F_TCHANGED));
     R.state[row] = (uint8_t)((R.state[row] & ~S_HAS_CLASS) | (cls[i] ? S_HAS_CLASS : 0u));
+    cls_col[row] = cls[i];
 }
 __global__ void k_unpack_vv(Rows R, uint32_t first, uint32_t count, const uint8_t *__restrict__ vv) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2229,15 +2621,15 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 static unsigned long long g_launches = 0;
 unsigned long long kernel_launch_count() { return g_launches; }
 
-static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile, 2 warp per tile (default)
+static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile, 2 warp per tile, 3 TMA + scout warp
 static int tile_kernel_choice() {
     if (g_tile_kernel < 0) {
         const char *e = getenv("B200VIS_TILE_KERNEL");
-        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 't') ? 1 : 2;
+        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 't') ? 1 : (e && e[0] == 'w') ? 2 : 3;
     }
     return g_tile_kernel;
 }
-bool tile_kernel_is_tma() { return tile_kernel_choice() == 1; }
+bool tile_kernel_is_tma() { return tile_kernel_choice() == 1 || tile_kernel_choice() == 3; }
 bool tile_kernel_publishes_light_snapshot() { return tile_kernel_choice() != 0; }
 template <bool C, bool S, int MINB, bool PIPE>
 static void launch_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, const uint8_t *sched, uint32_t n_tiles, const CullViews &cvw,
@@ -2296,6 +2688,44 @@ void launch_tile_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, con
 #undef B200VIS_WARP_CASE
 }
 bool tile_kernel_is_warp() { return tile_kernel_choice() == 2; }
+template <bool C, bool S, int MINB>
+static void launch_scout(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
+                         const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity) {
+    static int grid = 0, tiles_per_cta = 0;
+    if (!grid) {
+        cudaFuncSetAttribute(k_propagate_cull_scout<C, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoutSmem));
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate_cull_scout<C, S, MINB>, kScoutThreads, sizeof(ScoutSmem));
+        grid = sms * (per_sm > 0 ? per_sm : 1);    // persistent: one CTA per resident slot
+        // B200VIS_SCOUT_TILES_PER_CTA=k bounds the tiles one CTA walks (0 = fully persistent, the default: the scout's
+        // one-tile lead pays off over a run of tiles; the first tile of every CTA has none)
+        const char *e = getenv("B200VIS_SCOUT_TILES_PER_CTA");
+        tiles_per_cta = e ? atoi(e) : 0;
+    }
+    uint32_t g = n_tiles < (uint32_t)grid ? n_tiles : (uint32_t)grid;
+    if (tiles_per_cta > 0) {
+        uint32_t want = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+        want = ((want + (uint32_t)grid - 1) / (uint32_t)grid) * (uint32_t)grid;      // whole waves of resident CTAs
+        if (want > n_tiles) want = n_tiles;
+        if (want > g) g = want;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g); cfg.blockDim = dim3(kScoutThreads); cfg.dynamicSmemBytes = sizeof(ScoutSmem); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ++g_launches; cudaLaunchKernelEx(&cfg, k_propagate_cull_scout<C, S, MINB>, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
+}
+template <int MINB>
+static void launch_scout_m(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw, const VisibleBufs &vb,
+                           DevStats *stats, bool cull, bool simple, uint32_t static_opt, uint32_t parity) {
+    if (cull) { if (simple) launch_scout<true, true, MINB>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
+                else launch_scout<true, false, MINB>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity); }
+    else launch_scout<false, true, MINB>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
+}
 template <bool P, bool C, bool S>
 static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                        const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity) {
@@ -2351,7 +2781,14 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
     if (n_tiles == 0) return;
     const bool prop = stages & 1u, cull = stages & 2u;
     const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
-    if (tile_kernel_choice() == 1) {
+    if (tile_kernel_choice() == 3 && prop) {       // TMA-staged tiles + a scout warp one tile ahead (default)
+        static int per_sm = 0;
+        if (!per_sm) { const char *e = getenv("B200VIS_SCOUT_CTAS_PER_SM"); per_sm = (e && atoi(e) == 4) ? 4 : 3; }
+        if (per_sm == 4) launch_scout_m<4>(st, R, tiles, n_tiles, cvw, vb, stats, cull, simple, static_opt, parity);
+        else launch_scout_m<3>(st, R, tiles, n_tiles, cvw, vb, stats, cull, simple, static_opt, parity);
+        return;
+    }
+    if (tile_kernel_choice() == 1 || tile_kernel_choice() == 3) {
 #define B200VIS_LAUNCH_TMA(P, C, S) launch_tma<P, C, S>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity)
         if (prop && cull) { if (simple) B200VIS_LAUNCH_TMA(true, true, true); else B200VIS_LAUNCH_TMA(true, true, false); }
         else if (prop) B200VIS_LAUNCH_TMA(true, false, true);
@@ -2417,9 +2854,9 @@ bool launch_cluster_fused(cudaStream_t st, const Rows &R, const Lights &L, const
     ++g_launches; return cudaLaunchKernelEx(&cfg, k_cluster_fused, R, L, fc, cb, stats) == cudaSuccess;
 }
 void launch_publish_visible(cudaStream_t st, const VisibleBufs &vb, const DevStats *stats, uint32_t *host_rows, uint32_t host_stride,
-                            uint32_t n_rows, uint32_t n_views) {
+                            uint32_t n_rows, uint32_t n_views, uint8_t *host_classes) {
     if (!n_views || !n_rows) return;
-    ++g_launches; k_publish_visible<<<dim3(min(cdiv(n_rows, 256), 296u), n_views), 256, 0, st>>>(vb.lists, vb.list_stride, stats, host_rows, host_stride, n_views);
+    ++g_launches; k_publish_visible<<<dim3(min(cdiv(n_rows, 256), 296u), n_views), 256, 0, st>>>(vb.lists, vb.list_stride, stats, host_rows, host_stride, n_views, vb.classes, host_classes);
 }
 void launch_publish_clusters(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, uint32_t *host_offsets, uint32_t *host_indices,
                              uint32_t host_cap, const DevStats *stats, uint32_t *host_stats, uint32_t changed_slot, uint32_t frame, uint32_t max_views) {
@@ -2476,8 +2913,8 @@ void launch_pack_gt(cudaStream_t st, const Rows &R, uint32_t first, uint32_t cou
     if (count) { ++g_launches; k_pack_gt<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, dst, stride); }
 }
 void launch_unpack_bounds(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const float *bounds,
-                          const uint8_t *flags, const uint8_t *cls) {
-    if (count) { ++g_launches; k_unpack_bounds<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, bounds, flags, cls); }
+                          const uint8_t *flags, const uint8_t *cls, uint8_t *cls_col) {
+    if (count) { ++g_launches; k_unpack_bounds<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, bounds, flags, cls, cls_col); }
 }
 void launch_unpack_vv(cudaStream_t st, const Rows &R, uint32_t first, uint32_t count, const uint8_t *vv) {
     if (count) { ++g_launches; k_unpack_vv<<<cdiv(count, 256), 256, 0, st>>>(R, first, count, vv); }

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200VIS_ABI_VERSION 1
+#define B200VIS_ABI_VERSION 2
 #if defined(__GNUC__)
 #define B200VIS_API __attribute__((visibility("default")))
 #else
@@ -295,6 +295,12 @@ B200VIS_API int32_t b200vis_download_view_visibility(b200vis_ctx *ctx, uint32_t 
  * Entity::to_bits() (visibility/mod.rs:861-874).  An inactive view keeps last frame's list (:780-782). */
 B200VIS_API int32_t b200vis_download_visible(b200vis_ctx *ctx, uint32_t view, uint32_t *rows, uint32_t capacity,
                                  uint32_t *count);
+/* VisibleEntities::entities is one sorted Vec per VisibilityClass, and an entity with k classes is pushed k times
+ * (visibility/mod.rs:344-347, 852-857).  classes[i] = the class mask (as uploaded by b200vis_upload_bounds, bit k = class k
+ * of the shim's TypeId registry, at most 8) of the i-th row of b200vis_download_visible's list: walking the list once and
+ * pushing entity i into every class list whose bit is set yields each class's list already sorted. */
+B200VIS_API int32_t b200vis_download_visible_classes(b200vis_ctx *ctx, uint32_t view, uint8_t *classes, uint32_t capacity,
+                                                     uint32_t *count);
 /* Clusters of one view in CSR form: offsets[n_clusters+1], light ordinals (index into the
  * b200vis_set_lights arrays; with world_size>1: global ordinal = rank-major) in the reference's
  * push order, cluster index = (y*dims.x + x)*dims.z + z (assign.rs:676-678). */
@@ -318,6 +324,7 @@ B200VIS_API int32_t b200vis_download_frame(b200vis_ctx *ctx, b200vis_frame_stats
 typedef struct b200vis_result_sink {
     b200vis_frame_stats *stats;
     uint32_t *visible_rows;   uint32_t visible_capacity;
+    uint8_t  *visible_classes; /* nullable: [max_views][visible_capacity] VisibilityClass mask of each listed row */
     uint32_t *cluster_offsets;
     uint32_t *cluster_indices; uint32_t cluster_capacity;
 } b200vis_result_sink;

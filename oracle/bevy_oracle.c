@@ -645,6 +645,28 @@ typedef struct {
 } orc_cluster_view_out;
 
 /* ClusterConfig::dimensions_for_screen_size (cluster/mod.rs:311-347) */
+/* VisibleEntities::entities is one Vec<Entity> PER VisibilityClass (TypeIdHashMap<Vec<Entity>>,
+ * crates/bevy_camera/src/visibility/mod.rs:344-347): a visible entity is pushed once for every class id in its
+ * VisibilityClass (:846-857, thread-local queues merged per class :861-868), and every class list is sorted by
+ * Entity::to_bits() at the end (:870-874).  class_mask bit k = "the entity's VisibilityClass contains class k" (the shim's
+ * registry of TypeIds, at most 8).  `visible` = the rows one view found visible AND classed (orc_cull's list, any order).
+ * out_rows[k * n_visible + i], out_count[k] for k in 0..8. */
+ORC_API void orc_visible_entities_by_class(uint32_t n_visible, const uint32_t *visible, const uint8_t *class_mask,
+                                           const uint64_t *entity_bits, uint32_t *out_rows, uint32_t *out_count) {
+    sort_item *items = (sort_item *)malloc((size_t)(n_visible ? n_visible : 1) * sizeof(sort_item));
+    for (uint32_t k = 0; k < 8; ++k) {
+        uint32_t cnt = 0;
+        for (uint32_t i = 0; i < n_visible; ++i) {                  /* for class_id in visibility_class.iter(): push */
+            uint32_t r = visible[i];
+            if (class_mask[r] & (1u << k)) { items[cnt].key = entity_bits[r]; items[cnt].row = r; cnt++; }
+        }
+        qsort(items, cnt, sizeof(sort_item), cmp_sort_item);        /* entities.sort_unstable() per class */
+        for (uint32_t i = 0; i < cnt; ++i) out_rows[(size_t)k * n_visible + i] = items[i].row;
+        out_count[k] = cnt;
+    }
+    free(items);
+}
+
 ORC_API void orc_cluster_dimensions_for_screen_size(uint32_t kind, const uint32_t *cfg_dims, uint32_t total,
                                                     uint32_t z_slices, uint32_t w, uint32_t h, uint32_t *out3) {
     if (kind == 0) { out3[0] = out3[1] = out3[2] = 0; return; }

@@ -300,6 +300,20 @@ def cull(gt, bounds, flags, class_mask, entity_bits, vv, view_planes, view_layer
     return vv_changed, lists
 
 
+def visible_entities_by_class(visible_rows, class_mask, entity_bits):
+    """VisibleEntities::entities of one view: {class k: sorted rows} (orc_visible_entities_by_class)."""
+    vis = np.ascontiguousarray(visible_rows, np.uint32)
+    class_mask = np.ascontiguousarray(class_mask, np.uint8)
+    entity_bits = np.ascontiguousarray(entity_bits, np.uint64)
+    m = len(vis)
+    out = np.zeros((8, max(m, 1)), np.uint32)
+    cnt = np.zeros(8, np.uint32)
+    fn = lib().orc_visible_entities_by_class
+    fn.restype = None
+    fn(m, _p(vis, C.c_uint32), _p(class_mask, C.c_uint8), _p(entity_bits, C.c_uint64), _p(out, C.c_uint32), _p(cnt, C.c_uint32))
+    return {k: out[k, :cnt[k]].copy() for k in range(8) if cnt[k]}
+
+
 def default_cluster_view_in(camera_gt12, clip_from_view, frustum, screen=(1920, 1080), view_layers=1,
                             config_kind=3, cfg_dims=(0, 0, 0), total=4096, z_slices=24, first_slice_depth=5.0,
                             far_z_mode=0, far_z_constant=0.0, dynamic_resizing=True, max_indices=16384,

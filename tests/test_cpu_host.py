@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in include/b200vis.h but not exported"
     assert declared == set(abi.EXPORTED_SYMBOLS), declared ^ set(abi.EXPORTED_SYMBOLS)
-    assert bb.abi_version() == 1
+    assert bb.abi_version() == 2
 
 
 def test_create_without_cuda_fails_loudly():

@@ -472,3 +472,34 @@ def test_column_write_back_keeps_a_host_mirror_identical_to_the_device(stride):
         pipe.ctx.set_column_sinks()
     finally:
         pipe.close()
+
+
+def test_visible_entities_per_visibility_class():
+    """VisibleEntities::entities is one sorted Vec per VisibilityClass; an entity with k classes is pushed k times
+    (visibility/mod.rs:344-347, 852-857).  The device returns each view's sorted list plus the class mask of every entry; the
+    split the shim performs must equal the oracle's push-per-class + sort-per-class restatement."""
+    import oracle as orc
+    sc = scenes.forest(n_trees=90, levels=6, n_lights=10)
+    rng = np.random.default_rng(5)
+    sc.class_mask = rng.choice(np.array([0, 1, 2, 3, 6, 0x81, 0xFF], np.uint8), sc.n).astype(np.uint8)
+    sc.entity_bits = rng.permutation(sc.n).astype(np.uint64) + np.uint64(7)          # rows are NOT in Entity order
+    pipe = bb.VisibilityPipeline(sc)
+    world = OracleWorld(sc)
+    try:
+        for f in range(3):
+            if f:
+                scenes.advance_cameras(sc, 0.08)
+                rows, trs = scenes.mutate_roots(sc, f)
+                pipe.ctx.upload_transforms_scattered(rows, trs)
+                world.tchanged[rows] = 1
+            pipe.update_views()
+            compare_frame(pipe, world, f)
+            for v in range(len(sc.cameras)):
+                got = pipe.ctx.download_visible_by_class(v)
+                want = orc.visible_entities_by_class(world.last_lists[v], sc.class_mask, sc.entity_bits)
+                assert sorted(got) == sorted(want), (f, v, sorted(got), sorted(want))
+                for k in want:
+                    assert len(got[k]) == len(want[k]) and (got[k] == want[k]).all(), f"frame {f} view {v} class {k}"
+                assert sum(len(x) for x in want.values()) >= len(world.last_lists[v])     # multi-class rows are pushed more than once
+    finally:
+        pipe.close()
