@@ -136,13 +136,30 @@ def emit(line):
 # reference arm / cpu baseline: the oracle's multithreaded restatement on the host cores
 # ---------------------------------------------------------------------------------------------
 def physical_cores():
+    """Threads for the CPU arm: physical cores this process may use -- affinity mask, SMT siblings counted once, and the
+    container's CPU quota (cgroup cpu.max), because threads beyond the quota are throttled, not run."""
     aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         import psutil
         phys = psutil.cpu_count(logical=False) or aff
     except Exception:
         phys = aff
-    return max(1, min(aff, phys))
+    n = max(1, min(aff, phys))
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = max(1, min(n, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = max(1, min(n, q // period))
+            break
+        except Exception:
+            continue
+    return n
 
 
 class CpuArm:
@@ -159,10 +176,23 @@ class CpuArm:
         from bevy_b200 import scenes
         from parity import OracleWorld
         self.orc, self.scenes, self.scene = orc, scenes, scene
-        self.threads = physical_cores()
-        orc.lib_mt().orc_mt_set_threads(self.threads)
         self.world = OracleWorld(scene, static_opt=True)
         self.frame_no = 0
+        # thread count: physical cores (quota-aware); on a shared or quota-limited host fewer threads can be faster (threads
+        # beyond the CPUs actually granted are throttled, and the merge + sort of the visible lists is serial), so a few
+        # fixed fractions are tried on warm frames and the best median is kept -- the figure reported is that one
+        cores = physical_cores()
+        self.frame(); self.frame()                    # first touch / page faults
+        best = None
+        for nt in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16), min(cores, 8)}, reverse=True):
+            orc.lib_mt().orc_mt_set_threads(nt)
+            self.frame()
+            med = float(np.median([self.frame() for _ in range(3)]))
+            if best is None or med < best[0]:
+                best = (med, nt)
+        self.threads = best[1]
+        self.calibration = f"{self.threads} of {cores} cores (best median of 3 warm frames among fixed fractions of the core count)"
+        orc.lib_mt().orc_mt_set_threads(self.threads)
 
     def frame(self):
         f = self.frame_no; self.frame_no += 1
@@ -182,11 +212,12 @@ class CpuArm:
         return np.array([self.frame() for _ in range(steps)])
 
 
-def cpu_summary(times, n, threads, what):
+def cpu_summary(times, n, threads, what, calibration=""):
     med = float(np.median(times))
     return {"value": n / med, "unit": "entities/s", "cores": threads, "kind": "port",
             "ms_per_step_median": med * 1e3, "ms_per_step_min": float(times.min()) * 1e3, "ms_per_step_max": float(times.max()) * 1e3,
-            "sample": what + "; OpenMP, threads = physical cores, pinned (OMP_PROC_BIND=close, OMP_PLACES=cores); Rust toolchain "
+            "threads": calibration,
+            "sample": what + "; OpenMP, pinned (OMP_PROC_BIND=close, OMP_PLACES=cores); Rust toolchain "
                              "absent: C restatement of the reference algorithm (oracle/bevy_oracle_mt.c), not Bevy itself"}
 
 
@@ -214,7 +245,7 @@ def run_reference(args):
                        f"a full frame takes {probe * 1e3:.1f} ms here")
     times = arm.run(K, W)
     n = scene.n
-    cb = cpu_summary(times, n, arm.threads, sample_note)
+    cb = cpu_summary(times, n, arm.threads, sample_note, arm.calibration)
     val = cb["value"]
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "entities/s", "n_gpus": args.gpus,
@@ -862,7 +893,8 @@ def main():
             arm = CpuArm(cpu_scene)
             times = arm.run(args.cpu_frames, 3)
             line["cpu_baseline"] = cpu_summary(times, cpu_scene.n, arm.threads,
-                                               f"{args.cpu_frames} frames of the same {cpu_scene.n}-entity workload after 3 warm-up frames")
+                                               f"{args.cpu_frames} frames of the same {cpu_scene.n}-entity workload after 3 warm-up frames",
+                                               arm.calibration)
         emit(line)
     if world > 1:
         dist.barrier()

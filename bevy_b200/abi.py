@@ -88,6 +88,11 @@ class ColumnSinks(C.Structure):
                 ("view_visibility", C.c_void_p), ("vv_changed_bits", C.c_void_p)]
 
 
+class ShadowItem(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("light_row", C.c_uint32), ("range", C.c_float), ("range_view_index", C.c_int32),
+                ("layer_mask", C.c_uint64), ("frusta", C.c_float * 144)]
+
+
 class ResultSink(C.Structure):
     _fields_ = [("stats", C.POINTER(FrameStats)), ("visible_rows", C.c_void_p), ("visible_capacity", C.c_uint32),
                 ("visible_classes", C.c_void_p), ("cluster_offsets", C.c_void_p), ("cluster_indices", C.c_void_p), ("cluster_capacity", C.c_uint32)]
@@ -109,10 +114,14 @@ _SIGNATURES = {
     "b200vis_tail_stream": (C.c_int32, [_vp, _P(_vp)]),
     "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
     "b200vis_kernel_launch_count": (C.c_uint64, []),
+    "b200vis_upload_render_layers_ext": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "b200vis_set_view_render_layers_ext": (C.c_int32, [_vp, C.c_uint32, _vp]),
+    "b200vis_set_shadow_items": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32]),
     "b200vis_download_visible_classes": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_cluster_view_dims": (C.c_int32, [_vp, C.c_uint32, _P(C.c_uint32)]),
     "b200vis_set_column_sinks": (C.c_int32, [_vp, _P(ColumnSinks)]),
     "b200vis_writeback_columns": (C.c_int32, [_vp]),
+    "b200vis_writeback_columns_ex": (C.c_int32, [_vp, C.c_uint32]),
     "b200vis_host_plan_summary": (C.c_int32, [C.c_uint32, _vp, _P(C.c_uint32)]),
     "b200vis_host_warp_plan": (C.c_int32, [C.c_uint32, _vp, C.c_uint32, C.c_uint32, _P(C.c_uint32), _vp, _vp, _vp, _vp]),
     "b200vis_plan_row_order": (C.c_int32, [C.c_uint32, _vp, _vp]),
@@ -365,6 +374,14 @@ class Context:
         l = _arr(layer_mask, np.uint64); r = _arr(range_mask, np.uint32)
         self._check(self._lib.b200vis_upload_bounds(self._h, first_row, len(b), _ptr(b), _ptr(f), _ptr(c), _ptr(l), _ptr(r)))
 
+    def upload_render_layers_ext(self, first_row, blocks):
+        blocks = _arr(blocks, np.uint64).reshape(-1, 3)
+        self._check(self._lib.b200vis_upload_render_layers_ext(self._h, first_row, len(blocks), _ptr(blocks)))
+
+    def set_view_render_layers_ext(self, view, blocks):
+        b = _arr(blocks, np.uint64).reshape(3)
+        self._check(self._lib.b200vis_set_view_render_layers_ext(self._h, view, _ptr(b)))
+
     def upload_view_visibility(self, first_row, vv):
         v = _arr(vv, np.uint8)
         self._check(self._lib.b200vis_upload_view_visibility(self._h, first_row, len(v), _ptr(v)))
@@ -467,6 +484,21 @@ class Context:
         lm = None if layer_mask is None else np.ascontiguousarray(layer_mask, np.uint64)
         self._check(self._lib.b200vis_set_shadow_lights(self._h, len(o), _ptr(o), _ptr(fr), None if lm is None else _ptr(lm),
                                                         int(lod_origin_range_index), int(list_capacity)))
+
+    def set_shadow_items(self, items, list_capacity=0):
+        """items: list of dicts(kind, light_row, range, range_view_index, layer_mask, frusta [6,6,4] or [6,4])."""
+        arr = (ShadowItem * max(len(items), 1))()
+        for i, it in enumerate(items):
+            arr[i].kind = it["kind"]; arr[i].light_row = it.get("light_row", 0); arr[i].range = it.get("range", 0.0)
+            arr[i].range_view_index = it.get("range_view_index", -1); arr[i].layer_mask = it.get("layer_mask", 1)
+            fr = np.zeros((6, 6, 4), np.float32)
+            f = np.asarray(it["frusta"], np.float32)
+            if f.ndim == 2:
+                fr[0] = f
+            else:
+                fr[:] = f
+            arr[i].frusta[:] = fr.reshape(-1).tolist()
+        self._check(self._lib.b200vis_set_shadow_items(self._h, len(items), arr, list_capacity))
 
     def run_shadow_culling(self):
         self._check(self._lib.b200vis_run_shadow_culling(self._h))
@@ -588,8 +620,9 @@ class Context:
         self._colsink_keep = (gt, gt_changed_bits, view_visibility, vv_changed_bits)
         self._check(self._lib.b200vis_set_column_sinks(self._h, C.byref(s)))
 
-    def writeback_columns(self):
-        self._check(self._lib.b200vis_writeback_columns(self._h))
+    def writeback_columns(self, which=3):
+        """which: 1 = GlobalTransform (+ its change bits), 2 = ViewVisibility (+ its change bits), 3 = both."""
+        self._check(self._lib.b200vis_writeback_columns_ex(self._h, which))
 
     def p2p_export(self):
         """CUDA IPC handle (64 bytes) of this rank's gathered buffer."""

@@ -76,6 +76,7 @@ struct b200vis_ctx {
 
     uint32_t n = 0;                 // current row count
     Rows rows{};                    // device SoA (capacity cfg.max_entities)
+    uint64_t *d_layers_ext = nullptr; bool have_layers_ext = false; uint64_t view_layers_ext[kMaxViews][3] = {};   // RenderLayers blocks 1..3
     uint32_t *d_parent = nullptr; uint64_t *d_layers = nullptr; uint32_t *d_range = nullptr;
     uint32_t *d_rank = nullptr, *d_row_of_rank = nullptr; uint8_t *d_dirty = nullptr;
     bool have_layers = false, have_range = false, rank_identity = true, topology_set = false;
@@ -129,6 +130,7 @@ struct b200vis_ctx {
     uint32_t frame = 0, parity = 0;
 
     // lights + clusters
+    std::vector<uint32_t> h_light_row; std::vector<float> h_light_range;   // host copies (b200vis_set_shadow_lights resolves ordinals)
     Lights lights{}; uint32_t *d_light_row = nullptr; float *d_light_range = nullptr; uint64_t *d_light_layers = nullptr;
     ClusterBufs cl{}; uint32_t *d_slab = nullptr; void *ext_send = nullptr, *ext_recv = nullptr;
     size_t slab_bytes = 0;
@@ -140,6 +142,9 @@ struct b200vis_ctx {
 
     b200vis_column_sinks colsink{}; bool have_colsink = false;          // b200vis_set_column_sinks (device aliases below)
     float *col_gt_d = nullptr; uint32_t *col_gt_bits_d = nullptr, *col_vv_bits_d = nullptr; uint8_t *col_vv_d = nullptr;
+    uint8_t *d_vv_shadow = nullptr;     // what the host ViewVisibility column holds (0xFF = unknown)
+    float *d_gt_aos = nullptr;          // dense write-back: the GlobalTransform column in the host's layout, copied by the DMA engine
+    uint32_t last_gt_changed = 0;       // Changed<GlobalTransform> rows of the last frame whose statistics the host has seen
     double step_t[6] = {0, 0, 0, 0, 0, 0}; uint64_t step_n = 0;   // B200VIS_STEP_TRACE: host time per phase of b200vis_step
     void *nccl_comm = nullptr;          // b200vis_comm_init
     uint32_t *d_gather = nullptr;       // [world][slab] when the library owns the exchange
@@ -192,7 +197,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     Rows &r = ctx->rows;
     void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
-                   ctx->d_tiles, ctx->d_wtiles, ctx->d_sched, ctx->d_wtopo, ctx->d_tile_counter, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_light_snap, ctx->d_tag_flag, ctx->d_light_ord,
+                   ctx->d_layers_ext, ctx->d_vv_shadow, ctx->d_gt_aos, ctx->d_tiles, ctx->d_wtiles, ctx->d_sched, ctx->d_wtopo, ctx->d_tile_counter, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_light_snap, ctx->d_tag_flag, ctx->d_light_ord,
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->vis.classes, ctx->d_cls, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage,
                    ctx->diff.prev, ctx->diff.words, ctx->diff.chunk, ctx->diff.lists, ctx->diff.count,
@@ -612,7 +617,7 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     std::vector<uint32_t> &topo = plan.topo; std::vector<Tile> &tiles = plan.tiles;
     std::vector<uint32_t> &pass_begin = plan.pass_begin, &pass_small = plan.pass_small;
     if (tiles.size() > ctx->tiles_cap) {
-        void *old[] = {ctx->d_tiles, ctx->d_wtiles, ctx->d_sched};
+        void *old[] = {ctx->d_layers_ext, ctx->d_vv_shadow, ctx->d_gt_aos, ctx->d_tiles, ctx->d_wtiles, ctx->d_sched};
         for (void *q : old) if (q) cudaFree(q);
         ctx->d_tiles = nullptr; ctx->d_wtiles = nullptr; ctx->d_sched = nullptr; ctx->tiles_cap = (uint32_t)tiles.size() + 1024;
         CU(dalloc(&ctx->d_tiles, ctx->tiles_cap));
@@ -817,6 +822,26 @@ extern "C" int32_t b200vis_upload_bounds(b200vis_ctx *ctx, uint32_t first, uint3
     ctx->lights_tag_dirty = true;   // flags were rewritten: re-verify that every light row is a sphere-from-GT row
     return B200VIS_OK;
 }
+extern "C" int32_t b200vis_upload_render_layers_ext(b200vis_ctx *ctx, uint32_t first, uint32_t count, const uint64_t *blocks) {
+    CHECK_CTX();
+    if (count && !blocks) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_render_layers_ext: null");
+    int32_t rc = check_range(ctx, first, count, "upload_render_layers_ext"); if (rc) return rc;
+    if (!ctx->d_layers_ext) CU(dalloc(&ctx->d_layers_ext, (size_t)ctx->cfg.max_entities * 3));   // rows never uploaded: blocks empty
+    CU(cudaMemcpyAsync(ctx->d_layers_ext + (size_t)first * 3, blocks, (size_t)count * 24, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->have_layers) {   // the general cull path reads block 0 per row too: default layer for everybody until uploaded
+        std::vector<uint64_t> ones(ctx->cfg.max_entities, 1ull);
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(ctx->d_layers, ones.data(), ones.size() * 8, cudaMemcpyHostToDevice));
+        ctx->have_layers = true;
+    }
+    ctx->have_layers_ext = true;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_set_view_render_layers_ext(b200vis_ctx *ctx, uint32_t view, const uint64_t blocks[3]) {
+    if (!ctx || view >= (uint32_t)kMaxViews) return B200VIS_ERR_INVALID_ARG;
+    for (int k = 0; k < 3; ++k) ctx->view_layers_ext[view][k] = blocks ? blocks[k] : 0ull;
+    return B200VIS_OK;
+}
 extern "C" int32_t b200vis_upload_view_visibility(b200vis_ctx *ctx, uint32_t first, uint32_t count, const uint8_t *vv) {
     CHECK_CTX();
     if (count && !vv) return fail(ctx, B200VIS_ERR_INVALID_ARG, "upload_view_visibility: null");
@@ -891,6 +916,7 @@ extern "C" int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, const
     CU(cudaMemcpyAsync(ctx->d_light_row, light_row, (size_t)n_lights * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_light_range, range, (size_t)n_lights * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (layer_mask) CU(cudaMemcpyAsync(ctx->d_light_layers, layer_mask, (size_t)n_lights * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_light_row.assign(light_row, light_row + n_lights); ctx->h_light_range.assign(range, range + n_lights);
     ctx->lights.n = n_lights; ctx->lights.row = ctx->d_light_row; ctx->lights.range = ctx->d_light_range;
     ctx->lights.layers = layer_mask ? ctx->d_light_layers : nullptr;
     ctx->lights_tag_dirty = true;
@@ -1186,9 +1212,11 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         fc = ctx->d_consts;
     }
     cl.blob = reinterpret_cast<const float *>(fc);
-    const CullViews cvw = make_cull_views(active_consts(ctx));
+    CullViews cvw = make_cull_views(active_consts(ctx));
     Rows R = ctx->rows;
     R.layers = ctx->have_layers ? ctx->d_layers : nullptr;
+    R.layers_ext = ctx->have_layers_ext ? ctx->d_layers_ext : nullptr;
+    if (ctx->have_layers_ext) memcpy(cvw.layers_ext, ctx->view_layers_ext, sizeof cvw.layers_ext);
     R.range = ctx->have_range ? ctx->d_range : nullptr;
     R.range_se = ctx->d_range_se; R.range_use_aabb = ctx->d_range_ua;
     R.range_views = ctx->d_range_views; R.n_range_views = ctx->n_range_views;
@@ -1341,6 +1369,7 @@ extern "C" int32_t b200vis_download_frame_stats(b200vis_ctx *ctx, b200vis_frame_
     }
     const uint32_t lp = (ctx->frame + 2u) % 3u;   // slot the last CULL frame (frame - 1) accumulated into
     out->gt_changed_count = s.changed[lp][0]; out->vv_changed_count = s.changed[lp][1]; out->frame = ctx->frame;
+    ctx->last_gt_changed = out->gt_changed_count;
     return B200VIS_OK;
 }
 
@@ -1434,21 +1463,15 @@ extern "C" int32_t b200vis_upload_shadow_casters(b200vis_ctx *ctx, uint32_t firs
     CU(cudaMemcpyAsync(ctx->d_caster + first, caster, count, cudaMemcpyHostToDevice, ctx->stream));
     return B200VIS_OK;
 }
-extern "C" int32_t b200vis_set_shadow_lights(b200vis_ctx *ctx, uint32_t n_lights, const uint32_t *light_ordinals, const float *frusta,
-                                             const uint64_t *layer_mask, int32_t lod_origin_range_index, uint32_t list_capacity) {
-    CHECK_CTX_JOIN();
-    if (n_lights && (!light_ordinals || !frusta)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_shadow_lights: null");
-    if (!ctx->d_caster) return fail(ctx, B200VIS_ERR_NOT_READY, "set_shadow_lights: upload the shadow-caster column first");
-    for (uint32_t i = 0; i < n_lights; ++i)
-        if (light_ordinals[i] >= ctx->lights.n) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_shadow_lights: light ordinal %u >= %u lights", light_ordinals[i], ctx->lights.n);
+static int32_t install_shadow_items(b200vis_ctx *ctx, uint32_t n_items, uint32_t list_capacity) {
     if (!list_capacity) list_capacity = std::max<uint32_t>(ctx->cfg.max_entities, 1);
-    if (!ctx->diff_on) return fail(ctx, B200VIS_ERR_NOT_READY, "set_shadow_lights: the visible-set bookkeeping was switched off after upload_shadow_casters");
+    if (!ctx->diff_on) return fail(ctx, B200VIS_ERR_NOT_READY, "set_shadow_items: the visible-set bookkeeping was switched off after upload_shadow_casters");
     CU(cudaStreamSynchronize(ctx->stream));
-    if (n_lights > ctx->shadow_cap_lights || list_capacity > ctx->shadow_cap_list) {
+    if (n_items > ctx->shadow_cap_lights || list_capacity > ctx->shadow_cap_list) {
         void *old[] = {ctx->d_shadow_lights, ctx->shadow.mask, ctx->shadow.chunk_count, ctx->shadow.lists, ctx->shadow.count, ctx->shadow.active};
         for (void *p : old) if (p) cudaFree(p);
         ctx->d_shadow_lights = nullptr; ctx->shadow = ShadowBufs{};
-        const size_t nl = std::max<uint32_t>(n_lights, ctx->shadow_cap_lights), lc = std::max<uint32_t>(list_capacity, ctx->shadow_cap_list);
+        const size_t nl = std::max<uint32_t>(n_items, ctx->shadow_cap_lights), lc = std::max<uint32_t>(list_capacity, ctx->shadow_cap_list);
         CU(dalloc(&ctx->d_shadow_lights, nl));
         CU(dalloc(&ctx->shadow.mask, nl * 6 * ctx->vis.words_stride));
         CU(dalloc(&ctx->shadow.chunk_count, nl * 6 * ctx->vis.chunks_stride));
@@ -1457,17 +1480,46 @@ extern "C" int32_t b200vis_set_shadow_lights(b200vis_ctx *ctx, uint32_t n_lights
         CU(dalloc(&ctx->shadow.active, nl));
         ctx->shadow_cap_lights = (uint32_t)nl; ctx->shadow_cap_list = (uint32_t)lc;
     }
+    if (n_items) CU(cudaMemcpy(ctx->d_shadow_lights, ctx->h_shadow.data(), n_items * sizeof(ShadowLight), cudaMemcpyHostToDevice));
+    ctx->shadow.n_lights = n_items; ctx->shadow.lights = ctx->d_shadow_lights; ctx->shadow.caster = ctx->d_caster;
+    ctx->shadow.list_cap = ctx->shadow_cap_list;
+    return B200VIS_OK;
+}
+extern "C" int32_t b200vis_set_shadow_lights(b200vis_ctx *ctx, uint32_t n_lights, const uint32_t *light_ordinals, const float *frusta,
+                                             const uint64_t *layer_mask, int32_t lod_origin_range_index, uint32_t list_capacity) {
+    CHECK_CTX_JOIN();
+    if (n_lights && (!light_ordinals || !frusta)) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_shadow_lights: null");
+    if (!ctx->d_caster) return fail(ctx, B200VIS_ERR_NOT_READY, "set_shadow_lights: upload the shadow-caster column first");
+    for (uint32_t i = 0; i < n_lights; ++i)
+        if (light_ordinals[i] >= ctx->lights.n) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_shadow_lights: light ordinal %u >= %u lights", light_ordinals[i], ctx->lights.n);
     ctx->h_shadow.resize(n_lights);
     for (uint32_t i = 0; i < n_lights; ++i) {
         ShadowLight &s = ctx->h_shadow[i];
+        memset(&s, 0, sizeof s);
         memcpy(s.planes, frusta + (size_t)i * 144, sizeof s.planes);
-        s.layers = layer_mask ? layer_mask[i] : 1ull; s.light = light_ordinals[i]; s.pad = 0;
+        s.layers = layer_mask ? layer_mask[i] : 1ull;
+        s.row = ctx->h_light_row[light_ordinals[i]]; s.range = ctx->h_light_range[light_ordinals[i]]; s.kind = 0;
+        s.range_index = (lod_origin_range_index >= 0 && lod_origin_range_index < 32) ? lod_origin_range_index : -1;
     }
-    if (n_lights) CU(cudaMemcpy(ctx->d_shadow_lights, ctx->h_shadow.data(), n_lights * sizeof(ShadowLight), cudaMemcpyHostToDevice));
-    ctx->shadow.n_lights = n_lights; ctx->shadow.lights = ctx->d_shadow_lights; ctx->shadow.caster = ctx->d_caster;
-    ctx->shadow.lod_origin = (lod_origin_range_index >= 0 && lod_origin_range_index < 32) ? lod_origin_range_index : -1;
-    ctx->shadow.list_cap = ctx->shadow_cap_list;
-    return B200VIS_OK;
+    return install_shadow_items(ctx, n_lights, list_capacity);
+}
+extern "C" int32_t b200vis_set_shadow_items(b200vis_ctx *ctx, uint32_t n_items, const b200vis_shadow_item *items, uint32_t list_capacity) {
+    CHECK_CTX_JOIN();
+    if (n_items && !items) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_shadow_items: null");
+    if (!ctx->d_caster) return fail(ctx, B200VIS_ERR_NOT_READY, "set_shadow_items: upload the shadow-caster column first");
+    ctx->h_shadow.resize(n_items);
+    for (uint32_t i = 0; i < n_items; ++i) {
+        const b200vis_shadow_item &it = items[i];
+        if (it.kind > B200VIS_SHADOW_DIRECTIONAL_CASCADE) return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_shadow_items: item %u has kind %u", i, it.kind);
+        if (it.kind != B200VIS_SHADOW_DIRECTIONAL_CASCADE && it.light_row >= ctx->n)
+            return fail(ctx, B200VIS_ERR_INVALID_ARG, "set_shadow_items: item %u: light row %u out of range", i, it.light_row);
+        ShadowLight &s = ctx->h_shadow[i];
+        memset(&s, 0, sizeof s);
+        memcpy(s.planes, it.frusta, sizeof s.planes);
+        s.layers = it.layer_mask; s.row = it.kind == B200VIS_SHADOW_DIRECTIONAL_CASCADE ? 0u : it.light_row; s.range = it.range;
+        s.kind = it.kind; s.range_index = (it.range_view_index >= 0 && it.range_view_index < 32) ? it.range_view_index : -1;
+    }
+    return install_shadow_items(ctx, n_items, list_capacity);
 }
 extern "C" int32_t b200vis_run_shadow_culling(b200vis_ctx *ctx) {
     CHECK_CTX_JOIN();   // reads what the frame's CULL stage (incl. its tail on the side stream) left behind
@@ -1483,7 +1535,7 @@ extern "C" int32_t b200vis_run_shadow_culling(b200vis_ctx *ctx) {
     ShadowBufs sb = ctx->shadow;
     sb.has_ranges = ctx->have_range ? 1u : 0u;
     CU(cudaMemsetAsync(sb.chunk_count, 0, (size_t)sb.n_lights * 6 * ctx->vis.chunks_stride * 4, st));
-    launch_shadow_cull(st, R, sb, ctx->lights, ctx->diff.prev, active_consts(ctx).n_views, ctx->vis.n_words, ctx->vis.n_chunks,
+    launch_shadow_cull(st, R, sb, ctx->diff.prev, active_consts(ctx).n_views, ctx->vis.n_words, ctx->vis.n_chunks,
                        ctx->vis.words_stride, ctx->vis.chunks_stride, ctx->d_stats, (ctx->frame + 2u) % 3u);
     CU(cudaGetLastError());
     return B200VIS_OK;
@@ -1741,17 +1793,35 @@ extern "C" int32_t b200vis_set_column_sinks(b200vis_ctx *ctx, const b200vis_colu
     if ((rc = map_host(ctx, sinks->view_visibility, N, &d))) return rc;
     ctx->col_vv_d = reinterpret_cast<uint8_t *>(d);
     if ((rc = map_host(ctx, sinks->vv_changed_bits, W * 4, &ctx->col_vv_bits_d))) return rc;
+    if (!ctx->d_vv_shadow) CU(dalloc(&ctx->d_vv_shadow, N + 32));
+    CU(cudaMemset(ctx->d_vv_shadow, 0xFF, N + 32));      // the host column's contents are unknown: the first write-back sends all
     ctx->colsink = *sinks;
     ctx->have_colsink = true;
     return B200VIS_OK;
 }
-extern "C" int32_t b200vis_writeback_columns(b200vis_ctx *ctx) {
+extern "C" int32_t b200vis_writeback_columns_ex(b200vis_ctx *ctx, uint32_t which);
+extern "C" int32_t b200vis_writeback_columns(b200vis_ctx *ctx) { return b200vis_writeback_columns_ex(ctx, B200VIS_WB_GLOBAL_TRANSFORM | B200VIS_WB_VIEW_VISIBILITY); }
+extern "C" int32_t b200vis_writeback_columns_ex(b200vis_ctx *ctx, uint32_t which) {
     CHECK_CTX();
     if (!ctx->have_colsink) return fail(ctx, B200VIS_ERR_NOT_READY, "writeback_columns: call b200vis_set_column_sinks first");
     // on the main stream, right behind the tile pass (and the shadow-culling stage, if the caller ran it): the tail of the
     // frame (list expansion, clusters) runs beside it on the side stream, the next frame's tile pass behind it
-    launch_writeback_columns(ctx->stream, ctx->rows, ctx->col_gt_d, ctx->colsink.gt_stride_floats, ctx->col_gt_bits_d, ctx->col_vv_d,
-                             ctx->col_vv_bits_d);
+    const bool wgt = which & B200VIS_WB_GLOBAL_TRANSFORM, wvv = which & B200VIS_WB_VIEW_VISIBILITY;
+    float *gt_sink = wgt ? ctx->col_gt_d : nullptr;
+    static int dense_env = -1;
+    if (dense_env < 0) { const char *e = getenv("B200VIS_WRITEBACK_DENSE"); dense_env = e ? atoi(e) : 1; }
+    if (gt_sink && dense_env && (uint64_t)ctx->last_gt_changed * 2u >= ctx->n && ctx->n) {
+        // most rows changed last frame (and will again): repack the whole column on the device (HBM speed) and let the copy
+        // engine move it -- unchanged rows are rewritten with the bytes the host already holds.  Sparse frames take the
+        // scatter kernel below instead (it touches only the changed rows).
+        const uint32_t stride = ctx->colsink.gt_stride_floats;
+        if (!ctx->d_gt_aos) CU(dalloc(&ctx->d_gt_aos, (size_t)ctx->cfg.max_entities * 16));
+        launch_pack_gt(ctx->stream, ctx->rows, 0, ctx->n, ctx->d_gt_aos, stride);
+        CU(cudaMemcpyAsync(ctx->colsink.global_transforms, ctx->d_gt_aos, (size_t)ctx->n * stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        gt_sink = nullptr;
+    }
+    launch_writeback_columns(ctx->stream, ctx->rows, gt_sink, ctx->colsink.gt_stride_floats, wgt ? ctx->col_gt_bits_d : nullptr,
+                             wvv ? ctx->col_vv_d : nullptr, wvv ? ctx->col_vv_bits_d : nullptr, ctx->d_vv_shadow);
     CU(cudaGetLastError());
     return B200VIS_OK;
 }
@@ -1828,6 +1898,7 @@ extern "C" int32_t b200vis_step(b200vis_ctx *ctx, uint32_t n_changed, const uint
     if (ctx->have_sink) { CU(cudaStreamSynchronize(ctx->stream)); st = ctx->sink.stats; }
     else { if ((rc = b200vis_download_frame_stats(ctx, &local))) return rc; st = &local; }
     lap(5);
+    ctx->last_gt_changed = st->gt_changed_count;
     if (clusters)
         for (uint32_t v = 0; v < n_cameras; ++v) {   // Clusters::last_frame_* (assign.rs:810-811)
             b200vis_cluster_feedback &fb = ctx->auto_fb[v];

@@ -63,6 +63,7 @@ struct Rows {
     const uint32_t *wtopo;   // T_* | depth | parent slots, for k_tile_warp
     const uint32_t *parent;  // global parent row (read only for T_EXT_PARENT rows)
     const uint64_t *layers;  // RenderLayers first block, or nullptr
+    const uint64_t *layers_ext;  // [n][3] RenderLayers blocks 1..3 (layers 64..255), or nullptr (render_layers.rs:20-23)
     uint32_t *range;         // VisibleEntityRanges bitmask, or nullptr
     // VisibilityRange columns; when resident the cull phase computes `range` itself
     const float2 *range_se;      // (start_margin.start, end_margin.end), or nullptr
@@ -93,6 +94,7 @@ struct CullViews {
     uint32_t on[kMaxViews];            // bit0 camera.is_active, bit1 NoCpuCulling camera, bit2 default layer in the view's mask
     int32_t range_index[kMaxViews];
     unsigned long long layers[kMaxViews];
+    unsigned long long layers_ext[kMaxViews][3];   // the views' RenderLayers blocks 1..3
     float4 planes[kMaxViews][5];       // L,R,T,B,Near (the far plane is never used by culling)
 };
 
@@ -178,17 +180,19 @@ struct ClusterBufs {
 };
 
 // check_point_light_mesh_visibility (bevy_light/src/lib.rs:517-668) for the shadow-casting point lights
-struct ShadowLight {
-    float4 planes[6][6];     // CubemapFrusta: face, half space (normal, d)
+struct ShadowLight {         // one shadow item: a point light (six cubemap faces), a spot light or one directional-light cascade (frustum 0)
+    float4 planes[6][6];     // frustum (face), half space (normal, d)
     unsigned long long layers;
-    uint32_t light;          // ordinal in the b200vis_set_lights arrays
-    uint32_t pad;
+    uint32_t row;            // point / spot: the light's row (range sphere centre = its GlobalTransform translation)
+    float range;
+    uint32_t kind;           // 0 point, 1 spot, 2 directional cascade (no range sphere, near plane not tested, always active)
+    int32_t range_index;     // bit of the VisibleEntityRanges masks that gates ranged rows: shadow LOD origin / the cascade's view; -1 none
+    uint32_t pad[2];
 };
 struct ShadowBufs {
     uint32_t n_lights;       // shadow lights this frame
     const ShadowLight *lights;
     const uint8_t *caster;   // per row: in visible_entity_query (Mesh3d, no NotShadowCaster, no DirectionalLight)
-    int32_t lod_origin;      // bit of the shadow LOD origin in the range masks, -1 = none
     uint32_t has_ranges;     // a VisibleEntityRanges resource exists
     uint32_t *mask;          // [n_lights * 6][words_stride], bit = rank; zeroed by the expand kernel as it reads
     uint32_t *chunk_count;   // [n_lights * 6][chunks_stride]

@@ -56,6 +56,13 @@ __device__ __forceinline__ float plane_dot_point(float4 n, float px, float py, f
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
     return (ax * bx + ay * by) + az * bz;
 }
+// RenderLayers::intersects (render_layers.rs:121-135): any block-wise AND over the common prefix; block 0 is `elayers`
+__device__ __forceinline__ bool layers_intersect(const Rows &R, const CullViews &cvw, uint32_t row, uint32_t v, unsigned long long elayers) {
+    if (cvw.layers[v] & elayers) return true;
+    if (R.layers_ext == nullptr) return false;
+    const uint64_t *e = R.layers_ext + (size_t)row * 3;
+    return ((cvw.layers_ext[v][0] & e[0]) | (cvw.layers_ext[v][1] & e[1]) | (cvw.layers_ext[v][2] & e[2])) != 0ull;
+}
 __device__ __forceinline__ float gl_min(float a, float b) { return a < b ? a : b; }   // glam / SSE min,max
 __device__ __forceinline__ float gl_max(float a, float b) { return a > b ? a : b; }
 
@@ -250,7 +257,7 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const __grid_constant__
             if (SIMPLE && !(von & 4u)) continue;                       // bit2: the view includes the default layer
             bool vis = base;
             if (!SIMPLE) {
-                vis = vis && (cvw.layers[v] & elayers) != 0ull;
+                vis = vis && layers_intersect(R, cvw, row, v, elayers);
                 if ((f & F_RANGE) && R.range != nullptr) {
                     const int32_t ri = cvw.range_index[v];
                     vis = vis && ri >= 0 && ((erange >> ri) & 1u);
@@ -566,7 +573,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
                 if (SIMPLE && !(von & 4u)) continue;   // bit2: the view includes the default layer
                 bool vis = base;
                 if (!SIMPLE) {
-                    vis = vis && (cvw.layers[v] & elayers) != 0ull;
+                    vis = vis && layers_intersect(R, cvw, row, v, elayers);
                     if ((f & F_RANGE) && R.range != nullptr) {
                         const int32_t ri = cvw.range_index[v];
                         vis = vis && ri >= 0 && ((erange >> ri) & 1u);
@@ -965,7 +972,7 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                     if (SIMPLE && !(von & 4u)) continue;   // bit2: the view includes the default layer
                     bool vis = base;
                     if (!SIMPLE) {
-                        vis = vis && (cvw.layers[v] & elayers) != 0ull;
+                        vis = vis && layers_intersect(R, cvw, row, v, elayers);
                         if ((f & F_RANGE) && R.range != nullptr) {
                             const int32_t ri = cvw.range_index[v];
                             vis = vis && ri >= 0 && ((erange >> ri) & 1u);
@@ -1288,7 +1295,7 @@ k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restric
                     if (SIMPLE && !(von & 4u)) continue;                       // bit2: the view includes the default layer
                     bool vis = base_vis;
                     if (!SIMPLE) {
-                        vis = vis && (cvw.layers[v] & elayers) != 0ull;
+                        vis = vis && layers_intersect(R, cvw, row, v, elayers);
                         if ((f & F_RANGE) && R.range != nullptr) {
                             const int32_t ri = cvw.range_index[v];
                             vis = vis && ri >= 0 && ((erange >> ri) & 1u);
@@ -1434,7 +1441,7 @@ k_cull(Rows R, const __grid_constant__ CullViews cvw, VisibleBufs vb, DevStats *
         if (SIMPLE && !(von & 4u)) { continue; }
         bool vis = base;
         if (!SIMPLE) {
-            vis = vis && (cvw.layers[v] & elayers) != 0ull;
+            vis = vis && layers_intersect(R, cvw, row, v, elayers);
             if ((f & F_RANGE) && R.range != nullptr) {
                 const int32_t ri = cvw.range_index[v];
                 vis = vis && ri >= 0 && ((erange >> ri) & 1u);
@@ -2196,44 +2203,64 @@ __global__ void k_publish_clusters(const FrameConsts *__restrict__ fc, const uin
 }
 
 // ---- column write-back: the frame's GlobalTransform / ViewVisibility results into the caller's ECS columns (mapped host
-// memory, PCIe posted writes).  One warp per 32 rows: the changed rows' matrices are transposed through shared memory so
-// that every store instruction covers 512 contiguous bytes of the host column (whole PCIe write bursts), the change flags
-// travel as bit sets (one word per warp), the ViewVisibility bytes as they are.
+// memory, PCIe posted writes).  One warp per 128 rows: the state bytes are read four at a time, the change flags travel as
+// bit sets, a ViewVisibility word crosses PCIe only when one of its four bytes differs from what the host already holds
+// (device-side shadow), and the changed rows' matrices are transposed through shared memory so that every store
+// instruction covers up to 512 contiguous bytes of the host column (whole PCIe write bursts).
 template <int STRIDE>
 __global__ void __launch_bounds__(256)
 k_writeback_columns(Rows R, float *__restrict__ host_gt, uint32_t *__restrict__ host_gt_bits, uint8_t *__restrict__ host_vv,
-                    uint32_t *__restrict__ host_vv_bits) {
+                    uint32_t *__restrict__ host_vv_bits, uint8_t *__restrict__ vv_shadow) {
     __shared__ float4 s_t[8][32 * (STRIDE / 4)];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t n_groups = (R.n + 31u) / 32u;
+    const uint32_t n_groups = (R.n + 127u) / 128u, n_words = (R.n + 31u) / 32u;
     for (uint32_t grp = blockIdx.x * 8u + warp; grp < n_groups; grp += gridDim.x * 8u) {
-        const uint32_t row = grp * 32u + lane;
-        const bool active = row < R.n;
-        const uint32_t st = active ? R.state[row] : 0u;
-        const uint32_t gbits = __ballot_sync(0xFFFFFFFFu, st & S_GT_CHANGED), vbits = __ballot_sync(0xFFFFFFFFu, st & S_VV_CHANGED);
-        if (lane == 0) {
-            if (host_gt_bits != nullptr) host_gt_bits[grp] = gbits;
-            if (host_vv_bits != nullptr) host_vv_bits[grp] = vbits;
+        const uint32_t r4 = grp * 128u + lane * 4u;          // this lane's four rows (the state column is padded past n)
+        uint32_t st4 = (r4 < R.n) ? *reinterpret_cast<const uint32_t *>(R.state + r4) : 0u;
+        if (r4 + 3u >= R.n) st4 &= (r4 >= R.n) ? 0u : (0xFFFFFFFFu >> (8u * (3u - (R.n - 1u - r4))));   // bytes past the last row
+        if (host_vv != nullptr && r4 < R.n) {
+            const uint32_t vv4 = st4 & 0x03030303u;
+            uint32_t *sh = reinterpret_cast<uint32_t *>(vv_shadow + r4);
+            if (*sh != vv4) {
+                *sh = vv4;
+                if (r4 + 3u < R.n && (reinterpret_cast<uintptr_t>(host_vv) & 3u) == 0u) *reinterpret_cast<uint32_t *>(host_vv + r4) = vv4;
+                else for (uint32_t j = 0; j < 4u && r4 + j < R.n; ++j) host_vv[r4 + j] = (uint8_t)(vv4 >> (8u * j));   // tail / unaligned column
+            }
         }
-        if (host_vv != nullptr && active) host_vv[row] = (uint8_t)(st & S_VV);
-        if (host_gt != nullptr && gbits) {
-            constexpr int Q = STRIDE / 4;                 // float4 per row in the host layout
-            if (st & S_GT_CHANGED) {
+        // change bits: bit j of the lane's nibble = row r4 + j; eight lanes make one 32-row word
+        uint32_t g = ((st4 >> 4) & 1u) | ((st4 >> 11) & 2u) | ((st4 >> 18) & 4u) | ((st4 >> 25) & 8u);
+        uint32_t v = ((st4 >> 5) & 1u) | ((st4 >> 12) & 2u) | ((st4 >> 19) & 4u) | ((st4 >> 26) & 8u);
+        g <<= 4u * (lane & 7u); v <<= 4u * (lane & 7u);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { g |= __shfl_xor_sync(0xFFFFFFFFu, g, o); v |= __shfl_xor_sync(0xFFFFFFFFu, v, o); }
+        const uint32_t w = grp * 4u + (lane >> 3);
+        if ((lane & 7u) == 0u && w < n_words) {
+            if (host_gt_bits != nullptr) host_gt_bits[w] = g;
+            if (host_vv_bits != nullptr) host_vv_bits[w] = v;
+        }
+        if (host_gt == nullptr) continue;
+        constexpr int Q = STRIDE / 4;                         // float4 per row in the host layout
+#pragma unroll 1
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t gbits = __shfl_sync(0xFFFFFFFFu, g, j * 8u);
+            if (!gbits) continue;
+            const uint32_t row = grp * 128u + j * 32u + lane;
+            if ((gbits >> lane) & 1u) {
                 const float4 a = R.gt0[row], b = R.gt1[row], c = R.gt2[row];
                 float4 *o = &s_t[warp][lane * Q];
-                if (STRIDE == 16) {                       // glam Affine3A: x_axis, y_axis, z_axis, translation as Vec3A
+                if (STRIDE == 16) {                           // glam Affine3A: x_axis, y_axis, z_axis, translation as Vec3A
                     o[0] = make_float4(a.x, b.x, c.x, 0.0f); o[1] = make_float4(a.y, b.y, c.y, 0.0f);
                     o[2] = make_float4(a.z, b.z, c.z, 0.0f); o[3] = make_float4(a.w, b.w, c.w, 0.0f);
-                } else {                                  // packed X.xyz Y.xyz Z.xyz T.xyz
+                } else {                                      // packed X.xyz Y.xyz Z.xyz T.xyz
                     o[0] = make_float4(a.x, b.x, c.x, a.y); o[1] = make_float4(b.y, c.y, a.z, b.z);
                     o[2] = make_float4(c.z, a.w, b.w, c.w);
                 }
             }
             __syncwarp();
-            float4 *dst = reinterpret_cast<float4 *>(host_gt) + (size_t)grp * 32u * Q;
+            float4 *dst = reinterpret_cast<float4 *>(host_gt) + ((size_t)grp * 128u + j * 32u) * Q;
 #pragma unroll
             for (int k = 0; k < Q; ++k) {
-                const uint32_t idx = k * 32u + lane;      // consecutive lanes -> consecutive 16-byte pieces of the column
+                const uint32_t idx = k * 32u + lane;          // consecutive lanes -> consecutive 16-byte pieces of the column
                 if ((gbits >> (idx / Q)) & 1u) dst[idx] = s_t[warp][idx];
             }
             __syncwarp();
@@ -2263,26 +2290,28 @@ __global__ void k_cluster_clear(const FrameConsts *__restrict__ fc, ClusterBufs 
 // k_expand_shadow turns into the sorted CubemapVisibleEntities lists; a row seen by any light gets
 // ViewVisibility::set_visible (visibility/mod.rs:292-306) applied on top of what the camera cull left.
 // ------------------------------------------------------------------------------------------
-constexpr int kShadowChunk = 4;   // lights staged per round (4 x 592 B)
-// a light takes part only if it is in some view's VisibleEntities (lib.rs:561-563): its rank bit in the per-view sets
-__global__ void k_shadow_select(ShadowBufs sb, Lights L, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ view_sets,
+constexpr int kShadowChunk = 4;   // items staged per round (4 x 608 B)
+// a point / spot light takes part only if it is in some view's VisibleEntities (lib.rs:561-563): its rank bit in the per-view
+// sets; directional cascades are pre-filtered by the caller (shadow_maps_enabled && visible, lib.rs:395-399)
+__global__ void k_shadow_select(ShadowBufs sb, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ view_sets,
                                 uint32_t words_stride, uint32_t n_views) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= sb.n_lights) return;
-    const uint32_t row = L.row[sb.lights[s].light], rk = rank ? rank[row] : row;
+    if (sb.lights[s].kind == 2u) { sb.active[s] = 1; return; }
+    const uint32_t row = sb.lights[s].row, rk = rank ? rank[row] : row;
     uint32_t on = 0;
     for (uint32_t v = 0; v < n_views; ++v) on |= (view_sets[(size_t)v * words_stride + (rk >> 5)] >> (rk & 31u)) & 1u;
     sb.active[s] = on;
 }
 __global__ void __launch_bounds__(256)
-k_shadow_cull(Rows R, ShadowBufs sb, Lights L, uint32_t words_stride, uint32_t chunks_stride, DevStats *__restrict__ stats,
+k_shadow_cull(Rows R, ShadowBufs sb, uint32_t words_stride, uint32_t chunks_stride, DevStats *__restrict__ stats,
               uint32_t changed_slot) {
     __shared__ ShadowLight s_light[kShadowChunk];
     __shared__ float4 s_sphere[kShadowChunk];
     __shared__ uint32_t s_on[kShadowChunk];
     const uint32_t row = blockIdx.x * 256u + threadIdx.x, lane = threadIdx.x & 31u;
     const bool active = row < R.n;
-    uint32_t f = 0, st8 = 0;
+    uint32_t f = 0, st8 = 0, erange = 0;
     Aff g; g.r0 = g.r1 = g.r2 = make_float4(0, 0, 0, 0);
     float4 bA = g.r0; float2 bB = make_float2(0, 0);
     bool eligible = false;
@@ -2291,15 +2320,15 @@ k_shadow_cull(Rows R, ShadowBufs sb, Lights L, uint32_t words_stride, uint32_t c
     if (active) {
         f = R.flags[row]; st8 = R.state[row];
         eligible = sb.caster[row] && !(f & F_NO_CPU_CULL) && (f & F_INHERITED);
-        if (eligible && (f & F_RANGE) && sb.has_ranges)   // visible range gate against the shadow LOD origin (lib.rs:607-616)
-            eligible = sb.lod_origin >= 0 && R.range != nullptr && ((R.range[row] >> sb.lod_origin) & 1u);
         if (eligible) {
             g.r0 = R.gt0[row]; g.r1 = R.gt1[row]; g.r2 = R.gt2[row];
             bA = R.bndA[row]; bB = R.bndB[row];
             if (R.layers != nullptr) elayers = R.layers[row];
+            if ((f & F_RANGE) && sb.has_ranges && R.range != nullptr) erange = R.range[row];
         }
         if (R.rank != nullptr) rnk = R.rank[row];
     }
+    const bool ranged = (f & F_RANGE) && sb.has_ranges;   // gated on one bit of the VisibleEntityRanges mask (lib.rs:607-616, 432-441)
     const bool has_aabb = f & F_AABB, no_fc = f & F_NO_FRUSTUM;
     const float hx = bA.w, hy = bB.x, hz = bB.y;
     // transform_point3a(aabb.center)
@@ -2313,20 +2342,22 @@ k_shadow_cull(Rows R, ShadowBufs sb, Lights L, uint32_t words_stride, uint32_t c
         for (uint32_t i = threadIdx.x; i < nl * (sizeof(ShadowLight) / 16); i += 256u)
             reinterpret_cast<float4 *>(s_light)[i] = reinterpret_cast<const float4 *>(sb.lights + s0)[i];
         if (threadIdx.x < nl) {
-            const uint32_t ord = sb.lights[s0 + threadIdx.x].light;
+            const ShadowLight &sl = sb.lights[s0 + threadIdx.x];
             s_on[threadIdx.x] = sb.active[s0 + threadIdx.x];
-            const uint32_t lrow = L.row[ord];   // light_sphere = (GlobalTransform translation, range) (lib.rs:575-578)
-            s_sphere[threadIdx.x] = make_float4(R.gt0[lrow].w, R.gt1[lrow].w, R.gt2[lrow].w, L.range[ord]);
+            // light_sphere = (GlobalTransform translation, range) (lib.rs:575-578, 680-683)
+            s_sphere[threadIdx.x] = sl.kind < 2u ? make_float4(R.gt0[sl.row].w, R.gt1[sl.row].w, R.gt2[sl.row].w, sl.range) : make_float4(0, 0, 0, 0);
         }
         __syncthreads();
         for (uint32_t i = 0; i < nl; ++i) {
             if (!s_on[i]) continue;                                  // warp-uniform
             const ShadowLight &sl = s_light[i];
+            const uint32_t kind = sl.kind, n_faces = kind == 0u ? 6u : 1u;
             bool in = eligible && (sl.layers & elayers) != 0ull;
-            uint32_t faces = 0x3Fu;                                  // no Aabb: pushed to all six faces (lib.rs:639-645)
-            if (in && has_aabb) {
-                if (!no_fc) {
-                    // Sphere::intersects_obb: d_sq <= radius * d + relative_radius(v)
+            if (in && ranged) in = sl.range_index >= 0 && sl.range_index < 32 && ((erange >> sl.range_index) & 1u);
+            uint32_t faces = kind == 0u ? 0x3Fu : 1u;                // no Aabb: pushed to every list of the item (lib.rs:639-645)
+            if (in && has_aabb && !no_fc) {
+                if (kind < 2u) {
+                    // Sphere::intersects_obb: d_sq <= radius * d + relative_radius(v) (primitives.rs:219-226)
                     const float4 sp = s_sphere[i];
                     const float vx = cx - sp.x, vy = cy - sp.y, vz = cz - sp.z;
                     const float d_sq = (vx * vx + vy * vy) + vz * vz, d = sqrtf(d_sq);
@@ -2335,28 +2366,29 @@ k_shadow_cull(Rows R, ShadowBufs sb, Lights L, uint32_t words_stride, uint32_t c
                     const float az = fabsf(dot3(vx, vy, vz, g.r0.z, g.r1.z, g.r2.z));
                     const float rr = (ax * hx + ay * hy) + az * hz;
                     in = d_sq <= sp.w * d + rr;
-                    if (in) {
-                        faces = 0;
-                        for (uint32_t fc = 0; fc < 6; ++fc) {
-                            bool inside = true;
+                }
+                if (in) {
+                    faces = 0;
+                    for (uint32_t fc = 0; fc < n_faces; ++fc) {
+                        bool inside = true;
 #pragma unroll
-                            for (int k = 0; k < 6; ++k) {   // intersect_near = intersect_far = true
-                                const float4 n = sl.planes[fc][k];
-                                const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
-                                const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
-                                const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
-                                const float prr = (dx * hx + dy * hy) + dz * hz;
-                                inside = inside && !(plane_dot_point(n, cx, cy, cz) + prr <= 0.0f);
-                            }
-                            faces |= inside ? (1u << fc) : 0u;
+                        for (int k = 0; k < 6; ++k) {   // cubemap faces and spot lights test near and far; cascades skip the near plane (lib.rs:455-458)
+                            if (k == 4 && kind == 2u) continue;
+                            const float4 n = sl.planes[fc][k];
+                            const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+                            const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+                            const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+                            const float prr = (dx * hx + dy * hy) + dz * hz;
+                            inside = inside && !(plane_dot_point(n, cx, cy, cz) + prr <= 0.0f);
                         }
+                        faces |= inside ? (1u << fc) : 0u;
                     }
                 }
             }
             if (!in) faces = 0;
             any |= faces != 0u;
             if (__any_sync(0xFFFFFFFFu, faces != 0u)) {
-                for (uint32_t fc = 0; fc < 6; ++fc) {
+                for (uint32_t fc = 0; fc < n_faces; ++fc) {
                     const uint32_t list = (s0 + i) * 6u + fc;
                     uint32_t *mask = sb.mask + (size_t)list * words_stride;
                     uint32_t *cc = sb.chunk_count + (size_t)list * chunks_stride;
@@ -2663,7 +2695,7 @@ template <int MINB, bool PIPE>
 static void launch_tile_warp_m(cudaStream_t st, const Rows &R, const WarpTile *tiles, const uint8_t *sched, uint32_t n_tiles, const CullViews &cvw,
                                const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity, uint32_t *counter) {
     const bool cull = stages & 2u;
-    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+    const bool simple = R.layers == nullptr && R.layers_ext == nullptr && R.range == nullptr && R.rank == nullptr;
     if (cull) { if (simple) launch_warp<true, true, MINB, PIPE>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter);
                 else launch_warp<true, false, MINB, PIPE>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter); }
     else launch_warp<false, true, MINB, PIPE>(st, R, tiles, sched, n_tiles, cvw, vb, stats, static_opt, parity, counter);
@@ -2769,7 +2801,7 @@ void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *til
                                  const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
     if (n_tiles == 0) return;
     const bool prop = stages & 1u, cull = stages & 2u;
-    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+    const bool simple = R.layers == nullptr && R.layers_ext == nullptr && R.range == nullptr && R.rank == nullptr;
 #define B200VIS_LAUNCH_SMALL(P, C, S) ++g_launches, k_propagate_cull<P, C, S><<<n_tiles, 32, 0, st>>>(R, tiles, cvw, vb, stats, static_opt, parity)
     if (prop && cull) { if (simple) B200VIS_LAUNCH_SMALL(true, true, true); else B200VIS_LAUNCH_SMALL(true, true, false); }
     else if (prop) B200VIS_LAUNCH_SMALL(true, false, true);
@@ -2780,7 +2812,7 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
                            const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
     if (n_tiles == 0) return;
     const bool prop = stages & 1u, cull = stages & 2u;
-    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+    const bool simple = R.layers == nullptr && R.layers_ext == nullptr && R.range == nullptr && R.rank == nullptr;
     if (tile_kernel_choice() == 3 && prop) {       // TMA-staged tiles + a scout warp one tile ahead (default)
         static int per_sm = 0;
         if (!per_sm) { const char *e = getenv("B200VIS_SCOUT_CTAS_PER_SM"); per_sm = (e && atoi(e) == 4) ? 4 : 3; }
@@ -2804,7 +2836,7 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
 }
 void launch_cull(cudaStream_t st, const Rows &R, const CullViews &cvw, const VisibleBufs &vb, DevStats *stats, uint32_t parity) {
     if (!R.n) return;
-    const bool simple = R.layers == nullptr && R.range == nullptr && R.rank == nullptr;
+    const bool simple = R.layers == nullptr && R.layers_ext == nullptr && R.range == nullptr && R.rank == nullptr;
     if (simple) { ++g_launches; k_cull<true><<<cdiv(R.n, 256), 256, 0, st>>>(R, cvw, vb, stats, parity); }
     else { ++g_launches; k_cull<false><<<cdiv(R.n, 256), 256, 0, st>>>(R, cvw, vb, stats, parity); }
 }
@@ -2863,11 +2895,11 @@ void launch_publish_clusters(cudaStream_t st, const FrameConsts *fc, const Clust
     ++g_launches; k_publish_clusters<<<dim3(kMaxClusters / 256 + 1, max_views), 256, 0, st>>>(fc, cb.offsets, cb.indices, cb.index_cap, host_offsets, host_indices,
                                                                                 host_cap, stats, host_stats, changed_slot, frame);
 }
-void launch_shadow_cull(cudaStream_t st, const Rows &R, const ShadowBufs &sb, const Lights &L, const uint32_t *view_sets, uint32_t n_views,
+void launch_shadow_cull(cudaStream_t st, const Rows &R, const ShadowBufs &sb, const uint32_t *view_sets, uint32_t n_views,
                         uint32_t n_words, uint32_t n_chunks, uint32_t words_stride, uint32_t chunks_stride, DevStats *stats, uint32_t changed_slot) {
     if (!sb.n_lights || !R.n) return;
-    ++g_launches; k_shadow_select<<<cdiv(sb.n_lights, 128), 128, 0, st>>>(sb, L, R.rank, view_sets, words_stride, n_views);
-    ++g_launches; k_shadow_cull<<<cdiv(R.n, 256), 256, 0, st>>>(R, sb, L, words_stride, chunks_stride, stats, changed_slot);
+    ++g_launches; k_shadow_select<<<cdiv(sb.n_lights, 128), 128, 0, st>>>(sb, R.rank, view_sets, words_stride, n_views);
+    ++g_launches; k_shadow_cull<<<cdiv(R.n, 256), 256, 0, st>>>(R, sb, words_stride, chunks_stride, stats, changed_slot);
     ++g_launches; k_expand_shadow<<<dim3(n_chunks, sb.n_lights * 6), kChunkWords, 0, st>>>(sb, n_words, n_chunks, words_stride, chunks_stride, R.row_of_rank);
 }
 void launch_pack_cluster_bindings(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, const BindingBufs &bb, uint32_t max_views) {
@@ -2880,11 +2912,11 @@ void launch_snapshot_lights(cudaStream_t st, const Rows &R, const Lights &L, flo
     if (L.n) { ++g_launches; k_snapshot_lights<<<cdiv(L.n, 128), 128, 0, st>>>(R, L, snap); }
 }
 void launch_writeback_columns(cudaStream_t st, const Rows &R, float *host_gt, uint32_t stride, uint32_t *host_gt_bits, uint8_t *host_vv,
-                              uint32_t *host_vv_bits) {
+                              uint32_t *host_vv_bits, uint8_t *vv_shadow) {
     if (!R.n) return;
-    const unsigned groups = cdiv(R.n, 32), grid = groups < 8u * 1184u ? cdiv(groups, 8) : 1184u;
-    if (stride == 16) { ++g_launches; k_writeback_columns<16><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits); }
-    else { ++g_launches; k_writeback_columns<12><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits); }
+    const unsigned groups = cdiv(R.n, 128), grid = groups < 8u * 1184u ? cdiv(groups, 8) : 1184u;
+    if (stride == 16) { ++g_launches; k_writeback_columns<16><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits, vv_shadow); }
+    else { ++g_launches; k_writeback_columns<12><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits, vv_shadow); }
 }
 void launch_slab_push(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, uint32_t *done, uint32_t max_views) {
     ++g_launches; k_slab_push<<<dim3(8, max_views), 256, 0, st>>>(fc, cb, done);

@@ -223,6 +223,12 @@ B200VIS_API int32_t b200vis_upload_bounds(b200vis_ctx *ctx, uint32_t first_row, 
                               const uint8_t *flags, const uint8_t *class_mask, const uint64_t *layer_mask,
                               const uint32_t *range_mask);
 /* ViewVisibility column (bit0 current, bit1 previous; visibility/mod.rs:226-242) */
+/* RenderLayers beyond the first 64 layers: the component is a SmallVec of 64-bit blocks (render_layers.rs:20-23) and
+ * intersects() ORs the block-wise ANDs (:121-135).  Block 0 is the layer_mask of b200vis_upload_bounds / b200vis_view;
+ * blocks[count][3] / blocks[3] are blocks 1..3 (layers 64..255) of the rows / of a view.  Lights keep to block 0
+ * (b200vis_set_lights, shadow items). */
+B200VIS_API int32_t b200vis_upload_render_layers_ext(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const uint64_t *blocks);
+B200VIS_API int32_t b200vis_set_view_render_layers_ext(b200vis_ctx *ctx, uint32_t view, const uint64_t blocks[3]);
 B200VIS_API int32_t b200vis_upload_view_visibility(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const uint8_t *vv);
 
 /* StaticTransformOptimizations resource (systems.rs:87-103); default Enabled (1). */
@@ -352,6 +358,11 @@ typedef struct b200vis_column_sinks {
 } b200vis_column_sinks;
 B200VIS_API int32_t b200vis_set_column_sinks(b200vis_ctx *ctx, const b200vis_column_sinks *sinks);
 B200VIS_API int32_t b200vis_writeback_columns(b200vis_ctx *ctx);
+/* The same for a subset of the columns: a shim that runs the stages from separate systems writes the GlobalTransform
+ * column back right after PROPAGATE and the ViewVisibility column after CULL (and the light-visibility systems). */
+#define B200VIS_WB_GLOBAL_TRANSFORM 0x1u
+#define B200VIS_WB_VIEW_VISIBILITY  0x2u
+B200VIS_API int32_t b200vis_writeback_columns_ex(b200vis_ctx *ctx, uint32_t which);
 #define B200VIS_STEP_WRITEBACK 0x2u  /* b200vis_step: enqueue the column write-back right behind the tile pass */
 
 /* ---- the render world's visible-entity diff ---------------------------------------------
@@ -396,6 +407,27 @@ B200VIS_API int32_t b200vis_set_visible_diff_sink(b200vis_ctx *ctx, uint32_t *ro
 B200VIS_API int32_t b200vis_upload_shadow_casters(b200vis_ctx *ctx, uint32_t first_row, uint32_t count, const uint8_t *caster);
 B200VIS_API int32_t b200vis_set_shadow_lights(b200vis_ctx *ctx, uint32_t n_lights, const uint32_t *light_ordinals, const float *frusta,
                                               const uint64_t *layer_mask, int32_t lod_origin_range_index, uint32_t list_capacity);
+/* The general form: point lights, SPOT lights (the second half of check_point_light_mesh_visibility, lib.rs:670-749: one
+ * Frustum, near and far planes tested, the same range-sphere pre-test) and DIRECTIONAL-light cascades
+ * (check_dir_light_mesh_visibility, lib.rs:342-510: one item per (light, view, cascade) with that cascade's Frustum; the near
+ * plane is not tested, :455-458; there is no range sphere; the caller lists only lights with shadow_maps_enabled that are
+ * visible, :395-399).  A point / spot item names the light's ROW (spot lights are not clustered, so they have no ordinal);
+ * it takes part only while that row is in some view's VisibleEntities.  range_view_index = the bit of the
+ * VisibleEntityRanges masks that gates rows with a VisibilityRange: the shadow LOD origin's for point / spot lights, the
+ * cascade's own view for directional lights; -1 = that view is not in the map (ranged rows are then skipped).
+ * Lists: b200vis_download_shadow_visible(item, face) with face 0 for spot lights and cascades. */
+#define B200VIS_SHADOW_POINT 0u
+#define B200VIS_SHADOW_SPOT 1u
+#define B200VIS_SHADOW_DIRECTIONAL_CASCADE 2u
+typedef struct b200vis_shadow_item {
+    uint32_t kind;
+    uint32_t light_row;          /* point / spot */
+    float    range;              /* point / spot: PointLight::range / SpotLight::range */
+    int32_t  range_view_index;
+    uint64_t layer_mask;         /* the light's RenderLayers (first block; default layer = 1) */
+    float    frusta[6][6][4];    /* point: the six CubemapFrusta faces; spot / cascade: frusta[0] */
+} b200vis_shadow_item;
+B200VIS_API int32_t b200vis_set_shadow_items(b200vis_ctx *ctx, uint32_t n_items, const b200vis_shadow_item *items, uint32_t list_capacity);
 B200VIS_API int32_t b200vis_run_shadow_culling(b200vis_ctx *ctx);
 B200VIS_API int32_t b200vis_download_shadow_visible(b200vis_ctx *ctx, uint32_t shadow_light, uint32_t face, uint32_t *rows,
                                                     uint32_t capacity, uint32_t *count);

@@ -509,13 +509,27 @@ static int cmp_sort_item(const void *a, const void *b) {
     return ka < kb ? -1 : (ka > kb ? 1 : 0);
 }
 
+/* RenderLayers is a SmallVec of 64-bit blocks (render_layers.rs:20-23); intersects() ORs the block-wise ANDs over the
+ * common prefix (:121-135).  Block 0 travels in the layer_mask arguments; blocks 1..3 (layers 64..255) are registered here
+ * for the next orc_cull call(s): entity_ext[n][3], view_ext[V][3], NULL = every further block empty. */
+static const uint64_t *g_entity_layers_ext = NULL, *g_view_layers_ext = NULL;
+static uint32_t g_current_view = 0;   /* the view orc_cull is working on (single-threaded oracle) */
+ORC_API void orc_set_render_layers_ext(const uint64_t *entity_ext, const uint64_t *view_ext) {
+    g_entity_layers_ext = entity_ext; g_view_layers_ext = view_ext;
+}
+static inline int layers_ext_intersect(uint32_t r, uint32_t v) {
+    if (!g_entity_layers_ext || !g_view_layers_ext) return 0;
+    for (int k = 0; k < 3; ++k)
+        if (g_entity_layers_ext[(size_t)r * 3 + k] & g_view_layers_ext[(size_t)v * 3 + k]) return 1;
+    return 0;
+}
 /* one entity x one view: the closure at visibility/mod.rs:788-858 */
 static inline int entity_visible_in_view(uint32_t r, const float *gt, const float *bounds, uint8_t f,
                                          uint64_t entity_layers, uint64_t view_layers,
                                          const uint32_t *range_mask, int range_view_index,
                                          const v4 *hs, int view_no_cpu_culling) {
     if (!(f & F_INHERITED_VISIBLE)) return 0;
-    if (!(view_layers & entity_layers)) return 0;
+    if (!(view_layers & entity_layers) && !layers_ext_intersect(r, g_current_view)) return 0;
     if ((f & F_HAS_VIS_RANGE) && range_mask) {
         if (range_view_index < 0 || range_view_index > 31) return 0;
         if (!((range_mask[r] >> range_view_index) & 1u)) return 0;
@@ -581,6 +595,7 @@ ORC_API int orc_cull(uint32_t n, const float *gt, const float *bounds, const uin
         if (!(view_flags[v] & VIEW_ACTIVE)) { visible_count[v] = 0xFFFFFFFFu; continue; }
         v4 hs[6]; memcpy(hs, view_planes + (size_t)v * 24, sizeof hs);
         uint32_t cnt = 0;
+        g_current_view = v;
         for (uint32_t r = 0; r < n; ++r) {
             uint8_t f = flags[r];
             if (f & F_NO_CPU_CULLING) continue;                 /* Without<NoCpuCulling> */

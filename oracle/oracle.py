@@ -300,6 +300,24 @@ def cull(gt, bounds, flags, class_mask, entity_bits, vv, view_planes, view_layer
     return vv_changed, lists
 
 
+def set_render_layers_ext(entity_ext=None, view_ext=None):
+    """RenderLayers blocks 1..3 (layers 64..255) for the following cull() calls: entity_ext [n, 3], view_ext [V, 3] uint64; the
+    arrays are kept alive here.  None switches the extension off."""
+    global _layers_ext_keep
+    fn = lib().orc_set_render_layers_ext
+    fn.restype = None
+    if entity_ext is None or view_ext is None:
+        _layers_ext_keep = None
+        fn(None, None)
+        return
+    e = np.ascontiguousarray(entity_ext, np.uint64); v = np.ascontiguousarray(view_ext, np.uint64)
+    _layers_ext_keep = (e, v)
+    fn(_p(e, C.c_uint64), _p(v, C.c_uint64))
+
+
+_layers_ext_keep = None
+
+
 def visible_entities_by_class(visible_rows, class_mask, entity_bits):
     """VisibleEntities::entities of one view: {class k: sorted rows} (orc_visible_entities_by_class)."""
     vis = np.ascontiguousarray(visible_rows, np.uint32)

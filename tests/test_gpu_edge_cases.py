@@ -503,3 +503,40 @@ def test_visible_entities_per_visibility_class():
                 assert sum(len(x) for x in want.values()) >= len(world.last_lists[v])     # multi-class rows are pushed more than once
     finally:
         pipe.close()
+
+
+def test_render_layers_beyond_the_first_64():
+    """RenderLayers is a SmallVec of 64-bit blocks (render_layers.rs:20-23): an entity on layer 70 and a camera on layers
+    {3, 70} intersect through block 1 although their first blocks do not (intersects(), :121-135)."""
+    import oracle as orc
+    sc = scenes.forest(n_trees=60, levels=6, n_lights=8)
+    rng = np.random.default_rng(3)
+    n, V = sc.n, len(sc.cameras)
+    sc.layer_mask = rng.choice(np.array([0, 1, 2, 8], np.uint64), n).astype(np.uint64)      # block 0 (0: none of the first 64 layers)
+    ext = np.zeros((n, 3), np.uint64)
+    pick = rng.random(n) < 0.5
+    ext[pick, rng.integers(0, 3, pick.sum())] = np.uint64(1) << rng.integers(0, 64, pick.sum()).astype(np.uint64)
+    sc.view_layers = [1, 0, 2, 8][:V]
+    view_ext = np.zeros((V, 3), np.uint64)
+    view_ext[1 % V] = [0xFFFFFFFFFFFFFFFF, 0, 0]
+    view_ext[2 % V, 2] = 0xFFFFFFFF00000000
+    pipe = bb.VisibilityPipeline(sc)
+    world = OracleWorld(sc)
+    orc.set_render_layers_ext(ext, view_ext)
+    try:
+        pipe.ctx.upload_render_layers_ext(0, ext)
+        for v in range(V):
+            pipe.ctx.set_view_render_layers_ext(v, view_ext[v])
+        for f in range(3):
+            if f:
+                scenes.advance_cameras(sc, 0.1)
+                rows, trs = scenes.mutate_roots(sc, f)
+                pipe.ctx.upload_transforms_scattered(rows, trs)
+                world.tchanged[rows] = 1
+            pipe.update_views()
+            compare_frame(pipe, world, f)
+        only_ext = (sc.layer_mask[world.last_lists[1 % V]] & np.uint64(sc.view_layers[1 % V])) == 0
+        assert only_ext.any()          # some rows are listed through a block beyond the first
+    finally:
+        orc.set_render_layers_ext(None, None)
+        pipe.close()

@@ -262,3 +262,115 @@ def test_n3_rows_only_lights_see_become_visible():
         assert (vv & 1).sum() > len(cam)                     # rows visible to lights only
     finally:
         pipe.close()
+
+
+@pytest.mark.parametrize("seed,shuffle", [(12, True), (13, False)])
+def test_n3_spot_lights_and_directional_cascades(seed, shuffle):
+    """The other two halves of shadow-view culling on the device (b200vis_set_shadow_items): spot lights
+    (bevy_light/src/lib.rs:670-749: one frustum, near + far planes, range-sphere pre-test, only lights some view lists) and
+    directional-light cascades (lib.rs:342-510: one frustum per cascade, near plane skipped, gated on the VIEW's range bit),
+    mixed with point lights in one pass.  Lists, ViewVisibility and its change flags against the oracle, frame after frame."""
+    import oracle as orc
+    sc = _random_scene(seed, n_roots=90, n_lights=20, shuffle_entities=shuffle)
+    rng = np.random.default_rng(seed)
+    n = sc.n
+    caster = (rng.random(n) < 0.8).astype(np.uint8)
+    caster[sc.light_row] = 0
+    lights = rng.permutation(len(sc.light_row))
+    spot_ords, point_ords = np.sort(lights[:6]), np.sort(lights[6:10])
+    ident = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)
+    pipe = bb.VisibilityPipeline(sc)
+    world = OracleWorld(sc, True)
+    V = len(sc.cameras)
+    try:
+        pipe.ctx.upload_shadow_casters(0, caster)
+        seen = 0
+        for f in range(4):
+            if f:
+                scenes.advance_cameras(sc, 0.2)
+                rows = np.unique(rng.integers(0, n, n // 20)).astype(np.uint32)
+                sc.trs[rows, 0:3] += rng.uniform(-2, 2, (len(rows), 3)).astype(np.float32)
+                pipe.ctx.upload_transforms_scattered(rows, sc.trs[rows])
+                world.tchanged[rows] = 1
+            pipe.update_views()
+            planes = np.stack([np.ctypeslib.as_array(v.half_spaces).reshape(6, 4).copy() for v in pipe.views])
+            # ---- oracle: check_visibility with mark_newly_hidden deferred, the light passes, then mark_newly_hidden
+            rc, _ = orc.propagate(sc.parent, sc.trs, world.gt, world.tchanged, True)
+            world.tchanged[:] = 0
+            orc.set_defer_mark_newly_hidden(True)
+            try:
+                vv_changed, lists = orc.cull(world.gt, sc.bounds, sc.flags, sc.class_mask, sc.entity_bits, world.vv, planes,
+                                             view_layers=sc.view_layers, view_flags=sc.view_flags, layer_mask=sc.layer_mask,
+                                             range_mask=sc.range_mask, view_range_index=sc.view_range_index)
+            finally:
+                orc.set_defer_mark_newly_hidden(False)
+            lists = [l if l is not None else world.last_lists[v] for v, l in enumerate(lists)]
+            world.last_lists = lists
+            listed = set(np.concatenate(lists).tolist())
+            # ---- this frame's items: frusta from the lights' GlobalTransforms of this frame
+            items, oracle_jobs = [], []
+            for o in spot_ords:
+                row = int(sc.light_row[o])
+                fr = orc.point_light_frusta(world.gt[row], sc.light_range[o], 0.1)[int(o) % 6]    # any single frustum at the light
+                ll = 1 if sc.light_layers is None else int(sc.light_layers[o])
+                items.append(dict(kind=1, light_row=row, range=float(sc.light_range[o]), range_view_index=0, layer_mask=ll, frusta=fr))
+                oracle_jobs.append(("spot", row, o, fr, ll))
+            for o in point_ords:
+                row = int(sc.light_row[o])
+                fr = orc.point_light_frusta(world.gt[row], sc.light_range[o], 0.1)
+                ll = 1 if sc.light_layers is None else int(sc.light_layers[o])
+                items.append(dict(kind=0, light_row=row, range=float(sc.light_range[o]), range_view_index=0, layer_mask=ll, frusta=fr))
+                oracle_jobs.append(("point", row, o, fr, ll))
+            casc = []
+            for v in range(min(V, 2)):                            # one directional light, cascades of views 0 and 1
+                for c, rr in enumerate((25.0, 80.0)):
+                    centre = np.asarray(sc.cameras[v].gt[9:12], np.float32) + np.float32(5.0 * c)
+                    fr = orc.point_light_frusta(np.concatenate([ident, centre]).astype(np.float32), rr, 0.1)[(v + c) % 6]
+                    vri = -1 if sc.view_range_index is None else int(sc.view_range_index[v])
+                    items.append(dict(kind=2, range_view_index=vri, layer_mask=3, frusta=fr))
+                    casc.append((v, fr, vri))
+            pipe.ctx.run(bb.STAGE_ALL if len(sc.light_row) else (bb.STAGE_PROPAGATE | bb.STAGE_CULL))
+            pipe.ctx.set_shadow_items(items)
+            pipe.ctx.run_shadow_culling()
+            # ---- oracle light passes in the reference's order: directional first (lib.rs:342), then point / spot (:517)
+            want = {}
+            dir_items = []
+            for v in range(min(V, 2)):
+                frs = np.stack([fr for (vv_, fr, _) in casc if vv_ == v])
+                dir_items.append((frs, 3, casc[[i for i, c_ in enumerate(casc) if c_[0] == v][0]][2]))
+            got_dir = orc.check_dir_light_mesh_visibility(world.gt, sc.bounds, sc.flags, caster, sc.entity_bits, world.vv, vv_changed,
+                                                          dir_items, layer_mask=sc.layer_mask, range_mask=sc.range_mask)
+            k = len(spot_ords) + len(point_ords)
+            for lists_of_item in got_dir:
+                for rows_ in lists_of_item:
+                    want[(k, 0)] = rows_; k += 1
+            for i, (kind, row, o, fr, ll) in enumerate(oracle_jobs):
+                if row not in listed:                               # the light is in no view's VisibleEntities: not processed
+                    for face in range(6):
+                        want[(i, face)] = np.zeros(0, np.uint32)
+                    continue
+                sphere = np.concatenate([world.gt[row, 9:12], [sc.light_range[o]]]).astype(np.float32)[None]
+                if kind == "spot":
+                    r = orc.check_spot_light_mesh_visibility(world.gt, sc.bounds, sc.flags, caster, sc.entity_bits, world.vv, vv_changed,
+                                                             sphere, fr[None], layer_mask=sc.layer_mask, range_mask=sc.range_mask,
+                                                             lod_origin_index=0, light_layers=np.array([ll], np.uint64))
+                    want[(i, 0)] = r[0]
+                else:
+                    r = orc.check_point_light_mesh_visibility(world.gt, sc.bounds, sc.flags, caster, sc.entity_bits, world.vv, vv_changed,
+                                                              sphere, fr[None], layer_mask=sc.layer_mask, range_mask=sc.range_mask,
+                                                              lod_origin_index=0, light_layers=np.array([ll], np.uint64))
+                    for face in range(6):
+                        want[(i, face)] = r[0][face]
+            orc.mark_newly_hidden(sc.flags, world.vv, vv_changed)
+            # ---- compare
+            for (i, face), rows_ in want.items():
+                got = pipe.ctx.download_shadow_visible(i, face)
+                assert len(got) == len(rows_) and (got == rows_).all(), f"frame {f} item {i} face {face}: {len(got)} vs {len(rows_)}"
+                seen += len(rows_)
+            vv, vch = pipe.ctx.download_view_visibility(0, n)
+            assert (vv == world.vv).all(), f"frame {f}: ViewVisibility differs on rows {np.nonzero(vv != world.vv)[0][:8]}"
+            assert (vch == vv_changed).all(), f"frame {f}: Changed<ViewVisibility> differs"
+            pipe.read_feedback()
+        assert seen > 200
+    finally:
+        pipe.close()
