@@ -114,6 +114,7 @@ _SIGNATURES = {
     "b200vis_tail_stream": (C.c_int32, [_vp, _P(_vp)]),
     "b200vis_set_topology": (C.c_int32, [_vp, C.c_uint32, _vp, _vp]),
     "b200vis_kernel_launch_count": (C.c_uint64, []),
+    "b200vis_p2p_link": (C.c_int32, [_vp, C.c_uint32]),
     "b200vis_upload_render_layers_ext": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "b200vis_set_view_render_layers_ext": (C.c_int32, [_vp, C.c_uint32, _vp]),
     "b200vis_set_shadow_items": (C.c_int32, [_vp, C.c_uint32, _vp, C.c_uint32]),
@@ -288,6 +289,14 @@ def host_warp_plan(parent, tile_rows=0):
     if rc:
         raise B200VisError(rc, "host_warp_plan")
     return desc, nonroot, sched, wtopo
+
+
+def p2p_link(contexts):
+    """b200vis_p2p_link: contexts[r] was created with world_size=len(contexts), rank=r (one process, several devices)."""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = load_library().b200vis_p2p_link(arr, len(contexts))
+    if rc:
+        raise B200VisError(rc, contexts[0]._last_error() if hasattr(contexts[0], "_last_error") else "p2p_link")
 
 
 def plan_row_order(parent):

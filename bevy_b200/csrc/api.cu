@@ -149,7 +149,7 @@ struct b200vis_ctx {
     void *nccl_comm = nullptr;          // b200vis_comm_init
     uint32_t *d_gather = nullptr;       // [world][slab] when the library owns the exchange
     // peer-memory exchange (b200vis_p2p_export / _import): [2][world][slab] + flags [2][world], mapped into every rank
-    uint32_t *d_xbuf = nullptr; size_t xbuf_flag_offset = 0; void *peer_map[8] = {}; bool p2p_ready = false;
+    uint32_t *d_xbuf = nullptr; size_t xbuf_flag_offset = 0; void *peer_map[8] = {}; bool peer_ipc[8] = {}; bool p2p_ready = false;
     uint32_t *d_push_done = nullptr;
     b200vis_cluster_feedback auto_fb[kMaxViews]{};   // b200vis_step: last frame's Clusters feedback
 
@@ -222,7 +222,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
                 1e6 * ctx->step_t[3] / ctx->step_n, 1e6 * ctx->step_t[4] / ctx->step_n, 1e6 * ctx->step_t[5] / ctx->step_n);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->d_gather) cudaFree(ctx->d_gather);
-    for (uint32_t r = 0; r < 8; ++r) if (ctx->peer_map[r] && r != ctx->cl.rank) cudaIpcCloseMemHandle(ctx->peer_map[r]);
+    for (uint32_t r = 0; r < 8; ++r) if (ctx->peer_map[r] && r != ctx->cl.rank && ctx->peer_ipc[r]) cudaIpcCloseMemHandle(ctx->peer_map[r]);
     if (ctx->d_xbuf) cudaFree(ctx->d_xbuf);
     if (ctx->d_push_done) cudaFree(ctx->d_push_done);
     for (auto &r : ctx->recorded) if (r.dev) cudaFree(r.dev);
@@ -1103,7 +1103,7 @@ extern "C" int32_t b200vis_p2p_import(b200vis_ctx *ctx, const uint8_t *handles) 
         void *p = nullptr;
         const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, B200VIS_ERR_UNSUPPORTED, "p2p_import: cudaIpcOpenMemHandle(rank %u): %s", r, cudaGetErrorString(e)); }
-        ctx->peer_map[r] = p;
+        ctx->peer_map[r] = p; ctx->peer_ipc[r] = true;
     }
     CU(cudaStreamSynchronize(ctx->stream));
     for (uint32_t r = 0; r < ctx->cl.world; ++r) {
@@ -1112,6 +1112,42 @@ extern "C" int32_t b200vis_p2p_import(b200vis_ctx *ctx, const uint8_t *handles) 
     }
     ctx->cl.send = ctx->d_slab;
     ctx->p2p_ready = true;
+    return B200VIS_OK;
+}
+// The same exchange for contexts that live in ONE process (a Bevy App is one process driving all its GPUs): no IPC handles,
+// the contexts' gathered buffers are reached through plain peer access.  ctxs[r] must have been created with world_size = n and
+// rank = r, each on its own device.  Afterwards the host thread simply calls b200vis_run(ctxs[r], B200VIS_STAGE_ALL) for every r
+// (all launches are asynchronous; the list kernels wait for the peers' stamps on the device).
+extern "C" int32_t b200vis_p2p_link(b200vis_ctx *const *ctxs, uint32_t n) {
+    if (!ctxs || n < 2 || n > 8) return B200VIS_ERR_INVALID_ARG;
+    for (uint32_t r = 0; r < n; ++r) {
+        b200vis_ctx *ctx = ctxs[r];
+        if (!ctx || ctx->cl.world != n || ctx->cl.rank != r)
+            return fail(ctx, B200VIS_ERR_INVALID_ARG, "p2p_link: context %u must be created with world_size %u and rank %u", r, n, r);
+        uint8_t unused[B200VIS_P2P_HANDLE_BYTES];
+        const int32_t rc = b200vis_p2p_export(ctx, unused);      // allocates the gathered buffer + flags
+        if (rc) return rc;
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        b200vis_ctx *ctx = ctxs[r];
+        CU(cudaSetDevice(ctx->device));
+        for (uint32_t q = 0; q < n; ++q) {
+            if (q != r && ctxs[q]->device != ctx->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[q]->device));
+                if (!can) return fail(ctx, B200VIS_ERR_UNSUPPORTED, "p2p_link: device %d cannot access device %d", ctx->device, ctxs[q]->device);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return fail(ctx, B200VIS_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); }
+                cudaGetLastError();
+            }
+            ctx->peer_map[q] = ctxs[q]->d_xbuf; ctx->peer_ipc[q] = false;
+            ctx->cl.peer[q] = ctxs[q]->d_xbuf;
+            ctx->cl.peer_flags[q] = ctxs[q]->d_xbuf + ctxs[q]->xbuf_flag_offset;
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->cl.send = ctx->d_slab;
+        ctx->p2p_ready = true;
+    }
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_cluster_exchange_bytes(const b200vis_ctx *ctx, size_t *slab_bytes) {

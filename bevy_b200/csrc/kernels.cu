@@ -2335,6 +2335,37 @@ k_shadow_cull(Rows R, ShadowBufs sb, uint32_t words_stride, uint32_t chunks_stri
     const float cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;
     const float cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
     const float cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+    // ---- block pre-pass: an axis-aligned box around the world-space centres of this CTA's bounded candidate rows and the largest
+    // OBB reach E1 = sum_i h_i * |axis_i|_1 among them (>= relative_radius(v) / |v| for every direction v).  An item whose range
+    // sphere (or, for a cascade, one of whose half spaces) cannot reach the box is skipped for the whole CTA: every exact per-row
+    // test would fail.  Rows are spatially coherent (a CTA holds one tree), so almost every (CTA, light) pair goes this way.
+    __shared__ float s_red[8][7];
+    __shared__ float s_box[7];
+    const float e1_row = fabsf(hx) * ((fabsf(g.r0.x) + fabsf(g.r1.x)) + fabsf(g.r2.x)) + fabsf(hy) * ((fabsf(g.r0.y) + fabsf(g.r1.y)) + fabsf(g.r2.y)) +
+                         fabsf(hz) * ((fabsf(g.r0.z) + fabsf(g.r1.z)) + fabsf(g.r2.z));
+    // rows without an Aabb / with NoFrustumCulling pass without a test, rows with non-finite numbers behave arbitrarily in the
+    // exact tests: either kind switches the skipping off for its CTA
+    const bool bounded = eligible && has_aabb && !no_fc && isfinite(((cx + cy) + cz) + e1_row);
+    const int unbounded_any = __syncthreads_or(eligible && !bounded);
+    {
+        const float inf = __int_as_float(0x7f800000);
+        float v[7];
+        v[0] = bounded ? cx : inf; v[1] = bounded ? cy : inf; v[2] = bounded ? cz : inf;
+        v[3] = bounded ? -cx : inf; v[4] = bounded ? -cy : inf; v[5] = bounded ? -cz : inf;       // min of the negation = -max
+        v[6] = bounded ? -e1_row : inf;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] = fminf(v[k], __shfl_xor_sync(0xFFFFFFFFu, v[k], o));
+            if (lane == 0) s_red[threadIdx.x >> 5][k] = v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < 7) {
+            float m = s_red[0][threadIdx.x];
+            for (int w = 1; w < 8; ++w) m = fminf(m, s_red[w][threadIdx.x]);
+            s_box[threadIdx.x] = m;
+        }
+    }
     bool any = false;
     for (uint32_t s0 = 0; s0 < sb.n_lights; s0 += kShadowChunk) {
         const uint32_t nl = min((uint32_t)kShadowChunk, sb.n_lights - s0);
@@ -2352,6 +2383,25 @@ k_shadow_cull(Rows R, ShadowBufs sb, uint32_t words_stride, uint32_t chunks_stri
             if (!s_on[i]) continue;                                  // warp-uniform
             const ShadowLight &sl = s_light[i];
             const uint32_t kind = sl.kind, n_faces = kind == 0u ? 6u : 1u;
+            if (!unbounded_any) {                                    // CTA-uniform conservative rejection (see the pre-pass above)
+                const float bx0 = s_box[0], by0 = s_box[1], bz0 = s_box[2], bx1 = -s_box[3], by1 = -s_box[4], bz1 = -s_box[5], e1 = -s_box[6];
+                bool skip = !(bx0 <= bx1);                           // no bounded candidate row in this CTA at all
+                if (!skip && kind < 2u) {
+                    const float4 sp = s_sphere[i];
+                    const float dx = fmaxf(fmaxf(bx0 - sp.x, sp.x - bx1), 0.0f), dy = fmaxf(fmaxf(by0 - sp.y, sp.y - by1), 0.0f);
+                    const float dz = fmaxf(fmaxf(bz0 - sp.z, sp.z - bz1), 0.0f);
+                    const float reach = (sp.w + e1) * 1.001f + 1e-3f;        // d <= r + rr/d <= r + E1 where the exact test passes
+                    skip = (dx * dx + dy * dy) + dz * dz > reach * reach;
+                } else if (!skip) {
+                    for (int k = 0; k < 6 && !skip; ++k) {           // a half space no point of the box reaches, even grown by E1
+                        if (k == 4) continue;
+                        const float4 n = sl.planes[0][k];
+                        const float m = ((fmaxf(n.x * bx0, n.x * bx1) + fmaxf(n.y * by0, n.y * by1)) + fmaxf(n.z * bz0, n.z * bz1)) + n.w;
+                        skip = m + (e1 * 1.001f + 1e-3f) * ((fabsf(n.x) + fabsf(n.y)) + fabsf(n.z)) < 0.0f;
+                    }
+                }
+                if (skip) continue;
+            }
             bool in = eligible && (sl.layers & elayers) != 0ull;
             if (in && ranged) in = sl.range_index >= 0 && sl.range_index < 32 && ((erange >> sl.range_index) & 1u);
             uint32_t faces = kind == 0u ? 0x3Fu : 1u;                // no Aabb: pushed to every list of the item (lib.rs:639-645)

@@ -500,6 +500,10 @@ B200VIS_API int32_t b200vis_comm_init(b200vis_ctx *ctx, const uint8_t id[B200VIS
 #define B200VIS_P2P_HANDLE_BYTES 64
 B200VIS_API int32_t b200vis_p2p_export(b200vis_ctx *ctx, uint8_t handle[B200VIS_P2P_HANDLE_BYTES]);
 B200VIS_API int32_t b200vis_p2p_import(b200vis_ctx *ctx, const uint8_t *handles /* [world_size][64], rank-major */);
+/* One process, several GPUs (a Bevy App is one process): link the contexts of the process directly -- plain peer access, no
+ * IPC handles, no collective library.  ctxs[r]: created with world_size = n, rank = r, one device each.  Then one host thread
+ * calls b200vis_run(ctxs[r], B200VIS_STAGE_ALL) for every r per frame; the slab exchange happens on the devices. */
+B200VIS_API int32_t b200vis_p2p_link(b200vis_ctx *const *ctxs, uint32_t n);
 B200VIS_API int32_t b200vis_cluster_exchange_bytes(const b200vis_ctx *ctx, size_t *slab_bytes);
 B200VIS_API int32_t b200vis_set_cluster_exchange_buffers(b200vis_ctx *ctx, void *send_device, void *recv_device);
 
