@@ -693,6 +693,7 @@ struct ScoutSmem {
     uint8_t dirty[2][kTileRows];     // TransformTreeChanged, valid when slow[s]
     uint32_t slow[2];                // a row with an in-tile parent changed: workers read dirty[] instead of their own Changed bit
     uint32_t any_gt[2];              // a worker row's GlobalTransform changed: the tile must be stored
+    float4 ltop[32][3];              // scout only: the local affines of the tile's first 32 rows (the lane-split level rounds read them)
 };
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -785,37 +786,84 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                 const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
                 if (act && (topo & T_DETACHED)) s.pst[sidx][lane] = 0;     // never visited, and neither is its subtree
                 bool changed = false;
-                for (uint32_t lvl = 0; lvl < K; ++lvl) {
+                if (act) { s.ltop[lane][0] = l.r0; s.ltop[lane][1] = l.r1; s.ltop[lane][2] = l.r2; }
+                // ---- level 0 (roots, rows whose parent another pass finished): lane = row
+                if (in_top && depth == 0u) {
+                    bool visited = false;
+                    Aff n = l;
+                    if (topo & T_ROOT) {
+                        visited = has_children ? (!static_opt || dirty) : tchanged;
+                        changed = visited;
+                    } else {
+                        const uint32_t pr = R.parent[row];
+                        const uint32_t ps = R.state[pr];
+                        visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
+                        if (visited) {
+                            n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
+                            changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);
+                        }
+                    }
+                    if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+                    s.pst[sidx][lane] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+                }
+                bool any_changed = __any_sync(kFull, changed);
+                // ---- levels 1 .. K-1: a level of the top has at most 16 rows, so the matrix product of one row is split over
+                // 4 (or 2) lanes, one output COLUMN (3 floats, same operation order as affine_mul_row) each: the scout's chain is
+                // what the workers wait for, and it is bound by instruction issue, not by the five dependent products
+                for (uint32_t lvl = 1; lvl < K; ++lvl) {
                     __syncwarp();
-                    if (in_top && depth == lvl) {
-                        bool visited = false;
-                        Aff n = l;
-                        if (depth == 0u) {
-                            if (topo & T_ROOT) {
-                                visited = has_children ? (!static_opt || dirty) : tchanged;
-                                changed = visited;
-                            } else {
-                                const uint32_t pr = R.parent[row];
-                                const uint32_t ps = R.state[pr];
-                                visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
-                                if (visited) {
-                                    n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
-                                    changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);
-                                }
-                            }
-                        } else {
-                            const uint32_t pst = s.pst[sidx][plocal];
-                            const uint32_t pi = off + plocal;
-                            visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
-                            if (visited) {
-                                n.r0 = affine_mul_row(S.gt0[pi], l); n.r1 = affine_mul_row(S.gt1[pi], l); n.r2 = affine_mul_row(S.gt2[pi], l);
-                                changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);   // set_if_neq
+                    const uint32_t M = __ballot_sync(kFull, in_top && depth == lvl);
+                    const uint32_t c = __popc(M);
+                    if (!c) continue;
+                    const uint32_t F = c <= 8u ? 4u : (c <= 16u ? 2u : 1u), cols = 4u / F;
+                    const uint32_t idx = lane / F, part = lane % F;
+                    const bool work = idx < c;
+                    const uint32_t rl = work ? __fns(M, 0, idx + 1u) : 0u;       // the idx-th row of this level (a lane index)
+                    bool visited = false, neq = false;
+                    float nv[4][3];
+                    const uint32_t li2 = off + rl;
+                    if (work) {
+                        const uint32_t topo2 = S.topo[li2], pl = topo2 & 0x1FFu;
+                        bool d2 = S.flags[li2] & F_TCHANGED;
+                        if (static_opt) {
+                            if (R.dirty != nullptr) d2 = R.dirty[tile.base + rl];
+                            else if (slow) d2 = s.dirty[sidx][rl];
+                        }
+                        const uint32_t pst = s.pst[sidx][pl];
+                        visited = (pst & 1u) && !(static_opt && !d2 && !(pst & 2u));
+                        if (visited) {
+                            const float4 p0 = S.gt0[off + pl], p1 = S.gt1[off + pl], p2 = S.gt2[off + pl];
+                            const float *l0 = reinterpret_cast<const float *>(&s.ltop[rl][0]), *l1 = reinterpret_cast<const float *>(&s.ltop[rl][1]);
+                            const float *l2 = reinterpret_cast<const float *>(&s.ltop[rl][2]);
+                            const float *o0 = reinterpret_cast<const float *>(&S.gt0[li2]), *o1 = reinterpret_cast<const float *>(&S.gt1[li2]);
+                            const float *o2 = reinterpret_cast<const float *>(&S.gt2[li2]);
+#pragma unroll
+                            for (uint32_t q = 0; q < 4; ++q) {
+                                if (q >= cols) break;
+                                const uint32_t col = part * cols + q;
+                                const float a = l0[col], b = l1[col], cc = l2[col];
+                                float x = (p0.x * a + p0.y * b) + p0.z * cc, y = (p1.x * a + p1.y * b) + p1.z * cc, z = (p2.x * a + p2.y * b) + p2.z * cc;
+                                if (col == 3u) { x = x + p0.w; y = y + p1.w; z = z + p2.w; }
+                                nv[q][0] = x; nv[q][1] = y; nv[q][2] = z;
+                                neq |= (x != o0[col]) | (y != o1[col]) | (z != o2[col]);                       // set_if_neq
                             }
                         }
-                        if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
-                        s.pst[sidx][lane] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
                     }
+                    const uint32_t nb = __ballot_sync(kFull, neq);
+                    const bool row_changed = work && ((nb >> (idx * F)) & ((1u << F) - 1u)) != 0u;
+                    if (row_changed) {
+                        float *o0 = reinterpret_cast<float *>(&S.gt0[li2]), *o1 = reinterpret_cast<float *>(&S.gt1[li2]), *o2 = reinterpret_cast<float *>(&S.gt2[li2]);
+#pragma unroll
+                        for (uint32_t q = 0; q < 4; ++q) {
+                            if (q >= cols) break;
+                            const uint32_t col = part * cols + q;
+                            o0[col] = nv[q][0]; o1[col] = nv[q][1]; o2[col] = nv[q][2];
+                        }
+                    }
+                    if (work && part == 0u) s.pst[sidx][rl] = (uint8_t)((visited ? 1u : 0u) | (row_changed ? 2u : 0u));
+                    any_changed |= nb != 0u;
                 }
+                changed = any_changed;
                 top_changed = __any_sync(kFull, changed);
             }
             __syncwarp();
@@ -856,9 +904,12 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
         // ================================ 256 workers ================================
         const uint32_t lr = tid;
         uint32_t it = 0;
+        Tile next_tile = {};
+        if (blockIdx.x < n_tiles) next_tile = tiles[blockIdx.x];
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t sidx = it & 1u, ph = (it >> 1) & 1u;
-            const Tile tile = tiles[t];
+            const Tile tile = next_tile;
+            if (t + gridDim.x < n_tiles) next_tile = tiles[t + gridDim.x];    // the next descriptor: in flight during this tile
             mbar_wait(&s.full[sidx], ph);
             mbar_wait(&s.top[sidx], ph);
             TileStage &S = s.st[sidx];
