@@ -512,6 +512,9 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
             for (uint32_t r = t.base; r < t.base + t.n_rows; ++r) max_local[ldepth[r]] = std::max(max_local[ldepth[r]], r - t.base);
             uint32_t K = 0;
             while (K < t.n_levels && max_local[K] < 32u) ++K;
+            static int cap_env = -1;      // B200VIS_TOP_LEVELS_CAP: how many levels the scout may take (experiment knob)
+            if (cap_env < 0) { const char *e = getenv("B200VIS_TOP_LEVELS_CAP"); cap_env = e ? atoi(e) : 255; }
+            if (K > (uint32_t)cap_env) K = (uint32_t)cap_env;
             t.top_levels = (t.n_levels > 1) ? K : 0u;       // flat tiles have nothing to walk ahead
         }
     }

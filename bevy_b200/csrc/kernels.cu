@@ -67,6 +67,46 @@ __device__ __forceinline__ float gl_min(float a, float b) { return a < b ? a : b
 __device__ __forceinline__ float gl_max(float a, float b) { return a > b ? a : b; }
 
 // ------------------------------------------------------------------------------------------
+// Warp-level view rejection.  Thirty-two consecutive rows are neighbours in space (one level of one tree, a stretch of a
+// spiral of cubes), and a view's frustum holds a small part of the world: before the per-row plane tests of a view, the warp
+// builds an axis-aligned box around its rows' bounding-sphere centres (+ the largest radius) and lets 5 x n_views lanes test
+// one (view, plane) pair each against it.  A plane the whole box is behind -- by more than the float error any of the exact
+// evaluations can carry -- culls every row in Frustum::intersects_sphere already (primitives.rs:255-268), so the view's
+// ~70 instructions per row are skipped and every row simply reports "not visible" for it: same bits, less work.
+// Rows that are not frustum-tested (no bounds, NoFrustumCulling) or carry non-finite numbers switch the shortcut off for
+// their warp.  Returns a bit per view.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_order(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7FFFFFFF); }
+__device__ __forceinline__ float order_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7FFFFFFF)); }
+__device__ __forceinline__ uint32_t warp_view_reject(const CullViews &cvw, bool testable, bool blocks, float cx, float cy, float cz, float radius) {
+    const float inf = __int_as_float(0x7f800000);
+    const bool fin = testable && isfinite(((cx + cy) + cz) + radius);
+    if (__any_sync(0xFFFFFFFFu, blocks || (testable && !fin))) return 0u;
+    const float x0 = order_float(__reduce_min_sync(0xFFFFFFFFu, float_order(fin ? cx : inf)));
+    const float y0 = order_float(__reduce_min_sync(0xFFFFFFFFu, float_order(fin ? cy : inf)));
+    const float z0 = order_float(__reduce_min_sync(0xFFFFFFFFu, float_order(fin ? cz : inf)));
+    const float x1 = order_float(__reduce_max_sync(0xFFFFFFFFu, float_order(fin ? cx : -inf)));
+    const float y1 = order_float(__reduce_max_sync(0xFFFFFFFFu, float_order(fin ? cy : -inf)));
+    const float z1 = order_float(__reduce_max_sync(0xFFFFFFFFu, float_order(fin ? cz : -inf)));
+    const float r1 = order_float(__reduce_max_sync(0xFFFFFFFFu, float_order(fin ? radius : -inf)));
+    if (!(x0 <= x1)) return 0xFFFFFFFFu;          // no frustum-tested row in this warp (and none that blocks): nothing can be visible
+    const uint32_t lane = threadIdx.x & 31u;
+    bool rej = false;
+    if (lane < 5u * cvw.n_views && lane < 30u) {       // views 0..5; a seventh or eighth view is never rejected here
+        const float4 n = cvw.planes[lane / 5u][lane % 5u];
+        const float m = ((fmaxf(n.x * x0, n.x * x1) + fmaxf(n.y * y0, n.y * y1)) + fmaxf(n.z * z0, n.z * z1)) + n.w;
+        const float mag = ((fabsf(n.x) * fmaxf(fabsf(x0), fabsf(x1)) + fabsf(n.y) * fmaxf(fabsf(y0), fabsf(y1))) +
+                           fabsf(n.z) * fmaxf(fabsf(z0), fabsf(z1))) + (fabsf(n.w) + fabsf(r1));
+        rej = (m + r1) + (1e-5f * mag + 1e-6f) < 0.0f;     // ~25x the rounding any exact plane_dot_point(..) + radius can carry
+    }
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, rej);
+    uint32_t out = 0;
+#pragma unroll
+    for (uint32_t v = 0; v < 6u; ++v) out |= ((b >> (5u * v)) & 0x1Fu) ? (1u << v) : 0u;
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
 // Kernel 1: fused propagate -> cull over one tile of rows per CTA.
 //
 // A tile is a contiguous row range whose hierarchy edges stay inside the tile (parents in
@@ -218,6 +258,7 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const __grid_constant__
     if (CULL) {
         const bool in_query = active && !(f & F_NO_CPU_CULL);          // Without<NoCpuCulling>
         const bool base = in_query && (f & F_INHERITED);
+        const bool rej_base = base;
         const uint32_t prev = st8 & 1u;                                // reset_view_visibility: v = (v&1)<<1
         const uint32_t lane = lr & 31u;
         const bool has_aabb = f & F_AABB;
@@ -245,6 +286,8 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const __grid_constant__
             if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
             if (R.rank != nullptr) rnk = R.rank[row];
         }
+        // warp-level shortcut: views whose frustum the whole warp's rows are outside of (see warp_view_reject)
+        const uint32_t rejmask = warp_view_reject(cvw, rej_base && do_test, rej_base && !do_test, cx, cy, cz, radius);
         bool any = false;
         uint32_t my_ballot = 0;
         // The per-view constants arrive as a __grid_constant__ kernel parameter: with the view loop
@@ -255,6 +298,7 @@ k_propagate_cull(Rows R, const Tile *__restrict__ tiles, const __grid_constant__
             const uint32_t von = cvw.on[v];
             if (!(von & 1u)) continue;                                 // !camera.is_active (grid-uniform)
             if (SIMPLE && !(von & 4u)) continue;                       // bit2: the view includes the default layer
+            if (((rejmask >> v) & 1u) && !(von & 2u)) continue;         // every row of this warp is outside this view's frustum
             bool vis = base;
             if (!SIMPLE) {
                 vis = vis && layers_intersect(R, cvw, row, v, elayers);
@@ -538,6 +582,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
             Aff g; g.r0 = S.gt0[li]; g.r1 = S.gt1[li]; g.r2 = S.gt2[li];   // own row: written by this thread or untouched
             const bool in_query = active && !(f & F_NO_CPU_CULL);
             const bool base = in_query && (f & F_INHERITED);
+        const bool rej_base = base;
             const uint32_t prev = st8 & 1u;
             const uint32_t lane = lr & 31u;
             const bool has_aabb = f & F_AABB;
@@ -563,6 +608,8 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
                 if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
                 if (R.rank != nullptr) rnk = R.rank[row];
             }
+            // warp-level shortcut: views whose frustum the whole warp's rows are outside of (see warp_view_reject)
+            const uint32_t rejmask = warp_view_reject(cvw, rej_base && do_test, rej_base && !do_test, cx, cy, cz, radius);
             bool any = false;
             uint32_t my_ballot = 0;
 #pragma unroll
@@ -571,6 +618,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
                 const uint32_t von = cvw.on[v];
                 if (!(von & 1u)) continue;
                 if (SIMPLE && !(von & 4u)) continue;   // bit2: the view includes the default layer
+                if (((rejmask >> v) & 1u) && !(von & 2u)) continue;         // every row of this warp is outside this view's frustum
                 bool vis = base;
                 if (!SIMPLE) {
                     vis = vis && layers_intersect(R, cvw, row, v, elayers);
@@ -693,7 +741,6 @@ struct ScoutSmem {
     uint8_t dirty[2][kTileRows];     // TransformTreeChanged, valid when slow[s]
     uint32_t slow[2];                // a row with an in-tile parent changed: workers read dirty[] instead of their own Changed bit
     uint32_t any_gt[2];              // a worker row's GlobalTransform changed: the tile must be stored
-    float4 ltop[32][3];              // scout only: the local affines of the tile's first 32 rows (the lane-split level rounds read them)
 };
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -786,84 +833,37 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                 const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
                 if (act && (topo & T_DETACHED)) s.pst[sidx][lane] = 0;     // never visited, and neither is its subtree
                 bool changed = false;
-                if (act) { s.ltop[lane][0] = l.r0; s.ltop[lane][1] = l.r1; s.ltop[lane][2] = l.r2; }
-                // ---- level 0 (roots, rows whose parent another pass finished): lane = row
-                if (in_top && depth == 0u) {
-                    bool visited = false;
-                    Aff n = l;
-                    if (topo & T_ROOT) {
-                        visited = has_children ? (!static_opt || dirty) : tchanged;
-                        changed = visited;
-                    } else {
-                        const uint32_t pr = R.parent[row];
-                        const uint32_t ps = R.state[pr];
-                        visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
-                        if (visited) {
-                            n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
-                            changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);
-                        }
-                    }
-                    if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
-                    s.pst[sidx][lane] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
-                }
-                bool any_changed = __any_sync(kFull, changed);
-                // ---- levels 1 .. K-1: a level of the top has at most 16 rows, so the matrix product of one row is split over
-                // 4 (or 2) lanes, one output COLUMN (3 floats, same operation order as affine_mul_row) each: the scout's chain is
-                // what the workers wait for, and it is bound by instruction issue, not by the five dependent products
-                for (uint32_t lvl = 1; lvl < K; ++lvl) {
+                for (uint32_t lvl = 0; lvl < K; ++lvl) {
                     __syncwarp();
-                    const uint32_t M = __ballot_sync(kFull, in_top && depth == lvl);
-                    const uint32_t c = __popc(M);
-                    if (!c) continue;
-                    const uint32_t F = c <= 8u ? 4u : (c <= 16u ? 2u : 1u), cols = 4u / F;
-                    const uint32_t idx = lane / F, part = lane % F;
-                    const bool work = idx < c;
-                    const uint32_t rl = work ? __fns(M, 0, idx + 1u) : 0u;       // the idx-th row of this level (a lane index)
-                    bool visited = false, neq = false;
-                    float nv[4][3];
-                    const uint32_t li2 = off + rl;
-                    if (work) {
-                        const uint32_t topo2 = S.topo[li2], pl = topo2 & 0x1FFu;
-                        bool d2 = S.flags[li2] & F_TCHANGED;
-                        if (static_opt) {
-                            if (R.dirty != nullptr) d2 = R.dirty[tile.base + rl];
-                            else if (slow) d2 = s.dirty[sidx][rl];
-                        }
-                        const uint32_t pst = s.pst[sidx][pl];
-                        visited = (pst & 1u) && !(static_opt && !d2 && !(pst & 2u));
-                        if (visited) {
-                            const float4 p0 = S.gt0[off + pl], p1 = S.gt1[off + pl], p2 = S.gt2[off + pl];
-                            const float *l0 = reinterpret_cast<const float *>(&s.ltop[rl][0]), *l1 = reinterpret_cast<const float *>(&s.ltop[rl][1]);
-                            const float *l2 = reinterpret_cast<const float *>(&s.ltop[rl][2]);
-                            const float *o0 = reinterpret_cast<const float *>(&S.gt0[li2]), *o1 = reinterpret_cast<const float *>(&S.gt1[li2]);
-                            const float *o2 = reinterpret_cast<const float *>(&S.gt2[li2]);
-#pragma unroll
-                            for (uint32_t q = 0; q < 4; ++q) {
-                                if (q >= cols) break;
-                                const uint32_t col = part * cols + q;
-                                const float a = l0[col], b = l1[col], cc = l2[col];
-                                float x = (p0.x * a + p0.y * b) + p0.z * cc, y = (p1.x * a + p1.y * b) + p1.z * cc, z = (p2.x * a + p2.y * b) + p2.z * cc;
-                                if (col == 3u) { x = x + p0.w; y = y + p1.w; z = z + p2.w; }
-                                nv[q][0] = x; nv[q][1] = y; nv[q][2] = z;
-                                neq |= (x != o0[col]) | (y != o1[col]) | (z != o2[col]);                       // set_if_neq
+                    if (in_top && depth == lvl) {
+                        bool visited = false;
+                        Aff n = l;
+                        if (depth == 0u) {
+                            if (topo & T_ROOT) {
+                                visited = has_children ? (!static_opt || dirty) : tchanged;
+                                changed = visited;
+                            } else {
+                                const uint32_t pr = R.parent[row];
+                                const uint32_t ps = R.state[pr];
+                                visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
+                                if (visited) {
+                                    n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
+                                    changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);
+                                }
+                            }
+                        } else {
+                            const uint32_t pst = s.pst[sidx][plocal];
+                            const uint32_t pi = off + plocal;
+                            visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                            if (visited) {
+                                n.r0 = affine_mul_row(S.gt0[pi], l); n.r1 = affine_mul_row(S.gt1[pi], l); n.r2 = affine_mul_row(S.gt2[pi], l);
+                                changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);   // set_if_neq
                             }
                         }
+                        if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+                        s.pst[sidx][lane] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
                     }
-                    const uint32_t nb = __ballot_sync(kFull, neq);
-                    const bool row_changed = work && ((nb >> (idx * F)) & ((1u << F) - 1u)) != 0u;
-                    if (row_changed) {
-                        float *o0 = reinterpret_cast<float *>(&S.gt0[li2]), *o1 = reinterpret_cast<float *>(&S.gt1[li2]), *o2 = reinterpret_cast<float *>(&S.gt2[li2]);
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; ++q) {
-                            if (q >= cols) break;
-                            const uint32_t col = part * cols + q;
-                            o0[col] = nv[q][0]; o1[col] = nv[q][1]; o2[col] = nv[q][2];
-                        }
-                    }
-                    if (work && part == 0u) s.pst[sidx][rl] = (uint8_t)((visited ? 1u : 0u) | (row_changed ? 2u : 0u));
-                    any_changed |= nb != 0u;
                 }
-                changed = any_changed;
                 top_changed = __any_sync(kFull, changed);
             }
             __syncwarp();
@@ -988,6 +988,7 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                 Aff g; g.r0 = S.gt0[li]; g.r1 = S.gt1[li]; g.r2 = S.gt2[li];   // own row: written by this thread, the scout, or untouched
                 const bool in_query = active && !(f & F_NO_CPU_CULL);
                 const bool base = in_query && (f & F_INHERITED);
+        const bool rej_base = base;
                 const uint32_t prev = st8 & 1u;
                 const uint32_t lane = lr & 31u;
                 const bool has_aabb = f & F_AABB;
@@ -1013,6 +1014,8 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                     if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
                     if (R.rank != nullptr) rnk = R.rank[row];
                 }
+                // warp-level shortcut: views whose frustum the whole warp's rows are outside of (see warp_view_reject)
+                const uint32_t rejmask = warp_view_reject(cvw, rej_base && do_test, rej_base && !do_test, cx, cy, cz, radius);
                 bool any = false;
                 uint32_t my_ballot = 0;
 #pragma unroll
@@ -1021,6 +1024,7 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                     const uint32_t von = cvw.on[v];
                     if (!(von & 1u)) continue;
                     if (SIMPLE && !(von & 4u)) continue;   // bit2: the view includes the default layer
+                    if (((rejmask >> v) & 1u) && !(von & 2u)) continue;         // every row of this warp is outside this view's frustum
                     bool vis = base;
                     if (!SIMPLE) {
                         vis = vis && layers_intersect(R, cvw, row, v, elayers);
@@ -1310,6 +1314,7 @@ k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restric
             if (CULL) {
                 const bool in_query = active && !(f & F_NO_CPU_CULL);          // Without<NoCpuCulling>
                 const bool base_vis = in_query && (f & F_INHERITED);
+                const bool rej_base = base_vis;
                 const uint32_t prev = st8 & 1u;                                // reset_view_visibility: v = (v&1)<<1
                 const bool has_aabb = f & F_AABB;
                 const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
@@ -1336,6 +1341,8 @@ k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restric
                 }
                 // ballot bits map to mask bits when the occupied lanes hold consecutive rows (and rank == row)
                 const bool ballots = (SIMPLE || R.rank == nullptr) && ((contig_bits >> c) & 1u);
+                // warp-level shortcut: views whose frustum the whole warp's rows are outside of (see warp_view_reject)
+                const uint32_t rejmask = warp_view_reject(cvw, rej_base && do_test, rej_base && !do_test, cx, cy, cz, radius);
                 bool any = false;
                 uint32_t my_ballot = 0;
 #pragma unroll
@@ -1344,6 +1351,7 @@ k_tile_warp(Rows R, const WarpTile *__restrict__ tiles, const uint8_t *__restric
                     const uint32_t von = cvw.on[v];
                     if (!(von & 1u)) continue;                                 // !camera.is_active (grid-uniform)
                     if (SIMPLE && !(von & 4u)) continue;                       // bit2: the view includes the default layer
+                    if (((rejmask >> v) & 1u) && !(von & 2u)) continue;         // every row of this warp is outside this view's frustum
                     bool vis = base_vis;
                     if (!SIMPLE) {
                         vis = vis && layers_intersect(R, cvw, row, v, elayers);
@@ -1458,6 +1466,7 @@ k_cull(Rows R, const __grid_constant__ CullViews cvw, VisibleBufs vb, DevStats *
     }
     const bool in_query = active && !(f & F_NO_CPU_CULL);
     const bool base = in_query && (f & F_INHERITED);
+        const bool rej_base = base;
     const uint32_t prev = st8 & 1u;
     const bool has_aabb = f & F_AABB;
     const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
@@ -1482,6 +1491,8 @@ k_cull(Rows R, const __grid_constant__ CullViews cvw, VisibleBufs vb, DevStats *
         if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
         if (R.rank != nullptr) rnk = R.rank[row];
     }
+    // warp-level shortcut: views whose frustum the whole warp's rows are outside of (see warp_view_reject)
+    const uint32_t rejmask = warp_view_reject(cvw, rej_base && do_test, rej_base && !do_test, cx, cy, cz, radius);
     bool any = false;
     uint32_t my_ballot = 0;
 #pragma unroll
@@ -1490,6 +1501,7 @@ k_cull(Rows R, const __grid_constant__ CullViews cvw, VisibleBufs vb, DevStats *
         const uint32_t von = cvw.on[v];
         if (!(von & 1u)) continue;
         if (SIMPLE && !(von & 4u)) { continue; }
+        if (((rejmask >> v) & 1u) && !(von & 2u)) continue;         // every row of this warp is outside this view's frustum
         bool vis = base;
         if (!SIMPLE) {
             vis = vis && layers_intersect(R, cvw, row, v, elayers);
