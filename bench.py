@@ -844,8 +844,8 @@ def main():
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         algo_bytes = n * ALGO_BYTES_PER_ENTITY + 4 * visible_pairs_rank
         achieved = algo_bytes / (tile_ms_avg * 1e-3) / 1e9
-        tile_kernel = {"c": "k_propagate_cull", "t": "k_propagate_cull_tma", "w": "k_tile_warp"}.get(
-            os.environ.get("B200VIS_TILE_KERNEL", "s")[:1], "k_propagate_cull_scout")
+        tile_kernel = {"c": "k_propagate_cull", "s": "k_propagate_cull_scout", "w": "k_tile_warp"}.get(
+            os.environ.get("B200VIS_TILE_KERNEL", "t")[:1], "k_propagate_cull_tma")
         cfg_out = dict(cfg)
         line = {
             "metric": METRIC, "value": value, "unit": "entities/s", "n_gpus": world, "steps": K, "warmup": W,

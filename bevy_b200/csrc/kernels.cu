@@ -2533,6 +2533,8 @@ k_expand_shadow(ShadowBufs sb, uint32_t n_words, uint32_t n_chunks, uint32_t wor
     __shared__ uint32_t s_base, s_total;
     const uint32_t list = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
     const uint32_t *cc = sb.chunk_count + (size_t)list * chunks_stride;
+    // almost every (list, chunk) is empty (a light reaches a few trees): its mask words are all zero, nothing to read or emit
+    if (chunk != 0 && cc[chunk] == 0) return;
     const uint32_t word = chunk * kChunkWords + t;
     uint32_t *mask = sb.mask + (size_t)list * words_stride;
     uint32_t w = 0;
@@ -2766,11 +2768,11 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 static unsigned long long g_launches = 0;
 unsigned long long kernel_launch_count() { return g_launches; }
 
-static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile, 2 warp per tile, 3 TMA + scout warp
+static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile (default), 2 warp per tile, 3 TMA + scout warp
 static int tile_kernel_choice() {
     if (g_tile_kernel < 0) {
         const char *e = getenv("B200VIS_TILE_KERNEL");
-        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 't') ? 1 : (e && e[0] == 'w') ? 2 : 3;
+        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 'w') ? 2 : (e && e[0] == 's') ? 3 : 1;      // default: TMA-staged, persistent
     }
     return g_tile_kernel;
 }
@@ -2884,11 +2886,11 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
         grid = sms * (per_sm > 0 ? per_sm : 1);    // persistent: one CTA per resident slot
     }
     uint32_t g = n_tiles < (uint32_t)grid ? n_tiles : (uint32_t)grid;
-    // B200VIS_TILES_PER_CTA=k (default 2; 0 = fully persistent) bounds the tiles one CTA processes (grid = n_tiles / k):
+    // B200VIS_TILES_PER_CTA=k (default 0 = fully persistent, measured best in round 2; round 1 used 2) bounds the tiles one CTA processes (grid = n_tiles / k):
     // CTAs then retire continuously, which lets the (higher priority) tail kernels of the previous frame and the
     // all-gather slip in between instead of waiting for the whole persistent grid to drain
     static int tiles_per_cta = -1;
-    if (tiles_per_cta < 0) { const char *e = getenv("B200VIS_TILES_PER_CTA"); tiles_per_cta = e ? atoi(e) : 2; }
+    if (tiles_per_cta < 0) { const char *e = getenv("B200VIS_TILES_PER_CTA"); tiles_per_cta = e ? atoi(e) : 0; }
     if (tiles_per_cta > 0) {
         // round the grid up to whole waves of resident CTAs: the surplus CTAs then take one tile fewer, so the last
         // wave is made of short CTAs instead of a few full-length ones running on a mostly idle chip
@@ -2926,7 +2928,7 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
     if (n_tiles == 0) return;
     const bool prop = stages & 1u, cull = stages & 2u;
     const bool simple = R.layers == nullptr && R.layers_ext == nullptr && R.range == nullptr && R.rank == nullptr;
-    if (tile_kernel_choice() == 3 && prop) {       // TMA-staged tiles + a scout warp one tile ahead (default)
+    if (tile_kernel_choice() == 3 && prop) {       // TMA-staged tiles + a scout warp one tile ahead (B200VIS_TILE_KERNEL=scout)
         static int per_sm = 0;
         if (!per_sm) { const char *e = getenv("B200VIS_SCOUT_CTAS_PER_SM"); per_sm = (e && atoi(e) == 4) ? 4 : 3; }
         if (per_sm == 4) launch_scout_m<4>(st, R, tiles, n_tiles, cvw, vb, stats, cull, simple, static_opt, parity);

@@ -15,13 +15,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 VARIANTS = {
-    "scout": {},                                                                    # default: TMA-staged tiles + scout warp
-    "scout_4ctas": {"B200VIS_SCOUT_CTAS_PER_SM": "4"},
-    "scout_2_tiles": {"B200VIS_SCOUT_TILES_PER_CTA": "2"},
-    "scout_serial": {"B200VIS_PIPELINE": "0"},
+    "default": {},                                                                  # TMA-staged tiles, persistent CTAs
+    "default_serial": {"B200VIS_PIPELINE": "0"},
+    "scout": {"B200VIS_TILE_KERNEL": "scout"},                                      # TMA-staged tiles + a scout warp one tile ahead
+    "scout_4ctas": {"B200VIS_TILE_KERNEL": "scout", "B200VIS_SCOUT_CTAS_PER_SM": "4"},
+    "scout_2_tiles": {"B200VIS_TILE_KERNEL": "scout", "B200VIS_SCOUT_TILES_PER_CTA": "2"},
     "warp": {"B200VIS_TILE_KERNEL": "warp", "B200VIS_WARP_VARIANT": "2p"},          # one warp per tile
     "warp_dynamic": {"B200VIS_TILE_KERNEL": "warp", "B200VIS_WARP_DYNAMIC": "1", "B200VIS_WARP_VARIANT": "4n"},
-    "tma_persistent": {"B200VIS_TILE_KERNEL": "tma", "B200VIS_TILES_PER_CTA": "0"},  # every CTA loops over ~7 tiles
     "tma_2_tiles": {"B200VIS_TILE_KERNEL": "tma", "B200VIS_TILES_PER_CTA": "2"},
     "tma_4_tiles": {"B200VIS_TILE_KERNEL": "tma", "B200VIS_TILES_PER_CTA": "4"},
     "classic": {"B200VIS_TILE_KERNEL": "classic"},
@@ -45,20 +45,20 @@ def test_config3_bench_workload_1m_entities_256_lights_4_views(variant):
     run_case("run_parity(scenes.forest(3922, 8, 256), frames=3)", VARIANTS[variant])
 
 
-@pytest.mark.parametrize("variant", ["scout", "warp", "tma_2_tiles"])
+@pytest.mark.parametrize("variant", ["default", "scout", "warp", "tma_2_tiles"])
 def test_config3_static_frames_and_static_optimizations_off(variant):
     run_case("run_parity(scenes.forest(3922, 8, 256), frames=3, animate=False)\n"
              "run_parity(scenes.forest(1500, 8, 64, seed=5), frames=3, static_opt=False)", VARIANTS[variant])
 
 
-@pytest.mark.parametrize("variant", ["scout", "warp"])
+@pytest.mark.parametrize("variant", ["default", "scout", "warp"])
 def test_config4_many_lights_100k_meshes_1024_lights(variant):
     # 1024 lights = 32 mask words per cluster; range 0.3 as in many_lights.rs:48-86, and a wider range for denser clusters
     run_case("run_parity(scenes.many_cubes(100_000, n_lights=1024, light_range=(0.3, 0.3)), frames=3)\n"
              "run_parity(scenes.many_cubes(100_000, n_lights=1024, light_range=(0.3, 12.0), seed=3), frames=3)", VARIANTS[variant])
 
 
-@pytest.mark.parametrize("variant", ["scout"])
+@pytest.mark.parametrize("variant", ["default", "scout"])
 def test_config5_one_ranks_share_1_25m_rows_512_lights(variant):
     # config #5 on 8 GPUs: 39,220 trees / 8 = 4,903 trees (1,250,265 rows) + 4096 / 8 = 512 lights per rank
     run_case("run_parity(scenes.forest(4903, 8, 512, seed=11), frames=2)", VARIANTS[variant])
