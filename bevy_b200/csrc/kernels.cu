@@ -722,8 +722,9 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
 //
 // ncu on kernel 1b (round 1): the hierarchy walk of a 255-node tree is a chain of 8 levels; levels 0-4 (31 rows) keep ONE
 // warp busy while seven wait at the CTA barrier, and that chain (~6 k cycles) is longer than the tile's parallel work.  Here
-// a ninth warp -- the scout -- runs one tile AHEAD of the 256 workers: it owns the TMA traffic (loads of tile k+1, store of
-// tile k-1: one thread, so the bulk-group waits are its own), decides the tile's mark_dirty_trees state, and walks the tile's
+// two extra warps -- the scouts, alternating tiles -- run up to two tiles AHEAD of the 256 workers (three stages): a scout owns
+// the TMA traffic of its tiles (load of tile k, store of tile k-3 out of the same stage: one thread, so the bulk-group waits are
+// its own), decides the tile's mark_dirty_trees state, and walks the tile's
 // top levels (planner: Tile::top_levels = the leading levels that fit the first 32 rows) in place in the staged tile while
 // the workers are still culling the previous tile.  The workers then start at level K: three level rounds instead of eight
 // for a binary tree, no dirty-phase barrier, no load/store issue on their path.
@@ -732,16 +733,37 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
 //   done[s]  workers -> scout        stage s may be stored and reused
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kFull = 0xFFFFFFFFu;
-constexpr int kScoutThreads = kTileRows + 32;
-struct ScoutSmem {
-    TileStage st[2];
-    unsigned long long full[2], top[2], done[2];
-    uint16_t parent[kTileRows];      // scout only: the ancestor climb of the slow dirty path
-    uint8_t pst[2][kTileRows];       // bit0 visited, bit1 gt changed
-    uint8_t dirty[2][kTileRows];     // TransformTreeChanged, valid when slow[s]
-    uint32_t slow[2];                // a row with an in-tile parent changed: workers read dirty[] instead of their own Changed bit
-    uint32_t any_gt[2];              // a worker row's GlobalTransform changed: the tile must be stored
+constexpr int kScouts = 2;                       // scout warps per CTA: scout x prepares the CTA's tiles with (index % 2) == x
+constexpr int kScoutStages = 3;                  // tile k being culled, tiles k+1 and k+2 being prepared
+constexpr int kScoutThreads = kTileRows + 32 * kScouts;
+struct __align__(128) ScoutStage {               // the columns that must sit in shared memory: the GlobalTransform tile (walked in place,
+    float4 gt0[kWin], gt1[kWin], gt2[kWin];      // stored back in bulk) and the per-row words every phase looks at; Transform and bounds
+    uint32_t topo[kWin];                         // are read once per row and come straight from HBM into registers
+    uint8_t flags[kWin], state[kWin];
 };
+struct ScoutSmem {
+    ScoutStage st[kScoutStages];
+    unsigned long long full[kScoutStages], top[kScoutStages], done[kScoutStages];
+    uint16_t parent[kScouts][kTileRows];         // scouts only: the ancestor climb of the slow dirty path
+    uint8_t pst[kScoutStages][kTileRows];        // bit0 visited, bit1 gt changed
+    uint8_t dirty[kScoutStages][kTileRows];      // TransformTreeChanged, valid when slow[s]
+    uint32_t slow[kScoutStages];                 // a row with an in-tile parent changed: workers read dirty[] instead of their own Changed bit
+    uint32_t any_gt[kScoutStages];               // a worker row's GlobalTransform changed  \ either one: the tile must be stored
+    uint32_t any_top[kScoutStages];              // a row the scout walked changed          /
+};
+__device__ __forceinline__ void issue_scout_loads(const Rows &R, const Tile &t, ScoutStage &S, unsigned long long *bar) {
+    const uint32_t a = t.base & ~15u;
+    const uint32_t cnt = ((t.base - a) + t.n_rows + 15u) & ~15u;
+    mbar_expect_tx(bar, cnt * (48u + 4u + 2u));
+    bulk_g2s(S.gt0, R.gt0 + a, cnt * 16u, bar); bulk_g2s(S.gt1, R.gt1 + a, cnt * 16u, bar); bulk_g2s(S.gt2, R.gt2 + a, cnt * 16u, bar);
+    bulk_g2s(S.topo, R.topo + a, cnt * 4u, bar); bulk_g2s(S.flags, R.flags + a, cnt, bar); bulk_g2s(S.state, R.state + a, cnt, bar);
+}
+__device__ __forceinline__ void issue_scout_store(const Rows &R, const Tile &t, ScoutStage &P) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
+    const uint32_t poff = t.base & 15u, bytes = (uint32_t)t.n_rows * 16u;
+    bulk_s2g(R.gt0 + t.base, P.gt0 + poff, bytes); bulk_s2g(R.gt1 + t.base, P.gt1 + poff, bytes); bulk_s2g(R.gt2 + t.base, P.gt2 + poff, bytes);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -760,24 +782,40 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
     ScoutSmem &s = *reinterpret_cast<ScoutSmem *>(smem_scout);
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.top[i], 1); mbar_init(&s.done[i], 1); }
+        for (int i = 0; i < kScoutStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.top[i], 1); mbar_init(&s.done[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything above overlapped the previous kernel's tail
     uint32_t n_gt_total = 0, n_vv_total = 0;
+    const uint32_t n_mine = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;   // tiles of this CTA
     if (tid >= (uint32_t)kTileRows) {
-        // ================================ scout warp ================================
-        const uint32_t lane = tid - kTileRows;
-        uint32_t it = 0, t = blockIdx.x;
-        Tile prev_tile = {};
-        bool prev_top_changed = false;
-        if (t < n_tiles && lane == 0) issue_tile_loads<true, CULL>(R, tiles[t], s.st[0], &s.full[0]);
-        for (; t < n_tiles; t += gridDim.x, ++it) {
-            const uint32_t sidx = it & 1u, ph = (it >> 1) & 1u;
+        // ================================ scout warps ================================
+        // Scout x prepares tiles x, x+2, x+4, ... of this CTA, two tiles ahead of the workers: per tile it has two of the
+        // workers' tile periods for its ~1.3 k instructions (one scout and a one-tile lead made the workers wait, ncu round 2).
+        const uint32_t lane = tid & 31u, x = (tid - kTileRows) >> 5;
+        for (uint32_t it = x; it < n_mine; it += kScouts) {
+            const uint32_t t = blockIdx.x + it * gridDim.x;
+            const uint32_t sidx = it % kScoutStages, ph = (it / kScoutStages) & 1u;
             const Tile tile = tiles[t];
+            // ---- the stage: tile it-3 lived here; store it once the workers are done with it, then load this tile
+            if (it >= (uint32_t)kScoutStages) {
+                const uint32_t jt = it - kScoutStages;
+                mbar_wait(&s.done[sidx], (jt / kScoutStages) & 1u);
+                if (lane == 0 && (s.any_gt[sidx] | s.any_top[sidx])) issue_scout_store(R, tiles[blockIdx.x + jt * gridDim.x], s.st[sidx]);
+            }
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // this thread's stores have left their stages
+                issue_scout_loads(R, tile, s.st[sidx], &s.full[sidx]);
+            }
+            // the Transform of this lane's row (rows 0..31 hold the tile's top levels): straight from HBM, in flight with the bulk loads
+            const uint32_t K = tile.top_levels;
+            const bool act = lane < tile.n_rows;
+            const uint32_t row = tile.base + lane;
+            float4 tA = make_float4(0, 0, 0, 0), tq = tA; float2 tC = make_float2(0, 0);
+            if (K > 0 && act) { tA = R.trsA[row]; tq = R.trsB[row]; tC = R.trsC[row]; }
             mbar_wait(&s.full[sidx], ph);
-            TileStage &S = s.st[sidx];
+            ScoutStage &S = s.st[sidx];
             const uint32_t off = tile.base & 15u;
             // ---- mark_dirty_trees for the whole tile (systems.rs:111-306): each lane looks at 8 rows
             bool slow = false;
@@ -794,7 +832,7 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                         const uint32_t r = lane * 8u + j;
                         if (r < tile.n_rows) {
                             const uint32_t tp = S.topo[off + r];
-                            s.parent[r] = (uint16_t)((((tp >> 9) & 0x1FFu) > 0u) ? (tp & 0x1FFu) : 0xFFFFu);
+                            s.parent[x][r] = (uint16_t)((((tp >> 9) & 0x1FFu) > 0u) ? (tp & 0x1FFu) : 0xFFFFu);
                             s.dirty[sidx][r] = 0;
                         }
                     }
@@ -805,7 +843,7 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                             uint32_t c = r;
                             while (!s.dirty[sidx][c]) {       // benign race: every writer stores 1, every chain finishes
                                 s.dirty[sidx][c] = 1;
-                                const uint32_t p = s.parent[c];
+                                const uint32_t p = s.parent[x][c];
                                 if (p == 0xFFFFu) break;
                                 c = p;
                             }
@@ -816,11 +854,9 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
             }
             if (lane == 0) s.slow[sidx] = slow ? 1u : 0u;
             // ---- the tile's top levels (depth < K), lane = row
-            const uint32_t K = tile.top_levels;
             bool top_changed = false;
             if (K > 0) {
-                const bool act = lane < tile.n_rows;
-                const uint32_t li = off + lane, row = tile.base + lane;
+                const uint32_t li = off + lane;
                 const uint32_t topo = act ? S.topo[li] : T_DETACHED, f = act ? S.flags[li] : 0u;
                 const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
                 const bool tchanged = f & F_TCHANGED, has_children = topo & T_HAS_CHILDREN;
@@ -830,7 +866,7 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                     if (R.dirty != nullptr) dirty = act && R.dirty[row];
                     else if (slow) dirty = act && s.dirty[sidx][lane];
                 }
-                const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
+                const Aff l = affine_from_trs(tA, tq, tC);
                 if (act && (topo & T_DETACHED)) s.pst[sidx][lane] = 0;     // never visited, and neither is its subtree
                 bool changed = false;
                 for (uint32_t lvl = 0; lvl < K; ++lvl) {
@@ -866,38 +902,16 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                 }
                 top_changed = __any_sync(kFull, changed);
             }
+            if (lane == 0) s.any_top[sidx] = top_changed ? 1u : 0u;
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.top[sidx]);         // the workers may start this tile
-            // ---- the stage the previous tile used: store it once the workers are done with it, then load the next tile
-            const uint32_t tn = t + gridDim.x;
-            if (it >= 1u) {
-                mbar_wait(&s.done[sidx ^ 1u], ((it - 1u) >> 1) & 1u);
-                if (lane == 0 && (prev_top_changed || s.any_gt[sidx ^ 1u])) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
-                    TileStage &P = s.st[sidx ^ 1u];
-                    const uint32_t poff = prev_tile.base & 15u, bytes = (uint32_t)prev_tile.n_rows * 16u;
-                    bulk_s2g(R.gt0 + prev_tile.base, P.gt0 + poff, bytes); bulk_s2g(R.gt1 + prev_tile.base, P.gt1 + poff, bytes);
-                    bulk_s2g(R.gt2 + prev_tile.base, P.gt2 + poff, bytes);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            }
-            if (tn < n_tiles && lane == 0) {
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has left the stage
-                issue_tile_loads<true, CULL>(R, tiles[tn], s.st[sidx ^ 1u], &s.full[sidx ^ 1u]);
-            }
-            prev_tile = tile; prev_top_changed = top_changed;
         }
-        if (it >= 1u) {       // the last tile
-            const uint32_t ls = (it - 1u) & 1u;
-            mbar_wait(&s.done[ls], ((it - 1u) >> 1) & 1u);
-            if (lane == 0 && (prev_top_changed || s.any_gt[ls])) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                TileStage &P = s.st[ls];
-                const uint32_t poff = prev_tile.base & 15u, bytes = (uint32_t)prev_tile.n_rows * 16u;
-                bulk_s2g(R.gt0 + prev_tile.base, P.gt0 + poff, bytes); bulk_s2g(R.gt1 + prev_tile.base, P.gt1 + poff, bytes);
-                bulk_s2g(R.gt2 + prev_tile.base, P.gt2 + poff, bytes);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+        // ---- the CTA's last three tiles are still in their stages: each scout stores the ones with its parity
+        for (uint32_t jt = (n_mine > (uint32_t)kScoutStages ? n_mine - kScoutStages : 0u); jt < n_mine; ++jt) {
+            if ((jt % kScouts) != x) continue;
+            const uint32_t sj = jt % kScoutStages;
+            mbar_wait(&s.done[sj], (jt / kScoutStages) & 1u);
+            if (lane == 0 && (s.any_gt[sj] | s.any_top[sj])) issue_scout_store(R, tiles[blockIdx.x + jt * gridDim.x], s.st[sj]);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
@@ -907,16 +921,19 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
         Tile next_tile = {};
         if (blockIdx.x < n_tiles) next_tile = tiles[blockIdx.x];
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const uint32_t sidx = it & 1u, ph = (it >> 1) & 1u;
+            const uint32_t sidx = it % kScoutStages, ph = (it / kScoutStages) & 1u;
             const Tile tile = next_tile;
             if (t + gridDim.x < n_tiles) next_tile = tiles[t + gridDim.x];    // the next descriptor: in flight during this tile
-            mbar_wait(&s.full[sidx], ph);
-            mbar_wait(&s.top[sidx], ph);
-            TileStage &S = s.st[sidx];
             const uint32_t off = tile.base & 15u;
             const uint32_t li = off + lr;                 // index into the staged window
             const bool active = lr < tile.n_rows;
             const uint32_t row = tile.base + lr;
+            // this row's Transform: read once, so it skips shared memory; requested before the waits below
+            float4 tA = make_float4(0, 0, 0, 0), tq = tA; float2 tC = make_float2(0, 0);
+            if (active) { tA = R.trsA[row]; tq = R.trsB[row]; tC = R.trsC[row]; }
+            mbar_wait(&s.full[sidx], ph);
+            mbar_wait(&s.top[sidx], ph);
+            ScoutStage &S = s.st[sidx];
             const uint32_t f = active ? S.flags[li] : 0u;
             const uint32_t st8 = active ? S.state[li] : 0u;
             float4 bA = make_float4(0, 0, 0, 0); float2 bB = make_float2(0, 0);
@@ -939,7 +956,7 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
             } else {
                 if (active && (topo & T_DETACHED) && has_children) s.pst[sidx][lr] = 0;
                 if (my_level != 0xFFFFFFFFu) {
-                    const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
+                    const Aff l = affine_from_trs(tA, tq, tC);
                     if (my_level == 0u) {                 // only when K == 0: roots, flat entities, rows with a parent in another tile
                         Aff n = l;
                         if (topo & T_ROOT) {
@@ -967,7 +984,7 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
                         if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) __syncwarp(); else workers_sync();
                     }
                     if (my_level == lvl) {
-                        const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
+                        const Aff l = affine_from_trs(tA, tq, tC);
                         const uint32_t pst = s.pst[sidx][plocal];
                         const uint32_t pi = off + plocal;
                         visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
@@ -2429,42 +2446,56 @@ k_shadow_cull(Rows R, ShadowBufs sb, uint32_t words_stride, uint32_t chunks_stri
             s_box[threadIdx.x] = m;
         }
     }
+    // ---- which items can reach this CTA at all: one thread per item tests the block box (nothing else does per-item work)
+    constexpr uint32_t kLiveWords = 8;                               // up to 256 items are pre-tested; further items are always live
+    __shared__ uint32_t s_live[kLiveWords];
+    if (threadIdx.x < kLiveWords) s_live[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < sb.n_lights; i += 256u) {
+        bool live = sb.active[i] != 0u;
+        if (live && !unbounded_any && i < 32u * kLiveWords) {
+            const ShadowLight &sl = sb.lights[i];
+            const float bx0 = s_box[0], by0 = s_box[1], bz0 = s_box[2], bx1 = -s_box[3], by1 = -s_box[4], bz1 = -s_box[5], e1 = -s_box[6];
+            bool skip = !(bx0 <= bx1);                               // no bounded candidate row in this CTA at all
+            if (!skip && sl.kind < 2u) {
+                // light_sphere = (GlobalTransform translation, range) (lib.rs:575-578, 680-683)
+                const float sx = R.gt0[sl.row].w, sy = R.gt1[sl.row].w, sz = R.gt2[sl.row].w;
+                const float dx = fmaxf(fmaxf(bx0 - sx, sx - bx1), 0.0f), dy = fmaxf(fmaxf(by0 - sy, sy - by1), 0.0f);
+                const float dz = fmaxf(fmaxf(bz0 - sz, sz - bz1), 0.0f);
+                const float reach = (sl.range + e1) * 1.001f + 1e-3f;      // d <= r + rr/d <= r + E1 where the exact test passes
+                skip = (dx * dx + dy * dy) + dz * dz > reach * reach;
+            } else if (!skip) {
+                for (int k = 0; k < 6 && !skip; ++k) {               // a half space no point of the box reaches, even grown by E1
+                    if (k == 4) continue;
+                    const float4 n = sl.planes[0][k];
+                    const float m = ((fmaxf(n.x * bx0, n.x * bx1) + fmaxf(n.y * by0, n.y * by1)) + fmaxf(n.z * bz0, n.z * bz1)) + n.w;
+                    skip = m + (e1 * 1.001f + 1e-3f) * ((fabsf(n.x) + fabsf(n.y)) + fabsf(n.z)) < 0.0f;
+                }
+            }
+            live = !skip;
+        }
+        if (live && i < 32u * kLiveWords) atomicOr(&s_live[i >> 5], 1u << (i & 31u));
+    }
+    __syncthreads();
     bool any = false;
-    for (uint32_t s0 = 0; s0 < sb.n_lights; s0 += kShadowChunk) {
-        const uint32_t nl = min((uint32_t)kShadowChunk, sb.n_lights - s0);
+    for (uint32_t i0 = 0; i0 < sb.n_lights; ++i0) {
+        if (i0 < 32u * kLiveWords) {                                 // jump to the next live item (CTA-uniform)
+            uint32_t w = s_live[i0 >> 5] >> (i0 & 31u);
+            if (!w) { i0 |= 31u; continue; }
+            i0 += (uint32_t)__ffs(w) - 1u;
+        } else if (!sb.active[i0]) continue;
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < nl * (sizeof(ShadowLight) / 16); i += 256u)
-            reinterpret_cast<float4 *>(s_light)[i] = reinterpret_cast<const float4 *>(sb.lights + s0)[i];
-        if (threadIdx.x < nl) {
-            const ShadowLight &sl = sb.lights[s0 + threadIdx.x];
-            s_on[threadIdx.x] = sb.active[s0 + threadIdx.x];
-            // light_sphere = (GlobalTransform translation, range) (lib.rs:575-578, 680-683)
-            s_sphere[threadIdx.x] = sl.kind < 2u ? make_float4(R.gt0[sl.row].w, R.gt1[sl.row].w, R.gt2[sl.row].w, sl.range) : make_float4(0, 0, 0, 0);
+        for (uint32_t q = threadIdx.x; q < sizeof(ShadowLight) / 16; q += 256u)
+            reinterpret_cast<float4 *>(s_light)[q] = reinterpret_cast<const float4 *>(sb.lights + i0)[q];
+        if (threadIdx.x == 0) {
+            const ShadowLight &sl = sb.lights[i0];
+            s_sphere[0] = sl.kind < 2u ? make_float4(R.gt0[sl.row].w, R.gt1[sl.row].w, R.gt2[sl.row].w, sl.range) : make_float4(0, 0, 0, 0);
         }
         __syncthreads();
-        for (uint32_t i = 0; i < nl; ++i) {
-            if (!s_on[i]) continue;                                  // warp-uniform
+        {
+            const uint32_t i = 0, s0 = i0;
             const ShadowLight &sl = s_light[i];
             const uint32_t kind = sl.kind, n_faces = kind == 0u ? 6u : 1u;
-            if (!unbounded_any) {                                    // CTA-uniform conservative rejection (see the pre-pass above)
-                const float bx0 = s_box[0], by0 = s_box[1], bz0 = s_box[2], bx1 = -s_box[3], by1 = -s_box[4], bz1 = -s_box[5], e1 = -s_box[6];
-                bool skip = !(bx0 <= bx1);                           // no bounded candidate row in this CTA at all
-                if (!skip && kind < 2u) {
-                    const float4 sp = s_sphere[i];
-                    const float dx = fmaxf(fmaxf(bx0 - sp.x, sp.x - bx1), 0.0f), dy = fmaxf(fmaxf(by0 - sp.y, sp.y - by1), 0.0f);
-                    const float dz = fmaxf(fmaxf(bz0 - sp.z, sp.z - bz1), 0.0f);
-                    const float reach = (sp.w + e1) * 1.001f + 1e-3f;        // d <= r + rr/d <= r + E1 where the exact test passes
-                    skip = (dx * dx + dy * dy) + dz * dz > reach * reach;
-                } else if (!skip) {
-                    for (int k = 0; k < 6 && !skip; ++k) {           // a half space no point of the box reaches, even grown by E1
-                        if (k == 4) continue;
-                        const float4 n = sl.planes[0][k];
-                        const float m = ((fmaxf(n.x * bx0, n.x * bx1) + fmaxf(n.y * by0, n.y * by1)) + fmaxf(n.z * bz0, n.z * bz1)) + n.w;
-                        skip = m + (e1 * 1.001f + 1e-3f) * ((fabsf(n.x) + fabsf(n.y)) + fabsf(n.z)) < 0.0f;
-                    }
-                }
-                if (skip) continue;
-            }
             bool in = eligible && (sl.layers & elayers) != 0ull;
             if (in && ranged) in = sl.range_index >= 0 && sl.range_index < 32 && ((erange >> sl.range_index) & 1u);
             uint32_t faces = kind == 0u ? 0x3Fu : 1u;                // no Aabb: pushed to every list of the item (lib.rs:639-645)
@@ -2531,43 +2562,49 @@ k_expand_shadow(ShadowBufs sb, uint32_t n_words, uint32_t n_chunks, uint32_t wor
                 const uint32_t *__restrict__ row_of_rank) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_base, s_total;
-    const uint32_t list = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
-    const uint32_t *cc = sb.chunk_count + (size_t)list * chunks_stride;
-    // almost every (list, chunk) is empty (a light reaches a few trees): its mask words are all zero, nothing to read or emit
-    if (chunk != 0 && cc[chunk] == 0) return;
-    const uint32_t word = chunk * kChunkWords + t;
-    uint32_t *mask = sb.mask + (size_t)list * words_stride;
-    uint32_t w = 0;
-    if (word < n_words) { w = mask[word]; if (w) mask[word] = 0; }
-    const uint32_t c = __popc(w);
-    uint32_t incl = c;
+    const uint32_t item = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+    const uint32_t n_faces = sb.lights[item].kind == 0u ? 6u : 1u;
+    for (uint32_t face = 0; face < 6u; ++face) {
+        const uint32_t list = item * 6u + face;
+        if (face >= n_faces) { if (chunk == 0 && t == 0) sb.count[list] = 0; continue; }
+        const uint32_t *cc = sb.chunk_count + (size_t)list * chunks_stride;
+        // almost every (list, chunk) is empty (a light reaches a few trees): its mask words are all zero, nothing to read or emit
+        if (chunk != 0 && cc[chunk] == 0) continue;
+        const uint32_t word = chunk * kChunkWords + t;
+        uint32_t *mask = sb.mask + (size_t)list * words_stride;
+        uint32_t w = 0;
+        if (word < n_words) { w = mask[word]; if (w) mask[word] = 0; }
+        const uint32_t c = __popc(w);
+        uint32_t incl = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((t & 31u) >= (uint32_t)o) incl += y; }
-    if ((t & 31u) == 31u) s_warp[t >> 5] = incl;
-    if (t < 32) {
-        uint32_t part = 0, tot = 0;
-        for (uint32_t i = t; i < n_chunks; i += 32) { const uint32_t x = cc[i]; tot += x; if (i < chunk) part += x; }
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((t & 31u) >= (uint32_t)o) incl += y; }
+        __syncthreads();                       // the previous face's readers of s_warp / s_base are done
+        if ((t & 31u) == 31u) s_warp[t >> 5] = incl;
+        if (t < 32) {
+            uint32_t part = 0, tot = 0;
+            for (uint32_t i = t; i < n_chunks; i += 32) { const uint32_t x = cc[i]; tot += x; if (i < chunk) part += x; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xFFFFFFFFu, part, o); tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o); }
-        if (t == 0) { s_base = part; s_total = tot; }
-    }
-    __syncthreads();
-    if (t < 32) {
-        uint32_t x = s_warp[t];
+            for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xFFFFFFFFu, part, o); tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o); }
+            if (t == 0) { s_base = part; s_total = tot; }
+        }
+        __syncthreads();
+        if (t < 32) {
+            uint32_t x = s_warp[t];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
-        s_warp[t] = x;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (t >= (uint32_t)o) x += y; }
+            s_warp[t] = x;
+        }
+        __syncthreads();
+        uint32_t pos = s_base + (incl - c) + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+        uint32_t *out = sb.lists + (size_t)list * sb.list_cap;
+        while (w) {
+            const uint32_t b = __ffs(w) - 1; w &= w - 1;
+            const uint32_t rk = word * 32u + b;
+            if (pos < sb.list_cap) out[pos] = row_of_rank ? row_of_rank[rk] : rk;
+            ++pos;
+        }
+        if (chunk == 0 && t == 0) sb.count[list] = s_total;
     }
-    __syncthreads();
-    uint32_t pos = s_base + (incl - c) + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
-    uint32_t *out = sb.lists + (size_t)list * sb.list_cap;
-    while (w) {
-        const uint32_t b = __ffs(w) - 1; w &= w - 1;
-        const uint32_t rk = word * 32u + b;
-        if (pos < sb.list_cap) out[pos] = row_of_rank ? row_of_rank[rk] : rk;
-        ++pos;
-    }
-    if (chunk == 0 && t == 0) sb.count[list] = s_total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2929,9 +2966,9 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
     const bool prop = stages & 1u, cull = stages & 2u;
     const bool simple = R.layers == nullptr && R.layers_ext == nullptr && R.range == nullptr && R.rank == nullptr;
     if (tile_kernel_choice() == 3 && prop) {       // TMA-staged tiles + a scout warp one tile ahead (B200VIS_TILE_KERNEL=scout)
-        static int per_sm = 0;
-        if (!per_sm) { const char *e = getenv("B200VIS_SCOUT_CTAS_PER_SM"); per_sm = (e && atoi(e) == 4) ? 4 : 3; }
-        if (per_sm == 4) launch_scout_m<4>(st, R, tiles, n_tiles, cvw, vb, stats, cull, simple, static_opt, parity);
+        static int per_sm = 0;      // 3 CTAs per SM at 64 registers (default) or 2 at ~100
+        if (!per_sm) { const char *e = getenv("B200VIS_SCOUT_CTAS_PER_SM"); per_sm = (e && atoi(e) == 2) ? 2 : 3; }
+        if (per_sm == 2) launch_scout_m<2>(st, R, tiles, n_tiles, cvw, vb, stats, cull, simple, static_opt, parity);
         else launch_scout_m<3>(st, R, tiles, n_tiles, cvw, vb, stats, cull, simple, static_opt, parity);
         return;
     }
@@ -3015,7 +3052,7 @@ void launch_shadow_cull(cudaStream_t st, const Rows &R, const ShadowBufs &sb, co
     if (!sb.n_lights || !R.n) return;
     ++g_launches; k_shadow_select<<<cdiv(sb.n_lights, 128), 128, 0, st>>>(sb, R.rank, view_sets, words_stride, n_views);
     ++g_launches; k_shadow_cull<<<cdiv(R.n, 256), 256, 0, st>>>(R, sb, words_stride, chunks_stride, stats, changed_slot);
-    ++g_launches; k_expand_shadow<<<dim3(n_chunks, sb.n_lights * 6), kChunkWords, 0, st>>>(sb, n_words, n_chunks, words_stride, chunks_stride, R.row_of_rank);
+    ++g_launches; k_expand_shadow<<<dim3(n_chunks, sb.n_lights), kChunkWords, 0, st>>>(sb, n_words, n_chunks, words_stride, chunks_stride, R.row_of_rank);
 }
 void launch_pack_cluster_bindings(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, const BindingBufs &bb, uint32_t max_views) {
     if (bb.mode) { ++g_launches; k_pack_cluster_bindings<<<dim3(16, max_views), 256, 0, st>>>(fc, cb, bb); }

@@ -18,7 +18,7 @@ VARIANTS = {
     "default": {},                                                                  # TMA-staged tiles, persistent CTAs
     "default_serial": {"B200VIS_PIPELINE": "0"},
     "scout": {"B200VIS_TILE_KERNEL": "scout"},                                      # TMA-staged tiles + a scout warp one tile ahead
-    "scout_4ctas": {"B200VIS_TILE_KERNEL": "scout", "B200VIS_SCOUT_CTAS_PER_SM": "4"},
+    "scout_2ctas": {"B200VIS_TILE_KERNEL": "scout", "B200VIS_SCOUT_CTAS_PER_SM": "2"},
     "scout_2_tiles": {"B200VIS_TILE_KERNEL": "scout", "B200VIS_SCOUT_TILES_PER_CTA": "2"},
     "warp": {"B200VIS_TILE_KERNEL": "warp", "B200VIS_WARP_VARIANT": "2p"},          # one warp per tile
     "warp_dynamic": {"B200VIS_TILE_KERNEL": "warp", "B200VIS_WARP_DYNAMIC": "1", "B200VIS_WARP_VARIANT": "4n"},
@@ -28,7 +28,7 @@ VARIANTS = {
 }
 
 
-def run_case(code, env, timeout=900):
+def run_case(code, env, timeout=240):
     e = dict(os.environ)
     for k in [k for k in e if k.startswith("B200VIS_")]:
         del e[k]
