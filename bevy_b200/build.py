@@ -36,13 +36,17 @@ def build(force=False, verbose=False):
     if not force and not _newer_than_lib(deps):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    tmp = LIB + ".tmp%d" % os.getpid()     # link into a scratch name, then rename: a reader never sees a half-written library
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
     res = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"], env=env, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building libb200vis.so")
+    os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(res.stderr)
     return LIB

@@ -143,6 +143,8 @@ struct b200vis_ctx {
     b200vis_column_sinks colsink{}; bool have_colsink = false;          // b200vis_set_column_sinks (device aliases below)
     float *col_gt_d = nullptr; uint32_t *col_gt_bits_d = nullptr, *col_vv_bits_d = nullptr; uint8_t *col_vv_d = nullptr;
     uint8_t *d_vv_shadow = nullptr;     // what the host ViewVisibility column holds (0xFF = unknown)
+    bool gt_aos_valid = false;
+    bool step_defers_stats = false;     // inside b200vis_step: the CULL run leaves the sink's stats block to the CLUSTER run
     float *d_gt_aos = nullptr;          // dense write-back: the GlobalTransform column in the host's layout, copied by the DMA engine
     uint32_t last_gt_changed = 0;       // Changed<GlobalTransform> rows of the last frame whose statistics the host has seen
     double step_t[6] = {0, 0, 0, 0, 0, 0}; uint64_t step_n = 0;   // B200VIS_STEP_TRACE: host time per phase of b200vis_step
@@ -470,7 +472,7 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
         }
         for (uint32_t part = 0; part < (cut ? 2u : 1u); ++part) {
             const uint32_t b = (part == 0) ? start : start + cut, e = (cut && part == 0) ? start + cut : end;
-            Tile t; t.base = b; t.n_rows = (uint16_t)(e - b); t.n_levels = 1; t.warp_sync_mask = 0xFFFFFFFFu; t.top_levels = 0;
+            Tile t; t.base = b; t.n_rows = (uint16_t)(e - b); t.n_levels = 1; t.warp_sync_mask = 0xFFFFFFFFu; t.top_levels = 0; t.lvl_warps = 0;
             for (uint32_t r = b; r < e; ++r) tile_of[r] = (uint32_t)tiles.size();
             tiles.push_back(t);
         }
@@ -516,6 +518,24 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
             if (cap_env < 0) { const char *e = getenv("B200VIS_TOP_LEVELS_CAP"); cap_env = e ? atoi(e) : 255; }
             if (K > (uint32_t)cap_env) K = (uint32_t)cap_env;
             t.top_levels = (t.n_levels > 1) ? K : 0u;       // flat tiles have nothing to walk ahead
+        }
+    }
+    {   // lvl_warps: which warps meet at which level hand-over (named barriers, k_propagate_cull_tma)
+        static int level_sync = -1;     // B200VIS_LEVEL_SYNC=cta: keep the CTA-wide level barriers (A/B switch)
+        if (level_sync < 0) { const char *e = getenv("B200VIS_LEVEL_SYNC"); level_sync = (e && e[0] == 'c') ? 0 : 1; }
+        for (size_t ti = 0; level_sync && ti < tiles.size(); ++ti) {
+            Tile &t = tiles[ti];
+            if (t.n_levels < 2 || t.n_levels > 8) continue;      // seven barrier ids per tile parity (levels 1..7)
+            uint32_t lv[kTileRows / 32] = {};          // per warp: bit l = the warp holds a (non-detached) row of in-tile depth l
+            for (uint32_t r = t.base; r < t.base + t.n_rows; ++r)
+                if (!(topo[r] & T_DETACHED)) lv[(r - t.base) >> 5] |= 1u << ldepth[r];
+            unsigned long long packed = 0;
+            for (uint32_t l = 1; l < t.n_levels; ++l) {
+                unsigned long long c = 0;
+                for (uint32_t w = 0; w < (uint32_t)kTileRows / 32u; ++w) c += ((lv[w] >> (l - 1)) & 3u) ? 1u : 0u;
+                packed |= c << (4u * l);
+            }
+            t.lvl_warps = packed;
         }
     }
     // ---- warp work items: schedule, parent slots, wtopo ------------------------------------------------------------
@@ -620,7 +640,7 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     std::vector<uint32_t> &topo = plan.topo; std::vector<Tile> &tiles = plan.tiles;
     std::vector<uint32_t> &pass_begin = plan.pass_begin, &pass_small = plan.pass_small;
     if (tiles.size() > ctx->tiles_cap) {
-        void *old[] = {ctx->d_layers_ext, ctx->d_vv_shadow, ctx->d_gt_aos, ctx->d_tiles, ctx->d_wtiles, ctx->d_sched};
+        void *old[] = {ctx->d_tiles, ctx->d_wtiles, ctx->d_sched};
         for (void *q : old) if (q) cudaFree(q);
         ctx->d_tiles = nullptr; ctx->d_wtiles = nullptr; ctx->d_sched = nullptr; ctx->tiles_cap = (uint32_t)tiles.size() + 1024;
         CU(dalloc(&ctx->d_tiles, ctx->tiles_cap));
@@ -663,6 +683,7 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     CU(cudaMemset(ctx->d_slab, 0, ctx->slab_bytes));
     if (ctx->diff.prev) CU(cudaMemset(ctx->diff.prev, 0, (size_t)ctx->vis.words_stride * ctx->cfg.max_views * 4));   // ranks changed: old list = empty
     ctx->topology_set = true;
+    ctx->gt_aos_valid = false;
     return B200VIS_OK;
 }
 
@@ -1377,7 +1398,8 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         launch_cluster_lists(tail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if ((stages & B200VIS_STAGE_CLUSTER_LISTS) && ctx->bind.mode)
         launch_pack_cluster_bindings(tail, fc, cl, ctx->bind, ctx->cfg.max_views);
-    if (ctx->have_sink && (do_cull || (stages & B200VIS_STAGE_CLUSTER_LISTS)))
+    // (b200vis_step with clusters runs CLUSTER right behind PROPAGATE|CULL: that run publishes the stats block once for both)
+    if (ctx->have_sink && (do_cull || (stages & B200VIS_STAGE_CLUSTER_LISTS)) && !(ctx->step_defers_stats && !(stages & B200VIS_STAGE_CLUSTER_LISTS)))
         launch_publish_clusters(tail, fc, cl, (stages & B200VIS_STAGE_CLUSTER_LISTS) ? ctx->sink_off_d : nullptr, ctx->sink_idx_d,
                                 ctx->sink.cluster_capacity, ctx->d_stats, ctx->sink_stats_d, do_cull ? cslot : (frame + 2u) % 3u, frame + (do_cull ? 1u : 0u), ctx->cfg.max_views);
     if (pe) CU(cudaEventRecord(pe[4], tail));
@@ -1836,6 +1858,7 @@ extern "C" int32_t b200vis_set_column_sinks(b200vis_ctx *ctx, const b200vis_colu
     CU(cudaMemset(ctx->d_vv_shadow, 0xFF, N + 32));      // the host column's contents are unknown: the first write-back sends all
     ctx->colsink = *sinks;
     ctx->have_colsink = true;
+    ctx->gt_aos_valid = false;
     return B200VIS_OK;
 }
 extern "C" int32_t b200vis_writeback_columns_ex(b200vis_ctx *ctx, uint32_t which);
@@ -1853,12 +1876,19 @@ extern "C" int32_t b200vis_writeback_columns_ex(b200vis_ctx *ctx, uint32_t which
         // most rows changed last frame (and will again): repack the whole column on the device (HBM speed) and let the copy
         // engine move it -- unchanged rows are rewritten with the bytes the host already holds.  Sparse frames take the
         // scatter kernel below instead (it touches only the changed rows).
+        // (the staging copy starts as the device column in the host's layout, so that rows the scatter kernel skips -- unchanged
+        // ones -- still carry the bytes the host holds)
         const uint32_t stride = ctx->colsink.gt_stride_floats;
-        if (!ctx->d_gt_aos) CU(dalloc(&ctx->d_gt_aos, (size_t)ctx->cfg.max_entities * 16));
-        launch_pack_gt(ctx->stream, ctx->rows, 0, ctx->n, ctx->d_gt_aos, stride);
+        if (!ctx->d_gt_aos) { CU(dalloc(&ctx->d_gt_aos, (size_t)ctx->cfg.max_entities * 16)); ctx->gt_aos_valid = false; }
+        if (!ctx->gt_aos_valid) { launch_pack_gt(ctx->stream, ctx->rows, 0, ctx->n, ctx->d_gt_aos, stride); ctx->gt_aos_valid = true; }
+        // the same kernel as the sparse path (512-byte contiguous stores through shared memory), aimed at HBM instead of PCIe
+        launch_writeback_columns(ctx->stream, ctx->rows, ctx->d_gt_aos, stride, wgt ? ctx->col_gt_bits_d : nullptr,
+                                 wvv ? ctx->col_vv_d : nullptr, wvv ? ctx->col_vv_bits_d : nullptr, ctx->d_vv_shadow);
         CU(cudaMemcpyAsync(ctx->colsink.global_transforms, ctx->d_gt_aos, (size_t)ctx->n * stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        gt_sink = nullptr;
+        CU(cudaGetLastError());
+        return B200VIS_OK;
     }
+    if (gt_sink) ctx->gt_aos_valid = false;   // rows written straight to the host bypass the staging copy: it is stale from here on
     launch_writeback_columns(ctx->stream, ctx->rows, gt_sink, ctx->colsink.gt_stride_floats, wgt ? ctx->col_gt_bits_d : nullptr,
                              wvv ? ctx->col_vv_d : nullptr, wvv ? ctx->col_vv_bits_d : nullptr, ctx->d_vv_shadow);
     CU(cudaGetLastError());
@@ -1919,7 +1949,10 @@ extern "C" int32_t b200vis_step(b200vis_ctx *ctx, uint32_t n_changed, const uint
     for (uint32_t v = 0; v < n_cameras; ++v)
         if ((rc = b200vis_update_camera(ctx, v, &cameras[v], nullptr, nullptr, nullptr))) return rc;
     lap(1);
-    if ((rc = b200vis_run(ctx, B200VIS_STAGE_PROPAGATE | B200VIS_STAGE_CULL))) return rc;
+    ctx->step_defers_stats = clusters;
+    rc = b200vis_run(ctx, B200VIS_STAGE_PROPAGATE | B200VIS_STAGE_CULL);
+    ctx->step_defers_stats = false;
+    if (rc) return rc;
     if ((flags & B200VIS_STEP_WRITEBACK) && (rc = b200vis_writeback_columns(ctx))) return rc;
     lap(2);
     if (clusters) {

@@ -28,6 +28,10 @@ struct Tile {               // one CTA's work: a contiguous, (mostly) hierarchy-
                              //   so __syncwarp orders the shared-memory hand-over instead of a CTA barrier
     uint32_t top_levels;     // K: every row of in-tile depth < K is one of the tile's first 32 rows (a BFS-ordered tree: its top
                              //   5 levels), so ONE warp can walk those levels on its own (k_propagate_cull_scout), a tile ahead
+    unsigned long long lvl_warps;   // tiles of 2..8 levels: nibble l (1 <= l < n_levels) = how many of the tile's warps hold a row of
+                             //   level l-1 (producers) or level l (consumers).  Level l is then handed over through hardware named
+                             //   barrier l with exactly those warps: consumers bar.sync, pure producers bar.arrive and move on, all
+                             //   other warps never touch it (k_propagate_cull_tma).  0: the kernel walks with CTA-wide barriers
 };
 
 // The same tile as one WARP's work (k_tile_warp): the warp walks the tile in chunks of 32 schedule slots.  The schedule

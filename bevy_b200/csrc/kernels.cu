@@ -402,12 +402,16 @@ struct __align__(128) TileStage {
 };
 struct TmaSmem {
     TileStage st[2];
-    unsigned long long bar[2];
+    unsigned long long bar[2];       // full[s]: the tile's columns have landed in stage s (TMA complete_tx)
+    unsigned long long walked[2];    // walked[s]: all 8 warps are done walking the tile in stage s, hold their rows in registers,
+                                     //            and have looked at the NEXT tile's change flags (climb[s ^ 1] is final)
+    uint32_t climb[2];               // climb[s] == it: a non-root row of the tile of iteration it (stage s) has Changed<Transform>
     uint16_t parent[kTileRows];
     uint8_t pst[kTileRows];      // bit0 visited, bit1 gt changed
     uint8_t dirty[kTileRows];
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -425,6 +429,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// the same wait with a watchdog: a hand-over that never comes (a protocol bug) traps -- the launch fails -- instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_guarded(unsigned long long *bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_cta(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -702,6 +719,326 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         }
     }
     if (lr == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    TT(14);
+    // block-reduce the per-thread tallies (warp shuffle, then one shared-memory atomic per warp)
+    __shared__ uint32_t s_cnt[2];
+    if (lr < 2) s_cnt[lr] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n_gt_total += __shfl_xor_sync(0xFFFFFFFFu, n_gt_total, o); n_vv_total += __shfl_xor_sync(0xFFFFFFFFu, n_vv_total, o); }
+    if ((lr & 31u) == 0) { if (n_gt_total) atomicAdd(&s_cnt[0], n_gt_total); if (n_vv_total) atomicAdd(&s_cnt[1], n_vv_total); }
+    __syncthreads();
+    if (lr == 0) {
+        if (s_cnt[0]) atomicAdd(&stats->changed[parity][0], s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&stats->changed[parity][1], s_cnt[1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 1f (B200VIS_TILE_KERNEL=flow): the TMA-staged pass WITHOUT a CTA-wide barrier between tiles, per-warp level hand-overs
+// through named barriers, GlobalTransforms stored straight from registers.  Parity-clean, measured slower than kernel 1b
+// (DESIGN.md section 7): kept selectable as the record of that experiment.
+// ------------------------------------------------------------------------------------------
+template <bool PROP, bool CULL, bool SIMPLE>
+__global__ void __launch_bounds__(kTileRows, 4)
+k_propagate_cull_flow(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, const __grid_constant__ CullViews cvw,
+                     VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TmaSmem &s = *reinterpret_cast<TmaSmem *>(smem_raw);
+    const uint32_t lr = threadIdx.x;
+    if (lr == 0) {
+        mbar_init(&s.bar[0], 1); mbar_init(&s.bar[1], 1);
+        mbar_init(&s.walked[0], kTileRows / 32); mbar_init(&s.walked[1], kTileRows / 32);
+        s.climb[0] = 0; s.climb[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // launched with programmatic stream serialization: everything above overlapped the previous kernel's tail
+    TT(0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    TT(1);
+    // ---- Tile FLOW --------------------------------------------------------------------------------------------------------
+    // A tile's hierarchy walk is a chain of its levels; the cull that follows is wide.  There is NO CTA-wide barrier between
+    // tiles: a warp that has walked its rows of tile k takes them into registers, looks at tile k+1's change flags
+    // (mark_dirty_trees: does anything have to climb?), arrives on walked[stage] and culls; whoever is done culling goes on to
+    // tile k+1 and starts its walk as soon as walked[stage of k] completes -- that is, when the LAST warp has left tile k's
+    // walk, while those last (leaf-level) warps are still culling.  So the chain of tile k+1 runs under the cull of tile k, in
+    // the same CTA, and the SM always has wide work to issue.  Hand-overs:
+    //   full[s]    TMA -> all       tile landed in stage s                       (loads issued one tile ahead by thread 0)
+    //   walked[s]  8 warps -> all   stage s free, pst/parent/dirty free, climb[s ^ 1] final
+    //   named barriers 1..7 (even tiles) / 8..14 (odd tiles): the level hand-overs inside a walk (Tile::lvl_warps)
+    // A warp is never more than one tile ahead of another (it needs walked[] of the tile before), which is what makes two
+    // stages, one pst array and two barrier-id sets enough.
+    uint32_t t = blockIdx.x;
+    if (lr == 0 && t < n_tiles) issue_tile_loads<PROP, CULL>(R, tiles[t], s.st[0], &s.bar[0]);
+    uint32_t n_gt_total = 0, n_vv_total = 0;
+    const bool scan_flags = PROP && static_opt && R.dirty == nullptr;     // in-tile mark_dirty_trees (single-pass plans)
+    for (uint32_t it = 0; t < n_tiles; t += gridDim.x, ++it) {
+        const uint32_t sidx = it & 1u;
+        const Tile tile = tiles[t];
+        const uint32_t tn = t + gridDim.x;
+        const bool has_next = tn < n_tiles;
+        // the previous tile (other stage) is walked by everybody: its stage, the pst/parent/dirty arrays and this tile's climb
+        // flag are ours now
+        if (it > 0) mbar_wait_guarded(&s.walked[sidx ^ 1u], ((it - 1u) >> 1) & 1u);
+        if (lr == 0 && has_next) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage's old generic accesses -> async proxy
+            issue_tile_loads<PROP, CULL>(R, tiles[tn], s.st[sidx ^ 1u], &s.bar[sidx ^ 1u]);
+        }
+        mbar_wait_guarded(&s.bar[sidx], (it >> 1) & 1u);
+        if (it == 1) { TT(2); }
+        TileStage &S = s.st[sidx];
+        const uint32_t off = tile.base & 15u;
+        const uint32_t li = off + lr;                 // index into the staged window
+        const bool active = lr < tile.n_rows;
+        const uint32_t row = tile.base + lr;
+        const uint32_t f = active ? S.flags[li] : 0u;
+        const uint32_t st8 = active ? S.state[li] : 0u;
+        // bounds are only needed after the hierarchy walk (keeping them out of the staged window lets a fourth CTA fit in
+        // shared memory, loading them late keeps six registers free during the walk): start them towards L2 now
+        if (CULL && active) { prefetch_l2(R.bndA + row); if ((lr & 1u) == 0) prefetch_l2(R.bndB + row); }
+        const uint32_t topo = (PROP && active) ? S.topo[li] : T_DETACHED;
+        const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
+        const bool tchanged = PROP && (f & F_TCHANGED);
+        // mark_dirty_trees: only when a non-root row of the tile changed does anything have to climb; otherwise every row's
+        // TransformTreeChanged bit equals its own Changed<Transform> bit.  The first tile asks the CTA; later tiles were looked
+        // at by every warp on its way out of the previous walk.
+        bool climb = false;
+        if (scan_flags && tile.n_levels > 1) climb = (it == 0) ? (__syncthreads_or(tchanged && depth > 0) != 0) : (s.climb[sidx] == it);
+
+        bool visited = false, changed = false;
+        if (PROP) {
+            const bool has_children = topo & T_HAS_CHILDREN;
+            bool dirty = tchanged;
+            if (static_opt && R.dirty != nullptr) {
+                dirty = active && R.dirty[row];
+            } else if (climb) {
+                s.parent[lr] = (uint16_t)((depth > 0) ? plocal : 0xFFFFu);
+                s.dirty[lr] = 0;
+                __syncthreads();
+                if (active && tchanged) {
+                    uint32_t c = lr;
+                    while (!s.dirty[c]) {
+                        s.dirty[c] = 1;
+                        const uint32_t p = s.parent[c];
+                        if (p == 0xFFFFu) break;
+                        c = p;
+                    }
+                }
+                __syncthreads();
+                dirty = s.dirty[lr];
+            }
+            if (it == 1) { TT(3); }    // dirty phase done
+            const Aff l = affine_from_trs(S.trsA[li], S.trsB[li], S.trsC[li]);
+            const uint32_t my_level = (active && !(topo & T_DETACHED)) ? depth : 0xFFFFFFFFu;
+            if (active && (topo & T_DETACHED) && has_children) s.pst[lr] = 0;
+            // set_if_neq, in place in the staged tile (where a row's in-tile children read it)
+            auto commit = [&](const Aff &n) {
+                changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);
+                if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+            };
+            if (my_level == 0) {
+                if (topo & T_ROOT) {
+                    visited = has_children ? (!static_opt || dirty) : tchanged;
+                    changed = visited;
+                    // roots are written without a compare (systems.rs: `*gt = GlobalTransform::from(*t)`)
+                    if (changed) { S.gt0[li] = l.r0; S.gt1[li] = l.r1; S.gt2[li] = l.r2; }
+                } else {
+                    const uint32_t pr = R.parent[row];
+                    const uint32_t ps = R.state[pr];
+                    visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
+                    if (visited) {
+                        Aff n;
+                        n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
+                        commit(n);
+                    }
+                }
+                if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+            }
+            if (it == 1) { TT(4); }    // local affine + level 0 done
+            // one level of the walk for this thread's row: the parent's rows are the tile's own (in-place) GlobalTransform entries
+            auto walk_row = [&]() {
+                const uint32_t pst = s.pst[plocal];
+                const uint32_t pi = off + plocal;
+                visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                if (visited) {
+                    Aff n;
+                    n.r0 = affine_mul_row(S.gt0[pi], l); n.r1 = affine_mul_row(S.gt1[pi], l); n.r2 = affine_mul_row(S.gt2[pi], l);
+                    commit(n);
+                }
+                if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+            };
+            if (tile.lvl_warps != 0ull) {
+                // Per-warp level schedule (2..8 levels).  A warp only takes part in the hand-over of the levels its own rows
+                // produce (level l-1) or consume (level l), through hardware named barrier l with exactly the warps the planner
+                // counted (Tile::lvl_warps): consumers bar.sync, pure producers bar.arrive and go on.  The warps that hold a
+                // tree's upper levels are thus culling while the chain is still running down the lower ones, a leaf warp waits
+                // once instead of once per level, and nobody pays the loop for levels that are not theirs.
+                const uint32_t lmask = __reduce_or_sync(0xFFFFFFFFu, my_level < 16u ? (1u << my_level) : 0u);
+                uint32_t need = (lmask | (lmask << 1)) & ((1u << tile.n_levels) - 2u);
+                while (need) {
+                    const uint32_t lvl = (uint32_t)__ffs((int)need) - 1u;
+                    need &= need - 1u;
+                    const bool consumer = (lmask >> lvl) & 1u;
+                    if ((tile.warp_sync_mask >> lvl) & 1u) {       // every edge into this level stays inside a warp
+                        if (!consumer) continue;
+                        __syncwarp();
+                    } else {
+                        const uint32_t cnt = ((uint32_t)(tile.lvl_warps >> (4u * lvl)) & 15u) * 32u;
+                        const uint32_t id = lvl + sidx * 7u;        // levels 1..7; two id sets: a warp may be one tile ahead
+                        if (!consumer) {
+                            __threadfence_block();
+                            asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(cnt) : "memory");
+                            continue;
+                        }
+                        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(cnt) : "memory");
+                    }
+                    if (my_level == lvl) walk_row();
+                }
+            } else {
+                for (uint32_t lvl = 1; lvl < tile.n_levels; ++lvl) {
+                    if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) __syncwarp(); else __syncthreads();
+                    if (my_level == lvl) walk_row();
+                    if (it == 1 && lvl <= 7) { TT(4 + lvl); }   // thread 0 after the level's barrier and (for level-lvl rows) work
+                }
+            }
+            if (active && tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
+        }
+        if (it == 1) { TT(12); }   // walk done
+        // bounds: plain coalesced loads (keeping them out of the staged window lets a fourth CTA fit in shared memory)
+        float4 bA = make_float4(0, 0, 0, 0); float2 bB = make_float2(0, 0);
+        if (CULL && active) { bA = R.bndA[row]; bB = R.bndB[row]; }
+        uint32_t out = st8 & (S_VV | S_HAS_CLASS);
+        if (PROP) out |= (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
+        else out |= st8 & (S_GT_CHANGED | S_VISITED);
+
+        // on the way out of the walk: the next tile's change flags (it landed while this one was walked) ...
+        if (scan_flags && has_next) {
+            const Tile nt = tiles[tn];
+            if (nt.n_levels > 1) {
+                mbar_wait_guarded(&s.bar[sidx ^ 1u], ((it + 1u) >> 1) & 1u);
+                const TileStage &N = s.st[sidx ^ 1u];
+                const uint32_t nli = (nt.base & 15u) + lr;
+                const bool hit = lr < nt.n_rows && (N.flags[nli] & F_TCHANGED) && ((N.topo[nli] >> 9) & 0x1FFu) != 0u && !(N.topo[nli] & T_DETACHED);
+                if (__any_sync(0xFFFFFFFFu, hit) && (lr & 31u) == 0) s.climb[sidx ^ 1u] = it + 1u;     // stamped with the tile's iteration: never cleared
+            }
+        }
+        // ... then the own row -- written by this thread or untouched -- into registers (a changed matrix goes to HBM straight
+        // from them: three coalesced 512-byte stores per warp), and walked[stage]: this warp is done with the staged tile
+        Aff g; g.r0 = S.gt0[li]; g.r1 = S.gt1[li]; g.r2 = S.gt2[li];
+        if (PROP && changed) { R.gt0[row] = g.r0; R.gt1[row] = g.r1; R.gt2[row] = g.r2; }
+        __syncwarp();
+        if ((lr & 31u) == 0) mbar_arrive_cta(&s.walked[sidx]);
+        bool vv_changed = false;
+        if (CULL) {
+            const bool in_query = active && !(f & F_NO_CPU_CULL);
+            const bool base = in_query && (f & F_INHERITED);
+            const bool rej_base = base;
+            const uint32_t prev = st8 & 1u;
+            const uint32_t lane = lr & 31u;
+            const bool has_aabb = f & F_AABB;
+            const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
+            float cx, cy, cz, radius;
+            const float hx = bA.w, hy = bB.x, hz = bB.y;
+            if (has_aabb) {
+                cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;
+                cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
+                cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+                const float vx = (g.r0.x * hx + g.r0.y * hy) + g.r0.z * hz;
+                const float vy = (g.r1.x * hx + g.r1.y * hy) + g.r1.z * hz;
+                const float vz = (g.r2.x * hx + g.r2.y * hy) + g.r2.z * hz;
+                radius = sqrtf((vx * vx + vy * vy) + vz * vz);
+            } else {
+                const bool from_gt = f & F_SPHERE_GT;
+                cx = from_gt ? g.r0.w : bA.x; cy = from_gt ? g.r1.w : bA.y; cz = from_gt ? g.r2.w : bA.z;
+                radius = bA.w;
+            }
+            unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
+            if (!SIMPLE && active) {
+                if (R.layers != nullptr) elayers = R.layers[row];
+                if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
+                if (R.rank != nullptr) rnk = R.rank[row];
+            }
+            // warp-level shortcut: views whose frustum the whole warp's rows are outside of (see warp_view_reject)
+            const uint32_t rejmask = warp_view_reject(cvw, rej_base && do_test, rej_base && !do_test, cx, cy, cz, radius);
+            bool any = false;
+            uint32_t my_ballot = 0;
+#pragma unroll
+            for (uint32_t v = 0; v < kMaxViews; ++v) {
+                if (v >= cvw.n_views) break;
+                const uint32_t von = cvw.on[v];
+                if (!(von & 1u)) continue;
+                if (SIMPLE && !(von & 4u)) continue;   // bit2: the view includes the default layer
+                if (((rejmask >> v) & 1u) && !(von & 2u)) continue;         // every row of this warp is outside this view's frustum
+                bool vis = base;
+                if (!SIMPLE) {
+                    vis = vis && layers_intersect(R, cvw, row, v, elayers);
+                    if ((f & F_RANGE) && R.range != nullptr) {
+                        const int32_t ri = cvw.range_index[v];
+                        vis = vis && ri >= 0 && ((erange >> ri) & 1u);
+                    }
+                }
+                if (do_test && !(von & 2u)) {
+                    const float d0 = plane_dot_point(cvw.planes[v][0], cx, cy, cz), d1 = plane_dot_point(cvw.planes[v][1], cx, cy, cz);
+                    const float d2 = plane_dot_point(cvw.planes[v][2], cx, cy, cz), d3 = plane_dot_point(cvw.planes[v][3], cx, cy, cz);
+                    const float d4 = plane_dot_point(cvw.planes[v][4], cx, cy, cz);
+                    const bool out_s = (d0 + radius <= 0.0f) | (d1 + radius <= 0.0f) | (d2 + radius <= 0.0f) |
+                                       (d3 + radius <= 0.0f) | (d4 + radius <= 0.0f);
+                    vis = vis && !out_s;
+                    if (vis && has_aabb) {
+                        const float d[5] = {d0, d1, d2, d3, d4};
+                        bool out_o = false;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            const float4 n = cvw.planes[v][k];
+                            const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+                            const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+                            const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+                            const float rr = (dx * hx + dy * hy) + dz * hz;
+                            out_o |= (d[k] + rr <= 0.0f);
+                        }
+                        vis = !out_o;
+                    }
+                }
+                any |= vis;
+                const bool listed = vis && (st8 & S_HAS_CLASS);
+                if (SIMPLE || R.rank == nullptr) {
+                    const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
+                    if (lane == v) my_ballot = b;
+                } else if (listed) {
+                    uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
+                    uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
+                    atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+                    atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
+                }
+            }
+            if (my_ballot) {
+                uint32_t *mask = vb.mask + (size_t)lane * vb.words_stride;
+                uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + lane) * vb.chunks_stride;
+                const uint32_t row0 = row - lane, w0 = row0 >> 5, sh = row0 & 31u;
+                const uint32_t lo = my_ballot << sh, hi = sh ? (my_ballot >> (32u - sh)) : 0u;
+                if (lo) { atomicOr(mask + w0, lo); atomicAdd(cc + (w0 / kChunkWords), __popc(lo)); }
+                if (hi) { atomicOr(mask + w0 + 1, hi); atomicAdd(cc + ((w0 + 1) / kChunkWords), __popc(hi)); }
+            }
+            if (in_query) {
+                out = (out & ~S_VV) | (any ? (1u | (prev << 1)) : 0u);
+                vv_changed = (any ? 1u : 0u) != prev;
+                if (vv_changed) out |= S_VV_CHANGED;
+            }
+            // a light row publishes what assign_objects_to_clusters needs of it (GlobalTransform::translation,
+            // ViewVisibility::get) so that the cluster kernels never touch the row arrays again
+            if (R.light_snap != nullptr && (f & F_SPHERE_GT) && active) {
+                const uint32_t ord = R.light_ord[row];     // 0xFFFFFFFF: a sphere-from-GT row that is not a current light
+                if (ord < R.n_lights) R.light_snap[ord] = make_float4(g.r0.w, g.r1.w, g.r2.w, (out & 1u) ? 1.0f : 0.0f);
+            }
+        } else {
+            out |= st8 & S_VV_CHANGED;
+        }
+        if (active && out != st8) R.state[row] = (uint8_t)out;
+        n_gt_total += (PROP && changed) ? 1u : 0u;      // per-thread tallies, reduced once at the end of the kernel
+        n_vv_total += vv_changed ? 1u : 0u;
+        if (it == 1) { TT(13); }   // cull done: no barrier here -- the warp goes on to the next tile's rendezvous
+    }
     TT(14);
     // block-reduce the per-thread tallies (warp shuffle, then one shared-memory atomic per warp)
     __shared__ uint32_t s_cnt[2];
@@ -1149,7 +1486,6 @@ struct __align__(16) WarpSmem {
 // byte c (0..7) of the register pair (w0, w1)
 __device__ __forceinline__ uint32_t sel_byte(uint32_t w0, uint32_t w1, uint32_t c) { return ((c < 4u ? w0 : w1) >> (8u * (c & 3u))) & 0xFFu; }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // PIPE: the next chunk's columns are loaded into registers while the current chunk is culled (needs ~100 registers);
 // !PIPE: they are only prefetched into L2 (no registers), and loaded at the top of their own iteration
 template <bool CULL, bool SIMPLE, int MINB, bool PIPE>
@@ -2805,15 +3141,15 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 static unsigned long long g_launches = 0;
 unsigned long long kernel_launch_count() { return g_launches; }
 
-static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile (default), 2 warp per tile, 3 TMA + scout warp
+static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile (default), 2 warp per tile, 3 TMA + scout warp, 4 TMA flow (no inter-tile barrier)
 static int tile_kernel_choice() {
     if (g_tile_kernel < 0) {
         const char *e = getenv("B200VIS_TILE_KERNEL");
-        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 'w') ? 2 : (e && e[0] == 's') ? 3 : 1;      // default: TMA-staged, persistent
+        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 'w') ? 2 : (e && e[0] == 's') ? 3 : (e && e[0] == 'f') ? 4 : 1;      // default: TMA-staged, persistent
     }
     return g_tile_kernel;
 }
-bool tile_kernel_is_tma() { return tile_kernel_choice() == 1 || tile_kernel_choice() == 3; }
+bool tile_kernel_is_tma() { return tile_kernel_choice() == 1 || tile_kernel_choice() == 3 || tile_kernel_choice() == 4; }
 bool tile_kernel_publishes_light_snapshot() { return tile_kernel_choice() != 0; }
 template <bool C, bool S, int MINB, bool PIPE>
 static void launch_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, const uint8_t *sched, uint32_t n_tiles, const CullViews &cvw,
@@ -2910,16 +3246,16 @@ static void launch_scout_m(cudaStream_t st, const Rows &R, const Tile *tiles, ui
                 else launch_scout<true, false, MINB>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity); }
     else launch_scout<false, true, MINB>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
 }
-template <bool P, bool C, bool S>
+template <bool P, bool C, bool S, bool FLOW>
 static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                        const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity) {
     static int grid = 0;
     if (!grid) {
-        cudaFuncSetAttribute(k_propagate_cull_tma<P, C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem));
+        cudaFuncSetAttribute((FLOW ? k_propagate_cull_flow<P, C, S> : k_propagate_cull_tma<P, C, S>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem));
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate_cull_tma<P, C, S>, kTileRows, sizeof(TmaSmem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (FLOW ? k_propagate_cull_flow<P, C, S> : k_propagate_cull_tma<P, C, S>), kTileRows, sizeof(TmaSmem));
         grid = sms * (per_sm > 0 ? per_sm : 1);    // persistent: one CTA per resident slot
     }
     uint32_t g = n_tiles < (uint32_t)grid ? n_tiles : (uint32_t)grid;
@@ -2946,7 +3282,7 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    ++g_launches; cudaLaunchKernelEx(&cfg, k_propagate_cull_tma<P, C, S>, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
+    ++g_launches; cudaLaunchKernelEx(&cfg, (FLOW ? k_propagate_cull_flow<P, C, S> : k_propagate_cull_tma<P, C, S>), R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
 }
 // tiles of <= 32 rows (the tops of split deep tiles): the classic kernel with one warp per tile, 16 CTAs per SM
 void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
@@ -2972,8 +3308,9 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
         else launch_scout_m<3>(st, R, tiles, n_tiles, cvw, vb, stats, cull, simple, static_opt, parity);
         return;
     }
-    if (tile_kernel_choice() == 1 || tile_kernel_choice() == 3) {
-#define B200VIS_LAUNCH_TMA(P, C, S) launch_tma<P, C, S>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity)
+    if (tile_kernel_choice() == 1 || tile_kernel_choice() == 3 || tile_kernel_choice() == 4) {
+#define B200VIS_LAUNCH_TMA(P, C, S) do { if (tile_kernel_choice() == 4) launch_tma<P, C, S, true>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity); \
+                                         else launch_tma<P, C, S, false>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity); } while (0)
         if (prop && cull) { if (simple) B200VIS_LAUNCH_TMA(true, true, true); else B200VIS_LAUNCH_TMA(true, true, false); }
         else if (prop) B200VIS_LAUNCH_TMA(true, false, true);
         else if (cull) { if (simple) B200VIS_LAUNCH_TMA(false, true, true); else B200VIS_LAUNCH_TMA(false, true, false); }

@@ -25,6 +25,8 @@ VARIANTS = {
     "tma_2_tiles": {"B200VIS_TILE_KERNEL": "tma", "B200VIS_TILES_PER_CTA": "2"},
     "tma_4_tiles": {"B200VIS_TILE_KERNEL": "tma", "B200VIS_TILES_PER_CTA": "4"},
     "classic": {"B200VIS_TILE_KERNEL": "classic"},
+    "flow": {"B200VIS_TILE_KERNEL": "flow"},                                        # no CTA barrier between tiles, named level barriers
+    "flow_cta_levels": {"B200VIS_TILE_KERNEL": "flow", "B200VIS_LEVEL_SYNC": "cta"},
 }
 
 
@@ -45,7 +47,7 @@ def test_config3_bench_workload_1m_entities_256_lights_4_views(variant):
     run_case("run_parity(scenes.forest(3922, 8, 256), frames=3)", VARIANTS[variant])
 
 
-@pytest.mark.parametrize("variant", ["default", "scout", "warp", "tma_2_tiles"])
+@pytest.mark.parametrize("variant", ["default", "scout", "warp", "tma_2_tiles", "flow"])
 def test_config3_static_frames_and_static_optimizations_off(variant):
     run_case("run_parity(scenes.forest(3922, 8, 256), frames=3, animate=False)\n"
              "run_parity(scenes.forest(1500, 8, 64, seed=5), frames=3, static_opt=False)", VARIANTS[variant])
