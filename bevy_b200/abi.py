@@ -124,6 +124,7 @@ _SIGNATURES = {
     "b200vis_writeback_columns": (C.c_int32, [_vp]),
     "b200vis_writeback_columns_ex": (C.c_int32, [_vp, C.c_uint32]),
     "b200vis_host_plan_summary": (C.c_int32, [C.c_uint32, _vp, _P(C.c_uint32)]),
+    "b200vis_host_tile_plan": (C.c_int32, [C.c_uint32, _vp, C.c_uint32, C.c_uint32, _P(C.c_uint32), _vp, _vp]),
     "b200vis_host_warp_plan": (C.c_int32, [C.c_uint32, _vp, C.c_uint32, C.c_uint32, _P(C.c_uint32), _vp, _vp, _vp, _vp]),
     "b200vis_plan_row_order": (C.c_int32, [C.c_uint32, _vp, _vp]),
     "b200vis_upload_transforms": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
@@ -272,6 +273,23 @@ def host_plan_summary(parent):
     if rc:
         raise B200VisError(rc, load_library().b200vis_last_error(None).decode())
     return tuple(out)
+
+
+def host_tile_plan(parent, tile_rows=0):
+    """The CTA-per-tile plan (b200vis_host_tile_plan): (tile_desc[T,8], topo[n]); desc columns = base, rows, levels,
+    warp_sync_mask, top_levels, lvl_warps lo, lvl_warps hi, pass."""
+    parent = _arr(parent, np.uint32)
+    lib = load_library()
+    nt = C.c_uint32(0)
+    rc = lib.b200vis_host_tile_plan(len(parent), _ptr(parent), tile_rows, 0, C.byref(nt), None, None)
+    if rc:
+        raise B200VisError(rc, "host_tile_plan")
+    T = nt.value
+    desc = np.zeros((T, 8), np.uint32); topo = np.zeros(len(parent), np.uint32)
+    rc = lib.b200vis_host_tile_plan(len(parent), _ptr(parent), tile_rows, T, C.byref(nt), _ptr(desc), _ptr(topo))
+    if rc:
+        raise B200VisError(rc, "host_tile_plan")
+    return desc, topo
 
 
 def host_warp_plan(parent, tile_rows=0):

@@ -526,9 +526,9 @@ static int32_t build_plan(b200vis_ctx *ctx, uint32_t n, const uint32_t *parent, 
         for (size_t ti = 0; level_sync && ti < tiles.size(); ++ti) {
             Tile &t = tiles[ti];
             if (t.n_levels < 2 || t.n_levels > 8) continue;      // seven barrier ids per tile parity (levels 1..7)
-            uint32_t lv[kTileRows / 32] = {};          // per warp: bit l = the warp holds a (non-detached) row of in-tile depth l
-            for (uint32_t r = t.base; r < t.base + t.n_rows; ++r)
-                if (!(topo[r] & T_DETACHED)) lv[(r - t.base) >> 5] |= 1u << ldepth[r];
+            uint32_t lv[kTileRows / 32] = {};          // per warp: bit l = the warp holds a row of in-tile depth l (a detached
+            for (uint32_t r = t.base; r < t.base + t.n_rows; ++r)      // row has depth 0: it publishes "not visited" to its children)
+                lv[(r - t.base) >> 5] |= 1u << ldepth[r];
             unsigned long long packed = 0;
             for (uint32_t l = 1; l < t.n_levels; ++l) {
                 unsigned long long c = 0;
@@ -720,6 +720,28 @@ extern "C" int32_t b200vis_host_warp_plan(uint32_t n, const uint32_t *parent, ui
         memcpy(sched + i * (size_t)kTileRows, plan.sched.data() + (size_t)w.sched * kTileRows, kTileRows);
     }
     if (n) memcpy(wtopo, plan.wtopo.data(), (size_t)n * 4);
+    return B200VIS_OK;
+}
+
+extern "C" int32_t b200vis_host_tile_plan(uint32_t n, const uint32_t *parent, uint32_t tile_rows, uint32_t tiles_capacity, uint32_t *n_tiles,
+                                          uint32_t *tile_desc, uint32_t *topo) {
+    if ((n && !parent) || !n_tiles) return B200VIS_ERR_INVALID_ARG;
+    Plan plan;
+    const int32_t rc = build_plan(nullptr, n, parent, tile_rows ? tile_rows : kTileRows, plan);
+    if (rc) return rc;
+    *n_tiles = (uint32_t)plan.tiles.size();
+    if (!tile_desc) return B200VIS_OK;
+    if (plan.tiles.size() > tiles_capacity || (n && !topo)) return B200VIS_ERR_CAPACITY;
+    std::vector<uint32_t> pass_of(plan.tiles.size(), 0);
+    for (size_t p = 0; p + 1 < plan.pass_begin.size(); ++p)
+        for (uint32_t i = plan.pass_begin[p]; i < plan.pass_begin[p + 1]; ++i) pass_of[i] = (uint32_t)p;
+    for (size_t i = 0; i < plan.tiles.size(); ++i) {
+        const Tile &t = plan.tiles[i];
+        uint32_t *d = tile_desc + i * 8;
+        d[0] = t.base; d[1] = t.n_rows; d[2] = t.n_levels; d[3] = t.warp_sync_mask; d[4] = t.top_levels;
+        d[5] = (uint32_t)t.lvl_warps; d[6] = (uint32_t)(t.lvl_warps >> 32); d[7] = pass_of[i];
+    }
+    if (n) memcpy(topo, plan.topo.data(), (size_t)n * 4);
     return B200VIS_OK;
 }
 

@@ -561,21 +561,52 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
                 if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
             }
             if (it == 1) { TT(4); }    // local affine + level 0 done
-            for (uint32_t lvl = 1; lvl < tile.n_levels; ++lvl) {
-                if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) __syncwarp(); else __syncthreads();
-                if (my_level == lvl) {
-                    const uint32_t pst = s.pst[plocal];
-                    const uint32_t pi = off + plocal;
-                    visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
-                    if (visited) {
-                        Aff n;   // the parent's rows are the tile's own (in-place) GlobalTransform entries
-                        n.r0 = affine_mul_row(S.gt0[pi], l); n.r1 = affine_mul_row(S.gt1[pi], l); n.r2 = affine_mul_row(S.gt2[pi], l);
-                        changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);   // set_if_neq
-                        if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
-                    }
-                    if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+            // one level of the walk for this thread's row: the parent's rows are the tile's own (in-place) GlobalTransform entries
+            auto walk_row = [&]() {
+                const uint32_t pst = s.pst[plocal];
+                const uint32_t pi = off + plocal;
+                visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                if (visited) {
+                    Aff n;
+                    n.r0 = affine_mul_row(S.gt0[pi], l); n.r1 = affine_mul_row(S.gt1[pi], l); n.r2 = affine_mul_row(S.gt2[pi], l);
+                    changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);   // set_if_neq
+                    if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
                 }
-                if (it == 1 && lvl <= 7) { TT(4 + lvl); }   // thread 0 after the level's barrier and (for level-lvl rows) work
+                if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+            };
+            if (tile.lvl_warps != 0ull) {
+                // Per-warp level schedule (2..8 levels).  A warp only takes part in the hand-over of the levels its own rows
+                // produce (level l-1) or consume (level l), through hardware named barrier l with exactly the warps the planner
+                // counted (Tile::lvl_warps): consumers bar.sync, pure producers bar.arrive and go on; a leaf warp waits once
+                // instead of once per level, and nobody pays the loop for levels that are not theirs.  (The tile still ends in a
+                // CTA-wide barrier, so one set of barrier ids is enough here.)
+                // (a detached row takes no part in the walk but publishes pst = 0 for its children: it counts as a level-0 row)
+                const uint32_t lmask = __reduce_or_sync(0xFFFFFFFFu, active ? (1u << (depth & 15u)) : 0u);
+                uint32_t need = (lmask | (lmask << 1)) & ((1u << tile.n_levels) - 2u);
+                while (need) {
+                    const uint32_t lvl = (uint32_t)__ffs((int)need) - 1u;
+                    need &= need - 1u;
+                    const bool consumer = (lmask >> lvl) & 1u;
+                    if ((tile.warp_sync_mask >> lvl) & 1u) {       // every edge into this level stays inside a warp
+                        if (!consumer) continue;
+                        __syncwarp();
+                    } else {
+                        const uint32_t cnt = ((uint32_t)(tile.lvl_warps >> (4u * lvl)) & 15u) * 32u;
+                        if (!consumer) {
+                            __threadfence_block();
+                            asm volatile("bar.arrive %0, %1;" ::"r"(lvl), "r"(cnt) : "memory");
+                            continue;
+                        }
+                        asm volatile("bar.sync %0, %1;" ::"r"(lvl), "r"(cnt) : "memory");
+                    }
+                    if (my_level == lvl) walk_row();
+                }
+            } else {
+                for (uint32_t lvl = 1; lvl < tile.n_levels; ++lvl) {
+                    if (lvl < 32u && ((tile.warp_sync_mask >> lvl) & 1u)) __syncwarp(); else __syncthreads();
+                    if (my_level == lvl) walk_row();
+                    if (it == 1 && lvl <= 7) { TT(4 + lvl); }   // thread 0 after the level's barrier and (for level-lvl rows) work
+                }
             }
             if (active && tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
         }
@@ -794,9 +825,10 @@ k_propagate_cull_flow(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
         const uint32_t row = tile.base + lr;
         const uint32_t f = active ? S.flags[li] : 0u;
         const uint32_t st8 = active ? S.state[li] : 0u;
-        // bounds are only needed after the hierarchy walk (keeping them out of the staged window lets a fourth CTA fit in
-        // shared memory, loading them late keeps six registers free during the walk): start them towards L2 now
-        if (CULL && active) { prefetch_l2(R.bndA + row); if ((lr & 1u) == 0) prefetch_l2(R.bndB + row); }
+        // bounds are only needed after the hierarchy walk: plain coalesced loads issued now, consumed in the cull
+        // (keeping them out of the staged window lets a fourth CTA fit in shared memory)
+        float4 bA = make_float4(0, 0, 0, 0); float2 bB = make_float2(0, 0);
+        if (CULL && active) { bA = R.bndA[row]; bB = R.bndB[row]; }
         const uint32_t topo = (PROP && active) ? S.topo[li] : T_DETACHED;
         const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
         const bool tchanged = PROP && (f & F_TCHANGED);
@@ -874,7 +906,8 @@ k_propagate_cull_flow(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
                 // counted (Tile::lvl_warps): consumers bar.sync, pure producers bar.arrive and go on.  The warps that hold a
                 // tree's upper levels are thus culling while the chain is still running down the lower ones, a leaf warp waits
                 // once instead of once per level, and nobody pays the loop for levels that are not theirs.
-                const uint32_t lmask = __reduce_or_sync(0xFFFFFFFFu, my_level < 16u ? (1u << my_level) : 0u);
+                // (a detached row takes no part in the walk but publishes pst = 0 for its children: it counts as a level-0 row)
+                const uint32_t lmask = __reduce_or_sync(0xFFFFFFFFu, active ? (1u << (depth & 15u)) : 0u);
                 uint32_t need = (lmask | (lmask << 1)) & ((1u << tile.n_levels) - 2u);
                 while (need) {
                     const uint32_t lvl = (uint32_t)__ffs((int)need) - 1u;
@@ -905,9 +938,6 @@ k_propagate_cull_flow(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
             if (active && tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
         }
         if (it == 1) { TT(12); }   // walk done
-        // bounds: plain coalesced loads (keeping them out of the staged window lets a fourth CTA fit in shared memory)
-        float4 bA = make_float4(0, 0, 0, 0); float2 bB = make_float2(0, 0);
-        if (CULL && active) { bA = R.bndA[row]; bB = R.bndB[row]; }
         uint32_t out = st8 & (S_VV | S_HAS_CLASS);
         if (PROP) out |= (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
         else out |= st8 & (S_GT_CHANGED | S_VISITED);

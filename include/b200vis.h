@@ -194,7 +194,14 @@ B200VIS_API int32_t b200vis_plan_row_order(uint32_t n_rows, const uint32_t *pare
 /* What b200vis_set_topology would plan for this hierarchy (no GPU needed): out = { tiles, passes (kernel launches per
  * propagate), deepest in-tile level count, rows whose parent lives in another tile }.  Same error codes. */
 B200VIS_API int32_t b200vis_host_plan_summary(uint32_t n_rows, const uint32_t *parent_row, uint32_t out[4]);
-/* The plan as the default tile kernel sees it (no GPU needed; for tests and tools): one work item per WARP.
+/* The plan as the default tile kernel (one CTA of 8 warps per tile) sees it (no GPU needed; for tests and tools):
+ * tile_desc[i] = { first row, rows, in-tile levels, warp_sync_mask (bit l: every edge into level l stays inside a warp),
+ * top_levels, lvl_warps low word, lvl_warps high word (nibble l = warps that meet at the hand-over of level l; 0 = the
+ * tile is walked with CTA-wide barriers), pass }, topo[row] = parent's local row | in-tile depth << 9 | flags (bits 28-31).
+ * With tile_desc == NULL only *n_tiles is written. */
+B200VIS_API int32_t b200vis_host_tile_plan(uint32_t n_rows, const uint32_t *parent_row, uint32_t tile_rows, uint32_t tiles_capacity,
+                                           uint32_t *n_tiles, uint32_t *tile_desc, uint32_t *topo);
+/* The plan as the warp-per-tile kernel (B200VIS_TILE_KERNEL=warp) sees it (no GPU needed; for tests and tools): one work item per WARP.
  * tile_desc[i] = { first row, rows, chunks | contiguous-chunk bits << 8, pass }, nonroot[i][8] = per chunk the schedule
  * slots holding a row whose parent is in the tile, sched[i][256] = schedule slot -> local row (0xFF = padding, except in
  * a 256-row tile), wtopo[row] = depth | own slot << 8 | parent's slot << 15 | has-slot << 22 | flags (bits 28-31).
