@@ -68,7 +68,10 @@ struct b200vis_ctx {
     // a frame whose tail was started (expand + cluster assign on the side stream) but whose CLUSTER_LISTS stage is
     // still to come in a later b200vis_run call (multi-GPU: the host all-gathers the slabs in between)
     bool tail_open = false; uint32_t open_frame = 0; const FrameConsts *open_fc = nullptr;
-    float4 *d_light_snap = nullptr;     // [3][max_lights]
+    // light blocks [3 frame slots]: float4 snap[cap32] | float range[cap32] | uint64 layers[cap32] (cap32 = cl.max_lights).  The
+    // snap part is what the tile pass fills per frame; with several GPUs the whole block is what one all-gather exchanges
+    uint8_t *d_lrec = nullptr, *d_lrec_all = nullptr; size_t lrec_bytes = 0;
+    float4 *light_snap_slot(uint32_t slot) const { return reinterpret_cast<float4 *>(d_lrec + (size_t)slot * lrec_bytes); }
     uint32_t *d_tag_flag = nullptr;     // 1 if every light row carries its ordinal (k_tag_lights)
     uint32_t *d_light_ord = nullptr;    // [max_entities] light ordinal per row, 0xFFFFFFFF = not a light (rewritten on set_lights)
     bool lights_tag_dirty = true, lights_tagged = false;
@@ -199,7 +202,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     Rows &r = ctx->rows;
     void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
-                   ctx->d_layers_ext, ctx->d_vv_shadow, ctx->d_gt_aos, ctx->d_tiles, ctx->d_wtiles, ctx->d_sched, ctx->d_wtopo, ctx->d_tile_counter, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_light_snap, ctx->d_tag_flag, ctx->d_light_ord,
+                   ctx->d_layers_ext, ctx->d_vv_shadow, ctx->d_gt_aos, ctx->d_tiles, ctx->d_wtiles, ctx->d_sched, ctx->d_wtopo, ctx->d_tile_counter, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_lrec, ctx->d_lrec_all, ctx->d_tag_flag, ctx->d_light_ord,
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->vis.classes, ctx->d_cls, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage,
                    ctx->diff.prev, ctx->diff.words, ctx->diff.chunk, ctx->diff.lists, ctx->diff.count,
@@ -310,7 +313,6 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         CU(cudaMallocHost(&ctx->h_stats, sizeof(DevStats)));
         // lights + clusters
         const size_t Lm = std::max<uint32_t>(cfg->max_lights, 1);
-        CU(dalloc(&ctx->d_light_snap, 3 * Lm));
         CU(dalloc(&ctx->d_tag_flag, 1));
         CU(dalloc(&ctx->d_light_ord, N));
         CU(cudaMemset(ctx->d_light_ord, 0xFF, std::max<size_t>(N, 1) * 4));
@@ -318,6 +320,9 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         ClusterBufs &cl = ctx->cl;
         cl.words = (uint32_t)((Lm + 31) / 32); cl.max_lights = cl.words * 32; cl.world = ctx->cfg.world_size;
         cl.rank = cfg->rank; cl.max_views = (uint32_t)V; cl.index_cap = ctx->cfg.max_cluster_indices;
+        ctx->lrec_bytes = (size_t)cl.max_lights * 28;
+        CU(cudaMalloc(&ctx->d_lrec, 3 * ctx->lrec_bytes)); CU(cudaMemset(ctx->d_lrec, 0, 3 * ctx->lrec_bytes));
+        if (cl.world > 1) { CU(cudaMalloc(&ctx->d_lrec_all, cl.world * ctx->lrec_bytes)); CU(cudaMemset(ctx->d_lrec_all, 0, cl.world * ctx->lrec_bytes)); }
         cl.slab_words = (uint32_t)(V * cl.words * kMaxClusters + kMaxViews);   // bit matrix + per-view farthest_z trailer
         ctx->slab_bytes = (size_t)cl.slab_words * sizeof(uint32_t);
         CU(dalloc(&ctx->d_slab, ctx->slab_bytes / 4));
@@ -966,6 +971,16 @@ extern "C" int32_t b200vis_set_lights(b200vis_ctx *ctx, uint32_t n_lights, const
     ctx->lights.n = n_lights; ctx->lights.row = ctx->d_light_row; ctx->lights.range = ctx->d_light_range;
     ctx->lights.layers = layer_mask ? ctx->d_light_layers : nullptr;
     ctx->lights_tag_dirty = true;
+    {   // the light blocks: stale snapshots out, ranges and layer masks in (rare: the tail of the frame in flight is joined first)
+        const int32_t jrc = join_all(ctx); if (jrc) return jrc;
+        const uint32_t cap = ctx->cl.max_lights;
+        std::vector<uint8_t> blk(ctx->lrec_bytes, 0);
+        float *rg = reinterpret_cast<float *>(blk.data() + (size_t)cap * 16);
+        uint64_t *ly = reinterpret_cast<uint64_t *>(blk.data() + (size_t)cap * 20);
+        for (uint32_t i = 0; i < n_lights; ++i) { rg[i] = range[i]; ly[i] = layer_mask ? layer_mask[i] : 1ull; }
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < 3; ++k) CU(cudaMemcpy(ctx->d_lrec + k * ctx->lrec_bytes, blk.data(), ctx->lrec_bytes, cudaMemcpyHostToDevice));
+    }
     return B200VIS_OK;
 }
 
@@ -1332,7 +1347,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
         for (uint32_t x : ctx->pass_small) any_small |= x != 0;
         tile_snap = ctx->lights_tagged && tile_kernel_publishes_light_snapshot() && !any_small;   // the 32-thread kernel does not publish snapshots
         if (tile_snap) {
-            R.light_snap = ctx->d_light_snap + (size_t)cslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
+            R.light_snap = ctx->light_snap_slot(cslot);
             R.light_ord = ctx->d_light_ord; R.n_lights = ctx->lights.n;
         }
     }
@@ -1359,7 +1374,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     lights.snap = nullptr;
     cudaStream_t tail = st;
     if (pipelined) {
-        lights.snap = ctx->d_light_snap + (size_t)cslot * std::max<uint32_t>(ctx->cfg.max_lights, 1);
+        lights.snap = ctx->light_snap_slot(cslot);
         if (!tile_snap) launch_snapshot_lights(st, R, lights, const_cast<float4 *>(lights.snap));
         if (pe) CU(cudaEventRecord(pe[1], st));
         CU(cudaEventRecord(ctx->ev_tile, st));
@@ -1371,8 +1386,28 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     // the slab push / all-gather are issued before the visible-list expansion (they do not depend on it), and the peers'
     // data travels while this rank expands its lists.
     const bool exchange_first = has_assign && has_lists && cl.world > 1;
-    bool fused_clusters = false;     // single GPU, both cluster stages in this call: one launch does assign + lists
+    // Several GPUs, built-in collective: what travels is the LIGHT RECORD block (28 bytes per light: position + ViewVisibility
+    // from this frame's tile pass, range, layers) instead of the cluster x light bit slabs, and every rank then runs the
+    // one-launch cluster stage over all ranks' lights -- the same kernel, the same ordinals (rank * capacity + local), the same
+    // Clusters feedback on every rank, and a few KB on the wire instead of V x words x 16 KB.  Used whenever the gathered bit
+    // matrix fits the fused kernel's distributed shared memory (<= 6400 lights in all); B200VIS_EXCHANGE_WHAT=slabs (or a host-
+    // driven / peer-store exchange) keeps the slab path.
+    static int records_env = -1;
+    if (records_env < 0) { const char *e = getenv("B200VIS_EXCHANGE_WHAT"); records_env = (e && e[0] == 's') ? 0 : 1; }
+    const bool records = exchange_first && records_env && ctx->nccl_comm && !ctx->p2p_ready && ctx->ext_send == nullptr &&
+                         cluster_fused_fits(cl.world * cl.max_lights);
+    bool fused_clusters = false;     // both cluster stages in this call and all lights at hand: one launch does assign + lists
     auto issue_assign_and_exchange = [&]() -> int32_t {
+        if (records) {
+            if (!(pipelined && ctx->lights.n)) {      // no snapshot was taken with the tile pass: take it now (same stream order)
+                Lights lsnap = ctx->lights;
+                launch_snapshot_lights(tail, R, lsnap, ctx->light_snap_slot(cslot));
+            }
+            const int nrc = g_nccl.AllGather(ctx->d_lrec + (size_t)cslot * ctx->lrec_bytes, ctx->d_lrec_all, ctx->lrec_bytes / 4, kNcclUint32,
+                                             ctx->nccl_comm, tail);
+            if (nrc) return fail(ctx, B200VIS_ERR_CUDA, "ncclAllGather: %s", g_nccl.GetErrorString(nrc));
+            return B200VIS_OK;
+        }
         if (has_assign && has_lists && cl.world == 1 && ctx->ext_send == nullptr && lights.n)
             fused_clusters = launch_cluster_fused(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
         if ((stages & B200VIS_STAGE_CLUSTER_ASSIGN) && !fused_clusters)
@@ -1416,6 +1451,12 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     }
     if (pe) CU(cudaEventRecord(pe[3], tail));
     if (!exchange_first) { const int32_t rc = issue_assign_and_exchange(); if (rc) return rc; }
+    if (records) {
+        Lights lg{};
+        lg.n = cl.world * cl.max_lights; lg.per_rank = cl.max_lights; lg.block_bytes = (uint32_t)ctx->lrec_bytes; lg.blocks = ctx->d_lrec_all;
+        fused_clusters = launch_cluster_fused(tail, R, lg, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+        if (!fused_clusters) return fail(ctx, B200VIS_ERR_CUDA, "run: the cluster kernel could not be launched over the gathered light records");
+    }
     if ((stages & B200VIS_STAGE_CLUSTER_LISTS) && !fused_clusters)
         launch_cluster_lists(tail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if ((stages & B200VIS_STAGE_CLUSTER_LISTS) && ctx->bind.mode)

@@ -161,7 +161,29 @@ struct Lights {
     const uint32_t *row;
     const float *range;
     const uint64_t *layers;  // or nullptr
+    // Several GPUs, light-RECORD exchange: `blocks` holds every rank's light block (gathered), light li = rank * per_rank + j
+    // is entry j of block `rank`.  A block = float4 snap[per_rank] | float range[per_rank] | uint64 layers[per_rank]
+    // (28 bytes per light: what assign_objects_to_clusters needs of a light).  per_rank == 0: the flat arrays above.
+    uint32_t per_rank, block_bytes;
+    const uint8_t *blocks;
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 light_snap_of(const Lights &L, uint32_t li) {
+    if (!L.per_rank) return L.snap[li];
+    const uint32_t r = li / L.per_rank, j = li - r * L.per_rank;
+    return reinterpret_cast<const float4 *>(L.blocks + (size_t)r * L.block_bytes)[j];
+}
+__device__ __forceinline__ float light_range_of(const Lights &L, uint32_t li) {
+    if (!L.per_rank) return L.range[li];
+    const uint32_t r = li / L.per_rank, j = li - r * L.per_rank;
+    return reinterpret_cast<const float *>(L.blocks + (size_t)r * L.block_bytes + (size_t)L.per_rank * 16u)[j];
+}
+__device__ __forceinline__ unsigned long long light_layers_of(const Lights &L, uint32_t li) {
+    if (!L.per_rank) return L.layers ? L.layers[li] : 1ull;
+    const uint32_t r = li / L.per_rank, j = li - r * L.per_rank;
+    return reinterpret_cast<const unsigned long long *>(L.blocks + (size_t)r * L.block_bytes + (size_t)L.per_rank * 20u)[j];
+}
+#endif
 
 struct ClusterBufs {
     uint32_t words;          // mask words per rank = ceil(max_lights/32)

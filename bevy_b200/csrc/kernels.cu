@@ -2370,21 +2370,21 @@ k_cluster_fused(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBuf
     // ---- assign: light li is handled by warp (li / nrank) % 32 of CTA li % nrank
     for (uint32_t li = rank + nrank * warp; li < L.n; li += nrank * (kFusedThreads / 32)) {
         float px, py, pz;
-        if (L.snap != nullptr) {
-            const float4 sp = L.snap[li];
-            if (sp.w == 0.0f) continue;                                     // view_visibility.get() (assign.rs:195)
+        if (L.snap != nullptr || L.per_rank) {
+            const float4 sp = light_snap_of(L, li);
+            if (sp.w == 0.0f) continue;                                     // view_visibility.get() (assign.rs:195); unused slot
             px = sp.x; py = sp.y; pz = sp.z;
         } else {
             const uint32_t row = L.row[li];
             if (!(R.state[row] & 1u)) continue;
             px = R.gt0[row].w; py = R.gt1[row].w; pz = R.gt2[row].w;
         }
-        const unsigned long long ll = L.layers ? L.layers[li] : 1ull;
+        const unsigned long long ll = light_layers_of(L, li);
         if (!(cv.layer_mask & ll)) continue;                                // assign.rs:489
         const uint32_t bit = 1u << (li & 31u), wbase = (li >> 5) * per;
         uint32_t count = 0;
         float this_far = 0.0f;
-        const bool in = assign_one_light(cv, tb, px, py, pz, L.range[li], lane, this_far, count, [&](uint32_t ci) {
+        const bool in = assign_one_light(cv, tb, px, py, pz, light_range_of(L, li), lane, this_far, count, [&](uint32_t ci) {
             const uint32_t owner = ci / per;
             dsmem_or(dsmem_addr(&s_mask[wbase + (ci - owner * per)], owner), bit);
         });
@@ -3171,6 +3171,16 @@ static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 static unsigned long long g_launches = 0;
 unsigned long long kernel_launch_count() { return g_launches; }
 
+// Function attributes (dynamic shared memory size, cluster size) are per DEVICE: a process that drives several GPUs
+// (b200vis_p2p_link) must set them on each.  Returns true the first time it is called for (this call site, current device).
+static bool first_call_on_device(unsigned long long &seen) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
 static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile (default), 2 warp per tile, 3 TMA + scout warp, 4 TMA flow (no inter-tile barrier)
 static int tile_kernel_choice() {
     if (g_tile_kernel < 0) {
@@ -3186,7 +3196,8 @@ static void launch_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, c
                         const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity, uint32_t *counter) {
     constexpr size_t smem = (kTileRows / 32) * sizeof(WarpSmem);
     static int grid = 0, dynamic = 0;
-    if (!grid) {
+    static unsigned long long seen = 0;
+    if (first_call_on_device(seen)) {
         cudaFuncSetAttribute(k_tile_warp<C, S, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
@@ -3242,7 +3253,8 @@ template <bool C, bool S, int MINB>
 static void launch_scout(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                          const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity) {
     static int grid = 0, tiles_per_cta = 0;
-    if (!grid) {
+    static unsigned long long seen = 0;
+    if (first_call_on_device(seen)) {
         cudaFuncSetAttribute(k_propagate_cull_scout<C, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoutSmem));
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
@@ -3280,7 +3292,8 @@ template <bool P, bool C, bool S, bool FLOW>
 static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                        const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity) {
     static int grid = 0;
-    if (!grid) {
+    static unsigned long long seen = 0;
+    if (first_call_on_device(seen)) {
         cudaFuncSetAttribute((FLOW ? k_propagate_cull_flow<P, C, S> : k_propagate_cull_tma<P, C, S>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem));
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
@@ -3379,14 +3392,24 @@ void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, cons
     ++g_launches; k_cluster_assign<<<dim3(cdiv(L.n, 8), max_views), 256, 0, st>>>(R, L, fc, cb, stats);
 }
 // assign + lists of every view in one launch (single GPU): thread-block clusters of 8 (16 beyond ~3200 lights) CTAs per view
+// Can the one-launch cluster stage hold `n_lights` mask bits per cluster in a thread-block cluster's shared memory?
+bool cluster_fused_fits(uint32_t n_lights) {
+    const char *e = getenv("B200VIS_CLUSTER_KERNEL");
+    if (e && e[0] == 's') return false;
+    const size_t words = (n_lights + 31u) / 32u;
+    return words * (kMaxClusters / 16) * 4 <= 200u * 1024u;
+}
 bool launch_cluster_fused(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
                           DevStats *stats, uint32_t max_views) {
     static int enabled = -1, nrank_env = 0;
+    static unsigned long long seen = 0;
     if (enabled < 0) {
         const char *e = getenv("B200VIS_CLUSTER_KERNEL");
         enabled = (e && e[0] == 's') ? 0 : 1;                 // "split": the assign / lists / clear kernels
         const char *r = getenv("B200VIS_CLUSTER_CTAS");
         nrank_env = r ? atoi(r) : 0;
+    }
+    if (first_call_on_device(seen)) {
         cudaFuncSetAttribute(k_cluster_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_cluster_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     }

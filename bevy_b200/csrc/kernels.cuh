@@ -25,6 +25,7 @@ void launch_publish_visible_diff(cudaStream_t st, const VisibleBufs &vb, const D
                                  uint32_t *host_counts, uint32_t n_views, uint32_t max_views);
 void launch_cluster_assign(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
                            DevStats *stats, uint32_t max_views);
+bool cluster_fused_fits(uint32_t n_lights);
 bool launch_cluster_fused(cudaStream_t st, const Rows &R, const Lights &L, const FrameConsts *fc, const ClusterBufs &cb,
                           DevStats *stats, uint32_t max_views);
 void launch_publish_visible(cudaStream_t st, const VisibleBufs &vb, const DevStats *stats, uint32_t *host_rows, uint32_t host_stride,
