@@ -19,8 +19,11 @@ path) and the cameras rotate.
                 (b200vis_set_column_sinks).  `e2e_resident` = the same without the column write-back (round 1's figure),
                 `e2e_sparse` = the reference bench's own mutation pattern (8 roots per frame, propagate.rs:115-128).
   N > 1         --scaling strong (default; what BASELINE.json's metric quotes): the SAME 1M / 256 scene split by whole-tree
-                row ranges; --scaling weak: every rank owns a 1M / 256 shard.  One exchange per frame (all-gather of the
-                fixed-size cluster x light slabs, which also carry the Clusters::last_frame_* feedback).
+                row ranges; --scaling weak: every rank owns a 1M / 256 shard.  One exchange per frame: an all-gather of the
+                ranks' light-record blocks (28 B per light: this frame's position + ViewVisibility, range, layers), after
+                which every rank runs the one-launch cluster stage over all lights.  B200VIS_EXCHANGE=p2p sends the same
+                blocks as peer stores over NVLink; B200VIS_EXCHANGE_WHAT=slabs exchanges the cluster x light bit slabs
+                instead (the path for light counts beyond the cluster kernel's shared memory).
   parity        outside the timed regions the frame that follows each timed loop is checked bit for bit against the CPU
                 oracle (GlobalTransform bits, both change columns, ViewVisibility, sorted visible lists, cluster CSR, column
                 write-back) on every rank: `parity_checked`.
@@ -844,7 +847,7 @@ def main():
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         algo_bytes = n * ALGO_BYTES_PER_ENTITY + 4 * visible_pairs_rank
         achieved = algo_bytes / (tile_ms_avg * 1e-3) / 1e9
-        tile_kernel = {"c": "k_propagate_cull", "s": "k_propagate_cull_scout", "w": "k_tile_warp"}.get(
+        tile_kernel = {"c": "k_propagate_cull", "s": "k_propagate_cull_scout", "w": "k_tile_warp", "f": "k_propagate_cull_flow"}.get(
             os.environ.get("B200VIS_TILE_KERNEL", "t")[:1], "k_propagate_cull_tma")
         cfg_out = dict(cfg)
         line = {
@@ -854,7 +857,9 @@ def main():
             "value_note": "pipelined throughput: frames enqueued back to back, the tail of frame f (list expansion, clusters) overlaps "
                           "the tile pass of frame f+1; the latency of one live frame (feedback loop closed) is what e2e measures",
             "run": {"entities_per_gpu": n, "lights_per_gpu": lights_rank,
-                    "sharding": ("contiguous row ranges (whole trees) per GPU; cluster slabs (+ Clusters feedback trailer) exchanged by " +
+                    "sharding": ("contiguous row ranges (whole trees) per GPU; " +
+                                 ("cluster x light bit slabs (+ Clusters feedback trailer)" if os.environ.get("B200VIS_EXCHANGE_WHAT", "r")[:1] == "s"
+                                  else "light-record blocks (28 B per light), cluster stage on every rank over all lights,") + " exchanged by " +
                                  ("peer stores over NVLink (CUDA IPC) + per-frame stamps" if rig.exchange == "p2p" else "one ncclAllGather"))
                     if world > 1 else "single GPU",
                     "visible_pairs_last_frame": int(visible_pairs), "cluster_indices_last_frame": int(cluster_indices)},

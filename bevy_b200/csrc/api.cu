@@ -89,6 +89,7 @@ struct b200vis_ctx {
     Tile *d_tiles = nullptr; uint32_t tiles_cap = 0;
     WarpTile *d_wtiles = nullptr; uint8_t *d_sched = nullptr; uint32_t *d_wtopo = nullptr;   // k_tile_warp's view of the plan
     uint32_t *d_tile_counter = nullptr;
+    uint32_t *d_tile_ticket = nullptr; uint32_t tile_ticket_base = 0;   // dynamic tile hand-out of the default kernel: never reset, the host tracks the base
     std::vector<uint32_t> pass_begin;   // tile index ranges per pass: [pass_begin[p], pass_begin[p+1])
     std::vector<uint32_t> pass_small;   // the first pass_small[p] tiles of pass p have <= 32 rows (B200VIS_SPLIT_DEEP_TILES)
     int static_opt = 1;
@@ -202,7 +203,7 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     Rows &r = ctx->rows;
     void *dev[] = {r.trsA, r.trsB, r.trsC, r.gt0, r.gt1, r.gt2, r.bndA, r.bndB, r.flags, r.state, r.topo,
                    ctx->d_parent, ctx->d_layers, ctx->d_range, ctx->d_rank, ctx->d_row_of_rank, ctx->d_dirty,
-                   ctx->d_layers_ext, ctx->d_vv_shadow, ctx->d_gt_aos, ctx->d_tiles, ctx->d_wtiles, ctx->d_sched, ctx->d_wtopo, ctx->d_tile_counter, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_lrec, ctx->d_lrec_all, ctx->d_tag_flag, ctx->d_light_ord,
+                   ctx->d_layers_ext, ctx->d_vv_shadow, ctx->d_gt_aos, ctx->d_tiles, ctx->d_wtiles, ctx->d_sched, ctx->d_wtopo, ctx->d_tile_counter, ctx->d_tile_ticket, ctx->d_blob2[0], ctx->d_blob2[1], ctx->d_blob2[2], ctx->d_lrec, ctx->d_lrec_all, ctx->d_tag_flag, ctx->d_light_ord,
                    ctx->vis.mask, ctx->vis.chunk_count, ctx->vis.lists, ctx->vis.classes, ctx->d_cls, ctx->d_stats, ctx->d_light_row,
                    ctx->d_light_range, ctx->d_light_layers, ctx->d_slab, ctx->cl.offsets, ctx->cl.indices, ctx->d_stage,
                    ctx->diff.prev, ctx->diff.words, ctx->diff.chunk, ctx->diff.lists, ctx->diff.count,
@@ -278,6 +279,7 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
         CU(dalloc(&ctx->d_sched, (size_t)ctx->tiles_cap * kTileRows));
         CU(dalloc(&ctx->d_wtopo, NP));
         CU(dalloc(&ctx->d_tile_counter, 1));
+        CU(dalloc(&ctx->d_tile_ticket, 1)); CU(cudaMemset(ctx->d_tile_ticket, 0, 4));
         r.wtopo = ctx->d_wtopo;
         // worst case tables: every view with three (kMaxClusters+1)-entry plane tables + kMaxClusters thresholds
         ctx->blob_cap = sizeof(FrameConsts) + V * (3 * (size_t)(kMaxClusters + 1) * 16 + (size_t)kMaxClusters * 4);
@@ -1364,7 +1366,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
                                      cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot, ctx->d_tile_counter);
                 else
                     launch_propagate_cull(st, R, ctx->d_tiles + b + ns, ctx->pass_begin[p + 1] - b - ns,
-                                          cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot);
+                                          cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot, ctx->d_tile_ticket, &ctx->tile_ticket_base);
             }
         } else if (n_pass) {
             launch_cull(st, R, cvw, vb, ctx->d_stats, cslot);
@@ -1394,7 +1396,7 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     // driven / peer-store exchange) keeps the slab path.
     static int records_env = -1;
     if (records_env < 0) { const char *e = getenv("B200VIS_EXCHANGE_WHAT"); records_env = (e && e[0] == 's') ? 0 : 1; }
-    const bool records = exchange_first && records_env && ctx->nccl_comm && !ctx->p2p_ready && ctx->ext_send == nullptr &&
+    const bool records = exchange_first && records_env && (ctx->nccl_comm || ctx->p2p_ready) && ctx->ext_send == nullptr &&
                          cluster_fused_fits(cl.world * cl.max_lights);
     bool fused_clusters = false;     // both cluster stages in this call and all lights at hand: one launch does assign + lists
     auto issue_assign_and_exchange = [&]() -> int32_t {
@@ -1402,6 +1404,11 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
             if (!(pipelined && ctx->lights.n)) {      // no snapshot was taken with the tile pass: take it now (same stream order)
                 Lights lsnap = ctx->lights;
                 launch_snapshot_lights(tail, R, lsnap, ctx->light_snap_slot(cslot));
+            }
+            if (ctx->p2p_ready) {        // peer stores over NVLink + stamps; the cluster kernel waits for every rank's stamp
+                cl.p2p = 1; cl.xparity = mslot; cl.stamp = frame + 1u;
+                launch_record_push(tail, reinterpret_cast<const uint32_t *>(ctx->d_lrec + (size_t)cslot * ctx->lrec_bytes), (uint32_t)(ctx->lrec_bytes / 4), cl);
+                return B200VIS_OK;
             }
             const int nrc = g_nccl.AllGather(ctx->d_lrec + (size_t)cslot * ctx->lrec_bytes, ctx->d_lrec_all, ctx->lrec_bytes / 4, kNcclUint32,
                                              ctx->nccl_comm, tail);
@@ -1454,6 +1461,10 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     if (records) {
         Lights lg{};
         lg.n = cl.world * cl.max_lights; lg.per_rank = cl.max_lights; lg.block_bytes = (uint32_t)ctx->lrec_bytes; lg.blocks = ctx->d_lrec_all;
+        if (ctx->p2p_ready) {       // the gathered buffer the peers wrote into: one slab-sized region per (parity, rank), the block at its front
+            lg.block_bytes = (uint32_t)ctx->slab_bytes;
+            lg.blocks = reinterpret_cast<const uint8_t *>(ctx->d_xbuf + (size_t)mslot * cl.world * (ctx->slab_bytes / 4));
+        }
         fused_clusters = launch_cluster_fused(tail, R, lg, fc, cl, ctx->d_stats, ctx->cfg.max_views);
         if (!fused_clusters) return fail(ctx, B200VIS_ERR_CUDA, "run: the cluster kernel could not be launched over the gathered light records");
     }

@@ -405,6 +405,7 @@ struct TmaSmem {
     unsigned long long bar[2];       // full[s]: the tile's columns have landed in stage s (TMA complete_tx)
     unsigned long long walked[2];    // walked[s]: all 8 warps are done walking the tile in stage s, hold their rows in registers,
                                      //            and have looked at the NEXT tile's change flags (climb[s ^ 1] is final)
+    uint32_t next_tile[2];           // k_propagate_cull_tma: the tile this CTA processes after the one in stage s
     uint32_t climb[2];               // climb[s] == it: a non-root row of the tile of iteration it (stage s) has Changed<Transform>
     uint16_t parent[kTileRows];
     uint8_t pst[kTileRows];      // bit0 visited, bit1 gt changed
@@ -479,7 +480,8 @@ __device__ unsigned long long g_tile_timing[8192 * 16];
 template <bool PROP, bool CULL, bool SIMPLE>
 __global__ void __launch_bounds__(kTileRows, 4)
 k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, const __grid_constant__ CullViews cvw,
-                     VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity) {
+                     VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity,
+                     uint32_t *__restrict__ ticket, uint32_t ticket_base) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TmaSmem &s = *reinterpret_cast<TmaSmem *>(smem_raw);
     const uint32_t lr = threadIdx.x;
@@ -495,7 +497,11 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
     uint32_t t = blockIdx.x;
     if (lr == 0 && t < n_tiles) issue_tile_loads<PROP, CULL>(R, tiles[t], s.st[0], &s.bar[0]);
     uint32_t n_gt_total = 0, n_vv_total = 0;
-    for (uint32_t it = 0; t < n_tiles; t += gridDim.x, ++it) {
+    // Tile hand-out: a CTA starts on tile blockIdx.x and then takes the tiles the grid has not started yet in ticket order
+    // (one atomic per tile, drawn by thread 0 when it prefetches, i.e. one tile ahead).  A fixed stride would leave a CTA with
+    // ceil(n/g) tiles running next to finished neighbours with floor(n/g) -- a fifth of the pass at 3.3 tiles per CTA.  The
+    // ticket counter is never reset: every launch draws exactly n_tiles tickets, and the host passes the running base.
+    for (uint32_t it = 0; t < n_tiles; ++it) {
         const uint32_t sidx = it & 1u;
         const Tile tile = tiles[t];
         mbar_wait(&s.bar[sidx], (it >> 1) & 1u);
@@ -615,11 +621,12 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         // issued most of an iteration ago, so the wait below is (almost always) already satisfied: putting the
         // prefetch here instead of at the top of the loop keeps the store drain off every warp's critical path.
         if (lr == 0) {
-            const uint32_t tn = t + gridDim.x;
+            const uint32_t tn = ticket ? gridDim.x + (atomicAdd(ticket, 1u) - ticket_base) : t + gridDim.x;
             if (tn < n_tiles) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 issue_tile_loads<PROP, CULL>(R, tiles[tn], s.st[sidx ^ 1u], &s.bar[sidx ^ 1u]);
             }
+            s.next_tile[sidx] = tn;      // read by everybody behind the tile's closing barrier
         }
         uint32_t out = st8 & (S_VV | S_HAS_CLASS);
         if (PROP) out |= (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
@@ -739,6 +746,7 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
         if (it == 1) { TT(13); }   // cull done
         const int any_gt = __syncthreads_or(PROP && changed);
         if (it == 1) { TT(15); }
+        t = s.next_tile[sidx];
         if (lr == 0) {
             if (PROP && any_gt) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
@@ -773,7 +781,8 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
 template <bool PROP, bool CULL, bool SIMPLE>
 __global__ void __launch_bounds__(kTileRows, 4)
 k_propagate_cull_flow(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, const __grid_constant__ CullViews cvw,
-                     VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity) {
+                     VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity,
+                     uint32_t *__restrict__ /*ticket*/, uint32_t /*ticket_base*/) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TmaSmem &s = *reinterpret_cast<TmaSmem *>(smem_raw);
     const uint32_t lr = threadIdx.x;
@@ -2329,6 +2338,14 @@ __device__ __forceinline__ uint32_t dsmem_ld(uint32_t addr) {
     uint32_t v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
 }
 
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __global__ void __launch_bounds__(kFusedThreads)
 k_cluster_fused(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__restrict__ stats) {
     extern __shared__ __align__(16) uint8_t smem_fused[];
@@ -2345,6 +2362,17 @@ k_cluster_fused(Rows R, Lights L, const FrameConsts *__restrict__ fc, ClusterBuf
     if (!cv.enabled) {
         if (rank == 0 && t == 0) { offsets[0] = 0; stats->cl_overflow[v] = 0; stats->cl_index_count[v] = 0; stats->cl_farthest_bits[v] = 0; }
         return;
+    }
+    if (cb.p2p && L.per_rank) {     // light records pushed by the peers (k_record_push): wait for every rank's stamp of this frame
+        if (t < cb.world) {
+            const uint32_t *flag = cb.peer_flags[cb.rank] + cb.xparity * cb.world + t;
+            uint32_t spins = 0;
+            while ((int32_t)(ld_acquire_sys(flag) - cb.stamp) < 0) {
+                __nanosleep(64);
+                if (++spins > (1u << 22)) { stats->cl_overflow[v] = 2u; break; }   // a peer never arrived (~0.3 s): report, do not hang
+            }
+        }
+        __syncthreads();
     }
     const uint32_t nc = cv.n_clusters, per = (nc + nrank - 1) / nrank, words = (L.n + 31u) / 32u;
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem_fused);      // [words][per]
@@ -2464,14 +2492,6 @@ constexpr uint32_t kListBlocks = kMaxClusters / 1024;
 // at most one frame ahead of the slowest one, because its next-but-one push comes after its own list build, which
 // waited for everybody's stamp of the frame in between.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __global__ void __launch_bounds__(256)
 k_slab_push(const FrameConsts *__restrict__ fc, ClusterBufs cb, uint32_t *__restrict__ done) {
     const uint32_t v = blockIdx.y;
@@ -2503,6 +2523,18 @@ k_slab_push(const FrameConsts *__restrict__ fc, ClusterBufs cb, uint32_t *__rest
     }
 }
 
+// The light-record exchange as peer stores: CTA r copies this rank's light block (28 bytes per light) into rank r's gathered
+// buffer and stamps it; k_cluster_fused waits for every rank's stamp of the frame before it reads a light.
+__global__ void __launch_bounds__(256)
+k_record_push(const uint32_t *__restrict__ block, uint32_t block_words, ClusterBufs cb) {
+    const uint32_t r = blockIdx.x;
+    uint32_t *dst = cb.peer[r] + ((size_t)cb.xparity * cb.world + cb.rank) * cb.slab_words;
+    for (uint32_t i = threadIdx.x; i < block_words; i += blockDim.x) dst[i] = block[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(cb.peer_flags[r] + cb.xparity * cb.world + cb.rank, cb.stamp);
+}
+
 __global__ void __launch_bounds__(1024)
 k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__restrict__ stats) {
     __shared__ uint32_t s_warp[32];
@@ -2520,7 +2552,7 @@ k_cluster_lists(const FrameConsts *__restrict__ fc, ClusterBufs cb, DevStats *__
             uint32_t spins = 0;
             while ((int32_t)(ld_acquire_sys(flag) - cb.stamp) < 0) {
                 __nanosleep(64);
-                if (++spins > (1u << 26)) { stats->cl_overflow[v] = 2u; break; }   // a peer never arrived: report, do not hang
+                if (++spins > (1u << 22)) { stats->cl_overflow[v] = 2u; break; }   // a peer never arrived (~0.3 s): report, do not hang
             }
         }
         __syncthreads();
@@ -3290,7 +3322,7 @@ static void launch_scout_m(cudaStream_t st, const Rows &R, const Tile *tiles, ui
 }
 template <bool P, bool C, bool S, bool FLOW>
 static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
-                       const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity) {
+                       const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity, uint32_t *ticket, uint32_t *ticket_base) {
     static int grid = 0;
     static unsigned long long seen = 0;
     if (first_call_on_device(seen)) {
@@ -3325,7 +3357,12 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    ++g_launches; cudaLaunchKernelEx(&cfg, (FLOW ? k_propagate_cull_flow<P, C, S> : k_propagate_cull_tma<P, C, S>), R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
+    // dynamic tile hand-out (fully persistent grids of the default kernel; B200VIS_TILE_HANDOUT=static keeps the fixed stride)
+    static int dynamic = -1;
+    if (dynamic < 0) { const char *e = getenv("B200VIS_TILE_HANDOUT"); dynamic = (e && e[0] == 's') ? 0 : 1; }
+    uint32_t *tk = nullptr, base = 0;
+    if (!FLOW && dynamic && tiles_per_cta == 0 && ticket && ticket_base) { tk = ticket; base = *ticket_base; *ticket_base += n_tiles; }
+    ++g_launches; cudaLaunchKernelEx(&cfg, (FLOW ? k_propagate_cull_flow<P, C, S> : k_propagate_cull_tma<P, C, S>), R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, tk, base);
 }
 // tiles of <= 32 rows (the tops of split deep tiles): the classic kernel with one warp per tile, 16 CTAs per SM
 void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
@@ -3340,7 +3377,8 @@ void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *til
 #undef B200VIS_LAUNCH_SMALL
 }
 void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
-                           const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity) {
+                           const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity,
+                           uint32_t *ticket, uint32_t *ticket_base) {
     if (n_tiles == 0) return;
     const bool prop = stages & 1u, cull = stages & 2u;
     const bool simple = R.layers == nullptr && R.layers_ext == nullptr && R.range == nullptr && R.rank == nullptr;
@@ -3352,8 +3390,8 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
         return;
     }
     if (tile_kernel_choice() == 1 || tile_kernel_choice() == 3 || tile_kernel_choice() == 4) {
-#define B200VIS_LAUNCH_TMA(P, C, S) do { if (tile_kernel_choice() == 4) launch_tma<P, C, S, true>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity); \
-                                         else launch_tma<P, C, S, false>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity); } while (0)
+#define B200VIS_LAUNCH_TMA(P, C, S) do { if (tile_kernel_choice() == 4) launch_tma<P, C, S, true>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
+                                         else launch_tma<P, C, S, false>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); } while (0)
         if (prop && cull) { if (simple) B200VIS_LAUNCH_TMA(true, true, true); else B200VIS_LAUNCH_TMA(true, true, false); }
         else if (prop) B200VIS_LAUNCH_TMA(true, false, true);
         else if (cull) { if (simple) B200VIS_LAUNCH_TMA(false, true, true); else B200VIS_LAUNCH_TMA(false, true, false); }
@@ -3459,6 +3497,9 @@ void launch_writeback_columns(cudaStream_t st, const Rows &R, float *host_gt, ui
     const unsigned groups = cdiv(R.n, 128), grid = groups < 8u * 1184u ? cdiv(groups, 8) : 1184u;
     if (stride == 16) { ++g_launches; k_writeback_columns<16><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits, vv_shadow); }
     else { ++g_launches; k_writeback_columns<12><<<grid, 256, 0, st>>>(R, host_gt, host_gt_bits, host_vv, host_vv_bits, vv_shadow); }
+}
+void launch_record_push(cudaStream_t st, const uint32_t *block, uint32_t block_words, const ClusterBufs &cb) {
+    ++g_launches; k_record_push<<<cb.world, 256, 0, st>>>(block, block_words, cb);
 }
 void launch_slab_push(cudaStream_t st, const FrameConsts *fc, const ClusterBufs &cb, uint32_t *done, uint32_t max_views) {
     ++g_launches; k_slab_push<<<dim3(8, max_views), 256, 0, st>>>(fc, cb, done);

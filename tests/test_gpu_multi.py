@@ -9,24 +9,24 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode", ["host_collective", "builtin", "builtin_slabs", "p2p"])
+@pytest.mark.parametrize("mode", ["host_collective", "builtin", "builtin_slabs", "p2p", "p2p_slabs"])
 def test_two_gpu_shard_gather_matches_oracle(mode):
     # builtin: the library's own ncclAllGather of the light-record blocks + the one-launch cluster stage on every rank;
     # builtin_slabs: the same collective over the cluster x light bit slabs (B200VIS_EXCHANGE_WHAT=slabs, the path that
-    # remains for light counts beyond the fused kernel's shared memory); host_collective / p2p: slabs by the host's own
-    # all-gather / by peer stores
+    # remains for light counts beyond the fused kernel's shared memory); p2p / p2p_slabs: the same two payloads as peer stores
+    # over NVLink (CUDA IPC) + per-frame stamps; host_collective: slabs by the host's own all-gather
     torch = pytest.importorskip("torch")
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", {"builtin": "29533", "host_collective": "29534", "p2p": "29535", "builtin_slabs": "29536"}[mode],
+           "--master-port", {"builtin": "29533", "host_collective": "29534", "p2p": "29535", "builtin_slabs": "29536", "p2p_slabs": "29537"}[mode],
            os.path.join(here, "multi_gpu_parity.py")]
     if mode != "host_collective":
         cmd.append("--" + mode.split("_")[0])
     env = dict(os.environ)
     env.pop("B200VIS_EXCHANGE_WHAT", None)
-    if mode == "builtin_slabs":
+    if mode.endswith("_slabs"):
         env["B200VIS_EXCHANGE_WHAT"] = "slabs"
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     print(res.stdout[-2000:]); print(res.stderr[-3000:])
