@@ -62,6 +62,7 @@ struct b200vis_ctx {
     // stream while frame f+1's tile pass already runs on the main stream (masks / counters / constants are
     // double or triple buffered by frame number).
     cudaStream_t side_stream = nullptr;
+    cudaStream_t clus_stream = nullptr; cudaEvent_t ev_clus = nullptr;   // pipelined frames: the cluster branch of the tail (exchange -> cluster kernel) runs beside the list expansion
     cudaEvent_t ev_tile = nullptr, ev_side[3] = {nullptr, nullptr, nullptr}, ev_expand[2] = {nullptr, nullptr}, ev_pub = nullptr;
     bool pub_pending = false;           // a publish_visible copy is in flight on the side stream
     bool pipeline = true, side_pending = false;
@@ -233,6 +234,8 @@ extern "C" void b200vis_destroy(b200vis_ctx *ctx) {
     if (ctx->d_push_done) cudaFree(ctx->d_push_done);
     for (auto &r : ctx->recorded) if (r.dev) cudaFree(r.dev);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->clus_stream) { cudaStreamSynchronize(ctx->clus_stream); cudaStreamDestroy(ctx->clus_stream); }
+    if (ctx->ev_clus) cudaEventDestroy(ctx->ev_clus);
     if (ctx->ev_tile) cudaEventDestroy(ctx->ev_tile);
     if (ctx->ev_pub) cudaEventDestroy(ctx->ev_pub);
     for (cudaEvent_t e : ctx->ev_side) if (e) cudaEventDestroy(e);
@@ -290,6 +293,8 @@ extern "C" int32_t b200vis_create(const b200vis_config *cfg, b200vis_ctx **out) 
             int lo = 0, hi = 0;
             CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
             CU(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+            CU(cudaStreamCreateWithPriority(&ctx->clus_stream, cudaStreamNonBlocking, hi));
+            CU(cudaEventCreateWithFlags(&ctx->ev_clus, cudaEventDisableTiming));
         }
         CU(cudaEventCreateWithFlags(&ctx->ev_tile, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_pub, cudaEventDisableTiming));
@@ -1399,36 +1404,49 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
     const bool records = exchange_first && records_env && (ctx->nccl_comm || ctx->p2p_ready) && ctx->ext_send == nullptr &&
                          cluster_fused_fits(cl.world * cl.max_lights);
     bool fused_clusters = false;     // both cluster stages in this call and all lights at hand: one launch does assign + lists
+    // Pipelined frames: the cluster branch of the tail (exchange -> cluster kernel(s) -> bindings) depends on the tile pass only,
+    // not on the list expansion, and its first step may wait for other GPUs: it gets a stream of its own (`ctail`) beside the
+    // expansion / visible-list publish on `tail`; the two meet again before the stats + cluster lists are published.  The
+    // branch also waits for the previous frame's tail (its cluster lists and stats are single-buffered).
+    static int branch_env = -1;
+    if (branch_env < 0) { const char *e = getenv("B200VIS_CLUSTER_BRANCH"); branch_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool branch = pipelined && has_assign && has_lists && branch_env && ctx->clus_stream != nullptr;
+    cudaStream_t ctail = tail;
+    if (branch) {
+        ctail = ctx->clus_stream;
+        CU(cudaStreamWaitEvent(ctail, ctx->ev_tile, 0));
+        if (ctx->side_pending && frame >= 1) CU(cudaStreamWaitEvent(ctail, ctx->ev_side[(frame + 2u) % 3u], 0));
+    }
     auto issue_assign_and_exchange = [&]() -> int32_t {
         if (records) {
             if (!(pipelined && ctx->lights.n)) {      // no snapshot was taken with the tile pass: take it now (same stream order)
                 Lights lsnap = ctx->lights;
-                launch_snapshot_lights(tail, R, lsnap, ctx->light_snap_slot(cslot));
+                launch_snapshot_lights(ctail, R, lsnap, ctx->light_snap_slot(cslot));
             }
             if (ctx->p2p_ready) {        // peer stores over NVLink + stamps; the cluster kernel waits for every rank's stamp
                 cl.p2p = 1; cl.xparity = mslot; cl.stamp = frame + 1u;
-                launch_record_push(tail, reinterpret_cast<const uint32_t *>(ctx->d_lrec + (size_t)cslot * ctx->lrec_bytes), (uint32_t)(ctx->lrec_bytes / 4), cl);
+                launch_record_push(ctail, reinterpret_cast<const uint32_t *>(ctx->d_lrec + (size_t)cslot * ctx->lrec_bytes), (uint32_t)(ctx->lrec_bytes / 4), cl);
                 return B200VIS_OK;
             }
             const int nrc = g_nccl.AllGather(ctx->d_lrec + (size_t)cslot * ctx->lrec_bytes, ctx->d_lrec_all, ctx->lrec_bytes / 4, kNcclUint32,
-                                             ctx->nccl_comm, tail);
+                                             ctx->nccl_comm, ctail);
             if (nrc) return fail(ctx, B200VIS_ERR_CUDA, "ncclAllGather: %s", g_nccl.GetErrorString(nrc));
             return B200VIS_OK;
         }
         if (has_assign && has_lists && cl.world == 1 && ctx->ext_send == nullptr && lights.n)
-            fused_clusters = launch_cluster_fused(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+            fused_clusters = launch_cluster_fused(ctail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
         if ((stages & B200VIS_STAGE_CLUSTER_ASSIGN) && !fused_clusters)
-            launch_cluster_assign(tail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+            launch_cluster_assign(ctail, R, lights, fc, cl, ctx->d_stats, ctx->cfg.max_views);
         if (has_assign && has_lists && cl.world > 1) {
             if (ctx->p2p_ready) {
                 // peer stores over NVLink + stamps; k_cluster_lists waits for every rank's stamp of this frame
                 cl.p2p = 1; cl.xparity = mslot; cl.stamp = frame + 1u;
                 cl.recv = ctx->d_xbuf + (size_t)mslot * cl.world * (ctx->slab_bytes / 4);
-                launch_slab_push(tail, fc, cl, ctx->d_push_done, ctx->cfg.max_views);
+                launch_slab_push(ctail, fc, cl, ctx->d_push_done, ctx->cfg.max_views);
             } else {
                 // the ONE data-path collective: rank-major all-gather of the fixed-size cluster x light slabs over NVLink
                 if (!ctx->nccl_comm) return fail(ctx, B200VIS_ERR_NOT_READY, "run(ALL) with world_size > 1 needs b200vis_p2p_import or b200vis_comm_init (or run ASSIGN and LISTS separately around your own all-gather)");
-                const int nrc = g_nccl.AllGather(cl.send, const_cast<uint32_t *>(cl.recv), ctx->slab_bytes / 4, kNcclUint32, ctx->nccl_comm, tail);
+                const int nrc = g_nccl.AllGather(cl.send, const_cast<uint32_t *>(cl.recv), ctx->slab_bytes / 4, kNcclUint32, ctx->nccl_comm, ctail);
                 if (nrc) return fail(ctx, B200VIS_ERR_CUDA, "ncclAllGather: %s", g_nccl.GetErrorString(nrc));
             }
         }
@@ -1465,13 +1483,14 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
             lg.block_bytes = (uint32_t)ctx->slab_bytes;
             lg.blocks = reinterpret_cast<const uint8_t *>(ctx->d_xbuf + (size_t)mslot * cl.world * (ctx->slab_bytes / 4));
         }
-        fused_clusters = launch_cluster_fused(tail, R, lg, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+        fused_clusters = launch_cluster_fused(ctail, R, lg, fc, cl, ctx->d_stats, ctx->cfg.max_views);
         if (!fused_clusters) return fail(ctx, B200VIS_ERR_CUDA, "run: the cluster kernel could not be launched over the gathered light records");
     }
     if ((stages & B200VIS_STAGE_CLUSTER_LISTS) && !fused_clusters)
-        launch_cluster_lists(tail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
+        launch_cluster_lists(ctail, fc, cl, ctx->d_stats, ctx->cfg.max_views);
     if ((stages & B200VIS_STAGE_CLUSTER_LISTS) && ctx->bind.mode)
-        launch_pack_cluster_bindings(tail, fc, cl, ctx->bind, ctx->cfg.max_views);
+        launch_pack_cluster_bindings(ctail, fc, cl, ctx->bind, ctx->cfg.max_views);
+    if (branch) { CU(cudaEventRecord(ctx->ev_clus, ctail)); CU(cudaStreamWaitEvent(tail, ctx->ev_clus, 0)); }   // the branches meet
     // (b200vis_step with clusters runs CLUSTER right behind PROPAGATE|CULL: that run publishes the stats block once for both)
     if (ctx->have_sink && (do_cull || (stages & B200VIS_STAGE_CLUSTER_LISTS)) && !(ctx->step_defers_stats && !(stages & B200VIS_STAGE_CLUSTER_LISTS)))
         launch_publish_clusters(tail, fc, cl, (stages & B200VIS_STAGE_CLUSTER_LISTS) ? ctx->sink_off_d : nullptr, ctx->sink_idx_d,
