@@ -774,6 +774,437 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
 }
 
 // ------------------------------------------------------------------------------------------
+// Kernel 1L (B200VIS_TILE_KERNEL=lean): kernel 1b on an instruction and exposed-latency diet.  ncu's source view of 1b
+// (profiles/r02b_*) shows a kernel that is bound by issue-slot latency (1.2 eligible warps per scheduler), with ~820 warp
+// instructions per 32 rows of which half are bookkeeping, and four places where a long latency is exposed on every tile:
+//   * the tile descriptor (LDG of tiles[t]) at the top of a tile                  -> descriptors travel through shared memory:
+//     the bookkeeping thread fetches the descriptor of the CTA's tile i+2 with cp.async while tile i is culled;
+//   * the TMA prefetch of tile i+1 is issued after the walk of tile i by thread 0 (the warp every level of the walk waits
+//     for), behind a dependent ticket atomic + descriptor load                    -> the bookkeeping thread is the LAST thread
+//     (a leaf warp that idles while the levels above it are walked), the ticket is drawn one tile further ahead and the
+//     prefetch goes out at the top of the tile, a whole walk earlier;
+//   * the view-rejection test reads its planes with register-indexed LDC          -> planes are staged in shared memory once
+//     per CTA; the box is built with f32 warp reductions (CREDUX.F32) instead of order-preserving integer transforms;
+//   * the per-view loop was unrolled 8x with the plane operands in the constant bank (48 KB of code, a test + branch per
+//     view even when the warp rejected it)                                         -> one rolled loop over the set bits of
+//     (active views & ~rejected), planes from shared memory: a warp that rejects every view skips the loop in 3 instructions.
+// Same results bit for bit (tests/test_gpu_bench_scale.py runs the bench workload through it).
+// ------------------------------------------------------------------------------------------
+// MINB = 4: the whole tile (Transform, GlobalTransform, topo, flags, state: 94 B/row) is staged in both stages, as in kernel 1b.
+// MINB = 5, 6: Transform stays out of the staged window (54 B/row staged) -- it is consumed in the first hundred instructions of a
+// tile, so it comes in through plain coalesced loads issued above the wait for the tile (the bookkeeping thread has pulled the
+// columns into L2 a tile ahead) -- which lets a 5th / 6th CTA fit an SM's shared memory; the register budget (48 / 40) is met with
+// a handful of spills, and the named level barriers use immediate ids so that a CTA owns 8 of the SM's hardware barriers, not 16.
+template <bool WITH_TRS> struct __align__(128) LeanStage;
+template <> struct __align__(128) LeanStage<true> {
+    float4 gt0[kWin], gt1[kWin], gt2[kWin];
+    uint32_t topo[kWin];
+    uint8_t flags[kWin], state[kWin];
+    float4 trsA[kWin], trsB[kWin];
+    float2 trsC[kWin];
+};
+template <> struct __align__(128) LeanStage<false> {
+    float4 gt0[kWin], gt1[kWin], gt2[kWin];
+    uint32_t topo[kWin];
+    uint8_t flags[kWin], state[kWin];
+};
+template <bool WITH_TRS>
+struct LeanSmem {
+    LeanStage<WITH_TRS> st[2];
+    unsigned long long bar[2];       // full[s]: the tile's columns have landed in stage s
+    Tile tdesc[3];                   // descriptor of the CTA's i-th tile in slot i % 3 (i+2 is fetched while i is processed)
+    uint32_t next_tile[2];
+    float4 vplanes[kMaxViews * 5];   // the views' culling planes, [view][L,R,T,B,Near]
+    uint16_t parent[kTileRows];
+    uint8_t pst[kTileRows];          // bit0 visited, bit1 gt changed
+    uint8_t dirty[kTileRows];
+};
+template <bool PROP, bool CULL, bool WITH_TRS>
+__device__ __forceinline__ void issue_lean_loads(const Rows &R, const Tile &t, LeanStage<WITH_TRS> &S, unsigned long long *bar) {
+    const uint32_t a = t.base & ~15u;
+    const uint32_t cnt = ((t.base - a) + t.n_rows + 15u) & ~15u;
+    uint32_t bytes = cnt * (48u + 2u);
+    if (PROP) bytes += cnt * 4u;
+    if (PROP && WITH_TRS) bytes += cnt * 40u;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(S.gt0, R.gt0 + a, cnt * 16u, bar); bulk_g2s(S.gt1, R.gt1 + a, cnt * 16u, bar); bulk_g2s(S.gt2, R.gt2 + a, cnt * 16u, bar);
+    bulk_g2s(S.flags, R.flags + a, cnt, bar); bulk_g2s(S.state, R.state + a, cnt, bar);
+    if (PROP) bulk_g2s(S.topo, R.topo + a, cnt * 4u, bar);
+    if constexpr (WITH_TRS) {
+        if (PROP) {
+            bulk_g2s(S.trsA, R.trsA + a, cnt * 16u, bar); bulk_g2s(S.trsB, R.trsB + a, cnt * 16u, bar);
+            bulk_g2s(S.trsC, R.trsC + a, cnt * 8u, bar);
+        }
+    } else if (PROP) {     // the Transform columns of that tile into L2: its rows load them straight into registers
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R.trsA + a), "r"(cnt * 16u) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R.trsB + a), "r"(cnt * 16u) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(R.trsC + a), "r"(cnt * 8u) : "memory");
+    }
+}
+// hardware named barrier `id` (1..7) with IMMEDIATE ids: ptxas then counts 8 barriers per CTA instead of assuming all 16 (the SM
+// has 64, i.e. 16 per CTA cap residency at 4 CTAs).  Seven predicated barrier instructions, no jump table: this sits on the walk's
+// critical path and every instruction here has a fixed latency.
+#define B200VIS_BAR_SEQ(OP) \
+    "{\n.reg .pred p;\n" \
+    "setp.eq.u32 p, %0, 1;\n@p " OP " 1, %1;\n" "setp.eq.u32 p, %0, 2;\n@p " OP " 2, %1;\n" "setp.eq.u32 p, %0, 3;\n@p " OP " 3, %1;\n" \
+    "setp.eq.u32 p, %0, 4;\n@p " OP " 4, %1;\n" "setp.eq.u32 p, %0, 5;\n@p " OP " 5, %1;\n" "setp.eq.u32 p, %0, 6;\n@p " OP " 6, %1;\n" \
+    "setp.ge.u32 p, %0, 7;\n@p " OP " 7, %1;\n}\n"
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t cnt) { asm volatile(B200VIS_BAR_SEQ("bar.sync") ::"r"(id), "r"(cnt) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t cnt) { asm volatile(B200VIS_BAR_SEQ("bar.arrive") ::"r"(id), "r"(cnt) : "memory"); }
+#undef B200VIS_BAR_SEQ
+__device__ __forceinline__ float redux_min_f32(float x) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float redux_max_f32(float x) { float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void cp_async_tile_desc(Tile *dst, const Tile *src) {     // 24 bytes, 8-byte aligned on both sides
+    const uint32_t d = smem_u32(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8u), "l"(reinterpret_cast<const uint8_t *>(src) + 8) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 16u), "l"(reinterpret_cast<const uint8_t *>(src) + 16) : "memory");
+}
+// warp_view_reject with the planes in shared memory and f32 warp reductions; lane = plane * 6 + view, so that the ballot folds
+// into one bit per view with four shifts.  Returns a bit per view (views 6 and 7 are never rejected here).
+__device__ __forceinline__ uint32_t warp_view_reject_lean(const float4 *vplanes, uint32_t n_views, bool testable, bool blocks,
+                                                          float cx, float cy, float cz, float radius) {
+    const float inf = __int_as_float(0x7f800000);
+    const bool fin = testable && isfinite(((cx + cy) + cz) + radius);
+    if (__any_sync(0xFFFFFFFFu, blocks || (testable && !fin))) return 0u;
+    const float x0 = redux_min_f32(fin ? cx : inf), x1 = redux_max_f32(fin ? cx : -inf);
+    const float y0 = redux_min_f32(fin ? cy : inf), y1 = redux_max_f32(fin ? cy : -inf);
+    const float z0 = redux_min_f32(fin ? cz : inf), z1 = redux_max_f32(fin ? cz : -inf);
+    const float r1 = redux_max_f32(fin ? radius : -inf);
+    if (!(x0 <= x1)) return 0xFFu;                // no frustum-tested row in this warp (and none that blocks): nothing can be visible
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t k = (lane * 43u) >> 8, v = lane - 6u * k;      // k = lane / 6 (lane < 32), v = lane % 6
+    bool rej = false;
+    if (v < n_views && lane < 30u) {
+        const float4 n = vplanes[v * 5u + k];
+        const float m = ((fmaxf(n.x * x0, n.x * x1) + fmaxf(n.y * y0, n.y * y1)) + fmaxf(n.z * z0, n.z * z1)) + n.w;
+        const float mag = ((fabsf(n.x) * fmaxf(fabsf(x0), fabsf(x1)) + fabsf(n.y) * fmaxf(fabsf(y0), fabsf(y1))) +
+                           fabsf(n.z) * fmaxf(fabsf(z0), fabsf(z1))) + (fabsf(n.w) + fabsf(r1));
+        rej = (m + r1) + (1e-5f * mag + 1e-6f) < 0.0f;     // ~25x the rounding any exact plane_dot_point(..) + radius can carry
+    }
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, rej);
+    return (b | (b >> 6) | (b >> 12) | (b >> 18) | (b >> 24)) & 0x3Fu;
+}
+
+template <bool PROP, bool CULL, bool SIMPLE, int MINB>
+__global__ void __launch_bounds__(kTileRows, MINB)
+k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, const __grid_constant__ CullViews cvw,
+                      VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity,
+                      uint32_t *__restrict__ ticket, uint32_t ticket_base) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr bool WITH_TRS = MINB <= 4;
+    LeanSmem<WITH_TRS> &s = *reinterpret_cast<LeanSmem<WITH_TRS> *>(smem_raw);
+    const uint32_t lr = threadIdx.x;
+    const bool keeper = lr == (uint32_t)kTileRows - 1u;      // the bookkeeping thread: tickets, descriptors, TMA loads and stores
+    if (keeper) {
+        mbar_init(&s.bar[0], 1); mbar_init(&s.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // per-launch view constants: planes into shared memory, the "which views does a row have to be tested against" masks
+    uint32_t v_on = 0, v_nofr = 0;
+    if (CULL) {
+        if (lr < (uint32_t)kMaxViews * 5u) s.vplanes[lr] = cvw.planes[lr / 5u][lr % 5u];
+#pragma unroll
+        for (uint32_t v = 0; v < (uint32_t)kMaxViews; ++v) {
+            if (v < cvw.n_views) {
+                const uint32_t on = cvw.on[v];
+                if ((on & 1u) && (!SIMPLE || (on & 4u))) v_on |= 1u << v;       // active camera (SIMPLE: whose layers hold the default layer)
+                if (on & 2u) v_nofr |= 1u << v;                                  // NoCpuCulling camera: no frustum test
+            }
+        }
+    }
+    // launched with programmatic stream serialization: everything above overlapped the previous kernel's tail
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t t = blockIdx.x;
+    uint32_t k_next = n_tiles;          // keeper only: the CTA's next tile (i + 1 at the top of iteration i)
+    if (keeper && t < n_tiles) {
+        const Tile d0 = tiles[t];
+        s.tdesc[0] = d0;
+        issue_lean_loads<PROP, CULL, WITH_TRS>(R, d0, s.st[0], &s.bar[0]);
+    }
+    __syncthreads();      // barriers initialised, planes and the first descriptor staged
+    if (keeper && t < n_tiles) {
+        // Tile hand-out: a CTA starts on tile blockIdx.x and then takes the tiles the grid has not started yet in ticket order.
+        // The ticket counter is never reset: every launch draws exactly n_tiles tickets, and the host passes the running base.
+        // (behind the barrier: only this thread's warp waits for the atomic)
+        k_next = ticket ? gridDim.x + (atomicAdd(ticket, 1u) - ticket_base) : t + gridDim.x;
+        if (k_next < n_tiles) cp_async_tile_desc(&s.tdesc[1], tiles + k_next);
+    }
+    uint32_t n_gt_total = 0, n_vv_total = 0;
+    uint32_t slot = 0;                  // it % 3
+    for (uint32_t it = 0; t < n_tiles; ++it) {
+        const uint32_t sidx = it & 1u;
+        const uint32_t slot1 = slot == 2u ? 0u : slot + 1u;
+        LeanStage<WITH_TRS> &S = s.st[sidx];
+        const uint2 tb = *reinterpret_cast<const uint2 *>(&s.tdesc[slot]);     // base | n_rows, n_levels
+        const uint32_t tile_base = tb.x, tile_rows = tb.y & 0xFFFFu, tile_levels = tb.y >> 16;
+        const uint32_t off = tile_base & 15u;
+        const uint32_t li = off + lr;                 // index into the staged window
+        const bool active = lr < tile_rows;
+        const uint32_t row = tile_base + lr;
+        // columns that are not staged: plain coalesced loads issued above the wait for the tile.  Transform (MINB > 4) is consumed
+        // right behind the tile's opening barrier, the bounds only after the hierarchy walk
+        float4 tA = make_float4(0, 0, 0, 1), tB = make_float4(0, 0, 0, 1); float2 tC = make_float2(1, 1);
+        if (PROP && !WITH_TRS && active) { tA = R.trsA[row]; tB = R.trsB[row]; tC = R.trsC[row]; }
+        float4 bA = make_float4(0, 0, 0, 0); float2 bB = make_float2(0, 0);
+        if (CULL && active) { bA = R.bndA[row]; bB = R.bndB[row]; }
+        mbar_wait(&s.bar[sidx], (it >> 1) & 1u);
+        const uint32_t f = active ? S.flags[li] : 0u;
+        const uint32_t st8 = active ? S.state[li] : 0u;
+
+        // The bookkeeping thread prefetches the NEXT tile a whole walk ahead of its use: the other stage was last read by the
+        // previous tile's bulk store (issued just before, so this thread may wait here -- its warp has nothing to do until the
+        // levels above its rows are walked), and the next tile's descriptor was fetched while the previous tile was culled.
+        auto prefetch_next = [&]() {
+            const uint32_t tn = k_next;
+            if (tn < n_tiles) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                const Tile dn = s.tdesc[slot1];
+                issue_lean_loads<PROP, CULL, WITH_TRS>(R, dn, s.st[sidx ^ 1u], &s.bar[sidx ^ 1u]);
+                k_next = ticket ? gridDim.x + (atomicAdd(ticket, 1u) - ticket_base) : tn + gridDim.x;   // consumed after the walk
+            }
+            s.next_tile[sidx] = tn;      // read by everybody behind the tile's closing barrier
+        };
+        if (!PROP && keeper) prefetch_next();
+        bool visited = false, changed = false;
+        if (PROP) {
+            const uint32_t topo = active ? S.topo[li] : T_DETACHED;
+            const uint32_t depth = (topo >> 9) & 0x1FFu, plocal = topo & 0x1FFu;
+            const bool tchanged = f & F_TCHANGED;
+            const bool has_children = topo & T_HAS_CHILDREN;
+            bool dirty = tchanged;
+            if (static_opt && R.dirty != nullptr) {
+                dirty = active && R.dirty[row];
+            } else if (static_opt && tile_levels > 1 && __syncthreads_or(tchanged && depth > 0)) {
+                // only when a non-root row of the tile changed does anything have to climb: otherwise every row's
+                // TransformTreeChanged bit equals its own Changed<Transform> bit (one barrier instead of two + a climb)
+                s.parent[lr] = (uint16_t)((depth > 0) ? plocal : 0xFFFFu);
+                s.dirty[lr] = 0;
+                __syncthreads();
+                if (active && tchanged) {
+                    uint32_t c = lr;
+                    while (!s.dirty[c]) {
+                        s.dirty[c] = 1;
+                        const uint32_t p = s.parent[c];
+                        if (p == 0xFFFFu) break;
+                        c = p;
+                    }
+                }
+                __syncthreads();
+                dirty = s.dirty[lr];
+            }
+            if (keeper) prefetch_next();      // behind the tile's opening barrier(s): the walk's first warp never waits for it
+            if constexpr (WITH_TRS) { tA = S.trsA[li]; tB = S.trsB[li]; tC = S.trsC[li]; }
+            const Aff l = affine_from_trs(tA, tB, tC);
+            const uint32_t my_level = (active && !(topo & T_DETACHED)) ? depth : 0xFFFFFFFFu;
+            if (active && (topo & T_DETACHED) && has_children) s.pst[lr] = 0;
+            if (my_level == 0) {
+                Aff n = l;
+                if (topo & T_ROOT) {
+                    visited = has_children ? (!static_opt || dirty) : tchanged;
+                    changed = visited;
+                } else {
+                    const uint32_t pr = R.parent[row];
+                    const uint32_t ps = R.state[pr];
+                    visited = (ps & S_VISITED) && !(static_opt && !dirty && !(ps & S_GT_CHANGED));
+                    if (visited) {
+                        n.r0 = affine_mul_row(R.gt0[pr], l); n.r1 = affine_mul_row(R.gt1[pr], l); n.r2 = affine_mul_row(R.gt2[pr], l);
+                        changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);
+                    }
+                }
+                if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+                if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+            }
+            // one level of the walk for this thread's row: the parent's rows are the tile's own (in-place) GlobalTransform entries
+            auto walk_row = [&]() {
+                const uint32_t pst = s.pst[plocal];
+                const uint32_t pi = off + plocal;
+                visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
+                if (visited) {
+                    Aff n;
+                    n.r0 = affine_mul_row(S.gt0[pi], l); n.r1 = affine_mul_row(S.gt1[pi], l); n.r2 = affine_mul_row(S.gt2[pi], l);
+                    changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);   // set_if_neq
+                    if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
+                }
+                if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+            };
+            if (tile_levels > 1u) {
+                const uint32_t wsm = s.tdesc[slot].warp_sync_mask;
+                const unsigned long long lvl_warps = s.tdesc[slot].lvl_warps;
+                if (lvl_warps != 0ull) {
+                    // per-warp level schedule through named barriers (see kernel 1b)
+                    const uint32_t lmask = __reduce_or_sync(0xFFFFFFFFu, active ? (1u << (depth & 15u)) : 0u);
+                    uint32_t need = (lmask | (lmask << 1)) & ((1u << tile_levels) - 2u);
+                    while (need) {
+                        const uint32_t lvl = (uint32_t)__ffs((int)need) - 1u;
+                        need &= need - 1u;
+                        const bool consumer = (lmask >> lvl) & 1u;
+                        if ((wsm >> lvl) & 1u) {       // every edge into this level stays inside a warp
+                            if (!consumer) continue;
+                            __syncwarp();
+                        } else {
+                            const uint32_t cnt = ((uint32_t)(lvl_warps >> (4u * lvl)) & 15u) * 32u;
+                            if (!consumer) {
+                                asm volatile("fence.acq_rel.cta;" ::: "memory");
+                                named_bar_arrive(lvl, cnt);
+                                continue;
+                            }
+                            named_bar_sync(lvl, cnt);
+                        }
+                        if (my_level == lvl) walk_row();
+                    }
+                } else {
+                    for (uint32_t lvl = 1; lvl < tile_levels; ++lvl) {
+                        if (lvl < 32u && ((wsm >> lvl) & 1u)) __syncwarp(); else __syncthreads();
+                        if (my_level == lvl) walk_row();
+                    }
+                }
+            }
+            if (active && tchanged) R.flags[row] = (uint8_t)(f & ~F_TCHANGED);
+        }
+        // the descriptor of the tile after next: the ticket drawn at the top of this tile is back by now
+        if (keeper && k_next < n_tiles) cp_async_tile_desc(&s.tdesc[slot == 0u ? 2u : slot - 1u], tiles + k_next);
+        uint32_t out = st8 & (S_VV | S_HAS_CLASS);
+        if (PROP) out |= (changed ? S_GT_CHANGED : 0u) | (visited ? S_VISITED : 0u);
+        else out |= st8 & (S_GT_CHANGED | S_VISITED);
+
+        bool vv_changed = false;
+        if (CULL) {
+            Aff g; g.r0 = S.gt0[li]; g.r1 = S.gt1[li]; g.r2 = S.gt2[li];   // own row: written by this thread or untouched
+            const bool in_query = active && !(f & F_NO_CPU_CULL);
+            const bool base = in_query && (f & F_INHERITED);
+            const uint32_t prev = st8 & 1u;
+            const uint32_t lane = lr & 31u;
+            const bool has_aabb = f & F_AABB;
+            const bool do_test = (f & (F_AABB | F_SPHERE)) && !(f & F_NO_FRUSTUM);
+            float cx, cy, cz, radius;
+            const float hx = bA.w, hy = bB.x, hz = bB.y;
+            if (has_aabb) {
+                cx = ((g.r0.x * bA.x + g.r0.y * bA.y) + g.r0.z * bA.z) + g.r0.w;
+                cy = ((g.r1.x * bA.x + g.r1.y * bA.y) + g.r1.z * bA.z) + g.r1.w;
+                cz = ((g.r2.x * bA.x + g.r2.y * bA.y) + g.r2.z * bA.z) + g.r2.w;
+                const float vx = (g.r0.x * hx + g.r0.y * hy) + g.r0.z * hz;
+                const float vy = (g.r1.x * hx + g.r1.y * hy) + g.r1.z * hz;
+                const float vz = (g.r2.x * hx + g.r2.y * hy) + g.r2.z * hz;
+                radius = sqrtf((vx * vx + vy * vy) + vz * vz);
+            } else {
+                const bool from_gt = f & F_SPHERE_GT;
+                cx = from_gt ? g.r0.w : bA.x; cy = from_gt ? g.r1.w : bA.y; cz = from_gt ? g.r2.w : bA.z;
+                radius = bA.w;
+            }
+            unsigned long long elayers = 1ull; uint32_t erange = 0xFFFFFFFFu, rnk = row;
+            if (!SIMPLE && active) {
+                if (R.layers != nullptr) elayers = R.layers[row];
+                if ((f & F_RANGE) && R.range != nullptr) erange = range_mask_of(R, row, has_aabb, cx, cy, cz, g);
+                if (R.rank != nullptr) rnk = R.rank[row];
+            }
+            // warp-level shortcut: views whose frustum the whole warp's rows are outside of (see warp_view_reject)
+            const uint32_t rejmask = warp_view_reject_lean(s.vplanes, cvw.n_views, base && do_test, base && !do_test, cx, cy, cz, radius);
+            uint32_t todo = v_on & ~(rejmask & ~v_nofr);     // a NoCpuCulling camera lists without frustum tests: never rejected
+            bool any = false;
+            uint32_t my_ballot = 0;
+            while (todo) {
+                const uint32_t v = (uint32_t)__ffs((int)todo) - 1u;
+                todo &= todo - 1u;
+                bool vis = base;
+                if (!SIMPLE) {
+                    vis = vis && layers_intersect(R, cvw, row, v, elayers);
+                    if ((f & F_RANGE) && R.range != nullptr) {
+                        const int32_t ri = cvw.range_index[v];
+                        vis = vis && ri >= 0 && ((erange >> ri) & 1u);
+                    }
+                }
+                if (do_test && !((v_nofr >> v) & 1u)) {
+                    const float4 *pl = s.vplanes + v * 5u;
+                    float d[5];
+                    bool out_s = false;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        d[k] = plane_dot_point(pl[k], cx, cy, cz);
+                        out_s |= (d[k] + radius <= 0.0f);
+                    }
+                    vis = vis && !out_s;
+                    if (vis && has_aabb) {
+                        bool out_o = false;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            const float4 n = pl[k];
+                            const float dx = fabsf(dot3(n.x, n.y, n.z, g.r0.x, g.r1.x, g.r2.x));
+                            const float dy = fabsf(dot3(n.x, n.y, n.z, g.r0.y, g.r1.y, g.r2.y));
+                            const float dz = fabsf(dot3(n.x, n.y, n.z, g.r0.z, g.r1.z, g.r2.z));
+                            const float rr = (dx * hx + dy * hy) + dz * hz;
+                            out_o |= (d[k] + rr <= 0.0f);
+                        }
+                        vis = !out_o;
+                    }
+                }
+                any |= vis;
+                const bool listed = vis && (st8 & S_HAS_CLASS);
+                if (SIMPLE || R.rank == nullptr) {
+                    const uint32_t b = __ballot_sync(0xFFFFFFFFu, listed);
+                    if (lane == v) my_ballot = b;
+                } else if (listed) {
+                    uint32_t *mask = vb.mask + (size_t)v * vb.words_stride;
+                    uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + v) * vb.chunks_stride;
+                    atomicOr(mask + (rnk >> 5), 1u << (rnk & 31u));
+                    atomicAdd(cc + ((rnk >> 5) / kChunkWords), 1u);
+                }
+            }
+            if (my_ballot) {
+                uint32_t *mask = vb.mask + (size_t)lane * vb.words_stride;
+                uint32_t *cc = vb.chunk_count + ((size_t)parity * kMaxViews + lane) * vb.chunks_stride;
+                const uint32_t row0 = row - lane, w0 = row0 >> 5, sh = row0 & 31u;
+                const uint32_t lo = my_ballot << sh, hi = sh ? (my_ballot >> (32u - sh)) : 0u;
+                if (lo) { atomicOr(mask + w0, lo); atomicAdd(cc + (w0 / kChunkWords), __popc(lo)); }
+                if (hi) { atomicOr(mask + w0 + 1, hi); atomicAdd(cc + ((w0 + 1) / kChunkWords), __popc(hi)); }
+            }
+            if (in_query) {
+                out = (out & ~S_VV) | (any ? (1u | (prev << 1)) : 0u);
+                vv_changed = (any ? 1u : 0u) != prev;
+                if (vv_changed) out |= S_VV_CHANGED;
+            }
+        } else {
+            out |= st8 & S_VV_CHANGED;
+        }
+        if (active && out != st8) R.state[row] = (uint8_t)out;
+        // a light row publishes what assign_objects_to_clusters needs of it (GlobalTransform::translation,
+        // ViewVisibility::get) so that the cluster kernels never touch the row arrays again
+        if (CULL && R.light_snap != nullptr && (f & F_SPHERE_GT) && active) {
+            const uint32_t ord = R.light_ord[row];     // 0xFFFFFFFF: a sphere-from-GT row that is not a current light
+            if (ord < R.n_lights) R.light_snap[ord] = make_float4(S.gt0[li].w, S.gt1[li].w, S.gt2[li].w, (out & 1u) ? 1.0f : 0.0f);
+        }
+
+        // end of tile: everybody is done with this stage; count changes; write the tile's matrices back
+        n_gt_total += (PROP && changed) ? 1u : 0u;      // per-thread tallies, reduced once at the end of the kernel
+        n_vv_total += vv_changed ? 1u : 0u;
+        const int any_gt = __syncthreads_or(PROP && changed);
+        t = s.next_tile[sidx];
+        if (keeper && PROP && any_gt) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
+            const uint32_t bytes = tile_rows * 16u;
+            bulk_s2g(R.gt0 + tile_base, S.gt0 + off, bytes); bulk_s2g(R.gt1 + tile_base, S.gt1 + off, bytes);
+            bulk_s2g(R.gt2 + tile_base, S.gt2 + off, bytes);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        slot = slot1;
+    }
+    if (keeper) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // block-reduce the per-thread tallies (warp shuffle, then one shared-memory atomic per warp)
+    __shared__ uint32_t s_cnt[2];
+    if (lr < 2) s_cnt[lr] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n_gt_total += __shfl_xor_sync(0xFFFFFFFFu, n_gt_total, o); n_vv_total += __shfl_xor_sync(0xFFFFFFFFu, n_vv_total, o); }
+    if ((lr & 31u) == 0) { if (n_gt_total) atomicAdd(&s_cnt[0], n_gt_total); if (n_vv_total) atomicAdd(&s_cnt[1], n_vv_total); }
+    __syncthreads();
+    if (lr == 0) {
+        if (s_cnt[0]) atomicAdd(&stats->changed[parity][0], s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&stats->changed[parity][1], s_cnt[1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Kernel 1f (B200VIS_TILE_KERNEL=flow): the TMA-staged pass WITHOUT a CTA-wide barrier between tiles, per-warp level hand-overs
 // through named barriers, GlobalTransforms stored straight from registers.  Parity-clean, measured slower than kernel 1b
 // (DESIGN.md section 7): kept selectable as the record of that experiment.
@@ -3213,15 +3644,20 @@ static bool first_call_on_device(unsigned long long &seen) {
     seen |= bit;
     return true;
 }
-static int g_tile_kernel = -1;   // 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile (default), 2 warp per tile, 3 TMA + scout warp, 4 TMA flow (no inter-tile barrier)
+static int g_tile_kernel = -1;   // 5 lean (TMA-staged, bookkeeping thread, rolled view loop), 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile (default), 2 warp per tile, 3 TMA + scout warp, 4 TMA flow (no inter-tile barrier)
 static int tile_kernel_choice() {
     if (g_tile_kernel < 0) {
         const char *e = getenv("B200VIS_TILE_KERNEL");
-        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 'w') ? 2 : (e && e[0] == 's') ? 3 : (e && e[0] == 'f') ? 4 : 1;      // default: TMA-staged, persistent
+        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 'w') ? 2 : (e && e[0] == 's') ? 3 : (e && e[0] == 'f') ? 4 : (e && e[0] == 'l') ? 5 : 1;      // default: TMA-staged, persistent
     }
     return g_tile_kernel;
 }
-bool tile_kernel_is_tma() { return tile_kernel_choice() == 1 || tile_kernel_choice() == 3 || tile_kernel_choice() == 4; }
+static int lean_ctas_per_sm() {       // B200VIS_LEAN_CTAS = 4 | 5 | 6 resident CTAs per SM of the lean kernel
+    static int n = 0;
+    if (!n) { const char *e = getenv("B200VIS_LEAN_CTAS"); n = (e && (atoi(e) == 4 || atoi(e) == 6)) ? atoi(e) : 5; }
+    return n;
+}
+bool tile_kernel_is_tma() { return tile_kernel_choice() == 1 || tile_kernel_choice() == 3 || tile_kernel_choice() == 4 || tile_kernel_choice() == 5; }
 bool tile_kernel_publishes_light_snapshot() { return tile_kernel_choice() != 0; }
 template <bool C, bool S, int MINB, bool PIPE>
 static void launch_warp(cudaStream_t st, const Rows &R, const WarpTile *tiles, const uint8_t *sched, uint32_t n_tiles, const CullViews &cvw,
@@ -3320,17 +3756,21 @@ static void launch_scout_m(cudaStream_t st, const Rows &R, const Tile *tiles, ui
                 else launch_scout<true, false, MINB>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity); }
     else launch_scout<false, true, MINB>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
 }
-template <bool P, bool C, bool S, bool FLOW>
+template <bool P, bool C, bool S, int KIND>      // KIND: 0 kernel 1b, 1 flow, 4 / 5 / 6 lean with that many CTAs per SM
 static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                        const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity, uint32_t *ticket, uint32_t *ticket_base) {
     static int grid = 0;
     static unsigned long long seen = 0;
+    constexpr bool FLOW = KIND == 1;
+    auto kern = KIND == 1 ? k_propagate_cull_flow<P, C, S> : KIND == 4 ? k_propagate_cull_lean<P, C, S, 4> : KIND == 5 ? k_propagate_cull_lean<P, C, S, 5> :
+                KIND == 6 ? k_propagate_cull_lean<P, C, S, 6> : k_propagate_cull_tma<P, C, S>;
+    constexpr size_t smem = KIND == 4 ? sizeof(LeanSmem<true>) : KIND >= 5 ? sizeof(LeanSmem<false>) : sizeof(TmaSmem);
     if (first_call_on_device(seen)) {
-        cudaFuncSetAttribute((FLOW ? k_propagate_cull_flow<P, C, S> : k_propagate_cull_tma<P, C, S>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem));
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (FLOW ? k_propagate_cull_flow<P, C, S> : k_propagate_cull_tma<P, C, S>), kTileRows, sizeof(TmaSmem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileRows, smem);
         grid = sms * (per_sm > 0 ? per_sm : 1);    // persistent: one CTA per resident slot
     }
     uint32_t g = n_tiles < (uint32_t)grid ? n_tiles : (uint32_t)grid;
@@ -3352,7 +3792,7 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
     // programmatic dependent launch: this kernel's CTAs may become resident (barrier init, parameter loads) while the
     // previous kernel in the stream drains; griddepcontrol.wait in the kernel orders the actual data accesses
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(g); cfg.blockDim = dim3(kTileRows); cfg.dynamicSmemBytes = sizeof(TmaSmem); cfg.stream = st;
+    cfg.gridDim = dim3(g); cfg.blockDim = dim3(kTileRows); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -3362,7 +3802,7 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
     if (dynamic < 0) { const char *e = getenv("B200VIS_TILE_HANDOUT"); dynamic = (e && e[0] == 's') ? 0 : 1; }
     uint32_t *tk = nullptr, base = 0;
     if (!FLOW && dynamic && tiles_per_cta == 0 && ticket && ticket_base) { tk = ticket; base = *ticket_base; *ticket_base += n_tiles; }
-    ++g_launches; cudaLaunchKernelEx(&cfg, (FLOW ? k_propagate_cull_flow<P, C, S> : k_propagate_cull_tma<P, C, S>), R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, tk, base);
+    ++g_launches; cudaLaunchKernelEx(&cfg, kern, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, tk, base);
 }
 // tiles of <= 32 rows (the tops of split deep tiles): the classic kernel with one warp per tile, 16 CTAs per SM
 void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
@@ -3389,9 +3829,12 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
         else launch_scout_m<3>(st, R, tiles, n_tiles, cvw, vb, stats, cull, simple, static_opt, parity);
         return;
     }
-    if (tile_kernel_choice() == 1 || tile_kernel_choice() == 3 || tile_kernel_choice() == 4) {
-#define B200VIS_LAUNCH_TMA(P, C, S) do { if (tile_kernel_choice() == 4) launch_tma<P, C, S, true>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
-                                         else launch_tma<P, C, S, false>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); } while (0)
+    if (tile_kernel_is_tma()) {
+#define B200VIS_LAUNCH_TMA(P, C, S) do { if (tile_kernel_choice() == 4) launch_tma<P, C, S, 1>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
+                                         else if (tile_kernel_choice() == 5 && lean_ctas_per_sm() == 4) launch_tma<P, C, S, 4>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
+                                         else if (tile_kernel_choice() == 5 && lean_ctas_per_sm() == 6) launch_tma<P, C, S, 6>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
+                                         else if (tile_kernel_choice() == 5) launch_tma<P, C, S, 5>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
+                                         else launch_tma<P, C, S, 0>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); } while (0)
         if (prop && cull) { if (simple) B200VIS_LAUNCH_TMA(true, true, true); else B200VIS_LAUNCH_TMA(true, true, false); }
         else if (prop) B200VIS_LAUNCH_TMA(true, false, true);
         else if (cull) { if (simple) B200VIS_LAUNCH_TMA(false, true, true); else B200VIS_LAUNCH_TMA(false, true, false); }
