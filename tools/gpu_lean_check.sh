@@ -1,20 +1,19 @@
 #!/bin/bash
-# one GPU call: timing of the default and the lean tile kernel (4 / 5 / 6 CTAs per SM), bench-scale parity of the lean kernel,
-# the small parity suites under it, ncu --set full captures
+# one GPU call: lean tile kernel with the top levels walked in registers (default) vs through the level loop (B200VIS_LEAN_PROBE=4)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
 echo "== timing";
+export B200VIS_TILE_KERNEL=lean B200VIS_LEAN_CTAS=4
+B200VIS_LEAN_PROBE=4 timeout 120 python tools/tile_variants.py
 timeout 120 python tools/tile_variants.py
-for n in 4 5 6; do B200VIS_TILE_KERNEL=lean B200VIS_LEAN_CTAS=$n timeout 120 python tools/tile_variants.py; done
-echo "== bench-scale parity (lean)";
-timeout 500 python -m pytest tests/test_gpu_bench_scale.py -q -x -m gpu -k "lean" 2>&1 | tail -15
-echo "== small suites under lean 5 / 6";
-B200VIS_TILE_KERNEL=lean timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py -q -x -m gpu 2>&1 | tail -4
-B200VIS_TILE_KERNEL=lean B200VIS_LEAN_CTAS=6 timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py -q -x -m gpu 2>&1 | tail -4
-echo "== ncu lean";
-for n in 5 6; do
-B200VIS_TILE_KERNEL=lean B200VIS_LEAN_CTAS=$n timeout 200 ncu --set full --import-source on --clock-control none -k regex:k_propagate_cull_lean --launch-skip 40 --launch-count 1 -f -o gpurun_out/r02d_lean$n python tools/tile_variants.py 2>&1 | tail -2
-done
+B200VIS_LEAN_PROBE=4 timeout 120 python tools/tile_variants.py
+timeout 120 python tools/tile_variants.py
+echo "== parity (lean4)";
+timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py -q -x -m gpu 2>&1 | tail -4
+unset B200VIS_TILE_KERNEL B200VIS_LEAN_CTAS
+timeout 400 python -m pytest tests/test_gpu_bench_scale.py -q -x -m gpu -k "lean" 2>&1 | tail -5
+echo "== ncu lean4";
+B200VIS_TILE_KERNEL=lean B200VIS_LEAN_CTAS=4 timeout 200 ncu --set full --import-source on --clock-control none -k regex:k_propagate_cull_lean --launch-skip 40 --launch-count 1 -f -o gpurun_out/r02f_lean4top python tools/tile_variants.py 2>&1 | tail -2
 } > gpurun_out/lean_check.log 2>&1
 tail -40 gpurun_out/lean_check.log
