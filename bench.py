@@ -847,8 +847,8 @@ def main():
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         algo_bytes = n * ALGO_BYTES_PER_ENTITY + 4 * visible_pairs_rank
         achieved = algo_bytes / (tile_ms_avg * 1e-3) / 1e9
-        tile_kernel = {"c": "k_propagate_cull", "s": "k_propagate_cull_scout", "w": "k_tile_warp", "f": "k_propagate_cull_flow"}.get(
-            os.environ.get("B200VIS_TILE_KERNEL", "t")[:1], "k_propagate_cull_tma")
+        tile_kernel = {"c": "k_propagate_cull", "s": "k_propagate_cull_scout", "w": "k_tile_warp", "f": "k_propagate_cull_flow",
+                       "t": "k_propagate_cull_tma"}.get(os.environ.get("B200VIS_TILE_KERNEL", "l")[:1], "k_propagate_cull_lean")
         cfg_out = dict(cfg)
         line = {
             "metric": METRIC, "value": value, "unit": "entities/s", "n_gpus": world, "steps": K, "warmup": W,

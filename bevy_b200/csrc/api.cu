@@ -93,6 +93,7 @@ struct b200vis_ctx {
     uint32_t *d_tile_ticket = nullptr; uint32_t tile_ticket_base = 0;   // dynamic tile hand-out of the default kernel: never reset, the host tracks the base
     std::vector<uint32_t> pass_begin;   // tile index ranges per pass: [pass_begin[p], pass_begin[p+1])
     std::vector<uint32_t> pass_small;   // the first pass_small[p] tiles of pass p have <= 32 rows (B200VIS_SPLIT_DEEP_TILES)
+    std::vector<uint8_t> pass_named;    // every tile of pass p is flat or walks with named level barriers (Tile::lvl_warps): the tile kernel may let a CTA's warps drift a tile apart
     int static_opt = 1;
 
     // per-frame constants
@@ -683,6 +684,10 @@ extern "C" int32_t b200vis_set_topology(b200vis_ctx *ctx, uint32_t n, const uint
     }
     ctx->pass_begin = pass_begin;
     ctx->pass_small = pass_small;
+    ctx->pass_named.assign(pass_begin.empty() ? 0 : pass_begin.size() - 1, 1);
+    for (size_t pi = 0; pi + 1 < pass_begin.size(); ++pi)
+        for (uint32_t ti = pass_begin[pi]; ti < pass_begin[pi + 1]; ++ti)
+            if (tiles[ti].n_levels > 1 && tiles[ti].lvl_warps == 0ull) { ctx->pass_named[pi] = 0; break; }
     ctx->rank_identity = sorted;
     ctx->n = n;
     ctx->rows.n = n;
@@ -1371,7 +1376,8 @@ extern "C" int32_t b200vis_run(b200vis_ctx *ctx, uint32_t stages) {
                                      cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot, ctx->d_tile_counter);
                 else
                     launch_propagate_cull(st, R, ctx->d_tiles + b + ns, ctx->pass_begin[p + 1] - b - ns,
-                                          cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot, ctx->d_tile_ticket, &ctx->tile_ticket_base);
+                                          cvw, vb, ctx->d_stats, tile_stages, (uint32_t)ctx->static_opt, cslot, ctx->d_tile_ticket, &ctx->tile_ticket_base,
+                                          p < ctx->pass_named.size() && ctx->pass_named[p] != 0);
             }
         } else if (n_pass) {
             launch_cull(st, R, cvw, vb, ctx->d_stats, cslot);

@@ -815,8 +815,10 @@ struct LeanSmem {
     Tile tdesc[3];                   // descriptor of the CTA's i-th tile in slot i % 3 (i+2 is fetched while i is processed)
     uint32_t next_tile[2];
     float4 vplanes[kMaxViews * 5];   // the views' culling planes, [view][L,R,T,B,Near]
+    unsigned long long done[2];      // PIPE: all 8 warps are through with the tile in stage s (one arrival per warp)
+    uint32_t anyflag[2];             // PIPE: some row of the tile in stage s got a new GlobalTransform (the stage has to be stored)
     uint16_t parent[kTileRows];
-    uint8_t pst[kTileRows];          // bit0 visited, bit1 gt changed
+    uint8_t pst[2][kTileRows];       // bit0 visited, bit1 gt changed; PIPE: one copy per stage, else copy 0
     uint8_t dirty[kTileRows];
 };
 template <bool PROP, bool CULL, bool WITH_TRS>
@@ -886,7 +888,18 @@ __device__ __forceinline__ uint32_t warp_view_reject_lean(const float4 *vplanes,
     return (b | (b >> 6) | (b >> 12) | (b >> 18) | (b >> 24)) & 0x3Fu;
 }
 
-template <bool PROP, bool CULL, bool SIMPLE, int MINB>
+// PIPE (PROP && CULL, MINB == 4; host side: every tile of the launch is flat or walks with named level barriers): the CTA's warps
+// are NOT held together at tile boundaries.  What bounds a tile's time is the longest dependent instruction stream through it
+// (a warp issues an instruction every ~7 cycles here whatever the occupancy: ncu r02, probes in DESIGN.md section 7): prologue ->
+// top levels (warp 0) -> level K .. 7 hand-overs -> the leaf warps' cull -> closing barrier.  Without the closing barrier, warp 0
+// starts the next tile's top levels while the leaf warps still cull this one, and the chain of tile k+1 runs under the cull of tile
+// k.  Protocol: a warp that is through with a tile arrives on done[stage] (mbarrier, 8 arrivals) and moves on; only the bookkeeping
+// thread waits for it, stores the stage and reloads it with the tile after next.  A tile is loaded after every warp has left the
+// tile two before it, so the warps of a CTA are never more than one tile apart: everything per-tile exists twice (stages, pst, the
+// named barrier ids lvl + 8 * stage, done, anyflag).  The next tile index travels with the TMA barrier (written before the
+// arrive.expect_tx that releases it; "no more tiles" is an arrive without bytes).  mark_dirty_trees' "did a non-root row change"
+// is answered by every warp for itself from the staged flags (8 rows per lane) instead of a CTA-wide vote.
+template <bool PROP, bool CULL, bool SIMPLE, int MINB, bool PIPE = false>
 __global__ void __launch_bounds__(kTileRows, MINB)
 k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, const __grid_constant__ CullViews cvw,
                       VisibleBufs vb, DevStats *__restrict__ stats, uint32_t static_opt, uint32_t parity,
@@ -900,8 +913,11 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
     const uint32_t lr = threadIdx.x ^ (warp_flip & 0xE0u);
     const uint32_t probe = warp_flip >> 8;     // bits 0-1: timing probes (results are WRONG): 1 = no level hand-overs at all, 2 = none for levels 1..4; bit 2: top levels through the level loop (A/B switch, correct)
     const bool keeper = lr == (uint32_t)kTileRows - 1u;      // the bookkeeping thread: tickets, descriptors, TMA loads and stores
+    static_assert(!PIPE || (PROP && CULL && MINB == 4), "PIPE needs the fused pass with staged Transforms");
     if (keeper) {
         mbar_init(&s.bar[0], 1); mbar_init(&s.bar[1], 1);
+        mbar_init(&s.done[0], kTileRows / 32); mbar_init(&s.done[1], kTileRows / 32);
+        s.anyflag[0] = 0; s.anyflag[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // per-launch view constants: planes into shared memory, the "which views does a row have to be tested against" masks
@@ -938,8 +954,15 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
     uint32_t slot = 0;                  // it % 3
     for (uint32_t it = 0; t < n_tiles; ++it) {
         const uint32_t sidx = it & 1u;
+        const uint32_t pp = PIPE ? sidx : 0u;        // which copy of the per-tile scratch
         const uint32_t slot1 = slot == 2u ? 0u : slot + 1u;
         LeanStage<WITH_TRS> &S = s.st[sidx];
+        if constexpr (PIPE) {
+            // the tile has landed -- or the bookkeeping thread has signalled that there is none; either way what it wrote before
+            // (next tile index, the tile's descriptor) is visible behind this wait
+            mbar_wait(&s.bar[sidx], (it >> 1) & 1u);
+            if (it > 0u) { t = s.next_tile[sidx ^ 1u]; if (t >= n_tiles) break; }
+        }
         const uint2 tb = *reinterpret_cast<const uint2 *>(&s.tdesc[slot]);     // base | n_rows, n_levels
         const uint32_t tile_base = tb.x, tile_rows = tb.y & 0xFFFFu, tile_levels = tb.y >> 16;
         const uint32_t off = tile_base & 15u;
@@ -952,7 +975,7 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
         if (PROP && !WITH_TRS && active) { tA = R.trsA[row]; tB = R.trsB[row]; tC = R.trsC[row]; }
         float4 bA = make_float4(0, 0, 0, 0); float2 bB = make_float2(0, 0);
         if (CULL && active) { bA = R.bndA[row]; bB = R.bndB[row]; }
-        mbar_wait(&s.bar[sidx], (it >> 1) & 1u);
+        if constexpr (!PIPE) mbar_wait(&s.bar[sidx], (it >> 1) & 1u);
         const uint32_t f = active ? S.flags[li] : 0u;
         const uint32_t st8 = active ? S.state[li] : 0u;
 
@@ -961,14 +984,16 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
         // levels above its rows are walked), and the next tile's descriptor was fetched while the previous tile was culled.
         auto prefetch_next = [&]() {
             const uint32_t tn = k_next;
+            s.next_tile[sidx] = tn;      // read by everybody behind the tile's closing barrier (PIPE: behind the next stage's TMA barrier)
             if (tn < n_tiles) {
                 asm volatile("cp.async.wait_all;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 const Tile dn = s.tdesc[slot1];
                 issue_lean_loads<PROP, CULL, WITH_TRS>(R, dn, s.st[sidx ^ 1u], &s.bar[sidx ^ 1u]);
                 k_next = ticket ? gridDim.x + (atomicAdd(ticket, 1u) - ticket_base) : tn + gridDim.x;   // consumed after the walk
+            } else if (PIPE) {
+                mbar_arrive_cta(&s.bar[sidx ^ 1u]);      // no more tiles: complete the phase the CTA's warps will wait on
             }
-            s.next_tile[sidx] = tn;      // read by everybody behind the tile's closing barrier
         };
         if (!PROP && keeper) prefetch_next();
         bool visited = false, changed = false;
@@ -979,9 +1004,23 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
             const bool has_children = topo & T_HAS_CHILDREN;
             bool dirty = tchanged;
             bool climbed = false;      // s.dirty[] holds this tile's TransformTreeChanged bits
+            bool must_climb = false;
+            if (static_opt && R.dirty == nullptr && tile_levels > 1) {
+                if constexpr (PIPE) {
+                    // every warp answers for the whole tile from the staged columns: 8 rows per lane, no CTA-wide vote
+                    const uint32_t r0 = (lr & 31u) * 8u;
+                    bool mine = false;
+#pragma unroll
+                    for (uint32_t j = 0; j < 8u; ++j)
+                        if (r0 + j < tile_rows) mine |= (S.flags[off + r0 + j] & F_TCHANGED) && (((S.topo[off + r0 + j] >> 9) & 0x1FFu) > 0u);
+                    must_climb = __any_sync(0xFFFFFFFFu, mine);
+                } else {
+                    must_climb = __syncthreads_or(tchanged && depth > 0);
+                }
+            }
             if (static_opt && R.dirty != nullptr) {
                 dirty = active && R.dirty[row];
-            } else if (static_opt && tile_levels > 1 && __syncthreads_or(tchanged && depth > 0)) {
+            } else if (must_climb) {
                 climbed = true;
                 // only when a non-root row of the tile changed does anything have to climb: otherwise every row's
                 // TransformTreeChanged bit equals its own Changed<Transform> bit (one barrier instead of two + a climb)
@@ -1002,7 +1041,7 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
             }
             if (keeper) prefetch_next();      // behind the tile's opening barrier(s): the walk's first warp never waits for it
             const uint32_t my_level = (active && !(topo & T_DETACHED)) ? depth : 0xFFFFFFFFu;
-            if (active && (topo & T_DETACHED) && has_children) s.pst[lr] = 0;
+            if (active && (topo & T_DETACHED) && has_children) s.pst[pp][lr] = 0;
             // ---- the tile's TOP LEVELS in registers (tiles whose first K >= 2 depth levels sit among the first 32 rows: a BFS-ordered
             // tree).  The rows of those levels form a serial chain of K matrix products that every other row of the tile waits for.
             // Level by level through shared memory that chain costs a store / __syncwarp / load round trip and a pass through the
@@ -1060,7 +1099,7 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
                 if (my_level < top_k) {
                     visited = vis; changed = chg;
                     if (chg) { S.gt0[li] = G.r0; S.gt1[li] = G.r1; S.gt2[li] = G.r2; }
-                    if (has_children) s.pst[lr] = (uint8_t)((vis ? 1u : 0u) | (chg ? 2u : 0u));
+                    if (has_children) s.pst[pp][lr] = (uint8_t)((vis ? 1u : 0u) | (chg ? 2u : 0u));
                 }
             }
             if (my_level == 0 && !top_k) {
@@ -1078,11 +1117,11 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
                     }
                 }
                 if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
-                if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+                if (has_children) s.pst[pp][lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
             }
             // one level of the walk for this thread's row: the parent's rows are the tile's own (in-place) GlobalTransform entries
             auto walk_row = [&]() {
-                const uint32_t pst = s.pst[plocal];
+                const uint32_t pst = s.pst[pp][plocal];
                 const uint32_t pi = off + plocal;
                 visited = (pst & 1u) && !(static_opt && !dirty && !(pst & 2u));
                 if (visited) {
@@ -1091,7 +1130,7 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
                     changed = row_neq(n.r0, S.gt0[li]) | row_neq(n.r1, S.gt1[li]) | row_neq(n.r2, S.gt2[li]);   // set_if_neq
                     if (changed) { S.gt0[li] = n.r0; S.gt1[li] = n.r1; S.gt2[li] = n.r2; }
                 }
-                if (has_children) s.pst[lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
+                if (has_children) s.pst[pp][lr] = (uint8_t)((visited ? 1u : 0u) | (changed ? 2u : 0u));
             };
             if (tile_levels > 1u) {
                 if (lvl_warps != 0ull) {
@@ -1112,10 +1151,15 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
                             const uint32_t cnt = ((uint32_t)(lvl_warps >> (4u * lvl)) & 15u) * 32u;
                             if (!consumer) {
                                 asm volatile("fence.acq_rel.cta;" ::: "memory");
-                                named_bar_arrive(lvl, cnt);
+                                // (4 CTAs per SM may own 16 hardware barriers each: a register id costs nothing there)
+                                if constexpr (PIPE) asm volatile("bar.arrive %0, %1;" ::"r"(lvl + 8u * sidx), "r"(cnt) : "memory");
+                                else if constexpr (MINB <= 4) asm volatile("bar.arrive %0, %1;" ::"r"(lvl), "r"(cnt) : "memory");
+                                else named_bar_arrive(lvl, cnt);
                                 continue;
                             }
-                            named_bar_sync(lvl, cnt);
+                            if constexpr (PIPE) asm volatile("bar.sync %0, %1;" ::"r"(lvl + 8u * sidx), "r"(cnt) : "memory");
+                            else if constexpr (MINB <= 4) asm volatile("bar.sync %0, %1;" ::"r"(lvl), "r"(cnt) : "memory");
+                            else named_bar_sync(lvl, cnt);
                         }
                         if (my_level == lvl) walk_row();
                     }
@@ -1243,8 +1287,22 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
         // end of tile: everybody is done with this stage; count changes; write the tile's matrices back
         n_gt_total += (PROP && changed) ? 1u : 0u;      // per-thread tallies, reduced once at the end of the kernel
         n_vv_total += vv_changed ? 1u : 0u;
-        const int any_gt = __syncthreads_or(PROP && changed);
-        t = s.next_tile[sidx];
+        int any_gt;
+        if constexpr (PIPE) {
+            // this warp is through with the stage: say so and move on; only the bookkeeping thread waits for the other warps
+            if (__any_sync(0xFFFFFFFFu, changed) && (lr & 31u) == 0u) s.anyflag[sidx] = 1u;
+            __syncwarp();
+            if ((lr & 31u) == 0u) mbar_arrive_cta(&s.done[sidx]);
+            any_gt = 0;
+            if (keeper) {
+                mbar_wait_guarded(&s.done[sidx], (it >> 1) & 1u);
+                any_gt = (int)s.anyflag[sidx];
+                s.anyflag[sidx] = 0u;       // the next writers (two tiles on) start behind the load this thread issues after this
+            }
+        } else {
+            any_gt = __syncthreads_or(PROP && changed);
+            t = s.next_tile[sidx];
+        }
         if (keeper && PROP && any_gt) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
             const uint32_t bytes = tile_rows * 16u;
@@ -3713,14 +3771,19 @@ static int g_tile_kernel = -1;   // 5 lean (TMA-staged, bookkeeping thread, roll
 static int tile_kernel_choice() {
     if (g_tile_kernel < 0) {
         const char *e = getenv("B200VIS_TILE_KERNEL");
-        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 'w') ? 2 : (e && e[0] == 's') ? 3 : (e && e[0] == 'f') ? 4 : (e && e[0] == 'l') ? 5 : 1;      // default: TMA-staged, persistent
+        g_tile_kernel = (e && e[0] == 'c') ? 0 : (e && e[0] == 'w') ? 2 : (e && e[0] == 's') ? 3 : (e && e[0] == 'f') ? 4 : (e && e[0] == 't') ? 1 : 5;      // default: lean (kernel 1L); tma = kernel 1b
     }
     return g_tile_kernel;
 }
 static int lean_ctas_per_sm() {       // B200VIS_LEAN_CTAS = 4 | 5 | 6 resident CTAs per SM of the lean kernel
     static int n = 0;
-    if (!n) { const char *e = getenv("B200VIS_LEAN_CTAS"); n = (e && (atoi(e) == 4 || atoi(e) == 6)) ? atoi(e) : 5; }
+    if (!n) { const char *e = getenv("B200VIS_LEAN_CTAS"); n = (e && (atoi(e) == 5 || atoi(e) == 6)) ? atoi(e) : 4; }
     return n;
+}
+static bool lean_pipe() {       // B200VIS_LEAN_PIPE=1: the CTA's warps are not held together at tile boundaries (measured slower: DESIGN.md section 7)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("B200VIS_LEAN_PIPE"); v = (e && atoi(e) == 1) ? 1 : 0; }
+    return v != 0;
 }
 bool tile_kernel_is_tma() { return tile_kernel_choice() == 1 || tile_kernel_choice() == 3 || tile_kernel_choice() == 4 || tile_kernel_choice() == 5; }
 bool tile_kernel_publishes_light_snapshot() { return tile_kernel_choice() != 0; }
@@ -3821,18 +3884,19 @@ static void launch_scout_m(cudaStream_t st, const Rows &R, const Tile *tiles, ui
                 else launch_scout<true, false, MINB>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity); }
     else launch_scout<false, true, MINB>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity);
 }
-template <bool P, bool C, bool S, int KIND>      // KIND: 0 kernel 1b, 1 flow, 4 / 5 / 6 lean with that many CTAs per SM
+template <bool P, bool C, bool S, int KIND>      // KIND: 0 kernel 1b, 1 flow, 4 / 5 / 6 lean with that many CTAs per SM, 7 lean with drifting warps (PIPE)
 static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                        const VisibleBufs &vb, DevStats *stats, uint32_t static_opt, uint32_t parity, uint32_t *ticket, uint32_t *ticket_base) {
     static int grid = 0;
     static unsigned long long seen = 0;
     constexpr bool FLOW = KIND == 1;
-    constexpr size_t smem = KIND == 4 ? sizeof(LeanSmem<true>) : KIND >= 5 ? sizeof(LeanSmem<false>) : sizeof(TmaSmem);
+    constexpr size_t smem = (KIND == 4 || KIND == 7) ? sizeof(LeanSmem<true>) : KIND >= 5 ? sizeof(LeanSmem<false>) : sizeof(TmaSmem);
     auto with_kernel = [&](auto &&fn) {
         if constexpr (KIND == 1) fn(k_propagate_cull_flow<P, C, S>);
         else if constexpr (KIND == 4) fn(k_propagate_cull_lean<P, C, S, 4>);
         else if constexpr (KIND == 5) fn(k_propagate_cull_lean<P, C, S, 5>);
         else if constexpr (KIND == 6) fn(k_propagate_cull_lean<P, C, S, 6>);
+        else if constexpr (KIND == 7) fn(k_propagate_cull_lean<P, C, S, 4, P && C>);
         else fn(k_propagate_cull_tma<P, C, S>);
     };
     if (first_call_on_device(seen)) {
@@ -3877,8 +3941,8 @@ static void launch_tma(cudaStream_t st, const Rows &R, const Tile *tiles, uint32
     ++g_launches;
     with_kernel([&](auto kern) {
         if constexpr (KIND >= 4) {
-            static int flip = -1;     // B200VIS_LEAN_WARP_FLIP=0 keeps the CTA's warps in thread order
-            if (flip < 0) { const char *e = getenv("B200VIS_LEAN_WARP_FLIP"); flip = (e && atoi(e) == 0) ? 0 : 0xE0; }
+            static int flip = -1;     // B200VIS_LEAN_WARP_FLIP=1 reverses the CTA's warp order (no measurable effect: DESIGN.md section 7)
+            if (flip < 0) { const char *e = getenv("B200VIS_LEAN_WARP_FLIP"); flip = (e && atoi(e) == 1) ? 0xE0 : 0; }
             static int probe = -1;    // B200VIS_LEAN_PROBE: timing probes, wrong results (tools/ only)
             if (probe < 0) { const char *e = getenv("B200VIS_LEAN_PROBE"); probe = e ? atoi(e) : 0; }
             cudaLaunchKernelEx(&cfg, kern, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, tk, base, (uint32_t)flip | ((uint32_t)probe << 8));
@@ -3901,7 +3965,7 @@ void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *til
 }
 void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                            const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity,
-                           uint32_t *ticket, uint32_t *ticket_base) {
+                           uint32_t *ticket, uint32_t *ticket_base, bool named_levels_only) {
     if (n_tiles == 0) return;
     const bool prop = stages & 1u, cull = stages & 2u;
     const bool simple = R.layers == nullptr && R.layers_ext == nullptr && R.range == nullptr && R.rank == nullptr;
@@ -3914,6 +3978,7 @@ void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, ui
     }
     if (tile_kernel_is_tma()) {
 #define B200VIS_LAUNCH_TMA(P, C, S) do { if (tile_kernel_choice() == 4) launch_tma<P, C, S, 1>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
+                                         else if (tile_kernel_choice() == 5 && lean_ctas_per_sm() == 4 && (P) && (C) && named_levels_only && lean_pipe()) launch_tma<P, C, S, 7>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
                                          else if (tile_kernel_choice() == 5 && lean_ctas_per_sm() == 4) launch_tma<P, C, S, 4>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
                                          else if (tile_kernel_choice() == 5 && lean_ctas_per_sm() == 6) launch_tma<P, C, S, 6>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \
                                          else if (tile_kernel_choice() == 5) launch_tma<P, C, S, 5>(st, R, tiles, n_tiles, cvw, vb, stats, static_opt, parity, ticket, ticket_base); \

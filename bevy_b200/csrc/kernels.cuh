@@ -6,7 +6,7 @@
 namespace b200vis {
 void launch_propagate_cull(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                            const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity,
-                           uint32_t *ticket = nullptr, uint32_t *ticket_base = nullptr);
+                           uint32_t *ticket = nullptr, uint32_t *ticket_base = nullptr, bool named_levels_only = false);
 void launch_propagate_cull_small(cudaStream_t st, const Rows &R, const Tile *tiles, uint32_t n_tiles, const CullViews &cvw,
                                  const VisibleBufs &vb, DevStats *stats, uint32_t stages, uint32_t static_opt, uint32_t parity);
 unsigned long long kernel_launch_count();
