@@ -815,6 +815,7 @@ struct LeanSmem {
     Tile tdesc[3];                   // descriptor of the CTA's i-th tile in slot i % 3 (i+2 is fetched while i is processed)
     uint32_t next_tile[2];
     float4 vplanes[kMaxViews * 5];   // the views' culling planes, [view][L,R,T,B,Near]
+    float vlen[kMaxViews * 5];       // |normal| of each plane, rounded up (1 for normalised half spaces)
     unsigned long long done[2];      // PIPE: all 8 warps are through with the tile in stage s (one arrival per warp)
     uint32_t anyflag[2];             // PIPE: some row of the tile in stage s got a new GlobalTransform (the stage has to be stored)
     uint16_t parent[kTileRows];
@@ -888,6 +889,37 @@ __device__ __forceinline__ uint32_t warp_view_reject_lean(const float4 *vplanes,
     return (b | (b >> 6) | (b >> 12) | (b >> 18) | (b >> 24)) & 0x3Fu;
 }
 
+// The same shortcut with a bounding SPHERE instead of a box: centre c0 = the bounding-sphere centre of the warp's first frustum-tested
+// row, radius Rmax = max over its rows of |c_i - c0|_1 + r_i (the 1-norm bounds the 2-norm from above and needs no square root).
+// For a plane (n, w): n.c_i + w + r_i <= n.c0 + w + |n| * Rmax, so a plane the sphere is behind -- by the same float margin as
+// above, `len` being max(|n| rounded up, 1) (1 for Bevy's normalised half spaces) -- has every row of the warp behind it in
+// Frustum::intersects_sphere.  Looser than the box by at most sqrt(3) in radius, a third of the instructions: 3 shuffles and one
+// warp reduction instead of seven reductions.  vlen[v * 5 + k] = |n| of plane k of view v (staged once per CTA).
+__device__ __forceinline__ uint32_t warp_view_reject_sphere(const float4 *vplanes, const float *vlen, uint32_t n_views, bool testable, bool blocks,
+                                                            float cx, float cy, float cz, float radius) {
+    const bool fin = testable && isfinite(((cx + cy) + cz) + radius);
+    if (__any_sync(0xFFFFFFFFu, blocks || (testable && !fin))) return 0u;
+    const uint32_t have = __ballot_sync(0xFFFFFFFFu, fin);
+    if (!have) return 0xFFu;                      // no frustum-tested row in this warp (and none that blocks): nothing can be visible
+    const int src = __ffs((int)have) - 1;
+    const float x0 = __shfl_sync(0xFFFFFFFFu, cx, src), y0 = __shfl_sync(0xFFFFFFFFu, cy, src), z0 = __shfl_sync(0xFFFFFFFFu, cz, src);
+    const float mine = ((fabsf(cx - x0) + fabsf(cy - y0)) + fabsf(cz - z0)) + fabsf(radius);
+    const float rmax = redux_max_f32(fin ? mine : 0.0f);
+    if (!isfinite(rmax)) return 0u;               // (differences of huge finite centres)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t k = (lane * 43u) >> 8, v = lane - 6u * k;      // k = lane / 6 (lane < 32), v = lane % 6
+    bool rej = false;
+    if (v < n_views && lane < 30u) {
+        const float4 n = vplanes[v * 5u + k];
+        const float reach = vlen[v * 5u + k] * rmax;
+        const float d = ((n.x * x0 + n.y * y0) + n.z * z0) + n.w;
+        const float mag = ((fabsf(n.x * x0) + fabsf(n.y * y0)) + fabsf(n.z * z0)) + (fabsf(n.w) + reach);
+        rej = (d + reach) + (1e-5f * mag + 1e-6f) < 0.0f;      // ~25x the rounding of either side
+    }
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, rej);
+    return (b | (b >> 6) | (b >> 12) | (b >> 18) | (b >> 24)) & 0x3Fu;
+}
+
 // PIPE (PROP && CULL, MINB == 4; host side: every tile of the launch is flat or walks with named level barriers): the CTA's warps
 // are NOT held together at tile boundaries.  What bounds a tile's time is the longest dependent instruction stream through it
 // (a warp issues an instruction every ~7 cycles here whatever the occupancy: ncu r02, probes in DESIGN.md section 7): prologue ->
@@ -911,7 +943,7 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
     // levels -- the serial chain every other warp waits for -- then sit in the CTA's LAST hardware warp, which the SM's issue
     // arbiter prefers (highest warp id first) when several warps are eligible
     const uint32_t lr = threadIdx.x ^ (warp_flip & 0xE0u);
-    const uint32_t probe = warp_flip >> 8;     // bits 0-1: timing probes (results are WRONG): 1 = no level hand-overs at all, 2 = none for levels 1..4; bit 2: top levels through the level loop (A/B switch, correct)
+    const uint32_t probe = warp_flip >> 8;     // bits 0-1: timing probes (results are WRONG): 1 = no level hand-overs at all, 2 = none for levels 1..4; bit 2: top levels through the level loop, bit 3: box instead of sphere in the warp-level view rejection (A/B switches, correct results)
     const bool keeper = lr == (uint32_t)kTileRows - 1u;      // the bookkeeping thread: tickets, descriptors, TMA loads and stores
     static_assert(!PIPE || (PROP && CULL && MINB == 4), "PIPE needs the fused pass with staged Transforms");
     if (keeper) {
@@ -923,7 +955,11 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
     // per-launch view constants: planes into shared memory, the "which views does a row have to be tested against" masks
     uint32_t v_on = 0, v_nofr = 0;
     if (CULL) {
-        if (lr < (uint32_t)kMaxViews * 5u) s.vplanes[lr] = cvw.planes[lr / 5u][lr % 5u];
+        if (lr < (uint32_t)kMaxViews * 5u) {
+            const float4 pl = cvw.planes[lr / 5u][lr % 5u];
+            s.vplanes[lr] = pl;
+            s.vlen[lr] = fmaxf(sqrtf((pl.x * pl.x + pl.y * pl.y) + pl.z * pl.z) * 1.000001f, 1.0f);   // >= 1: it also scales the rows' own radii
+        }
 #pragma unroll
         for (uint32_t v = 0; v < (uint32_t)kMaxViews; ++v) {
             if (v < cvw.n_views) {
@@ -1209,7 +1245,8 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
                 if (R.rank != nullptr) rnk = R.rank[row];
             }
             // warp-level shortcut: views whose frustum the whole warp's rows are outside of (see warp_view_reject)
-            const uint32_t rejmask = warp_view_reject_lean(s.vplanes, cvw.n_views, base && do_test, base && !do_test, cx, cy, cz, radius);
+            const uint32_t rejmask = (probe & 8u) ? warp_view_reject_lean(s.vplanes, cvw.n_views, base && do_test, base && !do_test, cx, cy, cz, radius)
+                                                 : warp_view_reject_sphere(s.vplanes, s.vlen, cvw.n_views, base && do_test, base && !do_test, cx, cy, cz, radius);
             uint32_t todo = v_on & ~(rejmask & ~v_nofr);     // a NoCpuCulling camera lists without frustum tests: never rejected
             bool any = false;
             uint32_t my_ballot = 0;

@@ -1,6 +1,6 @@
 """Host-side planner of the default (CTA-per-tile) kernel, checked on CPU.
 
-k_propagate_cull_tma hands a tile's levels over through hardware NAMED BARRIERS: barrier l is joined by exactly the warps
+The tile kernels (k_propagate_cull_lean, k_propagate_cull_tma) hand a tile's levels over through hardware NAMED BARRIERS: barrier l is joined by exactly the warps
 that hold a row of level l-1 (producers: bar.arrive, or bar.sync when they also consume) or of level l (consumers:
 bar.sync), with the participant count the planner wrote into Tile::lvl_warps.  A count that disagrees with what the warps
 derive from their own rows' topo words is a hang on the device, so the protocol is replayed here: every warp runs the
