@@ -16,8 +16,11 @@ NO_PARENT, DETACHED = 0xFFFFFFFF, 0xFFFFFFFE
 T_DETACHED = 1 << 31
 
 
-def replay_tile(base, nr, n_levels, wsm, lvl_warps, topo):
-    """Warps as coroutines over the kernel's level loop; returns the order in which rows were computed."""
+def replay_tile(base, nr, n_levels, wsm, lvl_warps, topo, top_k=0):
+    """Warps as coroutines over the kernel's level loop; returns the order in which rows were computed.
+    top_k >= 2 (kernel 1L): the rows of in-tile depth < top_k are walked in registers by warp 0 before the loop -- a child takes
+    its parent's matrix with a warp shuffle from lane `parent`, so all of them must sit among the tile's first 32 rows -- and
+    levels 1 .. top_k - 1 drop out of every warp's schedule."""
     n_warps = 8
     local = topo[base:base + nr]
     depth = ((local >> 9) & 0x1FF).astype(np.int64)
@@ -28,10 +31,20 @@ def replay_tile(base, nr, n_levels, wsm, lvl_warps, topo):
         lmask[i >> 5] |= 1 << int(level_of[i])
     done = np.zeros(nr, bool)
     done[level_of == 0] = True       # level 0 is computed before the loop
+    if top_k >= 2:
+        for d in range(1, top_k):    # the shuffle walk: level by level inside warp 0
+            for i in np.nonzero(level_of == d)[0]:
+                p = int(local[i] & 0x1FF)
+                assert i < 32 and p < 32, f"row {base + i} of top level {d} (parent {base + p}) is outside the first warp"
+                if not (int(local[i]) & T_DETACHED):
+                    assert done[p] and level_of[p] == d - 1
+                done[i] = True
     # per warp: the list of (level, role) steps the kernel's while loop takes
     steps = []
     for w in range(n_warps):
         need = (lmask[w] | (lmask[w] << 1)) & ((1 << n_levels) - 2)
+        if top_k >= 2:
+            need &= ~((1 << top_k) - 2)
         st = []
         for lvl in range(1, n_levels):
             if not (need >> lvl) & 1:
@@ -90,7 +103,7 @@ def check(parent, tile_rows=0):
     parent = np.asarray(parent, np.uint32)
     desc, topo = abi.host_tile_plan(parent, tile_rows)
     named = 0
-    for base, nr, n_levels, wsm, _top, lo, hi, _pass in desc.tolist():
+    for base, nr, n_levels, wsm, top, lo, hi, _pass in desc.tolist():
         lvl_warps = lo | (hi << 32)
         if not (2 <= n_levels <= 8):
             assert lvl_warps == 0
@@ -106,6 +119,8 @@ def check(parent, tile_rows=0):
             assert (lvl_warps >> (4 * l)) & 15 == len(warps), f"tile at {base}: level {l}"
         assert lvl_warps >> (4 * n_levels) == 0 and lvl_warps & 15 == 0
         replay_tile(base, nr, n_levels, wsm, lvl_warps, topo)
+        if top >= 2:                 # the default kernel's schedule: top levels in registers, the rest through the barriers
+            replay_tile(base, nr, n_levels, wsm, lvl_warps, topo, top_k=top)
     return desc, named
 
 
@@ -118,6 +133,7 @@ def test_bench_forest_levels_meet_at_named_barriers():
     # level 6 = warps 1..3; level 7 = warps 3..7
     lw = int(trees[0, 5]) | (int(trees[0, 6]) << 32)
     assert [(lw >> (4 * l)) & 15 for l in range(1, 8)] == [1, 1, 1, 1, 2, 4, 7]
+    assert (trees[:, 4] == 5).all()           # top_levels: rows 0..30 = levels 0..4 are walked in registers by warp 0
 
 
 def test_flat_deep_and_wide_shapes():
