@@ -774,9 +774,10 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 1L (B200VIS_TILE_KERNEL=lean): kernel 1b on an instruction and exposed-latency diet.  ncu's source view of 1b
-// (profiles/r02b_*) shows a kernel that is bound by issue-slot latency (1.2 eligible warps per scheduler), with ~820 warp
-// instructions per 32 rows of which half are bookkeeping, and four places where a long latency is exposed on every tile:
+// Kernel 1L (the DEFAULT tile kernel; B200VIS_TILE_KERNEL=tma selects 1b): kernel 1b on an instruction and exposed-latency diet.
+// ncu's source view of 1b (profiles/r02b_tma_basic_blocks.txt) shows ~820 warp instructions per 32 rows of which half are
+// bookkeeping, an SM that issues ~2 warp instructions per cycle whatever the occupancy, and four places where
+// a long latency is exposed on every tile:
 //   * the tile descriptor (LDG of tiles[t]) at the top of a tile                  -> descriptors travel through shared memory:
 //     the bookkeeping thread fetches the descriptor of the CTA's tile i+2 with cp.async while tile i is culled;
 //   * the TMA prefetch of tile i+1 is issued after the walk of tile i by thread 0 (the warp every level of the walk waits
@@ -788,6 +789,8 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
 //   * the per-view loop was unrolled 8x with the plane operands in the constant bank (48 KB of code, a test + branch per
 //     view even when the warp rejected it)                                         -> one rolled loop over the set bits of
 //     (active views & ~rejected), planes from shared memory: a warp that rejects every view skips the loop in 3 instructions.
+// On top of that: the tile's top levels are walked in registers with warp shuffles, and the warp-level view rejection bounds the
+// warp's rows with a sphere (3 shuffles + 1 reduction) instead of a box (7 reductions).
 // Same results bit for bit (tests/test_gpu_bench_scale.py runs the bench workload through it).
 // ------------------------------------------------------------------------------------------
 // MINB = 4: the whole tile (Transform, GlobalTransform, topo, flags, state: 94 B/row) is staged in both stages, as in kernel 1b.
@@ -2094,7 +2097,7 @@ k_propagate_cull_scout(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles,
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 1w (default): the fused propagate -> cull pass with one WARP per tile and no CTA barrier at all.
+// Kernel 1w (B200VIS_TILE_KERNEL=warp): the fused propagate -> cull pass with one WARP per tile and no CTA barrier at all.
 //
 // Why: the CTA-per-tile kernels above spend their time waiting -- the hierarchy walk of a 255-node tree is a chain of
 // 8 levels with one warp on the critical path and seven parked at a barrier (ncu round 1: barrier 28 % of stalls, issue
@@ -3804,7 +3807,7 @@ static bool first_call_on_device(unsigned long long &seen) {
     seen |= bit;
     return true;
 }
-static int g_tile_kernel = -1;   // 5 lean (TMA-staged, bookkeeping thread, rolled view loop), 0 classic (one tile per CTA, LDG), 1 persistent TMA-staged CTA per tile (default), 2 warp per tile, 3 TMA + scout warp, 4 TMA flow (no inter-tile barrier)
+static int g_tile_kernel = -1;   // 5 lean (default: TMA-staged, bookkeeping thread, top levels in registers, rolled view loop), 0 classic (one tile per CTA, LDG), 1 kernel 1b (persistent TMA-staged CTA per tile), 2 warp per tile, 3 TMA + scout warp, 4 TMA flow (no inter-tile barrier)
 static int tile_kernel_choice() {
     if (g_tile_kernel < 0) {
         const char *e = getenv("B200VIS_TILE_KERNEL");
