@@ -789,8 +789,8 @@ k_propagate_cull_tma(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, c
 //   * the per-view loop was unrolled 8x with the plane operands in the constant bank (48 KB of code, a test + branch per
 //     view even when the warp rejected it)                                         -> one rolled loop over the set bits of
 //     (active views & ~rejected), planes from shared memory: a warp that rejects every view skips the loop in 3 instructions.
-// On top of that: the tile's top levels are walked in registers with warp shuffles, and the warp-level view rejection bounds the
-// warp's rows with a sphere (3 shuffles + 1 reduction) instead of a box (7 reductions).
+// On top of that: the tile's top levels are walked in registers with warp shuffles; B200VIS_LEAN_PROBE=8 bounds the warp's rows
+// with a sphere (3 shuffles + 1 reduction) instead of a box (7 reductions) in the warp-level view rejection (measured: +1 %).
 // Same results bit for bit (tests/test_gpu_bench_scale.py runs the bench workload through it).
 // ------------------------------------------------------------------------------------------
 // MINB = 4: the whole tile (Transform, GlobalTransform, topo, flags, state: 94 B/row) is staged in both stages, as in kernel 1b.
@@ -946,7 +946,7 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
     // levels -- the serial chain every other warp waits for -- then sit in the CTA's LAST hardware warp, which the SM's issue
     // arbiter prefers (highest warp id first) when several warps are eligible
     const uint32_t lr = threadIdx.x ^ (warp_flip & 0xE0u);
-    const uint32_t probe = warp_flip >> 8;     // bits 0-1: timing probes (results are WRONG): 1 = no level hand-overs at all, 2 = none for levels 1..4; bit 2: top levels through the level loop, bit 3: box instead of sphere in the warp-level view rejection (A/B switches, correct results)
+    const uint32_t probe = warp_flip >> 8;     // bits 0-1: timing probes (results are WRONG): 1 = no level hand-overs at all, 2 = none for levels 1..4; bit 2: top levels through the level loop, bit 3: sphere instead of box in the warp-level view rejection (A/B switches, correct results)
     const bool keeper = lr == (uint32_t)kTileRows - 1u;      // the bookkeeping thread: tickets, descriptors, TMA loads and stores
     static_assert(!PIPE || (PROP && CULL && MINB == 4), "PIPE needs the fused pass with staged Transforms");
     if (keeper) {
@@ -1248,8 +1248,8 @@ k_propagate_cull_lean(Rows R, const Tile *__restrict__ tiles, uint32_t n_tiles, 
                 if (R.rank != nullptr) rnk = R.rank[row];
             }
             // warp-level shortcut: views whose frustum the whole warp's rows are outside of (see warp_view_reject)
-            const uint32_t rejmask = (probe & 8u) ? warp_view_reject_lean(s.vplanes, cvw.n_views, base && do_test, base && !do_test, cx, cy, cz, radius)
-                                                 : warp_view_reject_sphere(s.vplanes, s.vlen, cvw.n_views, base && do_test, base && !do_test, cx, cy, cz, radius);
+            const uint32_t rejmask = (probe & 8u) ? warp_view_reject_sphere(s.vplanes, s.vlen, cvw.n_views, base && do_test, base && !do_test, cx, cy, cz, radius)
+                                                 : warp_view_reject_lean(s.vplanes, cvw.n_views, base && do_test, base && !do_test, cx, cy, cz, radius);
             uint32_t todo = v_on & ~(rejmask & ~v_nofr);     // a NoCpuCulling camera lists without frustum tests: never rejected
             bool any = false;
             uint32_t my_ballot = 0;

@@ -18,6 +18,7 @@ VARIANTS = {
     "default": {},                                                                  # lean kernel 1L: TMA-staged tiles, 4 persistent CTAs per SM
     "default_serial": {"B200VIS_PIPELINE": "0"},
     "lean_top_through_loop": {"B200VIS_LEAN_PROBE": "4"},                           # A/B switch: top levels through the level loop instead of registers
+    "lean_sphere_reject": {"B200VIS_LEAN_PROBE": "8"},                              # A/B switch: sphere instead of box in the warp-level view rejection
     "lean_pipe": {"B200VIS_LEAN_PIPE": "1"},                                        # the CTA's warps drift up to a tile apart (no closing barrier)
     "lean_5ctas": {"B200VIS_LEAN_CTAS": "5"},                                       # Transform out of the staged window, 48 registers
     "lean_6ctas": {"B200VIS_LEAN_CTAS": "6"},
